@@ -1,0 +1,238 @@
+"""Golden-vector generator (run ONLY in the build container, where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+Imports the UNMODIFIED reference modules (src/models/*, src/utils/*) with three stub packages standing in
+for omegaconf / hydra / transforms3d (tests/golden/_stubs), loads the seeded weights of
+`params.init_params` into the reference `TrafficBots` (checking that the key set and shapes match the
+reference's own state_dict), runs the reference on the seeded synthetic inputs of `synth.make_scene_batch`
+and stores ONLY the reference's outputs (+ weight/input checksums) as small fixtures in tests/golden/*.pt.
+The PL module (pl_modules/waymo_motion.py) is not importable here (needs pytorch_lightning, tensorflow,
+waymo_open_dataset), so its loop body (:118-204, :206-311, :439-524) is restated around the real
+reference Dynamics / TeacherForcing / TrafficRuleChecker / TrafficBots objects.
+"""
+import hashlib
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "_stubs"))
+sys.path.insert(0, "/root/reference/src")
+
+import tbpkg  # noqa: E402,F401
+from trafficbotsv1_5_b200 import config, params, synth  # noqa: E402
+from omegaconf import DictConfig  # noqa: E402  (stub)
+
+from models.traffic_bots import TrafficBots  # noqa: E402  (reference)
+from models.modules.attention_rpe import AttentionRPE  # noqa: E402
+from models.modules.transformer_rpe import TransformerBlockRPE  # noqa: E402
+from utils.rpe import get_rel_pose, get_tgt_knn_idx  # noqa: E402
+from utils.pose_emb import PoseEmb  # noqa: E402
+from utils.dynamics import Dynamics  # noqa: E402
+from utils.teacher_forcing import TeacherForcing  # noqa: E402
+from utils.traffic_rule_checker import TrafficRuleChecker  # noqa: E402
+
+
+def checksum(t: torch.Tensor) -> str:
+    return hashlib.sha256(t.contiguous().cpu().numpy().tobytes()).hexdigest()[:16]
+
+
+def build_reference_model(cfg, P):
+    model = TrafficBots(**DictConfig(cfg))
+    sd = model.state_dict()
+    hot = {k: v for k, v in sd.items() if not k.startswith(("latent_encoder.", "navi_predictor."))}
+    bufs = {k for k in sd if k.endswith((".freqs", "pl_node_ohe", "hist_ohe"))}  # persistent buffers (App. B)
+    hot_params = {k: tuple(v.shape) for k, v in hot.items() if k not in bufs}
+    mine = {k: tuple(v) for k, v in params.param_shapes(cfg).items()}
+    assert hot_params == mine, (set(hot_params) ^ set(mine))
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected, unexpected
+    assert all(m.startswith(("latent_encoder.", "navi_predictor.")) or m in bufs for m in missing), missing
+    model.eval()
+    return model
+
+
+def tie_free_poses(g, B, N, lo, hi):
+    """positions on a jittered lattice; callers assert the K/K+1 distance gap."""
+    xy = torch.rand(B, N, 2, generator=g) * (hi - lo) + lo
+    yaw = (torch.rand(B, N, 1, generator=g) * 2 - 1) * 3.0
+    return torch.cat([xy, yaw], -1)
+
+
+@torch.no_grad()
+def golden_ops():
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    # ---- rel-pose + knn (utils/rpe.py)
+    for name, (B, S, T, K, lim) in dict(small=(2, 24, 50, 12, 60.0), self_=(2, 40, 40, 24, 250.0),
+                                        big=(1, 16, 1024, 64, 500.0)).items():
+        pose = tie_free_poses(g, B, S, -80, 80)
+        inv = torch.rand(B, S, generator=g) < 0.15
+        if name == "self_":
+            pose2, inv2 = None, None
+        else:
+            pose2 = tie_free_poses(g, B, T, -120, 120)
+            inv2 = torch.rand(B, T, generator=g) < 0.2
+        rel_pose, rel_dist = get_rel_pose(pose, inv, pose2, inv2)
+        idx, knn_inv, rpe = get_tgt_knn_idx(inv if inv2 is None else inv2, rel_pose, rel_dist, K, lim)
+        # tie-free check: gap between K-th and (K+1)-th finite distance must be comfortable
+        sd = torch.sort(rel_dist, -1)[0]
+        gap = (sd[..., K] - sd[..., K - 1])
+        fin = torch.isfinite(sd[..., K])
+        assert (gap[fin] > 1e-3).all(), gap[fin].min()
+        order = torch.argsort(torch.gather(rel_dist, 2, idx), dim=-1, stable=True)
+        srt = lambda t: torch.gather(t, 2, order if t.dim() == 3 else order[..., None].expand(-1, -1, -1, 3))  # noqa
+        out[f"knn_{name}"] = dict(pose=pose, inv=inv, pose2=pose2, inv2=inv2, K=K, lim=lim,
+                                  idx=srt(idx), knn_inv=srt(knn_inv), rpe=srt(rpe),
+                                  dist=srt(torch.gather(rel_dist, 2, idx)))
+    # ---- pose embedding (utils/pose_emb.py)
+    for pe in (64, 128, 256):
+        emb = PoseEmb("pe_xy_yaw", pe_dim=pe, theta_xy=1e3)
+        xy = (torch.rand(5, 7, 2, generator=g) * 2 - 1) * 300
+        yaw = (torch.rand(5, 7, 1, generator=g) * 2 - 1) * 9
+        out[f"pe_{pe}"] = dict(xy=xy, yaw=yaw, emb=emb(xy, yaw))
+    # ---- AttentionRPE / TransformerBlockRPE (modules/attention_rpe.py, transformer_rpe.py)
+    for name, (d, H, B, S, K) in dict(d128=(128, 4, 2, 16, 12), d256=(256, 4, 1, 8, 36)).items():
+        att = AttentionRPE(d, H, dropout_p=0.1, bias=True, d_rpe=d).eval()
+        att.load_state_dict(params.rand_like_state_dict(att.state_dict(), seed=11))
+        src = torch.randn(B, S, d, generator=g)
+        tgt = torch.randn(B, S, K, d, generator=g)
+        mask = torch.rand(B, S, K, generator=g) < 0.2
+        mask[0, 0] = True  # one all-masked row
+        rel = torch.cat([(torch.rand(B, S, K, 2, generator=g) * 2 - 1) * 100,
+                         (torch.rand(B, S, K, 1, generator=g) * 2 - 1) * 4], -1)
+        rpe = PoseEmb("pe_xy_yaw", pe_dim=d, theta_xy=1e3)(rel[..., :2], rel[..., 2:3])
+        o, _ = att(src, tgt, tgt_padding_mask=mask, rpe=rpe)
+        out[f"attn_{name}"] = dict(sd_shapes={k: tuple(v.shape) for k, v in att.state_dict().items()}, sd_seed=11,
+                                   src=src, tgt=tgt, mask=mask, rel=rel, out=o, n_head=H)
+    for mode in ("enc_self_attn", "dec_cross_attn"):
+        d, H, B, S, K, T2, K2 = 128, 4, 2, 20, 8, 30, 10
+        blk = TransformerBlockRPE(d_model=d, n_head=H, k_feedforward=4, dropout_p=0.1, bias=True, activation="relu",
+                                  out_layernorm=False, apply_q_rpe=False, n_layer=2, mode=mode, d_rpe=d).eval()
+        blk.load_state_dict(params.rand_like_state_dict(blk.state_dict(), seed=13))
+        pe = PoseEmb("pe_xy_yaw", pe_dim=d, theta_xy=1e3)
+        src = torch.randn(B, S, d, generator=g)
+        src_inv = torch.rand(B, S, generator=g) < 0.15
+        idx = torch.stack([torch.stack([torch.randperm(S, generator=g)[:K] for _ in range(S)]) for _ in range(B)])
+        m1 = torch.rand(B, S, K, generator=g) < 0.2
+        rel1 = torch.cat([(torch.rand(B, S, K, 2, generator=g) * 2 - 1) * 100,
+                          (torch.rand(B, S, K, 1, generator=g) * 2 - 1) * 4], -1)
+        rec = dict(sd_shapes={k: tuple(v.shape) for k, v in blk.state_dict().items()}, sd_seed=13, src=src, src_inv=src_inv, idx=idx, m1=m1,
+                   rel1=rel1, n_head=H, n_layer=2)
+        if mode == "enc_self_attn":
+            o, _ = blk(src=src, src_padding_mask=src_inv, tgt=idx, tgt_padding_mask=m1,
+                       rpe=pe(rel1[..., :2], rel1[..., 2:3]))
+        else:
+            tgt_tab = torch.randn(B, T2, d, generator=g)
+            idx2 = torch.stack([torch.stack([torch.randperm(T2, generator=g)[:K2] for _ in range(S)]) for _ in range(B)])
+            m2 = torch.rand(B, S, K2, generator=g) < 0.2
+            rel2 = torch.cat([(torch.rand(B, S, K2, 2, generator=g) * 2 - 1) * 100,
+                              (torch.rand(B, S, K2, 1, generator=g) * 2 - 1) * 4], -1)
+            tgt = tgt_tab[torch.arange(B)[:, None, None], idx2]
+            o, _ = blk(src=src, src_padding_mask=src_inv, tgt=tgt, tgt_padding_mask=m2,
+                       rpe=pe(rel2[..., :2], rel2[..., 2:3]), decoder_tgt=idx, decoder_tgt_padding_mask=m1,
+                       decoder_rpe=pe(rel1[..., :2], rel1[..., 2:3]))
+            rec.update(tgt_tab=tgt_tab, idx2=idx2, m2=m2, rel2=rel2)
+        rec["out"] = o
+        out[f"block_{mode}"] = rec
+    return out
+
+
+def make_dynamics():
+    dc = config.DYNAMICS_CFG
+    mk = lambda k: DictConfig(dict(_target_="utils.dynamics.MultiPathPP", **dc[k]))  # noqa: E731
+    return Dynamics(veh=mk("veh"), ped=mk("ped"), cyc=mk("cyc"), navi_mode="dest")
+
+
+@torch.no_grad()
+def reference_rollout(model, batch, R, step_end, record_steps=()):
+    """waymo_motion.py:439-524 (joint_future_pred) + :206-311 (rollout) + :118-204 (forward), restated."""
+    rc = config.ROLLOUT_CFG
+    mp_tokens = model.mp_encoder(batch["sc/mp_valid"], batch["sc/mp_attr"], batch["sc/mp_pose"], batch["ref/mp_type"])
+    tl_tokens = model.tl_encoder.pre_compute(tl_valid=batch["sc/tl_valid"], tl_attr=batch["sc/tl_attr"],
+                                             tl_pose=batch["sc/tl_pose"], **mp_tokens)
+    static = dict(mp={k: v.clone() for k, v in mp_tokens.items()},
+                  tl={k: v.clone() for k, v in tl_tokens.items() if v is not None})
+    rep = lambda t: t.repeat_interleave(R, 0)  # noqa: E731
+    n_sc = batch["sc/ag_valid"].shape[0]
+    ag_tokens = dict(ag_type=rep(batch["ref/ag_type"]), ag_size=rep(batch["ref/ag_size"]), ag_attr=rep(batch["sc/ag_attr"]),
+                     gt_valid=rep(batch["sc/ag_valid"]), gt_pose=rep(batch["sc/ag_pose"]), gt_motion=rep(batch["sc/ag_motion"]))
+    mp_tokens = {k: rep(v) for k, v in mp_tokens.items()}
+    tl_tokens = {k: (rep(v) if v is not None else None) for k, v in tl_tokens.items()}
+    ag_tokens["ag_latent"] = batch["ag_latent"][:, :R].reshape(n_sc * R, *batch["ag_latent"].shape[2:])
+    ag_tokens["ag_latent_valid"] = rep(batch["ag_latent_valid"])
+    ag_tokens["ag_navi"] = rep(batch["agent/dest"])
+    ag_tokens["ag_navi_valid"] = rep(batch["ag_navi_valid"])
+    rule_checker = TrafficRuleChecker(
+        mp_boundary=rep(batch["map/boundary"]), mp_valid=rep(batch["map/valid"]), mp_type=rep(batch["map/type"]),
+        mp_pos=rep(batch["map/pos"]), mp_dir=rep(batch["map/dir"]), ag_type=ag_tokens["ag_type"],
+        ag_size=ag_tokens["ag_size"], ag_goal=None, ag_dest=ag_tokens["ag_navi"], tl_valid=tl_tokens["tl_token_valid"],
+        tl_pose=tl_tokens["tl_token_pose"], disable_check=True)  # heavy logging-only checks off; feedback checks run
+    tl_state_gt = rep(batch["sc/tl_state"])
+    tf = TeacherForcing(step_spawn_agent=rc["step_spawn_agent"], step_warm_start=rc["step_warm_start"])
+    tf.init(ag_valid=ag_tokens["gt_valid"], ag_pose=ag_tokens["gt_pose"], ag_motion=ag_tokens["gt_motion"],
+            tl_state=tl_state_gt, current_epoch=0)
+    dyn = make_dynamics()
+    dyn.init(tl_state=tl_state_gt, **ag_tokens)
+    model.init()
+    out = dict(pred_valid=[], pred_pose=[], pred_motion=[], tl_state=[], action_mean=[])
+    rec = {}
+    for step in range(1, step_end + 1):
+        ag_override, tl_override = tf.get(step, dyn.ag_valid, dyn.ag_pose, dyn.ag_motion)
+        ag_valid = dyn.ag_valid
+        action_dist, tl_dist = model(
+            ag_valid=ag_valid, ag_pose=dyn.ag_pose, ag_motion=dyn.ag_motion, ag_attr=dyn.ag_attr, ag_type=dyn.ag_type,
+            ag_latent=dyn.ag_latent, ag_latent_valid=dyn.ag_latent_valid, ag_navi=dyn.ag_navi,
+            ag_navi_valid=dyn.ag_navi_valid, ag_navi_updated=dyn.ag_navi_updated, tl_state=dyn.tl_state,
+            tl_tokens=tl_tokens, mp_tokens=mp_tokens)
+        if step in record_steps:
+            rec[step] = dict(mean=action_dist.mean.clone(), logits=tl_dist.logits.clone(),
+                             valid=ag_valid.clone(), pose=dyn.ag_pose.clone())
+        dyn.update_ag(action_dist, True, None)
+        pred_pose, pred_motion = dyn.ag_pose, dyn.ag_motion
+        dyn.override_ag(ag_override)
+        dyn.override_tl(tl_dist, tl_override)
+        violation = rule_checker.check(ag_valid, pred_pose, pred_motion, dyn.tl_state)
+        gt_valid = ag_tokens["gt_valid"][:, :, step] if step < ag_tokens["gt_valid"].shape[-1] else None
+        out["pred_valid"].append(ag_valid); out["pred_pose"].append(pred_pose); out["pred_motion"].append(pred_motion)
+        out["tl_state"].append(dyn.tl_state); out["action_mean"].append(action_dist.mean)
+        dyn.disable_ag(violation, gt_valid)
+        dyn.disable_navi(violation)
+    res = {k: torch.stack(v, 2) for k, v in out.items()}
+    res["final_valid"], res["final_navi_valid"] = dyn.ag_valid, dyn.ag_navi_valid
+    return res, static, rec
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    ops = golden_ops()
+    torch.save(ops, os.path.join(HERE, "ops.pt"))
+    print("ops.pt", os.path.getsize(os.path.join(HERE, "ops.pt")) // 1024, "KiB")
+
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, seed=0)
+    model = build_reference_model(cfg, P)
+    shape = dict(n_sc=2, n_ag=32, n_mp=96, n_tl=30, seed=1000, boundary=105.0)
+    batch = synth.make_scene_batch(**shape)
+    R, T = 2, 24
+    res, static, rec = reference_rollout(model, batch, R, T, record_steps=(1, 5, 12, 20))
+    fix = dict(shape=shape, R=R, T=T, param_seed=0,
+               param_checksum=checksum(torch.cat([P[k].flatten() for k in sorted(P)])),
+               input_checksum=checksum(torch.cat([batch[k].float().flatten() for k in sorted(batch)])),
+               mp_token_feature=static["mp"]["mp_token_feature"], mp_token_invalid=static["mp"]["mp_token_invalid"],
+               tl_token_attr=static["tl"]["tl_token_attr"],
+               knn_idx_tl2tl=static["tl"]["knn_idx_tl2tl"].masked_fill(static["tl"]["knn_invalid_tl2tl"], -1).sort(-1)[0],
+               rec=rec, **res)
+    torch.save(fix, os.path.join(HERE, "rollout_small.pt"))
+    print("rollout_small.pt", os.path.getsize(os.path.join(HERE, "rollout_small.pt")) // 1024, "KiB")
+    print("outside/disabled agents:", int((~res["final_valid"]).sum()), "navi reached:", int((~res["final_navi_valid"]).sum()))
+    print("max |action mean|", float(res["action_mean"].abs().max()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""CPU: pin the oracle (oracle/tb_oracle.py) against golden vectors produced by the real reference
+(tests/golden/make_golden.py). fp32 tolerances are stated per check."""
+import hashlib
+
+import pytest
+import torch
+
+from oracle import tb_oracle as O
+from trafficbotsv1_5_b200 import config, params, synth
+
+
+def _close(a, b, rtol, atol, what):
+    err = (a - b).abs()
+    lim = atol + rtol * b.abs()
+    assert bool((err <= lim).all()), f"{what}: max abs err {float(err.max()):.3e}, max |ref| {float(b.abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("name", ["knn_small", "knn_self_", "knn_big"])
+def test_rel_pose_knn(golden_ops, name):
+    g = golden_ops[name]
+    rel_pose, rel_dist = O.get_rel_pose(g["pose"], g["inv"], g["pose2"], g["inv2"])
+    tgt_inv = g["inv"] if g["inv2"] is None else g["inv2"]
+    idx, inv, rpe = O.knn_select(tgt_inv, rel_pose, rel_dist, g["K"], g["lim"])
+    fin = torch.isfinite(g["dist"])
+    # KNN indices: bit-exact where the distance is finite (inf fillers are free, always masked)
+    assert torch.equal(idx[fin], g["idx"][fin])
+    assert torch.equal(inv[fin], g["knn_inv"][fin])
+    assert bool(inv[~fin].all()) and bool(g["knn_inv"][~fin].all())
+    _close(rpe[fin], g["rpe"][fin], 0, 1e-6, "rpe")
+
+
+@pytest.mark.parametrize("pe", [64, 128, 256])
+def test_pose_emb(golden_ops, pe):
+    g = golden_ops[f"pe_{pe}"]
+    _close(O.pose_emb_xy_yaw(g["xy"], g["yaw"][..., 0], pe), g["emb"], 0, 1e-6, "pose_emb")
+
+
+@pytest.mark.parametrize("name", ["attn_d128", "attn_d256"])
+def test_attention_rpe(golden_ops, name):
+    g = golden_ops[name]
+    P = {f"a.{k}": v for k, v in params.rand_like_state_dict(g["sd_shapes"], g["sd_seed"]).items()}
+    d = g["src"].shape[-1]
+    rpe = O.pose_emb_xy_yaw(g["rel"][..., :2], g["rel"][..., 2], d)
+    out = O.attention_rpe(P, "a", g["src"], g["tgt"], g["mask"], rpe, g["n_head"])
+    _close(out, g["out"], 1e-5, 1e-6, name)
+    assert float(out[0, 0].abs().max()) == 0.0  # all-masked row -> exact zero
+
+
+@pytest.mark.parametrize("mode", ["enc_self_attn", "dec_cross_attn"])
+def test_transformer_block(golden_ops, mode):
+    g = golden_ops[f"block_{mode}"]
+    P = {f"b.{k}": v for k, v in params.rand_like_state_dict(g["sd_shapes"], g["sd_seed"]).items()}
+    e = lambda r: O.pose_emb_xy_yaw(r[..., :2], r[..., 2], 128)  # noqa: E731
+    if mode == "enc_self_attn":
+        out = O.transformer_block(P, "b", mode, g["n_layer"], g["n_head"], g["src"], g["src_inv"], g["idx"], g["m1"],
+                                  e(g["rel1"]))
+    else:
+        tgt = O._gather_rows(g["tgt_tab"], g["idx2"])
+        out = O.transformer_block(P, "b", mode, g["n_layer"], g["n_head"], g["src"], g["src_inv"], tgt, g["m2"],
+                                  e(g["rel2"]), g["idx"], g["m1"], e(g["rel1"]))
+    _close(out, g["out"], 1e-5, 2e-6, mode)
+
+
+def _checksum(t):
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()[:16]
+
+
+def test_rollout_small(golden_rollout):
+    g = golden_rollout
+    cfg = config.default_model_cfg()
+    sz = config.derived_sizes(cfg)
+    P = params.init_params(cfg, seed=g["param_seed"])
+    batch = synth.make_scene_batch(**g["shape"])
+    # the seeded weights / inputs must be the ones the reference saw
+    assert _checksum(torch.cat([P[k].flatten() for k in sorted(P)])) == g["param_checksum"]
+    assert _checksum(torch.cat([batch[k].float().flatten() for k in sorted(batch)])) == g["input_checksum"]
+    mp = O.map_encoder(P, cfg, sz, batch["sc/mp_valid"], batch["sc/mp_attr"], batch["sc/mp_pose"])
+    assert torch.equal(mp["mp_token_invalid"], g["mp_token_invalid"])
+    _close(mp["mp_token_feature"], g["mp_token_feature"], 1e-4, 1e-5, "mp_token_feature")
+    tl = O.tl_pre_compute(P, cfg, sz, batch["sc/tl_valid"], batch["sc/tl_attr"], batch["sc/tl_pose"], mp)
+    assert torch.equal(tl["knn_idx_tl2tl"].masked_fill(tl["knn_invalid_tl2tl"], -1).sort(-1)[0], g["knn_idx_tl2tl"])
+    rec = {}
+    res = O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, g["R"], g["T"], mp=mp, tl=tl,
+                    record=lambda s, d: rec.__setitem__(s, d))
+    for s, r in g["rec"].items():
+        _close(rec[s]["mean"], r["mean"], 1e-4, 1e-5, f"action mean @ step {s}")
+        # Categorical(logits=...) stores normalised logits (traffic_bots.py:221)
+        _close(torch.log_softmax(rec[s]["logits"], -1), r["logits"], 1e-4, 1e-5, f"tl logits @ step {s}")
+    assert torch.equal(res["pred_valid"], g["pred_valid"])
+    assert torch.equal(res["tl_state"], g["tl_state"])
+    assert torch.equal(res["final_valid"], g["final_valid"])
+    assert torch.equal(res["final_navi_valid"], g["final_navi_valid"])
+    # per-step position tolerance over the rollout: 1e-3 m, 1e-4 rad
+    _close(res["pred_pose"][..., :2], g["pred_pose"][..., :2], 0, 1e-3, "pred xy")
+    _close(res["pred_pose"][..., 2], g["pred_pose"][..., 2], 0, 1e-4, "pred yaw")
+    _close(res["pred_motion"], g["pred_motion"], 0, 1e-3, "pred motion")

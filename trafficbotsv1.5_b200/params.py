@@ -1,0 +1,117 @@
+"""Parameter inventory of the hot-path modules, keyed by the reference's `state_dict` names
+(dumped from `models.traffic_bots.TrafficBots`, src/models/traffic_bots.py:17-121).
+
+`param_shapes` is the boundary contract (a reference checkpoint's tensors of these names load
+unchanged); `init_params` draws a seeded random-init set for benchmarks and parity tests — there is no
+network for checkpoints. `latent_encoder.*` / `navi_predictor.*` are off the rollout path and omitted.
+"""
+from collections import OrderedDict
+from typing import Dict, Tuple
+
+import torch
+
+
+def _tf_layer(shapes, p, d, d_rpe, dec):
+    def attn(q):
+        shapes[f"{q}.in_proj_weight"] = (3 * d, d)
+        shapes[f"{q}.out_proj_weight"] = (d, d)
+        shapes[f"{q}.in_proj_bias"] = (3 * d,)
+        shapes[f"{q}.out_proj_bias"] = (d,)
+        shapes[f"{q}.linear_rpe.weight"] = (2 * d, d_rpe)
+        shapes[f"{q}.linear_rpe.bias"] = (2 * d,)
+
+    def ln(q):
+        shapes[f"{q}.weight"] = (d,)
+        shapes[f"{q}.bias"] = (d,)
+
+    ln(f"{p}.norm1"); ln(f"{p}.norm_tgt")
+    if dec:
+        attn(f"{p}.attn_src"); ln(f"{p}.norm_src")
+    attn(f"{p}.attn")
+    shapes[f"{p}.linear1.weight"] = (4 * d, d); shapes[f"{p}.linear1.bias"] = (4 * d,)
+    shapes[f"{p}.linear2.weight"] = (d, 4 * d); shapes[f"{p}.linear2.bias"] = (d,)
+    ln(f"{p}.norm2")
+
+
+def _mlp(shapes, p, dims, idxs):
+    for i, (a, b) in zip(idxs, zip(dims[:-1], dims[1:])):
+        shapes[f"{p}.fc_layers.{i}.weight"] = (b, a)
+        shapes[f"{p}.fc_layers.{i}.bias"] = (b,)
+
+
+def param_shapes(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
+    d = cfg["hidden_dim"]
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    L = cfg["n_mp_pl_node"]
+    W = cfg["temp_window_size"]
+    # map encoder (map_encoder.py:29-48): input MLP [attr+L -> d-7]*3 (cat 7 polyline feats), PointNet, 8 enc layers
+    _mlp(s, "mp_encoder.input_encoder.mlp", [cfg["mp_attr_dim"] + L] + [d - 7] * 3, (0, 2, 4))
+    for i in range(3):
+        _mlp(s, f"mp_encoder.pl_encoder.mlp_layers.{i}", [d, d // 2], (0,))
+    for i in range(cfg["mp_encoder"]["n_layer_tf"]):
+        _tf_layer(s, f"mp_encoder.tf_mp2mp.layers.{i}", d, d, False)
+    # traffic-light encoder (traffic_light.py:40-74): input MLP [5+W -> d]*3 (add lane feature)
+    _mlp(s, "tl_encoder.input_encoder.mlp", [cfg["tl_state_dim"] + W] + [d] * 3, (0, 2, 4))
+    for i in range(3):
+        _mlp(s, f"tl_encoder.temp_encoder.mlp_layers.{i}", [d, d // 2], (0,))
+    for i in range(cfg["tl_encoder"]["n_layer_tf"]):
+        _tf_layer(s, f"tl_encoder.tf_tl2tlmp.layers.{i}", d, d, True)
+    _mlp(s, "tl_state_predictor.mlp", [d, d, d, cfg["tl_state_dim"]], (0, 2, 4))
+    # agent encoder (agent_encoder.py:39-70): input MLP [6+3+W -> d/2]*3 (cat d/2 pose emb)
+    _mlp(s, "ag_encoder.input_encoder.mlp", [cfg["ag_attr_dim"] + cfg["ag_motion_dim"] + W] + [d // 2] * 3, (0, 2, 4))
+    for i in range(3):
+        _mlp(s, f"ag_encoder.temp_encoder.mlp_layers.{i}", [d, d // 2], (0,))
+    for i in range(cfg["ag_encoder"]["n_layer_tf"]):
+        _tf_layer(s, f"ag_encoder.tf_ag2agmptl.layers.{i}", d, d, True)
+    # heads (navigation.py:37-40, add_navi_latent.py:27-31, action_head.py:25-50)
+    _mlp(s, "navi_encoder.mlp_mp", [d, d], (0,))
+    _mlp(s, "navi_encoder.mlp_pe", [d, d], (0,))
+    _mlp(s, "add_navi.mlp_in", [d, d, d, d], (0, 3, 6))
+    _mlp(s, "add_navi.mlp", [2 * d, d, d, d], (0, 3, 6))
+    _mlp(s, "add_latent.mlp_in", [cfg["latent_encoder"]["latent_dim"], d, d, d], (0, 3, 6))
+    _mlp(s, "add_latent.mlp", [2 * d, d, d, d], (0, 3, 6))
+    for t in range(3):
+        _mlp(s, f"action_head.mlp_mean.{t}", [d, d, d, cfg["action_dim"]], (0, 2, 4))
+        s[f"action_head.log_std.{t}"] = (cfg["action_dim"],)
+    return s
+
+
+def init_params(cfg: dict, seed: int = 0, bias_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """Seeded random init (CPU generator, fp32): Linear-style U(+-1/sqrt(fan_in)) for matrices and
+    biases (so attention biases are exercised, unlike the reference's zero init, attention_rpe.py:50-56),
+    LayerNorm gamma 1+0.1N / beta 0.1N, log_std -2 (action_head.py:48-50)."""
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    shapes = param_shapes(cfg)
+    for k, shp in shapes.items():
+        if "log_std" in k:
+            P[k] = torch.full(shp, -2.0)
+        elif ".norm" in k:
+            n = torch.randn(shp, generator=g) * 0.1
+            P[k] = (1.0 + n) if k.endswith("weight") else n
+        elif len(shp) == 2:
+            b = 1.0 / shp[1] ** 0.5
+            P[k] = (torch.rand(shp, generator=g) * 2 - 1) * b
+        else:
+            wk = k.replace("in_proj_bias", "in_proj_weight").replace("out_proj_bias", "out_proj_weight")
+            wk = wk[:-4] + "weight" if wk.endswith("bias") else wk
+            b = bias_scale / shapes[wk][1] ** 0.5
+            P[k] = (torch.rand(shp, generator=g) * 2 - 1) * b
+    return P
+
+
+def rand_like_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int) -> Dict[str, torch.Tensor]:
+    """Seeded tensors for an arbitrary {name: shape or tensor} dict (sorted-name order): matrices
+    U(+-1/sqrt(fan_in)), LayerNorm-like vectors 1+0.1N (weight) / 0.1N (other vectors). Used so golden
+    fixtures can store a seed instead of weights."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(shapes):
+        shp = tuple(shapes[k].shape) if hasattr(shapes[k], "shape") else tuple(shapes[k])
+        if len(shp) >= 2:
+            out[k] = (torch.rand(shp, generator=g) * 2 - 1) / shp[-1] ** 0.5
+        elif ".norm" in k and k.endswith("weight"):
+            out[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            out[k] = 0.1 * torch.randn(shp, generator=g)
+    return out

@@ -1,0 +1,89 @@
+"""Seeded synthetic WOMD-shaped scenes (there is no dataset in the build/GPU containers).
+
+The dict layout is what the reference's `SceneCentricPreProcessing.forward` hands to the model at
+test time (`src/data_modules/scene_centric.py:39-147`; tensor sizes `data_h5_womd.py:95-140`), i.e.
+the "sc/*", "ref/*" and "map/*" keys consumed by `WaymoMotion.test_step` / `joint_future_pred`
+(`src/pl_modules/waymo_motion.py:843-876, 439-524`). Recipe: SURVEY.md §8(d).
+"""
+import math
+from typing import Dict
+
+import torch
+
+
+def make_scene_batch(n_sc: int, n_ag: int = 128, n_mp: int = 1024, n_tl: int = 40, n_node: int = 20,
+                     n_hist: int = 11, seed: int = 1000, boundary: float = 400.0,
+                     n_rollout: int = 32, latent_dim: int = 16) -> Dict[str, torch.Tensor]:
+    """All tensors fp32/bool/int64 on CPU. Scene s is drawn from seed `seed + s`."""
+    out = {}
+    scenes = [_one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed + s, boundary, n_rollout, latent_dim)
+              for s in range(n_sc)]
+    for k in scenes[0]:
+        out[k] = torch.stack([sc[k] for sc in scenes], 0)
+    return out
+
+
+def _one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed, boundary, n_rollout, latent_dim):
+    g = torch.Generator().manual_seed(seed)
+    U = lambda *s, lo=0.0, hi=1.0: torch.rand(*s, generator=g) * (hi - lo) + lo  # noqa: E731
+    d = {}
+    # ---- map polylines: straight, 1 m node spacing, node 0 is the token pose (map_encoder.py:65)
+    p0 = U(n_mp, 2, lo=-150.0, hi=150.0)
+    hd = U(n_mp, lo=-math.pi, hi=math.pi)
+    dirv = torch.stack([hd.cos(), hd.sin()], -1)  # [n_mp, 2]
+    t = torch.arange(n_node, dtype=torch.float32)
+    pos = p0[:, None, :] + t[None, :, None] * dirv[:, None, :]  # [n_mp, n_node, 2]
+    mp_valid = torch.ones(n_mp, n_node, dtype=torch.bool)
+    tail = (U(n_mp) < 0.2)
+    n_keep = torch.randint(1, n_node, (n_mp,), generator=g)
+    mp_valid &= ~(tail[:, None] & (t[None, :] >= n_keep[:, None]))
+    mp_valid &= ~(U(n_mp) < 0.05)[:, None]
+    mp_type = torch.nn.functional.one_hot(torch.randint(0, 11, (n_mp,), generator=g), 11).bool()
+    d["map/valid"] = mp_valid
+    d["map/type"] = mp_type
+    d["map/pos"] = torch.cat([pos, torch.zeros(n_mp, n_node, 1)], -1)
+    d["map/dir"] = torch.cat([dirv[:, None, :].expand(-1, n_node, -1), torch.zeros(n_mp, n_node, 1)], -1).contiguous()
+    d["map/boundary"] = torch.tensor([-boundary, boundary, -boundary, boundary])
+    d["sc/mp_valid"] = mp_valid.clone()
+    d["sc/mp_attr"] = mp_type.float()
+    d["sc/mp_pose"] = torch.cat([pos, hd[:, None, None].expand(-1, n_node, 1)], -1).contiguous()
+    d["ref/mp_type"] = mp_type
+    # ---- traffic lights on lanes (tl_mode == "lane"; scene_centric.py:97-100)
+    tl_idx = torch.randperm(n_mp, generator=g)[:n_tl]
+    d["sc/tl_attr"] = tl_idx
+    d["sc/tl_pose"] = d["sc/mp_pose"][tl_idx, 0].clone()
+    d["sc/tl_valid"] = U(n_tl) < 0.9
+    st0 = torch.randint(0, 5, (n_tl,), generator=g)
+    st1 = torch.randint(0, 5, (n_tl,), generator=g)
+    t_sw = torch.randint(0, n_hist + 1, (n_tl,), generator=g)
+    st = torch.where(torch.arange(n_hist)[None, :] < t_sw[:, None], st0[:, None], st1[:, None])
+    d["sc/tl_state"] = torch.nn.functional.one_hot(st, 5).bool()  # [n_tl, n_hist, 5]
+    # ---- agents: constant-velocity history, dt = 0.1 s
+    a0 = U(n_ag, 2, lo=-100.0, hi=100.0)
+    yaw = U(n_ag, lo=-math.pi, hi=math.pi)
+    spd = U(n_ag, lo=0.0, hi=10.0)
+    th = torch.arange(n_hist, dtype=torch.float32) * 0.1
+    vel = torch.stack([yaw.cos(), yaw.sin()], -1) * spd[:, None]
+    apos = a0[:, None, :] + th[None, :, None] * vel[:, None, :]
+    d["sc/ag_pose"] = torch.cat([apos, yaw[:, None, None].expand(-1, n_hist, 1)], -1).contiguous()
+    d["sc/ag_motion"] = torch.stack([spd[:, None].expand(-1, n_hist), torch.zeros(n_ag, n_hist),
+                                     torch.zeros(n_ag, n_hist)], -1).contiguous()
+    ag_valid = torch.ones(n_ag, n_hist, dtype=torch.bool)
+    ag_valid &= ~(U(n_ag) < 0.1)[:, None]
+    late = U(n_ag) < 0.1
+    t_in = torch.randint(1, n_hist, (n_ag,), generator=g)
+    ag_valid &= ~(late[:, None] & (torch.arange(n_hist)[None, :] < t_in[:, None]))
+    d["sc/ag_valid"] = ag_valid
+    ag_type = torch.nn.functional.one_hot(torch.multinomial(torch.tensor([0.7, 0.2, 0.1]), n_ag, True, generator=g),
+                                          3).bool()
+    size = U(n_ag, 3, lo=1.0, hi=5.0)
+    d["ref/ag_type"] = ag_type
+    d["ref/ag_size"] = size
+    d["sc/ag_attr"] = torch.cat([size, ag_type.float()], -1)
+    # ---- fixed navigation + latent samples (north star: "fixed latent samples")
+    d["agent/dest"] = torch.randint(0, n_mp, (n_ag,), generator=g)
+    d["ag_navi_valid"] = ag_valid.any(-1)
+    gl = torch.Generator().manual_seed(seed + 1000)
+    d["ag_latent"] = torch.randn(n_rollout, n_ag, latent_dim, generator=gl)
+    d["ag_latent_valid"] = ag_valid.any(-1)
+    return d
