@@ -1,0 +1,180 @@
+/*
+ * tb_knarpe.h — C ABI of libtbknarpe.so: hand-written sm_100a kernels for the TrafficBots-V1.5 hot path
+ * (HPTR KNARPE attention + per-step closed-loop rollout).
+ *
+ * The reference (zhejz/TrafficBotsV1.5) is pure PyTorch and has no FFI; each entry point below replaces the
+ * chain of eager ATen ops behind the cited reference function (paths relative to the reference's src/).
+ *
+ * Conventions (all entry points):
+ *   - plain device pointers + sizes, no torch types; all buffers are caller-owned, on the current device;
+ *   - float = fp32 row-major; masks are uint8 (torch.bool storage), nonzero = INVALID unless stated;
+ *     indices are int32;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing allocates, nothing
+ *     synchronises, no global mutable state => CUDA-graph capturable and thread-safe per stream;
+ *   - return value: 0 (TB_OK) or a negative TB_ERR_* code; never throws.
+ */
+#ifndef TB_KNARPE_H_
+#define TB_KNARPE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_OK 0
+#define TB_ERR_BAD_SHAPE (-1)    /* non-positive / inconsistent dims                                  */
+#define TB_ERR_KNN_RANGE (-2)    /* needs 0 < K < T            (reference assert: utils/rpe.py:79)     */
+#define TB_ERR_UNSUPPORTED (-3)  /* size outside the compiled variants (e.g. T > 2048, D not 128/256) */
+#define TB_ERR_MISALIGNED (-4)   /* pointer / leading dimension not 16-byte aligned where required    */
+#define TB_ERR_NULL (-5)         /* required pointer is NULL                                          */
+#define TB_ERR_CUDA (-6)         /* kernel launch failed (cudaGetLastError)                           */
+
+const char* tb_strerror(int code);
+int tb_version(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused pairwise relative pose + K-nearest-target selection.
+ * Replaces utils/rpe.py:9-37 (get_rel_pose) + :62-90 (get_tgt_knn_idx) + the row gathers of the winners.
+ * For every source token (b,s): rel pose of every target in the source frame
+ *   x' = dx cos(yaw_s) + dy sin(yaw_s), y' = -dx sin(yaw_s) + dy cos(yaw_s), dyaw = yaw_t - yaw_s (unwrapped),
+ * dist = |(x',y')|, +inf if source or target invalid; the K smallest (ties: lower target index) are emitted
+ * in ascending target-index order with  invalid = tgt_invalid | dist > dist_limit.
+ * Targets of batch row b are taken from tgt batch (b / tgt_batch_div): the 32 WOSAC rollouts of one scene
+ * share the scene's map / traffic-light table instead of a repeat_interleave copy
+ * (pl_modules/waymo_motion.py:458-462).
+ * Outputs are written at column offset `out_koff` of rows with `out_ldk` columns, so several selections
+ * can be concatenated in place (agent_encoder.py:165-167).
+ *   src_pose [B,S,3] src_invalid [B,S]  tgt_pose [B/div,T,3] tgt_invalid [B/div,T]
+ *   out_idx [B,S,ldk] int32   out_invalid [B,S,ldk] u8   out_rel [B,S,ldk,3] f32
+ * Limits: 0 < K < T <= 2048.
+ * ------------------------------------------------------------------------------------------------- */
+int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float* tgt_pose,
+                  const uint8_t* tgt_invalid, int B, int S, int T, int tgt_batch_div, int K, float dist_limit,
+                  int32_t* out_idx, uint8_t* out_invalid, float* out_rel, int out_ldk, int out_koff, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * KNARPE attention core (gather + relative-pose bias + masked softmax + weighted sum).
+ * Replaces modules/attention_rpe.py:137-190 between the input projections and the output projection, in the
+ * re-associated form:
+ *   logit_hj = q_h . k_hj + u_h . e_j           (u_h = W_rk,h^T q_h, computed by the caller's projection)
+ *   a_h = softmax_j(logit_hj)  over the non-masked neighbours   (q, u already carry 1/sqrt(d_head)*log2 e)
+ *   ov_h = sum_j a_hj v_hj ,  z_h = sum_j a_hj e_j
+ * e_j = PoseEmb("pe_xy_yaw") of the neighbour's relative pose (utils/pose_emb.py:50-55) evaluated in
+ * registers from `rel` [B,S,K,3], or read from `emb` [B,S,K,D] when the caller has it materialised
+ * (exactly one of rel/emb non-NULL). Neighbour j < K0 is row idx of table kv0, j >= K0 of table kv1
+ * (K1 may be 0); a table row is [k(D) | v(D)] at `kvX + (b/divX * TX + row) * ldkvX`.
+ * Rows whose neighbours are all masked produce zeros and none_valid = 1 (attention_rpe.py:112-118,188-190).
+ *   q [B*S] rows, leading dim ldq (D floats used);  u [B*S] rows, leading dim ldu (H*D floats, head-major)
+ *   out_ov / out_z: rows with leading dim ldo (D and H*D floats)
+ *   pe_freq_xy: D/8 floats = PositionalEmbedding(dim=D/4, theta).freqs[::2] (utils/positional_emb.py:11)
+ * Limits: D in {128,256} (d_rpe == D), H == 4, all leading dims and pointers 16-byte aligned.
+ * ------------------------------------------------------------------------------------------------- */
+int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
+                   const float* kv0, int ldkv0, int T0, int div0, int K0,
+                   const float* kv1, int ldkv1, int T1, int div1, int K1,
+                   const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,
+                   const float* pe_freq_xy, int B, int S, int D, int H,
+                   float* out_ov, float* out_z, int ldo, uint8_t* out_none_valid, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Dense projection  Y = epilogue(X W^T + bias)  — replaces F.linear / nn.Linear call sites
+ * (attention_rpe.py:96-97,147,186; transformer_rpe.py:237-238; modules/mlp.py:69).
+ *   X [M,K] ld ldx;  W [N,K] (nn.Linear layout) ld K;  Y [M,N] ld ldy
+ *   v = acc + bias[n]; if relu: v = max(v,0); if mask_pre[m]: v = 0; if res: v += res[m*ldr+n];
+ *   if mask_post[m]: v = 0.
+ * precision: 0 = fp32 FFMA (parity path), 1 = bf16 tcgen05 tensor cores with fp32 accumulate.
+ * ------------------------------------------------------------------------------------------------- */
+int tb_linear(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+              int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
+              int precision, void* stream);
+
+/* LayerNorm over the last dim (eps 1e-5, affine) — transformer_rpe.py:156-171. D in {128,256}. */
+int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy, int M, int D,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * PointNet pooling step over groups of L consecutive rows — modules/polyline_encoder.py:50-53 and
+ * utils/pooling.py:18-19,38. X rows have 2*C columns; the left C columns hold relu(Linear(x)).
+ * mode 0 (layer): right half <- max over the group's valid rows of the left half; invalid rows <- 0 (both halves)
+ * mode 1 (final): out[g, 0:2C] = max over valid rows of X (0 if the group has no valid row)
+ *   X [G*L, 2C] ld ldx, invalid [G*L] u8, out [G, 2C] (mode 1 only). 2C in {128,256}.
+ * ------------------------------------------------------------------------------------------------- */
+int tb_pointnet_pool(float* X, int ldx, const uint8_t* invalid, int G, int L, int C2, int mode, float* out, int ldo,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * PoseEmb("pe_xy_yaw") of poses expressed in a reference frame — utils/pose_emb.py:50-55 with
+ * transform_utils.py:146-157,200-213 (cast=False). For row m: (x,y,yaw) = pose[m] seen from frame[m / frame_div]
+ * (frame NULL => identity). Writes pe_dim floats at out[m*ldo .. ]. pe_dim in {64,128,256}.
+ * freq_xy: pe_dim/8 floats.
+ * ------------------------------------------------------------------------------------------------- */
+int tb_pose_emb(const float* pose, const float* frame, int frame_div, const float* freq_xy, int M, int pe_dim,
+                float* out, int ldo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Rollout state: ring buffers of the last W=11 steps, slot = time % W.
+ * `d_step` points to the device-resident loop counter s (1-based policy step, waymo_motion.py:233);
+ * the state in the ring covers times max(0,s-W) .. s-1.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Agent history tokens — agent_encoder.py:130-157 and pooling.py:24-29 (last_valid).
+ *   hist_valid [B,A,W] u8 (1 = valid), hist_pose/hist_motion [B,A,W,3], ag_attr [B,A,6]
+ * out: tok_pose [B,A,3], tok_invalid [B,A], row_invalid [B,A,W] (window order, oldest first; absent = 1),
+ *      attr rows [B*A*W, 20] = [attr6 | motion3 | one-hot11 (agent_encoder.py:154)] (ld lda),
+ *      pe rows: PoseEmb pe_dim=64 of the history pose in the token frame, written at pe_out (ld ldpe). */
+int tb_ag_featurize(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
+                    const float* ag_attr, const int* d_step, const float* freq_xy, int B, int A, int W,
+                    float* tok_pose, uint8_t* tok_invalid, uint8_t* row_invalid, float* attr_out, int lda,
+                    float* pe_out, int ldpe, void* stream);
+
+/* Traffic-light history rows — traffic_light.py:223-225: [state5 | one-hot11] per (b,tl,window slot).
+ *   hist_tl [B,TL,W,5] u8 one-hot, tl_invalid [B,TL]; out rows [B*TL*W,16] (ld lda), row_invalid [B,TL,W]. */
+int tb_tl_featurize(const uint8_t* hist_tl, const uint8_t* tl_invalid, const int* d_step, int B, int TL, int W,
+                    float* attr_out, int lda, uint8_t* row_invalid, void* stream);
+
+/* Agent dynamics + closed-loop bookkeeping for one step — utils/dynamics.py:66-141,166-204 (update_ag,
+ * override_ag, disable_ag, disable_navi), MultiPathPP :237-274, teacher_forcing.py:126-147,
+ * traffic_rule_checker.py:107-116 (outside map) and :291-319 (dest reached), waymo_motion.py:179-190,250,289-290.
+ *   act_branch [B*A, 3*2]: per-type action-head outputs (veh,ped,cyc) (action_head.py:78-82)
+ *   ag_type [B,A,3] u8 one-hot, max_acc[3], max_yaw_rate[3] (HOST arrays; veh,ped,cyc), dt
+ *   state (in/out): valid/disabled/navi_invalid/dest_reached [B,A] u8 (1 = true), pose/motion [B,A,3]
+ *   gt_* [B/sc_div, A, n_gt(,3)], tf_mask [B/sc_div, A, n_gt] (teacher_forcing.py:51-82); sc_div = rollouts per scene
+ *   boundary [B/sc_div,4] (xmin,xmax,ymin,ymax); dest_idx [B,A] int32 polyline index of each agent's destination;
+ *   per-scene destination tables (traffic_rule_checker.py:86-105): mp_pos [B/sc_div,n_mp,n_node,2],
+ *   mp_dirn (unit direction) same shape, mp_node_invalid [B/sc_div,n_mp,n_node] u8,
+ *   mp_kind [B/sc_div,n_mp] u8 (1 = lane types 0..3, 2 = road edge type 4, 0 = never reached);
+ *   thresh_lane / thresh_edge (50 m / 50*(1-0.8) m) and cos_rot = cos(30 deg) as the reference rounds them
+ *   out: pred_valid [B,A,T] u8, pred_pose/pred_motion [B,A,T,3] at index s-1; ring slot s%W of hist_*. */
+int tb_dyn_step(const float* act_branch, const uint8_t* ag_type, const float* max_acc, const float* max_yaw_rate,
+                float dt, uint8_t* valid, uint8_t* disabled, uint8_t* navi_invalid, uint8_t* dest_reached,
+                float* pose, float* motion, const uint8_t* gt_valid, const float* gt_pose, const float* gt_motion,
+                const uint8_t* tf_mask, int n_gt, int sc_div, const float* boundary, const int32_t* dest_idx,
+                const float* mp_pos, const float* mp_dirn, const uint8_t* mp_node_invalid, const uint8_t* mp_kind,
+                int n_mp, int n_node, float thresh_lane, float thresh_edge, float cos_rot, const int* d_step, int B,
+                int A, int W, int T, uint8_t* hist_valid, float* hist_pose, float* hist_motion, uint8_t* pred_valid,
+                float* pred_pose, float* pred_motion, void* stream);
+
+/* Traffic-light feedback — utils/dynamics.py:144-163 (override_tl), traffic_light.py:286 (clamp +-3).
+ *   logits [B*TL,5] (pre-clamp, invalid rows are zeroed here), tl_invalid [B,TL], gt_tl [B,TL,n_gt,5] u8.
+ *   writes the new one-hot state into ring slot s%W of hist_tl [B,TL,W,5] and tl_out [B,TL,T,5] at s-1. */
+int tb_tl_step(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt_tl, int n_gt, const int* d_step,
+               int B, int TL, int W, int T, uint8_t* hist_tl, uint8_t* tl_out, void* stream);
+
+/* s <- s + 1 on the device (single thread); keeps the step graph replayable. */
+int tb_step_advance(int* d_step, void* stream);
+
+/* Gather rows: out[m, 0:C] = table[(m / rows_per_batch / div) * T + idx[m], 0:C] — navigation.py:69,
+ * traffic_light.py:115. */
+int tb_gather_rows(const float* table, int ldt, int T, const int32_t* idx, int M, int rows_per_batch, int div, int C,
+                   float* out, int ldo, void* stream);
+
+/* Sum of the three type-masked branches is done inside tb_dyn_step; this helper exposes the masked action
+ * mean [B,A,2] for the module-level API (action_head.py:78-82). */
+int tb_action_mean(const float* act_branch, const uint8_t* ag_type, const uint8_t* valid, int M, float* mean,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TB_KNARPE_H_ */

@@ -1,0 +1,260 @@
+"""GPU parity tests: every CUDA kernel (called through the C ABI via ops.*) against the CPU oracle and against
+the golden vectors produced by the real reference. Tolerances are written next to each check."""
+import pytest
+import torch
+
+from oracle import tb_oracle as O
+from trafficbotsv1_5_b200 import config, params
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from trafficbotsv1_5_b200 import ops
+    from trafficbotsv1_5_b200.model import HotPathModel, fuse_attention, H
+
+DEV = "cuda"
+
+
+def close(a, b, rtol, atol, what):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    err = (a - b).abs()
+    lim = atol + rtol * b.abs()
+    bad = err > lim
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{bad.numel()} out of tol; max abs err "
+                                 f"{float(err.max()):.3e} (ref max {float(b.abs().max()):.3e})")
+
+
+def rel_l2(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------ knn select
+def _knn_case(B, S, T, K, lim, seed, self_attn=False, div=1, p_inv=0.2):
+    g = torch.Generator().manual_seed(seed)
+    pose = torch.cat([(torch.rand(B, S, 2, generator=g) * 2 - 1) * 100, (torch.rand(B, S, 1, generator=g) * 2 - 1) * 3], -1)
+    inv = torch.rand(B, S, generator=g) < p_inv
+    if self_attn:
+        return pose, inv, pose, inv
+    Bt = B // div
+    pose2 = torch.cat([(torch.rand(Bt, T, 2, generator=g) * 2 - 1) * 150, (torch.rand(Bt, T, 1, generator=g) * 2 - 1) * 3], -1)
+    inv2 = torch.rand(Bt, T, generator=g) < p_inv
+    return pose, inv, pose2, inv2
+
+
+def _check_knn(pose, inv, pose2, inv2, K, lim, div=1):
+    idx, knn_inv, rel = ops.knn_select(pose.to(DEV), inv.to(DEV), pose2.to(DEV), inv2.to(DEV), K, lim, tgt_div=div)
+    idx, knn_inv, rel = idx.cpu().long(), knn_inv.cpu(), rel.cpu()
+    p2, i2 = pose2.repeat_interleave(div, 0), inv2.repeat_interleave(div, 0)
+    rel_pose, rel_dist = O.get_rel_pose(pose, inv, p2, i2)
+    o_idx, o_inv, o_rel = O.knn_select(i2, rel_pose, rel_dist, K, lim)
+    sd = torch.sort(rel_dist, -1)[0]
+    # rows whose K-th / (K+1)-th distances are separated (tie-free) must match the oracle bit-exactly as SETS
+    gap_ok = (sd[..., K] - sd[..., K - 1] > 1e-4 * sd[..., K - 1].clamp(min=1.0)) | ~torch.isfinite(sd[..., K - 1])
+    d_sel = torch.gather(rel_dist, 2, idx)
+    fin = torch.isfinite(d_sel)
+    a = idx.masked_fill(~fin, -1).sort(-1)[0]
+    b = o_idx.masked_fill(~torch.isfinite(torch.gather(rel_dist, 2, o_idx)), -1).sort(-1)[0]
+    assert torch.equal(a[gap_ok], b[gap_ok]), "KNN index sets differ on tie-free rows"
+    assert int(gap_ok.sum()) > 0.9 * gap_ok.numel()
+    # selected indices are distinct and in range; emitted in ascending index order
+    assert bool((idx[..., 1:] > idx[..., :-1]).all())
+    assert int(idx.min()) >= 0 and int(idx.max()) < pose2.shape[1]
+    # invalid flag and relative pose of every selected neighbour (1e-4 m / 1e-6 rad abs: fp32 rotation rounding)
+    exp_inv = torch.gather(i2[:, None].expand(-1, pose.shape[1], -1), 2, idx) | (d_sel > lim)
+    near = (d_sel - lim).abs() < 1e-3
+    assert torch.equal(knn_inv | near, exp_inv | near)
+    exp_rel = torch.gather(rel_pose, 2, idx[..., None].expand(-1, -1, -1, 3))
+    close(rel[fin][:, :2], exp_rel[fin][:, :2], 0, 1e-4, "rel xy")
+    close(rel[..., 2], exp_rel[..., 2], 0, 1e-6, "rel yaw")
+
+
+@pytest.mark.parametrize("B,S,T,K,lim,self_attn,div", [
+    (2, 24, 50, 12, 60.0, False, 1), (3, 40, 40, 24, 250.0, True, 1), (4, 128, 1024, 64, 500.0, False, 2),
+    (2, 128, 128, 25, 500.0, True, 1), (6, 128, 40, 25, 500.0, False, 3), (1, 7, 33, 32, 1e9, False, 1),
+    (1, 70, 2048, 100, 80.0, False, 1), (2, 5, 300, 1, 100.0, False, 1)])
+def test_knn_select_vs_oracle(B, S, T, K, lim, self_attn, div):
+    _check_knn(*_knn_case(B, S, T, K, lim, 100 + T + K, self_attn, div), K, lim, div)
+
+
+def test_knn_select_all_invalid_and_errors():
+    pose, inv, pose2, inv2 = _knn_case(1, 8, 64, 10, 100.0, 5)
+    inv[:] = True
+    idx, kinv, _ = ops.knn_select(pose.to(DEV), inv.to(DEV), pose2.to(DEV), inv2.to(DEV), 10, 100.0)
+    assert bool(kinv.all())
+    with pytest.raises(RuntimeError):  # reference assert 0 < K < T (utils/rpe.py:79)
+        ops.knn_select(pose.to(DEV), inv.to(DEV), pose2.to(DEV), inv2.to(DEV), 64, 100.0)
+
+
+@pytest.mark.parametrize("name", ["knn_small", "knn_self_", "knn_big"])
+def test_knn_select_golden(golden_ops, name):
+    g = golden_ops[name]
+    p2 = g["pose"] if g["pose2"] is None else g["pose2"]
+    i2 = g["inv"] if g["inv2"] is None else g["inv2"]
+    idx, kinv, rel = ops.knn_select(g["pose"].to(DEV), g["inv"].to(DEV), p2.to(DEV), i2.to(DEV), g["K"], g["lim"])
+    fin = torch.isfinite(g["dist"])
+    # golden rows are sorted by distance, ours by index: compare as sets (inf fillers free)
+    a = idx.cpu().long()
+    rel_pose, rel_dist = O.get_rel_pose(g["pose"], g["inv"], g["pose2"], g["inv2"])
+    mine_fin = torch.isfinite(torch.gather(rel_dist, 2, a))
+    assert torch.equal(a.masked_fill(~mine_fin, -1).sort(-1)[0], g["idx"].masked_fill(~fin, -1).sort(-1)[0])
+    assert int(kinv.sum()) == int(g["knn_inv"].sum())
+
+
+# ------------------------------------------------------------------------------------------------ small ops
+@pytest.mark.parametrize("M,N,K,flags", [(300, 128, 128, "b"), (1000, 896, 128, "b"), (77, 5, 128, "b"),
+                                         (513, 121, 31, "br"), (200, 121, 121, "b"), (129, 64, 128, "brm"),
+                                         (640, 128, 640, "bpr+"), (50, 2, 128, ""), (4097, 512, 128, "br"),
+                                         (333, 128, 512, "b+q")])
+def test_linear_f32(M, N, K, flags):
+    g = torch.Generator().manual_seed(M + N)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    mp, mq = torch.rand(M, generator=g) < 0.3, torch.rand(M, generator=g) < 0.3
+    y = torch.nn.functional.linear(x.double(), w.double(), b.double() if "b" in flags else None)
+    kw = {}
+    if "r" in flags:
+        y = y.relu(); kw["relu"] = True
+    if "p" in flags or "m" in flags:
+        y = y.masked_fill(mp[:, None], 0); kw["mask_pre"] = mp.to(DEV)
+    if "+" in flags:
+        y = y + res.double(); kw["res"] = res.to(DEV)
+    if "q" in flags:
+        y = y.masked_fill(mq[:, None], 0); kw["mask_post"] = mq.to(DEV)
+    out = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV) if "b" in flags else None, **kw)
+    close(out, y.float(), 1e-5, 1e-5, f"linear {M}x{N}x{K} {flags}")  # fp32 FFMA vs float64: 1e-5
+
+
+def test_linear_strided_views():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(100, 384, generator=g).to(DEV)
+    w = (torch.randn(128, 128, generator=g) / 11).to(DEV)
+    out = torch.zeros(100, 384, device=DEV)
+    ops.linear(x[:, 128:256], w, None, out=out[:, 256:])
+    close(out[:, 256:], x[:, 128:256] @ w.T, 1e-5, 1e-5, "strided linear")
+    assert float(out[:, :256].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("D", [128, 256])
+def test_layernorm(D):
+    g = torch.Generator().manual_seed(D)
+    x, w, b = torch.randn(333, D, generator=g) * 3 + 1, torch.randn(D, generator=g), torch.randn(D, generator=g)
+    y = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-5)
+    close(ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV)), y, 1e-5, 1e-5, "layernorm")
+
+
+@pytest.mark.parametrize("pe", [64, 128, 256])
+def test_pose_emb(golden_ops, pe):
+    g = golden_ops[f"pe_{pe}"]
+    pose = torch.cat([g["xy"], g["yaw"]], -1).reshape(-1, 3)
+    out = ops.pose_emb(pose.to(DEV), ops.pe_freq_xy(pe, 1e3, DEV), pe)
+    # SFU sin/cos after exact 2-term range reduction: 2e-6 abs (documented 2^-21.4 on [-pi,pi])
+    close(out, g["emb"].reshape(-1, pe), 0, 2e-6, f"pose_emb {pe}")
+
+
+def test_pose_emb_frame():
+    g = torch.Generator().manual_seed(9)
+    pose = torch.cat([(torch.rand(50, 2, generator=g) * 2 - 1) * 200, (torch.rand(50, 1, generator=g) * 2 - 1) * 3], -1)
+    frame = torch.cat([(torch.rand(50, 2, generator=g) * 2 - 1) * 200, (torch.rand(50, 1, generator=g) * 2 - 1) * 3], -1)
+    xy = O.to_local_xy(pose[:, None, :2], frame[:, None, :2], frame[:, 2]).squeeze(1)
+    ref = O.pose_emb_xy_yaw(xy, pose[:, 2] - frame[:, 2], 128)
+    out = ops.pose_emb(pose.to(DEV), ops.pe_freq_xy(128, 1e3, DEV), 128, frame=frame.to(DEV))
+    close(out, ref, 0, 1e-4, "pose_emb in frame")  # 1e-4: fp32 rounding of the rotated x,y times f_0 = 1 rad/m
+
+
+def test_pointnet(golden_ops):
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, 3)
+    g = torch.Generator().manual_seed(4)
+    B, N, Lg, d = 3, 17, 11, 128
+    x = torch.randn(B, N, Lg, d, generator=g)
+    inv = torch.rand(B, N, Lg, generator=g) < 0.4
+    inv[0, 0] = True
+    ref = O.pointnet(P, "ag_encoder.temp_encoder", x, inv)
+    m = HotPathModel(P, cfg, config.derived_sizes(cfg), DEV)
+    out = m.pointnet(x.reshape(-1, d).to(DEV), inv.reshape(-1).to(DEV), B * N, Lg, "ag_encoder.temp_encoder")
+    close(out, ref.reshape(-1, d), 1e-5, 1e-5, "pointnet")
+    assert float(out[0].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ KNARPE attention
+def _run_attention(sd, src, tgt, mask, rel, use_emb=False):
+    """AttentionRPE semantics with an arbitrary pre-gathered tgt [B,S,K,d]: table = tgt flattened, idx = s*K+k."""
+    B, S, K, d = tgt.shape
+    P = {f"a.{k}": v for k, v in sd.items()}
+    f = {k: v.to(DEV) for k, v in fuse_attention(P, "a", d).items()}
+    proj = ops.linear(src.reshape(B * S, d).to(DEV), f["w_in_q"], f["b_in_q"])
+    kv = ops.linear(tgt.reshape(B * S * K, d).to(DEV), f["w_kv"], f["b_kv"])
+    idx = torch.arange(S * K, dtype=torch.int32, device=DEV).view(1, S, K).expand(B, -1, -1).contiguous()
+    freq = ops.pe_freq_xy(d, 1e3, DEV)
+    emb = O.pose_emb_xy_yaw(rel[..., :2], rel[..., 2], d).to(DEV).contiguous() if use_emb else None
+    o, nv = ops.knarpe_attn(proj[:, :d], proj[:, d:], kv, S * K, 1, K, idx, mask.to(DEV).contiguous(),
+                            None if use_emb else rel.to(DEV).contiguous(), freq, B, S, d, H, emb=emb)
+    out = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv)
+    return out.view(B, S, d), nv.view(B, S)
+
+
+@pytest.mark.parametrize("name", ["attn_d128", "attn_d256"])
+@pytest.mark.parametrize("use_emb", [False, True])
+def test_attention_golden(golden_ops, name, use_emb):
+    g = golden_ops[name]
+    sd = params.rand_like_state_dict(g["sd_shapes"], g["sd_seed"])
+    out, nv = _run_attention(sd, g["src"], g["tgt"], g["mask"], g["rel"], use_emb)
+    # north star: attention outputs within 1e-4 relative in fp32 (relative to the output scale)
+    scale = float(g["out"].abs().max())
+    close(out, g["out"], 1e-4, 1e-4 * scale, f"{name} emb={use_emb}")
+    assert rel_l2(out, g["out"]) < 2e-5
+    assert bool(nv[0, 0]) and float(out[0, 0].abs().max()) == 0.0  # all-masked row -> exact zero
+
+
+@pytest.mark.parametrize("d,B,S,K", [(128, 2, 130, 89), (128, 1, 64, 25), (256, 1, 40, 36), (128, 3, 33, 1)])
+def test_attention_vs_oracle_and_properties(d, B, S, K):
+    g = torch.Generator().manual_seed(d + K)
+    shapes = {"in_proj_weight": (3 * d, d), "in_proj_bias": (3 * d,), "out_proj_weight": (d, d), "out_proj_bias": (d,),
+              "linear_rpe.weight": (2 * d, d), "linear_rpe.bias": (2 * d,)}
+    sd = params.rand_like_state_dict(shapes, 21)
+    src, tgt = torch.randn(B, S, d, generator=g), torch.randn(B, S, K, d, generator=g)
+    mask = torch.rand(B, S, K, generator=g) < 0.3
+    mask[0, 1] = True
+    rel = torch.cat([(torch.rand(B, S, K, 2, generator=g) * 2 - 1) * 300, (torch.rand(B, S, K, 1, generator=g) * 2 - 1) * 7], -1)
+    P = {f"a.{k}": v for k, v in sd.items()}
+    ref = O.attention_rpe(P, "a", src, tgt, mask, O.pose_emb_xy_yaw(rel[..., :2], rel[..., 2], d), H)
+    out, _ = _run_attention(sd, src, tgt, mask, rel)
+    scale = float(ref.abs().max())
+    close(out, ref, 1e-4, 1e-4 * scale, "attention vs oracle")
+    assert float(out[0, 1].abs().max()) == 0.0
+    # permutation invariance over the neighbour order (fp summation order only): 1e-5 relative
+    perm = torch.randperm(K, generator=g)
+    out_p, _ = _run_attention(sd, src, tgt[:, :, perm], mask[:, :, perm], rel[:, :, perm])
+    close(out_p, out, 1e-5, 1e-5 * scale, "permutation invariance")
+
+
+def _block_P(g):
+    return {f"b.{k}": v for k, v in params.rand_like_state_dict(g["sd_shapes"], g["sd_seed"]).items()}
+
+
+@pytest.mark.parametrize("mode", ["enc_self_attn", "dec_cross_attn"])
+def test_transformer_block_golden(golden_ops, mode):
+    g = golden_ops[f"block_{mode}"]
+    P = _block_P(g)
+    cfg = config.default_model_cfg()
+    full = params.init_params(cfg, 0)
+    full.update(P)
+    m = HotPathModel(full, cfg, config.derived_sizes(cfg), DEV)
+    B, S, d = g["src"].shape
+    src = g["src"].reshape(B * S, d).to(DEV)
+    inv = g["src_inv"].reshape(-1).to(DEV)
+    knn_self = dict(idx=g["idx"].to(DEV, torch.int32).contiguous(), inv=g["m1"].to(DEV).contiguous(),
+                    rel=g["rel1"].to(DEV).contiguous())
+    for i in range(g["n_layer"]):
+        p = f"b.layers.{i}"
+        cross = None
+        if mode == "dec_cross_attn":
+            T2 = g["tgt_tab"].shape[1]
+            kv = m.kv_table(g["tgt_tab"].reshape(-1, d).to(DEV), p, "norm_tgt")
+            cross = dict(kv0=kv, T0=T2, div0=1, K0=g["idx2"].shape[-1], idx=g["idx2"].to(DEV, torch.int32).contiguous(),
+                         inv=g["m2"].to(DEV).contiguous(), rel=g["rel2"].to(DEV).contiguous())
+        src = m.tf_layer(p, mode, src, inv, B, S, knn_self, cross)
+    scale = float(g["out"].abs().max())
+    close(src.view(B, S, d), g["out"], 1e-4, 1e-4 * scale, f"block {mode}")
+    assert rel_l2(src.view(B, S, d), g["out"]) < 2e-5

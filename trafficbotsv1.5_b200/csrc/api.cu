@@ -1,0 +1,37 @@
+// C-ABI glue: error strings, version, precision dispatch of tb_linear.
+#include "common.cuh"
+
+int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
+                  cudaStream_t st);
+int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+                 int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
+                 cudaStream_t st);
+
+extern "C" const char* tb_strerror(int code) {
+  switch (code) {
+    case TB_OK: return "ok";
+    case TB_ERR_BAD_SHAPE: return "bad shape";
+    case TB_ERR_KNN_RANGE: return "need 0 < K < T";
+    case TB_ERR_UNSUPPORTED: return "unsupported size";
+    case TB_ERR_MISALIGNED: return "misaligned pointer or leading dimension";
+    case TB_ERR_NULL: return "null pointer";
+    case TB_ERR_CUDA: return "CUDA launch failed";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int tb_version(void) { return 100; }
+
+extern "C" int tb_linear(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N,
+                         int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
+                         int precision, void* stream) {
+  if (!X || !W || !Y) return TB_ERR_NULL;
+  if (M <= 0 || N <= 0 || K <= 0 || ldx < K || ldy < N || (res && ldr < N)) return TB_ERR_BAD_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == 0)
+    return tb_linear_f32(X, ldx, W, bias, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+  if (precision == 1)
+    return tb_linear_tc(X, ldx, W, bias, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+  return TB_ERR_UNSUPPORTED;
+}

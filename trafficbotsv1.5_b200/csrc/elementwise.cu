@@ -1,0 +1,164 @@
+// Row-wise helpers around the projections: LayerNorm, PointNet pooling, pose embedding, row gather.
+#include "common.cuh"
+
+namespace {
+
+// ---- LayerNorm (transformer_rpe.py:156-171): one warp per row, D/32 floats per lane, two-pass in registers.
+template <int D>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float* __restrict__ Y, int ldy, int M) {
+  constexpr int NV = D / 32;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[NV];
+  const float* xp = X + (size_t)row * ldx + lane * NV;
+#pragma unroll
+  for (int i = 0; i < NV; i += 4) {
+    float4 t = *reinterpret_cast<const float4*>(xp + i);
+    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += v[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(TB_FULL_MASK, s, o);
+  const float mean = s * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(TB_FULL_MASK, q, o);
+  const float rstd = 1.f / sqrtf(q * (1.f / D) + 1e-5f);
+  float* yp = Y + (size_t)row * ldy + lane * NV;
+#pragma unroll
+  for (int i = 0; i < NV; i += 4) {
+    const float4 g = ldg4(gamma + lane * NV + i), bb = ldg4(beta + lane * NV + i);
+    float4 o;
+    o.x = (v[i] - mean) * rstd * g.x + bb.x;
+    o.y = (v[i + 1] - mean) * rstd * g.y + bb.y;
+    o.z = (v[i + 2] - mean) * rstd * g.z + bb.z;
+    o.w = (v[i + 3] - mean) * rstd * g.w + bb.w;
+    *reinterpret_cast<float4*>(yp + i) = o;
+  }
+}
+
+// ---- PointNet pooling (polyline_encoder.py:50-53, pooling.py:18-19,38): one warp per group of L rows.
+// mode 0: right half <- max over valid rows of left half (broadcast to valid rows); invalid rows <- 0.
+// mode 1: out[g] <- max over valid rows of all 2C columns (0 if none valid).
+__global__ void __launch_bounds__(256)
+pointnet_pool_kernel(float* __restrict__ X, int ldx, const uint8_t* __restrict__ invalid, int G, int L, int C2,
+                     int mode, float* __restrict__ out, int ldo) {
+  const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= G) return;
+  const int C = C2 / 2;
+  const uint8_t* inv = invalid + (size_t)g * L;
+  float* xg = X + (size_t)g * L * ldx;
+  if (mode == 0) {
+    for (int c = lane; c < C; c += 32) {
+      float m = -INFINITY;
+      for (int r = 0; r < L; ++r)
+        if (!inv[r]) m = fmaxf(m, xg[(size_t)r * ldx + c]);
+      for (int r = 0; r < L; ++r) {
+        if (inv[r]) { xg[(size_t)r * ldx + c] = 0.f; xg[(size_t)r * ldx + C + c] = 0.f; }
+        else xg[(size_t)r * ldx + C + c] = m;
+      }
+    }
+  } else {
+    for (int c = lane; c < C2; c += 32) {
+      float m = -INFINITY;
+      bool any = false;
+      for (int r = 0; r < L; ++r)
+        if (!inv[r]) { m = fmaxf(m, xg[(size_t)r * ldx + c]); any = true; }
+      out[(size_t)g * ldo + c] = any ? m : 0.f;
+    }
+  }
+}
+
+// ---- one component of PoseEmb("pe_xy_yaw") (pose_emb.py:50-55, positional_emb.py:24-25,40-41)
+__device__ __forceinline__ float pe_component(int c, int pe_dim, float x, float y, float w,
+                                              const float* __restrict__ freq_xy) {
+  const int n = pe_dim >> 3, q4 = pe_dim >> 2;
+  float a;
+  bool is_sin;
+  if (c < q4) { a = x * __ldg(freq_xy + (c % n)); is_sin = c >= n; }
+  else if (c < 2 * q4) { const int cc = c - q4; a = y * __ldg(freq_xy + (cc % n)); is_sin = cc >= n; }
+  else { const int cc = c - 2 * q4; a = w * (float)((cc % q4) + 1); is_sin = cc >= q4; }
+  const float r = tb_reduce_2pi(a);
+  return is_sin ? __sinf(r) : __cosf(r);
+}
+
+__global__ void __launch_bounds__(256)
+pose_emb_kernel(const float* __restrict__ pose, const float* __restrict__ frame, int frame_div,
+                const float* __restrict__ freq_xy, int M, int pe_dim, float* __restrict__ out, int ldo) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float x = pose[(size_t)m * 3], y = pose[(size_t)m * 3 + 1], w = pose[(size_t)m * 3 + 2];
+  if (frame) {
+    const float* f = frame + (size_t)(m / frame_div) * 3;
+    float sn, cs;
+    sincosf(f[2], &sn, &cs);
+    const float dx = x - f[0], dy = y - f[1];
+    x = fmaf(dx, cs, dy * sn);
+    y = fmaf(dy, cs, -dx * sn);
+    w = w - f[2];
+  }
+  for (int c = lane; c < pe_dim; c += 32) out[(size_t)m * ldo + c] = pe_component(c, pe_dim, x, y, w, freq_xy);
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ table, int ldt, int T, const int32_t* __restrict__ idx,
+                                   int M, int rows_per_batch, int div, int C, float* __restrict__ out, int ldo) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const int bt = (m / rows_per_batch) / div;
+  const float* src = table + ((size_t)bt * T + idx[m]) * ldt;
+  for (int c = lane; c < C; c += 32) out[(size_t)m * ldo + c] = src[c];
+}
+
+}  // namespace
+
+extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy, int M,
+                            int D, void* stream) {
+  if (!X || !gamma || !beta || !Y) return TB_ERR_NULL;
+  if (M <= 0 || ldx < D || ldy < D) return TB_ERR_BAD_SHAPE;
+  if (D != 128 && D != 256) return TB_ERR_UNSUPPORTED;
+  if ((ldx | ldy) & 3 || !tb_aligned16(X) || !tb_aligned16(Y) || !tb_aligned16(gamma) || !tb_aligned16(beta))
+    return TB_ERR_MISALIGNED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (M + 7) / 8;
+  if (D == 128) layernorm_kernel<128><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M);
+  else layernorm_kernel<256><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+extern "C" int tb_pointnet_pool(float* X, int ldx, const uint8_t* invalid, int G, int L, int C2, int mode, float* out,
+                                int ldo, void* stream) {
+  if (!X || !invalid || (mode == 1 && !out)) return TB_ERR_NULL;
+  if (G <= 0 || L <= 0 || C2 <= 0 || (C2 & 1) || ldx < C2 || (mode != 0 && mode != 1)) return TB_ERR_BAD_SHAPE;
+  pointnet_pool_kernel<<<(G + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, ldx, invalid, G, L, C2, mode, out,
+                                                                                 ldo);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+extern "C" int tb_pose_emb(const float* pose, const float* frame, int frame_div, const float* freq_xy, int M,
+                           int pe_dim, float* out, int ldo, void* stream) {
+  if (!pose || !freq_xy || !out) return TB_ERR_NULL;
+  if (M <= 0 || ldo < pe_dim || (frame && frame_div <= 0)) return TB_ERR_BAD_SHAPE;
+  if (pe_dim != 64 && pe_dim != 128 && pe_dim != 256) return TB_ERR_UNSUPPORTED;
+  pose_emb_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(pose, frame, frame_div, freq_xy, M, pe_dim,
+                                                                            out, ldo);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+extern "C" int tb_gather_rows(const float* table, int ldt, int T, const int32_t* idx, int M, int rows_per_batch,
+                              int div, int C, float* out, int ldo, void* stream) {
+  if (!table || !idx || !out) return TB_ERR_NULL;
+  if (M <= 0 || T <= 0 || rows_per_batch <= 0 || div <= 0 || C <= 0 || ldt < C || ldo < C) return TB_ERR_BAD_SHAPE;
+  gather_rows_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(table, ldt, T, idx, M, rows_per_batch,
+                                                                               div, C, out, ldo);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}

@@ -1,0 +1,227 @@
+"""Closed-loop WOSAC rollout engine: the reference's `WaymoMotion.test_step -> joint_future_pred -> rollout ->
+forward` chain (src/pl_modules/waymo_motion.py:843-876, 439-524, 206-311, 118-204) on the CUDA hot path.
+
+Differences in HOW (not WHAT), see DESIGN.md §4:
+  * the 32 rollouts of a scene index the scene's map / traffic-light tables (`b // R`) instead of
+    `repeat_interleave` copies (:458-462);
+  * the traffic-light branch depends only on (scene, TL history) — identical across a scene's rollouts and
+    deterministic (argmax, dynamics.py:154-159) — so it is evaluated once per scene (`tl_per_scene`);
+  * rollout state, history rings and the trajectory buffers stay resident in HBM for all steps; the loop counter
+    is a device scalar, so ONE captured CUDA graph is replayed for every step with no host sync.
+"""
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import config as C
+from . import lib as L
+from . import ops
+from .model import HotPathModel
+
+
+def teacher_forcing_mask(gt_valid: Tensor, step_spawn: int, step_warm: int) -> Tensor:
+    """TeacherForcing.init at test time (utils/teacher_forcing.py:51-82; schedules / thresholds off)."""
+    tf = torch.zeros_like(gt_valid)
+    tf[:, :, 0] |= gt_valid[:, :, 0]
+    if step_spawn > 0:
+        spawn = (~gt_valid[:, :, :-1]) & gt_valid[:, :, 1:]
+        spawn[:, :, step_spawn:] = False
+        tf[:, :, 1:] |= spawn
+    if step_warm >= 0:
+        tf[:, :, : step_warm + 1] |= gt_valid[:, :, : step_warm + 1]
+    return tf
+
+
+class RolloutEngine:
+    def __init__(self, P: Dict[str, Tensor], cfg: Optional[dict] = None, device="cuda", precision: int = 0,
+                 n_rollout: int = 32, step_end: Optional[int] = None, tl_per_scene: bool = True,
+                 use_graph: bool = True):
+        L.load()  # fail loudly if the CUDA library is missing
+        self.cfg = cfg or C.default_model_cfg()
+        self.sz = C.derived_sizes(self.cfg)
+        self.dev = torch.device(device)
+        self.model = HotPathModel(P, self.cfg, self.sz, device, precision)
+        self.R = n_rollout
+        self.T = step_end or C.ROLLOUT_CFG["time_step_end"]
+        self.tl_per_scene = tl_per_scene
+        self.use_graph = use_graph
+        self.dyn = C.DYNAMICS_CFG
+        self._graph = None
+        self._shape = None
+        # constants rounded the way the reference's fp32 tensor ops round them (traffic_rule_checker.py:94-96,103,308)
+        one = torch.ones(1)
+        self.thresh_lane = float(one * 50 * (1 - torch.zeros(1) * 0.8))
+        self.thresh_edge = float(one * 50 * (1 - one * 0.8))
+        self.cos_rot = float(torch.tensor(np.cos(np.deg2rad(30)), dtype=torch.float32))
+
+    # ---------------------------------------------------------------------------------------------- scene encoding
+    def encode_scenes(self, batch: Dict[str, Tensor]) -> dict:
+        """Once per scene: map encoder, TL static tokens, per-layer map K/V tables (test_step :847-851)."""
+        dev = self.dev
+        g = lambda k: batch[k].to(dev)  # noqa: E731
+        mp = self.model.map_encoder(g("sc/mp_valid"), g("sc/mp_attr"), g("sc/mp_pose"))
+        tl = self.model.tl_pre_compute(g("sc/tl_valid"), g("sc/tl_attr"), g("sc/tl_pose"), mp)
+        kv_mp = self.model.ag_static(mp)
+        return dict(mp=mp, tl=tl, kv_mp=kv_mp)
+
+    # ---------------------------------------------------------------------------------------------- state
+    def _alloc(self, n_sc: int, A: int, n_tl: int, n_gt: int, n_mp: int, n_node: int):
+        dev, R, W, T, d = self.dev, self.R, self.model.W, self.T, self.model.d
+        B = n_sc * R
+        Bt = n_sc if self.tl_per_scene else B
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
+        u8 = torch.uint8
+        st = dict(B=B, A=A, Bt=Bt, n_sc=n_sc, n_tl=n_tl, n_gt=n_gt, n_mp=n_mp, n_node=n_node,
+                  d_step=z(1, dt=torch.int32),
+                  valid=z(B, A, dt=u8), disabled=z(B, A, dt=u8), navi_invalid=z(B, A, dt=torch.bool),
+                  dest_reached=z(B, A, dt=u8), pose=z(B, A, 3), motion=z(B, A, 3),
+                  hist_valid=z(B, A, W, dt=u8), hist_pose=z(B, A, W, 3), hist_motion=z(B, A, W, 3),
+                  hist_tl=z(Bt, n_tl, W, 5, dt=u8),
+                  ag_attr=z(B, A, 6), ag_type=z(B, A, 3, dt=u8), latent=z(B * A, self.cfg["latent_encoder"]["latent_dim"]),
+                  latent_invalid=z(B, A, dt=torch.bool), dest_idx=z(B, A, dt=torch.int32),
+                  gt_valid=z(n_sc, A, n_gt, dt=u8), gt_pose=z(n_sc, A, n_gt, 3), gt_motion=z(n_sc, A, n_gt, 3),
+                  tf_mask=z(n_sc, A, n_gt, dt=u8), gt_tl=z(Bt, n_tl, n_gt, 5, dt=u8), boundary=z(n_sc, 4),
+                  mp_pos=z(n_sc, n_mp, n_node, 2), mp_dirn=z(n_sc, n_mp, n_node, 2),
+                  mp_node_invalid=z(n_sc, n_mp, n_node, dt=u8), mp_kind=z(n_sc, n_mp, dt=u8),
+                  pred_valid=z(B, A, T, dt=u8), pred_pose=z(B, A, T, 3), pred_motion=z(B, A, T, 3),
+                  tl_out=z(Bt, n_tl, T, 5, dt=u8), x_cat=z(B * A, 2 * d),
+                  init_navi_valid=z(B, A, dt=torch.bool))
+        return st
+
+    def _load_state(self, st: dict, batch: Dict[str, Tensor]):
+        """Dynamics.init / TeacherForcing.init / TrafficRuleChecker.__init__ inputs (dynamics.py:29-64,
+        teacher_forcing.py:51-82, traffic_rule_checker.py:86-105), replicated R times by index only."""
+        dev, R = self.dev, self.R
+        g = lambda k: batch[k].to(dev)  # noqa: E731
+        rep = lambda t: t.repeat_interleave(R, 0)  # noqa: E731
+        rc = C.ROLLOUT_CFG
+        n_sc = st["n_sc"]
+        gt_valid = g("sc/ag_valid")
+        st["gt_valid"].copy_(gt_valid)
+        st["gt_pose"].copy_(g("sc/ag_pose"))
+        st["gt_motion"].copy_(g("sc/ag_motion"))
+        st["tf_mask"].copy_(teacher_forcing_mask(gt_valid, rc["step_spawn_agent"], rc["step_warm_start"]))
+        tl_gt = g("sc/tl_state")
+        st["gt_tl"].copy_(tl_gt if self.tl_per_scene else rep(tl_gt))
+        st["boundary"].copy_(g("map/boundary"))
+        st["ag_attr"].copy_(rep(g("sc/ag_attr")))
+        st["ag_type"].copy_(rep(g("ref/ag_type")))
+        lat = g("ag_latent")[:, :R]
+        st["latent"].copy_(lat.reshape(n_sc * R * st["A"], -1))
+        st["latent_invalid"].copy_(~rep(g("ag_latent_valid")))
+        dest = g("agent/dest")
+        if dest.dim() == 2:  # one destination per (scene, agent); [n_sc, R, A] = per-rollout samples
+            dest = dest[:, None].expand(-1, R, -1)
+        st["dest_idx"].copy_(dest.reshape(n_sc * R, -1))
+        st["init_navi_valid"].copy_(rep(g("ag_navi_valid")))
+        mp_dir = g("map/dir")[..., :2]
+        st["mp_pos"].copy_(g("map/pos")[..., :2])
+        st["mp_dirn"].copy_(mp_dir / torch.norm(mp_dir, dim=-1, keepdim=True))
+        st["mp_node_invalid"].copy_(~g("map/valid"))
+        mp_type = g("map/type")
+        st["mp_kind"].copy_(mp_type[..., :4].any(-1).to(torch.uint8) + 2 * mp_type[..., 4].to(torch.uint8))
+
+    def _reset(self, st: dict):
+        """time 0 of the rollout (waymo_motion.py:219-227)."""
+        R = self.R
+        rep = lambda t: t.repeat_interleave(R, 0)  # noqa: E731
+        for k in ("disabled", "dest_reached", "hist_valid", "hist_pose", "hist_motion", "hist_tl", "pred_valid",
+                  "pred_pose", "pred_motion", "tl_out"):
+            st[k].zero_()
+        st["valid"].copy_(rep(st["gt_valid"][:, :, 0]))
+        st["pose"].copy_(rep(st["gt_pose"][:, :, 0]))
+        st["motion"].copy_(rep(st["gt_motion"][:, :, 0]))
+        st["navi_invalid"].copy_(~st["init_navi_valid"])
+        st["hist_valid"][:, :, 0] = st["valid"]
+        st["hist_pose"][:, :, 0] = st["pose"]
+        st["hist_motion"][:, :, 0] = st["motion"]
+        st["hist_tl"][:, :, 0] = st["gt_tl"][:, :, 0]
+        st["d_step"].fill_(1)
+
+    # ---------------------------------------------------------------------------------------------- one step
+    def _step(self, st: dict, static: dict, navi: dict, aux: Optional[dict] = None):
+        m, lib = self.model, L.load()
+        d = m.d
+        tl_feat, logits = m.tl_forward(st["hist_tl"], st["d_step"], static["tl"])
+        m.ag_forward(st, static["mp"], static["kv_mp"], static["tl"], tl_feat, self.R, out=st["x_cat"][:, :d],
+                     aux=aux)
+        act = m.heads(st["x_cat"], st, navi)
+        if aux is not None:
+            aux.update(tl_feat=tl_feat, logits=logits, act=act, ag_feat=st["x_cat"][:, :d].clone())
+        dy = self.dyn
+        order = ("veh", "ped", "cyc")
+        L.check(lib.tb_dyn_step(
+            L.ptr(act), L.ptr(st["ag_type"]), ops.host_f3([dy[k]["max_acc"] for k in order]),
+            ops.host_f3([dy[k]["max_yaw_rate"] for k in order]), dy["dt"], L.ptr(st["valid"]), L.ptr(st["disabled"]),
+            L.ptr(ops._u8(st["navi_invalid"])), L.ptr(st["dest_reached"]), L.ptr(st["pose"]), L.ptr(st["motion"]),
+            L.ptr(st["gt_valid"]), L.ptr(st["gt_pose"]), L.ptr(st["gt_motion"]), L.ptr(st["tf_mask"]), st["n_gt"],
+            self.R, L.ptr(st["boundary"]), L.ptr(st["dest_idx"]), L.ptr(st["mp_pos"]), L.ptr(st["mp_dirn"]),
+            L.ptr(st["mp_node_invalid"]), L.ptr(st["mp_kind"]), st["n_mp"], st["n_node"], self.thresh_lane,
+            self.thresh_edge, self.cos_rot, L.ptr(st["d_step"]), st["B"], st["A"], m.W, self.T, L.ptr(st["hist_valid"]),
+            L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]), L.ptr(st["pred_valid"]), L.ptr(st["pred_pose"]),
+            L.ptr(st["pred_motion"]), L.stream()), "tb_dyn_step")
+        L.check(lib.tb_tl_step(L.ptr(logits), L.ptr(ops._u8(static["tl"]["tl_token_invalid"])), L.ptr(st["gt_tl"]),
+                               st["n_gt"], L.ptr(st["d_step"]), st["Bt"], st["n_tl"], m.W, self.T, L.ptr(st["hist_tl"]),
+                               L.ptr(st["tl_out"]), L.stream()), "tb_tl_step")
+        L.check(lib.tb_step_advance(L.ptr(st["d_step"]), L.stream()), "tb_step_advance")
+        ops._count(3)
+
+    # ---------------------------------------------------------------------------------------------- public API
+    def prepare(self, batch: Dict[str, Tensor], static: Optional[dict] = None) -> dict:
+        """Upload a batch of scenes, encode them (unless `static` is given) and build the step graph."""
+        n_sc, A, n_gt = batch["sc/ag_valid"].shape
+        n_tl = batch["sc/tl_valid"].shape[1]
+        _, n_mp, n_node = batch["sc/mp_valid"].shape
+        shape = (n_sc, A, n_tl, n_gt, n_mp, n_node)
+        if self._shape != shape:
+            self._st = self._alloc(*shape)
+            self._shape, self._graph = shape, None
+        st = self._st
+        self._load_state(st, batch)
+        self._static = static if static is not None else self.encode_scenes(batch)
+        self._navi = self.model.navi_static(self._static["mp"], st["dest_idx"], self.R)
+        self._graph = None  # static tensors changed -> recapture
+        return st
+
+    def run(self, n_steps: Optional[int] = None, record=None) -> Dict[str, Tensor]:
+        """Run the closed loop from time 0 for n_steps (default: all). Returns views of the trajectory buffers."""
+        st, n_steps = self._st, n_steps or self.T
+        self._reset(st)
+        if self.use_graph and record is None:
+            if self._graph is None:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._step(st, self._static, self._navi)  # warm-up (allocator, lazy module load)
+                torch.cuda.current_stream().wait_stream(s)
+                self._reset(st)
+                n0 = ops.LAUNCHES
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._step(st, self._static, self._navi)
+                self.launches_per_step = ops.LAUNCHES - n0
+            for _ in range(n_steps):
+                self._graph.replay()
+        else:
+            for s_ in range(1, n_steps + 1):
+                aux = {} if record is not None else None
+                n0 = ops.LAUNCHES
+                self._step(st, self._static, self._navi, aux)
+                self.launches_per_step = ops.LAUNCHES - n0
+                if record is not None:
+                    record(s_, aux)
+        return self.results()
+
+    def results(self) -> Dict[str, Tensor]:
+        st, R = self._st, self.R
+        n_sc, A = st["n_sc"], st["A"]
+        tl = st["tl_out"] if not self.tl_per_scene else st["tl_out"].repeat_interleave(R, 0)
+        return dict(pred_valid=st["pred_valid"].bool(), pred_pose=st["pred_pose"], pred_motion=st["pred_motion"],
+                    tl_state=tl.bool(), final_valid=st["valid"].bool(), final_navi_valid=~st["navi_invalid"],
+                    joint_pose=st["pred_pose"].view(n_sc, R, A, self.T, 3))
+
+    def rollout(self, batch: Dict[str, Tensor], n_steps: Optional[int] = None) -> Dict[str, Tensor]:
+        self.prepare(batch)
+        return self.run(n_steps)

@@ -1,0 +1,87 @@
+"""ctypes binding of libtbknarpe.so (C ABI declared in include/tb_knarpe.h) + in-tree nvcc build.
+
+The product path fails loudly when the library is missing: there is no CPU / PyTorch fallback.
+"""
+import ctypes
+import glob
+import os
+import subprocess
+from ctypes import c_float, c_int, c_void_p
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+SO_PATH = os.path.join(_PKG, "libtbknarpe.so")
+_SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu",
+            "rollout_step.cu"]
+_lib = None
+
+EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_linear", "tb_layernorm",
+           "tb_pointnet_pool", "tb_pose_emb", "tb_ag_featurize", "tb_tl_featurize", "tb_dyn_step", "tb_tl_step",
+           "tb_step_advance", "tb_gather_rows", "tb_action_mean"]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a -> trafficbotsv1.5_b200/libtbknarpe.so (cross-compiles on CPU)."""
+    src = [os.path.join(_PKG, "csrc", s) for s in _SOURCES]
+    deps = src + glob.glob(os.path.join(_PKG, "csrc", "*.cuh")) + [os.path.join(_ROOT, "include", "tb_knarpe.h")]
+    if not force and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+           "-Xcompiler", "-fPIC", "-I", os.path.join(_ROOT, "include"), "-lcuda", "-o", SO_PATH] + src
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return SO_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(f"{SO_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                           "There is no CPU fallback for the CUDA hot path.")
+    lib = ctypes.CDLL(SO_PATH)
+    lib.tb_strerror.restype = ctypes.c_char_p
+    lib.tb_strerror.argtypes = [c_int]
+    P, I, F = c_void_p, c_int, c_float
+    sig = {
+        "tb_knn_select": [P, P, P, P, I, I, I, I, I, F, P, P, P, I, I, P],
+        "tb_knarpe_attn": [P, I, P, I, P, I, I, I, I, P, I, I, I, I, P, P, P, P, P, I, I, I, I, P, P, I, P, P],
+        "tb_linear": [P, I, P, P, P, I, I, I, I, I, P, P, I, P, I, P],
+        "tb_layernorm": [P, I, P, P, P, I, I, I, P],
+        "tb_pointnet_pool": [P, I, P, I, I, I, I, P, I, P],
+        "tb_pose_emb": [P, P, I, P, I, I, P, I, P],
+        "tb_ag_featurize": [P, P, P, P, P, P, I, I, I, P, P, P, P, I, P, I, P],
+        "tb_tl_featurize": [P, P, P, I, I, I, P, I, P, P],
+        "tb_dyn_step": [P, P, P, P, F, P, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P, I, I, F, F, F, P, I, I, I,
+                        I, P, P, P, P, P, P, P],
+        "tb_tl_step": [P, P, P, I, P, I, I, I, I, P, P, P],
+        "tb_step_advance": [P, P],
+        "tb_gather_rows": [P, I, I, P, I, I, I, I, P, I, P],
+        "tb_action_mean": [P, P, P, I, P, P],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = args
+    lib.tb_version.restype = c_int
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise RuntimeError(f"{what} failed: {load().tb_strerror(code).decode()} ({code})")
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream

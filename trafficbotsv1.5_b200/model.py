@@ -1,0 +1,299 @@
+"""Host-side composition of the CUDA kernels into the reference's modules (eval mode, HPTR config).
+
+Mirrors, function by function, the reference call chain (paths relative to the reference's src/):
+  MapEncoder.forward             models/map_encoder.py:50-113
+  TrafficLightEncoder.pre_compute / forward     models/traffic_light.py:76-154, 184-246
+  AgentEncoder._forward_hptr     models/agent_encoder.py:114-178, 321-387
+  TransformerRPE / AttentionRPE  models/modules/transformer_rpe.py:175-245, attention_rpe.py:58-198
+  NaviEncoder / AddNaviLatent / ActionHead / TrafficLightStatePredictor
+Weights arrive under the reference's state_dict names (params.param_shapes) and are re-packed once into the
+fused projection matrices described in DESIGN.md §3 (exact re-association, done in float64).
+All tensors here are 2-D [rows, channels] views of flat HBM buffers; every compute step is one ops.* launch.
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+H = 4
+
+
+def fuse_attention(P: Dict[str, Tensor], prefix: str, d: int, n_head: int = H) -> Dict[str, Tensor]:
+    """attention_rpe.py:35-41,92-97,147-161,180-186 -> packed projections.
+    in-proj rows: [ q*s (d) | u*s (H*d_rpe) | k (d) | v (d) ],  s = log2(e)/sqrt(d_head)
+        u_h = W_rk,h^T q_h  =>  W_u[h] = W_rk,h^T W_q,h ,  b_u[h] = W_rk,h^T b_q,h
+    out-proj columns: [ W_o (d) | W_o[:,h] W_rv,h (H*d_rpe) ],  bias b_o + W_o b_rv
+    (the logit constant q_h.b_rk,h is softmax-invariant and dropped)."""
+    f64 = lambda k: P[f"{prefix}.{k}"].detach().double().cpu()  # noqa: E731
+    w_in, b_in = f64("in_proj_weight"), f64("in_proj_bias")
+    w_o, b_o = f64("out_proj_weight"), f64("out_proj_bias")
+    w_r, b_r = f64("linear_rpe.weight"), f64("linear_rpe.bias")
+    dh = d // n_head
+    d_rpe = w_r.shape[1]
+    s = math.log2(math.e) / math.sqrt(dh)
+    w_q, b_q = w_in[:d] * s, b_in[:d] * s
+    w_rk, w_rv, b_rv = w_r[:d], w_r[d:], b_r[d:]
+    w_u, b_u, w_oz = [], [], []
+    for h in range(n_head):
+        sl = slice(h * dh, (h + 1) * dh)
+        w_u.append(w_rk[sl].T @ w_q[sl])          # [d_rpe, d]
+        b_u.append(w_rk[sl].T @ b_q[sl])          # [d_rpe]
+        w_oz.append(w_o[:, sl] @ w_rv[sl])        # [d, d_rpe]
+    w_qu = torch.cat([w_q] + w_u, 0)
+    b_qu = torch.cat([b_q] + b_u, 0)
+    out = dict(
+        w_in_self=torch.cat([w_qu, w_in[d:]], 0), b_in_self=torch.cat([b_qu, b_in[d:]], 0),
+        w_in_q=w_qu, b_in_q=b_qu, w_kv=w_in[d:], b_kv=b_in[d:],
+        w_out=torch.cat([w_o] + w_oz, 1), b_out=b_o + w_o @ b_rv,
+    )
+    return {k: v.float().contiguous() for k, v in out.items()}
+
+
+class HotPathModel:
+    """Device-resident weights + the kernel sequences of the hot-path modules."""
+
+    def __init__(self, P: Dict[str, Tensor], cfg: dict, sizes: dict, device="cuda", precision: int = 0):
+        self.cfg, self.sz, self.dev, self.precision = cfg, sizes, torch.device(device), precision
+        self.d = cfg["hidden_dim"]
+        self.W = cfg["temp_window_size"]
+        self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in P.items()}
+        self.fa: Dict[str, Dict[str, Tensor]] = {}
+        for k in P:
+            if k.endswith(".in_proj_weight"):
+                p = k[: -len(".in_proj_weight")]
+                self.fa[p] = {n: t.to(self.dev) for n, t in fuse_attention(P, p, self.d).items()}
+        self.freq_rpe = ops.pe_freq_xy(self.d, cfg["pose_rpe"]["theta_xy"], self.dev)          # d_rpe = hidden
+        self.freq_ag = ops.pe_freq_xy(self.d // 2, cfg["ag_encoder"]["pose_emb"]["theta_xy"], self.dev)
+        # action head: first layers of the 3 type branches stacked (action_head.py:25-36)
+        self.act_w0 = torch.cat([self.P[f"action_head.mlp_mean.{t}.fc_layers.0.weight"] for t in range(3)], 0)
+        self.act_b0 = torch.cat([self.P[f"action_head.mlp_mean.{t}.fc_layers.0.bias"] for t in range(3)], 0)
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def lin(self, x, wname, relu=False, **kw):
+        return ops.linear(x, self.P[f"{wname}.weight"], self.P[f"{wname}.bias"], relu=relu, precision=self.precision,
+                          **kw)
+
+    def ln(self, x, name):
+        return ops.layernorm(x, self.P[f"{name}.weight"], self.P[f"{name}.bias"])
+
+    def mlp(self, x, prefix, idxs, end_act, **last_kw):
+        for n, i in enumerate(idxs):
+            last = n == len(idxs) - 1
+            x = self.lin(x, f"{prefix}.fc_layers.{i}", relu=(not last) or end_act, **(last_kw if last else {}))
+        return x
+
+    def pointnet(self, x: Tensor, row_invalid: Tensor, G: int, Lg: int, prefix: str) -> Tensor:
+        """polyline_encoder.py:50-53 + pooling.py:18-19,38. x [G*L, d]."""
+        half = self.d // 2
+        for i in range(3):
+            xn = torch.empty_like(x)
+            self.lin(x, f"{prefix}.mlp_layers.{i}.fc_layers.0", relu=True, out=xn[:, :half])
+            ops.pointnet_pool(xn, row_invalid, G, Lg, 0)
+            x = xn
+        return ops.pointnet_pool(x, row_invalid, G, Lg, 1)
+
+    def kv_table(self, feat: Tensor, layer_prefix: str, norm: str, attn: str = "attn") -> Tensor:
+        """K/V rows of a target table for one layer: W_kv LN(x) + b  (project-once-then-gather)."""
+        f = self.fa[f"{layer_prefix}.{attn}"]
+        return ops.linear(self.ln(feat, f"{layer_prefix}.{norm}"), f["w_kv"], f["b_kv"], precision=self.precision)
+
+    def _attend(self, fa, proj, B, S, kv0, T0, div0, K0, knn, kv1=None, T1=0, div1=1, K1=0):
+        d = self.d
+        return ops.knarpe_attn(proj[:, :d], proj[:, d:d + H * d], kv0, T0, div0, K0, knn["idx"], knn["inv"],
+                               knn["rel"], self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1)
+
+    def tf_layer(self, p: str, mode: str, src: Tensor, src_inv: Tensor, B: int, S: int, knn_self: dict,
+                 cross: Optional[dict] = None, out: Optional[Tensor] = None) -> Tensor:
+        """TransformerRPE.forward (transformer_rpe.py:175-245), eval mode."""
+        d, pr = self.d, self.precision
+        if mode == "dec_cross_attn":
+            f = self.fa[f"{p}.attn_src"]
+            proj = ops.linear(self.ln(src, f"{p}.norm_src"), f["w_in_self"], f["b_in_self"], precision=pr)
+            o, nv = self._attend(f, proj, B, S, proj[:, d + H * d:], S, 1, knn_self["idx"].shape[-1], knn_self)
+            src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
+            f = self.fa[f"{p}.attn"]
+            proj = ops.linear(self.ln(src, f"{p}.norm1"), f["w_in_q"], f["b_in_q"], precision=pr)
+            o, nv = self._attend(f, proj, B, S, cross["kv0"], cross["T0"], cross["div0"], cross["K0"], cross,
+                                 cross.get("kv1"), cross.get("T1", 0), cross.get("div1", 1), cross.get("K1", 0))
+            src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
+        else:  # enc_self_attn: q and k/v both from norm1(src) (:218-221)
+            f = self.fa[f"{p}.attn"]
+            proj = ops.linear(self.ln(src, f"{p}.norm1"), f["w_in_self"], f["b_in_self"], precision=pr)
+            o, nv = self._attend(f, proj, B, S, proj[:, d + H * d:], S, 1, knn_self["idx"].shape[-1], knn_self)
+            src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
+        h = self.lin(self.ln(src, f"{p}.norm2"), f"{p}.linear1", relu=True)
+        return self.lin(h, f"{p}.linear2", res=src, mask_post=src_inv, out=out)
+
+    # ------------------------------------------------------------------------------------------ map (once / scene)
+    def map_encoder(self, mp_valid: Tensor, mp_attr: Tensor, mp_pose: Tensor) -> Dict[str, Tensor]:
+        """MapEncoder.forward, map_encoder.py:50-113. The geometric front-end (polyline-local frame + 7 features,
+        :65-77, pose_emb.py:59-89) runs once per scene and is plain torch; MLP / PointNet / KNN / 8 KNARPE layers
+        are the CUDA kernels."""
+        d, sz = self.d, self.sz
+        n_sc, n_mp, Ln = mp_valid.shape
+        tok_pose = mp_pose[:, :, 0].contiguous()
+        tok_inv = ~mp_valid[:, :, 0]
+        c, s = torch.cos(tok_pose[..., 2]), torch.sin(tok_pose[..., 2])
+        rot = torch.stack([torch.stack([c, -s], -1), torch.stack([s, c], -1)], -2)
+        xy = torch.matmul(mp_pose[..., :2] - tok_pose[:, :, None, :2], rot)
+        yaw = mp_pose[..., 2] - tok_pose[..., 2:3]
+        pe7 = _encode_polyline(xy, torch.stack([yaw.cos(), yaw.sin()], -1))
+        attr = torch.cat([mp_attr[:, :, None, :].expand(-1, -1, Ln, -1),
+                          torch.eye(Ln, device=self.dev)[None, None].expand(n_sc, n_mp, -1, -1)], -1)
+        M = n_sc * n_mp * Ln
+        x = torch.empty(M, d, device=self.dev)
+        x[:, d - 7:] = pe7.reshape(M, 7)
+        self.mlp(attr.reshape(M, -1).contiguous(), "mp_encoder.input_encoder.mlp", (0, 2, 4), False, out=x[:, : d - 7])
+        tok = self.pointnet(x, (~mp_valid).reshape(-1).contiguous(), n_sc * n_mp, Ln, "mp_encoder.pl_encoder")
+        idx, inv, rel = ops.knn_select(tok_pose, tok_inv, tok_pose, tok_inv, sz["k_mp2mp"], sz["dl_mp"])
+        knn = dict(idx=idx, inv=inv, rel=rel)
+        flat_inv = tok_inv.reshape(-1).contiguous()
+        for i in range(self.cfg["mp_encoder"]["n_layer_tf"]):
+            tok = self.tf_layer(f"mp_encoder.tf_mp2mp.layers.{i}", "enc_self_attn", tok, flat_inv, n_sc, n_mp, knn)
+        return dict(mp_token_invalid=tok_inv.contiguous(), mp_token_feature=tok.view(n_sc, n_mp, d),
+                    mp_token_pose=tok_pose, knn_mp2mp=knn)
+
+    # ------------------------------------------------------------------------------------------ traffic lights
+    def tl_pre_compute(self, tl_valid: Tensor, tl_attr: Tensor, tl_pose: Tensor, mp: Dict[str, Tensor]) -> dict:
+        """TrafficLightEncoder.pre_compute, traffic_light.py:76-154 + per-layer map K/V tables of tf_tl2tlmp."""
+        sz, d = self.sz, self.d
+        n_sc, n_tl = tl_valid.shape
+        n_mp = mp["mp_token_pose"].shape[1]
+        inv = (~tl_valid).contiguous()
+        tl_pose = tl_pose.contiguous()
+        feat2d = mp["mp_token_feature"].reshape(n_sc * n_mp, d)
+        attr = ops.gather_rows(mp["mp_token_feature"].contiguous(), tl_attr.to(torch.int32).reshape(-1).contiguous(),
+                               n_tl)                                                              # :115
+        i1, m1, r1 = ops.knn_select(tl_pose, inv, tl_pose, inv, sz["k_tl2tl"], sz["dl_tl"])       # :119,129-135
+        i2, m2, r2 = ops.knn_select(tl_pose, inv, mp["mp_token_pose"], mp["mp_token_invalid"], sz["k_tl2mp"],
+                                    sz["dl_tl"])                                                  # :120-145
+        kv = [self.kv_table(feat2d, f"tl_encoder.tf_tl2tlmp.layers.{i}", "norm_tgt")
+              for i in range(self.cfg["tl_encoder"]["n_layer_tf"])]
+        W = self.W
+        return dict(tl_token_invalid=inv, tl_token_pose=tl_pose, tl_token_attr=attr,
+                    tl_attr_rows=attr.view(n_sc * n_tl, 1, d).expand(-1, W, -1).reshape(-1, d).contiguous(),
+                    knn_self=dict(idx=i1, inv=m1, rel=r1),
+                    cross=[dict(kv0=kv[i], T0=n_mp, div0=1, K0=sz["k_tl2mp"], idx=i2, inv=m2, rel=r2)
+                           for i in range(len(kv))], n_sc=n_sc, n_tl=n_tl)
+
+    def tl_forward(self, hist_tl: Tensor, d_step: Tensor, tl: dict):
+        """TrafficLightEncoder.forward (traffic_light.py:210-240) + TrafficLightStatePredictor (:270-286, pre-clamp).
+        hist_tl [Bt, n_tl, W, 5] u8 ring."""
+        from . import lib as L
+        Bt, n_tl, W, d = tl["n_sc"], tl["n_tl"], self.W, self.d
+        M = Bt * n_tl * W
+        attr = torch.empty(M, 5 + W, device=self.dev)
+        row_inv = torch.empty(M, dtype=torch.bool, device=self.dev)
+        L.check(L.load().tb_tl_featurize(L.ptr(hist_tl), L.ptr(ops._u8(tl["tl_token_invalid"])), L.ptr(d_step), Bt,
+                                         n_tl, W, L.ptr(attr), 5 + W, L.ptr(ops._u8(row_inv)), L.stream()),
+                "tb_tl_featurize")
+        ops._count()
+        x = self.mlp(attr, "tl_encoder.input_encoder.mlp", (0, 2, 4), False, res=tl["tl_attr_rows"])  # :176-180
+        tok = self.pointnet(x, row_inv, Bt * n_tl, W, "tl_encoder.temp_encoder")                      # :228
+        flat_inv = tl["tl_token_invalid"].reshape(-1)
+        for i in range(self.cfg["tl_encoder"]["n_layer_tf"]):
+            tok = self.tf_layer(f"tl_encoder.tf_tl2tlmp.layers.{i}", "dec_cross_attn", tok, flat_inv, Bt, n_tl,
+                                tl["knn_self"], tl["cross"][i])                                       # :231-240
+        logits = self.mlp(tok, "tl_state_predictor.mlp", (0, 2, 4), False)                            # :284
+        return tok, logits
+
+    # ------------------------------------------------------------------------------------------ agents (per step)
+    def ag_static(self, mp: Dict[str, Tensor]) -> list:
+        """Per-scene map K/V tables of the 4 tf_ag2agmptl layers (static: shared by all rollouts and steps)."""
+        n_sc, n_mp, d = mp["mp_token_feature"].shape
+        feat2d = mp["mp_token_feature"].reshape(n_sc * n_mp, d)
+        return [self.kv_table(feat2d, f"ag_encoder.tf_ag2agmptl.layers.{i}", "norm_tgt")
+                for i in range(self.cfg["ag_encoder"]["n_layer_tf"])]
+
+    def ag_forward(self, st: dict, mp: Dict[str, Tensor], kv_mp: list, tl: dict, tl_feat: Tensor, R: int,
+                   out: Optional[Tensor] = None, aux: Optional[dict] = None) -> Tensor:
+        """AgentEncoder._forward_hptr (agent_encoder.py:114-178). `st` holds the rollout state rings
+        (engine.RolloutState); batch b uses map / traffic-light tables of scene b // R."""
+        from . import lib as L
+        sz, d, W = self.sz, self.d, self.W
+        B, A = st["B"], st["A"]
+        n_mp, n_tl = mp["mp_token_pose"].shape[1], tl["n_tl"]
+        tl_div = B // (tl_feat.shape[0] // n_tl)  # rollout-scenes per traffic-light batch row (R if TL runs per scene)
+        M, MW = B * A, B * A * W
+        tok_pose = torch.empty(B, A, 3, device=self.dev)
+        tok_inv = torch.empty(B, A, dtype=torch.bool, device=self.dev)
+        row_inv = torch.empty(MW, dtype=torch.bool, device=self.dev)
+        attr = torch.empty(MW, 9 + W, device=self.dev)
+        x = torch.empty(MW, d, device=self.dev)
+        L.check(L.load().tb_ag_featurize(L.ptr(st["hist_valid"]), L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]),
+                                         L.ptr(st["ag_attr"]), L.ptr(st["d_step"]), L.ptr(self.freq_ag), B, A, W,
+                                         L.ptr(tok_pose), L.ptr(ops._u8(tok_inv)), L.ptr(ops._u8(row_inv)),
+                                         L.ptr(attr), 9 + W, L.ptr(x[:, d // 2:]), d, L.stream()), "tb_ag_featurize")
+        ops._count()
+        self.mlp(attr, "ag_encoder.input_encoder.mlp", (0, 2, 4), False, out=x[:, : d // 2])          # :159
+        tok = self.pointnet(x, row_inv, M, W, "ag_encoder.temp_encoder")                              # :162
+        # re-localisation + KNN re-selection, every step (:321-387)
+        i_aa, m_aa, r_aa = ops.knn_select(tok_pose, tok_inv, tok_pose, tok_inv, sz["k_ag2ag"], sz["dl_ag"])
+        Kc = sz["k_ag2mp"] + sz["k_ag2tl"]
+        cidx = torch.empty(B, A, Kc, dtype=torch.int32, device=self.dev)
+        cinv = torch.empty(B, A, Kc, dtype=torch.bool, device=self.dev)
+        crel = torch.empty(B, A, Kc, 3, device=self.dev)
+        ops.knn_select(tok_pose, tok_inv, mp["mp_token_pose"], mp["mp_token_invalid"], sz["k_ag2mp"], sz["dl_ag"],
+                       tgt_div=R, out=(cidx, cinv, crel), koff=0)
+        ops.knn_select(tok_pose, tok_inv, tl["tl_token_pose"], tl["tl_token_invalid"], sz["k_ag2tl"], sz["dl_ag"],
+                       tgt_div=tl_div, out=(cidx, cinv, crel), koff=sz["k_ag2mp"])
+        knn_self = dict(idx=i_aa, inv=m_aa, rel=r_aa)
+        flat_inv = tok_inv.reshape(-1)
+        nl = self.cfg["ag_encoder"]["n_layer_tf"]
+        if aux is not None:
+            aux.update(tok_pose=tok_pose, tok_inv=tok_inv, tok0=tok, knn_self=knn_self, cidx=cidx, cinv=cinv, crel=crel)
+        for i in range(nl):
+            p = f"ag_encoder.tf_ag2agmptl.layers.{i}"
+            kv_tl = self.kv_table(tl_feat, p, "norm_tgt")
+            cross = dict(kv0=kv_mp[i], T0=n_mp, div0=R, K0=sz["k_ag2mp"], kv1=kv_tl, T1=n_tl, div1=tl_div,
+                         K1=sz["k_ag2tl"], idx=cidx, inv=cinv, rel=crel)
+            tok = self.tf_layer(p, "dec_cross_attn", tok, flat_inv, B, A, knn_self, cross,
+                                out=out if i == nl - 1 else None)
+        return tok
+
+    # ------------------------------------------------------------------------------------------ heads (per step)
+    def navi_static(self, mp: Dict[str, Tensor], dest_idx: Tensor, R: int) -> dict:
+        """Static halves of NaviEncoder.forward (navigation.py:65-71): mlp_mp(map feature of the destination) and the
+        destination's global pose. dest_idx int32 [B, A]."""
+        B, A = dest_idx.shape
+        flat = dest_idx.reshape(-1).contiguous()
+        f = ops.gather_rows(mp["mp_token_feature"].contiguous(), flat, A, R)
+        pose = ops.gather_rows(mp["mp_token_pose"].contiguous(), flat, A, R)
+        return dict(feat=self.lin(f, "navi_encoder.mlp_mp.fc_layers.0"), pose=pose)
+
+    def heads(self, x_cat: Tensor, st: dict, navi: dict) -> Tensor:
+        """navi_encoder (per-step half) -> add_navi -> add_latent -> action-head branches
+        (traffic_bots.py:191-217). x_cat [M, 2d] with the agent feature already in the left half.
+        Returns act_branch [M, 6] (veh, ped, cyc) x (acc, yaw-rate) pre-tanh, unmasked."""
+        d = self.d
+        M = x_cat.shape[0]
+        pe = ops.pose_emb(navi["pose"], self.freq_rpe, d, frame=st["pose"], frame_div=1)             # navigation.py:73-79
+        nf = self.lin(pe, "navi_encoder.mlp_pe.fc_layers.0", res=navi["feat"])
+        x_cat2 = torch.empty(M, 2 * d, device=self.dev)
+        for prefix, z, zinv, cat_in, cat_out in (("add_navi", nf, st["navi_invalid"], x_cat, x_cat2[:, :d]),
+                                                 ("add_latent", st["latent"], st["latent_invalid"], x_cat2, None)):
+            zinv = zinv.reshape(-1)                                                                  # add_navi_latent.py:46-64
+            self.mlp(z, f"{prefix}.mlp_in", (0, 3, 6), True, mask_post=zinv, out=cat_in[:, d:])
+            h = self.mlp(cat_in, f"{prefix}.mlp", (0, 3, 6), True, mask_pre=zinv, res=cat_in[:, :d], out=cat_out)
+        h0 = ops.linear(h, self.act_w0, self.act_b0, relu=True, precision=self.precision)            # action_head.py:78-82
+        h1 = torch.empty_like(h0)
+        act = torch.empty(M, 6, device=self.dev)
+        for t in range(3):
+            self.lin(h0[:, t * d:(t + 1) * d], f"action_head.mlp_mean.{t}.fc_layers.2", relu=True,
+                     out=h1[:, t * d:(t + 1) * d])
+            self.lin(h1[:, t * d:(t + 1) * d], f"action_head.mlp_mean.{t}.fc_layers.4", out=act[:, 2 * t:2 * t + 2])
+        return act
+
+
+def _encode_polyline(pos: Tensor, dirv: Tensor) -> Tensor:
+    """PoseEmb mode mpa_pl, utils/pose_emb.py:59-89 (once per scene)."""
+    eps = torch.finfo(pos.dtype).eps
+    proj = (-pos * dirv).sum(-1) / ((dirv * dirv).sum(-1) + eps)
+    closest = pos + proj.clamp(0, 1).unsqueeze(-1) * dirv
+    r = torch.norm(closest, dim=-1, keepdim=True)
+    dn = torch.norm(dirv, dim=-1, keepdim=True)
+    return torch.cat([r, closest / (r + eps), dirv / (dn + eps), dn,
+                      torch.norm(pos + dirv - closest, dim=-1, keepdim=True)], -1)

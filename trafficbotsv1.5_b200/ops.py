@@ -1,0 +1,166 @@
+"""Tensor-level wrappers over the C ABI (include/tb_knarpe.h). torch is used for device memory and streams
+only; every op below is one launch of a hand-written sm_100a kernel on torch's current stream."""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import lib as L
+
+LAUNCHES = 0  # number of kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _u8(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype == torch.bool:
+        return t.view(torch.uint8)
+    assert t.dtype == torch.uint8, t.dtype
+    return t
+
+
+def _f32c(t: Tensor) -> Tensor:
+    assert t.dtype == torch.float32 and t.is_cuda, (t.dtype, t.device)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def pe_freq_xy(pe_dim: int, theta: float = 1e3, device="cuda") -> Tensor:
+    """PositionalEmbedding(dim=pe_dim/4, theta).freqs[::2] with the reference's own fp32 formula
+    (utils/positional_emb.py:11): pe_dim/8 frequencies."""
+    dim = pe_dim // 4
+    f = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+    return f.to(device)
+
+
+def knn_select(src_pose: Tensor, src_invalid: Tensor, tgt_pose: Tensor, tgt_invalid: Tensor, k: int,
+               dist_limit: float, tgt_div: int = 1, out: Optional[Tuple[Tensor, Tensor, Tensor]] = None,
+               koff: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
+    """Fused get_rel_pose + get_tgt_knn_idx (utils/rpe.py:9-90). Returns idx int32 [B,S,K], invalid bool [B,S,K],
+    rel [B,S,K,3]; with `out`/`koff` writes into columns koff..koff+K of preallocated [B,S,ldk(,3)] buffers."""
+    B, S, _ = src_pose.shape
+    T = tgt_pose.shape[1]
+    assert tgt_pose.shape[0] * tgt_div == B, (tgt_pose.shape, tgt_div, B)
+    src_pose, tgt_pose = _f32c(src_pose), _f32c(tgt_pose)
+    si, ti = _u8(src_invalid).contiguous(), _u8(tgt_invalid).contiguous()
+    if out is None:
+        idx = torch.empty(B, S, k, dtype=torch.int32, device=src_pose.device)
+        inv = torch.empty(B, S, k, dtype=torch.bool, device=src_pose.device)
+        rel = torch.empty(B, S, k, 3, dtype=torch.float32, device=src_pose.device)
+    else:
+        idx, inv, rel = out
+    ldk = idx.shape[2]
+    L.check(L.load().tb_knn_select(L.ptr(src_pose), L.ptr(si), L.ptr(tgt_pose), L.ptr(ti), B, S, T, tgt_div, k,
+                                   float(dist_limit), L.ptr(idx), L.ptr(_u8(inv)), L.ptr(rel), ldk, koff, L.stream()),
+            "tb_knn_select")
+    _count()
+    return idx, inv, rel
+
+
+def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, idx: Tensor, invalid: Tensor,
+                rel: Optional[Tensor], freq_xy: Tensor, B: int, S: int, D: int, H: int = 4,
+                kv1: Optional[Tensor] = None, T1: int = 0, div1: int = 1, K1: int = 0,
+                emb: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """KNARPE core. q/u/kv*: 2-D (possibly column-sliced, row-strided) views; returns (out [B*S, D+H*D] = [ov|z],
+    none_valid bool [B*S])."""
+    M = B * S
+    for t in (q, u, kv0) + ((kv1,) if kv1 is not None else ()):
+        assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
+    if out is None:
+        out = torch.empty(M, D + H * D, dtype=torch.float32, device=q.device)
+    none_valid = torch.empty(M, dtype=torch.bool, device=q.device)
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.shape[-1] == K0 + K1
+    inv = _u8(invalid)
+    assert inv.is_contiguous()
+    if rel is not None:
+        assert rel.is_contiguous() and rel.dtype == torch.float32
+    if emb is not None:
+        assert emb.is_contiguous() and emb.dtype == torch.float32
+    z = out[:, D:]
+    L.check(L.load().tb_knarpe_attn(
+        L.ptr(q), q.stride(0), L.ptr(u), u.stride(0), L.ptr(kv0), kv0.stride(0), T0, div0, K0,
+        L.ptr(kv1), kv1.stride(0) if kv1 is not None else 0, T1, div1, K1, L.ptr(idx), L.ptr(inv), L.ptr(rel),
+        L.ptr(emb), L.ptr(freq_xy), B, S, D, H, L.ptr(out), L.ptr(z), out.stride(0), L.ptr(_u8(none_valid)),
+        L.stream()), "tb_knarpe_attn")
+    _count()
+    return out, none_valid
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False, mask_pre: Optional[Tensor] = None,
+           res: Optional[Tensor] = None, mask_post: Optional[Tensor] = None, out: Optional[Tensor] = None,
+           precision: int = 0) -> Tensor:
+    """Y = epilogue(X W^T + b) on 2-D row-strided views (see tb_linear)."""
+    assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.dtype == torch.float32
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (w.shape, x.shape)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    assert out.stride(1) == 1 and out.shape[0] == M and out.shape[1] == N
+    if res is not None:
+        assert res.stride(1) == 1 and res.shape == (M, N)
+    L.check(L.load().tb_linear(L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), L.ptr(out), out.stride(0), M, N, K,
+                               int(relu), L.ptr(_u8(mask_pre)), L.ptr(res), res.stride(0) if res is not None else 0,
+                               L.ptr(_u8(mask_post)), precision, L.stream()), "tb_linear")
+    _count()
+    return out
+
+
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    assert x.dim() == 2 and x.stride(1) == 1
+    M, D = x.shape
+    if out is None:
+        out = torch.empty(M, D, dtype=torch.float32, device=x.device)
+    L.check(L.load().tb_layernorm(L.ptr(x), x.stride(0), L.ptr(gamma), L.ptr(beta), L.ptr(out), out.stride(0), M, D,
+                                  L.stream()), "tb_layernorm")
+    _count()
+    return out
+
+
+def pointnet_pool(x: Tensor, invalid: Tensor, G: int, Lg: int, mode: int) -> Optional[Tensor]:
+    """x [G*L, 2C] modified in place (mode 0) / pooled to [G, 2C] (mode 1)."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == G * Lg
+    C2 = x.shape[1]
+    out = torch.empty(G, C2, dtype=torch.float32, device=x.device) if mode == 1 else None
+    inv = _u8(invalid)
+    assert inv.is_contiguous() and inv.numel() == G * Lg
+    L.check(L.load().tb_pointnet_pool(L.ptr(x), x.stride(0), L.ptr(inv), G, Lg, C2, mode, L.ptr(out),
+                                      out.stride(0) if out is not None else 0, L.stream()), "tb_pointnet_pool")
+    _count()
+    return out
+
+
+def pose_emb(pose: Tensor, freq_xy: Tensor, pe_dim: int, frame: Optional[Tensor] = None, frame_div: int = 1,
+             out: Optional[Tensor] = None) -> Tensor:
+    pose = _f32c(pose).view(-1, 3)
+    M = pose.shape[0]
+    if out is None:
+        out = torch.empty(M, pe_dim, dtype=torch.float32, device=pose.device)
+    if frame is not None:
+        frame = _f32c(frame).view(-1, 3)
+    L.check(L.load().tb_pose_emb(L.ptr(pose), L.ptr(frame), frame_div, L.ptr(freq_xy), M, pe_dim, L.ptr(out),
+                                 out.stride(0), L.stream()), "tb_pose_emb")
+    _count()
+    return out
+
+
+def gather_rows(table: Tensor, idx: Tensor, rows_per_batch: int, div: int = 1, out: Optional[Tensor] = None) -> Tensor:
+    """table [Bt, T, C] (contiguous), idx int32 [M] -> out [M, C]; batch of row m is (m // rows_per_batch) // div."""
+    assert table.dim() == 3 and table.is_contiguous() and idx.dtype == torch.int32 and idx.is_contiguous()
+    Bt, T, C = table.shape
+    M = idx.numel()
+    if out is None:
+        out = torch.empty(M, C, dtype=torch.float32, device=table.device)
+    L.check(L.load().tb_gather_rows(L.ptr(table), C, T, L.ptr(idx), M, rows_per_batch, div, C, L.ptr(out),
+                                    out.stride(0), L.stream()), "tb_gather_rows")
+    _count()
+    return out
+
+
+def host_f3(vals):
+    return (ctypes.c_float * 3)(*[float(v) for v in vals])
