@@ -36,8 +36,7 @@ def teacher_forcing_mask(gt_valid: Tensor, step_spawn: int, step_warm: int) -> T
 
 class RolloutEngine:
     def __init__(self, P: Dict[str, Tensor], cfg: Optional[dict] = None, device="cuda", precision: int = 0,
-                 n_rollout: int = 32, step_end: Optional[int] = None, tl_per_scene: bool = True,
-                 use_graph: bool = True):
+                 n_rollout: int = 32, step_end: Optional[int] = None, use_graph: bool = True):
         L.load()  # fail loudly if the CUDA library is missing
         self.cfg = cfg or C.default_model_cfg()
         self.sz = C.derived_sizes(self.cfg)
@@ -45,7 +44,7 @@ class RolloutEngine:
         self.model = HotPathModel(P, self.cfg, self.sz, device, precision)
         self.R = n_rollout
         self.T = step_end or C.ROLLOUT_CFG["time_step_end"]
-        self.tl_per_scene = tl_per_scene
+        self.tl_per_scene = True  # the TL branch is a function of (scene, TL history) only: evaluated once per scene
         self.use_graph = use_graph
         self.dyn = C.DYNAMICS_CFG
         self._graph = None
