@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the closed-loop WOSAC rollout hot path (BASELINE.json metric: scenario-rollout-steps/s).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (N>1: launched by torchrun, one rank/GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores (oracle port)
+
+A bench "step" = ONE complete closed-loop rollout of the per-GPU workload (BASELINE config 3: 16 scenes x 32 rollouts,
+128 agents, 1024 polylines x 20 nodes, 40 traffic lights, 11-step history): 90 policy iterations of which the 80
+post-history ones count. value = scenes x 32 x 80 / time, summed over ranks (weak scaling: 16 scenes per GPU).
+  value : rollout loop only, scene tokens and inputs resident in HBM (what `WaymoMotion.rollout` times)
+  e2e   : RolloutEngine.rollout(host batch): H2D of the pinned inputs + map/TL scene encoding + 90 steps + D2H of the
+          80-step trajectories, every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import tbpkg  # noqa: E402,F401
+from trafficbotsv1_5_b200 import config, params, synth  # noqa: E402
+
+METRIC = "closed_loop_scenario_rollout_steps_per_sec"
+UNIT = "rollout-scene-steps/s"
+N_COUNTED, N_ITER = 80, 90
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU")
+    ap.add_argument("--rollouts", type=int, default=32)
+    ap.add_argument("--precision", type=int, default=0, help="0 fp32 FFMA projections, 1 bf16 tcgen05 projections")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------ CPU arm
+def cpu_rollout_rate(n_threads, n_sc=1, R=8, iters=6):
+    """The reference algorithm (oracle port, torch CPU fp32) on a bounded sample of the same workload shape:
+    n_sc scene x R rollouts x `iters` policy iterations (history warm-up included, scene encoding excluded, like
+    `value`). Rate is scaled to the metric's 80-of-90 accounting."""
+    from oracle import tb_oracle as O
+    torch.set_num_threads(n_threads)
+    cfg = config.default_model_cfg()
+    sz = config.derived_sizes(cfg)
+    P = params.init_params(cfg, 0)
+    batch = synth.make_scene_batch(n_sc=n_sc, seed=1000)
+    with torch.no_grad():
+        mp = O.map_encoder(P, cfg, sz, batch["sc/mp_valid"], batch["sc/mp_attr"], batch["sc/mp_pose"])
+        tl = O.tl_pre_compute(P, cfg, sz, batch["sc/tl_valid"], batch["sc/tl_attr"], batch["sc/tl_pose"], mp)
+        mp = {k: mp[k] for k in ("mp_token_invalid", "mp_token_feature", "mp_token_pose")}
+        O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, 1, mp=mp, tl=tl)  # warm-up
+        t0 = time.perf_counter()
+        O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, iters, mp=mp, tl=tl)
+        dt = time.perf_counter() - t0
+    per_iter = dt / iters
+    rate = n_sc * R * N_COUNTED / (N_ITER * per_iter)
+    sample = (f"{n_sc} scene x {R} rollouts x {iters} policy iterations (128 agents, 1024 polylines, 40 TL) in "
+              f"{dt:.1f} s; scaled to 80 counted of 90 iterations")
+    return rate, sample, per_iter
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals, sample, per_iter = [], "", 0.0
+    for i in range(args.warmup + args.steps):
+        rate, sample, per_iter = cpu_rollout_rate(cores, 1, 8, 6)
+        if i >= args.warmup:
+            vals.append(rate)
+    v = sum(vals) / len(vals)
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=per_iter * 1e3 * 6, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="closed-loop WOSAC rollout, 128 agents / 1024 polylines x 20 / 40 TL / 11-step "
+                                     "history; CPU sample per step: " + sample),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------ GPU arm
+def attention_roofline(eng, peaks):
+    """Dominant kernel = KNARPE attention core on the agent cross-attention (K = 64 map + 25 TL neighbours).
+    achieved = algorithmic bytes of one launch / CUDA-event time of that launch (same tensors as the step)."""
+    from trafficbotsv1_5_b200 import ops
+    m, st, static = eng.model, eng._st, eng._static
+    aux = {}
+    eng._reset(st)
+    for _ in range(12):  # advance past the warm-start so histories are full
+        eng._step(st, static, eng._navi, aux)
+    d, B, A = m.d, st["B"], st["A"]
+    M = B * A
+    p = "ag_encoder.tf_ag2agmptl.layers.0"
+    f = m.fa[f"{p}.attn"]
+    x = aux["ag_feat"]
+    proj = ops.linear(m.ln(x, f"{p}.norm1"), f["w_in_q"], f["b_in_q"])
+    kv_tl = m.kv_table(aux["tl_feat"], p, "norm_tgt")
+    sz = eng.sz
+    n_mp, n_tl = static["mp"]["mp_token_pose"].shape[1], static["tl"]["n_tl"]
+    out = torch.empty(M, 5 * d, device=x.device)
+
+    def launch():
+        ops.knarpe_attn(proj[:, :d], proj[:, d:], static["kv_mp"][0], n_mp, eng.R, sz["k_ag2mp"], aux["cidx"],
+                        aux["cinv"], aux["crel"], m.freq_rpe, B, A, d, 4, kv1=kv_tl, T1=n_tl, div1=eng.R,
+                        K1=sz["k_ag2tl"], out=out)
+    for _ in range(3):
+        launch()
+    n = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / n * 1e-3
+    K = sz["k_ag2mp"] + sz["k_ag2tl"]
+    n_valid = int((~aux["cinv"]).sum())
+    # algorithmic bytes: K,V rows of the unmasked neighbours as issued + q,u in + ov,z out + idx/mask/rel
+    bytes_alg = n_valid * 2 * d * 4 + M * (d + 4 * d) * 4 * 2 + M * K * (4 + 1 + 12)
+    peak = peaks.get("hbm_gbs", 6650.0)
+    ach = bytes_alg / t / 1e9
+    return dict(bound="hbm", kernel="knarpe_attn_kernel<128,false> (agent cross-attn, K=89)", achieved=ach, peak=peak,
+                unit="GB/s", frac=ach / peak, traffic=None, us_per_launch=t * 1e6, algorithmic_bytes=bytes_alg,
+                valid_pairs=n_valid, pairs=M * K, peak_source="MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback")
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from trafficbotsv1_5_b200 import ops
+    from trafficbotsv1_5_b200.engine import RolloutEngine
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback for the product path"
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, 0)
+    eng = RolloutEngine(P, cfg, dev, precision=args.precision, n_rollout=args.rollouts, step_end=N_ITER)
+    n_sc = args.scenes
+    batch = synth.make_scene_batch(n_sc=n_sc, seed=1000 + rank * n_sc, n_rollout=args.rollouts)
+    batch = {k: v.pin_memory() for k, v in batch.items()}
+    h2d = sum(v.numel() * v.element_size() for v in batch.values())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- value: rollout loop only, inputs + scene tokens resident
+    eng.prepare(batch)
+    gathered = None
+    if world > 1:
+        gathered = [torch.empty(n_sc * args.rollouts, batch["sc/ag_valid"].shape[1], N_COUNTED, 3, device=dev)
+                    for _ in range(world)]
+
+    def loop_step():
+        res = eng.run()
+        if world > 1:  # the only cross-GPU step: gather of the 80-step trajectories (waymo_motion.py:894-909)
+            dist.all_gather(gathered, res["pred_pose"][:, :, N_ITER - N_COUNTED:].contiguous())
+
+    for _ in range(args.warmup):
+        loop_step()
+    l0 = ops.LAUNCHES
+    with ClockSampler(local) as cs:
+        t_loop = timed(loop_step, args.steps)
+    launches = args.steps * N_ITER * eng.launches_per_step + (ops.LAUNCHES - l0)
+    clocks = cs.summary()
+    units = world * n_sc * args.rollouts * N_COUNTED
+    value = units * args.steps / t_loop
+
+    # ---- e2e: host batch in, host trajectories out, scene encoding included, every step
+    host_out = torch.empty(n_sc * args.rollouts, batch["sc/ag_valid"].shape[1], N_COUNTED, 3).pin_memory()
+    host_valid = torch.empty(n_sc * args.rollouts, batch["sc/ag_valid"].shape[1], N_COUNTED, dtype=torch.bool).pin_memory()
+
+    def e2e_step():
+        res = eng.rollout(batch)
+        host_out.copy_(res["pred_pose"][:, :, N_ITER - N_COUNTED:], non_blocking=True)
+        host_valid.copy_(res["pred_valid"][:, :, N_ITER - N_COUNTED:], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    t_e2e = timed(e2e_step, max(1, args.steps))
+    e2e = dict(value=units * max(1, args.steps) / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d,
+               d2h_bytes_per_step=host_out.numel() * 4 + host_valid.numel())
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        roof = attention_roofline(eng, peaks)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=t_loop / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32" if args.precision == 0 else "bf16-proj/f32", data="synthetic",
+                    config=dict(workload=f"config 3: closed-loop WOSAC rollout, {n_sc} scenes x {args.rollouts} rollouts "
+                                         f"per GPU, 128 agents, 1024 polylines x 20, 40 TL, 11-step history, 90 policy "
+                                         f"iterations (80 counted)", scenes_per_gpu=n_sc, rollouts=args.rollouts,
+                                policy_iterations=N_ITER, counted_steps=N_COUNTED,
+                                l2="per-iteration working set (>1 GB of activations) exceeds the 126 MB L2; no flush",
+                                launches_per_policy_iteration=eng.launches_per_step),
+                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, sample, _ = cpu_rollout_rate(cores, 1, 8, 12)
+        line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -258,3 +258,46 @@ def test_transformer_block_golden(golden_ops, mode):
     scale = float(g["out"].abs().max())
     close(src.view(B, S, d), g["out"], 1e-4, 1e-4 * scale, f"block {mode}")
     assert rel_l2(src.view(B, S, d), g["out"]) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 projections
+@pytest.mark.parametrize("M,N,K,flags", [(300, 128, 128, "b"), (1000, 896, 128, "b"), (4097, 512, 128, "br"),
+                                         (640, 128, 640, "bpr+"), (129, 64, 128, "brm"), (720, 64, 20, "br"),
+                                         (333, 128, 512, "b+q"), (77, 40, 16, "b"), (65536, 640, 128, "b"),
+                                         (50, 384, 128, "br")])
+def test_linear_tensor_core(M, N, K, flags):
+    """precision=1: tcgen05 kind::tf32 (10-bit mantissa operands, fp32 accumulate). Stated tolerance: 2e-3 of the
+    output scale (rms) per element — vs 1e-5 for the fp32 FFMA path."""
+    g = torch.Generator().manual_seed(M + N)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    mp, mq = torch.rand(M, generator=g) < 0.3, torch.rand(M, generator=g) < 0.3
+    y = torch.nn.functional.linear(x.double(), w.double(), b.double() if "b" in flags else None)
+    kw = {}
+    if "r" in flags:
+        y = y.relu(); kw["relu"] = True
+    if "p" in flags or "m" in flags:
+        y = y.masked_fill(mp[:, None], 0); kw["mask_pre"] = mp.to(DEV)
+    if "+" in flags:
+        y = y + res.double(); kw["res"] = res.to(DEV)
+    if "q" in flags:
+        y = y.masked_fill(mq[:, None], 0); kw["mask_post"] = mq.to(DEV)
+    out = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV) if "b" in flags else None, precision=1, **kw)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - y).abs()
+    scale = float(y.std())
+    print(f"tf32 linear {M}x{N}x{K} {flags}: max err {float(err.max()):.3e}, rms err {float(err.pow(2).mean().sqrt()):.3e}, "
+          f"out rms {scale:.3e}")
+    assert float(err.max()) < 4e-3 * max(scale, 1.0), "tf32 projection out of tolerance"
+    assert float(err.pow(2).mean().sqrt()) < 1e-3 * max(scale, 1.0)
+
+
+def test_linear_tensor_core_strided():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1000, 384, generator=g).to(DEV)
+    w = (torch.randn(128, 128, generator=g) / 11).to(DEV)
+    out = torch.zeros(1000, 384, device=DEV)
+    ops.linear(x[:, 128:256], w, None, out=out[:, 256:], precision=1)
+    ref = x[:, 128:256].double() @ w.double().T
+    assert float((out[:, 256:].double() - ref).abs().max()) < 4e-3
+    assert float(out[:, :256].abs().max()) == 0.0

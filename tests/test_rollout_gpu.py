@@ -128,3 +128,25 @@ def test_full_shape_properties():
     # all 32 rollouts share the warm-start; they must diverge afterwards only through the latent
     jp = r1["joint_pose"]
     assert float((jp[:, 0, :, 12] - jp[:, 1, :, 12]).abs().max()) > 0
+
+
+# Tensor-core mode (precision=1: tcgen05 kind::tf32 projections, everything else fp32). Stated closed-loop tolerance vs
+# the fp32 reference over the 24-step golden rollout: position 2e-2 m, yaw 5e-3 rad, speed 2e-2 m/s per step;
+# validity / traffic-light masks identical on this fixture.
+TC_TOL_XY, TC_TOL_YAW, TC_TOL_SPD = 2e-2, 5e-3, 2e-2
+
+
+def test_rollout_golden_tensor_core(golden_rollout):
+    g = golden_rollout
+    eng, batch, P, cfg = _engine(g["shape"], g["R"], g["T"], precision=1)
+    res = eng.rollout(batch)
+    torch.cuda.synchronize()
+    e_xy = maxerr(res["pred_pose"][..., :2], g["pred_pose"][..., :2])
+    e_yaw = maxerr(res["pred_pose"][..., 2], g["pred_pose"][..., 2])
+    e_spd = maxerr(res["pred_motion"], g["pred_motion"])
+    n_valid_diff = int((res["pred_valid"].cpu() != g["pred_valid"]).sum())
+    n_tl_diff = int((res["tl_state"].cpu() != g["tl_state"]).sum())
+    print(f"tf32 rollout vs reference golden: xy {e_xy:.3e} m, yaw {e_yaw:.3e} rad, motion {e_spd:.3e}, "
+          f"valid mismatches {n_valid_diff}, tl mismatches {n_tl_diff}")
+    assert n_valid_diff == 0 and n_tl_diff == 0
+    assert e_xy < TC_TOL_XY and e_yaw < TC_TOL_YAW and e_spd < TC_TOL_SPD

@@ -1,8 +1,283 @@
-// Tensor-core projection path (tb_linear precision 1). Placeholder until the tcgen05 kernel lands: reports
-// TB_ERR_UNSUPPORTED so callers fail loudly instead of silently falling back.
+// Tensor-core projection path (tb_linear precision 1): Y = epilogue(X W^T + bias) on the 5th-gen tensor cores.
+//   tcgen05.mma kind::tf32 (fp32 operands straight from HBM, no conversion pass), fp32 accumulators in TMEM,
+//   operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a 4-stage mbarrier pipeline,
+//   warp-specialised: warps 0-3 epilogue (tcgen05.ld -> bias/ReLU/mask/residual -> global), warp 4 TMA producer,
+//   warp 5 MMA issuer + TMEM allocator. Two TMEM accumulator buffers overlap the epilogue of tile n with the MMAs of
+//   tile n+1. One CTA per 128-row M tile walks all of its N tiles, so the A tile is re-read from L2 only.
+// Shapes the TMA/UMMA constraints do not cover (K or ldx not a multiple of 4 floats, N < 32, misaligned pointers)
+// are executed by the fp32 FFMA kernel instead (higher precision, same semantics).
+#include <cuda.h>
 #include "common.cuh"
 
-int tb_linear_tc(const float*, int, const float*, const float*, float*, int, int, int, int, int, const uint8_t*,
-                 const float*, int, const uint8_t*, cudaStream_t) {
-  return TB_ERR_UNSUPPORTED;
+int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
+                  cudaStream_t st);
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;  // BK floats = 128 bytes = one swizzle-128B row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 2 * BN;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+
+struct Epi {
+  const float* bias; int relu; const uint8_t* mask_pre; const float* res; int ldr; const uint8_t* mask_post;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (canonical 1),
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp bit layout).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::tf32 instruction descriptor: D fp32 (bit 4), A/B tf32 (2 at bits 7 / 10), K-major A and B, N>>3 at bit 17,
+// M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   float* __restrict__ Y, int ldy, int M, int N, int K, Epi ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int nt = blockIdx.y; nt < n_tiles; nt += gridDim.y) {
+        for (int k = 0; k < num_k; ++k, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+          tma_load_2d(&mapA, &full[s], sA + s * A_BYTES, k * BK, m0);
+          tma_load_2d(&mapB, &full[s], sB + s * B_BYTES, k * BK, nt * BN);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer (one elected lane) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int it = 0, lt = 0;
+      for (int nt = blockIdx.y; nt < n_tiles; nt += gridDim.y, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int k = 0; k < num_k; ++k, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t adesc = make_desc(smem_u32(sA + s * A_BYTES));
+          const uint64_t bdesc = make_desc(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk)  // UMMA_K = 8 tf32 = 32 bytes -> +2 in 16-byte units
+            umma_tf32(tmem_base + buf * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+          umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+        }
+        umma_commit(&tfull[buf]);  // accumulator of this tile complete
+      }
+    }
+  } else {
+    // ===== epilogue warps 0..3: TMEM lanes [32*warp, 32*warp+32) = rows m0 + 32*warp + lane =====
+    const int row = m0 + warp * 32 + lane;
+    const bool row_ok = row < M;
+    const bool zpre = row_ok && ep.mask_pre && ep.mask_pre[row];
+    const bool zpost = row_ok && ep.mask_post && ep.mask_post[row];
+    const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
+                        (!ep.res || (((ep.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.res) & 15) == 0)));
+    int lt = 0;
+    for (int nt = blockIdx.y; nt < n_tiles; nt += gridDim.y, ++lt) {
+      const int buf = lt & 1;
+      mbar_wait(&tfull[buf], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int n0 = nt * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row_ok) {
+          const int cbase = n0 + c0;
+          float* yp = Y + (size_t)row * ldy + cbase;
+          const float* rp = ep.res ? ep.res + (size_t)row * ep.ldr + cbase : nullptr;
+          if (vec_ok && cbase + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float t = __uint_as_float(r[j + q]);
+                if (ep.bias) t += __ldg(ep.bias + cbase + j + q);
+                if (ep.relu) t = fmaxf(t, 0.f);
+                if (zpre) t = 0.f;
+                v[q] = t;
+              }
+              if (rp) {
+                const float4 rr = *reinterpret_cast<const float4*>(rp + j);
+                v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+              }
+              if (zpost) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+              *reinterpret_cast<float4*>(yp + j) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (cbase + j < N) {
+                float t = __uint_as_float(r[j]);
+                if (ep.bias) t += __ldg(ep.bias + cbase + j);
+                if (ep.relu) t = fmaxf(t, 0.f);
+                if (zpre) t = 0.f;
+                if (rp) t += rp[j];
+                if (zpost) t = 0.f;
+                yp[j] = t;
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row stride ld (floats); box = 32 cols (128 B) x box_rows, 128-byte swizzle,
+// out-of-bounds elements read as zero (handles the M / N / K tails).
+bool make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+                 int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
+                 cudaStream_t st) {
+  const bool ok = (K % 4 == 0) && (ldx % 4 == 0) && N >= 32 && tb_aligned16(X) && tb_aligned16(W);
+  if (!ok) return tb_linear_f32(X, ldx, W, bias, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+  CUtensorMap mapA, mapB;
+  if (!make_map(&mapA, X, M, K, ldx, BM) || !make_map(&mapB, W, N, K, K, BN)) return TB_ERR_CUDA;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
+        cudaSuccess)
+      return TB_ERR_CUDA;
+    attr_set = true;
+  }
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  int gy = (2 * 148 + m_tiles - 1) / m_tiles;  // enough CTAs for two waves when M is small
+  gy = gy < 1 ? 1 : (gy > n_tiles ? n_tiles : gy);
+  Epi ep{bias, relu, mask_pre, res, ldr, mask_post};
+  linear_tf32_kernel<<<dim3(m_tiles, gy), NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
 }
