@@ -1,0 +1,61 @@
+"""Summarise ncu outputs brought back in gpurun_out/ (run in the build container, no GPU needed):
+  python profiles/summarize.py launches gpurun_out/launches_X.csv      -> per-kernel share of one policy iteration
+  python profiles/summarize.py raw gpurun_out/prof_X.ncu-rep           -> key metrics of each captured launch
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__t_bytes.sum",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_xu.sum",
+        "sm__inst_executed_pipe_lsu.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subunit_cycles_active.avg.pct_of_peak_sustained_active"
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed_op_shfl.sum",
+        "sm__cycles_elapsed.avg", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
+        "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    agg, tot = collections.OrderedDict(), 0.0
+    for r in rows:
+        t = float(r["Metric Value"].replace(",", ""))
+        t = t / 1e3 if r["Metric Unit"] == "ns" else t * (1e3 if r["Metric Unit"] == "ms" else 1)
+        k = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void <unnamed>::", "").replace("<unnamed>::", "")
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += t
+        tot += t
+    print(f"{len(rows)} launches, {tot:.1f} us total (ncu: serialised, cold cache)")
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{t:10.1f} us {100 * t / tot:5.1f}%  n={n:3d}  {k}")
+
+
+def raw(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        print("=====", d.get("Kernel Name", "")[:90], "grid", d.get("Grid Size"), "block", d.get("Block Size"))
+        for k in KEYS:
+            if k in d and d[k] != "":
+                print(f"  {k:75s} {d[k]:>16s} {units[hdr.index(k)]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])

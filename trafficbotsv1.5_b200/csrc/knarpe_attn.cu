@@ -7,17 +7,28 @@
 // so the kernel needs no weights: it consumes q, u_h = W_rk,h^T q_h (both pre-scaled by log2(e)/sqrt(d_head) by the
 // caller's projection) and emits ov = sum a v and z_h = sum a e; the dense parts stay in the projections.
 //
-// Mapping: one warp per source token; lane l owns feature columns [l*D/32, (l+1)*D/32) of q/k/v (=> head l/8, a
-// K or V row is one fully coalesced 512 B / 1 KiB request) and embedding components {l + 32 r}. The 128/256-d
-// sin/cos relative-pose embedding is evaluated in registers from the 12-byte relative pose (2-term Cody-Waite
-// reduction + SFU sin/cos), never materialised. Neighbours are processed in groups of G with all K/V rows of a
-// group in flight before use, and one online-softmax rescale per group.
+// Mapping (v2, from the ncu instruction mix of v1 — profiles/r1_notes.md): one warp per source token.
+//   * q/k/v: lane l owns feature columns [l*D/32, (l+1)*D/32) => head l>>3; a K or V row is one fully coalesced
+//     512 B / 1 KiB request; the rows of G neighbours are in flight before first use.
+//   * relative-pose embedding e_j (D sin/cos components, utils/pose_emb.py:50-55): evaluated cooperatively, lane l
+//     computes components {l + 32k} in registers from the 12-byte relative pose (2-term Cody-Waite reduction + SFU),
+//     then exchanged through a bank-conflict-free shared-memory transpose so that lane (h = l>>3, s = l&7) holds the
+//     D/8 components {s + 8r} it needs for ITS head only. The RPE logit term and z_h therefore share the 8-lane
+//     reduction of q.k (3 shuffles per neighbour), the softmax is evaluated once per head (not once per lane x head),
+//     and the fp32 multiply-adds are issued as packed FFMA2.
+//   * online softmax with lazy rescale (accumulators are rescaled only when a head's running max grows).
 #include "common.cuh"
 
 namespace {
 
 constexpr int kWarps = 8;
 constexpr int H = 4;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int D, bool FROM_EMB>
 __global__ void __launch_bounds__(kWarps * 32)
@@ -29,23 +40,26 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
                    const float* __restrict__ pe_freq_xy, int n_tok, int S,
                    float* __restrict__ out_ov, float* __restrict__ out_z, int ldo,
                    uint8_t* __restrict__ out_none_valid) {
-  constexpr int NV = D / 32;          // q/k/v floats per lane
-  constexpr int NR = D / 32;          // embedding components per lane
-  constexpr int G = (D == 128) ? 4 : 2;
-  constexpr int NF = D / 8;           // xy frequencies
+  constexpr int NV = D / 32;            // q/k/v floats per lane
+  constexpr int NC = D / 32;            // embedding components a lane COMPUTES (l + 32k)
+  constexpr int NO = D / 8;             // embedding components a lane OWNS for its head (s + 8r)
+  constexpr int G = (D == 128) ? 4 : 2; // neighbours with K/V rows in flight
+  constexpr int NF = D / 8;             // number of xy frequencies
+  constexpr int ES = NO + 4;            // padded stride of the transpose (conflict-free, see header)
   __shared__ int s_idx[kWarps][32];
   __shared__ float s_rel[kWarps][32][3];
+  __shared__ __align__(16) float s_e[kWarps][G][8 * ES];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok = blockIdx.x * kWarps + warp;
-  if (tok >= n_tok) return;  // warp-uniform; no block-level sync below
+  if (tok >= n_tok) return;  // warp-uniform; only __syncwarp below
   const int b = tok / S;
   const int Ktot = K0 + K1;
-  const int hh = lane >> 3;  // own head
+  const int hh = lane >> 3, sub = lane & 7;
 
-  // per-lane constants of the embedding
-  float fxy, ph;  // D=128: one x and one y component per lane: freq index lane&15, cos for lane<16 else sin
-  if (D == 128) {
+  // per-lane constants of the components this lane computes
+  float fxy, ph;
+  if (D == 128) {  // one x and one y component per lane: frequency lane&15, cos for lane<16 else sin
     fxy = __ldg(pe_freq_xy + (lane & (NF - 1)));
     ph = (lane < NF) ? 1.57079632679489662f : 0.f;
   } else {
@@ -53,8 +67,10 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
     ph = 0.f;
   }
   const float m1 = (float)(lane + 1), m2 = (float)(lane + 33);
+  const int wpos = sub * ES + hh;  // transpose: component c -> (c & 7) * ES + (c >> 3); c = lane + 32k -> wpos + 4k
 
-  float qr[NV], ur[H][NR];
+  float qr[NV];
+  float2 uo[NO / 2], zo[NO / 2];
   {
     const float* qp = q + (size_t)tok * ldq + lane * NV;
 #pragma unroll
@@ -62,22 +78,17 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
       float4 t = ldg4(qp + i);
       qr[i] = t.x; qr[i + 1] = t.y; qr[i + 2] = t.z; qr[i + 3] = t.w;
     }
-    const float* up = u + (size_t)tok * ldu;
+    const float* up = u + (size_t)tok * ldu + hh * D + sub;
 #pragma unroll
-    for (int h = 0; h < H; ++h)
-#pragma unroll
-      for (int r = 0; r < NR; ++r) ur[h][r] = __ldg(up + h * D + lane + 32 * r);
+    for (int r = 0; r < NO / 2; ++r) {
+      uo[r] = make_float2(__ldg(up + 16 * r), __ldg(up + 16 * r + 8));
+      zo[r] = make_float2(0.f, 0.f);
+    }
   }
-
-  float ov[NV], z[H][NR], mx[H], sm[H];
+  float ov[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) ov[i] = 0.f;
-#pragma unroll
-  for (int h = 0; h < H; ++h) {
-    mx[h] = -INFINITY; sm[h] = 0.f;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) z[h][r] = 0.f;
-  }
+  float mx = -INFINITY, sm = 0.f;
 
   const size_t prow = (size_t)tok * Ktot;
   const float* kb0 = kv0 + (size_t)(b / div0) * T0 * ldkv0 + lane * NV;
@@ -121,126 +132,99 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
             float4 w = ldg4(rp + D + i);
             vr[g][i] = w.x; vr[g][i + 1] = w.y; vr[g][i + 2] = w.z; vr[g][i + 3] = w.w;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < NV; ++i) { kr[g][i] = 0.f; vr[g][i] = 0.f; }
         }
       }
 
-      // ---- embedding + logits
-      float e[G][NR], lg[G];
+      // ---- embedding components {lane + 32k} of the group's neighbours -> transposed into shared memory
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        if (id[g] >= 0) {
-          if (FROM_EMB) {
-            const float* ep = emb + (prow + c0 + g0 + g) * D + lane;
+        if (id[g] < 0) continue;  // warp-uniform
+        float ec[NC];
+        if (FROM_EMB) {
+          const float* ep = emb + (prow + c0 + g0 + g) * D + lane;
 #pragma unroll
-            for (int r = 0; r < NR; ++r) e[g][r] = __ldg(ep + 32 * r);
-          } else {
-            const float x = s_rel[warp][g0 + g][0], y = s_rel[warp][g0 + g][1], w = s_rel[warp][g0 + g][2];
-            if (D == 128) {
-              e[g][0] = __sinf(tb_reduce_2pi(x * fxy) + ph);
-              e[g][1] = __sinf(tb_reduce_2pi(y * fxy) + ph);
-              const float rw = tb_reduce_2pi(w * m1);
-              e[g][2] = __cosf(rw);
-              e[g][3] = __sinf(rw);
-            } else {
-              const float rx = tb_reduce_2pi(x * fxy), ry = tb_reduce_2pi(y * fxy);
-              const float r1 = tb_reduce_2pi(w * m1), r2 = tb_reduce_2pi(w * m2);
-              e[g][0] = __cosf(rx); e[g][1] = __sinf(rx);
-              e[g][2] = __cosf(ry); e[g][3] = __sinf(ry);
-              e[g][4 % NR] = __cosf(r1); e[g][5 % NR] = __cosf(r2);
-              e[g][6 % NR] = __sinf(r1); e[g][7 % NR] = __sinf(r2);
-            }
-          }
-          float p[H];
-#pragma unroll
-          for (int h = 0; h < H; ++h) {
-            float a = 0.f;
-#pragma unroll
-            for (int r = 0; r < NR; ++r) a = fmaf(ur[h][r], e[g][r], a);
-            p[h] = a;
-          }
-          float qk = 0.f;
-#pragma unroll
-          for (int i = 0; i < NV; ++i) qk = fmaf(qr[i], kr[g][i], qk);
-          // 4 partial sums over 32 lanes -> lane keeps head (lane>>3): halving butterfly, 6 shuffles
-          const bool b4 = lane & 16, b3 = lane & 8;
-          float a0 = b4 ? p[2] : p[0], a1 = b4 ? p[3] : p[1];
-          const float s0 = b4 ? p[0] : p[2], s1 = b4 ? p[1] : p[3];
-          a0 += __shfl_xor_sync(TB_FULL_MASK, s0, 16);
-          a1 += __shfl_xor_sync(TB_FULL_MASK, s1, 16);
-          float t = (b3 ? a1 : a0) + __shfl_xor_sync(TB_FULL_MASK, b3 ? a0 : a1, 8);
-          t += qk;
-          t += __shfl_xor_sync(TB_FULL_MASK, t, 4);
-          t += __shfl_xor_sync(TB_FULL_MASK, t, 2);
-          t += __shfl_xor_sync(TB_FULL_MASK, t, 1);
-          lg[g] = t;
+          for (int k = 0; k < NC; ++k) ec[k] = __ldg(ep + 32 * k);
         } else {
-          lg[g] = -INFINITY;
-#pragma unroll
-          for (int r = 0; r < NR; ++r) e[g][r] = 0.f;
+          const float x = s_rel[warp][g0 + g][0], y = s_rel[warp][g0 + g][1], w = s_rel[warp][g0 + g][2];
+          if (D == 128) {
+            ec[0] = __sinf(tb_reduce_2pi(x * fxy) + ph);
+            ec[1] = __sinf(tb_reduce_2pi(y * fxy) + ph);
+            const float rw = tb_reduce_2pi(w * m1);
+            ec[2] = __cosf(rw);
+            ec[3] = __sinf(rw);
+          } else {
+            const float rx = tb_reduce_2pi(x * fxy), ry = tb_reduce_2pi(y * fxy);
+            const float r1 = tb_reduce_2pi(w * m1), r2 = tb_reduce_2pi(w * m2);
+            ec[0] = __cosf(rx); ec[1] = __sinf(rx);
+            ec[2] = __cosf(ry); ec[3] = __sinf(ry);
+            ec[4 % NC] = __cosf(r1); ec[5 % NC] = __cosf(r2);
+            ec[6 % NC] = __sinf(r1); ec[7 % NC] = __sinf(r2);
+          }
         }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) s_e[warp][g][wpos + 4 * k] = ec[k];
       }
+      __syncwarp();
 
-      // ---- online softmax: one rescale per group and head
-      float corr_o = 1.f, p_o[G];
+      // ---- per neighbour: own-head logit (q.k + u_h.e_j), 8-lane reduction, online softmax, accumulate
 #pragma unroll
-      for (int g = 0; g < G; ++g) p_o[g] = 0.f;
+      for (int g = 0; g < G; ++g) {
+        if (id[g] < 0) continue;  // warp-uniform
+        float2 eo[NO / 2];
+        const float4* sp = reinterpret_cast<const float4*>(&s_e[warp][g][sub * ES]);
 #pragma unroll
-      for (int h = 0; h < H; ++h) {
-        float l[G], gm = -INFINITY;
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          l[g] = __shfl_sync(TB_FULL_MASK, lg[g], h * 8);
-          gm = fmaxf(gm, l[g]);
+        for (int r = 0; r < NO / 4; ++r) {
+          const float4 t = sp[r];  // components sub + 8*(4r .. 4r+3)
+          eo[2 * r] = make_float2(t.x, t.y);
+          eo[2 * r + 1] = make_float2(t.z, t.w);
         }
-        const float mn = fmaxf(mx[h], gm);  // finite: the group has >= 1 valid neighbour
-        const float corr = exp2f(mx[h] - mn);
-        mx[h] = mn;
-        float ps = 0.f, pg[G];
+        float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int g = 0; g < G; ++g) { pg[g] = exp2f(l[g] - mn); ps += pg[g]; }
-        sm[h] = fmaf(sm[h], corr, ps);
+        for (int r = 0; r < NO / 2; ++r) acc = __ffma2_rn(uo[r], eo[r], acc);
+        float t = acc.x + acc.y;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          float a = z[h][r] * corr;
+        for (int i = 0; i < NV; ++i) t = fmaf(qr[i], kr[g][i], t);
+        t += __shfl_xor_sync(TB_FULL_MASK, t, 4);
+        t += __shfl_xor_sync(TB_FULL_MASK, t, 2);
+        t += __shfl_xor_sync(TB_FULL_MASK, t, 1);
+        if (__any_sync(TB_FULL_MASK, t > mx)) {  // lazy rescale: some head's running max grows
+          const float mn = fmaxf(mx, t);
+          const float corr = ex2(mx - mn);  // mx = -inf -> 0
+          mx = mn;
+          sm *= corr;
+          const float2 c2 = make_float2(corr, corr);
 #pragma unroll
-          for (int g = 0; g < G; ++g) a = fmaf(pg[g], e[g][r], a);
-          z[h][r] = a;
+          for (int r = 0; r < NO / 2; ++r) zo[r] = __fmul2_rn(zo[r], c2);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) ov[i] *= corr;
         }
-        if (hh == h) {
-          corr_o = corr;
+        const float p = ex2(t - mx);
+        sm += p;
+        const float2 p2 = make_float2(p, p);
 #pragma unroll
-          for (int g = 0; g < G; ++g) p_o[g] = pg[g];
-        }
+        for (int r = 0; r < NO / 2; ++r) zo[r] = __ffma2_rn(p2, eo[r], zo[r]);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ov[i] = fmaf(p, vr[g][i], ov[i]);
       }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        float a = ov[i] * corr_o;
-#pragma unroll
-        for (int g = 0; g < G; ++g) a = fmaf(p_o[g], vr[g][i], a);
-        ov[i] = a;
-      }
+      __syncwarp();  // s_e is rewritten by the next group
     }
   }
 
   // ---- normalise + store (all-masked row: zeros, attention_rpe.py:188-190)
-  float inv_s[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) inv_s[h] = sm[h] > 0.f ? 1.f / sm[h] : 0.f;
-  const float inv_o = hh == 0 ? inv_s[0] : hh == 1 ? inv_s[1] : hh == 2 ? inv_s[2] : inv_s[3];
+  const float inv_s = sm > 0.f ? 1.f / sm : 0.f;
   float* op = out_ov + (size_t)tok * ldo + lane * NV;
 #pragma unroll
   for (int i = 0; i < NV; i += 4)
     *reinterpret_cast<float4*>(op + i) =
-        make_float4(ov[i] * inv_o, ov[i + 1] * inv_o, ov[i + 2] * inv_o, ov[i + 3] * inv_o);
-  float* zp = out_z + (size_t)tok * ldo;
+        make_float4(ov[i] * inv_s, ov[i + 1] * inv_s, ov[i + 2] * inv_s, ov[i + 3] * inv_s);
+  // z_h[c], c = sub + 8r, r = 2*rr (+1): eo pairs hold r = 4k+{0,1} / 4k+{2,3}  => zo[r2] = (c = sub + 8*(2*r2), +8)
+  float* zp = out_z + (size_t)tok * ldo + hh * D + sub;
 #pragma unroll
-  for (int h = 0; h < H; ++h)
-#pragma unroll
-    for (int r = 0; r < NR; ++r) zp[h * D + lane + 32 * r] = z[h][r] * inv_s[h];
-  if (lane == 0 && out_none_valid) out_none_valid[tok] = sm[0] > 0.f ? 0 : 1;
+  for (int r = 0; r < NO / 2; ++r) {
+    zp[16 * r] = zo[r].x * inv_s;
+    zp[16 * r + 8] = zo[r].y * inv_s;
+  }
+  if (lane == 0 && out_none_valid) out_none_valid[tok] = sm > 0.f ? 0 : 1;
 }
 
 template <int D, bool FROM_EMB>
