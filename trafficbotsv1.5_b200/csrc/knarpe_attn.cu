@@ -7,16 +7,18 @@
 // so the kernel needs no weights: it consumes q, u_h = W_rk,h^T q_h (both pre-scaled by log2(e)/sqrt(d_head) by the
 // caller's projection) and emits ov = sum a v and z_h = sum a e; the dense parts stay in the projections.
 //
-// Mapping (v2, from the ncu instruction mix of v1 — profiles/r1_notes.md): one warp per source token.
+// Mapping (v3; v1/v2 and their ncu instruction mixes are summarised in profiles/r1_notes.md): one warp per token.
 //   * q/k/v: lane l owns feature columns [l*D/32, (l+1)*D/32) => head l>>3; a K or V row is one fully coalesced
-//     512 B / 1 KiB request; the rows of G neighbours are in flight before first use.
-//   * relative-pose embedding e_j (D sin/cos components, utils/pose_emb.py:50-55): evaluated cooperatively, lane l
-//     computes components {l + 32k} in registers from the 12-byte relative pose (2-term Cody-Waite reduction + SFU),
-//     then exchanged through a bank-conflict-free shared-memory transpose so that lane (h = l>>3, s = l&7) holds the
-//     D/8 components {s + 8r} it needs for ITS head only. The RPE logit term and z_h therefore share the 8-lane
-//     reduction of q.k (3 shuffles per neighbour), the softmax is evaluated once per head (not once per lane x head),
-//     and the fp32 multiply-adds are issued as packed FFMA2.
-//   * online softmax with lazy rescale (accumulators are rescaled only when a head's running max grows).
+//     512 B / 1 KiB request; the rows of the G neighbours of a group are in flight before first use.
+//   * relative-pose embedding e_j (D sin/cos components, utils/pose_emb.py:50-55): lane l evaluates components
+//     {l + 32k} in registers from the 12-byte relative pose (2-term Cody-Waite reduction + SFU) and multiplies them
+//     with its slice of u for all 4 heads (packed FFMA2). Heads are held in a lane-permuted order (slot i = head
+//     i ^ (l>>3)), which turns the 4-value cross-lane reduction into a select-free halving butterfly (3 shuffles)
+//     that ends with each 8-lane group holding ITS head's partial, so it shares the 3-shuffle reduction of q.k.
+//   * softmax: one evaluation per head and group of G neighbours (lanes of a head group compute their own head
+//     only, probabilities are exchanged with 3 xor-shuffles), one accumulator rescale per group.
+//   * everything inside a group is branch-free (masked neighbours get logit -inf), so the G dependency chains
+//     interleave (the v2 kernel was latency-bound: 33% stall_wait, 26% short-scoreboard at 14 warps/SM).
 #include "common.cuh"
 
 namespace {
@@ -41,23 +43,19 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
                    float* __restrict__ out_ov, float* __restrict__ out_z, int ldo,
                    uint8_t* __restrict__ out_none_valid) {
   constexpr int NV = D / 32;            // q/k/v floats per lane
-  constexpr int NC = D / 32;            // embedding components a lane COMPUTES (l + 32k)
-  constexpr int NO = D / 8;             // embedding components a lane OWNS for its head (s + 8r)
-  constexpr int G = (D == 128) ? 4 : 2; // neighbours with K/V rows in flight
+  constexpr int NC = D / 32;            // embedding components per lane (l + 32k)
+  constexpr int G = (D == 128) ? 4 : 2; // neighbours per group
   constexpr int NF = D / 8;             // number of xy frequencies
-  constexpr int ES = NO + 4;            // padded stride of the transpose (conflict-free, see header)
   __shared__ int s_idx[kWarps][32];
   __shared__ float s_rel[kWarps][32][3];
-  __shared__ __align__(16) float s_e[kWarps][G][8 * ES];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok = blockIdx.x * kWarps + warp;
   if (tok >= n_tok) return;  // warp-uniform; only __syncwarp below
   const int b = tok / S;
   const int Ktot = K0 + K1;
-  const int hh = lane >> 3, sub = lane & 7;
+  const int hh = lane >> 3;  // own head; slot i of the per-head arrays holds head (i ^ hh)
 
-  // per-lane constants of the components this lane computes
   float fxy, ph;
   if (D == 128) {  // one x and one y component per lane: frequency lane&15, cos for lane<16 else sin
     fxy = __ldg(pe_freq_xy + (lane & (NF - 1)));
@@ -67,10 +65,9 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
     ph = 0.f;
   }
   const float m1 = (float)(lane + 1), m2 = (float)(lane + 33);
-  const int wpos = sub * ES + hh;  // transpose: component c -> (c & 7) * ES + (c >> 3); c = lane + 32k -> wpos + 4k
 
   float qr[NV];
-  float2 uo[NO / 2], zo[NO / 2];
+  float2 ur[H][NC / 2], z[H][NC / 2];
   {
     const float* qp = q + (size_t)tok * ldq + lane * NV;
 #pragma unroll
@@ -78,12 +75,15 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
       float4 t = ldg4(qp + i);
       qr[i] = t.x; qr[i + 1] = t.y; qr[i + 2] = t.z; qr[i + 3] = t.w;
     }
-    const float* up = u + (size_t)tok * ldu + hh * D + sub;
+    const float* up = u + (size_t)tok * ldu + lane;
 #pragma unroll
-    for (int r = 0; r < NO / 2; ++r) {
-      uo[r] = make_float2(__ldg(up + 16 * r), __ldg(up + 16 * r + 8));
-      zo[r] = make_float2(0.f, 0.f);
-    }
+    for (int i = 0; i < H; ++i)
+#pragma unroll
+      for (int k = 0; k < NC / 2; ++k) {
+        const float* uh = up + (i ^ hh) * D + 64 * k;
+        ur[i][k] = make_float2(__ldg(uh), __ldg(uh + 32));
+        z[i][k] = make_float2(0.f, 0.f);
+      }
   }
   float ov[NV];
 #pragma unroll
@@ -105,124 +105,143 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
         s_rel[warp][lane][1] = rel[p * 3 + 1];
         s_rel[warp][lane][2] = rel[p * 3 + 2];
       }
+    } else {
+      s_idx[warp][lane] = -1;
+      if (!FROM_EMB) { s_rel[warp][lane][0] = 0.f; s_rel[warp][lane][1] = 0.f; s_rel[warp][lane][2] = 0.f; }
     }
     __syncwarp();
 
-    for (int g0 = 0; g0 < cnt; g0 += G) {
+    for (int g0 = 0; g0 < cnt; g0 += G) {  // cnt <= 32 and 32 % G == 0: reads of s_idx stay in range
       int id[G];
       bool any = false;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        id[g] = (g0 + g < cnt) ? s_idx[warp][g0 + g] : -1;
+        id[g] = s_idx[warp][g0 + g];
         any |= id[g] >= 0;
       }
       if (!any) continue;  // warp-uniform
 
-      // ---- gather: all K and V rows of the group in flight before first use
+      // ---- gather (branch-free: masked neighbours read row 0 and are weighted 0)
       float kr[G][NV], vr[G][NV];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        if (id[g] >= 0) {
-          const int j = c0 + g0 + g;
-          const float* rp = (j < K0) ? kb0 + (size_t)id[g] * ldkv0 : kb1 + (size_t)id[g] * ldkv1;
+        const int j = c0 + g0 + g;
+        const int row = max(id[g], 0);
+        const float* rp = (j < K0) ? kb0 + (size_t)row * ldkv0 : kb1 + (size_t)row * ldkv1;
 #pragma unroll
-          for (int i = 0; i < NV; i += 4) {
-            float4 t = ldg4(rp + i);
-            kr[g][i] = t.x; kr[g][i + 1] = t.y; kr[g][i + 2] = t.z; kr[g][i + 3] = t.w;
-            float4 w = ldg4(rp + D + i);
-            vr[g][i] = w.x; vr[g][i + 1] = w.y; vr[g][i + 2] = w.z; vr[g][i + 3] = w.w;
-          }
+        for (int i = 0; i < NV; i += 4) {
+          float4 t = ldg4(rp + i);
+          kr[g][i] = t.x; kr[g][i + 1] = t.y; kr[g][i + 2] = t.z; kr[g][i + 3] = t.w;
+          float4 w = ldg4(rp + D + i);
+          vr[g][i] = w.x; vr[g][i + 1] = w.y; vr[g][i + 2] = w.z; vr[g][i + 3] = w.w;
         }
       }
 
-      // ---- embedding components {lane + 32k} of the group's neighbours -> transposed into shared memory
+      // ---- embedding, per-head partial logits, reductions: G independent chains
+      float2 e[G][NC / 2];
+      float lg[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        if (id[g] < 0) continue;  // warp-uniform
-        float ec[NC];
         if (FROM_EMB) {
-          const float* ep = emb + (prow + c0 + g0 + g) * D + lane;
+          const size_t pj = prow + min(c0 + g0 + g, Ktot - 1);
+          const float* ep = emb + pj * D + lane;
 #pragma unroll
-          for (int k = 0; k < NC; ++k) ec[k] = __ldg(ep + 32 * k);
+          for (int k = 0; k < NC / 2; ++k) e[g][k] = make_float2(__ldg(ep + 64 * k), __ldg(ep + 64 * k + 32));
         } else {
           const float x = s_rel[warp][g0 + g][0], y = s_rel[warp][g0 + g][1], w = s_rel[warp][g0 + g][2];
           if (D == 128) {
-            ec[0] = __sinf(tb_reduce_2pi(x * fxy) + ph);
-            ec[1] = __sinf(tb_reduce_2pi(y * fxy) + ph);
             const float rw = tb_reduce_2pi(w * m1);
-            ec[2] = __cosf(rw);
-            ec[3] = __sinf(rw);
+            e[g][0] = make_float2(__sinf(tb_reduce_2pi(x * fxy) + ph), __sinf(tb_reduce_2pi(y * fxy) + ph));
+            e[g][1 % (NC / 2)] = make_float2(__cosf(rw), __sinf(rw));
           } else {
             const float rx = tb_reduce_2pi(x * fxy), ry = tb_reduce_2pi(y * fxy);
             const float r1 = tb_reduce_2pi(w * m1), r2 = tb_reduce_2pi(w * m2);
-            ec[0] = __cosf(rx); ec[1] = __sinf(rx);
-            ec[2] = __cosf(ry); ec[3] = __sinf(ry);
-            ec[4 % NC] = __cosf(r1); ec[5 % NC] = __cosf(r2);
-            ec[6 % NC] = __sinf(r1); ec[7 % NC] = __sinf(r2);
+            e[g][0] = make_float2(__cosf(rx), __sinf(rx));
+            e[g][1 % (NC / 2)] = make_float2(__cosf(ry), __sinf(ry));
+            e[g][2 % (NC / 2)] = make_float2(__cosf(r1), __cosf(r2));
+            e[g][3 % (NC / 2)] = make_float2(__sinf(r1), __sinf(r2));
           }
         }
+        float p[H];
 #pragma unroll
-        for (int k = 0; k < NC; ++k) s_e[warp][g][wpos + 4 * k] = ec[k];
-      }
-      __syncwarp();
-
-      // ---- per neighbour: own-head logit (q.k + u_h.e_j), 8-lane reduction, online softmax, accumulate
+        for (int i = 0; i < H; ++i) {
+          float2 a = __fmul2_rn(ur[i][0], e[g][0]);
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (id[g] < 0) continue;  // warp-uniform
-        float2 eo[NO / 2];
-        const float4* sp = reinterpret_cast<const float4*>(&s_e[warp][g][sub * ES]);
-#pragma unroll
-        for (int r = 0; r < NO / 4; ++r) {
-          const float4 t = sp[r];  // components sub + 8*(4r .. 4r+3)
-          eo[2 * r] = make_float2(t.x, t.y);
-          eo[2 * r + 1] = make_float2(t.z, t.w);
+          for (int k = 1; k < NC / 2; ++k) a = __ffma2_rn(ur[i][k], e[g][k], a);
+          p[i] = a.x + a.y;
         }
-        float2 acc = make_float2(0.f, 0.f);
+        // select-free halving butterfly over the permuted head slots (slot i = head i ^ hh)
+        p[0] += __shfl_xor_sync(TB_FULL_MASK, p[2], 16);
+        p[1] += __shfl_xor_sync(TB_FULL_MASK, p[3], 16);
+        float t = p[0] + __shfl_xor_sync(TB_FULL_MASK, p[1], 8);
+        float qk = 0.f;
 #pragma unroll
-        for (int r = 0; r < NO / 2; ++r) acc = __ffma2_rn(uo[r], eo[r], acc);
-        float t = acc.x + acc.y;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) t = fmaf(qr[i], kr[g][i], t);
+        for (int i = 0; i < NV; ++i) qk = fmaf(qr[i], kr[g][i], qk);
+        t += qk;
         t += __shfl_xor_sync(TB_FULL_MASK, t, 4);
         t += __shfl_xor_sync(TB_FULL_MASK, t, 2);
         t += __shfl_xor_sync(TB_FULL_MASK, t, 1);
-        if (__any_sync(TB_FULL_MASK, t > mx)) {  // lazy rescale: some head's running max grows
-          const float mn = fmaxf(mx, t);
-          const float corr = ex2(mx - mn);  // mx = -inf -> 0
-          mx = mn;
-          sm *= corr;
-          const float2 c2 = make_float2(corr, corr);
-#pragma unroll
-          for (int r = 0; r < NO / 2; ++r) zo[r] = __fmul2_rn(zo[r], c2);
-#pragma unroll
-          for (int i = 0; i < NV; ++i) ov[i] *= corr;
-        }
-        const float p = ex2(t - mx);
-        sm += p;
-        const float2 p2 = make_float2(p, p);
-#pragma unroll
-        for (int r = 0; r < NO / 2; ++r) zo[r] = __ffma2_rn(p2, eo[r], zo[r]);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) ov[i] = fmaf(p, vr[g][i], ov[i]);
+        lg[g] = id[g] >= 0 ? t : -INFINITY;
       }
-      __syncwarp();  // s_e is rewritten by the next group
+
+      // ---- softmax of the group for the lane's own head; one rescale per group
+      float gm = lg[0];
+#pragma unroll
+      for (int g = 1; g < G; ++g) gm = fmaxf(gm, lg[g]);
+      const float mn = fmaxf(mx, gm);  // finite: the group has a valid neighbour (same validity for all heads)
+      const float corr = ex2(mx - mn);
+      mx = mn;
+      float pg[G], ps = 0.f;
+#pragma unroll
+      for (int g = 0; g < G; ++g) { pg[g] = ex2(lg[g] - mn); ps += pg[g]; }
+      sm = fmaf(sm, corr, ps);
+      // rescale factors / probabilities of the other heads: slot i lives in lane ^ (8 i)
+      float cs[H];
+      cs[0] = corr;
+#pragma unroll
+      for (int i = 1; i < H; ++i) cs[i] = __shfl_xor_sync(TB_FULL_MASK, corr, 8 * i);
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float2 c2 = make_float2(cs[i], cs[i]);
+#pragma unroll
+        for (int k = 0; k < NC / 2; ++k) z[i][k] = __fmul2_rn(z[i][k], c2);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) ov[i] *= corr;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float pi[H];
+        pi[0] = pg[g];
+#pragma unroll
+        for (int i = 1; i < H; ++i) pi[i] = __shfl_xor_sync(TB_FULL_MASK, pg[g], 8 * i);
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const float2 p2 = make_float2(pi[i], pi[i]);
+#pragma unroll
+          for (int k = 0; k < NC / 2; ++k) z[i][k] = __ffma2_rn(p2, e[g][k], z[i][k]);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ov[i] = fmaf(pg[g], vr[g][i], ov[i]);
+      }
     }
   }
 
   // ---- normalise + store (all-masked row: zeros, attention_rpe.py:188-190)
-  const float inv_s = sm > 0.f ? 1.f / sm : 0.f;
+  const float inv_o = sm > 0.f ? 1.f / sm : 0.f;
   float* op = out_ov + (size_t)tok * ldo + lane * NV;
 #pragma unroll
   for (int i = 0; i < NV; i += 4)
     *reinterpret_cast<float4*>(op + i) =
-        make_float4(ov[i] * inv_s, ov[i + 1] * inv_s, ov[i + 2] * inv_s, ov[i + 3] * inv_s);
-  // z_h[c], c = sub + 8r, r = 2*rr (+1): eo pairs hold r = 4k+{0,1} / 4k+{2,3}  => zo[r2] = (c = sub + 8*(2*r2), +8)
-  float* zp = out_z + (size_t)tok * ldo + hh * D + sub;
+        make_float4(ov[i] * inv_o, ov[i + 1] * inv_o, ov[i + 2] * inv_o, ov[i + 3] * inv_o);
+  float* zp = out_z + (size_t)tok * ldo + lane;
 #pragma unroll
-  for (int r = 0; r < NO / 2; ++r) {
-    zp[16 * r] = zo[r].x * inv_s;
-    zp[16 * r + 8] = zo[r].y * inv_s;
+  for (int i = 0; i < H; ++i) {
+    const float inv_i = i == 0 ? inv_o : __shfl_xor_sync(TB_FULL_MASK, inv_o, 8 * i);
+#pragma unroll
+    for (int k = 0; k < NC / 2; ++k) {
+      zp[(i ^ hh) * D + 64 * k] = z[i][k].x * inv_i;
+      zp[(i ^ hh) * D + 64 * k + 32] = z[i][k].y * inv_i;
+    }
   }
   if (lane == 0 && out_none_valid) out_none_valid[tok] = sm > 0.f ? 0 : 1;
 }
