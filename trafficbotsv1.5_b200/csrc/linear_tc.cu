@@ -3,7 +3,9 @@
 //   operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a 4-stage mbarrier pipeline,
 //   warp-specialised: warps 0-3 epilogue (tcgen05.ld -> bias/ReLU/mask/residual -> global), warp 4 TMA producer,
 //   warp 5 MMA issuer + TMEM allocator. Two TMEM accumulator buffers overlap the epilogue of tile n with the MMAs of
-//   tile n+1. One CTA per 128-row M tile walks all of its N tiles, so the A tile is re-read from L2 only.
+//   tile n+1. Persistent CTAs (one per SM) walk the (m, n) tiles n-fastest, so an A tile is fetched from HBM once and
+//   re-read from L2 by the neighbouring SMs; the epilogue transposes each 32x32 accumulator block through swizzled
+//   shared memory so that global stores / residual loads are full 128-byte lines.
 // Shapes the TMA/UMMA constraints do not cover (K or ldx not a multiple of 4 floats, N < 32, misaligned pointers)
 // are executed by the fp32 FFMA kernel instead (higher precision, same semantics).
 #include <cuda.h>
@@ -20,7 +22,8 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 2 * BN;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+constexpr int EPI_BYTES = 4 * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + 256;
 
 struct Epi {
   const float* bias; int relu; const uint8_t* mask_pre; const float* res; int ldr; const uint8_t* mask_post;
@@ -82,15 +85,16 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  float* sE = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES) + EPI_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
   const int n_tiles = (N + BN - 1) / BN;
+  const int total_tiles = ((M + BM - 1) / BM) * n_tiles;
   const int num_k = (K + BK - 1) / BK;
 
   if (warp == 4 && lane == 0) {
@@ -114,13 +118,14 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
-      for (int nt = blockIdx.y; nt < n_tiles; nt += gridDim.y) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
         for (int k = 0; k < num_k; ++k, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
           tma_load_2d(&mapA, &full[s], sA + s * A_BYTES, k * BK, m0);
-          tma_load_2d(&mapB, &full[s], sB + s * B_BYTES, k * BK, nt * BN);
+          tma_load_2d(&mapB, &full[s], sB + s * B_BYTES, k * BK, n0);
         }
       }
     }
@@ -129,7 +134,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       int it = 0, lt = 0;
-      for (int nt = blockIdx.y; nt < n_tiles; nt += gridDim.y, ++lt) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -149,21 +154,22 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
   } else {
     // ===== epilogue warps 0..3: TMEM lanes [32*warp, 32*warp+32) = rows m0 + 32*warp + lane =====
-    const int row = m0 + warp * 32 + lane;
-    const bool row_ok = row < M;
-    const bool zpre = row_ok && ep.mask_pre && ep.mask_pre[row];
-    const bool zpost = row_ok && ep.mask_post && ep.mask_post[row];
+    float* st = sE + warp * (32 * 32);  // this warp's 32x32 staging block, 16-byte chunks XOR-swizzled by row
     const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
-                        (!ep.res || (((ep.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.res) & 15) == 0)));
+                        (!ep.res || (((ep.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.res) & 15) == 0))) &&
+                        (!ep.bias || ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0));
+    const int rsub = lane >> 3, cc = lane & 7;  // store phase: lane -> (row i*4 + rsub, 16-byte chunk cc)
     int lt = 0;
-    for (int nt = blockIdx.y; nt < n_tiles; nt += gridDim.y, ++lt) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       const int buf = lt & 1;
       mbar_wait(&tfull[buf], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int n0 = nt * BN;
+      const int rbase = m0 + warp * 32;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= N) break;  // warp-uniform
+        const int cbase = n0 + c0;
+        if (cbase >= N) break;  // warp-uniform
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + c0);
         asm volatile(
@@ -176,44 +182,48 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row_ok) {
-          const int cbase = n0 + c0;
-          float* yp = Y + (size_t)row * ldy + cbase;
-          const float* rp = ep.res ? ep.res + (size_t)row * ep.ldr + cbase : nullptr;
-          if (vec_ok && cbase + 32 <= N) {
+        // registers (row = lane) -> swizzled staging block
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float v[4];
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(st + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+              make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        __syncwarp();
+        if (vec_ok && cbase + 32 <= N) {
+          const int col = cbase + cc * 4;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float t = __uint_as_float(r[j + q]);
-                if (ep.bias) t += __ldg(ep.bias + cbase + j + q);
-                if (ep.relu) t = fmaxf(t, 0.f);
-                if (zpre) t = 0.f;
-                v[q] = t;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub, row = rbase + rr;
+            if (row < M) {
+              float4 v = *reinterpret_cast<const float4*>(st + rr * 32 + ((cc ^ (rr & 7)) << 2));
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              if (ep.mask_pre && ep.mask_pre[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ep.res) {
+                const float4 rv = *reinterpret_cast<const float4*>(ep.res + (size_t)row * ep.ldr + col);
+                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
               }
-              if (rp) {
-                const float4 rr = *reinterpret_cast<const float4*>(rp + j);
-                v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-              }
-              if (zpost) { v[0] = v[1] = v[2] = v[3] = 0.f; }
-              *reinterpret_cast<float4*>(yp + j) = make_float4(v[0], v[1], v[2], v[3]);
+              if (ep.mask_post && ep.mask_post[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(Y + (size_t)row * ldy + col) = v;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (cbase + j < N) {
-                float t = __uint_as_float(r[j]);
-                if (ep.bias) t += __ldg(ep.bias + cbase + j);
-                if (ep.relu) t = fmaxf(t, 0.f);
-                if (zpre) t = 0.f;
-                if (rp) t += rp[j];
-                if (zpost) t = 0.f;
-                yp[j] = t;
-              }
+          }
+        } else {  // N tail / unaligned views: scalar, bounds-checked
+#pragma unroll 1
+          for (int i = 0; i < 32; ++i) {
+            const int row = rbase + i, col = cbase + lane;
+            if (row < M && col < N) {
+              float t = st[i * 32 + ((((lane >> 2) ^ (i & 7)) << 2) | (lane & 3))];
+              if (ep.bias) t += __ldg(ep.bias + col);
+              if (ep.relu) t = fmaxf(t, 0.f);
+              if (ep.mask_pre && ep.mask_pre[row]) t = 0.f;
+              if (ep.res) t += ep.res[(size_t)row * ep.ldr + col];
+              if (ep.mask_post && ep.mask_post[row]) t = 0.f;
+              Y[(size_t)row * ldy + col] = t;
             }
           }
         }
+        __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&tempty[buf]);
@@ -274,10 +284,17 @@ int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, flo
     attr_set = true;
   }
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
-  int gy = (2 * 148 + m_tiles - 1) / m_tiles;  // enough CTAs for two waves when M is small
-  gy = gy < 1 ? 1 : (gy > n_tiles ? n_tiles : gy);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
+      num_sms = 148;
+  }
+  const int total = m_tiles * n_tiles;
+  const int grid = total < num_sms ? total : num_sms;  // persistent: one CTA per SM
   Epi ep{bias, relu, mask_pre, res, ldr, mask_post};
-  linear_tf32_kernel<<<dim3(m_tiles, gy), NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
+  linear_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

@@ -49,6 +49,7 @@ class RolloutEngine:
         self.dyn = C.DYNAMICS_CFG
         self._graph = None
         self._shape = None
+        self._side = torch.cuda.Stream(device=self.dev)  # traffic-light branch runs beside the agent front-end
         # constants rounded the way the reference's fp32 tensor ops round them (traffic_rule_checker.py:94-96,103,308)
         one = torch.ones(1)
         self.thresh_lane = float(one * 50 * (1 - torch.zeros(1) * 0.8))
@@ -86,6 +87,7 @@ class RolloutEngine:
                   mp_node_invalid=z(n_sc, n_mp, n_node, dt=u8), mp_kind=z(n_sc, n_mp, dt=u8),
                   pred_valid=z(B, A, T, dt=u8), pred_pose=z(B, A, T, 3), pred_motion=z(B, A, T, 3),
                   tl_out=z(Bt, n_tl, T, 5, dt=u8), x_cat=z(B * A, 2 * d),
+                  tl_feat=z(Bt * n_tl, d), tl_logits=z(Bt * n_tl, self.cfg["tl_state_dim"]),
                   init_navi_valid=z(B, A, dt=torch.bool))
         return st
 
@@ -143,9 +145,14 @@ class RolloutEngine:
     def _step(self, st: dict, static: dict, navi: dict, aux: Optional[dict] = None):
         m, lib = self.model, L.load()
         d = m.d
-        tl_feat, logits = m.tl_forward(st["hist_tl"], st["d_step"], static["tl"])
+        # fork: the TL branch (640 rows, launch-latency bound) overlaps the agent featurise / PointNet / KNN kernels
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            m.tl_forward(st["hist_tl"], st["d_step"], static["tl"], out_feat=st["tl_feat"], out_logits=st["tl_logits"])
+        tl_feat, logits = st["tl_feat"], st["tl_logits"]
         m.ag_forward(st, static["mp"], static["kv_mp"], static["tl"], tl_feat, self.R, out=st["x_cat"][:, :d],
-                     aux=aux)
+                     aux=aux, before_tl=lambda: main.wait_stream(self._side))
         act = m.heads(st["x_cat"], st, navi)
         if aux is not None:
             aux.update(tl_feat=tl_feat, logits=logits, act=act, ag_feat=st["x_cat"][:, :d].clone())

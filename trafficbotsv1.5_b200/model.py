@@ -179,7 +179,8 @@ class HotPathModel:
                     cross=[dict(kv0=kv[i], T0=n_mp, div0=1, K0=sz["k_tl2mp"], idx=i2, inv=m2, rel=r2)
                            for i in range(len(kv))], n_sc=n_sc, n_tl=n_tl)
 
-    def tl_forward(self, hist_tl: Tensor, d_step: Tensor, tl: dict):
+    def tl_forward(self, hist_tl: Tensor, d_step: Tensor, tl: dict, out_feat: Optional[Tensor] = None,
+                   out_logits: Optional[Tensor] = None):
         """TrafficLightEncoder.forward (traffic_light.py:210-240) + TrafficLightStatePredictor (:270-286, pre-clamp).
         hist_tl [Bt, n_tl, W, 5] u8 ring."""
         from . import lib as L
@@ -194,10 +195,11 @@ class HotPathModel:
         x = self.mlp(attr, "tl_encoder.input_encoder.mlp", (0, 2, 4), False, res=tl["tl_attr_rows"])  # :176-180
         tok = self.pointnet(x, row_inv, Bt * n_tl, W, "tl_encoder.temp_encoder")                      # :228
         flat_inv = tl["tl_token_invalid"].reshape(-1)
-        for i in range(self.cfg["tl_encoder"]["n_layer_tf"]):
+        nl = self.cfg["tl_encoder"]["n_layer_tf"]
+        for i in range(nl):
             tok = self.tf_layer(f"tl_encoder.tf_tl2tlmp.layers.{i}", "dec_cross_attn", tok, flat_inv, Bt, n_tl,
-                                tl["knn_self"], tl["cross"][i])                                       # :231-240
-        logits = self.mlp(tok, "tl_state_predictor.mlp", (0, 2, 4), False)                            # :284
+                                tl["knn_self"], tl["cross"][i], out=out_feat if i == nl - 1 else None)  # :231-240
+        logits = self.mlp(tok, "tl_state_predictor.mlp", (0, 2, 4), False, out=out_logits)            # :284
         return tok, logits
 
     # ------------------------------------------------------------------------------------------ agents (per step)
@@ -209,7 +211,7 @@ class HotPathModel:
                 for i in range(self.cfg["ag_encoder"]["n_layer_tf"])]
 
     def ag_forward(self, st: dict, mp: Dict[str, Tensor], kv_mp: list, tl: dict, tl_feat: Tensor, R: int,
-                   out: Optional[Tensor] = None, aux: Optional[dict] = None) -> Tensor:
+                   out: Optional[Tensor] = None, aux: Optional[dict] = None, before_tl=None) -> Tensor:
         """AgentEncoder._forward_hptr (agent_encoder.py:114-178). `st` holds the rollout state rings
         (engine.RolloutState); batch b uses map / traffic-light tables of scene b // R."""
         from . import lib as L
@@ -245,6 +247,8 @@ class HotPathModel:
         nl = self.cfg["ag_encoder"]["n_layer_tf"]
         if aux is not None:
             aux.update(tok_pose=tok_pose, tok_inv=tok_inv, tok0=tok, knn_self=knn_self, cidx=cidx, cinv=cinv, crel=crel)
+        if before_tl is not None:
+            before_tl()  # join point: the traffic-light branch (side stream) must have produced tl_feat
         for i in range(nl):
             p = f"ag_encoder.tf_ag2agmptl.layers.{i}"
             kv_tl = self.kv_table(tl_feat, p, "norm_tgt")
