@@ -301,3 +301,44 @@ def test_linear_tensor_core_strided():
     ref = x[:, 128:256].double() @ w.double().T
     assert float((out[:, 256:].double() - ref).abs().max()) < 4e-3
     assert float(out[:, :256].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ drop-in module API
+def test_dropin_modules_golden(golden_ops):
+    """reference-style calls (state_dict loading, materialised PoseEmb rpe, gathered tgt) through the drop-in classes."""
+    from trafficbotsv1_5_b200 import reference_api as R
+    g = golden_ops["attn_d128"]
+    att = R.AttentionRPE(128, 4, dropout_p=0.1, bias=True, d_rpe=128).eval()
+    att.load_state_dict(params.rand_like_state_dict(g["sd_shapes"], g["sd_seed"]))
+    att = att.to(DEV)
+    pe = R.PoseEmb("pe_xy_yaw", pe_dim=128, theta_xy=1e3).to(DEV)
+    rel = g["rel"].to(DEV)
+    out, w = att(g["src"].to(DEV), g["tgt"].to(DEV), tgt_padding_mask=g["mask"].to(DEV),
+                 rpe=pe(rel[..., :2], rel[..., 2:3]))
+    assert w is None
+    close(out, g["out"], 1e-4, 1e-4 * float(g["out"].abs().max()), "drop-in AttentionRPE")
+    with pytest.raises(NotImplementedError):
+        att(g["src"].to(DEV), g["tgt"].to(DEV), rpe=None)
+    for mode in ("enc_self_attn", "dec_cross_attn"):
+        b = golden_ops[f"block_{mode}"]
+        blk = R.TransformerBlockRPE(d_model=128, n_head=4, k_feedforward=4, dropout_p=0.1, bias=True, activation="relu",
+                                    out_layernorm=False, apply_q_rpe=False, n_layer=b["n_layer"], mode=mode, d_rpe=128)
+        missing, unexpected = blk.load_state_dict(params.rand_like_state_dict(b["sd_shapes"], b["sd_seed"]), strict=True)
+        blk = blk.eval().to(DEV)
+        e = lambda r: pe(r.to(DEV)[..., :2], r.to(DEV)[..., 2:3])  # noqa: E731
+        if mode == "enc_self_attn":
+            out, _ = blk(src=b["src"].to(DEV), src_padding_mask=b["src_inv"].to(DEV), tgt=b["idx"].to(DEV),
+                         tgt_padding_mask=b["m1"].to(DEV), rpe=e(b["rel1"]))
+        else:
+            tgt = b["tgt_tab"][torch.arange(b["src"].shape[0])[:, None, None], b["idx2"]].to(DEV)
+            out, _ = blk(src=b["src"].to(DEV), src_padding_mask=b["src_inv"].to(DEV), tgt=tgt,
+                         tgt_padding_mask=b["m2"].to(DEV), rpe=e(b["rel2"]), decoder_tgt=b["idx"].to(DEV),
+                         decoder_tgt_padding_mask=b["m1"].to(DEV), decoder_rpe=e(b["rel1"]))
+        close(out, b["out"], 1e-4, 1e-4 * float(b["out"].abs().max()), f"drop-in block {mode}")
+    # utils.rpe mirror
+    k = golden_ops["knn_small"]
+    rp, rd = R.get_rel_pose(k["pose"].to(DEV), k["inv"].to(DEV), k["pose2"].to(DEV), k["inv2"].to(DEV))
+    idx, kinv, rpe3 = R.get_tgt_knn_idx(k["inv2"].to(DEV), rp, rd, k["K"], k["lim"])
+    assert idx.dtype == torch.int64 and rpe3.shape[-1] == 3
+    with pytest.raises(AssertionError):
+        R.get_tgt_knn_idx(k["inv2"].to(DEV), rp, rd, k["pose2"].shape[1], k["lim"])

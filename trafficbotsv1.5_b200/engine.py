@@ -34,6 +34,42 @@ def teacher_forcing_mask(gt_valid: Tensor, step_spawn: int, step_warm: int) -> T
     return tf
 
 
+def _leaves(tree, out):
+    if isinstance(tree, Tensor):
+        out.append(tree)
+    elif isinstance(tree, dict):
+        for k in sorted(tree):
+            _leaves(tree[k], out)
+    elif isinstance(tree, (list, tuple)):
+        for v in tree:
+            _leaves(v, out)
+    else:
+        out.append(tree)
+    return out
+
+
+def _same_layout(a, b) -> bool:
+    la, lb = _leaves(a, []), _leaves(b, [])
+    if len(la) != len(lb):
+        return False
+    for x, y in zip(la, lb):
+        if isinstance(x, Tensor) != isinstance(y, Tensor):
+            return False
+        if isinstance(x, Tensor):
+            if x.shape != y.shape or x.dtype != y.dtype or x.stride() != y.stride():
+                return False
+        elif x != y:
+            return False
+    return True
+
+
+def _copy_tree(dst, src) -> None:
+    """dst <- src leaf by leaf (views that alias one buffer are copied redundantly but consistently)."""
+    for x, y in zip(_leaves(dst, []), _leaves(src, [])):
+        if isinstance(x, Tensor) and x.data_ptr() != y.data_ptr():
+            x.copy_(y)
+
+
 class RolloutEngine:
     def __init__(self, P: Dict[str, Tensor], cfg: Optional[dict] = None, device="cuda", precision: int = 0,
                  n_rollout: int = 32, step_end: Optional[int] = None, use_graph: bool = True):
@@ -186,9 +222,13 @@ class RolloutEngine:
             self._shape, self._graph = shape, None
         st = self._st
         self._load_state(st, batch)
-        self._static = static if static is not None else self.encode_scenes(batch)
-        self._navi = self.model.navi_static(self._static["mp"], st["dest_idx"], self.R)
-        self._graph = None  # static tensors changed -> recapture
+        new_static = static if static is not None else self.encode_scenes(batch)
+        new_navi = self.model.navi_static(new_static["mp"], st["dest_idx"], self.R)
+        if self._graph is not None and _same_layout((self._static, self._navi), (new_static, new_navi)):
+            # same shapes as the captured step graph: refresh the scene tensors in place, keep the graph
+            _copy_tree((self._static, self._navi), (new_static, new_navi))
+        else:
+            self._static, self._navi, self._graph = new_static, new_navi, None
         return st
 
     def run(self, n_steps: Optional[int] = None, record=None) -> Dict[str, Tensor]:

@@ -71,6 +71,23 @@ class HotPathModel:
         self.act_w0 = torch.cat([self.P[f"action_head.mlp_mean.{t}.fc_layers.0.weight"] for t in range(3)], 0)
         self.act_b0 = torch.cat([self.P[f"action_head.mlp_mean.{t}.fc_layers.0.bias"] for t in range(3)], 0)
 
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, Tensor], d_model: int, theta_xy: float = 1e3, device="cuda",
+                        precision: int = 0) -> "HotPathModel":
+        """Runner over an arbitrary module's state_dict (used by the drop-in nn.Modules in reference_api.py)."""
+        self = cls.__new__(cls)
+        self.cfg, self.sz, self.dev, self.precision = None, None, torch.device(device), precision
+        self.d, self.W = d_model, None
+        self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in sd.items()}
+        self.fa = {}
+        for k in sd:
+            if k.endswith("in_proj_weight"):
+                p = k[: -len(".in_proj_weight")] if k.endswith(".in_proj_weight") else ""
+                P = sd if p else {f".{n}": t for n, t in sd.items()}
+                self.fa[p] = {n: t.to(self.dev) for n, t in fuse_attention(P, p, d_model).items()}
+        self.freq_rpe = ops.pe_freq_xy(d_model, theta_xy, self.dev)
+        return self
+
     # ------------------------------------------------------------------------------------------ helpers
     def lin(self, x, wname, relu=False, **kw):
         return ops.linear(x, self.P[f"{wname}.weight"], self.P[f"{wname}.bias"], relu=relu, precision=self.precision,
@@ -103,7 +120,8 @@ class HotPathModel:
     def _attend(self, fa, proj, B, S, kv0, T0, div0, K0, knn, kv1=None, T1=0, div1=1, K1=0):
         d = self.d
         return ops.knarpe_attn(proj[:, :d], proj[:, d:d + H * d], kv0, T0, div0, K0, knn["idx"], knn["inv"],
-                               knn["rel"], self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1)
+                               knn.get("rel"), self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1,
+                               emb=knn.get("emb"))
 
     def tf_layer(self, p: str, mode: str, src: Tensor, src_inv: Tensor, B: int, S: int, knn_self: dict,
                  cross: Optional[dict] = None, out: Optional[Tensor] = None) -> Tensor:
