@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU")
     ap.add_argument("--rollouts", type=int, default=32)
-    ap.add_argument("--precision", type=int, default=0, help="0 fp32 FFMA projections, 1 bf16 tcgen05 projections")
+    ap.add_argument("--precision", type=int, default=1,
+                    help="1 (default): tcgen05 kind::tf32 projections, fp32 everything else; 0: fp32 FFMA projections")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -260,7 +261,7 @@ def run_ours(args):
         roof = attention_roofline(eng, peaks)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=t_loop / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32" if args.precision == 0 else "bf16-proj/f32", data="synthetic",
+                    dtype="f32" if args.precision == 0 else "tf32", data="synthetic",
                     config=dict(workload=f"config 3: closed-loop WOSAC rollout, {n_sc} scenes x {args.rollouts} rollouts "
                                          f"per GPU, 128 agents, 1024 polylines x 20, 40 TL, 11-step history, 90 policy "
                                          f"iterations (80 counted)", scenes_per_gpu=n_sc, rollouts=args.rollouts,

@@ -1,8 +1,8 @@
 // Tensor-core projection path (tb_linear precision 1): Y = epilogue(X W^T + bias) on the 5th-gen tensor cores.
 //   tcgen05.mma kind::tf32 (fp32 operands straight from HBM, no conversion pass), fp32 accumulators in TMEM,
 //   operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a 4-stage mbarrier pipeline,
-//   warp-specialised: warps 0-3 epilogue (tcgen05.ld -> bias/ReLU/mask/residual -> global), warp 4 TMA producer,
-//   warp 5 MMA issuer + TMEM allocator. Two TMEM accumulator buffers overlap the epilogue of tile n with the MMAs of
+//   warp-specialised: warps 0-7 epilogue (tcgen05.ld -> bias/ReLU/mask/residual -> global), warp 8 TMA producer,
+//   warp 9 MMA issuer + TMEM allocator. Two TMEM accumulator buffers overlap the epilogue of tile n with the MMAs of
 //   tile n+1. Persistent CTAs (one per SM) walk the (m, n) tiles n-fastest, so an A tile is fetched from HBM once and
 //   re-read from L2 by the neighbouring SMs; the epilogue transposes each 32x32 accumulator block through swizzled
 //   shared memory so that global stores / residual loads are full 128-byte lines.
@@ -20,9 +20,11 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 32;  // BK floats = 128 bytes = one swizzle-128B row
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 16;                 // 4 warps per TMEM lane quarter, each owning BN/4 of the tile's columns
+constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
+constexpr int NUM_THREADS = (EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 2 * BN;
-constexpr int EPI_BYTES = 4 * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
+constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + 256;
 
 struct Epi {
@@ -97,14 +99,14 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const int total_tiles = ((M + BM - 1) / BM) * n_tiles;
   const int num_k = (K + BK - 1) / BK;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == EPI_WARPS && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == EPI_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -114,7 +116,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
@@ -129,7 +131,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
@@ -153,7 +155,9 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
   } else {
-    // ===== epilogue warps 0..3: TMEM lanes [32*warp, 32*warp+32) = rows m0 + 32*warp + lane =====
+    // ===== epilogue warps 0..7: warp w reads TMEM lanes [32*(w&3), +32) (rows m0 + 32*(w&3) + lane) and owns the
+    // column slice (w>>2) of the tile =====
+    const int quarter = warp & 3, half = warp >> 2;
     float* st = sE + warp * (32 * 32);  // this warp's 32x32 staging block, 16-byte chunks XOR-swizzled by row
     const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
                         (!ep.res || (((ep.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.res) & 15) == 0))) &&
@@ -165,13 +169,13 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       const int buf = lt & 1;
       mbar_wait(&tfull[buf], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int rbase = m0 + warp * 32;
+      const int rbase = m0 + quarter * 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP; c0 += 32) {
         const int cbase = n0 + c0;
         if (cbase >= N) break;  // warp-uniform
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -232,7 +236,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 5) {
+  if (warp == EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
