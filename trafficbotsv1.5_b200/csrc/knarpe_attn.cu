@@ -46,8 +46,9 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   constexpr int NC = D / 32;            // embedding components per lane (l + 32k)
   constexpr int G = (D == 128) ? 4 : 2; // neighbours per group
   constexpr int NF = D / 8;             // number of xy frequencies
-  __shared__ int s_idx[kWarps][32];
-  __shared__ float s_rel[kWarps][32][3];
+  __shared__ const float* s_ptr[kWarps][32];  // compacted valid neighbours of the current chunk: K/V row pointer,
+  __shared__ float s_rel[kWarps][32][3];      // relative pose,
+  __shared__ int s_j[kWarps][32];             // and original neighbour slot (materialised-embedding mode)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok = blockIdx.x * kWarps + warp;
@@ -55,6 +56,7 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   const int b = tok / S;
   const int Ktot = K0 + K1;
   const int hh = lane >> 3;  // own head; slot i of the per-head arrays holds head (i ^ hh)
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   float fxy, ph;
   if (D == 128) {  // one x and one y component per lane: frequency lane&15, cos for lane<16 else sin
@@ -66,8 +68,9 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   }
   const float m1 = (float)(lane + 1), m2 = (float)(lane + 33);
 
+  // u slices: component k (= lane + 32k) of head slots (0,1) and (2,3) packed for head-pair FFMA2
   float qr[NV];
-  float2 ur[H][NC / 2], z[H][NC / 2];
+  float2 u01[NC], u23[NC], z[H][NC / 2];
   {
     const float* qp = q + (size_t)tok * ldq + lane * NV;
 #pragma unroll
@@ -77,13 +80,14 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
     }
     const float* up = u + (size_t)tok * ldu + lane;
 #pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      u01[k] = make_float2(__ldg(up + (0 ^ hh) * D + 32 * k), __ldg(up + (1 ^ hh) * D + 32 * k));
+      u23[k] = make_float2(__ldg(up + (2 ^ hh) * D + 32 * k), __ldg(up + (3 ^ hh) * D + 32 * k));
+    }
+#pragma unroll
     for (int i = 0; i < H; ++i)
 #pragma unroll
-      for (int k = 0; k < NC / 2; ++k) {
-        const float* uh = up + (i ^ hh) * D + 64 * k;
-        ur[i][k] = make_float2(__ldg(uh), __ldg(uh + 32));
-        z[i][k] = make_float2(0.f, 0.f);
-      }
+      for (int k = 0; k < NC / 2; ++k) z[i][k] = make_float2(0.f, 0.f);
   }
   float ov[NV];
 #pragma unroll
@@ -91,43 +95,42 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   float mx = -INFINITY, sm = 0.f;
 
   const size_t prow = (size_t)tok * Ktot;
-  const float* kb0 = kv0 + (size_t)(b / div0) * T0 * ldkv0 + lane * NV;
-  const float* kb1 = (K1 > 0) ? kv1 + (size_t)(b / div1) * T1 * ldkv1 + lane * NV : kb0;
+  const float* kb0 = kv0 + (size_t)(b / div0) * T0 * ldkv0;
+  const float* kb1 = (K1 > 0) ? kv1 + (size_t)(b / div1) * T1 * ldkv1 : kb0;
 
   for (int c0 = 0; c0 < Ktot; c0 += 32) {
-    const int cnt = min(32, Ktot - c0);
+    // ---- stage the chunk: compact the unmasked neighbours (ballot), pad the last group with weight-0 dummies
+    const int j = c0 + lane;
+    bool valid = false;
+    const float* rptr = kb0;
+    float rx = 0.f, ry = 0.f, rw = 0.f;
+    if (j < Ktot) {
+      const size_t p = prow + j;
+      valid = invalid[p] == 0;
+      const int id = idx[p];
+      rptr = (j < K0) ? kb0 + (size_t)id * ldkv0 : kb1 + (size_t)id * ldkv1;
+      if (!FROM_EMB) { rx = rel[p * 3 + 0]; ry = rel[p * 3 + 1]; rw = rel[p * 3 + 2]; }
+    }
+    const unsigned vb = __ballot_sync(TB_FULL_MASK, valid);
+    const int nvalid = __popc(vb);
+    if (nvalid == 0) continue;  // warp-uniform
     __syncwarp();
-    if (lane < cnt) {
-      const size_t p = prow + c0 + lane;
-      s_idx[warp][lane] = invalid[p] ? -1 : idx[p];
-      if (!FROM_EMB) {
-        s_rel[warp][lane][0] = rel[p * 3 + 0];
-        s_rel[warp][lane][1] = rel[p * 3 + 1];
-        s_rel[warp][lane][2] = rel[p * 3 + 2];
-      }
-    } else {
-      s_idx[warp][lane] = -1;
-      if (!FROM_EMB) { s_rel[warp][lane][0] = 0.f; s_rel[warp][lane][1] = 0.f; s_rel[warp][lane][2] = 0.f; }
+    const int pos = valid ? __popc(vb & lt_mask) : nvalid + __popc(~vb & lt_mask);  // invalid lanes fill the tail
+    s_ptr[warp][pos] = valid ? rptr : kb0;
+    s_j[warp][pos] = valid ? j : 0;
+    if (!FROM_EMB) {
+      s_rel[warp][pos][0] = valid ? rx : 0.f;
+      s_rel[warp][pos][1] = valid ? ry : 0.f;
+      s_rel[warp][pos][2] = valid ? rw : 0.f;
     }
     __syncwarp();
 
-    for (int g0 = 0; g0 < cnt; g0 += G) {  // cnt <= 32 and 32 % G == 0: reads of s_idx stay in range
-      int id[G];
-      bool any = false;
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        id[g] = s_idx[warp][g0 + g];
-        any |= id[g] >= 0;
-      }
-      if (!any) continue;  // warp-uniform
-
-      // ---- gather (branch-free: masked neighbours read row 0 and are weighted 0)
+    for (int g0 = 0; g0 < nvalid; g0 += G) {  // 32 % G == 0: slots g0..g0+G-1 are always staged
+      // ---- gather: K and V rows of the group in flight before first use
       float kr[G][NV], vr[G][NV];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const int j = c0 + g0 + g;
-        const int row = max(id[g], 0);
-        const float* rp = (j < K0) ? kb0 + (size_t)row * ldkv0 : kb1 + (size_t)row * ldkv1;
+        const float* rp = s_ptr[warp][g0 + g] + lane * NV;
 #pragma unroll
         for (int i = 0; i < NV; i += 4) {
           float4 t = ldg4(rp + i);
@@ -143,52 +146,51 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         if (FROM_EMB) {
-          const size_t pj = prow + min(c0 + g0 + g, Ktot - 1);
-          const float* ep = emb + pj * D + lane;
+          const float* ep = emb + (prow + s_j[warp][g0 + g]) * D + lane;
 #pragma unroll
           for (int k = 0; k < NC / 2; ++k) e[g][k] = make_float2(__ldg(ep + 64 * k), __ldg(ep + 64 * k + 32));
         } else {
           const float x = s_rel[warp][g0 + g][0], y = s_rel[warp][g0 + g][1], w = s_rel[warp][g0 + g][2];
           if (D == 128) {
-            const float rw = tb_reduce_2pi(w * m1);
+            const float aw = tb_reduce_2pi(w * m1);
             e[g][0] = make_float2(__sinf(tb_reduce_2pi(x * fxy) + ph), __sinf(tb_reduce_2pi(y * fxy) + ph));
-            e[g][1 % (NC / 2)] = make_float2(__cosf(rw), __sinf(rw));
+            e[g][1 % (NC / 2)] = make_float2(__cosf(aw), __sinf(aw));
           } else {
-            const float rx = tb_reduce_2pi(x * fxy), ry = tb_reduce_2pi(y * fxy);
-            const float r1 = tb_reduce_2pi(w * m1), r2 = tb_reduce_2pi(w * m2);
-            e[g][0] = make_float2(__cosf(rx), __sinf(rx));
-            e[g][1 % (NC / 2)] = make_float2(__cosf(ry), __sinf(ry));
-            e[g][2 % (NC / 2)] = make_float2(__cosf(r1), __cosf(r2));
-            e[g][3 % (NC / 2)] = make_float2(__sinf(r1), __sinf(r2));
+            const float ax = tb_reduce_2pi(x * fxy), ay = tb_reduce_2pi(y * fxy);
+            const float a1 = tb_reduce_2pi(w * m1), a2 = tb_reduce_2pi(w * m2);
+            e[g][0] = make_float2(__cosf(ax), __sinf(ax));
+            e[g][1 % (NC / 2)] = make_float2(__cosf(ay), __sinf(ay));
+            e[g][2 % (NC / 2)] = make_float2(__cosf(a1), __cosf(a2));
+            e[g][3 % (NC / 2)] = make_float2(__sinf(a1), __sinf(a2));
           }
         }
-        float p[H];
+        // head-pair FFMA2 with the component as broadcast scalar: slots (0,1) and (2,3)
+        float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < H; ++i) {
-          float2 a = __fmul2_rn(ur[i][0], e[g][0]);
-#pragma unroll
-          for (int k = 1; k < NC / 2; ++k) a = __ffma2_rn(ur[i][k], e[g][k], a);
-          p[i] = a.x + a.y;
+        for (int k = 0; k < NC / 2; ++k) {
+          const float2 ex = make_float2(e[g][k].x, e[g][k].x), ey = make_float2(e[g][k].y, e[g][k].y);
+          p01 = __ffma2_rn(ex, u01[2 * k], p01);
+          p23 = __ffma2_rn(ex, u23[2 * k], p23);
+          p01 = __ffma2_rn(ey, u01[2 * k + 1], p01);
+          p23 = __ffma2_rn(ey, u23[2 * k + 1], p23);
         }
         // select-free halving butterfly over the permuted head slots (slot i = head i ^ hh)
-        p[0] += __shfl_xor_sync(TB_FULL_MASK, p[2], 16);
-        p[1] += __shfl_xor_sync(TB_FULL_MASK, p[3], 16);
-        float t = p[0] + __shfl_xor_sync(TB_FULL_MASK, p[1], 8);
-        float qk = 0.f;
+        p01.x += __shfl_xor_sync(TB_FULL_MASK, p23.x, 16);
+        p01.y += __shfl_xor_sync(TB_FULL_MASK, p23.y, 16);
+        float t = p01.x + __shfl_xor_sync(TB_FULL_MASK, p01.y, 8);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) qk = fmaf(qr[i], kr[g][i], qk);
-        t += qk;
+        for (int i = 0; i < NV; ++i) t = fmaf(qr[i], kr[g][i], t);
         t += __shfl_xor_sync(TB_FULL_MASK, t, 4);
         t += __shfl_xor_sync(TB_FULL_MASK, t, 2);
         t += __shfl_xor_sync(TB_FULL_MASK, t, 1);
-        lg[g] = id[g] >= 0 ? t : -INFINITY;
+        lg[g] = (g0 + g < nvalid) ? t : -INFINITY;
       }
 
       // ---- softmax of the group for the lane's own head; one rescale per group
       float gm = lg[0];
 #pragma unroll
       for (int g = 1; g < G; ++g) gm = fmaxf(gm, lg[g]);
-      const float mn = fmaxf(mx, gm);  // finite: the group has a valid neighbour (same validity for all heads)
+      const float mn = fmaxf(mx, gm);  // finite: slot g0 is a valid neighbour
       const float corr = ex2(mx - mn);
       mx = mn;
       float pg[G], ps = 0.f;
