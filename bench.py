@@ -115,12 +115,12 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     vals, sample, per_iter = [], "", 0.0
     for i in range(args.warmup + args.steps):
-        rate, sample, per_iter = cpu_rollout_rate(cores, 1, 8, 6)
+        rate, sample, per_iter = cpu_rollout_rate(cores, 1, 16, 12)
         if i >= args.warmup:
             vals.append(rate)
     v = sum(vals) / len(vals)
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=per_iter * 1e3 * 6, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                ms_per_step=per_iter * 1e3 * 12, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
                 config=dict(workload="closed-loop WOSAC rollout, 128 agents / 1024 polylines x 20 / 40 TL / 11-step "
                                      "history; CPU sample per step: " + sample),
@@ -171,8 +171,15 @@ def attention_roofline(eng, peaks):
     bytes_alg = n_valid * 2 * d * 4 + M * (d + 4 * d) * 4 * 2 + M * K * (4 + 1 + 12)
     peak = peaks.get("hbm_gbs", 6650.0)
     ach = bytes_alg / t / 1e9
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["knarpe_attn_ag_cross_bytes"]
+    except Exception:
+        pass
     return dict(bound="hbm", kernel="knarpe_attn_kernel<128,false> (agent cross-attn, K=89)", achieved=ach, peak=peak,
-                unit="GB/s", frac=ach / peak, traffic=None, us_per_launch=t * 1e6, algorithmic_bytes=bytes_alg,
+                unit="GB/s", frac=ach / peak, traffic=traffic, us_per_launch=t * 1e6,
+                note="as-issued gather bytes are served by L2 (80 % hit): DRAM traffic is ~7 % of them, so frac can exceed 1; "
+                     "the kernel's real ceiling is FP32 issue (DESIGN.md 5)", algorithmic_bytes=bytes_alg,
                 valid_pairs=n_valid, pairs=M * K, peak_source="MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback")
 
 
@@ -271,7 +278,7 @@ def run_ours(args):
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rate, sample, _ = cpu_rollout_rate(cores, 1, 8, 12)
+        rate, sample, _ = cpu_rollout_rate(cores, 1, 16, 16)
         line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample)
     if rank == 0:
         print(json.dumps(line))
