@@ -81,12 +81,13 @@ int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
  * Dense projection  Y = epilogue(X W^T + bias)  — replaces F.linear / nn.Linear call sites
  * (attention_rpe.py:96-97,147,186; transformer_rpe.py:237-238; modules/mlp.py:69).
  *   X [M,K] ld ldx;  W [N,K] (nn.Linear layout) ld K;  Y [M,N] ld ldy
- *   v = acc + bias[n]; if relu: v = max(v,0); if mask_pre[m]: v = 0; if res: v += res[m*ldr+n];
- *   if mask_post[m]: v = 0.
+ *   v = acc + bias[n]  (bias_group == 0)  or  acc + bias[(m / bias_group) * N + n]  (one bias row per group of
+ *   bias_group consecutive rows: the PointNet "concat the group max" term W_right max_g + b, polyline_encoder.py:52);
+ *   if relu: v = max(v,0); if mask_pre[m]: v = 0; if res: v += res[m*ldr+n]; if mask_post[m]: v = 0.
  * precision: 0 = fp32 FFMA (parity path), 1 = bf16 tcgen05 tensor cores with fp32 accumulate.
  * ------------------------------------------------------------------------------------------------- */
-int tb_linear(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
-              int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
+int tb_linear(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
+              int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
               int precision, void* stream);
 
 /* LayerNorm over the last dim (eps 1e-5, affine) — transformer_rpe.py:156-171. D in {128,256}. */
@@ -97,7 +98,8 @@ int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta,
  * PointNet pooling step over groups of L consecutive rows — modules/polyline_encoder.py:50-53 and
  * utils/pooling.py:18-19,38. X rows have 2*C columns; the left C columns hold relu(Linear(x)).
  * mode 0 (layer): right half <- max over the group's valid rows of the left half; invalid rows <- 0 (both halves)
- * mode 1 (final): out[g, 0:2C] = max over valid rows of X (0 if the group has no valid row)
+ * mode 1 (final): out[g, 0:C2] = max over valid rows of X (0 if the group has no valid row)
+ * mode 2: as mode 1 but written twice, out[g] = [max | max] (C2 columns each)
  *   X [G*L, 2C] ld ldx, invalid [G*L] u8, out [G, 2C] (mode 1 only). 2C in {128,256}.
  * ------------------------------------------------------------------------------------------------- */
 int tb_pointnet_pool(float* X, int ldx, const uint8_t* invalid, int G, int L, int C2, int mode, float* out, int ldo,

@@ -342,3 +342,16 @@ def test_dropin_modules_golden(golden_ops):
     assert idx.dtype == torch.int64 and rpe3.shape[-1] == 3
     with pytest.raises(AssertionError):
         R.get_tgt_knn_idx(k["inv2"].to(DEV), rp, rd, k["pose2"].shape[1], k["lim"])
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("M,N,K,g", [(1100, 64, 64, 11), (257, 128, 128, 20), (330, 40, 64, 11)])
+def test_linear_grouped_bias(M, N, K, g, prec):
+    """bias_group: one bias row per group of g consecutive rows (de-duplicated PointNet, polyline_encoder.py:52)."""
+    gen = torch.Generator().manual_seed(M)
+    x, w = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen) / K ** 0.5
+    gb = torch.randn((M + g - 1) // g, N, generator=gen)
+    ref = (x.double() @ w.double().T + gb.double().repeat_interleave(g, 0)[:M]).relu()
+    out = ops.linear(x.to(DEV), w.to(DEV), gb.to(DEV), relu=True, bias_group=g, precision=prec)
+    tol = 1e-5 if prec == 0 else 4e-3
+    close(out, ref.float(), tol, tol, f"grouped bias prec={prec}")

@@ -1,10 +1,12 @@
 // C-ABI glue: error strings, version, precision dispatch of tb_linear.
 #include "common.cuh"
 
-int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
+                  int N, int K,
                   int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                   cudaStream_t st);
-int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
+                 int N, int K,
                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                  cudaStream_t st);
 
@@ -23,15 +25,15 @@ extern "C" const char* tb_strerror(int code) {
 
 extern "C" int tb_version(void) { return 100; }
 
-extern "C" int tb_linear(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N,
-                         int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
+extern "C" int tb_linear(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy,
+                         int M, int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                          int precision, void* stream) {
   if (!X || !W || !Y) return TB_ERR_NULL;
-  if (M <= 0 || N <= 0 || K <= 0 || ldx < K || ldy < N || (res && ldr < N)) return TB_ERR_BAD_SHAPE;
+  if (M <= 0 || N <= 0 || K <= 0 || ldx < K || ldy < N || (res && ldr < N) || bias_group < 0) return TB_ERR_BAD_SHAPE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == 0)
-    return tb_linear_f32(X, ldx, W, bias, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+    return tb_linear_f32(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
   if (precision == 1)
-    return tb_linear_tc(X, ldx, W, bias, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+    return tb_linear_tc(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
   return TB_ERR_UNSUPPORTED;
 }

@@ -45,7 +45,8 @@ layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
 
 // ---- PointNet pooling (polyline_encoder.py:50-53, pooling.py:18-19,38): one warp per group of L rows.
 // mode 0: right half <- max over valid rows of left half (broadcast to valid rows); invalid rows <- 0.
-// mode 1: out[g] <- max over valid rows of all 2C columns (0 if none valid).
+// mode 1: out[g] <- max over valid rows of all C2 columns (0 if none valid); mode 2: same, written twice
+// ([m | m], the final token of the de-duplicated PointNet: max_valid([h | max]) = [max h | max h]).
 __global__ void __launch_bounds__(256)
 pointnet_pool_kernel(float* __restrict__ X, int ldx, const uint8_t* __restrict__ invalid, int G, int L, int C2,
                      int mode, float* __restrict__ out, int ldo) {
@@ -71,6 +72,7 @@ pointnet_pool_kernel(float* __restrict__ X, int ldx, const uint8_t* __restrict__
       for (int r = 0; r < L; ++r)
         if (!inv[r]) { m = fmaxf(m, xg[(size_t)r * ldx + c]); any = true; }
       out[(size_t)g * ldo + c] = any ? m : 0.f;
+      if (mode == 2) out[(size_t)g * ldo + C2 + c] = any ? m : 0.f;
     }
   }
 }
@@ -134,8 +136,8 @@ extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const f
 
 extern "C" int tb_pointnet_pool(float* X, int ldx, const uint8_t* invalid, int G, int L, int C2, int mode, float* out,
                                 int ldo, void* stream) {
-  if (!X || !invalid || (mode == 1 && !out)) return TB_ERR_NULL;
-  if (G <= 0 || L <= 0 || C2 <= 0 || (C2 & 1) || ldx < C2 || (mode != 0 && mode != 1)) return TB_ERR_BAD_SHAPE;
+  if (!X || !invalid || (mode != 0 && !out)) return TB_ERR_NULL;
+  if (G <= 0 || L <= 0 || C2 <= 0 || (C2 & 1) || ldx < C2 || mode < 0 || mode > 2) return TB_ERR_BAD_SHAPE;
   pointnet_pool_kernel<<<(G + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, ldx, invalid, G, L, C2, mode, out,
                                                                                  ldo);
   TB_CHECK_LAUNCH();

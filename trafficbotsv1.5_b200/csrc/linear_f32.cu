@@ -10,6 +10,7 @@ constexpr int BM = 128, BK = 16, NT = 256;
 
 struct Epi {
   const float* bias;
+  int bgroup;  // 0: bias[N]; g > 0: bias[(row / g) * N + n] (one bias row per group of g consecutive rows)
   int relu;
   const uint8_t* mask_pre;
   const float* res;
@@ -132,7 +133,7 @@ linear_f32_kernel(const float* __restrict__ X, int ldx, const float* __restrict_
       const int gn = n0 + (j / 4) * 64 + tx * 4 + (j & 3);
       if (gn >= N) continue;
       float v = acc[i][j];
-      if (ep.bias) v += __ldg(ep.bias + gn);
+      if (ep.bias) v += __ldg(ep.bias + (ep.bgroup ? (size_t)(gm / ep.bgroup) * N : 0) + gn);
       if (ep.relu) v = fmaxf(v, 0.f);
       if (zpre) v = 0.f;
       if (ep.res) v += ep.res[(size_t)gm * ep.ldr + gn];
@@ -144,10 +145,11 @@ linear_f32_kernel(const float* __restrict__ X, int ldx, const float* __restrict_
 
 }  // namespace
 
-int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
+                  int N, int K,
                   int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                   cudaStream_t st) {
-  Epi ep{bias, relu, mask_pre, res, ldr, mask_post};
+  Epi ep{bias, bias_group, relu, mask_pre, res, ldr, mask_post};
   const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && tb_aligned16(X) && tb_aligned16(W);
   const bool wide = N > 64;
   dim3 grid((M + BM - 1) / BM, wide ? (N + 127) / 128 : 1);

@@ -11,7 +11,8 @@
 #include <cuda.h>
 #include "common.cuh"
 
-int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
+                  int N, int K,
                   int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                   cudaStream_t st);
 
@@ -28,7 +29,7 @@ constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 staging bl
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + 256;
 
 struct Epi {
-  const float* bias; int relu; const uint8_t* mask_pre; const float* res; int ldr; const uint8_t* mask_post;
+  const float* bias; int bgroup; int relu; const uint8_t* mask_pre; const float* res; int ldr; const uint8_t* mask_post;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,7 +162,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     float* st = sE + warp * (32 * 32);  // this warp's 32x32 staging block, 16-byte chunks XOR-swizzled by row
     const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
                         (!ep.res || (((ep.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.res) & 15) == 0))) &&
-                        (!ep.bias || ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0));
+                        (!ep.bias || (((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) && (!ep.bgroup || (N & 3) == 0)));
     const int rsub = lane >> 3, cc = lane & 7;  // store phase: lane -> (row i*4 + rsub, 16-byte chunk cc)
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
@@ -170,6 +171,9 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       mbar_wait(&tfull[buf], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int rbase = m0 + quarter * 32;
+      // grouped bias: this thread's accumulator row (TMEM lane) is fixed for the tile -> one division per tile
+      const float* gb_row = (ep.bgroup && rbase + lane < M)
+                                ? ep.bias + (size_t)((rbase + lane) / ep.bgroup) * N : nullptr;
 #pragma unroll 1
       for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP; c0 += 32) {
         const int cbase = n0 + c0;
@@ -186,6 +190,22 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (gb_row) {  // add the group's bias row while the accumulators are still row-per-thread
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (vec_ok && cbase + 32 <= N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(gb_row + cbase + j));
+              r[j] = __float_as_uint(__uint_as_float(r[j]) + b4.x);
+              r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b4.y);
+              r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b4.z);
+              r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b4.w);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (cbase + j + q < N) r[j + q] = __float_as_uint(__uint_as_float(r[j + q]) + __ldg(gb_row + cbase + j + q));
+            }
+          }
+        }
         // registers (row = lane) -> swizzled staging block
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -195,7 +215,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (vec_ok && cbase + 32 <= N) {
           const int col = cbase + cc * 4;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.bias) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+          if (ep.bias && !ep.bgroup) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + rsub, row = rbase + rr;
@@ -218,7 +238,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             const int row = rbase + i, col = cbase + lane;
             if (row < M && col < N) {
               float t = st[i * 32 + ((((lane >> 2) ^ (i & 7)) << 2) | (lane & 3))];
-              if (ep.bias) t += __ldg(ep.bias + col);
+              if (ep.bias && !ep.bgroup) t += __ldg(ep.bias + col);
               if (ep.relu) t = fmaxf(t, 0.f);
               if (ep.mask_pre && ep.mask_pre[row]) t = 0.f;
               if (ep.res) t += ep.res[(size_t)row * ep.ldr + col];
@@ -273,11 +293,12 @@ bool make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, in
 
 }  // namespace
 
-int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
+                 int N, int K,
                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                  cudaStream_t st) {
   const bool ok = (K % 4 == 0) && (ldx % 4 == 0) && N >= 32 && tb_aligned16(X) && tb_aligned16(W);
-  if (!ok) return tb_linear_f32(X, ldx, W, bias, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+  if (!ok) return tb_linear_f32(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
   CUtensorMap mapA, mapB;
   if (!make_map(&mapA, X, M, K, ldx, BM) || !make_map(&mapB, W, N, K, K, BN)) return TB_ERR_CUDA;
   static bool attr_set = false;
@@ -297,7 +318,7 @@ int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, flo
   }
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms ? total : num_sms;  // persistent: one CTA per SM
-  Epi ep{bias, relu, mask_pre, res, ldr, mask_post};
+  Epi ep{bias, bias_group, relu, mask_pre, res, ldr, mask_post};
   linear_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
   TB_CHECK_LAUNCH();
   return TB_OK;

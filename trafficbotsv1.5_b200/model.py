@@ -104,13 +104,28 @@ class HotPathModel:
 
     def pointnet(self, x: Tensor, row_invalid: Tensor, G: int, Lg: int, prefix: str) -> Tensor:
         """polyline_encoder.py:50-53 + pooling.py:18-19,38. x [G*L, d]."""
+        # De-duplicated form: cat(h, max_g) W^T = h W_left^T + (max_g W_right^T), the second term being one row per
+        # group -> a [G, d/2] GEMM whose result enters the big GEMM as a grouped bias. Rows stay d/2 wide, the
+        # broadcast copy of the max is never written, and the final token is [max h | max h]. Values on invalid rows
+        # differ from the reference's (zeros) but are masked out of every max, exactly like there.
         half = self.d // 2
-        for i in range(3):
-            xn = torch.empty_like(x)
-            self.lin(x, f"{prefix}.mlp_layers.{i}.fc_layers.0", relu=True, out=xn[:, :half])
-            ops.pointnet_pool(xn, row_invalid, G, Lg, 0)
-            x = xn
-        return ops.pointnet_pool(x, row_invalid, G, Lg, 1)
+        h = self.lin(x, f"{prefix}.mlp_layers.0.fc_layers.0", relu=True)
+        for i in (1, 2):
+            m = ops.pointnet_pool(h, row_invalid, G, Lg, 1)
+            w_l, w_r = self._pointnet_split(prefix, i)
+            gb = ops.linear(m, w_r, self.P[f"{prefix}.mlp_layers.{i}.fc_layers.0.bias"], precision=self.precision)
+            h = ops.linear(h, w_l, gb, relu=True, bias_group=Lg, precision=self.precision)
+        return ops.pointnet_pool(h, row_invalid, G, Lg, 2)
+
+    def _pointnet_split(self, prefix: str, i: int):
+        key = f"{prefix}.{i}"
+        if not hasattr(self, "_pn_split"):
+            self._pn_split = {}
+        if key not in self._pn_split:
+            w = self.P[f"{prefix}.mlp_layers.{i}.fc_layers.0.weight"]
+            half = w.shape[1] // 2
+            self._pn_split[key] = (w[:, :half].contiguous(), w[:, half:].contiguous())
+        return self._pn_split[key]
 
     def kv_table(self, feat: Tensor, layer_prefix: str, norm: str, attn: str = "attn") -> Tensor:
         """K/V rows of a target table for one layer: W_kv LN(x) + b  (project-once-then-gather)."""

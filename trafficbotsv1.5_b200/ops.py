@@ -93,7 +93,7 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
 
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False, mask_pre: Optional[Tensor] = None,
            res: Optional[Tensor] = None, mask_post: Optional[Tensor] = None, out: Optional[Tensor] = None,
-           precision: int = 0) -> Tensor:
+           precision: int = 0, bias_group: int = 0) -> Tensor:
     """Y = epilogue(X W^T + b) on 2-D row-strided views (see tb_linear)."""
     assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.dtype == torch.float32
     M, K = x.shape
@@ -104,7 +104,9 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False,
     assert out.stride(1) == 1 and out.shape[0] == M and out.shape[1] == N
     if res is not None:
         assert res.stride(1) == 1 and res.shape == (M, N)
-    L.check(L.load().tb_linear(L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), L.ptr(out), out.stride(0), M, N, K,
+    if bias_group:
+        assert b is not None and b.is_contiguous() and b.shape == ((M + bias_group - 1) // bias_group, N), b.shape
+    L.check(L.load().tb_linear(L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), bias_group, L.ptr(out), out.stride(0), M, N, K,
                                int(relu), L.ptr(_u8(mask_pre)), L.ptr(res), res.stride(0) if res is not None else 0,
                                L.ptr(_u8(mask_post)), precision, L.stream()), "tb_linear")
     _count()
@@ -123,10 +125,11 @@ def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, out: Optional[Tensor] = No
 
 
 def pointnet_pool(x: Tensor, invalid: Tensor, G: int, Lg: int, mode: int) -> Optional[Tensor]:
-    """x [G*L, 2C] modified in place (mode 0) / pooled to [G, 2C] (mode 1)."""
+    """x [G*L, C2] modified in place (mode 0) / max-pooled over valid rows to [G, C2] (mode 1) or [G, 2*C2] = [m|m]
+    (mode 2)."""
     assert x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == G * Lg
     C2 = x.shape[1]
-    out = torch.empty(G, C2, dtype=torch.float32, device=x.device) if mode == 1 else None
+    out = torch.empty(G, C2 * mode, dtype=torch.float32, device=x.device) if mode else None
     inv = _u8(invalid)
     assert inv.is_contiguous() and inv.numel() == G * Lg
     L.check(L.load().tb_pointnet_pool(L.ptr(x), x.stride(0), L.ptr(inv), G, Lg, C2, mode, L.ptr(out),
