@@ -2,17 +2,61 @@
 // Reference behaviour: utils/rpe.py:9-37 (get_rel_pose) + :62-90 (get_tgt_knn_idx).
 //
 // One warp per source token. The scene's targets (x, y, yaw, invalid) are staged once per CTA in shared
-// memory and shared by all of the CTA's source rows; each lane keeps T/32 candidate distances in registers
-// (never materialising the [S,T,3] rel-pose / [S,T] distance tensors of the reference). The K-th smallest
-// distance is found by bisection on the fp32 bit pattern (non-negative floats order like unsigned ints) with
-// one REDUX per probe; winners are compacted with ballots in ascending target-index order and their
-// relative pose is recomputed from shared memory.
+// memory and shared by all of the CTA's source rows; each lane keeps T/32 candidate keys (squared distances) in
+// registers (never materialising the [S,T,3] rel-pose / [S,T] distance tensors of the reference).
+// Selection: (1) prune — the per-lane two smallest keys give 64 candidates whose maximum U bounds the K-th smallest
+// from above, so only keys <= U (typically ~15 % of T) survive and are ballot-compacted into a per-warp list;
+// (2) the K-th smallest of the survivors is found by bisection on the fp32 bit pattern (non-negative floats order
+// like unsigned ints) with one REDUX per probe; (3) winners are compacted in ascending target-index order (ties: lower
+// index) and their rotated relative pose / exact distance are evaluated from shared memory. Rows whose survivor list
+// would overflow (many invalid targets, K > 64, T <= 128) take the general path: bisection over all T keys.
 #include "common.cuh"
 
 namespace {
 
 constexpr int kWarps = 8;
 constexpr int kRowsPerWarp = 8;  // source rows per warp => 64 rows per CTA amortise the target staging
+constexpr int kCap = 12;         // pruned candidate list: up to kCap*32 survivors per row
+
+// K-th smallest of the warp's keys (N per lane) by bisection on the bit pattern; returns tau and #keys < tau.
+template <int N>
+__device__ __forceinline__ uint32_t kth_smallest(const uint32_t (&key)[N], int K, uint32_t hi, int* c_lt_out) {
+  uint32_t lo = 0u;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) c += (key[i] <= mid);
+    c = __reduce_add_sync(TB_FULL_MASK, c);
+    if (c >= K) hi = mid; else lo = mid + 1u;
+  }
+  int c_lt = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) c_lt += (key[i] < lo);
+  *c_lt_out = __reduce_add_sync(TB_FULL_MASK, c_lt);
+  return lo;
+}
+
+struct RowCtx {
+  float sx, sy, syaw, sn, cs, dist_limit;
+  const float *tx, *ty, *tyaw;
+  const uint8_t* tinv;
+  bool sinv;
+  int32_t* out_idx; uint8_t* out_invalid; float* out_rel;
+  size_t obase;
+};
+
+// winner t -> outputs (relative pose in the source frame, utils/rpe.py:26-36; invalid flag :85-86)
+__device__ __forceinline__ void emit(const RowCtx& c, int pos, int t) {
+  const float dx = c.tx[t] - c.sx, dy = c.ty[t] - c.sy;
+  const float lx = fmaf(dx, c.cs, dy * c.sn), ly = fmaf(dy, c.cs, -dx * c.sn);
+  const bool dead = c.sinv || c.tinv[t];
+  const float d = dead ? __int_as_float(0x7f800000) : sqrtf(fmaf(lx, lx, ly * ly));
+  c.out_idx[c.obase + pos] = t;
+  c.out_invalid[c.obase + pos] = (uint8_t)((c.tinv[t] != 0) | (d > c.dist_limit));
+  float* r = c.out_rel + (c.obase + pos) * 3;
+  r[0] = lx; r[1] = ly; r[2] = c.tyaw[t] - c.syaw;
+}
 
 template <int TPL>
 __global__ void __launch_bounds__(kWarps * 32)
@@ -25,6 +69,9 @@ knn_select_kernel(const float* __restrict__ src_pose, const uint8_t* __restrict_
   float* ty = tx + T;
   float* tyaw = ty + T;
   uint8_t* tinv = reinterpret_cast<uint8_t*>(tyaw + T);
+  // pruned candidate lists (fast path), one per warp: keys then target indices
+  uint32_t* ckey_all = reinterpret_cast<uint32_t*>(smem + 3 * T + ((T + 15) / 16) * 4);
+  uint16_t* cidx_all = reinterpret_cast<uint16_t*>(ckey_all + kWarps * kCap * 32);
 
   const int b = blockIdx.y;
   const int bt = b / div;
@@ -41,74 +88,104 @@ knn_select_kernel(const float* __restrict__ src_pose, const uint8_t* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int row0 = (blockIdx.x * kWarps + warp) * kRowsPerWarp;
+  uint32_t* ckey = ckey_all + warp * kCap * 32;
+  uint16_t* cidx = cidx_all + warp * kCap * 32;
 
   for (int rr = 0; rr < kRowsPerWarp; ++rr) {
     const int s = row0 + rr;
     if (s >= S) break;  // warp-uniform
     const size_t row = (size_t)b * S + s;
-    const float sx = src_pose[row * 3 + 0], sy = src_pose[row * 3 + 1], syaw = src_pose[row * 3 + 2];
-    const bool sinv = src_invalid[row] != 0;
-    float sn, cs;
-    sincosf(syaw, &sn, &cs);
+    RowCtx c;
+    c.sx = src_pose[row * 3 + 0]; c.sy = src_pose[row * 3 + 1]; c.syaw = src_pose[row * 3 + 2];
+    c.sinv = src_invalid[row] != 0;
+    sincosf(c.syaw, &c.sn, &c.cs);
+    c.dist_limit = dist_limit; c.tx = tx; c.ty = ty; c.tyaw = tyaw; c.tinv = tinv;
+    c.out_idx = out_idx; c.out_invalid = out_invalid; c.out_rel = out_rel;
+    c.obase = row * (size_t)ldk + koff;
 
-    // distances of this lane's candidates t = i*32 + lane
+    if (c.sinv) {  // invalid source: every distance is +inf, the (always masked) fillers are targets 0..K-1
+      for (int pos = lane; pos < K; pos += 32) emit(c, pos, pos);
+      continue;
+    }
+
+    // selection keys of this lane's candidates t = i*32 + lane: squared distance (the rotation into the source frame
+    // preserves it; the winners' rotated pose and exact distance are evaluated in emit()), +inf if either end invalid
     uint32_t key[TPL];
 #pragma unroll
     for (int i = 0; i < TPL; ++i) {
       const int t = i * 32 + lane;
       uint32_t k = 0xffffffffu;  // beyond T: never selected (K < T)
       if (t < T) {
-        float d = __int_as_float(0x7f800000);
-        if (!sinv && !tinv[t]) {
-          const float dx = tx[t] - sx, dy = ty[t] - sy;
-          const float lx = fmaf(dx, cs, dy * sn);
-          const float ly = fmaf(dy, cs, -dx * sn);
-          d = sqrtf(fmaf(lx, lx, ly * ly));
-        }
-        k = __float_as_uint(d);
+        const float dx = tx[t] - c.sx, dy = ty[t] - c.sy;
+        k = (c.sinv || tinv[t]) ? 0x7f800000u : __float_as_uint(fmaf(dx, dx, dy * dy));
       }
       key[i] = k;
     }
 
-    // smallest tau with count(key <= tau) >= K
-    uint32_t lo = 0u, hi = 0x7f800000u;
-    while (lo < hi) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      int c = 0;
+    bool done = false;
+    if (TPL >= 8 && K <= 64) {
+      // ---- prune: the 64 (32) per-lane two-smallest (smallest) keys bound the K-th smallest from above
+      uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
 #pragma unroll
-      for (int i = 0; i < TPL; ++i) c += (key[i] <= mid);
-      c = __reduce_add_sync(TB_FULL_MASK, c);
-      if (c >= K) hi = mid; else lo = mid + 1u;
+      for (int i = 0; i < TPL; ++i) {
+        m2 = min(m2, max(m1, key[i]));
+        m1 = min(m1, key[i]);
+      }
+      const uint32_t U = __reduce_max_sync(TB_FULL_MASK, K <= 32 ? m1 : m2);
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < TPL; ++i) cnt += (key[i] <= U);
+      cnt = __reduce_add_sync(TB_FULL_MASK, cnt);
+      if (cnt <= kCap * 32) {  // warp-uniform
+        __syncwarp();
+        int base = 0;
+#pragma unroll
+        for (int i = 0; i < TPL; ++i) {  // compaction keeps ascending target-index order
+          const bool sel = key[i] <= U;
+          const unsigned sb = __ballot_sync(TB_FULL_MASK, sel);
+          if (sel) {
+            const int p = base + __popc(sb & lt_mask);
+            ckey[p] = key[i];
+            cidx[p] = (uint16_t)(i * 32 + lane);
+          }
+          base += __popc(sb);
+        }
+        __syncwarp();
+        uint32_t ck[kCap];
+#pragma unroll
+        for (int j = 0; j < kCap; ++j) ck[j] = (j * 32 + lane < cnt) ? ckey[j * 32 + lane] : 0xffffffffu;
+        int c_lt;
+        const uint32_t tau = kth_smallest<kCap>(ck, K, U, &c_lt);
+        const int need_ties = K - c_lt;
+        int n_out = 0, n_tie = 0;
+#pragma unroll
+        for (int j = 0; j < kCap; ++j) {
+          if (j * 32 >= cnt) break;  // warp-uniform
+          const bool is_tie = ck[j] == tau;
+          const unsigned tie_b = __ballot_sync(TB_FULL_MASK, is_tie);
+          const bool sel = (ck[j] < tau) || (is_tie && n_tie + __popc(tie_b & lt_mask) < need_ties);
+          const unsigned sel_b = __ballot_sync(TB_FULL_MASK, sel);
+          if (sel) emit(c, n_out + __popc(sel_b & lt_mask), cidx[j * 32 + lane]);
+          n_out += __popc(sel_b);
+          n_tie += __popc(tie_b);
+        }
+        done = true;
+      }
     }
-    const uint32_t tau = lo;
-    int c_lt = 0;
-#pragma unroll
-    for (int i = 0; i < TPL; ++i) c_lt += (key[i] < tau);
-    c_lt = __reduce_add_sync(TB_FULL_MASK, c_lt);
-    const int need_ties = K - c_lt;  // >= 1
+    if (done) continue;
 
-    // compaction in ascending target index (i-major, then lane)
+    // ---- general path: bisection over all T keys
+    int c_lt;
+    const uint32_t tau = kth_smallest<TPL>(key, K, 0x7f800000u, &c_lt);
+    const int need_ties = K - c_lt;  // >= 1
     int n_out = 0, n_tie = 0;
-    const size_t obase = row * (size_t)ldk + koff;
 #pragma unroll
-    for (int i = 0; i < TPL; ++i) {
+    for (int i = 0; i < TPL; ++i) {  // compaction in ascending target index (i-major, then lane)
       const bool is_tie = key[i] == tau;
       const unsigned tie_b = __ballot_sync(TB_FULL_MASK, is_tie);
-      const int tie_rank = n_tie + __popc(tie_b & lt_mask);
-      const bool sel = (key[i] < tau) || (is_tie && tie_rank < need_ties);
+      const bool sel = (key[i] < tau) || (is_tie && n_tie + __popc(tie_b & lt_mask) < need_ties);
       const unsigned sel_b = __ballot_sync(TB_FULL_MASK, sel);
-      if (sel) {
-        const int pos = n_out + __popc(sel_b & lt_mask);
-        const int t = i * 32 + lane;
-        const float d = __uint_as_float(key[i]);
-        const float dx = tx[t] - sx, dy = ty[t] - sy;
-        out_idx[obase + pos] = t;
-        out_invalid[obase + pos] = (uint8_t)((tinv[t] != 0) | (d > dist_limit));
-        float* r = out_rel + (obase + pos) * 3;
-        r[0] = fmaf(dx, cs, dy * sn);
-        r[1] = fmaf(dy, cs, -dx * sn);
-        r[2] = tyaw[t] - syaw;
-      }
+      if (sel) emit(c, n_out + __popc(sel_b & lt_mask), i * 32 + lane);
       n_out += __popc(sel_b);
       n_tie += __popc(tie_b);
     }
@@ -120,7 +197,7 @@ int launch(const float* src_pose, const uint8_t* src_invalid, const float* tgt_p
            int B, int S, int T, int div, int K, float dist_limit, int32_t* out_idx, uint8_t* out_invalid,
            float* out_rel, int ldk, int koff, cudaStream_t st) {
   dim3 grid((S + kWarps * kRowsPerWarp - 1) / (kWarps * kRowsPerWarp), B);
-  size_t smem = (size_t)T * 13 + 16;
+  size_t smem = (size_t)T * 12 + ((T + 15) / 16) * 16 + (size_t)kWarps * kCap * 32 * 6;
   knn_select_kernel<TPL><<<grid, kWarps * 32, smem, st>>>(src_pose, src_invalid, tgt_pose, tgt_invalid, S, T, div, K,
                                                          dist_limit, out_idx, out_invalid, out_rel, ldk, koff);
   TB_CHECK_LAUNCH();
