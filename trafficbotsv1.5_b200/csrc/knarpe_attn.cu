@@ -23,7 +23,16 @@
 
 namespace {
 
-constexpr int kWarps = 8;
+#ifndef TB_ATTN_WARPS
+#define TB_ATTN_WARPS 8
+#endif
+#ifndef TB_ATTN_MINB
+#define TB_ATTN_MINB 2
+#endif
+#ifndef TB_ATTN_G
+#define TB_ATTN_G 4
+#endif
+constexpr int kWarps = TB_ATTN_WARPS;
 constexpr int H = 4;
 
 __device__ __forceinline__ float ex2(float x) {
@@ -33,7 +42,7 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 template <int D, bool FROM_EMB>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, TB_ATTN_MINB)
 knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ u, int ldu,
                    const float* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
                    const float* __restrict__ kv1, int ldkv1, int T1, int div1, int K1,
@@ -44,7 +53,7 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
                    uint8_t* __restrict__ out_none_valid) {
   constexpr int NV = D / 32;            // q/k/v floats per lane
   constexpr int NC = D / 32;            // embedding components per lane (l + 32k)
-  constexpr int G = (D == 128) ? 4 : 2; // neighbours per group
+  constexpr int G = (D == 128) ? TB_ATTN_G : 2; // neighbours per group
   constexpr int NF = D / 8;             // number of xy frequencies
   __shared__ const float* s_ptr[kWarps][32];  // compacted valid neighbours of the current chunk: K/V row pointer,
   __shared__ float s_rel[kWarps][32][3];      // relative pose,

@@ -12,7 +12,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-SO_PATH = os.path.join(_PKG, "libtbknarpe.so")
+SO_PATH = os.environ.get("TB_LIB", os.path.join(_PKG, "libtbknarpe.so"))
 _SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu",
             "rollout_step.cu"]
 _lib = None
@@ -33,6 +33,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-Xcompiler", "-fPIC", "-I", os.path.join(_ROOT, "include"), "-lcuda", "-o", SO_PATH] + src
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    extra = os.environ.get("TB_NVCC_FLAGS")  # tuning experiments only (e.g. -DTB_ATTN_G=2)
+    if extra:
+        cmd[1:1] = extra.split()
     subprocess.run(cmd, check=True)
     return SO_PATH
 
