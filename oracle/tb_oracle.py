@@ -423,8 +423,159 @@ def check_dest_reached(valid, pose, dest, dest_reached) -> Tensor:
     return (~dest_reached) & valid & ((lane & pos_ok & rot_ok) | (edge & pos_ok))
 
 
+# --------------------------------------------------------------------------------------------------
+# logging-only traffic-rule checks: utils/traffic_rule_checker.py:119-274, utils/wosac_collision.py
+# --------------------------------------------------------------------------------------------------
+def ag_bbox(pose: Tensor, size: Tensor) -> Tensor:
+    """get_ag_bbox, wosac_collision.py:22-48. pose [B,A,3], size [B,A,2] (length, width) -> corners [B,A,4,2] (CCW)."""
+    c, s = pose[..., 2].cos(), pose[..., 2].sin()
+    f, r = torch.stack([c, s], -1), torch.stack([s, -c], -1)
+    of, orr = 0.5 * size[..., [0]] * f, 0.5 * size[..., [1]] * r
+    off = torch.stack([of - orr, -of - orr, -of + orr, of + orr], 2)
+    return pose[:, :, None, :2] + off
+
+
+def check_collided(valid, bbox, invalid_pair_mask) -> Tensor:
+    """_check_collided, traffic_rule_checker.py:119-149 (separating-axis test on the box edge lines)."""
+    nxt = bbox.roll(-1, dims=2)
+    line = torch.cat([nxt[..., [1]] - bbox[..., [1]], bbox[..., [0]] - nxt[..., [0]],
+                      nxt[..., [0]] * bbox[..., [1]] - nxt[..., [1]] * bbox[..., [0]]], -1)      # [B,A,4,3]
+    pt = torch.cat([bbox, torch.ones_like(bbox[..., [0]])], -1)                                  # [B,A,4,3]
+    outside = (line[:, :, None, :, None, :] * pt[:, None, :, None, :, :]).sum(-1) > 0            # [B,A,A,4,4]
+    no_col = outside.all(-1).any(-1)
+    no_col = no_col | no_col.transpose(1, 2)
+    no_col = no_col | invalid_pair_mask | ~(valid[:, :, None] & valid[:, None, :])
+    return ~no_col.all(-1)
+
+
+def _signed_dist_origin_to_polygon(poly: Tensor) -> Tensor:
+    """_signed_distance_from_point_to_convex_polygon with query = origin, wosac_collision.py:51-113. poly [..., n, 2]."""
+    nxt = poly.roll(-1, dims=-2)
+    ev = nxt - poly
+    el = torch.norm(ev, dim=-1)
+    tan = ev / el.unsqueeze(-1)
+    nrm = torch.stack([-tan[..., 1], tan[..., 0]], -1)
+    v2q = -poly
+    vd = torch.norm(v2q, dim=-1)
+    sperp = (-nrm * v2q).sum(-1)
+    inside = (sperp <= 0).all(-1)
+    prop = (tan * v2q).sum(-1) / el
+    on_edge = (prop >= 0.0) & (prop <= 1.0)
+    ed = torch.where(on_edge, sperp.abs(), torch.zeros_like(sperp) + 1e10)
+    md = torch.cat([ed, vd], -1).amin(-1)
+    return torch.where(inside, -md, md)
+
+
+def _minkowski_sum(box1: Tensor, box2: Tensor) -> Tensor:
+    """_minkowski_sum_of_box_and_box_points + _get_downmost_edge_in_box, wosac_collision.py:140-192. [..., 4, 2]."""
+    def downmost(box):
+        i0 = torch.argmin(box[..., 1], dim=-1, keepdim=True)
+        st = torch.gather(box, -2, i0[..., None].expand(*i0.shape, 2))
+        en = torch.gather(box, -2, ((i0 + 1) % 4)[..., None].expand(*i0.shape, 2))
+        e = en - st
+        return i0, e / torch.norm(e, dim=-1, keepdim=True)
+    o1 = torch.tensor([0, 0, 1, 1, 2, 2, 3, 3])
+    o2 = torch.tensor([0, 1, 1, 2, 2, 3, 3, 0])
+    s1, d1 = downmost(box1)
+    s2, d2 = downmost(box2)
+    cond = ((d1[..., 0] * d2[..., 1] - d1[..., 1] * d2[..., 0]) >= 0.0).expand(*s1.shape[:-1], 8)
+    i1 = (torch.where(cond, o2, o1) + s1) % 4
+    i2 = (torch.where(cond, o1, o2) + s2) % 4
+    g = lambda b, i: torch.gather(b, -2, i[..., None].expand(*i.shape, 2))  # noqa: E731
+    return g(box1, i1) + g(box2, i2)
+
+
+def check_collided_wosac(pose, size, valid) -> Tensor:
+    """check_collided_wosac, wosac_collision.py:196-239 (Minkowski-difference signed distance of rounded boxes)."""
+    B, A, _ = pose.shape
+    shrink = torch.minimum(size[:, :, 0], size[:, :, 1]) * 0.7 / 2.0
+    corners = ag_bbox(pose, size[:, :, :2] - 2.0 * shrink.unsqueeze(-1))
+    ev = corners[:, :, None].expand(-1, -1, A, -1, -1)
+    al = corners[:, None].expand(-1, A, -1, -1, -1)
+    sd = _signed_dist_origin_to_polygon(_minkowski_sum(ev, -1.0 * al))
+    sd = sd - shrink[:, None, :] - shrink[:, :, None]
+    bad = ~(valid[:, None, :] & valid[:, :, None]) | torch.eye(A, dtype=torch.bool)[None]
+    return sd.masked_fill(bad, 1e10).amin(2) < 0.0
+
+
+def _ccw(a, b, c):
+    return (c[..., 1] - a[..., 1]) * (b[..., 0] - a[..., 0]) > (b[..., 1] - a[..., 1]) * (c[..., 0] - a[..., 0])
+
+
+def check_run_road_edge(valid, bbox, veh, edge, edge_valid) -> Tensor:
+    """_check_run_road_edge, traffic_rule_checker.py:152-173. edge [B,E,2,2], edge_valid [B,E]."""
+    nxt = bbox.roll(-1, dims=2)
+    a, b = bbox[:, :, None], nxt[:, :, None]                       # [B,A,1,4,2]
+    c, d = edge[:, None, :, None, 0], edge[:, None, :, None, 1]   # [B,1,E,1,2]
+    hit = (_ccw(a, c, d) != _ccw(b, c, d)) & (_ccw(a, b, c) != _ccw(a, b, d))
+    return (hit.any(-1) & edge_valid[:, None]).any(-1) & valid & veh
+
+
+def check_run_red_light(valid, pose, motion, tl_valid, tl_pose, tl_state, size, veh) -> Tensor:
+    """_check_run_red_light, traffic_rule_checker.py:176-218. size = UNscaled ag_size [B,A,>=2]."""
+    hc, hs = pose[..., 2].cos(), pose[..., 2].sin()
+    hf, hr = torch.stack([hc, hs], -1)[:, :, None], torch.stack([hs, -hc], -1)[:, :, None]
+    ln, wd = size[:, :, [0]] * 0.5 * 0.6, size[:, :, [1]] * 0.5 * 1.8
+    x0 = pose[:, :, None, :2]
+    x1 = x0 + 0.1 * motion[:, :, None, [0]] * hf
+    tp = tl_pose[:, None, :, :2]
+    ins = lambda x: (((tp - x) * hf).sum(-1).abs() < ln) & (((tp - x) * hr).sum(-1).abs() < wd)  # noqa: E731
+    m = (valid & veh)[:, :, None] & (tl_valid & tl_state[:, :, 1])[:, None]
+    return (ins(x0) & ~ins(x1) & m).any(-1)
+
+
+def check_passive(valid, pose, motion, tl_valid, tl_pose, tl_state, lane, lane_valid, veh, counter):
+    """_check_passive, traffic_rule_checker.py:221-274. Returns (passive_this_step, new counter)."""
+    A = pose.shape[1]
+    close = ((torch.norm(pose[:, :, None, :2] - lane[:, None], dim=-1) < 2) & lane_valid[:, None]).any(-1)
+    slow = motion[:, :, 0] < 5
+    hf = torch.stack([pose[..., 2].cos(), pose[..., 2].sin()], -1)[:, :, None]
+    mtl = (tl_valid & tl_state[:, :, [0, 1, 2, 4]].any(-1))[:, None]
+    tv = tl_pose[:, None, :, :2] - pose[:, :, None, :2]
+    tn = torch.norm(tv, dim=-1)
+    red = ((tn < 10) & (((hf * tv).sum(-1) / tn) > 0.95) & mtl).any(-1)
+    av = pose[:, None, :, :2] - pose[:, :, None, :2]
+    an = torch.norm(av, dim=-1)
+    ahead = ((an < 10) & (((hf * av).sum(-1) / an) > 0.95) & valid[:, None] & valid[:, :, None]
+             & ~torch.eye(A, dtype=torch.bool)[None]).any(-1)
+    p = valid & veh & close & slow & ~red & ~ahead
+    counter = (counter + p) * p
+    return counter > 20, counter
+
+
+class RuleCheckOracle:
+    """State + per-step evaluation of the five logging-only checks (TrafficRuleChecker.__init__ / check,
+    traffic_rule_checker.py:10-84, 343-451). Inputs are the rollout-replicated tensors."""
+
+    def __init__(self, mp_valid, mp_type, mp_pos, mp_dir, ag_type, ag_size, tl_valid, tl_pose, size_scale=1.1):
+        self.size_raw = ag_size
+        self.size = ag_size[..., :2] * size_scale                                                   # :27
+        self.veh = ag_type[:, :, 0]
+        A = ag_type.shape[1]
+        ped = ag_type[:, :, 1]
+        self.pair_invalid = torch.eye(A, dtype=torch.bool)[None] | (ped[:, None] & ped[:, :, None])  # :48-51
+        self.edge_valid = (mp_valid & mp_type[:, :, [4, 5, 7]].any(-1, keepdim=True)).flatten(1, 2)  # :476-478
+        self.edge = torch.stack([mp_pos, mp_pos + mp_dir], -2).flatten(1, 2)
+        self.lane_valid = (mp_valid & mp_type[:, :, :3].any(-1, keepdim=True)).flatten(1, 2)         # :493-495
+        self.lane = mp_pos.flatten(1, 2)
+        self.tl_valid, self.tl_pose = tl_valid, tl_pose
+        self.counter = torch.zeros(ag_type.shape[:2])
+
+    def check(self, valid, pose, motion, tl_state) -> Dict[str, Tensor]:
+        bbox = ag_bbox(pose, self.size)
+        out = dict(collided=check_collided(valid, bbox, self.pair_invalid),
+                   collided_wosac=check_collided_wosac(pose, self.size, valid),
+                   run_road_edge=check_run_road_edge(valid, bbox, self.veh, self.edge, self.edge_valid),
+                   run_red_light=check_run_red_light(valid, pose, motion, self.tl_valid, self.tl_pose, tl_state,
+                                                     self.size_raw, self.veh))
+        out["passive"], self.counter = check_passive(valid, pose, motion, self.tl_valid, self.tl_pose, tl_state,
+                                                     self.lane, self.lane_valid, self.veh, self.counter)
+        return out
+
+
 def rollout(P, cfg, sz, dyn, rcfg, batch: Dict[str, Tensor], n_rollout: int, step_end: Optional[int] = None,
-            mp: Optional[dict] = None, tl: Optional[dict] = None, record=None) -> Dict[str, Tensor]:
+            mp: Optional[dict] = None, tl: Optional[dict] = None, record=None, rule_checks: bool = False
+            ) -> Dict[str, Tensor]:
     """Restated WOSAC driver: test_step -> joint_future_pred -> rollout -> forward
     (pl_modules/waymo_motion.py:843-876, 439-524, 206-311, 118-204) with the feedback-relevant subset of
     TrafficRuleChecker.check (outside_map, dest_reached; traffic_rule_checker.py:343-451) and fixed
@@ -457,6 +608,12 @@ def rollout(P, cfg, sz, dyn, rcfg, batch: Dict[str, Tensor], n_rollout: int, ste
     tl_state = tl_gt[:, :, 0]
     policy = PolicyOracle(P, cfg, sz)
     out = dict(pred_valid=[], pred_pose=[], pred_motion=[], tl_state=[], action_mean=[])
+    checker = None
+    if rule_checks:
+        checker = RuleCheckOracle(rep(batch["map/valid"]), rep(batch["map/type"]), rep(batch["map/pos"][..., :2]),
+                                  rep(batch["map/dir"][..., :2]), ag_type, rep(batch["ref/ag_size"]),
+                                  rep(batch["sc/tl_valid"]), rep(batch["sc/tl_pose"]))
+        out.update({k: [] for k in ("collided", "collided_wosac", "run_road_edge", "run_red_light", "passive")})
     for step in range(1, step_end + 1):                                                                 # :233
         mean, logits = policy.step(valid, pose, motion, ag_attr, ag_type, latent, latent_valid, navi, navi_valid,
                                    tl_state, tlR, mpR)                                                  # :163-177
@@ -473,6 +630,9 @@ def rollout(P, cfg, sz, dyn, rcfg, batch: Dict[str, Tensor], n_rollout: int, ste
             motion = torch.where(ov.unsqueeze(-1), gt_motion[:, :, step], motion)
         tl_new = F.one_hot(torch.softmax(logits, -1).argmax(-1), logits.shape[-1]).bool()               # dynamics.py:154-159
         tl_state = tl_gt[:, :, step] if step < n_gt else tl_new                                         # :161-163, tf.py:65,159
+        if checker is not None:                                                                         # :250, checker :343-451
+            for k, v in checker.check(pred_valid, pred_pose, pred_motion, tl_state).items():
+                out[k].append(v)
         outside = check_outside_map(pred_valid, pred_pose, boundary)                                    # :250
         reached = check_dest_reached(pred_valid, pred_pose, dest, dest_reached)
         dest_reached = dest_reached | reached

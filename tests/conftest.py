@@ -32,3 +32,8 @@ def golden_ops():
 @pytest.fixture(scope="session")
 def golden_rollout():
     return torch.load(os.path.join(GOLDEN, "rollout_small.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_checks():
+    return torch.load(os.path.join(GOLDEN, "checks_dense.pt"), weights_only=False)

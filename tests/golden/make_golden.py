@@ -149,7 +149,7 @@ def make_dynamics():
 
 
 @torch.no_grad()
-def reference_rollout(model, batch, R, step_end, record_steps=()):
+def reference_rollout(model, batch, R, step_end, record_steps=(), disable_check=True):
     """waymo_motion.py:439-524 (joint_future_pred) + :206-311 (rollout) + :118-204 (forward), restated."""
     rc = config.ROLLOUT_CFG
     mp_tokens = model.mp_encoder(batch["sc/mp_valid"], batch["sc/mp_attr"], batch["sc/mp_pose"], batch["ref/mp_type"])
@@ -171,7 +171,7 @@ def reference_rollout(model, batch, R, step_end, record_steps=()):
         mp_boundary=rep(batch["map/boundary"]), mp_valid=rep(batch["map/valid"]), mp_type=rep(batch["map/type"]),
         mp_pos=rep(batch["map/pos"]), mp_dir=rep(batch["map/dir"]), ag_type=ag_tokens["ag_type"],
         ag_size=ag_tokens["ag_size"], ag_goal=None, ag_dest=ag_tokens["ag_navi"], tl_valid=tl_tokens["tl_token_valid"],
-        tl_pose=tl_tokens["tl_token_pose"], disable_check=True)  # heavy logging-only checks off; feedback checks run
+        tl_pose=tl_tokens["tl_token_pose"], disable_check=disable_check)  # True: logging-only checks off
     tl_state_gt = rep(batch["sc/tl_state"])
     tf = TeacherForcing(step_spawn_agent=rc["step_spawn_agent"], step_warm_start=rc["step_warm_start"])
     tf.init(ag_valid=ag_tokens["gt_valid"], ag_pose=ag_tokens["gt_pose"], ag_motion=ag_tokens["gt_motion"],
@@ -180,6 +180,9 @@ def reference_rollout(model, batch, R, step_end, record_steps=()):
     dyn.init(tl_state=tl_state_gt, **ag_tokens)
     model.init()
     out = dict(pred_valid=[], pred_pose=[], pred_motion=[], tl_state=[], action_mean=[])
+    vio_keys = ("collided", "collided_wosac", "run_road_edge", "run_red_light", "passive")
+    if not disable_check:
+        out.update({k: [] for k in vio_keys})
     rec = {}
     for step in range(1, step_end + 1):
         ag_override, tl_override = tf.get(step, dyn.ag_valid, dyn.ag_pose, dyn.ag_motion)
@@ -200,6 +203,9 @@ def reference_rollout(model, batch, R, step_end, record_steps=()):
         gt_valid = ag_tokens["gt_valid"][:, :, step] if step < ag_tokens["gt_valid"].shape[-1] else None
         out["pred_valid"].append(ag_valid); out["pred_pose"].append(pred_pose); out["pred_motion"].append(pred_motion)
         out["tl_state"].append(dyn.tl_state); out["action_mean"].append(action_dist.mean)
+        if not disable_check:
+            for k in vio_keys:
+                out[k].append(violation[f"{k}_this_step"])
         dyn.disable_ag(violation, gt_valid)
         dyn.disable_navi(violation)
     res = {k: torch.stack(v, 2) for k, v in out.items()}
@@ -232,6 +238,18 @@ def main():
     print("rollout_small.pt", os.path.getsize(os.path.join(HERE, "rollout_small.pt")) // 1024, "KiB")
     print("outside/disabled agents:", int((~res["final_valid"]).sum()), "navi reached:", int((~res["final_navi_valid"]).sum()))
     print("max |action mean|", float(res["action_mean"].abs().max()))
+
+    # ---- dense scene with ALL TrafficRuleChecker checks on (traffic_rule_checker.py:343-451): SURVEY 8(f) rank 1
+    shape = dict(n_sc=2, n_ag=48, n_mp=96, n_tl=30, seed=3000, boundary=60.0, scale=0.2)
+    batch = synth.make_scene_batch(**shape)
+    R, T = 2, 36
+    res, _, _ = reference_rollout(model, batch, R, T, disable_check=False)
+    keep = ("pred_valid", "pred_pose", "pred_motion", "tl_state", "collided", "collided_wosac", "run_road_edge",
+            "run_red_light", "passive")
+    fix = dict(shape=shape, R=R, T=T, param_seed=0, **{k: res[k] for k in keep})
+    torch.save(fix, os.path.join(HERE, "checks_dense.pt"))
+    print("checks_dense.pt", os.path.getsize(os.path.join(HERE, "checks_dense.pt")) // 1024, "KiB",
+          {k: int(res[k].sum()) for k in keep[4:]})
 
 
 if __name__ == "__main__":

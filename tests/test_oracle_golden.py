@@ -94,3 +94,22 @@ def test_rollout_small(golden_rollout):
     _close(res["pred_pose"][..., :2], g["pred_pose"][..., :2], 0, 1e-3, "pred xy")
     _close(res["pred_pose"][..., 2], g["pred_pose"][..., 2], 0, 1e-4, "pred yaw")
     _close(res["pred_motion"], g["pred_motion"], 0, 1e-3, "pred motion")
+
+
+def test_rule_checks_oracle_vs_reference(golden_checks):
+    """The five logging-only checks of TrafficRuleChecker.check (collision, WOSAC collision, road edge, red light,
+    passive) replayed on the reference's own per-step predictions: flags must be identical."""
+    g = golden_checks
+    batch = synth.make_scene_batch(**g["shape"])
+    R = g["R"]
+    rep = lambda t: t.repeat_interleave(R, 0)  # noqa: E731
+    chk = O.RuleCheckOracle(rep(batch["map/valid"]), rep(batch["map/type"]), rep(batch["map/pos"][..., :2]),
+                            rep(batch["map/dir"][..., :2]), rep(batch["ref/ag_type"]), rep(batch["ref/ag_size"]),
+                            rep(batch["sc/tl_valid"]), rep(batch["sc/tl_pose"]))
+    keys = ("collided", "collided_wosac", "run_road_edge", "run_red_light", "passive")
+    for t in range(g["T"]):
+        out = chk.check(g["pred_valid"][:, :, t], g["pred_pose"][:, :, t], g["pred_motion"][:, :, t],
+                        g["tl_state"][:, :, t])
+        for k in keys:
+            assert torch.equal(out[k], g[k][:, :, t]), f"{k} differs at step {t + 1}"
+    assert int(g["collided"].sum()) > 100 and int(g["run_road_edge"].sum()) > 100  # fixture exercises the checks

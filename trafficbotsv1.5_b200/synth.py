@@ -13,22 +13,23 @@ import torch
 
 def make_scene_batch(n_sc: int, n_ag: int = 128, n_mp: int = 1024, n_tl: int = 40, n_node: int = 20,
                      n_hist: int = 11, seed: int = 1000, boundary: float = 400.0,
-                     n_rollout: int = 32, latent_dim: int = 16) -> Dict[str, torch.Tensor]:
-    """All tensors fp32/bool/int64 on CPU. Scene s is drawn from seed `seed + s`."""
+                     n_rollout: int = 32, latent_dim: int = 16, scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """All tensors fp32/bool/int64 on CPU. Scene s is drawn from seed `seed + s`. `scale` shrinks/expands the
+    spatial extent of map and agents (dense scenes exercise the collision / road-edge checks)."""
     out = {}
-    scenes = [_one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed + s, boundary, n_rollout, latent_dim)
+    scenes = [_one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed + s, boundary, n_rollout, latent_dim, scale)
               for s in range(n_sc)]
     for k in scenes[0]:
         out[k] = torch.stack([sc[k] for sc in scenes], 0)
     return out
 
 
-def _one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed, boundary, n_rollout, latent_dim):
+def _one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed, boundary, n_rollout, latent_dim, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     U = lambda *s, lo=0.0, hi=1.0: torch.rand(*s, generator=g) * (hi - lo) + lo  # noqa: E731
     d = {}
     # ---- map polylines: straight, 1 m node spacing, node 0 is the token pose (map_encoder.py:65)
-    p0 = U(n_mp, 2, lo=-150.0, hi=150.0)
+    p0 = U(n_mp, 2, lo=-150.0 * scale, hi=150.0 * scale)
     hd = U(n_mp, lo=-math.pi, hi=math.pi)
     dirv = torch.stack([hd.cos(), hd.sin()], -1)  # [n_mp, 2]
     t = torch.arange(n_node, dtype=torch.float32)
@@ -59,7 +60,7 @@ def _one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed, boundary, n_rollout, late
     st = torch.where(torch.arange(n_hist)[None, :] < t_sw[:, None], st0[:, None], st1[:, None])
     d["sc/tl_state"] = torch.nn.functional.one_hot(st, 5).bool()  # [n_tl, n_hist, 5]
     # ---- agents: constant-velocity history, dt = 0.1 s
-    a0 = U(n_ag, 2, lo=-100.0, hi=100.0)
+    a0 = U(n_ag, 2, lo=-100.0 * scale, hi=100.0 * scale)
     yaw = U(n_ag, lo=-math.pi, hi=math.pi)
     spd = U(n_ag, lo=0.0, hi=10.0)
     th = torch.arange(n_hist, dtype=torch.float32) * 0.1
