@@ -187,3 +187,62 @@ def test_rollout_full_90_steps_vs_oracle():
     assert float(e64.max()) < 1e-2
     # WOSAC slice = the 80 steps after the 10-step warm start (wosac_post_processing / waymo_motion.py:888-902)
     assert res["pred_pose"][:, :, 10:].shape[2] == 80
+
+
+# ---------------------------------------------------------------------------------------------- rule checks (8(f) rank 1)
+VIO = ("collided", "collided_wosac", "run_road_edge", "run_red_light", "passive")
+
+
+def test_rule_check_kernel_on_reference_predictions(golden_checks):
+    """tb_rule_check replayed step by step on the reference's own per-step predictions of a dense scene (thousands of
+    collision / road-edge events): flags must equal the reference's, up to knife-edge fp32 cases (<= 0.5 % of the
+    positives may flip; cos/sin of the heading differ by 1 ulp between libm and CUDA)."""
+    from trafficbotsv1_5_b200 import lib as L, ops
+    from trafficbotsv1_5_b200.engine import rule_tables
+    g = golden_checks
+    batch = {k: v.to(DEV) for k, v in synth.make_scene_batch(**g["shape"]).items()}
+    R, T, W = g["R"], g["T"], 11
+    B, A = g["pred_valid"].shape[:2]
+    n_sc, n_tl = batch["sc/tl_valid"].shape
+    tab = rule_tables(batch["map/valid"], batch["map/type"], batch["map/pos"][..., :2].contiguous(),
+                      batch["map/dir"][..., :2].contiguous())
+    pv = g["pred_valid"].to(DEV).to(torch.uint8).contiguous()
+    pp, pm = g["pred_pose"].to(DEV).contiguous(), g["pred_motion"].to(DEV).contiguous()
+    ag_type = batch["ref/ag_type"].repeat_interleave(R, 0).to(torch.uint8).contiguous()
+    hist_tl = torch.zeros(B, n_tl, W, 5, dtype=torch.uint8, device=DEV)
+    tl_inv = (~batch["sc/tl_valid"]).to(torch.uint8).contiguous()
+    counter = torch.zeros(B, A, device=DEV)
+    outs = {k: torch.zeros(B, A, T, dtype=torch.uint8, device=DEV) for k in VIO}
+    d_step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for s in range(1, T + 1):
+        d_step.fill_(s)
+        hist_tl[:, :, s % W] = g["tl_state"][:, :, s - 1].to(DEV).to(torch.uint8)
+        L.check(L.load().tb_rule_check(
+            L.ptr(pv), L.ptr(pp), L.ptr(pm), L.ptr(ag_type), L.ptr(batch["ref/ag_size"].contiguous()), L.ptr(hist_tl),
+            L.ptr(tl_inv), L.ptr(batch["sc/tl_pose"].contiguous()), L.ptr(tab["edges"]), L.ptr(tab["n_edge"]),
+            tab["edges"].shape[1], L.ptr(tab["lanes"]), L.ptr(tab["n_lane"]), tab["lanes"].shape[1], L.ptr(counter),
+            *[L.ptr(outs[k]) for k in VIO], L.ptr(d_step), B, A, T, W, n_tl, R, 1, 1.1, L.stream()), "tb_rule_check")
+    torch.cuda.synchronize()
+    for k in VIO:
+        mine, ref = outs[k].bool().cpu(), g[k]
+        n_diff, n_pos = int((mine != ref).sum()), int(ref.sum())
+        print(f"{k}: reference positives {n_pos}, mismatches {n_diff}")
+        assert n_diff <= max(1, int(0.005 * n_pos)), f"{k}: {n_diff} mismatches of {n_pos} positives"
+
+
+def test_rule_checks_in_rollout_vs_oracle():
+    """engine(rule_checks=True) vs the oracle's closed loop with the same checks on a dense scene (other seed)."""
+    shape = dict(n_sc=1, n_ag=40, n_mp=96, n_tl=30, seed=77, boundary=60.0, scale=0.2)
+    R, T = 2, 30
+    eng, batch, P, cfg = _engine(shape, R, T, rule_checks=True)
+    res = eng.rollout(batch)
+    ref = O.rollout(P, cfg, config.derived_sizes(cfg), config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, T,
+                    rule_checks=True)
+    assert torch.equal(res["pred_valid"].cpu(), ref["pred_valid"])
+    tot = 0
+    for k in VIO:
+        n_diff, n_pos = int((res[k].cpu() != ref[k]).sum()), int(ref[k].sum())
+        tot += n_pos
+        print(f"{k}: oracle positives {n_pos}, mismatches {n_diff}")
+        assert n_diff <= max(2, int(0.01 * n_pos))
+    assert tot > 100

@@ -21,6 +21,27 @@ from . import ops
 from .model import HotPathModel
 
 
+VIOLATIONS = ("collided", "collided_wosac", "run_road_edge", "run_red_light", "passive")
+
+
+def rule_tables(mp_valid: Tensor, mp_type: Tensor, mp_pos: Tensor, mp_dir: Tensor) -> Dict[str, Tensor]:
+    """Per-scene compacted tables of TrafficRuleChecker._get_road_edge / _get_lane_center
+    (utils/traffic_rule_checker.py:452-497): valid road-edge segments (types 4,5,7) as (x0,y0,x1,y1) and valid
+    lane-centre points (types 0..2), padded to the largest scene, with their counts."""
+    n_sc = mp_valid.shape[0]
+    ev = (mp_valid & mp_type[:, :, [4, 5, 7]].any(-1, keepdim=True)).flatten(1, 2)
+    seg = torch.cat([mp_pos, mp_pos + mp_dir], -1).flatten(1, 2)                      # [n_sc, n_mp*n_node, 4]
+    lv = (mp_valid & mp_type[:, :, :3].any(-1, keepdim=True)).flatten(1, 2)
+    pts = mp_pos.flatten(1, 2)
+    ne, nl = ev.sum(1).to(torch.int32), lv.sum(1).to(torch.int32)
+    edges = torch.zeros(n_sc, max(int(ne.max()), 1), 4, device=mp_pos.device)
+    lanes = torch.zeros(n_sc, max(int(nl.max()), 1), 2, device=mp_pos.device)
+    for s in range(n_sc):
+        edges[s, : int(ne[s])] = seg[s][ev[s]]
+        lanes[s, : int(nl[s])] = pts[s][lv[s]]
+    return dict(edges=edges, n_edge=ne.contiguous(), lanes=lanes, n_lane=nl.contiguous())
+
+
 def teacher_forcing_mask(gt_valid: Tensor, step_spawn: int, step_warm: int) -> Tensor:
     """TeacherForcing.init at test time (utils/teacher_forcing.py:51-82; schedules / thresholds off)."""
     tf = torch.zeros_like(gt_valid)
@@ -72,7 +93,8 @@ def _copy_tree(dst, src) -> None:
 
 class RolloutEngine:
     def __init__(self, P: Dict[str, Tensor], cfg: Optional[dict] = None, device="cuda", precision: int = 0,
-                 n_rollout: int = 32, step_end: Optional[int] = None, use_graph: bool = True):
+                 n_rollout: int = 32, step_end: Optional[int] = None, use_graph: bool = True,
+                 rule_checks: bool = False):
         L.load()  # fail loudly if the CUDA library is missing
         self.cfg = cfg or C.default_model_cfg()
         self.sz = C.derived_sizes(self.cfg)
@@ -82,6 +104,7 @@ class RolloutEngine:
         self.T = step_end or C.ROLLOUT_CFG["time_step_end"]
         self.tl_per_scene = True  # the TL branch is a function of (scene, TL history) only: evaluated once per scene
         self.use_graph = use_graph
+        self.rule_checks = rule_checks  # also evaluate the logging-only TrafficRuleChecker checks every step
         self.dyn = C.DYNAMICS_CFG
         self._graph = None
         self._shape = None
@@ -125,6 +148,10 @@ class RolloutEngine:
                   tl_out=z(Bt, n_tl, T, 5, dt=u8), x_cat=z(B * A, 2 * d),
                   tl_feat=z(Bt * n_tl, d), tl_logits=z(Bt * n_tl, self.cfg["tl_state_dim"]),
                   init_navi_valid=z(B, A, dt=torch.bool))
+        if self.rule_checks:
+            st.update(ag_size=z(n_sc, A, 3), passive_counter=z(B, A), edges=z(n_sc, n_mp * n_node, 4),
+                      lanes=z(n_sc, n_mp * n_node, 2), n_edge=z(n_sc, dt=torch.int32), n_lane=z(n_sc, dt=torch.int32),
+                      **{f"vio_{k}": z(B, A, T, dt=u8) for k in VIOLATIONS})
         return st
 
     def _load_state(self, st: dict, batch: Dict[str, Tensor]):
@@ -159,6 +186,13 @@ class RolloutEngine:
         st["mp_node_invalid"].copy_(~g("map/valid"))
         mp_type = g("map/type")
         st["mp_kind"].copy_(mp_type[..., :4].any(-1).to(torch.uint8) + 2 * mp_type[..., 4].to(torch.uint8))
+        if self.rule_checks:
+            st["ag_size"].copy_(g("ref/ag_size"))
+            tab = rule_tables(g("map/valid"), mp_type, g("map/pos")[..., :2], mp_dir)
+            st["edges"][:, : tab["edges"].shape[1]] = tab["edges"]  # fixed-capacity buffers: the step graph stays valid
+            st["lanes"][:, : tab["lanes"].shape[1]] = tab["lanes"]
+            st["n_edge"].copy_(tab["n_edge"])
+            st["n_lane"].copy_(tab["n_lane"])
 
     def _reset(self, st: dict):
         """time 0 of the rollout (waymo_motion.py:219-227)."""
@@ -167,6 +201,10 @@ class RolloutEngine:
         for k in ("disabled", "dest_reached", "hist_valid", "hist_pose", "hist_motion", "hist_tl", "pred_valid",
                   "pred_pose", "pred_motion", "tl_out"):
             st[k].zero_()
+        if self.rule_checks:
+            st["passive_counter"].zero_()
+            for k in VIOLATIONS:
+                st[f"vio_{k}"].zero_()
         st["valid"].copy_(rep(st["gt_valid"][:, :, 0]))
         st["pose"].copy_(rep(st["gt_pose"][:, :, 0]))
         st["motion"].copy_(rep(st["gt_motion"][:, :, 0]))
@@ -207,6 +245,16 @@ class RolloutEngine:
         L.check(lib.tb_tl_step(L.ptr(logits), L.ptr(ops._u8(static["tl"]["tl_token_invalid"])), L.ptr(st["gt_tl"]),
                                st["n_gt"], L.ptr(st["d_step"]), st["Bt"], st["n_tl"], m.W, self.T, L.ptr(st["hist_tl"]),
                                L.ptr(st["tl_out"]), L.stream()), "tb_tl_step")
+        if self.rule_checks:
+            tlp = static["tl"]
+            L.check(lib.tb_rule_check(
+                L.ptr(st["pred_valid"]), L.ptr(st["pred_pose"]), L.ptr(st["pred_motion"]), L.ptr(st["ag_type"]),
+                L.ptr(st["ag_size"]), L.ptr(st["hist_tl"]), L.ptr(ops._u8(tlp["tl_token_invalid"])),
+                L.ptr(tlp["tl_token_pose"]), L.ptr(st["edges"]), L.ptr(st["n_edge"]), st["edges"].shape[1],
+                L.ptr(st["lanes"]), L.ptr(st["n_lane"]), st["lanes"].shape[1], L.ptr(st["passive_counter"]),
+                *[L.ptr(st[f"vio_{k}"]) for k in VIOLATIONS], L.ptr(st["d_step"]), st["B"], st["A"], self.T, m.W,
+                st["n_tl"], self.R, self.R, 1.1, L.stream()), "tb_rule_check")
+            ops._count()
         L.check(lib.tb_step_advance(L.ptr(st["d_step"]), L.stream()), "tb_step_advance")
         ops._count(3)
 
@@ -264,7 +312,8 @@ class RolloutEngine:
         st, R = self._st, self.R
         n_sc, A = st["n_sc"], st["A"]
         tl = st["tl_out"] if not self.tl_per_scene else st["tl_out"].repeat_interleave(R, 0)
-        return dict(pred_valid=st["pred_valid"].bool(), pred_pose=st["pred_pose"], pred_motion=st["pred_motion"],
+        vio = {k: st[f"vio_{k}"].bool() for k in VIOLATIONS} if self.rule_checks else {}
+        return dict(**vio, pred_valid=st["pred_valid"].bool(), pred_pose=st["pred_pose"], pred_motion=st["pred_motion"],
                     tl_state=tl.bool(), final_valid=st["valid"].bool(), final_navi_valid=~st["navi_invalid"],
                     joint_pose=st["pred_pose"].view(n_sc, R, A, self.T, 3))
 

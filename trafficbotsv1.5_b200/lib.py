@@ -14,12 +14,12 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("TB_LIB", os.path.join(_PKG, "libtbknarpe.so"))
 _SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu",
-            "rollout_step.cu"]
+            "rollout_step.cu", "rule_check.cu"]
 _lib = None
 
 EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_linear", "tb_layernorm",
            "tb_pointnet_pool", "tb_pose_emb", "tb_ag_featurize", "tb_tl_featurize", "tb_dyn_step", "tb_tl_step",
-           "tb_step_advance", "tb_gather_rows", "tb_action_mean"]
+           "tb_step_advance", "tb_gather_rows", "tb_action_mean", "tb_rule_check"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -66,6 +66,7 @@ def load() -> ctypes.CDLL:
         "tb_step_advance": [P, P],
         "tb_gather_rows": [P, I, I, P, I, I, I, I, P, I, P],
         "tb_action_mean": [P, P, P, I, P, P],
+        "tb_rule_check": [P, P, P, P, P, P, P, P, P, P, I, P, P, I, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
