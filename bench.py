@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--precision", type=int, default=1,
                     help="1 (default): tcgen05 kind::tf32 projections, fp32 everything else; 0: fp32 FFMA projections")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rule-checks", action="store_true",
+                    help="also run the logging-only TrafficRuleChecker checks (collision, road edge, ...) every step")
     return ap.parse_args()
 
 
@@ -196,7 +198,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(dev))
     cfg = config.default_model_cfg()
     P = params.init_params(cfg, 0)
-    eng = RolloutEngine(P, cfg, dev, precision=args.precision, n_rollout=args.rollouts, step_end=N_ITER)
+    eng = RolloutEngine(P, cfg, dev, precision=args.precision, n_rollout=args.rollouts, step_end=N_ITER,
+                        rule_checks=args.rule_checks)
     n_sc = args.scenes
     batch = synth.make_scene_batch(n_sc=n_sc, seed=1000 + rank * n_sc, n_rollout=args.rollouts)
     batch = {k: v.pin_memory() for k, v in batch.items()}
@@ -272,7 +275,7 @@ def run_ours(args):
                     config=dict(workload=f"config 3: closed-loop WOSAC rollout, {n_sc} scenes x {args.rollouts} rollouts "
                                          f"per GPU, 128 agents, 1024 polylines x 20, 40 TL, 11-step history, 90 policy "
                                          f"iterations (80 counted)", scenes_per_gpu=n_sc, rollouts=args.rollouts,
-                                policy_iterations=N_ITER, counted_steps=N_COUNTED,
+                                policy_iterations=N_ITER, counted_steps=N_COUNTED, rule_checks=bool(args.rule_checks),
                                 l2="per-iteration working set (>1 GB of activations) exceeds the 126 MB L2; no flush",
                                 launches_per_policy_iteration=eng.launches_per_step),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof)

@@ -170,15 +170,16 @@ int tb_tl_step(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt
  * _check_passive (:221-274). Evaluated on the step's prediction (pred_* at index s-1) and the traffic-light state
  * after override_tl (ring slot s%W). One CTA per rollout-scene.
  *   ag_size [B/sc_div,A,3] (length,width,height; collision boxes use size_scale = 1.1, :27), ag_type [B,A,3] u8
- *   edges [B/sc_div,edge_cap,4] = (x0,y0,x1,y1) of the scene's valid road-edge segments (types 4,5,7; :476-479),
- *   n_edge [B/sc_div]; lanes [B/sc_div,lane_cap,2] valid lane-centre points (types 0..2; :493-495), n_lane
+ *   per-scene map tables (:452-497): seg [B/sc_div,n_mp,n_node,4] = (pos, pos+dir), node_invalid [.,n_mp,n_node] u8,
+ *   poly_circle [.,n_mp,3] = bounding circle (cx,cy,r) of each polyline's segments, poly_kind [.,n_mp] u8
+ *   (bit0: road-edge types 4,5,7; bit1: lane-centre types 0..2)
  *   passive_counter [B,A] f32 (in/out); outputs "*_this_step" flags [B,A,T] u8 at index s-1.
  * Limit: A <= 256.
  * ------------------------------------------------------------------------------------------------- */
 int tb_rule_check(const uint8_t* pred_valid, const float* pred_pose, const float* pred_motion, const uint8_t* ag_type,
                   const float* ag_size, const uint8_t* hist_tl, const uint8_t* tl_invalid, const float* tl_pose,
-                  const float* edges, const int* n_edge, int edge_cap, const float* lanes, const int* n_lane,
-                  int lane_cap, float* passive_counter, uint8_t* o_collided, uint8_t* o_collided_wosac,
+                  const float* seg, const uint8_t* node_invalid, const float* poly_circle, const uint8_t* poly_kind,
+                  int n_mp, int n_node, float* passive_counter, uint8_t* o_collided, uint8_t* o_collided_wosac,
                   uint8_t* o_run_road_edge, uint8_t* o_run_red_light, uint8_t* o_passive, const int* d_step, int B, int A,
                   int T, int W, int n_tl, int sc_div, int tl_div, float size_scale, void* stream);
 

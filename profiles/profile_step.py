@@ -17,7 +17,8 @@ from trafficbotsv1_5_b200.engine import RolloutEngine  # noqa: E402
 n_sc = int(os.environ.get("TB_SCENES", "16"))
 prec = int(os.environ.get("TB_PRECISION", "0"))
 cfg = config.default_model_cfg()
-eng = RolloutEngine(params.init_params(cfg, 0), cfg, "cuda", precision=prec, n_rollout=32, step_end=90, use_graph=False)
+eng = RolloutEngine(params.init_params(cfg, 0), cfg, "cuda", precision=prec, n_rollout=32, step_end=90, use_graph=False,
+                    rule_checks=bool(int(os.environ.get("TB_RULE_CHECKS", "0"))))
 eng.prepare(synth.make_scene_batch(n_sc=n_sc, seed=1000))
 st = eng._st
 eng._reset(st)

@@ -219,8 +219,8 @@ def test_rule_check_kernel_on_reference_predictions(golden_checks):
         hist_tl[:, :, s % W] = g["tl_state"][:, :, s - 1].to(DEV).to(torch.uint8)
         L.check(L.load().tb_rule_check(
             L.ptr(pv), L.ptr(pp), L.ptr(pm), L.ptr(ag_type), L.ptr(batch["ref/ag_size"].contiguous()), L.ptr(hist_tl),
-            L.ptr(tl_inv), L.ptr(batch["sc/tl_pose"].contiguous()), L.ptr(tab["edges"]), L.ptr(tab["n_edge"]),
-            tab["edges"].shape[1], L.ptr(tab["lanes"]), L.ptr(tab["n_lane"]), tab["lanes"].shape[1], L.ptr(counter),
+            L.ptr(tl_inv), L.ptr(batch["sc/tl_pose"].contiguous()), L.ptr(tab["seg"]), L.ptr(tab["node_invalid"]),
+            L.ptr(tab["poly_circle"]), L.ptr(tab["poly_kind"]), tab["seg"].shape[1], tab["seg"].shape[2], L.ptr(counter),
             *[L.ptr(outs[k]) for k in VIO], L.ptr(d_step), B, A, T, W, n_tl, R, 1, 1.1, L.stream()), "tb_rule_check")
     torch.cuda.synchronize()
     for k in VIO:

@@ -3,8 +3,9 @@
 // check_collided_wosac (utils/wosac_collision.py:196-239), _check_run_road_edge (:152-173), _check_run_red_light
 // (:176-218) and _check_passive (:221-274). The reference materialises [n_sc,n_ag,n_ag,4,4,3], [n_sc,n_ag,n_mp*20,4,2]
 // ... tensors every step (3x the model's CPU time); here one CTA owns one rollout-scene, agents live in
-// shared memory, pairs / map segments are pre-filtered by an exact conservative distance bound, and the per-scene
-// road-edge / lane-centre tables are compacted once per scene.
+// shared memory, agent pairs are pre-filtered by an exact conservative distance bound, and map segments / lane points
+// are reached through per-polyline bounding circles (computed once per scene), so an agent only visits the nodes of
+// the few polylines it can touch.
 // Comparisons replicate the reference's fp32 operation order without FMA contraction (__fmul_rn / __fadd_rn), so flags
 // can differ from the CPU reference only on knife-edge inputs (cos/sin of the heading may differ by 1 ulp).
 #include "common.cuh"
@@ -12,6 +13,7 @@
 namespace {
 
 constexpr int MAX_A = 256;
+constexpr int QCAP = 4096;  // (polyline, agent) candidate queue per rollout-scene
 enum : unsigned { F_COL = 1, F_WOSAC = 2, F_EDGE = 4, F_RED = 8, F_LANE = 16, F_TLAHEAD = 32, F_AGAHEAD = 64 };
 
 struct Args {
@@ -20,8 +22,11 @@ struct Args {
   const float* ag_size;    // [B/div,A,3]
   const uint8_t* hist_tl;  // [B/tl_div, n_tl, W, 5], slot s%W = state after override_tl
   const uint8_t* tl_invalid; const float* tl_pose;  // [B/div, n_tl(,3)]
-  const float* edges; const int* n_edge; int edge_cap;    // [B/div, edge_cap, 4] (x0,y0,x1,y1)
-  const float* lanes; const int* n_lane; int lane_cap;    // [B/div, lane_cap, 2]
+  const float* seg;             // [B/div, n_mp, n_node, 4] (x0,y0,x1,y1) = (pos, pos + dir)
+  const uint8_t* node_invalid;  // [B/div, n_mp, n_node]
+  const float* poly_circle;     // [B/div, n_mp, 3] bounding circle (cx, cy, r) of each polyline
+  const uint8_t* poly_kind;     // [B/div, n_mp]: bit0 road-edge types (4,5,7), bit1 lane-centre types (0..2)
+  int n_mp, n_node;
   float* passive_counter;  // [B,A]
   uint8_t *o_col, *o_wosac, *o_edge, *o_red, *o_passive;  // [B,A,T]
   const int* d_step; int A, T, W, n_tl, div, tl_div; float size_scale;
@@ -111,6 +116,8 @@ __global__ void __launch_bounds__(256) rule_check_kernel(Args p) {
   __shared__ float s_bx[MAX_A][4], s_by[MAX_A][4], s_wx[MAX_A][4], s_wy[MAX_A][4];
   __shared__ uint8_t s_valid[MAX_A], s_veh[MAX_A], s_ped[MAX_A];
   __shared__ unsigned s_flag[MAX_A];
+  __shared__ unsigned s_q[QCAP];
+  __shared__ int s_qn;
 
   const int b = blockIdx.x, sc = b / p.div, A = p.A;
   const int s = *p.d_step;
@@ -130,6 +137,7 @@ __global__ void __launch_bounds__(256) rule_check_kernel(Args p) {
     s_rad[a] = 0.5f * sqrtf(len * len + wid * wid) + 1e-3f;                       // conservative circumradius
     s_flag[a] = 0u;
   }
+  if (threadIdx.x == 0) s_qn = 0;
   __syncthreads();
 
   // ---- agent x agent: collision (SAT), WOSAC collision, "agent ahead" of the passive check
@@ -187,38 +195,51 @@ __global__ void __launch_bounds__(256) rule_check_kernel(Args p) {
     if (f) atomicOr(&s_flag[a], f);
   }
 
-  // ---- agent x road-edge segments (:152-173) — segments strided over threads, agents in the inner loop
-  const int ne = p.n_edge[sc];
-  const float* eg = p.edges + (size_t)sc * p.edge_cap * 4;
-  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
-    const float cx = eg[e * 4], cy = eg[e * 4 + 1], dx = eg[e * 4 + 2], dy = eg[e * 4 + 3];
-    const float mx = 0.5f * (cx + dx), my = 0.5f * (cy + dy);
-    const float hl = 0.5f * sqrtf((dx - cx) * (dx - cx) + (dy - cy) * (dy - cy)) + 1e-3f;
-    for (int a = 0; a < A; ++a) {
-      if (!s_valid[a] || !s_veh[a] || (s_flag[a] & F_EDGE)) continue;
-      const float rx = mx - s_x[a], ry = my - s_y[a], reach = s_rad[a] + hl;
-      if (rx * rx + ry * ry > reach * reach) continue;
+  // ---- agent x map: road-edge crossing (:152-173) and "close to lane" of the passive check (:243-247).
+  // Phase 1: polylines strided over threads, every (polyline, agent) whose bounding circles touch is queued.
+  // Phase 2: the queue is expanded to (pair, node) items over all threads — no divergent per-lane node loops.
+  auto test_node = [&](int a, size_t ni, unsigned kind) {
+    if (p.node_invalid[ni]) return;
+    const float cx = p.seg[ni * 4], cy = p.seg[ni * 4 + 1];
+    if ((kind & 1u) && !(s_flag[a] & F_EDGE)) {
+      const float dx = p.seg[ni * 4 + 2], dy = p.seg[ni * 4 + 3];
       bool hit = false;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int n = (k + 1) & 3;
-        const float ax = s_bx[a][k], ay = s_by[a][k], bx = s_bx[a][n], by = s_by[a][n];
+        const int m = (k + 1) & 3;
+        const float ax = s_bx[a][k], ay = s_by[a][k], bx = s_bx[a][m], by = s_by[a][m];
         hit |= (ccw(ax, ay, cx, cy, dx, dy) != ccw(bx, by, cx, cy, dx, dy)) &&
                (ccw(ax, ay, bx, by, cx, cy) != ccw(ax, ay, bx, by, dx, dy));
       }
       if (hit) atomicOr(&s_flag[a], F_EDGE);
     }
-  }
-  // ---- agent x lane-centre points: "close to lane" of the passive check (:243-247)
-  const int nl = p.n_lane[sc];
-  const float* lg = p.lanes + (size_t)sc * p.lane_cap * 2;
-  for (int l = threadIdx.x; l < nl; l += blockDim.x) {
-    const float lx = lg[l * 2], ly = lg[l * 2 + 1];
-    for (int a = 0; a < A; ++a) {
-      if (!s_valid[a] || !s_veh[a] || (s_flag[a] & F_LANE)) continue;
-      const float ex = sub(s_x[a], lx), ey = sub(s_y[a], ly);
+    if ((kind & 2u) && !(s_flag[a] & F_LANE)) {
+      const float ex = sub(s_x[a], cx), ey = sub(s_y[a], cy);
       if (sqrtf(add(mul(ex, ex), mul(ey, ey))) < 2.f) atomicOr(&s_flag[a], F_LANE);
     }
+  };
+  for (int pl = threadIdx.x; pl < p.n_mp; pl += blockDim.x) {
+    const size_t pi = (size_t)sc * p.n_mp + pl;
+    const unsigned kind = p.poly_kind[pi];
+    if (!kind) continue;
+    const float pcx = p.poly_circle[pi * 3], pcy = p.poly_circle[pi * 3 + 1], pr = p.poly_circle[pi * 3 + 2];
+    for (int a = 0; a < A; ++a) {
+      if (!s_valid[a] || !s_veh[a]) continue;
+      const float rx = pcx - s_x[a], ry = pcy - s_y[a], reach = pr + fmaxf(s_rad[a], 2.001f);
+      if (rx * rx + ry * ry > reach * reach) continue;
+      const int k = atomicAdd(&s_qn, 1);
+      if (k < QCAP) s_q[k] = ((unsigned)pl << 8) | (unsigned)a;
+      else for (int n = 0; n < p.n_node; ++n) test_node(a, pi * p.n_node + n, kind);  // queue full: inline (rare)
+    }
+  }
+  __syncthreads();
+  const int nq = min(s_qn, QCAP);
+  for (int it = threadIdx.x; it < nq * p.n_node; it += blockDim.x) {
+    const int h = it / p.n_node, n = it - h * p.n_node;
+    const unsigned e = s_q[h];
+    const int pl = (int)(e >> 8), a = (int)(e & 255u);
+    const size_t pi = (size_t)sc * p.n_mp + pl;
+    test_node(a, pi * p.n_node + n, p.poly_kind[pi]);
   }
   __syncthreads();
 
@@ -241,21 +262,21 @@ __global__ void __launch_bounds__(256) rule_check_kernel(Args p) {
 
 extern "C" int tb_rule_check(const uint8_t* pred_valid, const float* pred_pose, const float* pred_motion,
                              const uint8_t* ag_type, const float* ag_size, const uint8_t* hist_tl,
-                             const uint8_t* tl_invalid, const float* tl_pose, const float* edges, const int* n_edge,
-                             int edge_cap, const float* lanes, const int* n_lane, int lane_cap, float* passive_counter,
+                             const uint8_t* tl_invalid, const float* tl_pose, const float* seg,
+                             const uint8_t* node_invalid, const float* poly_circle, const uint8_t* poly_kind, int n_mp,
+                             int n_node, float* passive_counter,
                              uint8_t* o_collided, uint8_t* o_collided_wosac, uint8_t* o_run_road_edge,
                              uint8_t* o_run_red_light, uint8_t* o_passive, const int* d_step, int B, int A, int T, int W,
                              int n_tl, int sc_div, int tl_div, float size_scale, void* stream) {
   if (!pred_valid || !pred_pose || !pred_motion || !ag_type || !ag_size || !hist_tl || !tl_invalid || !tl_pose ||
-      !edges || !n_edge || !lanes || !n_lane || !passive_counter || !o_collided || !o_collided_wosac ||
+      !seg || !node_invalid || !poly_circle || !poly_kind || !passive_counter || !o_collided || !o_collided_wosac ||
       !o_run_road_edge || !o_run_red_light || !o_passive || !d_step)
     return TB_ERR_NULL;
-  if (B <= 0 || A <= 0 || T <= 0 || W <= 0 || n_tl <= 0 || sc_div <= 0 || tl_div <= 0 || edge_cap <= 0 ||
-      lane_cap <= 0)
+  if (B <= 0 || A <= 0 || T <= 0 || W <= 0 || n_tl <= 0 || sc_div <= 0 || tl_div <= 0 || n_mp <= 0 || n_node <= 0)
     return TB_ERR_BAD_SHAPE;
   if (A > MAX_A) return TB_ERR_UNSUPPORTED;
-  Args p{pred_valid, pred_pose, pred_motion, ag_type, ag_size, hist_tl, tl_invalid, tl_pose, edges, n_edge, edge_cap,
-         lanes, n_lane, lane_cap, passive_counter, o_collided, o_collided_wosac, o_run_road_edge, o_run_red_light,
+  Args p{pred_valid, pred_pose, pred_motion, ag_type, ag_size, hist_tl, tl_invalid, tl_pose, seg, node_invalid, poly_circle,
+         poly_kind, n_mp, n_node, passive_counter, o_collided, o_collided_wosac, o_run_road_edge, o_run_red_light,
          o_passive, d_step, A, T, W, n_tl, sc_div, tl_div, size_scale};
   rule_check_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   TB_CHECK_LAUNCH();

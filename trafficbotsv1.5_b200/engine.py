@@ -25,21 +25,17 @@ VIOLATIONS = ("collided", "collided_wosac", "run_road_edge", "run_red_light", "p
 
 
 def rule_tables(mp_valid: Tensor, mp_type: Tensor, mp_pos: Tensor, mp_dir: Tensor) -> Dict[str, Tensor]:
-    """Per-scene compacted tables of TrafficRuleChecker._get_road_edge / _get_lane_center
-    (utils/traffic_rule_checker.py:452-497): valid road-edge segments (types 4,5,7) as (x0,y0,x1,y1) and valid
-    lane-centre points (types 0..2), padded to the largest scene, with their counts."""
-    n_sc = mp_valid.shape[0]
-    ev = (mp_valid & mp_type[:, :, [4, 5, 7]].any(-1, keepdim=True)).flatten(1, 2)
-    seg = torch.cat([mp_pos, mp_pos + mp_dir], -1).flatten(1, 2)                      # [n_sc, n_mp*n_node, 4]
-    lv = (mp_valid & mp_type[:, :, :3].any(-1, keepdim=True)).flatten(1, 2)
-    pts = mp_pos.flatten(1, 2)
-    ne, nl = ev.sum(1).to(torch.int32), lv.sum(1).to(torch.int32)
-    edges = torch.zeros(n_sc, max(int(ne.max()), 1), 4, device=mp_pos.device)
-    lanes = torch.zeros(n_sc, max(int(nl.max()), 1), 2, device=mp_pos.device)
-    for s in range(n_sc):
-        edges[s, : int(ne[s])] = seg[s][ev[s]]
-        lanes[s, : int(nl[s])] = pts[s][lv[s]]
-    return dict(edges=edges, n_edge=ne.contiguous(), lanes=lanes, n_lane=nl.contiguous())
+    """Per-scene map tables for tb_rule_check (TrafficRuleChecker._get_road_edge / _get_lane_center,
+    utils/traffic_rule_checker.py:452-497): segments (pos, pos + dir), node validity, a bounding circle per polyline
+    and its kind bits (1: road-edge types 4,5,7; 2: lane-centre types 0..2)."""
+    end = mp_pos + mp_dir
+    seg = torch.cat([mp_pos, end], -1).contiguous()                                     # [n_sc, n_mp, n_node, 4]
+    pts = torch.cat([mp_pos, end], 2)                                                   # [n_sc, n_mp, 2*n_node, 2]
+    centre = 0.5 * (pts.amin(2) + pts.amax(2))
+    radius = torch.norm(pts - centre[:, :, None], dim=-1).amax(2) + 1e-3
+    kind = mp_type[:, :, [4, 5, 7]].any(-1).to(torch.uint8) + 2 * mp_type[:, :, :3].any(-1).to(torch.uint8)
+    return dict(seg=seg, node_invalid=(~mp_valid).to(torch.uint8).contiguous(),
+                poly_circle=torch.cat([centre, radius[..., None]], -1).contiguous(), poly_kind=kind.contiguous())
 
 
 def teacher_forcing_mask(gt_valid: Tensor, step_spawn: int, step_warm: int) -> Tensor:
@@ -149,8 +145,9 @@ class RolloutEngine:
                   tl_feat=z(Bt * n_tl, d), tl_logits=z(Bt * n_tl, self.cfg["tl_state_dim"]),
                   init_navi_valid=z(B, A, dt=torch.bool))
         if self.rule_checks:
-            st.update(ag_size=z(n_sc, A, 3), passive_counter=z(B, A), edges=z(n_sc, n_mp * n_node, 4),
-                      lanes=z(n_sc, n_mp * n_node, 2), n_edge=z(n_sc, dt=torch.int32), n_lane=z(n_sc, dt=torch.int32),
+            st.update(ag_size=z(n_sc, A, 3), passive_counter=z(B, A), seg=z(n_sc, n_mp, n_node, 4),
+                      node_invalid=z(n_sc, n_mp, n_node, dt=u8), poly_circle=z(n_sc, n_mp, 3),
+                      poly_kind=z(n_sc, n_mp, dt=u8),
                       **{f"vio_{k}": z(B, A, T, dt=u8) for k in VIOLATIONS})
         return st
 
@@ -188,11 +185,8 @@ class RolloutEngine:
         st["mp_kind"].copy_(mp_type[..., :4].any(-1).to(torch.uint8) + 2 * mp_type[..., 4].to(torch.uint8))
         if self.rule_checks:
             st["ag_size"].copy_(g("ref/ag_size"))
-            tab = rule_tables(g("map/valid"), mp_type, g("map/pos")[..., :2], mp_dir)
-            st["edges"][:, : tab["edges"].shape[1]] = tab["edges"]  # fixed-capacity buffers: the step graph stays valid
-            st["lanes"][:, : tab["lanes"].shape[1]] = tab["lanes"]
-            st["n_edge"].copy_(tab["n_edge"])
-            st["n_lane"].copy_(tab["n_lane"])
+            for k, v in rule_tables(g("map/valid"), mp_type, g("map/pos")[..., :2], mp_dir).items():
+                st[k].copy_(v)
 
     def _reset(self, st: dict):
         """time 0 of the rollout (waymo_motion.py:219-227)."""
@@ -250,8 +244,8 @@ class RolloutEngine:
             L.check(lib.tb_rule_check(
                 L.ptr(st["pred_valid"]), L.ptr(st["pred_pose"]), L.ptr(st["pred_motion"]), L.ptr(st["ag_type"]),
                 L.ptr(st["ag_size"]), L.ptr(st["hist_tl"]), L.ptr(ops._u8(tlp["tl_token_invalid"])),
-                L.ptr(tlp["tl_token_pose"]), L.ptr(st["edges"]), L.ptr(st["n_edge"]), st["edges"].shape[1],
-                L.ptr(st["lanes"]), L.ptr(st["n_lane"]), st["lanes"].shape[1], L.ptr(st["passive_counter"]),
+                L.ptr(tlp["tl_token_pose"]), L.ptr(st["seg"]), L.ptr(st["node_invalid"]), L.ptr(st["poly_circle"]),
+                L.ptr(st["poly_kind"]), st["n_mp"], st["n_node"], L.ptr(st["passive_counter"]),
                 *[L.ptr(st[f"vio_{k}"]) for k in VIOLATIONS], L.ptr(st["d_step"]), st["B"], st["A"], self.T, m.W,
                 st["n_tl"], self.R, self.R, 1.1, L.stream()), "tb_rule_check")
             ops._count()

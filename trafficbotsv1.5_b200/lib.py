@@ -66,7 +66,7 @@ def load() -> ctypes.CDLL:
         "tb_step_advance": [P, P],
         "tb_gather_rows": [P, I, I, P, I, I, I, I, P, I, P],
         "tb_action_mean": [P, P, P, I, P, P],
-        "tb_rule_check": [P, P, P, P, P, P, P, P, P, P, I, P, P, I, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
+        "tb_rule_check": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
