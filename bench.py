@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--precision", type=int, default=1,
                     help="1 (default): tcgen05 kind::tf32 projections, fp32 everything else; 0: fp32 FFMA projections")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32 / rule-check extra measurements")
     ap.add_argument("--rule-checks", action="store_true",
                     help="also run the logging-only TrafficRuleChecker checks (collision, road edge, ...) every step")
     return ap.parse_args()
@@ -279,6 +280,19 @@ def run_ours(args):
                                 l2="per-iteration working set (>1 GB of activations) exceeds the 126 MB L2; no flush",
                                 launches_per_policy_iteration=eng.launches_per_step),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof)
+    if rank == 0 and world == 1 and not args.rule_checks and not args.no_extras:
+        # extra lines (not the headline): fp32-parity projections, and the loop with ALL TrafficRuleChecker checks on
+        extras = {}
+        for name, kw in (("fp32_projections", dict(precision=0)), ("with_rule_checks", dict(precision=args.precision,
+                                                                                           rule_checks=True))):
+            del eng
+            torch.cuda.empty_cache()
+            eng = RolloutEngine(P, cfg, dev, n_rollout=args.rollouts, step_end=N_ITER, **kw)
+            eng.prepare(batch)
+            eng.run()
+            t = timed(eng.run, 2)
+            extras[name] = dict(value=units * 2 / t, unit=UNIT, ms_per_step=t / 2 * 1e3)
+        line["extras"] = extras
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         rate, sample, _ = cpu_rollout_rate(cores, 1, 16, 16)

@@ -246,3 +246,39 @@ def test_rule_checks_in_rollout_vs_oracle():
         print(f"{k}: oracle positives {n_pos}, mismatches {n_diff}")
         assert n_diff <= max(2, int(0.01 * n_pos))
     assert tot > 100
+
+
+@pytest.mark.parametrize("shape,R,T", [
+    (dict(n_sc=1, n_ag=37, n_mp=70, n_tl=27, seed=5, boundary=103.0), 3, 15),      # ragged sizes just above the K's
+    (dict(n_sc=3, n_ag=26, n_mp=65, n_tl=26, seed=6, boundary=101.0), 1, 13),      # minimum sizes (K < T), 1 rollout
+])
+def test_rollout_ragged_shapes_vs_oracle(shape, R, T):
+    """Row counts that are not multiples of any tile (128-row GEMM tiles, 8-token attention CTAs, 64-row select CTAs)
+    and target counts one above the KNN sizes (K_ag2ag = 25 < 26, K_ag2mp = 64 < 65, K_tl2* = 24)."""
+    eng, batch, P, cfg = _engine(shape, R, T)
+    res = eng.rollout(batch)
+    ref = O.rollout(P, cfg, config.derived_sizes(cfg), config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, T)
+    assert torch.equal(res["pred_valid"].cpu(), ref["pred_valid"])
+    assert torch.equal(res["tl_state"].cpu(), ref["tl_state"])
+    assert maxerr(res["pred_pose"][..., :2], ref["pred_pose"][..., :2]) < TOL_XY
+    assert maxerr(res["pred_pose"][..., 2], ref["pred_pose"][..., 2]) < TOL_YAW
+
+
+def test_rollout_degenerate_scenes():
+    """All agents invalid / all traffic lights invalid / all map polylines invalid: every attention row is fully
+    masked -> exact zeros, no NaN; agents that are never valid stay exactly zero."""
+    shape = dict(n_sc=2, n_ag=30, n_mp=80, n_tl=28, seed=9, boundary=110.0)
+    R, T = 2, 12
+    eng, batch, P, cfg = _engine(shape, R, T)
+    batch["sc/ag_valid"][0] = False          # scene 0: no agent at all
+    batch["ag_navi_valid"][0] = False
+    batch["ag_latent_valid"][0] = False
+    batch["sc/tl_valid"][1] = False          # scene 1: no traffic light
+    batch["sc/mp_valid"][1] = False          # ... and no valid map polyline
+    batch["map/valid"][1] = False
+    res = eng.rollout(batch)
+    ref = O.rollout(P, cfg, config.derived_sizes(cfg), config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, T)
+    assert bool(torch.isfinite(res["pred_pose"]).all()) and bool(torch.isfinite(res["pred_motion"]).all())
+    assert torch.equal(res["pred_valid"].cpu(), ref["pred_valid"])
+    assert float(res["pred_pose"][: R].abs().max()) == 0.0
+    assert maxerr(res["pred_pose"], ref["pred_pose"]) < TOL_XY
