@@ -65,6 +65,25 @@ pointnet_pool_kernel(float* __restrict__ X, int ldx, const uint8_t* __restrict__
         else xg[(size_t)r * ldx + C + c] = m;
       }
     }
+  } else if (C2 == 64 && L <= 16 && (ldx & 1) == 0 && (ldo & 1) == 0) {
+    // hot shape (PointNet rows of d/2 = 64 channels, 11 history steps): one float2 per lane and row, all rows of the
+    // group in flight before the max
+    float2 v[16];
+    unsigned vm = 0u;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (r < L && !inv[r]) {
+        v[r] = *reinterpret_cast<const float2*>(xg + (size_t)r * ldx + 2 * lane);
+        vm |= 1u << r;
+      }
+    }
+    float2 m = make_float2(-INFINITY, -INFINITY);
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (vm & (1u << r)) { m.x = fmaxf(m.x, v[r].x); m.y = fmaxf(m.y, v[r].y); }
+    if (!vm) m = make_float2(0.f, 0.f);
+    *reinterpret_cast<float2*>(out + (size_t)g * ldo + 2 * lane) = m;
+    if (mode == 2) *reinterpret_cast<float2*>(out + (size_t)g * ldo + C2 + 2 * lane) = m;
   } else {
     for (int c = lane; c < C2; c += 32) {
       float m = -INFINITY;

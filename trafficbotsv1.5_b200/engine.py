@@ -266,6 +266,7 @@ class RolloutEngine:
         self._load_state(st, batch)
         new_static = static if static is not None else self.encode_scenes(batch)
         new_navi = self.model.navi_static(new_static["mp"], st["dest_idx"], self.R)
+        self.model.latent_static(new_navi, st)
         if self._graph is not None and _same_layout((self._static, self._navi), (new_static, new_navi)):
             # same shapes as the captured step graph: refresh the scene tensors in place, keep the graph
             _copy_tree((self._static, self._navi), (new_static, new_navi))

@@ -301,6 +301,17 @@ class HotPathModel:
         pose = ops.gather_rows(mp["mp_token_pose"].contiguous(), flat, A, R)
         return dict(feat=self.lin(f, "navi_encoder.mlp_mp.fc_layers.0"), pose=pose)
 
+    def latent_static(self, navi: dict, st: dict) -> None:
+        """AddNaviLatent.mlp_in(latent) (add_navi_latent.py:50) depends only on the rollout's fixed latent sample:
+        evaluated once per rollout into the right half of a persistent cat buffer."""
+        d = self.d
+        M = st["latent"].shape[0]
+        cat = torch.zeros(M, 2 * d, device=self.dev)
+        self.mlp(st["latent"], "add_latent.mlp_in", (0, 3, 6), True, mask_post=st["latent_invalid"].reshape(-1),
+                 out=cat[:, d:])
+        navi["latent_cat"] = cat
+        navi["latent_feat"] = True
+
     def heads(self, x_cat: Tensor, st: dict, navi: dict) -> Tensor:
         """navi_encoder (per-step half) -> add_navi -> add_latent -> action-head branches
         (traffic_bots.py:191-217). x_cat [M, 2d] with the agent feature already in the left half.
@@ -309,11 +320,16 @@ class HotPathModel:
         M = x_cat.shape[0]
         pe = ops.pose_emb(navi["pose"], self.freq_rpe, d, frame=st["pose"], frame_div=1)             # navigation.py:73-79
         nf = self.lin(pe, "navi_encoder.mlp_pe.fc_layers.0", res=navi["feat"])
-        x_cat2 = torch.empty(M, 2 * d, device=self.dev)
+        # add_navi writes its result straight into the left half of add_latent's cat buffer
+        x_cat2 = navi["latent_cat"] if "latent_cat" in navi else torch.empty(M, 2 * d, device=self.dev)
         for prefix, z, zinv, cat_in, cat_out in (("add_navi", nf, st["navi_invalid"], x_cat, x_cat2[:, :d]),
                                                  ("add_latent", st["latent"], st["latent_invalid"], x_cat2, None)):
             zinv = zinv.reshape(-1)                                                                  # add_navi_latent.py:46-64
-            self.mlp(z, f"{prefix}.mlp_in", (0, 3, 6), True, mask_post=zinv, out=cat_in[:, d:])
+            if prefix == "add_latent" and "latent_feat" in navi:
+                # the latent sample is fixed for the whole rollout: mlp_in(latent) was evaluated once (latent_static)
+                cat_in = navi["latent_cat"]
+            else:
+                self.mlp(z, f"{prefix}.mlp_in", (0, 3, 6), True, mask_post=zinv, out=cat_in[:, d:])
             h = self.mlp(cat_in, f"{prefix}.mlp", (0, 3, 6), True, mask_pre=zinv, res=cat_in[:, :d], out=cat_out)
         h0 = ops.linear(h, self.act_w0, self.act_b0, relu=True, precision=self.precision)            # action_head.py:78-82
         h1 = torch.empty_like(h0)
