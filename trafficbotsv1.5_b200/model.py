@@ -244,7 +244,7 @@ class HotPathModel:
                 for i in range(self.cfg["ag_encoder"]["n_layer_tf"])]
 
     def ag_forward(self, st: dict, mp: Dict[str, Tensor], kv_mp: list, tl: dict, tl_feat: Tensor, R: int,
-                   out: Optional[Tensor] = None, aux: Optional[dict] = None, before_tl=None) -> Tensor:
+                   out: Optional[Tensor] = None, aux: Optional[dict] = None, before_tl=None, knn_stream=None) -> Tensor:
         """AgentEncoder._forward_hptr (agent_encoder.py:114-178). `st` holds the rollout state rings
         (engine.RolloutState); batch b uses map / traffic-light tables of scene b // R."""
         from . import lib as L
@@ -263,18 +263,34 @@ class HotPathModel:
                                          L.ptr(tok_pose), L.ptr(ops._u8(tok_inv)), L.ptr(ops._u8(row_inv)),
                                          L.ptr(attr), 9 + W, L.ptr(x[:, d // 2:]), d, L.stream()), "tb_ag_featurize")
         ops._count()
-        self.mlp(attr, "ag_encoder.input_encoder.mlp", (0, 2, 4), False, out=x[:, : d // 2])          # :159
-        tok = self.pointnet(x, row_inv, M, W, "ag_encoder.temp_encoder")                              # :162
-        # re-localisation + KNN re-selection, every step (:321-387)
-        i_aa, m_aa, r_aa = ops.knn_select(tok_pose, tok_inv, tok_pose, tok_inv, sz["k_ag2ag"], sz["dl_ag"])
-        Kc = sz["k_ag2mp"] + sz["k_ag2tl"]
+        # re-localisation + KNN re-selection, every step (:321-387). The three selects only need the token poses, so
+        # they run on a forked stream beside the (bandwidth-bound) input MLP + PointNet projections.
+        Kc, Ka = sz["k_ag2mp"] + sz["k_ag2tl"], sz["k_ag2ag"]
+        i_aa = torch.empty(B, A, Ka, dtype=torch.int32, device=self.dev)
+        m_aa = torch.empty(B, A, Ka, dtype=torch.bool, device=self.dev)
+        r_aa = torch.empty(B, A, Ka, 3, device=self.dev)
         cidx = torch.empty(B, A, Kc, dtype=torch.int32, device=self.dev)
         cinv = torch.empty(B, A, Kc, dtype=torch.bool, device=self.dev)
         crel = torch.empty(B, A, Kc, 3, device=self.dev)
-        ops.knn_select(tok_pose, tok_inv, mp["mp_token_pose"], mp["mp_token_invalid"], sz["k_ag2mp"], sz["dl_ag"],
-                       tgt_div=R, out=(cidx, cinv, crel), koff=0)
-        ops.knn_select(tok_pose, tok_inv, tl["tl_token_pose"], tl["tl_token_invalid"], sz["k_ag2tl"], sz["dl_ag"],
-                       tgt_div=tl_div, out=(cidx, cinv, crel), koff=sz["k_ag2mp"])
+
+        def selects():
+            ops.knn_select(tok_pose, tok_inv, mp["mp_token_pose"], mp["mp_token_invalid"], sz["k_ag2mp"], sz["dl_ag"],
+                           tgt_div=R, out=(cidx, cinv, crel), koff=0)
+            ops.knn_select(tok_pose, tok_inv, tok_pose, tok_inv, Ka, sz["dl_ag"], out=(i_aa, m_aa, r_aa))
+            ops.knn_select(tok_pose, tok_inv, tl["tl_token_pose"], tl["tl_token_invalid"], sz["k_ag2tl"], sz["dl_ag"],
+                           tgt_div=tl_div, out=(cidx, cinv, crel), koff=sz["k_ag2mp"])
+
+        main = torch.cuda.current_stream()
+        if knn_stream is not None:
+            knn_stream.wait_stream(main)
+            with torch.cuda.stream(knn_stream):
+                selects()
+        self.mlp(attr, "ag_encoder.input_encoder.mlp", (0, 2, 4), False, out=x[:, : d // 2])          # :159
+        tok = self.pointnet(x, row_inv, M, W, "ag_encoder.temp_encoder")                              # :162
+        if knn_stream is not None:
+            main.wait_stream(knn_stream)
+        else:
+            selects()
         knn_self = dict(idx=i_aa, inv=m_aa, rel=r_aa)
         flat_inv = tok_inv.reshape(-1)
         nl = self.cfg["ag_encoder"]["n_layer_tf"]
