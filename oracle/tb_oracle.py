@@ -574,8 +574,8 @@ class RuleCheckOracle:
 
 
 def rollout(P, cfg, sz, dyn, rcfg, batch: Dict[str, Tensor], n_rollout: int, step_end: Optional[int] = None,
-            mp: Optional[dict] = None, tl: Optional[dict] = None, record=None, rule_checks: bool = False
-            ) -> Dict[str, Tensor]:
+            mp: Optional[dict] = None, tl: Optional[dict] = None, record=None, rule_checks: bool = False,
+            policy=None) -> Dict[str, Tensor]:
     """Restated WOSAC driver: test_step -> joint_future_pred -> rollout -> forward
     (pl_modules/waymo_motion.py:843-876, 439-524, 206-311, 118-204) with the feedback-relevant subset of
     TrafficRuleChecker.check (outside_map, dest_reached; traffic_rule_checker.py:343-451) and fixed
@@ -606,7 +606,7 @@ def rollout(P, cfg, sz, dyn, rcfg, batch: Dict[str, Tensor], n_rollout: int, ste
     valid, pose, motion = gt_valid[:, :, 0], gt_pose[:, :, 0], gt_motion[:, :, 0]
     disabled = torch.zeros_like(valid)
     tl_state = tl_gt[:, :, 0]
-    policy = PolicyOracle(P, cfg, sz)
+    policy = policy or PolicyOracle(P, cfg, sz)  # tests may plug the CUDA drop-in module into the reference loop
     out = dict(pred_valid=[], pred_pose=[], pred_motion=[], tl_state=[], action_mean=[])
     checker = None
     if rule_checks:

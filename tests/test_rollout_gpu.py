@@ -282,3 +282,46 @@ def test_rollout_degenerate_scenes():
     assert torch.equal(res["pred_valid"].cpu(), ref["pred_valid"])
     assert float(res["pred_pose"][: R].abs().max()) == 0.0
     assert maxerr(res["pred_pose"], ref["pred_pose"]) < TOL_XY
+
+
+def test_module_api_in_reference_loop(golden_rollout):
+    """The `TrafficBots` drop-in (init / forward -> distributions, mp_encoder, tl_encoder.pre_compute) driven by the
+    reference's host-side loop (restated in the oracle: Dynamics, TeacherForcing, feedback checks on the CPU) with the
+    reference's repeat_interleave of every token tensor — vs the golden rollout of the real reference."""
+    from trafficbotsv1_5_b200.traffic_bots import TrafficBots
+    g = golden_rollout
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, seed=0)
+    model = TrafficBots(cfg)
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected and all(k.endswith(("freqs", "_ohe")) for k in missing)
+    model = model.eval().to(DEV)
+    batch = synth.make_scene_batch(**g["shape"])
+    R, T = g["R"], g["T"]
+    gb = {k: v.to(DEV) for k, v in batch.items()}
+    mp_tokens = model.mp_encoder(gb["sc/mp_valid"], gb["sc/mp_attr"], gb["sc/mp_pose"], gb["ref/mp_type"])
+    tl_tokens = model.tl_encoder.pre_compute(tl_valid=gb["sc/tl_valid"], tl_attr=gb["sc/tl_attr"], tl_pose=gb["sc/tl_pose"],
+                                             **mp_tokens)
+    mpR = {k: v.repeat_interleave(R, 0) for k, v in mp_tokens.items()}          # waymo_motion.py:458-462
+    tlR = {k: v.repeat_interleave(R, 0) for k, v in tl_tokens.items()}
+
+    class Adapter:
+        def step(self, valid, pose, motion, ag_attr, ag_type, latent, latent_valid, navi, navi_valid, tl_state, _tl, _mp):
+            c = lambda t: t.to(DEV)  # noqa: E731
+            act, tl_dist = model(ag_valid=c(valid), ag_pose=c(pose), ag_motion=c(motion), ag_attr=c(ag_attr),
+                                 ag_type=c(ag_type), ag_latent=c(latent), ag_latent_valid=c(latent_valid),
+                                 ag_navi=c(navi), ag_navi_valid=c(navi_valid), ag_navi_updated=False,
+                                 tl_state=c(tl_state), tl_tokens=tlR, mp_tokens=mpR)
+            assert abs(float(act.base_dist.scale[0, 0, 0]) - (torch.tensor(-2.0).exp() if bool(valid[0, 0]) else 1.0)) < 1e-6
+            return act.mean.cpu(), tl_dist.logits.cpu()
+
+    model.init()
+    sz = config.derived_sizes(cfg)
+    mp_cpu = dict(mp_token_invalid=mp_tokens["mp_token_invalid"].cpu(), mp_token_feature=mp_tokens["mp_token_feature"].cpu(),
+                  mp_token_pose=mp_tokens["mp_token_pose"].cpu())
+    tl_cpu = dict(tl_token_invalid=tl_tokens["tl_token_invalid"].cpu(), tl_token_pose=tl_tokens["tl_token_pose"].cpu())
+    res = O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, T, mp=mp_cpu, tl=tl_cpu, policy=Adapter())
+    assert torch.equal(res["pred_valid"], g["pred_valid"])
+    assert torch.equal(res["tl_state"], g["tl_state"])
+    assert maxerr(res["pred_pose"][..., :2], g["pred_pose"][..., :2]) < TOL_XY
+    assert maxerr(res["action_mean"], g["action_mean"]) < 2e-4
