@@ -68,6 +68,8 @@ int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float
  *   q [B*S] rows, leading dim ldq (D floats used);  u [B*S] rows, leading dim ldu (H*D floats, head-major)
  *   out_ov / out_z: rows with leading dim ldo (D and H*D floats)
  *   pe_freq_xy: D/8 floats = PositionalEmbedding(dim=D/4, theta).freqs[::2] (utils/positional_emb.py:11)
+ * flags bit 0: evaluate the embedding angles with the SFU's own range reduction (no 2-term Cody-Waite step): abs error
+ *   grows with |angle| (<= ~2e-5 at 150 rad, the fp32 rounding of a 150 m coordinate); used with the tf32 projections.
  * Limits: D in {128,256} (d_rpe == D), H == 4, all leading dims and pointers 16-byte aligned.
  * ------------------------------------------------------------------------------------------------- */
 int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
@@ -75,7 +77,7 @@ int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
                    const float* kv1, int ldkv1, int T1, int div1, int K1,
                    const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,
                    const float* pe_freq_xy, int B, int S, int D, int H,
-                   float* out_ov, float* out_z, int ldo, uint8_t* out_none_valid, void* stream);
+                   float* out_ov, float* out_z, int ldo, uint8_t* out_none_valid, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Dense projection  Y = epilogue(X W^T + bias)  — replaces F.linear / nn.Linear call sites

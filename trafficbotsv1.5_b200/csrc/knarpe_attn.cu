@@ -41,7 +41,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int D, bool FROM_EMB>
+template <int D, bool FROM_EMB, bool FAST_TRIG>
 __global__ void __launch_bounds__(kWarps * 32, TB_ATTN_MINB)
 knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ u, int ldu,
                    const float* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
@@ -161,12 +161,18 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
         } else {
           const float x = s_rel[warp][g0 + g][0], y = s_rel[warp][g0 + g][1], w = s_rel[warp][g0 + g][2];
           if (D == 128) {
-            const float aw = tb_reduce_2pi(w * m1);
-            e[g][0] = make_float2(__sinf(tb_reduce_2pi(x * fxy) + ph), __sinf(tb_reduce_2pi(y * fxy) + ph));
-            e[g][1 % (NC / 2)] = make_float2(__cosf(aw), __sinf(aw));
+            if (FAST_TRIG) {  // SFU range reduction only (abs error grows ~|arg| * 2^-22: <= ~2e-5 at 150 rad)
+              const float aw = w * m1;
+              e[g][0] = make_float2(__sinf(fmaf(x, fxy, ph)), __sinf(fmaf(y, fxy, ph)));
+              e[g][1 % (NC / 2)] = make_float2(__cosf(aw), __sinf(aw));
+            } else {
+              const float aw = tb_reduce_2pi(w * m1);
+              e[g][0] = make_float2(__sinf(tb_reduce_2pi(x * fxy) + ph), __sinf(tb_reduce_2pi(y * fxy) + ph));
+              e[g][1 % (NC / 2)] = make_float2(__cosf(aw), __sinf(aw));
+            }
           } else {
-            const float ax = tb_reduce_2pi(x * fxy), ay = tb_reduce_2pi(y * fxy);
-            const float a1 = tb_reduce_2pi(w * m1), a2 = tb_reduce_2pi(w * m2);
+            const float ax = FAST_TRIG ? x * fxy : tb_reduce_2pi(x * fxy), ay = FAST_TRIG ? y * fxy : tb_reduce_2pi(y * fxy);
+            const float a1 = FAST_TRIG ? w * m1 : tb_reduce_2pi(w * m1), a2 = FAST_TRIG ? w * m2 : tb_reduce_2pi(w * m2);
             e[g][0] = make_float2(__cosf(ax), __sinf(ax));
             e[g][1 % (NC / 2)] = make_float2(__cosf(ay), __sinf(ay));
             e[g][2 % (NC / 2)] = make_float2(__cosf(a1), __cosf(a2));
@@ -257,14 +263,14 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   if (lane == 0 && out_none_valid) out_none_valid[tok] = sm > 0.f ? 0 : 1;
 }
 
-template <int D, bool FROM_EMB>
+template <int D, bool FROM_EMB, bool FAST_TRIG>
 int launch(const float* q, int ldq, const float* u, int ldu, const float* kv0, int ldkv0, int T0, int div0, int K0,
            const float* kv1, int ldkv1, int T1, int div1, int K1, const int32_t* idx, const uint8_t* invalid,
            const float* rel, const float* emb, const float* pe_freq_xy, int B, int S, float* out_ov, float* out_z,
            int ldo, uint8_t* out_none_valid, cudaStream_t st) {
   const int n_tok = B * S;
   const int grid = (n_tok + kWarps - 1) / kWarps;
-  knarpe_attn_kernel<D, FROM_EMB><<<grid, kWarps * 32, 0, st>>>(q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1,
+  knarpe_attn_kernel<D, FROM_EMB, FAST_TRIG><<<grid, kWarps * 32, 0, st>>>(q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1,
                                                               T1, div1, K1, idx, invalid, rel, emb, pe_freq_xy, n_tok,
                                                               S, out_ov, out_z, ldo, out_none_valid);
   TB_CHECK_LAUNCH();
@@ -277,7 +283,7 @@ extern "C" int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu, 
                               int div0, int K0, const float* kv1, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,
                               const float* pe_freq_xy, int B, int S, int D, int Hh, float* out_ov, float* out_z,
-                              int ldo, uint8_t* out_none_valid, void* stream) {
+                              int ldo, uint8_t* out_none_valid, int flags, void* stream) {
   if (!q || !u || !kv0 || !idx || !invalid || !out_ov || !out_z || !pe_freq_xy) return TB_ERR_NULL;
   if ((rel == nullptr) == (emb == nullptr)) return TB_ERR_NULL;  // exactly one
   if (B <= 0 || S <= 0 || K0 <= 0 || K1 < 0 || T0 <= 0 || div0 <= 0 || (K1 > 0 && (!kv1 || T1 <= 0 || div1 <= 0)))
@@ -291,7 +297,12 @@ extern "C" int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define TB_ATT_ARGS q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1, T1, div1, K1, idx, invalid, rel, emb, \
                     pe_freq_xy, B, S, out_ov, out_z, ldo, out_none_valid, st
-  if (D == 128) return rel ? launch<128, false>(TB_ATT_ARGS) : launch<128, true>(TB_ATT_ARGS);
-  return rel ? launch<256, false>(TB_ATT_ARGS) : launch<256, true>(TB_ATT_ARGS);
+  const bool fast = (flags & 1) != 0;  // bit 0: SFU-only range reduction of the embedding angles (tensor-core mode)
+  if (D == 128) {
+    if (!rel) return launch<128, true, false>(TB_ATT_ARGS);
+    return fast ? launch<128, false, true>(TB_ATT_ARGS) : launch<128, false, false>(TB_ATT_ARGS);
+  }
+  if (!rel) return launch<256, true, false>(TB_ATT_ARGS);
+  return fast ? launch<256, false, true>(TB_ATT_ARGS) : launch<256, false, false>(TB_ATT_ARGS);
 #undef TB_ATT_ARGS
 }

@@ -136,7 +136,7 @@ class HotPathModel:
         d = self.d
         return ops.knarpe_attn(proj[:, :d], proj[:, d:d + H * d], kv0, T0, div0, K0, knn["idx"], knn["inv"],
                                knn.get("rel"), self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1,
-                               emb=knn.get("emb"))
+                               emb=knn.get("emb"), fast_trig=self.precision == 1)
 
     def tf_layer(self, p: str, mode: str, src: Tensor, src_inv: Tensor, B: int, S: int, knn_self: dict,
                  cross: Optional[dict] = None, out: Optional[Tensor] = None) -> Tensor:

@@ -65,7 +65,8 @@ def knn_select(src_pose: Tensor, src_invalid: Tensor, tgt_pose: Tensor, tgt_inva
 def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, idx: Tensor, invalid: Tensor,
                 rel: Optional[Tensor], freq_xy: Tensor, B: int, S: int, D: int, H: int = 4,
                 kv1: Optional[Tensor] = None, T1: int = 0, div1: int = 1, K1: int = 0,
-                emb: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+                emb: Optional[Tensor] = None, out: Optional[Tensor] = None, fast_trig: bool = False
+                ) -> Tuple[Tensor, Tensor]:
     """KNARPE core. q/u/kv*: 2-D (possibly column-sliced, row-strided) views; returns (out [B*S, D+H*D] = [ov|z],
     none_valid bool [B*S])."""
     M = B * S
@@ -86,7 +87,7 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
         L.ptr(q), q.stride(0), L.ptr(u), u.stride(0), L.ptr(kv0), kv0.stride(0), T0, div0, K0,
         L.ptr(kv1), kv1.stride(0) if kv1 is not None else 0, T1, div1, K1, L.ptr(idx), L.ptr(inv), L.ptr(rel),
         L.ptr(emb), L.ptr(freq_xy), B, S, D, H, L.ptr(out), L.ptr(z), out.stride(0), L.ptr(_u8(none_valid)),
-        L.stream()), "tb_knarpe_attn")
+        int(fast_trig), L.stream()), "tb_knarpe_attn")
     _count()
     return out, none_valid
 
