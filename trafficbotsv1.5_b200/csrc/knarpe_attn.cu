@@ -135,6 +135,12 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
     __syncwarp();
 
     for (int g0 = 0; g0 < nvalid; g0 += G) {  // 32 % G == 0: slots g0..g0+G-1 are always staged
+      // ---- L1 prefetch of the NEXT group's K|V rows (G rows x 2*D*4 B = 32 lines for D=128: one line per lane), so
+      // that its gathers hit L1 instead of stalling on L2 (ncu v4: 21 % long-scoreboard stalls)
+      if (D == 128 && g0 + G < nvalid) {
+        const char* pf = reinterpret_cast<const char*>(s_ptr[warp][g0 + G + (lane >> 3)]) + (lane & 7) * 128;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+      }
       // ---- gather: K and V rows of the group in flight before first use
       float kr[G][NV], vr[G][NV];
 #pragma unroll
