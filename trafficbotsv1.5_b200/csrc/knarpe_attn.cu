@@ -212,25 +212,28 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
 #pragma unroll
       for (int g = 1; g < G; ++g) gm = fmaxf(gm, lg[g]);
       const float mn = fmaxf(mx, gm);  // finite: slot g0 is a valid neighbour
-      const float corr = ex2(mx - mn);
-      mx = mn;
       float pg[G], ps = 0.f;
 #pragma unroll
       for (int g = 0; g < G; ++g) { pg[g] = ex2(lg[g] - mn); ps += pg[g]; }
-      sm = fmaf(sm, corr, ps);
-      // rescale factors / probabilities of the other heads: slot i lives in lane ^ (8 i)
-      float cs[H];
-      cs[0] = corr;
+      if (__any_sync(TB_FULL_MASK, mn > mx)) {  // lazy rescale: only when some head's running max grew (warp-uniform)
+        const float corr = ex2(mx - mn);        // 1 for the heads whose max did not move, 0 on the first group
+        mx = mn;
+        sm *= corr;
+        // rescale factors of the other heads: slot i lives in lane ^ (8 i)
+        float cs[H];
+        cs[0] = corr;
 #pragma unroll
-      for (int i = 1; i < H; ++i) cs[i] = __shfl_xor_sync(TB_FULL_MASK, corr, 8 * i);
+        for (int i = 1; i < H; ++i) cs[i] = __shfl_xor_sync(TB_FULL_MASK, corr, 8 * i);
 #pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const float2 c2 = make_float2(cs[i], cs[i]);
+        for (int i = 0; i < H; ++i) {
+          const float2 c2 = make_float2(cs[i], cs[i]);
 #pragma unroll
-        for (int k = 0; k < NC / 2; ++k) z[i][k] = __fmul2_rn(z[i][k], c2);
+          for (int k = 0; k < NC / 2; ++k) z[i][k] = __fmul2_rn(z[i][k], c2);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ov[i] *= corr;
       }
-#pragma unroll
-      for (int i = 0; i < NV; ++i) ov[i] *= corr;
+      sm += ps;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         float pi[H];
