@@ -355,3 +355,15 @@ def test_linear_grouped_bias(M, N, K, g, prec):
     out = ops.linear(x.to(DEV), w.to(DEV), gb.to(DEV), relu=True, bias_group=g, precision=prec)
     tol = 1e-5 if prec == 0 else 4e-3
     close(out, ref.float(), tol, tol, f"grouped bias prec={prec}")
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 6, 384), (640, 5, 128), (300, 2, 128), (513, 17, 64)])
+def test_linear_tensor_core_narrow_outputs(M, N, K):
+    """N far below the 128-wide tile: the missing weight rows are TMA zero fill, the epilogue writes N columns only."""
+    g = torch.Generator().manual_seed(M + N)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    y = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    out = torch.full((M, N + 3), 7.0, device=DEV)
+    ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), out=out[:, :N], precision=1)
+    assert float((out[:, :N].cpu().double() - y).abs().max()) < 4e-3 * max(float(y.std()), 1.0)
+    assert float((out[:, N:] - 7.0).abs().max()) == 0.0  # nothing written past column N

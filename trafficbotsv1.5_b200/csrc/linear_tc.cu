@@ -6,8 +6,9 @@
 //   tile n+1. Persistent CTAs (one per SM) walk the (m, n) tiles n-fastest, so an A tile is fetched from HBM once and
 //   re-read from L2 by the neighbouring SMs; the epilogue transposes each 32x32 accumulator block through swizzled
 //   shared memory so that global stores / residual loads are full 128-byte lines.
-// Shapes the TMA/UMMA constraints do not cover (K or ldx not a multiple of 4 floats, N < 32, misaligned pointers)
-// are executed by the fp32 FFMA kernel instead (higher precision, same semantics).
+// Shapes the TMA constraints do not cover (K or ldx not a multiple of 4 floats, misaligned pointers) are executed by
+// the fp32 FFMA kernel instead (higher precision, same semantics). Narrow outputs (N = 2, 5, 6) run as one 128-wide
+// tile whose missing weight rows are TMA zero fill.
 #include <cuda.h>
 #include "common.cuh"
 
@@ -297,7 +298,7 @@ int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, int
                  int N, int K,
                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                  cudaStream_t st) {
-  const bool ok = (K % 4 == 0) && (ldx % 4 == 0) && N >= 32 && tb_aligned16(X) && tb_aligned16(W);
+  const bool ok = (K % 4 == 0) && (ldx % 4 == 0) && tb_aligned16(X) && tb_aligned16(W);
   if (!ok) return tb_linear_f32(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
   CUtensorMap mapA, mapB;
   if (!make_map(&mapA, X, M, K, ldx, BM) || !make_map(&mapB, W, N, K, K, BN)) return TB_ERR_CUDA;

@@ -70,6 +70,9 @@ class HotPathModel:
         # action head: first layers of the 3 type branches stacked (action_head.py:25-36)
         self.act_w0 = torch.cat([self.P[f"action_head.mlp_mean.{t}.fc_layers.0.weight"] for t in range(3)], 0)
         self.act_b0 = torch.cat([self.P[f"action_head.mlp_mean.{t}.fc_layers.0.bias"] for t in range(3)], 0)
+        self.act_w4 = torch.block_diag(*[self.P[f"action_head.mlp_mean.{t}.fc_layers.4.weight"] for t in range(3)]
+                                       ).contiguous()
+        self.act_b4 = torch.cat([self.P[f"action_head.mlp_mean.{t}.fc_layers.4.bias"] for t in range(3)], 0)
 
     @classmethod
     def from_state_dict(cls, sd: Dict[str, Tensor], d_model: int, theta_xy: float = 1e3, device="cuda",
@@ -349,12 +352,11 @@ class HotPathModel:
             h = self.mlp(cat_in, f"{prefix}.mlp", (0, 3, 6), True, mask_pre=zinv, res=cat_in[:, :d], out=cat_out)
         h0 = ops.linear(h, self.act_w0, self.act_b0, relu=True, precision=self.precision)            # action_head.py:78-82
         h1 = torch.empty_like(h0)
-        act = torch.empty(M, 6, device=self.dev)
         for t in range(3):
             self.lin(h0[:, t * d:(t + 1) * d], f"action_head.mlp_mean.{t}.fc_layers.2", relu=True,
                      out=h1[:, t * d:(t + 1) * d])
-            self.lin(h1[:, t * d:(t + 1) * d], f"action_head.mlp_mean.{t}.fc_layers.4", out=act[:, 2 * t:2 * t + 2])
-        return act
+        # last layers of the 3 type branches as ONE block-diagonal [6, 3d] projection of the stacked hidden rows
+        return ops.linear(h1, self.act_w4, self.act_b4, precision=self.precision)
 
 
 def _encode_polyline(pos: Tensor, dirv: Tensor) -> Tensor:
