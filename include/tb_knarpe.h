@@ -70,11 +70,16 @@ int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float
  *   pe_freq_xy: D/8 floats = PositionalEmbedding(dim=D/4, theta).freqs[::2] (utils/positional_emb.py:11)
  * flags bit 0: evaluate the embedding angles with the SFU's own range reduction (no 2-term Cody-Waite step): abs error
  *   grows with |angle| (<= ~2e-5 at 150 rad, the fp32 rounding of a 150 m coordinate); used with the tf32 projections.
+ * flags bit 1: tensor-core mode. kv0 / kv1 are IEEE fp16 tables (leading dims in halves, multiples of 8) as written
+ *   by tb_linear's Yh output, and all four contractions (q.k, u.e, sum a e, sum a v) run on mma.sync (f16 operands,
+ *   f32 accumulate; q, u and a are split into fp16 head + residual, k, v and e are rounded to fp16: 2^-11 relative
+ *   per component, the rounding a tf32 projection applies to its inputs anyway). Needs D == 128, rel != NULL and
+ *   K0 + K1 <= 128 (TB_ERR_UNSUPPORTED otherwise). Implies the bit-0 trig.
  * Limits: D in {128,256} (d_rpe == D), H == 4, all leading dims and pointers 16-byte aligned.
  * ------------------------------------------------------------------------------------------------- */
 int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
-                   const float* kv0, int ldkv0, int T0, int div0, int K0,
-                   const float* kv1, int ldkv1, int T1, int div1, int K1,
+                   const void* kv0, int ldkv0, int T0, int div0, int K0,
+                   const void* kv1, int ldkv1, int T1, int div1, int K1,
                    const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,
                    const float* pe_freq_xy, int B, int S, int D, int H,
                    float* out_ov, float* out_z, int ldo, uint8_t* out_none_valid, int flags, void* stream);
@@ -86,11 +91,14 @@ int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
  *   v = acc + bias[n]  (bias_group == 0)  or  acc + bias[(m / bias_group) * N + n]  (one bias row per group of
  *   bias_group consecutive rows: the PointNet "concat the group max" term W_right max_g + b, polyline_encoder.py:52);
  *   if relu: v = max(v,0); if mask_pre[m]: v = 0; if res: v += res[m*ldr+n]; if mask_post[m]: v = 0.
- * precision: 0 = fp32 FFMA (parity path), 1 = bf16 tcgen05 tensor cores with fp32 accumulate.
+ * precision: 0 = fp32 FFMA (parity path), 1 = tf32 tcgen05 tensor cores (fp32 operands read as tf32, fp32 accumulate).
+ * Yh (optional, precision 1 only): columns [col_h, N) of the result are written as IEEE fp16 to
+ *   Yh[row*ldyh + col - col_h] instead of Y (col_h a multiple of 32; col_h == 0 => Y may be NULL). This is how the
+ *   K|V tables consumed by tb_knarpe_attn flags bit 1 are produced without a conversion pass.
  * ------------------------------------------------------------------------------------------------- */
 int tb_linear(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
               int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
-              int precision, void* stream);
+              int precision, void* Yh, int ldyh, int col_h, void* stream);
 
 /* LayerNorm over the last dim (eps 1e-5, affine) — transformer_rpe.py:156-171. D in {128,256}. */
 int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy, int M, int D,

@@ -178,18 +178,22 @@ def test_pointnet(golden_ops):
 
 
 # ------------------------------------------------------------------------------------------------ KNARPE attention
-def _run_attention(sd, src, tgt, mask, rel, use_emb=False):
+def _run_attention(sd, src, tgt, mask, rel, use_emb=False, half_kv=False, **flags):
     """AttentionRPE semantics with an arbitrary pre-gathered tgt [B,S,K,d]: table = tgt flattened, idx = s*K+k."""
     B, S, K, d = tgt.shape
     P = {f"a.{k}": v for k, v in sd.items()}
     f = {k: v.to(DEV) for k, v in fuse_attention(P, "a", d).items()}
     proj = ops.linear(src.reshape(B * S, d).to(DEV), f["w_in_q"], f["b_in_q"])
-    kv = ops.linear(tgt.reshape(B * S * K, d).to(DEV), f["w_kv"], f["b_kv"])
+    if half_kv:  # tensor-core mode: the projection writes the fp16 table (tf32 MMA), the attention runs on mma.sync
+        kv = torch.empty(B * S * K, 2 * d, dtype=torch.float16, device=DEV)
+        ops.linear(tgt.reshape(B * S * K, d).to(DEV), f["w_kv"], f["b_kv"], precision=1, out_h=kv, col_h=0)
+    else:
+        kv = ops.linear(tgt.reshape(B * S * K, d).to(DEV), f["w_kv"], f["b_kv"])
     idx = torch.arange(S * K, dtype=torch.int32, device=DEV).view(1, S, K).expand(B, -1, -1).contiguous()
     freq = ops.pe_freq_xy(d, 1e3, DEV)
     emb = O.pose_emb_xy_yaw(rel[..., :2], rel[..., 2], d).to(DEV).contiguous() if use_emb else None
     o, nv = ops.knarpe_attn(proj[:, :d], proj[:, d:], kv, S * K, 1, K, idx, mask.to(DEV).contiguous(),
-                            None if use_emb else rel.to(DEV).contiguous(), freq, B, S, d, H, emb=emb)
+                            None if use_emb else rel.to(DEV).contiguous(), freq, B, S, d, H, emb=emb, **flags)
     out = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv)
     return out.view(B, S, d), nv.view(B, S)
 
@@ -227,6 +231,32 @@ def test_attention_vs_oracle_and_properties(d, B, S, K):
     perm = torch.randperm(K, generator=g)
     out_p, _ = _run_attention(sd, src, tgt[:, :, perm], mask[:, :, perm], rel[:, :, perm])
     close(out_p, out, 1e-5, 1e-5 * scale, "permutation invariance")
+
+
+@pytest.mark.parametrize("B,S,K,p_mask", [(2, 130, 89, 0.3), (1, 64, 25, 0.0), (3, 33, 1, 0.0), (1, 50, 64, 0.9),
+                                          (2, 40, 112, 0.5)])
+def test_attention_tensor_core(B, S, K, p_mask):
+    """flags bit 1: fp16 K|V tables (written by the tf32 projection) and all four contractions on mma.sync with fp16
+    k / v / e and split-fp16 q / u / p. Error budget = 2^-11 relative rounding of k, v, e + the tf32 table projection:
+    3e-3 of the output scale, 1e-3 in L2 (same order as a tf32 projection, see test_linear_tensor_core)."""
+    d = 128
+    g = torch.Generator().manual_seed(K + S)
+    shapes = {"in_proj_weight": (3 * d, d), "in_proj_bias": (3 * d,), "out_proj_weight": (d, d), "out_proj_bias": (d,),
+              "linear_rpe.weight": (2 * d, d), "linear_rpe.bias": (2 * d,)}
+    sd = params.rand_like_state_dict(shapes, 22)
+    src, tgt = torch.randn(B, S, d, generator=g), torch.randn(B, S, K, d, generator=g)
+    mask = torch.rand(B, S, K, generator=g) < p_mask
+    mask[0, 1] = True
+    rel = torch.cat([(torch.rand(B, S, K, 2, generator=g) * 2 - 1) * 300, (torch.rand(B, S, K, 1, generator=g) * 2 - 1) * 3.2], -1)
+    P = {f"a.{k}": v for k, v in sd.items()}
+    ref = O.attention_rpe(P, "a", src, tgt, mask, O.pose_emb_xy_yaw(rel[..., :2], rel[..., 2], d), H)
+    out, nv = _run_attention(sd, src, tgt, mask, rel, half_kv=True, fast_trig=True)
+    scale = float(ref.abs().max())
+    print("tensor-core attention: max abs / scale", float((out.cpu() - ref).abs().max()) / scale, "rel_l2", rel_l2(out, ref))
+    close(out, ref, 3e-3, 3e-3 * scale, "tensor-core attention vs oracle")
+    assert rel_l2(out, ref) < 1e-3
+    assert bool(nv[0, 1]) and float(out[0, 1].abs().max()) == 0.0
+    assert torch.equal(nv.cpu(), mask.all(-1))
 
 
 def _block_P(g):
@@ -367,3 +397,22 @@ def test_linear_tensor_core_narrow_outputs(M, N, K):
     ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), out=out[:, :N], precision=1)
     assert float((out[:, :N].cpu().double() - y).abs().max()) < 4e-3 * max(float(y.std()), 1.0)
     assert float((out[:, N:] - 7.0).abs().max()) == 0.0  # nothing written past column N
+
+
+def test_linear_fp16_split_output():
+    """tb_linear Yh: columns >= col_h as fp16 into a second buffer (how the K|V tables of the tensor-core mode are made)."""
+    g = torch.Generator().manual_seed(5)
+    M, N, K, col_h = 1000, 896, 128, 640
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    y = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    yh = torch.full((M, N - col_h + 8), 3.0, dtype=torch.float16, device=DEV)
+    y32 = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), precision=1, out_h=yh[:, :N - col_h], col_h=col_h)
+    assert y32.shape == (M, col_h)
+    assert float((y32.cpu().double() - y[:, :col_h]).abs().max()) < 4e-3 * float(y.std())
+    assert float((yh[:, :N - col_h].cpu().double() - y[:, col_h:]).abs().max()) < 6e-3 * float(y.std())
+    assert float((yh[:, N - col_h:].float() - 3.0).abs().max()) == 0.0
+    tbl = torch.empty(M, N, dtype=torch.float16, device=DEV)          # col_h = 0: everything fp16, no fp32 output
+    assert ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), precision=1, out_h=tbl, col_h=0) is None
+    assert float((tbl.cpu().double() - y).abs().max()) < 6e-3 * float(y.std())
+    with pytest.raises(RuntimeError):                                  # the fp32 parity path has no fp16 output
+        ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), precision=0, out_h=tbl, col_h=0)

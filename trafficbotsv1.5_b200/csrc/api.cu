@@ -8,7 +8,7 @@ int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, in
 int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
                  int N, int K,
                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
-                 cudaStream_t st);
+                 void* Yh, int ldyh, int colh, cudaStream_t st);
 
 extern "C" const char* tb_strerror(int code) {
   switch (code) {
@@ -27,13 +27,20 @@ extern "C" int tb_version(void) { return 100; }
 
 extern "C" int tb_linear(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy,
                          int M, int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
-                         int precision, void* stream) {
-  if (!X || !W || !Y) return TB_ERR_NULL;
-  if (M <= 0 || N <= 0 || K <= 0 || ldx < K || ldy < N || (res && ldr < N) || bias_group < 0) return TB_ERR_BAD_SHAPE;
+                         int precision, void* Yh, int ldyh, int col_h, void* stream) {
+  if (!X || !W) return TB_ERR_NULL;
+  const int n32 = Yh ? col_h : N;  // columns written to the fp32 output
+  if (M <= 0 || N <= 0 || K <= 0 || ldx < K || (res && ldr < N) || bias_group < 0) return TB_ERR_BAD_SHAPE;
+  if (Yh && (col_h < 0 || col_h >= N || (col_h & 31) || ldyh < N - col_h)) return TB_ERR_BAD_SHAPE;
+  if (n32 > 0 && (!Y || ldy < n32)) return Y ? TB_ERR_BAD_SHAPE : TB_ERR_NULL;
+  if (Yh && ((reinterpret_cast<uintptr_t>(Yh) & 1) != 0)) return TB_ERR_MISALIGNED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (precision == 0)
+  if (precision == 0) {
+    if (Yh) return TB_ERR_UNSUPPORTED;  // fp16 tables belong to the tensor-core mode
     return tb_linear_f32(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+  }
   if (precision == 1)
-    return tb_linear_tc(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+    return tb_linear_tc(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, Yh, ldyh,
+                        col_h, st);
   return TB_ERR_UNSUPPORTED;
 }

@@ -288,11 +288,21 @@ int launch(const float* q, int ldq, const float* u, int ldu, const float* kv0, i
 
 }  // namespace
 
-extern "C" int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu, const float* kv0, int ldkv0, int T0,
-                              int div0, int K0, const float* kv1, int ldkv1, int T1, int div1, int K1,
+// tensor-core variant (knarpe_attn_mma.cu)
+int tb_knarpe_attn_mma_launch(const float* q, int ldq, const float* u, int ldu, const void* kv0, int ldkv0, int T0,
+                              int div0, int K0, const void* kv1, int ldkv1, int T1, int div1, int K1,
+                              const int32_t* idx, const uint8_t* invalid, const float* rel, const float* pe_freq_xy,
+                              int B, int S, float* out_ov, float* out_z, int ldo, uint8_t* out_none_valid,
+                              cudaStream_t st);
+bool tb_knarpe_attn_mma_supported(int D, int Hh, int Ktot);
+
+extern "C" int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu, const void* kv0_, int ldkv0, int T0,
+                              int div0, int K0, const void* kv1_, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,
                               const float* pe_freq_xy, int B, int S, int D, int Hh, float* out_ov, float* out_z,
                               int ldo, uint8_t* out_none_valid, int flags, void* stream) {
+  const float* kv0 = static_cast<const float*>(kv0_);
+  const float* kv1 = static_cast<const float*>(kv1_);
   if (!q || !u || !kv0 || !idx || !invalid || !out_ov || !out_z || !pe_freq_xy) return TB_ERR_NULL;
   if ((rel == nullptr) == (emb == nullptr)) return TB_ERR_NULL;  // exactly one
   if (B <= 0 || S <= 0 || K0 <= 0 || K1 < 0 || T0 <= 0 || div0 <= 0 || (K1 > 0 && (!kv1 || T1 <= 0 || div1 <= 0)))
@@ -307,6 +317,12 @@ extern "C" int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu, 
 #define TB_ATT_ARGS q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1, T1, div1, K1, idx, invalid, rel, emb, \
                     pe_freq_xy, B, S, out_ov, out_z, ldo, out_none_valid, st
   const bool fast = (flags & 1) != 0;  // bit 0: SFU-only range reduction of the embedding angles (tensor-core mode)
+  if (flags & 2) {  // bit 1: fp16 K|V tables, all contractions on mma.sync (knarpe_attn_mma.cu)
+    if (!rel || !tb_knarpe_attn_mma_supported(D, Hh, K0 + K1)) return TB_ERR_UNSUPPORTED;
+    if ((ldkv0 | (K1 > 0 ? ldkv1 : 0)) & 7) return TB_ERR_MISALIGNED;
+    return tb_knarpe_attn_mma_launch(q, ldq, u, ldu, kv0_, ldkv0, T0, div0, K0, kv1_, ldkv1, T1, div1, K1, idx, invalid,
+                                     rel, pe_freq_xy, B, S, out_ov, out_z, ldo, out_none_valid, st);
+  }
   if (D == 128) {
     if (!rel) return launch<128, true, false>(TB_ATT_ARGS);
     return fast ? launch<128, false, true>(TB_ATT_ARGS) : launch<128, false, false>(TB_ATT_ARGS);

@@ -10,6 +10,7 @@
 // the fp32 FFMA kernel instead (higher precision, same semantics). Narrow outputs (N = 2, 5, 6) run as one 128-wide
 // tile whose missing weight rows are TMA zero fill.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
@@ -31,6 +32,7 @@ constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES +
 
 struct Epi {
   const float* bias; int bgroup; int relu; const uint8_t* mask_pre; const float* res; int ldr; const uint8_t* mask_post;
+  __half* yh; int ldyh; int colh;  // columns >= colh (multiple of 32) are written as fp16 to yh[row*ldyh + col - colh]
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -162,6 +164,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const int quarter = warp & 3, half = warp >> 2;
     float* st = sE + warp * (32 * 32);  // this warp's 32x32 staging block, 16-byte chunks XOR-swizzled by row
     const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
+                        (!ep.yh || (((ep.ldyh & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.yh) & 7) == 0))) &&
                         (!ep.res || (((ep.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.res) & 15) == 0))) &&
                         (!ep.bias || (((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) && (!ep.bgroup || (N & 3) == 0)));
     const int rsub = lane >> 3, cc = lane & 7;  // store phase: lane -> (row i*4 + rsub, 16-byte chunk cc)
@@ -213,6 +216,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           *reinterpret_cast<uint4*>(st + lane * 32 + ((c ^ (lane & 7)) << 2)) =
               make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
         __syncwarp();
+        const bool to_h = ep.yh != nullptr && cbase >= ep.colh;  // warp-uniform: colh is a multiple of 32
         if (vec_ok && cbase + 32 <= N) {
           const int col = cbase + cc * 4;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -230,7 +234,13 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
               }
               if (ep.mask_post && ep.mask_post[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
-              *reinterpret_cast<float4*>(Y + (size_t)row * ldy + col) = v;
+              if (to_h) {
+                const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                *reinterpret_cast<uint2*>(ep.yh + (size_t)row * ep.ldyh + (col - ep.colh)) =
+                    make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+              } else {
+                *reinterpret_cast<float4*>(Y + (size_t)row * ldy + col) = v;
+              }
             }
           }
         } else {  // N tail / unaligned views: scalar, bounds-checked
@@ -244,7 +254,8 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               if (ep.mask_pre && ep.mask_pre[row]) t = 0.f;
               if (ep.res) t += ep.res[(size_t)row * ep.ldr + col];
               if (ep.mask_post && ep.mask_post[row]) t = 0.f;
-              Y[(size_t)row * ldy + col] = t;
+              if (to_h) ep.yh[(size_t)row * ep.ldyh + (col - ep.colh)] = __float2half_rn(t);
+              else Y[(size_t)row * ldy + col] = t;
             }
           }
         }
@@ -297,9 +308,12 @@ bool make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, in
 int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
                  int N, int K,
                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
-                 cudaStream_t st) {
+                 void* Yh, int ldyh, int colh, cudaStream_t st) {
   const bool ok = (K % 4 == 0) && (ldx % 4 == 0) && tb_aligned16(X) && tb_aligned16(W);
-  if (!ok) return tb_linear_f32(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+  if (!ok) {
+    if (Yh) return TB_ERR_UNSUPPORTED;  // the fp32 kernel has no fp16 output path
+    return tb_linear_f32(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+  }
   CUtensorMap mapA, mapB;
   if (!make_map(&mapA, X, M, K, ldx, BM) || !make_map(&mapB, W, N, K, K, BN)) return TB_ERR_CUDA;
   static bool attr_set = false;
@@ -319,7 +333,7 @@ int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, int
   }
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms ? total : num_sms;  // persistent: one CTA per SM
-  Epi ep{bias, bias_group, relu, mask_pre, res, ldr, mask_post};
+  Epi ep{bias, bias_group, relu, mask_pre, res, ldr, mask_post, static_cast<__half*>(Yh), ldyh, colh};
   linear_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
   TB_CHECK_LAUNCH();
   return TB_OK;

@@ -13,7 +13,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("TB_LIB", os.path.join(_PKG, "libtbknarpe.so"))
-_SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu",
+_SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "knarpe_attn_mma.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu",
             "rollout_step.cu", "rule_check.cu"]
 _lib = None
 
@@ -54,7 +54,7 @@ def load() -> ctypes.CDLL:
     sig = {
         "tb_knn_select": [P, P, P, P, I, I, I, I, I, F, P, P, P, I, I, P],
         "tb_knarpe_attn": [P, I, P, I, P, I, I, I, I, P, I, I, I, I, P, P, P, P, P, I, I, I, I, P, P, I, P, I, P],
-        "tb_linear": [P, I, P, P, I, P, I, I, I, I, I, P, P, I, P, I, P],
+        "tb_linear": [P, I, P, P, I, P, I, I, I, I, I, P, P, I, P, I, P, I, I, P],
         "tb_layernorm": [P, I, P, P, P, I, I, I, P],
         "tb_pointnet_pool": [P, I, P, I, I, I, I, P, I, P],
         "tb_pose_emb": [P, P, I, P, I, I, P, I, P],

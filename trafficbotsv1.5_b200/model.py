@@ -58,6 +58,7 @@ class HotPathModel:
     def __init__(self, P: Dict[str, Tensor], cfg: dict, sizes: dict, device="cuda", precision: int = 0):
         self.cfg, self.sz, self.dev, self.precision = cfg, sizes, torch.device(device), precision
         self.d = cfg["hidden_dim"]
+        self.kv_half = precision == 1 and self.d == 128  # fp16 K|V tables + tensor-core attention (tb_knarpe_attn bit 1)
         self.W = cfg["temp_window_size"]
         self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in P.items()}
         self.fa: Dict[str, Dict[str, Tensor]] = {}
@@ -81,6 +82,7 @@ class HotPathModel:
         self = cls.__new__(cls)
         self.cfg, self.sz, self.dev, self.precision = None, None, torch.device(device), precision
         self.d, self.W = d_model, None
+        self.kv_half = precision == 1 and d_model == 128
         self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in sd.items()}
         self.fa = {}
         for k in sd:
@@ -133,7 +135,22 @@ class HotPathModel:
     def kv_table(self, feat: Tensor, layer_prefix: str, norm: str, attn: str = "attn") -> Tensor:
         """K/V rows of a target table for one layer: W_kv LN(x) + b  (project-once-then-gather)."""
         f = self.fa[f"{layer_prefix}.{attn}"]
-        return ops.linear(self.ln(feat, f"{layer_prefix}.{norm}"), f["w_kv"], f["b_kv"], precision=self.precision)
+        x = self.ln(feat, f"{layer_prefix}.{norm}")
+        if self.kv_half:  # tensor-core mode: fp16 tables straight from the projection's epilogue
+            tbl = torch.empty(x.shape[0], 2 * self.d, dtype=torch.float16, device=x.device)
+            ops.linear(x, f["w_kv"], f["b_kv"], precision=1, out_h=tbl, col_h=0)
+            return tbl
+        return ops.linear(x, f["w_kv"], f["b_kv"], precision=self.precision)
+
+    def _in_self(self, f, x):
+        """[q|u] (fp32) and the token's own [k|v] rows from one projection; k|v are fp16 in tensor-core mode."""
+        nq = self.d + H * self.d
+        if self.kv_half:
+            kv = torch.empty(x.shape[0], 2 * self.d, dtype=torch.float16, device=x.device)
+            proj = ops.linear(x, f["w_in_self"], f["b_in_self"], precision=1, out_h=kv, col_h=nq)
+            return proj, kv
+        proj = ops.linear(x, f["w_in_self"], f["b_in_self"], precision=self.precision)
+        return proj, proj[:, nq:]
 
     def _attend(self, fa, proj, B, S, kv0, T0, div0, K0, knn, kv1=None, T1=0, div1=1, K1=0):
         d = self.d
@@ -147,8 +164,8 @@ class HotPathModel:
         d, pr = self.d, self.precision
         if mode == "dec_cross_attn":
             f = self.fa[f"{p}.attn_src"]
-            proj = ops.linear(self.ln(src, f"{p}.norm_src"), f["w_in_self"], f["b_in_self"], precision=pr)
-            o, nv = self._attend(f, proj, B, S, proj[:, d + H * d:], S, 1, knn_self["idx"].shape[-1], knn_self)
+            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm_src"))
+            o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
             f = self.fa[f"{p}.attn"]
             proj = ops.linear(self.ln(src, f"{p}.norm1"), f["w_in_q"], f["b_in_q"], precision=pr)
@@ -157,8 +174,8 @@ class HotPathModel:
             src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
         else:  # enc_self_attn: q and k/v both from norm1(src) (:218-221)
             f = self.fa[f"{p}.attn"]
-            proj = ops.linear(self.ln(src, f"{p}.norm1"), f["w_in_self"], f["b_in_self"], precision=pr)
-            o, nv = self._attend(f, proj, B, S, proj[:, d + H * d:], S, 1, knn_self["idx"].shape[-1], knn_self)
+            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm1"))
+            o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
         h = self.lin(self.ln(src, f"{p}.norm2"), f"{p}.linear1", relu=True)
         return self.lin(h, f"{p}.linear2", res=src, mask_post=src_inv, out=out)

@@ -68,10 +68,13 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
                 emb: Optional[Tensor] = None, out: Optional[Tensor] = None, fast_trig: bool = False
                 ) -> Tuple[Tensor, Tensor]:
     """KNARPE core. q/u/kv*: 2-D (possibly column-sliced, row-strided) views; returns (out [B*S, D+H*D] = [ov|z],
-    none_valid bool [B*S])."""
+    none_valid bool [B*S]). float16 kv tables select the tensor-core kernel (tb_knarpe_attn flags bit 1)."""
     M = B * S
-    for t in (q, u, kv0) + ((kv1,) if kv1 is not None else ()):
+    rpe_mma = kv0.dtype == torch.float16
+    for t in (q, u):
         assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
+    for t in (kv0,) + ((kv1,) if kv1 is not None else ()):
+        assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == kv0.dtype and t.dtype in (torch.float32, torch.float16)
     if out is None:
         out = torch.empty(M, D + H * D, dtype=torch.float32, device=q.device)
     none_valid = torch.empty(M, dtype=torch.bool, device=q.device)
@@ -87,29 +90,36 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
         L.ptr(q), q.stride(0), L.ptr(u), u.stride(0), L.ptr(kv0), kv0.stride(0), T0, div0, K0,
         L.ptr(kv1), kv1.stride(0) if kv1 is not None else 0, T1, div1, K1, L.ptr(idx), L.ptr(inv), L.ptr(rel),
         L.ptr(emb), L.ptr(freq_xy), B, S, D, H, L.ptr(out), L.ptr(z), out.stride(0), L.ptr(_u8(none_valid)),
-        int(fast_trig), L.stream()), "tb_knarpe_attn")
+        int(fast_trig) | (2 if rpe_mma else 0), L.stream()), "tb_knarpe_attn")
     _count()
     return out, none_valid
 
 
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False, mask_pre: Optional[Tensor] = None,
            res: Optional[Tensor] = None, mask_post: Optional[Tensor] = None, out: Optional[Tensor] = None,
-           precision: int = 0, bias_group: int = 0) -> Tensor:
-    """Y = epilogue(X W^T + b) on 2-D row-strided views (see tb_linear)."""
+           precision: int = 0, bias_group: int = 0, out_h: Optional[Tensor] = None, col_h: int = 0) -> Tensor:
+    """Y = epilogue(X W^T + b) on 2-D row-strided views (see tb_linear). With `out_h` (float16 [M, N - col_h]) the
+    columns >= col_h go there instead (tensor-core mode only) and `out` holds the first col_h columns
+    (returned; None when col_h == 0)."""
     assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.dtype == torch.float32
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K, (w.shape, x.shape)
-    if out is None:
-        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
-    assert out.stride(1) == 1 and out.shape[0] == M and out.shape[1] == N
+    n32 = N if out_h is None else col_h
+    if out is None and n32 > 0:
+        out = torch.empty(M, n32, dtype=torch.float32, device=x.device)
+    assert out is None or (out.stride(1) == 1 and out.shape[0] == M and out.shape[1] == n32)
+    if out_h is not None:
+        assert out_h.dtype == torch.float16 and out_h.stride(1) == 1 and out_h.shape == (M, N - col_h)
     if res is not None:
         assert res.stride(1) == 1 and res.shape == (M, N)
     if bias_group:
         assert b is not None and b.is_contiguous() and b.shape == ((M + bias_group - 1) // bias_group, N), b.shape
-    L.check(L.load().tb_linear(L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), bias_group, L.ptr(out), out.stride(0), M, N, K,
+    L.check(L.load().tb_linear(L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), bias_group, L.ptr(out),
+                               out.stride(0) if out is not None else 0, M, N, K,
                                int(relu), L.ptr(_u8(mask_pre)), L.ptr(res), res.stride(0) if res is not None else 0,
-                               L.ptr(_u8(mask_post)), precision, L.stream()), "tb_linear")
+                               L.ptr(_u8(mask_post)), precision, L.ptr(out_h),
+                               out_h.stride(0) if out_h is not None else 0, col_h, L.stream()), "tb_linear")
     _count()
     return out
 

@@ -229,6 +229,9 @@ class TransformerBlockRPE(nn.Module, _FusedMixin):
             idx2 = torch.arange(S * K2, dtype=torch.int32, device=src.device).view(1, S, K2).expand(B, -1, -1)
             cross = _knn_dict(idx2, tgt_padding_mask, rpe, self.d_rpe)
             table = tgt.reshape(B * S * K2, d).float().contiguous()
+        # fp16 K|V tables + tensor-core attention need the in-kernel embedding and <= 128 neighbours per token
+        m.kv_half = (m.precision == 1 and d == 128 and "rel" in knn_self and knn_self["idx"].shape[-1] <= 128 and
+                     (cross is None or ("rel" in cross and cross["idx"].shape[-1] <= 128)))
         for i in range(len(self.layers)):
             p = f"layers.{i}"
             c = None
