@@ -11,15 +11,15 @@
 // Here they run on mma.sync.m16n8k16 (f16 operands, f32 accumulate) with every operand built IN FRAGMENT LAYOUT in
 // registers - nothing is staged through shared memory:
 //   * a group = 16 compacted neighbours = two 8-wide MMA tiles. Lane (g = lane>>2, t = lane&3) owns neighbours g and
-//     g+8: it loads 16-byte pieces of their fp16 K and V rows that are exactly its B-fragment registers, and evaluates
-//     the cos/sin of 16 embedding angles per neighbour - the B-fragment elements (k = channel slot, n = neighbour) of
-//     the u.e MMA. The yaw harmonics of a lane form arithmetic progressions: 6 SFU evaluations + 7 plane rotations
+//     g+8: it loads 16-byte pieces of their fp16 K and V rows that are exactly its A-fragment registers, and evaluates
+//     the cos/sin of 16 embedding angles per neighbour - the A-fragment elements (m = neighbour, k = channel slot) of
+//     the e.u MMA. The yaw harmonics of a lane form arithmetic progressions: 6 SFU evaluations + 7 plane rotations
 //     replace 32 SFU evaluations; the geometric x/y frequencies are evaluated directly.
-//   * logits^T [16 x 16 nbr] = A(q, block-diagonal over heads) B(k) + A(u) B(e): A rows 0-3 hold fp16(operand), rows
-//     4-7 its fp16 residual (rows 8-15 zero), so q and u keep ~22 significant bits; one shuffle adds the row blocks.
-//   * the accumulator layout of the logits IS the B-fragment layout of z^T [128 x 8] = A(e^T) B(p^T) and of
-//     ov^T [32 x 8] = sum_heads A(v_head^T) B(p^T masked to that head): columns 0-3 take fp16(p_h), columns 4-7 the
-//     residual; the transposed A fragments come from movmatrix (register-only 8x8 transposes).
+//   * logits [16 nbr x 8] = A(k) B(q, block-diagonal over heads) + A(e) B(u): B columns 0-3 hold fp16(operand) of
+//     heads 0-3, columns 4-7 its fp16 residual, so q and u keep ~22 significant bits; one shuffle adds the halves.
+//   * z^T [128 x 8] = A(e^T) B(p^T) and ov^T [32 x 8] = sum_heads A(v_head^T) B(p^T masked to that head): columns 0-3
+//     take fp16(p_h), columns 4-7 the residual; the transposed fragments (e^T, v^T, p^T) come from movmatrix
+//     (register-only 8x8 transposes).
 // Channel "slots" inside a 16-wide MMA chunk are permutations of the reference orders (embedding:
 // utils/pose_emb.py:50-55 [cos x|sin x|cos y|sin y|cos yaw|sin yaw]); q/u are read and ov/z written through the same
 // permutations, so the C ABI layouts are unchanged.
@@ -96,68 +96,66 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
   const int b = tok / S;
   const int Ktot = K0 + K1;
   const int g = lane >> 2, t = lane & 3;
-  const int hA = g & 3;               // head of this lane's accumulator row / column and softmax state
-  const bool lo_part = (g & 4) != 0;  // rows / columns 4-7: fp16 residual operands
+  const int hA = g & 3;               // operand column g <-> head hA ...
+  const bool lo_part = (g & 4) != 0;  // ... columns 4-7: fp16 residual operands
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  // ---- per-token operands in A-fragment layout
+  // ---- neighbour list: every load of the row is issued before the first use (Ktot <= 128: at most 4 chunks of 32)
+  const size_t prow = (size_t)tok * Ktot;
+  const __half* kb0 = kv0 + (size_t)(b / div0) * T0 * ldkv0;
+  const __half* kb1 = (K1 > 0) ? kv1 + (size_t)(b / div1) * T1 * ldkv1 : kb0;
+  uint8_t n_inv[4];
+  int n_id[4];
+  float n_rel[4][3];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int j = c * 32 + lane;
+    n_inv[c] = 1; n_id[c] = 0; n_rel[c][0] = n_rel[c][1] = n_rel[c][2] = 0.f;
+    if (j < Ktot) {
+      const size_t p = prow + j;
+      n_inv[c] = __ldg(invalid + p);
+      n_id[c] = __ldg(idx + p);
+      n_rel[c][0] = __ldg(rel + p * 3 + 0);
+      n_rel[c][1] = __ldg(rel + p * 3 + 1);
+      n_rel[c][2] = __ldg(rel + p * 3 + 2);
+    }
+  }
+  // ---- per-token operands (loads in flight across the compaction)
   float fq[2][2];  // x/y frequencies of this lane's slots: chunk c (0/1), slot pair j
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     fq[c][0] = __ldg(pe_freq_xy + 8 * c + 2 * t);
     fq[c][1] = __ldg(pe_freq_xy + 8 * c + 2 * t + 1);
   }
-  uint32_t uA[8][2];  // u: registers a0, a2 of chunk c (a1 = a3 = 0)
+  float2 u_raw[8][2];
   {
     const float* up = u + (size_t)tok * ldu + hA * D + 2 * t;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const float2 a = __ldg(reinterpret_cast<const float2*>(up + cos_base(c)));
-      const float2 s = __ldg(reinterpret_cast<const float2*>(up + sin_base(c)));
-      uA[c][0] = split_h2(a.x, a.y, lo_part);
-      uA[c][1] = split_h2(s.x, s.y, lo_part);
+      u_raw[c][0] = __ldg(reinterpret_cast<const float2*>(up + cos_base(c)));
+      u_raw[c][1] = __ldg(reinterpret_cast<const float2*>(up + sin_base(c)));
     }
   }
-  uint32_t qA[2][2];  // q of head hA, channels 32 hA + 8 t + [0, 8): chunk (2 hA + e) registers a0, a2
-  {
-    const float* qp = q + (size_t)tok * ldq + 32 * hA + 8 * t;
-    const float4 a = ldg4(qp), c = ldg4(qp + 4);
-    qA[0][0] = split_h2(a.x, a.y, lo_part);
-    qA[0][1] = split_h2(a.z, a.w, lo_part);
-    qA[1][0] = split_h2(c.x, c.y, lo_part);
-    qA[1][1] = split_h2(c.z, c.w, lo_part);
-  }
-  float zacc[8][4], oacc[2][4];
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) zacc[c][r] = 0.f;
-#pragma unroll
-  for (int m = 0; m < 2; ++m)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) oacc[m][r] = 0.f;
-  float mx = -INFINITY, sm = 0.f;
+  const float* qp = q + (size_t)tok * ldq + 32 * hA + 8 * t;
+  const float4 q_lo4 = ldg4(qp), q_hi4 = ldg4(qp + 4);
 
-  // ---- compact the unmasked neighbours of the whole row; pad to a multiple of 16 with weight-0 dummies
-  const size_t prow = (size_t)tok * Ktot;
-  const __half* kb0 = kv0 + (size_t)(b / div0) * T0 * ldkv0;
-  const __half* kb1 = (K1 > 0) ? kv1 + (size_t)(b / div1) * T1 * ldkv1 : kb0;
+  // ---- compact the unmasked neighbours; pad to a multiple of 16 with weight-0 dummies
   int nvalid = 0;
-  for (int c0 = 0; c0 < Ktot; c0 += 32) {
-    const int j = c0 + lane;
-    bool valid = false;
-    if (j < Ktot) valid = invalid[prow + j] == 0;
-    const unsigned vb = __ballot_sync(TB_FULL_MASK, valid);
-    if (valid) {
-      const size_t p = prow + j;
-      const int id = idx[p];
-      const int pos = nvalid + __popc(vb & lt_mask);
-      s_ptr[pos] = (j < K0) ? kb0 + (size_t)id * ldkv0 : kb1 + (size_t)id * ldkv1;
-      s_rel[pos][0] = rel[p * 3 + 0];
-      s_rel[pos][1] = rel[p * 3 + 1];
-      s_rel[pos][2] = rel[p * 3 + 2];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c * 32 < Ktot) {  // warp-uniform
+      const int j = c * 32 + lane;
+      const bool valid = n_inv[c] == 0;
+      const unsigned vb = __ballot_sync(TB_FULL_MASK, valid);
+      if (valid) {
+        const int pos = nvalid + __popc(vb & lt_mask);
+        s_ptr[pos] = (j < K0) ? kb0 + (size_t)n_id[c] * ldkv0 : kb1 + (size_t)n_id[c] * ldkv1;
+        s_rel[pos][0] = n_rel[c][0];
+        s_rel[pos][1] = n_rel[c][1];
+        s_rel[pos][2] = n_rel[c][2];
+      }
+      nvalid += __popc(vb);
     }
-    nvalid += __popc(vb);
   }
   const int npad = (nvalid + 15) & ~15;
   if (lane < npad - nvalid) {
@@ -168,10 +166,35 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
   }
   __syncwarp();
 
+  // B fragments of u (chunk c: b0 = slots 2t,2t+1, b1 = slots 2t+8,2t+9; column g = head hA, residual for g >= 4) and
+  // of the block-diagonal q (chunks 2 hA + e only; other chunks are zero for this column)
+  uint32_t uB[8][2], qB[2][2];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uB[c][0] = split_h2(u_raw[c][0].x, u_raw[c][0].y, lo_part);
+    uB[c][1] = split_h2(u_raw[c][1].x, u_raw[c][1].y, lo_part);
+  }
+  qB[0][0] = split_h2(q_lo4.x, q_lo4.y, lo_part);
+  qB[0][1] = split_h2(q_lo4.z, q_lo4.w, lo_part);
+  qB[1][0] = split_h2(q_hi4.x, q_hi4.y, lo_part);
+  qB[1][1] = split_h2(q_hi4.z, q_hi4.w, lo_part);
+
+  float zacc[8][4], oacc[2][4];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) zacc[c][r] = 0.f;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) oacc[m][r] = 0.f;
+  // softmax state of the heads of this lane's accumulator columns 2t, 2t+1: heads 2 (t&1), 2 (t&1) + 1
+  float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f};
+
   for (int g0 = 0; g0 < npad; g0 += 16) {
     const int nb = nvalid - g0;  // valid neighbours in this group (>= 1; may exceed 16)
-    // ---- K fragments: row of neighbour g0 + 8 tile + g, 16 B at halves [32 i + 8 t, +8) = B registers of the chunks
-    // 2i (x, y) and 2i+1 (z, w) of the block-diagonal q.k MMA
+    // ---- K pieces: row of neighbour g0 + 8 tile + g, 16 B at halves [32 i + 8 t, +8): A registers (a0|a2 for tile 0,
+    // a1|a3 for tile 1) of the chunks 2i (x, y) and 2i+1 (z, w) of the q.k MMA
     const __half* rowp[2];
     uint4 kf[2][4];
 #pragma unroll
@@ -181,9 +204,9 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
       for (int i = 0; i < 4; ++i) kf[tile][i] = ldg128(rowp[tile] + 32 * i + 8 * t);
     }
 
-    // ---- relative-pose embedding in B-fragment layout: eB[chunk][tile] = {slots 2t,2t+1 | slots 2t+8,2t+9} of
-    // neighbour g0 + 8 tile + g. chunks 0-1: x, 2-3: y, 4-7: yaw; slots 0-7 cos, 8-15 sin of the same 8 angles
-    uint32_t eB[8][2][2];
+    // ---- relative-pose embedding in A-fragment layout: eA[chunk] = {a0, a1, a2, a3} = {slots 2t,2t+1 of neighbour g,
+    // of neighbour g+8, slots 2t+8,2t+9 of g, of g+8}. chunks 0-1: x, 2-3: y, 4-7: yaw; slots 0-7 cos, 8-15 sin
+    uint32_t eA[8][4];
 #pragma unroll
     for (int tile = 0; tile < 2; ++tile) {
       const float* rp = s_rel[g0 + tile * 8 + g];
@@ -193,103 +216,99 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
         float s0, c0, s1, c1;
         __sincosf(x * fq[c][0], &s0, &c0);
         __sincosf(x * fq[c][1], &s1, &c1);
-        eB[c][tile][0] = pack_h2(c0, c1);
-        eB[c][tile][1] = pack_h2(s0, s1);
+        eA[c][tile] = pack_h2(c0, c1);
+        eA[c][2 + tile] = pack_h2(s0, s1);
         __sincosf(y * fq[c][0], &s0, &c0);
         __sincosf(y * fq[c][1], &s1, &c1);
-        eB[2 + c][tile][0] = pack_h2(c0, c1);
-        eB[2 + c][tile][1] = pack_h2(s0, s1);
+        eA[2 + c][tile] = pack_h2(c0, c1);
+        eA[2 + c][2 + tile] = pack_h2(s0, s1);
       }
       // yaw harmonics 8 cc + 2t + 1 (+1): bases by SFU, steps of 8 by plane rotation (pose_emb.py:52, integer freqs)
       float cA, sA, c1, s1, c8, s8;
       __sincosf(w * (float)(2 * t + 1), &sA, &cA);
       __sincosf(w, &s1, &c1);
       __sincosf(w * 8.f, &s8, &c8);
-      float cB = fmaf(cA, c1, -sA * s1), sB = fmaf(sA, c1, cA * s1);
+      float2 cv = make_float2(cA, fmaf(cA, c1, -sA * s1)), sv = make_float2(sA, fmaf(sA, c1, cA * s1));
+      const float2 c8v = make_float2(c8, c8), s8v = make_float2(s8, s8), ns8v = make_float2(-s8, -s8);
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        eB[4 + cc][tile][0] = pack_h2(cA, cB);
-        eB[4 + cc][tile][1] = pack_h2(sA, sB);
-        if (cc < 3) {
-          const float nA = fmaf(cA, c8, -sA * s8), nB = fmaf(cB, c8, -sB * s8);
-          sA = fmaf(sA, c8, cA * s8);
-          sB = fmaf(sB, c8, cB * s8);
-          cA = nA;
-          cB = nB;
+        eA[4 + cc][tile] = pack_h2(cv.x, cv.y);
+        eA[4 + cc][2 + tile] = pack_h2(sv.x, sv.y);
+        if (cc < 3) {  // rotate both harmonics by 8 w (packed FMUL2 / FFMA2)
+          const float2 nc = __ffma2_rn(cv, c8v, __fmul2_rn(sv, ns8v));
+          sv = __ffma2_rn(sv, c8v, __fmul2_rn(cv, s8v));
+          cv = nc;
         }
       }
     }
 
-    // ---- logits^T[row = head (+4: residual of q / u)][col = neighbour]
-    float sc[2][4];
+    // ---- logits[row = neighbour g | g+8][col = head (+4: residual of q / u)]
+    // (four independent accumulator chains of 4 MMAs each instead of one chain of 16)
+    float sc[4] = {0.f, 0.f, 0.f, 0.f}, sc1[4] = {0.f, 0.f, 0.f, 0.f}, sc2[4] = {0.f, 0.f, 0.f, 0.f},
+          sc3[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int tile = 0; tile < 2; ++tile)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) sc[tile][r] = 0.f;
+    for (int c = 0; c < 8; ++c) mma16816((c & 1) ? sc1 : sc, eA[c][0], eA[c][1], eA[c][2], eA[c][3], uB[c][0], uB[c][1]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // q.k: chunks 2i, 2i+1 carry head i only
       const bool mine = hA == i;
-      const uint32_t a00 = mine ? qA[0][0] : 0u, a01 = mine ? qA[0][1] : 0u;
-      const uint32_t a10 = mine ? qA[1][0] : 0u, a11 = mine ? qA[1][1] : 0u;
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile) {
-        mma16816(sc[tile], a00, 0u, a01, 0u, kf[tile][i].x, kf[tile][i].y);
-        mma16816(sc[tile], a10, 0u, a11, 0u, kf[tile][i].z, kf[tile][i].w);
-      }
+      mma16816(sc2, kf[0][i].x, kf[1][i].x, kf[0][i].y, kf[1][i].y, mine ? qB[0][0] : 0u, mine ? qB[0][1] : 0u);
+      mma16816(sc3, kf[0][i].z, kf[1][i].z, kf[0][i].w, kf[1][i].w, mine ? qB[1][0] : 0u, mine ? qB[1][1] : 0u);
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile) mma16816(sc[tile], uA[c][0], 0u, uA[c][1], 0u, eB[c][tile][0], eB[c][tile][1]);
+    for (int r = 0; r < 4; ++r) sc[r] = (sc[r] + sc1[r]) + (sc2[r] + sc3[r]);
 
-    // ---- V fragments (same addressing as K, second half of the row): in flight across the softmax
+    // ---- V pieces (same addressing as K, second half of the row): in flight across the softmax
     uint4 vf[2][4];
 #pragma unroll
     for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
       for (int i = 0; i < 4; ++i) vf[tile][i] = ldg128(rowp[tile] + D + 32 * i + 8 * t);
 
-    // ---- softmax for head hA over this lane's 4 columns {2t, 2t+1, 8+2t, 9+2t}; lanes g and g^4 run in lockstep
-    float lg[2][2];
+    // ---- softmax: this lane holds neighbours g (sc[0..1]) and g+8 (sc[2..3]) for heads 2(t&1), 2(t&1)+1
+    float lg[2][2];  // [tile][head j]
 #pragma unroll
-    for (int tile = 0; tile < 2; ++tile)
+    for (int r = 0; r < 4; ++r) {
+      const float v = sc[r] + __shfl_xor_sync(TB_FULL_MASK, sc[r], 2);  // head + residual column
+      lg[r >> 1][r & 1] = ((r >> 1) * 8 + g < nb) ? v : -INFINITY;
+    }
+    float mn[2], p[2][2], ps[2];
+    bool grew = false;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        float v = sc[tile][j];
-        v += __shfl_xor_sync(TB_FULL_MASK, v, 16);
-        lg[tile][j] = (tile * 8 + 2 * t + j < nb) ? v : -INFINITY;
-      }
-    float gm = fmaxf(fmaxf(lg[0][0], lg[0][1]), fmaxf(lg[1][0], lg[1][1]));
-    gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 1));
-    gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 2));
-    const float mn = fmaxf(mx, gm);  // finite: slot g0 is a valid neighbour
-    float p[2][2], ps = 0.f;
-#pragma unroll
-    for (int tile = 0; tile < 2; ++tile)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) { p[tile][j] = ex2(lg[tile][j] - mn); ps += p[tile][j]; }
-    ps += __shfl_xor_sync(TB_FULL_MASK, ps, 1);
-    ps += __shfl_xor_sync(TB_FULL_MASK, ps, 2);
-    if (__any_sync(TB_FULL_MASK, mn > mx)) {  // lazy rescale (warp-uniform)
-      const float corr = ex2(mx - mn);        // 1 where the running max did not move, 0 on the first group
-      mx = mn;
-      sm *= corr;
-      // accumulator columns 2t, 2t+1 belong to heads (2t)&3, (2t+1)&3; their state lives in lanes with g == head
-      const float ca = __shfl_sync(TB_FULL_MASK, corr, ((2 * t) & 3) << 2);
-      const float cb = __shfl_sync(TB_FULL_MASK, corr, ((2 * t + 1) & 3) << 2);
+    for (int j = 0; j < 2; ++j) {
+      float gm = fmaxf(lg[0][j], lg[1][j]);
+      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 4));
+      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 8));
+      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 16));
+      mn[j] = fmaxf(mx[j], gm);  // finite: slot g0 is a valid neighbour
+      p[0][j] = ex2(lg[0][j] - mn[j]);
+      p[1][j] = ex2(lg[1][j] - mn[j]);
+      float s = p[0][j] + p[1][j];
+      s += __shfl_xor_sync(TB_FULL_MASK, s, 4);
+      s += __shfl_xor_sync(TB_FULL_MASK, s, 8);
+      s += __shfl_xor_sync(TB_FULL_MASK, s, 16);
+      ps[j] = s;
+      grew |= mn[j] > mx[j];
+    }
+    if (__any_sync(TB_FULL_MASK, grew)) {  // lazy rescale (warp-uniform); accumulator columns 2t, 2t+1 = these heads
+      const float ca = ex2(mx[0] - mn[0]), cb = ex2(mx[1] - mn[1]);  // 1 where the max did not move, 0 at the start
+      mx[0] = mn[0]; mx[1] = mn[1];
+      sm[0] *= ca; sm[1] *= cb;
 #pragma unroll
       for (int c = 0; c < 8; ++c) { zacc[c][0] *= ca; zacc[c][1] *= cb; zacc[c][2] *= ca; zacc[c][3] *= cb; }
 #pragma unroll
       for (int m = 0; m < 2; ++m) { oacc[m][0] *= ca; oacc[m][1] *= cb; oacc[m][2] *= ca; oacc[m][3] *= cb; }
     }
-    sm += ps;
-    const uint32_t pB0 = split_h2(p[0][0], p[0][1], lo_part), pB1 = split_h2(p[1][0], p[1][1], lo_part);
+    sm[0] += ps[0];
+    sm[1] += ps[1];
+    // p^T as B fragment: [neighbour g][cols 2t,2t+1] tiles (fp16 head for t < 2, residual for t >= 2) transposed
+    const uint32_t pB0 = movm_trans(split_h2(p[0][0], p[0][1], t >= 2));
+    const uint32_t pB1 = movm_trans(split_h2(p[1][0], p[1][1], t >= 2));
 
     // ---- z^T[row = channel slot][col = head (+4: residual of p)] += e^T p^T; e^T fragments by register transpose
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const uint32_t a0 = movm_trans(eB[c][0][0]), a1 = movm_trans(eB[c][0][1]);
-      const uint32_t a2 = movm_trans(eB[c][1][0]), a3 = movm_trans(eB[c][1][1]);
+      const uint32_t a0 = movm_trans(eA[c][0]), a1 = movm_trans(eA[c][2]);
+      const uint32_t a2 = movm_trans(eA[c][1]), a3 = movm_trans(eA[c][3]);
       mma16816(zacc[c], a0, a1, a2, a3, pB0, pB1);
     }
 
@@ -315,9 +334,8 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
 
   // ---- normalise, un-permute through shared memory, store coalesced (all-masked row: zeros,
   // attention_rpe.py:188-190)
-  const float inv = sm > 0.f ? 1.f / sm : 0.f;  // head hA
-  const float ia = __shfl_sync(TB_FULL_MASK, inv, ((2 * t) & 3) << 2);
-  const float ib = __shfl_sync(TB_FULL_MASK, inv, ((2 * t + 1) & 3) << 2);
+  const float ia = sm[0] > 0.f ? 1.f / sm[0] : 0.f, ib = sm[1] > 0.f ? 1.f / sm[1] : 0.f;
+  const int h0 = 2 * (t & 1);
   __syncwarp();  // every lane is done with s_ptr / s_rel
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
@@ -326,10 +344,10 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
     for (int r = 0; r < 4; ++r) v[r] = oacc[m][r] + __shfl_xor_sync(TB_FULL_MASK, oacc[m][r], 2);  // + residual cols
     if (t < 2) {  // columns 2t, 2t+1 = heads; rows g (register 2m of the piece) and g+8 (register 2m+1)
       const int cp = 8 * (g >> 1) + 4 * m + (g & 1);
-      s_out[32 * (2 * t) + cp] = v[0] * ia;
-      s_out[32 * (2 * t + 1) + cp] = v[1] * ib;
-      s_out[32 * (2 * t) + cp + 2] = v[2] * ia;
-      s_out[32 * (2 * t + 1) + cp + 2] = v[3] * ib;
+      s_out[32 * h0 + cp] = v[0] * ia;
+      s_out[32 * (h0 + 1) + cp] = v[1] * ib;
+      s_out[32 * h0 + cp + 2] = v[2] * ia;
+      s_out[32 * (h0 + 1) + cp + 2] = v[3] * ib;
     }
   }
 #pragma unroll
@@ -339,10 +357,10 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
     for (int r = 0; r < 4; ++r) v[r] = zacc[c][r] + __shfl_xor_sync(TB_FULL_MASK, zacc[c][r], 2);
     if (t < 2) {  // rows g (cos slot) and g+8 (sin slot)
       float* zs = s_out + D + g;
-      zs[(2 * t) * D + cos_base(c)] = v[0] * ia;
-      zs[(2 * t + 1) * D + cos_base(c)] = v[1] * ib;
-      zs[(2 * t) * D + sin_base(c)] = v[2] * ia;
-      zs[(2 * t + 1) * D + sin_base(c)] = v[3] * ib;
+      zs[h0 * D + cos_base(c)] = v[0] * ia;
+      zs[(h0 + 1) * D + cos_base(c)] = v[1] * ib;
+      zs[h0 * D + sin_base(c)] = v[2] * ia;
+      zs[(h0 + 1) * D + sin_base(c)] = v[3] * ib;
     }
   }
   __syncwarp();

@@ -13,6 +13,8 @@ All tensors here are 2-D [rows, channels] views of flat HBM buffers; every compu
 import math
 from typing import Dict, Optional
 
+import os
+
 import torch
 from torch import Tensor
 
@@ -59,6 +61,7 @@ class HotPathModel:
         self.cfg, self.sz, self.dev, self.precision = cfg, sizes, torch.device(device), precision
         self.d = cfg["hidden_dim"]
         self.kv_half = precision == 1 and self.d == 128  # fp16 K|V tables + tensor-core attention (tb_knarpe_attn bit 1)
+        self.mma_min_k = int(os.environ.get("TB_MMA_MIN_K", "0"))
         self.W = cfg["temp_window_size"]
         self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in P.items()}
         self.fa: Dict[str, Dict[str, Tensor]] = {}
@@ -83,6 +86,7 @@ class HotPathModel:
         self.cfg, self.sz, self.dev, self.precision = None, None, torch.device(device), precision
         self.d, self.W = d_model, None
         self.kv_half = precision == 1 and d_model == 128
+        self.mma_min_k = int(os.environ.get("TB_MMA_MIN_K", "0"))
         self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in sd.items()}
         self.fa = {}
         for k in sd:
@@ -142,10 +146,12 @@ class HotPathModel:
             return tbl
         return ops.linear(x, f["w_kv"], f["b_kv"], precision=self.precision)
 
-    def _in_self(self, f, x):
-        """[q|u] (fp32) and the token's own [k|v] rows from one projection; k|v are fp16 in tensor-core mode."""
+    def _in_self(self, f, x, K):
+        """[q|u] (fp32) and the token's own [k|v] rows from one projection; k|v are fp16 in tensor-core mode. Short
+        neighbour lists (K < mma_min_k) stay on the fp32 SIMT kernel: the tensor-core kernel works on groups of 16
+        neighbours and has a higher per-token cost (measured in profiles/r1_notes.md)."""
         nq = self.d + H * self.d
-        if self.kv_half:
+        if self.kv_half and K >= self.mma_min_k:
             kv = torch.empty(x.shape[0], 2 * self.d, dtype=torch.float16, device=x.device)
             proj = ops.linear(x, f["w_in_self"], f["b_in_self"], precision=1, out_h=kv, col_h=nq)
             return proj, kv
@@ -164,7 +170,7 @@ class HotPathModel:
         d, pr = self.d, self.precision
         if mode == "dec_cross_attn":
             f = self.fa[f"{p}.attn_src"]
-            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm_src"))
+            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm_src"), knn_self["idx"].shape[-1])
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
             f = self.fa[f"{p}.attn"]
@@ -174,7 +180,7 @@ class HotPathModel:
             src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
         else:  # enc_self_attn: q and k/v both from norm1(src) (:218-221)
             f = self.fa[f"{p}.attn"]
-            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm1"))
+            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm1"), knn_self["idx"].shape[-1])
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
         h = self.lin(self.ln(src, f"{p}.norm2"), f"{p}.linear1", relu=True)
