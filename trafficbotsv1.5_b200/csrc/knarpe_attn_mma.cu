@@ -18,8 +18,12 @@
 //   * logits [16 nbr x 8] = A(k) B(q, block-diagonal over heads) + A(e) B(u): B columns 0-3 hold fp16(operand) of
 //     heads 0-3, columns 4-7 its fp16 residual, so q and u keep ~22 significant bits; one shuffle adds the halves.
 //   * z^T [128 x 8] = A(e^T) B(p^T) and ov^T [32 x 8] = sum_heads A(v_head^T) B(p^T masked to that head): columns 0-3
-//     take fp16(p_h), columns 4-7 the residual; the transposed fragments (e^T, v^T, p^T) come from movmatrix
-//     (register-only 8x8 transposes).
+//     take fp16(p_h) (no residual: e and v are fp16-rounded anyway); the transposed fragments (e^T, v^T, p^T) come
+//     from movmatrix (register-only 8x8 transposes).
+// Staging the gathered rows in shared memory instead (cp.async + ldmatrix: 835 us, cp.async.bulk per row + ldmatrix:
+// 634 us on the agent cross-attention launch) lost against these direct fragment loads (493 us): the per-lane
+// cp.async clogs the LSU queue, and bulk copies need uniform-register operands, i.e. a serialised 16-trip loop per
+// tile (profiles/r1_notes.md).
 // Channel "slots" inside a 16-wide MMA chunk are permutations of the reference orders (embedding:
 // utils/pose_emb.py:50-55 [cos x|sin x|cos y|sin y|cos yaw|sin yaw]); q/u are read and ov/z written through the same
 // permutations, so the C ABI layouts are unchanged.
@@ -111,7 +115,7 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
   for (int c = 0; c < 4; ++c) {
     const int j = c * 32 + lane;
     n_inv[c] = 1; n_id[c] = 0; n_rel[c][0] = n_rel[c][1] = n_rel[c][2] = 0.f;
-    if (j < Ktot) {
+    if (c * 32 < Ktot && j < Ktot) {
       const size_t p = prow + j;
       n_inv[c] = __ldg(invalid + p);
       n_id[c] = __ldg(idx + p);
@@ -300,9 +304,10 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
     }
     sm[0] += ps[0];
     sm[1] += ps[1];
-    // p^T as B fragment: [neighbour g][cols 2t,2t+1] tiles (fp16 head for t < 2, residual for t >= 2) transposed
-    const uint32_t pB0 = movm_trans(split_h2(p[0][0], p[0][1], t >= 2));
-    const uint32_t pB1 = movm_trans(split_h2(p[1][0], p[1][1], t >= 2));
+    // p^T as B fragment: [neighbour g][cols 2t,2t+1] tiles transposed. Columns 4-7 stay zero: the e and v operands
+    // are fp16-rounded anyway, a residual of p would not buy accuracy
+    const uint32_t pB0 = movm_trans(t < 2 ? pack_h2(p[0][0], p[0][1]) : 0u);
+    const uint32_t pB1 = movm_trans(t < 2 ? pack_h2(p[1][0], p[1][1]) : 0u);
 
     // ---- z^T[row = channel slot][col = head (+4: residual of p)] += e^T p^T; e^T fragments by register transpose
 #pragma unroll
@@ -335,32 +340,24 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
   // ---- normalise, un-permute through shared memory, store coalesced (all-masked row: zeros,
   // attention_rpe.py:188-190)
   const float ia = sm[0] > 0.f ? 1.f / sm[0] : 0.f, ib = sm[1] > 0.f ? 1.f / sm[1] : 0.f;
-  const int h0 = 2 * (t & 1);
   __syncwarp();  // every lane is done with s_ptr / s_rel
+  if (t < 2) {   // accumulator columns 2t, 2t+1 = heads 2t, 2t+1 (columns 4-7 are unused)
+    const int h0 = 2 * t;
 #pragma unroll
-  for (int m = 0; m < 2; ++m) {
-    float v[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) v[r] = oacc[m][r] + __shfl_xor_sync(TB_FULL_MASK, oacc[m][r], 2);  // + residual cols
-    if (t < 2) {  // columns 2t, 2t+1 = heads; rows g (register 2m of the piece) and g+8 (register 2m+1)
+    for (int m = 0; m < 2; ++m) {  // rows g (register 2m of the piece) and g+8 (register 2m+1)
       const int cp = 8 * (g >> 1) + 4 * m + (g & 1);
-      s_out[32 * h0 + cp] = v[0] * ia;
-      s_out[32 * (h0 + 1) + cp] = v[1] * ib;
-      s_out[32 * h0 + cp + 2] = v[2] * ia;
-      s_out[32 * (h0 + 1) + cp + 2] = v[3] * ib;
+      s_out[32 * h0 + cp] = oacc[m][0] * ia;
+      s_out[32 * (h0 + 1) + cp] = oacc[m][1] * ib;
+      s_out[32 * h0 + cp + 2] = oacc[m][2] * ia;
+      s_out[32 * (h0 + 1) + cp + 2] = oacc[m][3] * ib;
     }
-  }
+    float* zs = s_out + D + g;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float v[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) v[r] = zacc[c][r] + __shfl_xor_sync(TB_FULL_MASK, zacc[c][r], 2);
-    if (t < 2) {  // rows g (cos slot) and g+8 (sin slot)
-      float* zs = s_out + D + g;
-      zs[h0 * D + cos_base(c)] = v[0] * ia;
-      zs[(h0 + 1) * D + cos_base(c)] = v[1] * ib;
-      zs[h0 * D + sin_base(c)] = v[2] * ia;
-      zs[(h0 + 1) * D + sin_base(c)] = v[3] * ib;
+    for (int c = 0; c < 8; ++c) {  // rows g (cos slot) and g+8 (sin slot)
+      zs[h0 * D + cos_base(c)] = zacc[c][0] * ia;
+      zs[(h0 + 1) * D + cos_base(c)] = zacc[c][1] * ib;
+      zs[h0 * D + sin_base(c)] = zacc[c][2] * ia;
+      zs[(h0 + 1) * D + sin_base(c)] = zacc[c][3] * ib;
     }
   }
   __syncwarp();
