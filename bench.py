@@ -171,7 +171,8 @@ def attention_roofline(eng, peaks):
     K = sz["k_ag2mp"] + sz["k_ag2tl"]
     n_valid = int((~aux["cinv"]).sum())
     # algorithmic bytes: K,V rows of the unmasked neighbours as issued + q,u in + ov,z out + idx/mask/rel
-    bytes_alg = n_valid * 2 * d * 4 + M * (d + 4 * d) * 4 * 2 + M * K * (4 + 1 + 12)
+    kv_sz = static["kv_mp"][0].element_size()  # 2 in the tensor-core mode (fp16 K|V tables), 4 in the fp32 mode
+    bytes_alg = n_valid * 2 * d * kv_sz + M * (d + 4 * d) * 4 * 2 + M * K * (4 + 1 + 12)
     peak = peaks.get("hbm_gbs", 6650.0)
     ach = bytes_alg / t / 1e9
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
@@ -179,10 +180,11 @@ def attention_roofline(eng, peaks):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["knarpe_attn_ag_cross_bytes"]
     except Exception:
         pass
-    return dict(bound="hbm", kernel="knarpe_attn_kernel<128,false> (agent cross-attn, K=89)", achieved=ach, peak=peak,
+    kname = "knarpe_attn_mma_kernel" if kv_sz == 2 else "knarpe_attn_kernel<128,false>"
+    return dict(bound="hbm", kernel=f"{kname} (agent cross-attn, K=89, {8 * kv_sz}-bit K|V rows)", achieved=ach, peak=peak,
                 unit="GB/s", frac=ach / peak, traffic=traffic, us_per_launch=t * 1e6,
-                note="as-issued gather bytes are served by L2 (80 % hit): DRAM traffic is ~7 % of them, so frac can exceed 1; "
-                     "the kernel's real ceiling is FP32 issue (DESIGN.md 5)", algorithmic_bytes=bytes_alg,
+                note="as-issued gather bytes are served by L2 (~85 % hit): DRAM traffic is a fraction of them; the "
+                     "kernel's real ceiling is instruction issue / latency, not HBM (DESIGN.md 5)", algorithmic_bytes=bytes_alg,
                 valid_pairs=n_valid, pairs=M * K, peak_source="MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback")
 
 
