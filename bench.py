@@ -294,6 +294,16 @@ def run_ours(args):
             eng.run()
             t = timed(eng.run, 2)
             extras[name] = dict(value=units * 2 / t, unit=UNIT, ms_per_step=t / 2 * 1e3)
+        # the once-per-scene step before the loop: destination classifier over all polylines
+        Pn = params.init_params(cfg, 0, with_navi_predictor=True)
+        del eng
+        torch.cuda.empty_cache()
+        eng = RolloutEngine(Pn, cfg, dev, n_rollout=args.rollouts, step_end=N_ITER, precision=args.precision, use_graph=False)
+        mp = eng.encode_scenes(batch)["mp"]
+        eng.predict_destinations(batch, mp=mp)
+        t = timed(lambda: eng.predict_destinations(batch, mp=mp), 3) / 3
+        extras["navi_predictor"] = dict(value=t * 1e3, unit="ms per batch of scenes (destination logits + sampling, map tokens given)",
+                                        scenes=args.scenes)
         line["extras"] = extras
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -310,6 +310,50 @@ def navi_encoder(P, cfg, ag_navi: Tensor, ag_pose: Tensor, mp) -> Tensor:
     return f + mlp(P, "navi_encoder.mlp_pe", pose_emb_xy_yaw(xy, yaw, cfg["hidden_dim"]), (0,), False)
 
 
+def navi_predictor(P, cfg, ag_valid: Tensor, ag_attr: Tensor, ag_motion: Tensor, ag_pose: Tensor, mp,
+                   ag_type: Tensor, mp_type: Tensor) -> Tensor:
+    """NaviPredictor.forward, "dest" mode, HPTR + pairwise_relative (models/navigation.py:175-278): destination
+    logits [n_sc, n_ag, n_mp] over the map polylines; the once-per-scene step before the rollout loop
+    (waymo_motion.py:469-495). ag_valid [n_sc,n_ag,n_step]; ag_type [n_sc,n_ag,3] / mp_type [n_sc,n_mp,11] bool."""
+    d, W = cfg["hidden_dim"], cfg["temp_window_size"]
+    n_sc, n_ag, n_step = ag_valid.shape
+    tok_valid = ag_valid.any(-1)
+    tok_pose = last_valid(ag_pose, ag_valid)                                                            # :204
+    if n_step > W:                                                                                      # :210-214
+        ag_pose, ag_motion, ag_valid, n_step = ag_pose[:, :, -W:], ag_motion[:, :, -W:], ag_valid[:, :, -W:], W
+    xy = to_local_xy(ag_pose[..., :2], tok_pose[:, :, None, :2], tok_pose[..., 2])                      # :218
+    yaw = ag_pose[..., 2] - tok_pose[..., 2:3]                                                          # :219
+    attr = torch.cat([ag_attr[:, :, None, :].expand(-1, -1, n_step, -1), ag_motion,
+                      torch.eye(W)[None, None, -n_step:].expand(n_sc, n_ag, -1, -1)], -1)               # :221-228
+    feat = torch.cat([mlp(P, "navi_predictor.input_encoder.mlp", attr, (0, 2, 4), False),
+                      pose_emb_xy_yaw(xy, yaw, d // 2)], -1)                                            # :230
+    tok = pointnet(P, "navi_predictor.temp_encoder", feat, ~ag_valid)                                   # :232
+    n_mp = mp["mp_token_invalid"].shape[1]
+    rel, _ = get_rel_pose(tok_pose, ~tok_valid, mp["mp_token_pose"], mp["mp_token_invalid"])            # :259
+    x = torch.cat([tok[:, :, None, :].expand(-1, -1, n_mp, -1),
+                   mp["mp_token_feature"][:, None].expand(-1, n_ag, -1, -1),
+                   pose_emb_xy_yaw(rel[..., :2], rel[..., 2], d)], -1)                                  # :248-261
+    for i in (0, 3):                                                                                    # mlp.py:47-51
+        x = F.linear(x, P[f"navi_predictor.mlp.fc_layers.{i}.weight"], P[f"navi_predictor.mlp.fc_layers.{i}.bias"])
+        x = F.relu(F.layer_norm(x, (d,), P[f"navi_predictor.mlp.fc_layers.{i + 1}.weight"],
+                                P[f"navi_predictor.mlp.fc_layers.{i + 1}.bias"]))
+    logits = F.linear(x, P["navi_predictor.mlp.fc_layers.6.weight"], P["navi_predictor.mlp.fc_layers.6.bias"]).squeeze(-1)
+    return navi_logit_mask(logits, tok_valid, mp["mp_token_invalid"], ag_type, mp_type)
+
+
+def navi_logit_mask(logits: Tensor, tok_valid: Tensor, mp_invalid: Tensor, ag_type: Tensor, mp_type: Tensor) -> Tensor:
+    """Type masks of the destination classifier (navigation.py:265-278): polyline types FREEWAY 0, SURFACE_STREET 1,
+    STOP_SIGN 2, BIKE_LANE 3, ROAD_EDGE_BOUNDARY 4 are the only candidates; vehicles exclude 3, pedestrians 0-3,
+    cyclists 0-2. Masked logits are -inf; rows of invalid agents or without any candidate are all 0."""
+    mp_mask = mp_invalid | ~(mp_type[:, :, :5].any(-1))
+    veh = ag_type[:, :, [0]] & mp_type[:, :, 3].unsqueeze(1)
+    ped = ag_type[:, :, [1]] & mp_type[:, :, :4].any(-1).unsqueeze(1)
+    cyc = ag_type[:, :, [2]] & mp_type[:, :, :3].any(-1).unsqueeze(1)
+    inv = mp_mask.unsqueeze(1) | veh | ped | cyc
+    logits = logits.masked_fill(inv, -INF)
+    return logits.masked_fill((~tok_valid).unsqueeze(-1) | inv.all(-1, keepdim=True), 0.0)
+
+
 def add_navi_latent(P, prefix: str, x: Tensor, z: Tensor, z_valid: Tensor) -> Tensor:
     """AddNaviLatent.forward (mode cat, res_add True), modules/add_navi_latent.py:33-65."""
     zi = ~z_valid

@@ -37,3 +37,8 @@ def golden_rollout():
 @pytest.fixture(scope="session")
 def golden_checks():
     return torch.load(os.path.join(GOLDEN, "checks_dense.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_navi():
+    return torch.load(os.path.join(GOLDEN, "navi_pred.pt"), weights_only=False)

@@ -213,9 +213,38 @@ def reference_rollout(model, batch, R, step_end, record_steps=(), disable_check=
     return res, static, rec
 
 
+@torch.no_grad()
+def golden_navi_predictor():
+    """the reference NaviPredictor ("dest" mode, navigation.py:175-278) on the reference's own map
+    tokens -> destination probabilities (DestCategorical.probs, distributions.py:123-137)."""
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, seed=0, with_navi_predictor=True)
+    model = build_reference_model(cfg, P)
+    sd = model.state_dict()
+    mine = {k: tuple(v) for k, v in params.navi_predictor_shapes(cfg).items()}
+    ref = {k: tuple(v.shape) for k, v in sd.items() if k.startswith("navi_predictor.")
+           and not k.endswith((".freqs", "hist_ohe"))}
+    assert ref == mine, set(ref) ^ set(mine)
+    assert all(torch.equal(sd[k], P[k]) for k in mine)
+    shape = dict(n_sc=2, n_ag=32, n_mp=96, n_tl=30, seed=5000, boundary=105.0)
+    batch = synth.make_scene_batch(**shape)
+    mp = model.mp_encoder(batch["sc/mp_valid"], batch["sc/mp_attr"], batch["sc/mp_pose"], batch["ref/mp_type"])
+    dist = model.navi_predictor(ag_valid=batch["sc/ag_valid"], ag_attr=batch["sc/ag_attr"], ag_motion=batch["sc/ag_motion"],
+                                ag_pose=batch["sc/ag_pose"], mp_token_invalid=mp["mp_token_invalid"],
+                                mp_token_feature=mp["mp_token_feature"], mp_token_pose=mp["mp_token_pose"],
+                                ag_type=batch["ref/ag_type"], mp_token_type=mp["mp_token_type"])
+    fix = dict(shape=shape, param_seed=0, probs=dist.probs, valid=dist.valid, dest_argmax=dist.sample(True),
+               input_checksum=checksum(torch.cat([batch[k].float().flatten() for k in sorted(batch)])))
+    torch.save(fix, os.path.join(HERE, "navi_pred.pt"))
+    print("navi_pred.pt", os.path.getsize(os.path.join(HERE, "navi_pred.pt")) // 1024, "KiB; candidates per agent:",
+          float((dist.probs > 0).sum(-1).float().mean()))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "navi":  # only (re)generate navi_pred.pt
+        return golden_navi_predictor()
     ops = golden_ops()
     torch.save(ops, os.path.join(HERE, "ops.pt"))
     print("ops.pt", os.path.getsize(os.path.join(HERE, "ops.pt")) // 1024, "KiB")
@@ -250,6 +279,7 @@ def main():
     torch.save(fix, os.path.join(HERE, "checks_dense.pt"))
     print("checks_dense.pt", os.path.getsize(os.path.join(HERE, "checks_dense.pt")) // 1024, "KiB",
           {k: int(res[k].sum()) for k in keep[4:]})
+    golden_navi_predictor()
 
 
 if __name__ == "__main__":

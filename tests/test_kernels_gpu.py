@@ -141,6 +141,7 @@ def test_layernorm(D):
     x, w, b = torch.randn(333, D, generator=g) * 3 + 1, torch.randn(D, generator=g), torch.randn(D, generator=g)
     y = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-5)
     close(ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV)), y, 1e-5, 1e-5, "layernorm")
+    close(ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), relu=True), y.relu(), 1e-5, 1e-5, "layernorm + relu")
 
 
 @pytest.mark.parametrize("pe", [64, 128, 256])

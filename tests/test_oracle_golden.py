@@ -113,3 +113,26 @@ def test_rule_checks_oracle_vs_reference(golden_checks):
         for k in keys:
             assert torch.equal(out[k], g[k][:, :, t]), f"{k} differs at step {t + 1}"
     assert int(g["collided"].sum()) > 100 and int(g["run_road_edge"].sum()) > 100  # fixture exercises the checks
+
+
+def test_navi_predictor_oracle_vs_reference(golden_navi):
+    """destination classifier (navigation.py:175-278) — oracle restatement vs the probabilities
+    the real reference NaviPredictor produced on the same seeded scene and weights."""
+    g = golden_navi
+    cfg = config.default_model_cfg()
+    sz = config.derived_sizes(cfg)
+    P = params.init_params(cfg, seed=g["param_seed"], with_navi_predictor=True)
+    batch = synth.make_scene_batch(**g["shape"])
+    assert _checksum(torch.cat([batch[k].float().flatten() for k in sorted(batch)])) == g["input_checksum"]
+    mp = O.map_encoder(P, cfg, sz, batch["sc/mp_valid"], batch["sc/mp_attr"], batch["sc/mp_pose"])
+    logits = O.navi_predictor(P, cfg, batch["sc/ag_valid"], batch["sc/ag_attr"], batch["sc/ag_motion"],
+                              batch["sc/ag_pose"], mp, batch["ref/ag_type"], batch["ref/mp_type"])
+    probs = torch.softmax(logits, -1)
+    assert torch.equal(probs > 0, g["probs"] > 0)  # same candidate sets (type masks, navigation.py:265-278)
+    _close(probs, g["probs"], 1e-4, 1e-6, "destination probabilities")
+    valid = batch["sc/ag_valid"].any(-1)
+    assert torch.equal(valid, g["valid"])
+    # argmax destinations agree wherever the reference's top-2 gap is not a rounding tie
+    top2 = g["probs"].topk(2, -1)[0]
+    clear = valid & (top2[..., 0] - top2[..., 1] > 1e-5)
+    assert torch.equal(probs.argmax(-1)[clear], g["dest_argmax"][clear]) and int(clear.sum()) > 40

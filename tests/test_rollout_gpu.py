@@ -325,3 +325,34 @@ def test_module_api_in_reference_loop(golden_rollout):
     assert torch.equal(res["tl_state"], g["tl_state"])
     assert maxerr(res["pred_pose"][..., :2], g["pred_pose"][..., :2]) < TOL_XY
     assert maxerr(res["action_mean"], g["action_mean"]) < 2e-4
+
+
+def test_navi_predictor_vs_reference_golden(golden_navi):
+    """destination classifier on the GPU (HotPathModel.navi_predictor through tb_linear /
+    tb_pose_emb / tb_layernorm / tb_pointnet_pool) vs the real reference's probabilities, fp32 and tensor-core mode;
+    then destinations sampled by the engine feed a rollout."""
+    g = golden_navi
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, seed=g["param_seed"], with_navi_predictor=True)
+    batch = synth.make_scene_batch(**g["shape"])
+    for prec, tol in ((0, 1e-5), (1, 2e-3)):  # measured 1e-7 / 8e-5
+        eng = RolloutEngine(P, cfg, "cuda", precision=prec, n_rollout=4, step_end=20, use_graph=False)
+        out = eng.predict_destinations(batch)
+        probs = out["probs"].cpu()
+        assert torch.equal(probs > 0, g["probs"] > 0)
+        err = float((probs - g["probs"]).abs().max())
+        print(f"navi_predictor precision={prec}: max |dprob| {err:.3e}")
+        assert err < tol * max(float(g["probs"].max()), 1e-3)
+        assert torch.equal(out["navi_valid"].cpu(), g["valid"])
+        top2 = g["probs"].topk(2, -1)[0]
+        clear = g["valid"] & (top2[..., 0] - top2[..., 1] > 10 * tol)
+        assert torch.equal(out["dest"][:, 0].cpu()[clear], g["dest_argmax"][clear])
+        # sampled destinations are candidates of their agent
+        d = out["dest"].cpu()
+        assert bool((torch.gather(g["probs"][:, None].expand(-1, d.shape[1], -1, -1), 3, d[..., None]) > 0)[
+            g["valid"][:, None].expand(-1, d.shape[1], -1)].all())
+    b2 = dict(batch)
+    b2["agent/dest"], b2["ag_navi_valid"] = out["dest"].cpu(), out["navi_valid"].cpu()
+    b2["ag_latent"] = b2["ag_latent"][:, :4]
+    res = eng.rollout(b2)
+    assert bool(torch.isfinite(res["pred_pose"]).all())

@@ -7,7 +7,7 @@ namespace {
 template <int D>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float* __restrict__ Y, int ldy, int M) {
+                 const float* __restrict__ beta, float* __restrict__ Y, int ldy, int M, int relu) {
   constexpr int NV = D / 32;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -39,6 +39,7 @@ layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
     o.y = (v[i + 1] - mean) * rstd * g.y + bb.y;
     o.z = (v[i + 2] - mean) * rstd * g.z + bb.z;
     o.w = (v[i + 3] - mean) * rstd * g.w + bb.w;
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     *reinterpret_cast<float4*>(yp + i) = o;
   }
 }
@@ -139,7 +140,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, int ldt, int
 }  // namespace
 
 extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy, int M,
-                            int D, void* stream) {
+                            int D, int relu, void* stream) {
   if (!X || !gamma || !beta || !Y) return TB_ERR_NULL;
   if (M <= 0 || ldx < D || ldy < D) return TB_ERR_BAD_SHAPE;
   if (D != 128 && D != 256) return TB_ERR_UNSUPPORTED;
@@ -147,8 +148,8 @@ extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const f
     return TB_ERR_MISALIGNED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = (M + 7) / 8;
-  if (D == 128) layernorm_kernel<128><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M);
-  else layernorm_kernel<256><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M);
+  if (D == 128) layernorm_kernel<128><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
+  else layernorm_kernel<256><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

@@ -122,6 +122,29 @@ class RolloutEngine:
         kv_mp = self.model.ag_static(mp)
         return dict(mp=mp, tl=tl, kv_mp=kv_mp)
 
+    @torch.no_grad()
+    def predict_destinations(self, batch: Dict[str, Tensor], mp: Optional[dict] = None, deterministic_k0: bool = True,
+                             generator: Optional[torch.Generator] = None) -> Dict[str, Tensor]:
+        """The once-per-scene step right before the loop (waymo_motion.py:469-495): destination
+        distribution of every agent over the map polylines (NaviPredictor "dest" mode, needs `navi_predictor.*`
+        weights) and one destination per rollout: rollout 0 takes the argmax when `deterministic_k0`
+        (`joint_future_pred_deterministic_k0`), the others are sampled (DestCategorical.sample, distributions.py:143-159).
+        Returns logits [n_sc,n_ag,n_mp], probs, dest int64 [n_sc,R,n_ag] (feed as batch["agent/dest"]) and
+        navi_valid [n_sc,n_ag] (batch["ag_navi_valid"])."""
+        dev = self.dev
+        g = lambda k: batch[k].to(dev)  # noqa: E731
+        if mp is None:
+            mp = self.model.map_encoder(g("sc/mp_valid"), g("sc/mp_attr"), g("sc/mp_pose"))
+        logits = self.model.navi_predictor(g("sc/ag_valid"), g("sc/ag_attr"), g("sc/ag_motion"), g("sc/ag_pose"), mp,
+                                           g("ref/ag_type"), g("ref/mp_type"))
+        probs = torch.softmax(logits, -1)
+        n_sc, A, n_mp = probs.shape
+        dest = torch.multinomial(probs.reshape(n_sc * A, n_mp), self.R, replacement=True, generator=generator)
+        dest = dest.view(n_sc, A, self.R).permute(0, 2, 1).contiguous()
+        if deterministic_k0:
+            dest[:, 0] = probs.argmax(-1)
+        return dict(logits=logits, probs=probs, dest=dest, navi_valid=g("sc/ag_valid").any(-1))
+
     # ---------------------------------------------------------------------------------------------- state
     def _alloc(self, n_sc: int, A: int, n_tl: int, n_gt: int, n_mp: int, n_node: int):
         dev, R, W, T, d = self.dev, self.R, self.model.W, self.T, self.model.d

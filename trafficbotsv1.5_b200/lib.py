@@ -55,7 +55,7 @@ def load() -> ctypes.CDLL:
         "tb_knn_select": [P, P, P, P, I, I, I, I, I, F, P, P, P, I, I, P],
         "tb_knarpe_attn": [P, I, P, I, P, I, I, I, I, P, I, I, I, I, P, P, P, P, P, I, I, I, I, P, P, I, P, I, P],
         "tb_linear": [P, I, P, P, I, P, I, I, I, I, I, P, P, I, P, I, P, I, I, P],
-        "tb_layernorm": [P, I, P, P, P, I, I, I, P],
+        "tb_layernorm": [P, I, P, P, P, I, I, I, I, P],
         "tb_pointnet_pool": [P, I, P, I, I, I, I, P, I, P],
         "tb_pose_emb": [P, P, I, P, I, I, P, I, P],
         "tb_ag_featurize": [P, P, P, P, P, P, I, I, I, P, P, P, P, I, P, I, P],

@@ -333,6 +333,56 @@ class HotPathModel:
                                 out=out if i == nl - 1 else None)
         return tok
 
+    # ------------------------------------------------------------------------------------------ destinations (once / scene)
+    def navi_predictor(self, ag_valid: Tensor, ag_attr: Tensor, ag_motion: Tensor, ag_pose: Tensor,
+                       mp: Dict[str, Tensor], ag_type: Tensor, mp_type: Tensor, scene_chunk: int = 4) -> Tensor:
+        """NaviPredictor.forward, "dest" mode (navigation.py:175-278): destination logits
+        [n_sc, n_ag, n_mp] — the once-per-scene step right before the rollout loop (waymo_motion.py:469-495).
+        The first Linear of the pair MLP over [agent | polyline | PE(rel pose)] is split column-wise: the agent part
+        is one row per agent and enters as a grouped bias, so the [n_sc, n_ag, n_mp, 384] input is never built."""
+        d, W = self.d, self.W
+        n_sc, A, n_step = ag_valid.shape
+        if n_step > W:                                                                                   # :210-214
+            # the token pose uses the full history (:204) - identical here because the last valid step is kept
+            ag_valid, ag_motion, ag_pose, n_step = ag_valid[:, :, -W:], ag_motion[:, :, -W:], ag_pose[:, :, -W:], W
+        tok_valid = ag_valid.any(-1)
+        last = n_step - 1 - torch.max(ag_valid.flip(2).to(torch.uint8), dim=2)[1]
+        tok_pose = torch.gather(ag_pose, 2, last[:, :, None, None].expand(-1, -1, 1, 3)).squeeze(2)
+        tok_pose = tok_pose.masked_fill(~tok_valid[..., None], 0.0).contiguous()                         # :204
+        M, MW = n_sc * A, n_sc * A * n_step
+        attr = torch.cat([ag_attr[:, :, None, :].expand(-1, -1, n_step, -1), ag_motion,
+                          torch.eye(W, device=self.dev)[None, None, -n_step:].expand(n_sc, A, -1, -1)], -1)  # :221-228
+        x = torch.empty(MW, d, device=self.dev)
+        self.mlp(attr.reshape(MW, -1).contiguous(), "navi_predictor.input_encoder.mlp", (0, 2, 4), False,
+                 out=x[:, : d // 2])
+        ops.pose_emb(ag_pose.reshape(MW, 3), self.freq_ag, d // 2, frame=tok_pose, frame_div=n_step, out=x[:, d // 2:])
+        tok = self.pointnet(x, (~ag_valid).reshape(-1).contiguous(), M, n_step, "navi_predictor.temp_encoder")  # :232
+        pr = "navi_predictor.mlp.fc_layers"
+        w0 = self.P[f"{pr}.0.weight"]
+        a_part = ops.linear(tok, w0[:, :d].contiguous(), self.P[f"{pr}.0.bias"], precision=self.precision)
+        w_mr = w0[:, d:].contiguous()
+        n_mp = mp["mp_token_pose"].shape[1]
+        logits = torch.empty(n_sc, A, n_mp, device=self.dev)
+        for s0 in range(0, n_sc, scene_chunk):
+            ns = min(scene_chunk, n_sc - s0)
+            Pn = ns * A * n_mp
+            X = torch.empty(Pn, 2 * d, device=self.dev)
+            X[:, :d].view(ns, A, n_mp, d).copy_(mp["mp_token_feature"][s0:s0 + ns, None])
+            pose_rows = mp["mp_token_pose"][s0:s0 + ns, None].expand(-1, A, -1, -1).reshape(Pn, 3)
+            ops.pose_emb(pose_rows, self.freq_rpe, d, frame=tok_pose[s0:s0 + ns], frame_div=n_mp, out=X[:, d:])  # :259-260
+            h = ops.linear(X, w_mr, a_part[s0 * A:(s0 + ns) * A], bias_group=n_mp, precision=self.precision)
+            h = ops.layernorm(h, self.P[f"{pr}.1.weight"], self.P[f"{pr}.1.bias"], relu=True, out=h)      # mlp.py:47-51
+            h = self.lin(h, f"{pr}.3")
+            h = ops.layernorm(h, self.P[f"{pr}.4.weight"], self.P[f"{pr}.4.bias"], relu=True, out=h)
+            logits[s0:s0 + ns] = self.lin(h, f"{pr}.6").view(ns, A, n_mp)
+        # type masks (:265-278)
+        mp_mask = mp["mp_token_invalid"] | ~(mp_type[:, :, :5].any(-1))
+        inv = (mp_mask.unsqueeze(1) | (ag_type[:, :, [0]] & mp_type[:, :, 3].unsqueeze(1))
+               | (ag_type[:, :, [1]] & mp_type[:, :, :4].any(-1).unsqueeze(1))
+               | (ag_type[:, :, [2]] & mp_type[:, :, :3].any(-1).unsqueeze(1)))
+        logits = logits.masked_fill(inv, float("-inf"))
+        return logits.masked_fill((~tok_valid).unsqueeze(-1) | inv.all(-1, keepdim=True), 0.0)
+
     # ------------------------------------------------------------------------------------------ heads (per step)
     def navi_static(self, mp: Dict[str, Tensor], dest_idx: Tensor, R: int) -> dict:
         """Static halves of NaviEncoder.forward (navigation.py:65-71): mlp_mp(map feature of the destination) and the

@@ -124,13 +124,13 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False,
     return out
 
 
-def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, out: Optional[Tensor] = None) -> Tensor:
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, out: Optional[Tensor] = None, relu: bool = False) -> Tensor:
     assert x.dim() == 2 and x.stride(1) == 1
     M, D = x.shape
     if out is None:
         out = torch.empty(M, D, dtype=torch.float32, device=x.device)
     L.check(L.load().tb_layernorm(L.ptr(x), x.stride(0), L.ptr(gamma), L.ptr(beta), L.ptr(out), out.stride(0), M, D,
-                                  L.stream()), "tb_layernorm")
+                                  int(relu), L.stream()), "tb_layernorm")
     _count()
     return out
 

@@ -76,13 +76,35 @@ def param_shapes(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
     return s
 
 
-def init_params(cfg: dict, seed: int = 0, bias_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+def navi_predictor_shapes(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
+    """`navi_predictor.*` (NaviPredictor in "dest" mode, navigation.py:100-160): the once-per-scene destination
+    classifier that runs immediately before the rollout loop."""
+    d, W = cfg["hidden_dim"], cfg["temp_window_size"]
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    for i in range(3):
+        _mlp(s, f"navi_predictor.temp_encoder.mlp_layers.{i}", [d, d // 2], (0,))
+    _mlp(s, "navi_predictor.input_encoder.mlp", [cfg["ag_attr_dim"] + cfg["ag_motion_dim"] + W] + [d // 2] * 3, (0, 2, 4))
+    # MLP [2d + d_rpe, d, d, 1] with LayerNorm after the first two Linears (mlp.py:47-51: Linear, LN, ReLU)
+    _mlp(s, "navi_predictor.mlp", [3 * d, d, d, 1], (0, 3, 6))
+    for i in (1, 4):
+        s[f"navi_predictor.mlp.fc_layers.{i}.weight"] = (d,)
+        s[f"navi_predictor.mlp.fc_layers.{i}.bias"] = (d,)
+    return s
+
+
+def init_params(cfg: dict, seed: int = 0, bias_scale: float = 1.0, with_navi_predictor: bool = False
+                ) -> Dict[str, torch.Tensor]:
     """Seeded random init (CPU generator, fp32): Linear-style U(+-1/sqrt(fan_in)) for matrices and
     biases (so attention biases are exercised, unlike the reference's zero init, attention_rpe.py:50-56),
-    LayerNorm gamma 1+0.1N / beta 0.1N, log_std -2 (action_head.py:48-50)."""
+    LayerNorm gamma 1+0.1N / beta 0.1N, log_std -2 (action_head.py:48-50). `navi_predictor.*` tensors are drawn
+    from a separate stream so that the hot-path weights of a seed do not depend on the flag."""
     g = torch.Generator().manual_seed(seed)
     P = {}
     shapes = param_shapes(cfg)
+    if with_navi_predictor:
+        P.update(rand_like_state_dict({k.replace("fc_layers.1.", "fc_layers.1.norm.").replace("fc_layers.4.", "fc_layers.4.norm."): v
+                                       for k, v in navi_predictor_shapes(cfg).items()}, seed + 7919))
+        P = {k.replace(".norm.", "."): v for k, v in P.items()}
     for k, shp in shapes.items():
         if "log_std" in k:
             P[k] = torch.full(shp, -2.0)
