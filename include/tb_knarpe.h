@@ -202,6 +202,24 @@ int tb_step_advance(int* d_step, void* stream);
 int tb_gather_rows(const float* table, int ldt, int T, const int32_t* idx, int M, int rows_per_batch, int div, int C,
                    float* out, int ldo, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * WOSAC post-processing on the device (the step right after the loop).
+ * tb_future_filter — data_modules/wosac_post_processing.py:31-64 (`_filter_futures`): per joint future k of scene sc
+ *   score[sc,k] = sum_a role_any[sc,a] * any_{t>=t0} collided[(sc K + k), a, t]
+ *               + w_road_edge * sum_a role_any[sc,a] * any_{t>=t0} run_road_edge[...]
+ *   and sel[sc, 0:n_keep] = the n_keep futures with the smallest score, ascending by (score, index) (the reference's
+ *   torch.topk(sorted=False) leaves order and tie-break unspecified). Flags [n_sc*K, A, T] u8 as written by
+ *   tb_rule_check; role_any [n_sc, A] u8; score [n_sc, K] f32, sel [n_sc, n_keep] i32. K <= 1024.
+ * tb_traj_global — wosac_post_processing.py:66-75 with transform_utils.py:160-171,215-225: gathers the selected
+ *   futures (sel NULL: all K in order) and maps them to the global frame:
+ *   out_pos[sc,i,a,t,:] = R(yaw[sc]) pose_xy[(sc K + sel[sc,i]), a, t0+t] + center[sc];
+ *   out_yaw[sc,i,a,t] = wrap_[-pi,pi)(pose_yaw + yaw[sc]). pose [n_sc*K, A, T, 3]; out_pos [n_sc,n_keep,A,T-t0,2].
+ * ------------------------------------------------------------------------------------------------- */
+int tb_future_filter(const uint8_t* collided, const uint8_t* run_road_edge, const uint8_t* role_any, int n_sc, int K,
+                     int A, int T, int t0, float w_road_edge, int n_keep, float* score, int32_t* sel, void* stream);
+int tb_traj_global(const float* pose, const int32_t* sel, const float* center, const float* yaw, int n_sc, int K,
+                   int n_keep, int A, int T, int t0, float* out_pos, float* out_yaw, void* stream);
+
 /* Sum of the three type-masked branches is done inside tb_dyn_step; this helper exposes the masked action
  * mean [B,A,2] for the module-level API (action_head.py:78-82). */
 int tb_action_mean(const float* act_branch, const uint8_t* ag_type, const uint8_t* valid, int M, float* mean,

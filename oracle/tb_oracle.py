@@ -689,3 +689,33 @@ def rollout(P, cfg, sz, dyn, rcfg, batch: Dict[str, Tensor], n_rollout: int, ste
     res = {k: torch.stack(v, 2) for k, v in out.items()}
     res["final_valid"], res["final_navi_valid"] = valid, navi_valid
     return res
+
+
+# --------------------------------------------------------------------------------------------------
+# WOSAC post-processing: data_modules/wosac_post_processing.py:31-75
+# --------------------------------------------------------------------------------------------------
+def wosac_future_scores(collided: Tensor, run_road_edge: Tensor, ag_role: Tensor, t0: int, w_road_edge: float) -> Tensor:
+    """`_filter_futures` violation score (:48-58). Flags [n_sc,K,n_ag,n_step] bool, ag_role [n_sc,n_ag,3] -> [n_sc,K]."""
+    role = (ag_role.any(-1) * 1.0).unsqueeze(1)
+    col = (collided[..., t0:].any(-1) * role).sum(-1)
+    edge = (run_road_edge[..., t0:].any(-1) * role).sum(-1)
+    return col + edge * w_road_edge
+
+
+def wosac_select_futures(scores: Tensor, n_keep: int) -> Tensor:
+    """The n_keep smallest scores per scene (:61), made deterministic: ascending (score, index)."""
+    K = scores.shape[1]
+    key = scores.double() * (K + 1) + torch.arange(K, dtype=torch.float64)  # scores are small non-negative numbers
+    return torch.argsort(key, dim=-1, stable=True)[:, :n_keep]
+
+
+def wosac_to_global(trajs: Tensor, center: Tensor, yaw: Tensor) -> Tuple[Tensor, Tensor]:
+    """`forward` (:69-74) with transform_utils.py:160-171 (torch_pos2global), :215-225 (torch_rad2global), :9-11
+    (cast_rad). trajs [n_sc,K,n_ag,T,3] scene-centric, center [n_sc,2], yaw [n_sc] -> pos [...,2], yaw [...,1]."""
+    c, s = torch.cos(yaw), torch.sin(yaw)
+    rot = torch.stack([torch.stack([c, -s], -1), torch.stack([s, c], -1)], -2)  # [n_sc,2,2]
+    pos = trajs[..., :2]
+    out = torch.matmul(pos.flatten(1, 3), rot.transpose(-1, -2)) + center.unsqueeze(1)
+    yy = trajs[..., 2:3]
+    oy = (yy.flatten(1, 4) + yaw.unsqueeze(-1) + math.pi) % (2 * math.pi) - math.pi
+    return out.view(pos.shape), oy.view(yy.shape)

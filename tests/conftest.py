@@ -42,3 +42,8 @@ def golden_checks():
 @pytest.fixture(scope="session")
 def golden_navi():
     return torch.load(os.path.join(GOLDEN, "navi_pred.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_wosac():
+    return torch.load(os.path.join(GOLDEN, "wosac_post.pt"), weights_only=False)

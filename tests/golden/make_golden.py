@@ -240,11 +240,45 @@ def golden_navi_predictor():
           float((dist.probs > 0).sum(-1).float().mean()))
 
 
+@torch.no_grad()
+def golden_wosac_post():
+    """the real WOSACPostProcessing (`_filter_futures` + the local -> global part of `forward`,
+    wosac_post_processing.py:31-75) on seeded joint futures; the Waymo proto imports are stubbed (never executed)."""
+    from types import SimpleNamespace
+    from data_modules.wosac_post_processing import WOSACPostProcessing  # reference
+    shape = dict(seed=7000, n_sc=2, K=40, A=40, T=12)
+    t0, w = 4, 0.01
+    inp = synth.make_wosac_post_inputs(**shape)
+    n_sc, K, A, T = shape["n_sc"], shape["K"], shape["A"], shape["T"]
+    pp = WOSACPostProcessing(step_gt=90, step_current=10, const_vel_z_sim=True, const_vel_no_sim=True, w_road_edge=w,
+                             use_wosac_col=True)
+    buffer = SimpleNamespace(pred_pose=inp["pose"].view(n_sc, K, A, T, 3), step_future_start=t0,
+                             violation=dict(collided_wosac=inp["collided"], run_road_edge=inp["run_road_edge"]))
+    z = torch.zeros
+    batch = {"ref/ag_role": inp["role"], "scenario_center": inp["center"], "scenario_yaw": inp["yaw"],
+             "history/agent_no_sim/pos": z(n_sc, 3, 11, 3), "history/agent_no_sim/yaw_bbox": z(n_sc, 3, 11, 1),
+             "scenario_id": ["abc"] * n_sc, "history/agent/valid": z(n_sc, A, 11, dtype=torch.bool),
+             "history/agent/pos": z(n_sc, A, 11, 3), "history/agent/object_id": z(n_sc, A),
+             "history/agent_no_sim/valid": z(n_sc, 3, 11, dtype=torch.bool),
+             "history/agent_no_sim/object_id": z(n_sc, 3)}
+    out = pp(batch, buffer)
+    # recover which futures the reference kept by matching its (untransformed) selection against the inputs
+    trajs = pp._filter_futures(buffer, inp["role"])
+    d = (trajs[:, :, None] - buffer.pred_pose[:, None, :, :, t0:]).abs().flatten(3).amax(-1)  # [n_sc, 32, K]
+    idx = d.argmin(-1)
+    assert float(d.min(-1)[0].max()) == 0.0 and all(len(set(r.tolist())) == 32 for r in idx)
+    fix = dict(shape=shape, t0=t0, w_road_edge=w, n_keep=32, sel=idx, pos_sim=out["pos_sim"], yaw_sim=out["yaw_sim"])
+    torch.save(fix, os.path.join(HERE, "wosac_post.pt"))
+    print("wosac_post.pt", os.path.getsize(os.path.join(HERE, "wosac_post.pt")) // 1024, "KiB")
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "navi":  # only (re)generate navi_pred.pt
         return golden_navi_predictor()
+    if len(sys.argv) > 1 and sys.argv[1] == "wosac":  # only (re)generate wosac_post.pt
+        return golden_wosac_post()
     ops = golden_ops()
     torch.save(ops, os.path.join(HERE, "ops.pt"))
     print("ops.pt", os.path.getsize(os.path.join(HERE, "ops.pt")) // 1024, "KiB")
@@ -280,6 +314,7 @@ def main():
     print("checks_dense.pt", os.path.getsize(os.path.join(HERE, "checks_dense.pt")) // 1024, "KiB",
           {k: int(res[k].sum()) for k in keep[4:]})
     golden_navi_predictor()
+    golden_wosac_post()
 
 
 if __name__ == "__main__":

@@ -136,3 +136,20 @@ def test_navi_predictor_oracle_vs_reference(golden_navi):
     top2 = g["probs"].topk(2, -1)[0]
     clear = valid & (top2[..., 0] - top2[..., 1] > 1e-5)
     assert torch.equal(probs.argmax(-1)[clear], g["dest_argmax"][clear]) and int(clear.sum()) > 40
+
+
+def test_wosac_post_processing_oracle_vs_reference(golden_wosac):
+    """future filter + local -> global transform (wosac_post_processing.py:31-75) — oracle vs the
+    real WOSACPostProcessing on the seeded, tie-free fixture (the reference's top-k order is unspecified: compare the
+    kept SET, and the trajectories future by future)."""
+    g = golden_wosac
+    sh = g["shape"]
+    inp = synth.make_wosac_post_inputs(**sh)
+    n_sc, K, A, T = sh["n_sc"], sh["K"], sh["A"], sh["T"]
+    sc = O.wosac_future_scores(inp["collided"], inp["run_road_edge"], inp["role"], g["t0"], g["w_road_edge"])
+    assert all(len(set(r.tolist())) == K for r in sc)  # tie-free by construction
+    sel = O.wosac_select_futures(sc, g["n_keep"])
+    assert torch.equal(sel.sort(-1)[0], g["sel"].sort(-1)[0])
+    trajs = inp["pose"].view(n_sc, K, A, T, 3)[torch.arange(n_sc)[:, None], g["sel"]][:, :, :, g["t0"]:]
+    pos, yaw = O.wosac_to_global(trajs, inp["center"], inp["yaw"])
+    assert torch.equal(pos, g["pos_sim"]) and torch.equal(yaw, g["yaw_sim"])

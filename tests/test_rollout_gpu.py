@@ -356,3 +356,56 @@ def test_navi_predictor_vs_reference_golden(golden_navi):
     b2["ag_latent"] = b2["ag_latent"][:, :4]
     res = eng.rollout(b2)
     assert bool(torch.isfinite(res["pred_pose"]).all())
+
+
+def test_wosac_post_processing_kernels_vs_reference(golden_wosac):
+    """SURVEY 8(f) rank 4 on the GPU (tb_future_filter + tb_traj_global through the C ABI) vs the real
+    WOSACPostProcessing: identical kept set, scores bit-exact vs the oracle, global trajectories within 1 ulp-level
+    tolerance of the reference's (positions ~5e3 m: 1e-3 m; yaw 1e-6 rad)."""
+    from trafficbotsv1_5_b200 import ops
+    g = golden_wosac
+    sh = g["shape"]
+    inp = synth.make_wosac_post_inputs(**sh)
+    n_sc, K, A, T = sh["n_sc"], sh["K"], sh["A"], sh["T"]
+    d = lambda t: t.to(DEV)  # noqa: E731
+    score, sel = ops.future_filter(d(inp["collided"]).view(n_sc * K, A, T).contiguous(),
+                                   d(inp["run_road_edge"]).view(n_sc * K, A, T).contiguous(),
+                                   d(inp["role"].any(-1)).contiguous(), n_sc, K, g["t0"], g["w_road_edge"], g["n_keep"])
+    ref_sc = O.wosac_future_scores(inp["collided"], inp["run_road_edge"], inp["role"], g["t0"], g["w_road_edge"])
+    assert torch.equal(score.cpu(), ref_sc)
+    assert torch.equal(sel.cpu().long(), O.wosac_select_futures(ref_sc, g["n_keep"]))
+    assert torch.equal(sel.cpu().long().sort(-1)[0], g["sel"].sort(-1)[0])
+    pos, yaw = ops.traj_global(d(inp["pose"]), d(g["sel"].to(torch.int32)).contiguous(), d(inp["center"]), d(inp["yaw"]),
+                               n_sc, K, g["t0"])
+    assert maxerr(pos, g["pos_sim"]) < 1e-3 and maxerr(yaw, g["yaw_sim"]) < 2e-6
+    # ties: equal scores are resolved by the lower future index, exactly like the oracle's definition
+    col = torch.zeros(1 * 6, 3, 5, dtype=torch.bool)
+    col[1, 0, 3] = col[4, 1, 4] = True
+    score, sel = ops.future_filter(d(col), d(torch.zeros_like(col)), d(torch.ones(1, 3, dtype=torch.bool)), 1, 6, 2, 0.0, 4)
+    assert score.cpu().tolist() == [[0.0, 1.0, 0.0, 0.0, 1.0, 0.0]] and sel.cpu().tolist() == [[0, 2, 3, 5]]
+    # all futures, no selection (R <= n_keep)
+    pos_all, _ = ops.traj_global(d(inp["pose"]), None, d(inp["center"]), d(inp["yaw"]), n_sc, K, g["t0"])
+    assert torch.equal(pos_all[torch.arange(n_sc)[:, None], d(g["sel"])], pos)
+
+
+def test_post_process_wosac_after_rollout():
+    """Engine-level: 6 rollouts with all rule checks, keep the best 4, global frame; vs the oracle on the engine's own
+    flags and trajectories."""
+    eng, batch, P, cfg = _engine(dict(n_sc=2, n_ag=48, n_mp=96, n_tl=30, seed=3000, boundary=60.0, scale=0.2), 6, 30,
+                                 rule_checks=True)
+    res = eng.rollout(batch)
+    g = torch.Generator().manual_seed(1)
+    batch["ref/ag_role"] = torch.rand(2, 48, 3, generator=g) < 0.3
+    batch["scenario_center"] = torch.randn(2, 2, generator=g) * 1000
+    batch["scenario_yaw"] = torch.randn(2, generator=g)
+    out = eng.post_process_wosac(res, batch, n_keep=4, w_road_edge=0.5)
+    c = lambda k: res[k].cpu().view(2, 6, 48, 30)  # noqa: E731
+    sc = O.wosac_future_scores(c("collided_wosac"), c("run_road_edge"), batch["ref/ag_role"], 10, 0.5)
+    assert torch.equal(out["score"].cpu(), sc) and float(sc.max()) > 0
+    sel = O.wosac_select_futures(sc, 4)
+    assert torch.equal(out["sel"].cpu().long(), sel)
+    trajs = res["pred_pose"].cpu().view(2, 6, 48, 30, 3)[torch.arange(2)[:, None], sel][:, :, :, 10:]
+    pos, yaw = O.wosac_to_global(trajs, batch["scenario_center"], batch["scenario_yaw"])
+    assert maxerr(out["pos_sim"], pos) < 5e-4 and maxerr(out["yaw_sim"], yaw) < 2e-6
+    with pytest.raises(RuntimeError):
+        RolloutEngine(P, cfg, DEV, n_rollout=6, step_end=30).post_process_wosac(res, batch, n_keep=4)

@@ -336,6 +336,29 @@ class RolloutEngine:
                     tl_state=tl.bool(), final_valid=st["valid"].bool(), final_navi_valid=~st["navi_invalid"],
                     joint_pose=st["pred_pose"].view(n_sc, R, A, self.T, 3))
 
+    @torch.no_grad()
+    def post_process_wosac(self, res: Dict[str, Tensor], batch: Dict[str, Tensor], n_keep: int = 32,
+                           step_future_start: Optional[int] = None, w_road_edge: float = 0.0,
+                           use_wosac_col: bool = True) -> Dict[str, Tensor]:
+        """The step right after the loop (WOSACPostProcessing._filter_futures + forward,
+        wosac_post_processing.py:31-75): keep the `n_keep` joint futures of every scene with the
+        fewest role-weighted collision / road-edge violations (needs `rule_checks=True` when R > n_keep) and express
+        them in the global frame (`scenario_center`, `scenario_yaw`). Only the kept futures leave the device
+        (R = 128 -> 32 in the reference's submission config)."""
+        R = self.R
+        if R > n_keep and not self.rule_checks:
+            raise RuntimeError("post_process_wosac with more than n_keep rollouts needs RolloutEngine(rule_checks=True)")
+        n_sc = res["pred_pose"].shape[0] // R
+        t0 = C.ROLLOUT_CFG["time_step_current"] if step_future_start is None else step_future_start
+        g = lambda k: batch[k].to(self.dev)  # noqa: E731
+        sel = score = None
+        if R > n_keep:
+            col = res["collided_wosac" if use_wosac_col else "collided"]
+            score, sel = ops.future_filter(col, res["run_road_edge"], g("ref/ag_role").any(-1).contiguous(), n_sc, R, t0,
+                                           w_road_edge, n_keep)
+        pos, yaw = ops.traj_global(res["pred_pose"], sel, g("scenario_center"), g("scenario_yaw"), n_sc, R, t0)
+        return dict(pos_sim=pos, yaw_sim=yaw, sel=sel, score=score)
+
     def rollout(self, batch: Dict[str, Tensor], n_steps: Optional[int] = None) -> Dict[str, Tensor]:
         self.prepare(batch)
         return self.run(n_steps)

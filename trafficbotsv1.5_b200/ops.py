@@ -178,3 +178,33 @@ def gather_rows(table: Tensor, idx: Tensor, rows_per_batch: int, div: int = 1, o
 
 def host_f3(vals):
     return (ctypes.c_float * 3)(*[float(v) for v in vals])
+
+
+def future_filter(collided: Tensor, run_road_edge: Tensor, role_any: Tensor, n_sc: int, K: int, t0: int,
+                  w_road_edge: float, n_keep: int) -> Tuple[Tensor, Tensor]:
+    """tb_future_filter: flags [n_sc*K, A, T] (bool/u8), role_any [n_sc, A] -> (score [n_sc, K], sel int32 [n_sc, n_keep])."""
+    col, edge, role = _u8(collided), _u8(run_road_edge), _u8(role_any)
+    assert col.is_contiguous() and edge.is_contiguous() and role.is_contiguous() and col.shape == edge.shape
+    B, A, T = col.shape
+    assert B == n_sc * K and role.shape == (n_sc, A)
+    score = torch.empty(n_sc, K, dtype=torch.float32, device=col.device)
+    sel = torch.empty(n_sc, n_keep, dtype=torch.int32, device=col.device)
+    L.check(L.load().tb_future_filter(L.ptr(col), L.ptr(edge), L.ptr(role), n_sc, K, A, T, t0, float(w_road_edge), n_keep,
+                                      L.ptr(score), L.ptr(sel), L.stream()), "tb_future_filter")
+    _count(2)
+    return score, sel
+
+
+def traj_global(pose: Tensor, sel: Optional[Tensor], center: Tensor, yaw: Tensor, n_sc: int, K: int, t0: int
+                ) -> Tuple[Tensor, Tensor]:
+    """tb_traj_global: pose [n_sc*K, A, T, 3] scene-centric -> (pos [n_sc, n_keep, A, T-t0, 2], yaw [.., 1]) global."""
+    pose, center, yaw = _f32c(pose), _f32c(center), _f32c(yaw).reshape(-1)
+    B, A, T, _ = pose.shape
+    n_keep = K if sel is None else sel.shape[1]
+    assert B == n_sc * K and (sel is None or (sel.dtype == torch.int32 and sel.is_contiguous()))
+    pos = torch.empty(n_sc, n_keep, A, T - t0, 2, dtype=torch.float32, device=pose.device)
+    oyaw = torch.empty(n_sc, n_keep, A, T - t0, 1, dtype=torch.float32, device=pose.device)
+    L.check(L.load().tb_traj_global(L.ptr(pose), L.ptr(sel), L.ptr(center), L.ptr(yaw), n_sc, K, n_keep, A, T, t0,
+                                    L.ptr(pos), L.ptr(oyaw), L.stream()), "tb_traj_global")
+    _count()
+    return pos, oyaw

@@ -88,3 +88,26 @@ def _one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed, boundary, n_rollout, late
     d["ag_latent"] = torch.randn(n_rollout, n_ag, latent_dim, generator=gl)
     d["ag_latent_valid"] = ag_valid.any(-1)
     return d
+
+
+def make_wosac_post_inputs(seed: int, n_sc: int, K: int, A: int, T: int):
+    """Seeded inputs of the WOSAC post-processing fixture (wosac_post_processing.py:31-75; shared by the golden
+    generator and the tests): scene-centric joint futures, violation
+    flags whose role-weighted counts are distinct per future (so the reference's top-k has no ties), roles, and the
+    scene -> global transform."""
+    g = torch.Generator().manual_seed(seed)
+    pose = torch.cat([(torch.rand(n_sc * K, A, T, 2, generator=g) * 2 - 1) * 150,
+                      (torch.rand(n_sc * K, A, T, 1, generator=g) * 2 - 1) * 3.1], -1)
+    role = torch.rand(n_sc, A, 3, generator=g) < 0.5
+    role[:, :, 0] |= ~role.any(-1)  # every agent has a role here: counts 0..K-1 need K-1 counted agents
+    col = torch.zeros(n_sc, K, A, T, dtype=torch.bool)
+    for s in range(n_sc):
+        perm = torch.randperm(K, generator=g)
+        for k in range(K):  # future k: perm[k] agents collide at some future step
+            ags = torch.randperm(A, generator=g)[: int(perm[k])]
+            col[s, k, ags, torch.randint(4, T, (len(ags),), generator=g)] = True
+    col[:, :, :, :4] |= torch.rand(n_sc, K, A, 4, generator=g) < 0.3  # history steps must be ignored
+    edge = torch.rand(n_sc, K, A, T, generator=g) < 0.02
+    center = (torch.rand(n_sc, 2, generator=g) * 2 - 1) * 5000
+    yaw = (torch.rand(n_sc, generator=g) * 2 - 1) * 3.1
+    return dict(pose=pose, role=role, collided=col, run_road_edge=edge, center=center, yaw=yaw)
