@@ -75,6 +75,8 @@ int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float
  *   f32 accumulate; q, u and a are split into fp16 head + residual, k, v and e are rounded to fp16: 2^-11 relative
  *   per component, the rounding a tf32 projection applies to its inputs anyway). Needs D == 128, rel != NULL and
  *   K0 + K1 <= 128 (TB_ERR_UNSUPPORTED otherwise). Implies the bit-0 trig.
+ * flags bit 2: out_ov / out_z are IEEE fp16 rows (ldo in halves, multiple of 8) — what tb_linear precision 2 consumes.
+ *   Needs D == 128, rel != NULL and bit 0 (or bit 1).
  * Limits: D in {128,256} (d_rpe == D), H == 4, all leading dims and pointers 16-byte aligned.
  * ------------------------------------------------------------------------------------------------- */
 int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
@@ -82,7 +84,7 @@ int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
                    const void* kv1, int ldkv1, int T1, int div1, int K1,
                    const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,
                    const float* pe_freq_xy, int B, int S, int D, int H,
-                   float* out_ov, float* out_z, int ldo, uint8_t* out_none_valid, int flags, void* stream);
+                   void* out_ov, void* out_z, int ldo, uint8_t* out_none_valid, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Dense projection  Y = epilogue(X W^T + bias)  — replaces F.linear / nn.Linear call sites
@@ -91,12 +93,14 @@ int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
  *   v = acc + bias[n]  (bias_group == 0)  or  acc + bias[(m / bias_group) * N + n]  (one bias row per group of
  *   bias_group consecutive rows: the PointNet "concat the group max" term W_right max_g + b, polyline_encoder.py:52);
  *   if relu: v = max(v,0); if mask_pre[m]: v = 0; if res: v += res[m*ldr+n]; if mask_post[m]: v = 0.
- * precision: 0 = fp32 FFMA (parity path), 1 = tf32 tcgen05 tensor cores (fp32 operands read as tf32, fp32 accumulate).
+ * precision: 0 = fp32 FFMA (parity path), 1 = tf32 tcgen05 tensor cores (fp32 operands read as tf32, fp32 accumulate),
+ *   2 = X and W are IEEE fp16 arrays (ldx in halves; tcgen05 kind::f16, fp32 accumulate) — the consumer side of the
+ *   fp16 intermediates of the tensor-core mode (attention output [ov|z], FFN hidden); bias / residual / Y stay fp32.
  * Yh (optional, precision 1 only): columns [col_h, N) of the result are written as IEEE fp16 to
  *   Yh[row*ldyh + col - col_h] instead of Y (col_h a multiple of 32; col_h == 0 => Y may be NULL). This is how the
  *   K|V tables consumed by tb_knarpe_attn flags bit 1 are produced without a conversion pass.
  * ------------------------------------------------------------------------------------------------- */
-int tb_linear(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
+int tb_linear(const void* X, int ldx, const void* W, const float* bias, int bias_group, float* Y, int ldy, int M,
               int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
               int precision, void* Yh, int ldyh, int col_h, void* stream);
 

@@ -417,3 +417,26 @@ def test_linear_fp16_split_output():
     assert float((tbl.cpu().double() - y).abs().max()) < 6e-3 * float(y.std())
     with pytest.raises(RuntimeError):                                  # the fp32 parity path has no fp16 output
         ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), precision=0, out_h=tbl, col_h=0)
+
+
+@pytest.mark.parametrize("M,N,K,flags", [(1000, 128, 640, "bm"), (4097, 128, 512, "bmr"), (300, 256, 64, "b"), (77, 40, 8, "")])
+def test_linear_fp16_operands(M, N, K, flags):
+    """tb_linear precision 2: fp16 activations x fp16 weights on tcgen05 kind::f16, fp32 accumulate / bias / residual
+    (the consumer of the tensor-core mode's fp16 [ov|z] rows and FFN hidden). The inputs are exactly representable in
+    fp16 here, so the result must match the fp64 product to fp32-accumulation accuracy."""
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g).half()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).half()
+    b = torch.randn(N, generator=g) if "b" in flags else None
+    res = torch.randn(M, N, generator=g) if "r" in flags else None
+    mask = torch.rand(M, generator=g) < 0.2 if "m" in flags else None
+    y = x.double() @ w.double().t() + (b.double() if b is not None else 0)
+    if mask is not None:
+        y = y.masked_fill(mask[:, None], 0.0)
+    if res is not None:
+        y = y + res.double()
+    dv = lambda t: None if t is None else t.to(DEV)  # noqa: E731
+    out = ops.linear(dv(x), dv(w), dv(b), mask_pre=dv(mask), res=dv(res), precision=2)
+    assert float((out.cpu().double() - y).abs().max()) < 2e-5 * max(1.0, float(y.abs().max()))
+    with pytest.raises(AssertionError):
+        ops.linear(dv(x).float(), dv(w), dv(b), precision=2)

@@ -5,8 +5,8 @@ int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, in
                   int N, int K,
                   int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                   cudaStream_t st);
-int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
-                 int N, int K,
+int tb_linear_tc(const void* X, int ldx, const void* W, int in_f16, const float* bias, int bias_group, float* Y,
+                 int ldy, int M, int N, int K,
                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                  void* Yh, int ldyh, int colh, cudaStream_t st);
 
@@ -25,7 +25,7 @@ extern "C" const char* tb_strerror(int code) {
 
 extern "C" int tb_version(void) { return 100; }
 
-extern "C" int tb_linear(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy,
+extern "C" int tb_linear(const void* X, int ldx, const void* W, const float* bias, int bias_group, float* Y, int ldy,
                          int M, int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                          int precision, void* Yh, int ldyh, int col_h, void* stream) {
   if (!X || !W) return TB_ERR_NULL;
@@ -37,10 +37,11 @@ extern "C" int tb_linear(const float* X, int ldx, const float* W, const float* b
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == 0) {
     if (Yh) return TB_ERR_UNSUPPORTED;  // fp16 tables belong to the tensor-core mode
-    return tb_linear_f32(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+    return tb_linear_f32(static_cast<const float*>(X), ldx, static_cast<const float*>(W), bias, bias_group, Y, ldy, M, N,
+                         K, relu, mask_pre, res, ldr, mask_post, st);
   }
-  if (precision == 1)
-    return tb_linear_tc(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, Yh, ldyh,
-                        col_h, st);
+  if (precision == 1 || precision == 2)
+    return tb_linear_tc(X, ldx, W, precision == 2, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr,
+                        mask_post, Yh, ldyh, col_h, st);
   return TB_ERR_UNSUPPORTED;
 }

@@ -19,6 +19,8 @@
 //     only, probabilities are exchanged with 3 xor-shuffles), one accumulator rescale per group.
 //   * everything inside a group is branch-free (masked neighbours get logit -inf), so the G dependency chains
 //     interleave (the v2 kernel was latency-bound: 33% stall_wait, 26% short-scoreboard at 14 warps/SM).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -41,7 +43,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int D, bool FROM_EMB, bool FAST_TRIG>
+template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false>  // OUT_H: [ov|z] written as fp16
 __global__ void __launch_bounds__(kWarps * 32, TB_ATTN_MINB)
 knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ u, int ldu,
                    const float* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
@@ -49,7 +51,7 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
                    const int32_t* __restrict__ idx, const uint8_t* __restrict__ invalid,
                    const float* __restrict__ rel, const float* __restrict__ emb,
                    const float* __restrict__ pe_freq_xy, int n_tok, int S,
-                   float* __restrict__ out_ov, float* __restrict__ out_z, int ldo,
+                   void* __restrict__ out_ov_, void* __restrict__ out_z_, int ldo,
                    uint8_t* __restrict__ out_none_valid) {
   constexpr int NV = D / 32;            // q/k/v floats per lane
   constexpr int NC = D / 32;            // embedding components per lane (l + 32k)
@@ -254,32 +256,48 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
 
   // ---- normalise + store (all-masked row: zeros, attention_rpe.py:188-190)
   const float inv_o = sm > 0.f ? 1.f / sm : 0.f;
-  float* op = out_ov + (size_t)tok * ldo + lane * NV;
+  if (OUT_H) {
+    __half* op = static_cast<__half*>(out_ov_) + (size_t)tok * ldo + lane * NV;
 #pragma unroll
-  for (int i = 0; i < NV; i += 4)
-    *reinterpret_cast<float4*>(op + i) =
-        make_float4(ov[i] * inv_o, ov[i + 1] * inv_o, ov[i + 2] * inv_o, ov[i + 3] * inv_o);
-  float* zp = out_z + (size_t)tok * ldo + lane;
+    for (int i = 0; i < NV; i += 2) *reinterpret_cast<__half2*>(op + i) = __floats2half2_rn(ov[i] * inv_o, ov[i + 1] * inv_o);
+    __half* zp = static_cast<__half*>(out_z_) + (size_t)tok * ldo + lane;
 #pragma unroll
-  for (int i = 0; i < H; ++i) {
-    const float inv_i = i == 0 ? inv_o : __shfl_xor_sync(TB_FULL_MASK, inv_o, 8 * i);
+    for (int i = 0; i < H; ++i) {
+      const float inv_i = i == 0 ? inv_o : __shfl_xor_sync(TB_FULL_MASK, inv_o, 8 * i);
 #pragma unroll
-    for (int k = 0; k < NC / 2; ++k) {
-      zp[(i ^ hh) * D + 64 * k] = z[i][k].x * inv_i;
-      zp[(i ^ hh) * D + 64 * k + 32] = z[i][k].y * inv_i;
+      for (int k = 0; k < NC / 2; ++k) {
+        zp[(i ^ hh) * D + 64 * k] = __float2half_rn(z[i][k].x * inv_i);
+        zp[(i ^ hh) * D + 64 * k + 32] = __float2half_rn(z[i][k].y * inv_i);
+      }
+    }
+  } else {
+    float* op = static_cast<float*>(out_ov_) + (size_t)tok * ldo + lane * NV;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4)
+      *reinterpret_cast<float4*>(op + i) =
+          make_float4(ov[i] * inv_o, ov[i + 1] * inv_o, ov[i + 2] * inv_o, ov[i + 3] * inv_o);
+    float* zp = static_cast<float*>(out_z_) + (size_t)tok * ldo + lane;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const float inv_i = i == 0 ? inv_o : __shfl_xor_sync(TB_FULL_MASK, inv_o, 8 * i);
+#pragma unroll
+      for (int k = 0; k < NC / 2; ++k) {
+        zp[(i ^ hh) * D + 64 * k] = z[i][k].x * inv_i;
+        zp[(i ^ hh) * D + 64 * k + 32] = z[i][k].y * inv_i;
+      }
     }
   }
   if (lane == 0 && out_none_valid) out_none_valid[tok] = sm > 0.f ? 0 : 1;
 }
 
-template <int D, bool FROM_EMB, bool FAST_TRIG>
+template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false>
 int launch(const float* q, int ldq, const float* u, int ldu, const float* kv0, int ldkv0, int T0, int div0, int K0,
            const float* kv1, int ldkv1, int T1, int div1, int K1, const int32_t* idx, const uint8_t* invalid,
-           const float* rel, const float* emb, const float* pe_freq_xy, int B, int S, float* out_ov, float* out_z,
+           const float* rel, const float* emb, const float* pe_freq_xy, int B, int S, void* out_ov, void* out_z,
            int ldo, uint8_t* out_none_valid, cudaStream_t st) {
   const int n_tok = B * S;
   const int grid = (n_tok + kWarps - 1) / kWarps;
-  knarpe_attn_kernel<D, FROM_EMB, FAST_TRIG><<<grid, kWarps * 32, 0, st>>>(q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1,
+  knarpe_attn_kernel<D, FROM_EMB, FAST_TRIG, OUT_H><<<grid, kWarps * 32, 0, st>>>(q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1,
                                                               T1, div1, K1, idx, invalid, rel, emb, pe_freq_xy, n_tok,
                                                               S, out_ov, out_z, ldo, out_none_valid);
   TB_CHECK_LAUNCH();
@@ -292,14 +310,14 @@ int launch(const float* q, int ldq, const float* u, int ldu, const float* kv0, i
 int tb_knarpe_attn_mma_launch(const float* q, int ldq, const float* u, int ldu, const void* kv0, int ldkv0, int T0,
                               int div0, int K0, const void* kv1, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* pe_freq_xy,
-                              int B, int S, float* out_ov, float* out_z, int ldo, uint8_t* out_none_valid,
+                              int B, int S, void* out_ov, void* out_z, int ldo, int out_f16, uint8_t* out_none_valid,
                               cudaStream_t st);
 bool tb_knarpe_attn_mma_supported(int D, int Hh, int Ktot);
 
 extern "C" int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu, const void* kv0_, int ldkv0, int T0,
                               int div0, int K0, const void* kv1_, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,
-                              const float* pe_freq_xy, int B, int S, int D, int Hh, float* out_ov, float* out_z,
+                              const float* pe_freq_xy, int B, int S, int D, int Hh, void* out_ov, void* out_z,
                               int ldo, uint8_t* out_none_valid, int flags, void* stream) {
   const float* kv0 = static_cast<const float*>(kv0_);
   const float* kv1 = static_cast<const float*>(kv1_);
@@ -317,11 +335,17 @@ extern "C" int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu, 
 #define TB_ATT_ARGS q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1, T1, div1, K1, idx, invalid, rel, emb, \
                     pe_freq_xy, B, S, out_ov, out_z, ldo, out_none_valid, st
   const bool fast = (flags & 1) != 0;  // bit 0: SFU-only range reduction of the embedding angles (tensor-core mode)
+  const int out_h = (flags & 4) != 0;  // bit 2: out_ov / out_z are fp16 rows (ldo in halves)
+  if (out_h && (ldo & 7)) return TB_ERR_MISALIGNED;
   if (flags & 2) {  // bit 1: fp16 K|V tables, all contractions on mma.sync (knarpe_attn_mma.cu)
     if (!rel || !tb_knarpe_attn_mma_supported(D, Hh, K0 + K1)) return TB_ERR_UNSUPPORTED;
     if ((ldkv0 | (K1 > 0 ? ldkv1 : 0)) & 7) return TB_ERR_MISALIGNED;
     return tb_knarpe_attn_mma_launch(q, ldq, u, ldu, kv0_, ldkv0, T0, div0, K0, kv1_, ldkv1, T1, div1, K1, idx, invalid,
-                                     rel, pe_freq_xy, B, S, out_ov, out_z, ldo, out_none_valid, st);
+                                     rel, pe_freq_xy, B, S, out_ov, out_z, ldo, out_h, out_none_valid, st);
+  }
+  if (out_h) {  // fp16 [ov|z] rows from the SIMT kernel: the tensor-core mode's short neighbour lists
+    if (D != 128 || !rel || !fast) return TB_ERR_UNSUPPORTED;
+    return launch<128, false, true, true>(TB_ATT_ARGS);
   }
   if (D == 128) {
     if (!rel) return launch<128, true, false>(TB_ATT_ARGS);

@@ -80,13 +80,14 @@ __device__ __forceinline__ uint4 ldg128(const __half* p) { return __ldg(reinterp
 __host__ __device__ constexpr int cos_base(int c) { return c < 2 ? 8 * c : (c < 4 ? 32 + 8 * (c - 2) : 64 + 8 * (c - 4)); }
 __host__ __device__ constexpr int sin_base(int c) { return cos_base(c) + (c < 4 ? 16 : 32); }
 
+template <bool OUT_H>  // OUT_H: [ov|z] rows are written as fp16 (consumed by the kind::f16 output projection)
 __global__ void __launch_bounds__(kWarps * 32, TB_MMA_MINB)
 knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ u, int ldu,
                        const __half* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
                        const __half* __restrict__ kv1, int ldkv1, int T1, int div1, int K1,
                        const int32_t* __restrict__ idx, const uint8_t* __restrict__ invalid,
                        const float* __restrict__ rel, const float* __restrict__ pe_freq_xy, int n_tok, int S,
-                       float* __restrict__ out_ov, float* __restrict__ out_z, int ldo,
+                       void* __restrict__ out_ov_, void* __restrict__ out_z_, int ldo,
                        uint8_t* __restrict__ out_none_valid) {
   __shared__ __align__(16) unsigned char s_raw[kWarps][kWarpSmem];
 
@@ -361,11 +362,25 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
     }
   }
   __syncwarp();
-  *reinterpret_cast<float4*>(out_ov + (size_t)tok * ldo + lane * 4) = *reinterpret_cast<const float4*>(s_out + lane * 4);
-  float* zp = out_z + (size_t)tok * ldo + lane * 4;
+  if (OUT_H) {
+    auto to_h4 = [](const float* p) {
+      const float4 v = *reinterpret_cast<const float4*>(p);
+      return make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+    };
+    __half* ov_h = static_cast<__half*>(out_ov_) + (size_t)tok * ldo + lane * 4;
+    __half* z_h = static_cast<__half*>(out_z_) + (size_t)tok * ldo + lane * 4;
+    *reinterpret_cast<uint2*>(ov_h) = to_h4(s_out + lane * 4);
 #pragma unroll
-  for (int k = 0; k < H; ++k)
-    *reinterpret_cast<float4*>(zp + k * D) = *reinterpret_cast<const float4*>(s_out + D + k * D + lane * 4);
+    for (int k = 0; k < H; ++k) *reinterpret_cast<uint2*>(z_h + k * D) = to_h4(s_out + D + k * D + lane * 4);
+  } else {
+    float* out_ov = static_cast<float*>(out_ov_);
+    float* out_z = static_cast<float*>(out_z_);
+    *reinterpret_cast<float4*>(out_ov + (size_t)tok * ldo + lane * 4) = *reinterpret_cast<const float4*>(s_out + lane * 4);
+    float* zp = out_z + (size_t)tok * ldo + lane * 4;
+#pragma unroll
+    for (int k = 0; k < H; ++k)
+      *reinterpret_cast<float4*>(zp + k * D) = *reinterpret_cast<const float4*>(s_out + D + k * D + lane * 4);
+  }
   if (lane == 0 && out_none_valid) out_none_valid[tok] = nvalid > 0 ? 0 : 1;
 }
 
@@ -376,13 +391,18 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
 int tb_knarpe_attn_mma_launch(const float* q, int ldq, const float* u, int ldu, const void* kv0, int ldkv0, int T0,
                               int div0, int K0, const void* kv1, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* pe_freq_xy,
-                              int B, int S, float* out_ov, float* out_z, int ldo, uint8_t* out_none_valid,
+                              int B, int S, void* out_ov, void* out_z, int ldo, int out_f16, uint8_t* out_none_valid,
                               cudaStream_t st) {
   const int n_tok = B * S;
   const int grid = (n_tok + kWarps - 1) / kWarps;
-  knarpe_attn_mma_kernel<<<grid, kWarps * 32, 0, st>>>(
-      q, ldq, u, ldu, static_cast<const __half*>(kv0), ldkv0, T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1,
-      div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid);
+  if (out_f16)
+    knarpe_attn_mma_kernel<true><<<grid, kWarps * 32, 0, st>>>(
+        q, ldq, u, ldu, static_cast<const __half*>(kv0), ldkv0, T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1,
+        div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid);
+  else
+    knarpe_attn_mma_kernel<false><<<grid, kWarps * 32, 0, st>>>(
+        q, ldq, u, ldu, static_cast<const __half*>(kv0), ldkv0, T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1,
+        div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

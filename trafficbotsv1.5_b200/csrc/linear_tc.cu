@@ -20,9 +20,10 @@ int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, in
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;  // BK floats = 128 bytes = one swizzle-128B row
+constexpr int BM = 128, BN = 128;
+constexpr int BK_BYTES = 128;  // one k-block = one swizzle-128B row per operand row: 32 tf32/fp32 or 64 fp16 elements
 constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+constexpr int A_BYTES = BM * BK_BYTES, B_BYTES = BN * BK_BYTES;
 constexpr int EPI_WARPS = 16;                 // 4 warps per TMEM lane quarter, each owning BN/4 of the tile's columns
 constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
 constexpr int NUM_THREADS = (EPI_WARPS + 2) * 32;
@@ -64,13 +65,21 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if (F16)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (canonical 1),
 // descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp bit layout).
@@ -78,15 +87,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// kind::tf32 instruction descriptor: D fp32 (bit 4), A/B tf32 (2 at bits 7 / 10), K-major A and B, N>>3 at bit 17,
-// M>>4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// Instruction descriptor: D fp32 (bit 4), A/B format at bits 7 / 10 (kind::tf32: 2 = tf32; kind::f16: 0 = fp16),
+// K-major A and B, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool f16) {
+  return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 
+// F16: operands are fp16 in memory (kind::f16, 64 elements per k-block) instead of fp32 read as tf32 (32 per k-block)
+template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                   float* __restrict__ Y, int ldy, int M, int N, int K, Epi ep) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 float* __restrict__ Y, int ldy, int M, int N, int K, Epi ep) {
+  constexpr int BK = F16 ? 64 : 32;  // elements per k-block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -138,7 +151,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   } else if (warp == EPI_WARPS + 1) {
     // ===== MMA issuer (one elected lane) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc = make_idesc(BM, BN, F16);
       int it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
@@ -151,8 +164,8 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           const uint64_t adesc = make_desc(smem_u32(sA + s * A_BYTES));
           const uint64_t bdesc = make_desc(smem_u32(sB + s * B_BYTES));
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk)  // UMMA_K = 8 tf32 = 32 bytes -> +2 in 16-byte units
-            umma_tf32(tmem_base + buf * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+          for (int kk = 0; kk < BK_BYTES / 32; ++kk)  // UMMA_K = 8 tf32 / 16 fp16 = 32 bytes -> +2 in 16-byte units
+            umma<F16>(tmem_base + buf * BN, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
           umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
         }
         umma_commit(&tfull[buf]);  // accumulator of this tile complete
@@ -289,37 +302,43 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] with row stride ld (floats); box = 32 cols (128 B) x box_rows, 128-byte swizzle,
-// out-of-bounds elements read as zero (handles the M / N / K tails).
-bool make_map(CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+// 2-D fp32 / fp16 tensor [rows, cols] with row stride ld (elements); box = 128 B of columns x box_rows, 128-byte
+// swizzle, out-of-bounds elements read as zero (handles the M / N / K tails).
+bool make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, bool f16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
+  const int esz = f16 ? 2 : 4;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(BK_BYTES / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+  return enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim,
+             gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
 
-int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, int bias_group, float* Y, int ldy, int M,
-                 int N, int K,
+int tb_linear_tc(const void* X, int ldx, const void* W, int in_f16, const float* bias, int bias_group, float* Y,
+                 int ldy, int M, int N, int K,
                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
                  void* Yh, int ldyh, int colh, cudaStream_t st) {
-  const bool ok = (K % 4 == 0) && (ldx % 4 == 0) && tb_aligned16(X) && tb_aligned16(W);
+  const int ea = in_f16 ? 8 : 4;  // elements per 16 bytes: TMA needs 16-byte aligned rows
+  const bool ok = (K % ea == 0) && (ldx % ea == 0) && tb_aligned16(X) && tb_aligned16(W);
   if (!ok) {
-    if (Yh) return TB_ERR_UNSUPPORTED;  // the fp32 kernel has no fp16 output path
-    return tb_linear_f32(X, ldx, W, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr, mask_post, st);
+    if (Yh || in_f16) return TB_ERR_UNSUPPORTED;  // the fp32 kernel has no fp16 input / output path
+    return tb_linear_f32(static_cast<const float*>(X), ldx, static_cast<const float*>(W), bias, bias_group, Y, ldy, M, N, K,
+                         relu, mask_pre, res, ldr, mask_post, st);
   }
   CUtensorMap mapA, mapB;
-  if (!make_map(&mapA, X, M, K, ldx, BM) || !make_map(&mapB, W, N, K, K, BN)) return TB_ERR_CUDA;
+  if (!make_map(&mapA, X, M, K, ldx, BM, in_f16) || !make_map(&mapB, W, N, K, K, BN, in_f16)) return TB_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
+            cudaSuccess)
       return TB_ERR_CUDA;
     attr_set = true;
   }
@@ -334,7 +353,8 @@ int tb_linear_tc(const float* X, int ldx, const float* W, const float* bias, int
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms ? total : num_sms;  // persistent: one CTA per SM
   Epi ep{bias, bias_group, relu, mask_pre, res, ldr, mask_post, static_cast<__half*>(Yh), ldyh, colh};
-  linear_tf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
+  if (in_f16) linear_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
+  else linear_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

@@ -162,7 +162,22 @@ class HotPathModel:
         d = self.d
         return ops.knarpe_attn(proj[:, :d], proj[:, d:d + H * d], kv0, T0, div0, K0, knn["idx"], knn["inv"],
                                knn.get("rel"), self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1,
-                               emb=knn.get("emb"), fast_trig=self.precision == 1)
+                               emb=knn.get("emb"), fast_trig=self.precision == 1,
+                               out_dtype=torch.float16 if self.kv_half else torch.float32)
+
+    def _half(self, key: str, w: Tensor) -> Tensor:
+        """fp16 copy of a weight matrix (tensor-core mode: operands of the kind::f16 projections), made once."""
+        if not hasattr(self, "_w_half"):
+            self._w_half = {}
+        if key not in self._w_half:
+            self._w_half[key] = w.to(torch.float16).contiguous()
+        return self._w_half[key]
+
+    def _out_proj(self, p: str, f: dict, o: Tensor, nv: Tensor, res: Tensor) -> Tensor:
+        """Output projection over [ov|z] (fp16 rows in tensor-core mode -> kind::f16 MMA, fp32 accumulate/residual)."""
+        if o.dtype == torch.float16:
+            return ops.linear(o, self._half(f"{p}.w_out", f["w_out"]), f["b_out"], mask_pre=nv, res=res, precision=2)
+        return ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=res, precision=self.precision)
 
     def tf_layer(self, p: str, mode: str, src: Tensor, src_inv: Tensor, B: int, S: int, knn_self: dict,
                  cross: Optional[dict] = None, out: Optional[Tensor] = None) -> Tensor:
@@ -172,18 +187,25 @@ class HotPathModel:
             f = self.fa[f"{p}.attn_src"]
             proj, kv = self._in_self(f, self.ln(src, f"{p}.norm_src"), knn_self["idx"].shape[-1])
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
-            src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
+            src = self._out_proj(f"{p}.attn_src", f, o, nv, src)
             f = self.fa[f"{p}.attn"]
             proj = ops.linear(self.ln(src, f"{p}.norm1"), f["w_in_q"], f["b_in_q"], precision=pr)
             o, nv = self._attend(f, proj, B, S, cross["kv0"], cross["T0"], cross["div0"], cross["K0"], cross,
                                  cross.get("kv1"), cross.get("T1", 0), cross.get("div1", 1), cross.get("K1", 0))
-            src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
+            src = self._out_proj(f"{p}.attn", f, o, nv, src)
         else:  # enc_self_attn: q and k/v both from norm1(src) (:218-221)
             f = self.fa[f"{p}.attn"]
             proj, kv = self._in_self(f, self.ln(src, f"{p}.norm1"), knn_self["idx"].shape[-1])
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
-            src = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=src, precision=pr)
-        h = self.lin(self.ln(src, f"{p}.norm2"), f"{p}.linear1", relu=True)
+            src = self._out_proj(f"{p}.attn", f, o, nv, src)
+        x2 = self.ln(src, f"{p}.norm2")
+        if self.kv_half:  # FFN hidden (ReLU output) as fp16: written by the first projection, read by a kind::f16 one
+            h = torch.empty(x2.shape[0], self.P[f"{p}.linear1.weight"].shape[0], dtype=torch.float16, device=x2.device)
+            ops.linear(x2, self.P[f"{p}.linear1.weight"], self.P[f"{p}.linear1.bias"], relu=True, precision=1, out_h=h,
+                       col_h=0)
+            return ops.linear(h, self._half(f"{p}.linear2", self.P[f"{p}.linear2.weight"]), self.P[f"{p}.linear2.bias"],
+                              res=src, mask_post=src_inv, out=out, precision=2)
+        h = self.lin(x2, f"{p}.linear1", relu=True)
         return self.lin(h, f"{p}.linear2", res=src, mask_post=src_inv, out=out)
 
     # ------------------------------------------------------------------------------------------ map (once / scene)

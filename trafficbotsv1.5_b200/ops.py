@@ -65,10 +65,11 @@ def knn_select(src_pose: Tensor, src_invalid: Tensor, tgt_pose: Tensor, tgt_inva
 def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, idx: Tensor, invalid: Tensor,
                 rel: Optional[Tensor], freq_xy: Tensor, B: int, S: int, D: int, H: int = 4,
                 kv1: Optional[Tensor] = None, T1: int = 0, div1: int = 1, K1: int = 0,
-                emb: Optional[Tensor] = None, out: Optional[Tensor] = None, fast_trig: bool = False
-                ) -> Tuple[Tensor, Tensor]:
+                emb: Optional[Tensor] = None, out: Optional[Tensor] = None, fast_trig: bool = False,
+                out_dtype: torch.dtype = torch.float32) -> Tuple[Tensor, Tensor]:
     """KNARPE core. q/u/kv*: 2-D (possibly column-sliced, row-strided) views; returns (out [B*S, D+H*D] = [ov|z],
-    none_valid bool [B*S]). float16 kv tables select the tensor-core kernel (tb_knarpe_attn flags bit 1)."""
+    none_valid bool [B*S]). float16 kv tables select the tensor-core kernel (tb_knarpe_attn flags bit 1), a float16
+    `out` (or out_dtype) the fp16 output rows (bit 2)."""
     M = B * S
     rpe_mma = kv0.dtype == torch.float16
     for t in (q, u):
@@ -76,7 +77,8 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
     for t in (kv0,) + ((kv1,) if kv1 is not None else ()):
         assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == kv0.dtype and t.dtype in (torch.float32, torch.float16)
     if out is None:
-        out = torch.empty(M, D + H * D, dtype=torch.float32, device=q.device)
+        out = torch.empty(M, D + H * D, dtype=out_dtype, device=q.device)
+    assert out.dtype in (torch.float32, torch.float16) and out.stride(1) == 1
     none_valid = torch.empty(M, dtype=torch.bool, device=q.device)
     assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.shape[-1] == K0 + K1
     inv = _u8(invalid)
@@ -90,7 +92,7 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
         L.ptr(q), q.stride(0), L.ptr(u), u.stride(0), L.ptr(kv0), kv0.stride(0), T0, div0, K0,
         L.ptr(kv1), kv1.stride(0) if kv1 is not None else 0, T1, div1, K1, L.ptr(idx), L.ptr(inv), L.ptr(rel),
         L.ptr(emb), L.ptr(freq_xy), B, S, D, H, L.ptr(out), L.ptr(z), out.stride(0), L.ptr(_u8(none_valid)),
-        int(fast_trig) | (2 if rpe_mma else 0), L.stream()), "tb_knarpe_attn")
+        int(fast_trig) | (2 if rpe_mma else 0) | (4 if out.dtype == torch.float16 else 0), L.stream()), "tb_knarpe_attn")
     _count()
     return out, none_valid
 
@@ -101,7 +103,9 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False,
     """Y = epilogue(X W^T + b) on 2-D row-strided views (see tb_linear). With `out_h` (float16 [M, N - col_h]) the
     columns >= col_h go there instead (tensor-core mode only) and `out` holds the first col_h columns
     (returned; None when col_h == 0)."""
-    assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.dtype == torch.float32
+    in_dt = torch.float16 if precision == 2 else torch.float32  # precision 2: fp16 activations x fp16 weights
+    assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.dtype == in_dt and w.dtype == in_dt, \
+        (x.dtype, w.dtype, precision)
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K, (w.shape, x.shape)
