@@ -77,9 +77,11 @@ int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float
  *   K0 + K1 <= 128 (TB_ERR_UNSUPPORTED otherwise). Implies the bit-0 trig.
  * flags bit 2: out_ov / out_z are IEEE fp16 rows (ldo in halves, multiple of 8) — what tb_linear precision 2 consumes.
  *   Needs D == 128, rel != NULL and bit 0 (or bit 1).
+ * flags bit 3: q / u are IEEE fp16 rows (ldq, ldu in halves, multiples of 8) as written by tb_linear's Yh output;
+ *   with bit 1 they are MMA operands as they are (no residual). Needs bit 2 when bit 1 is not set.
  * Limits: D in {128,256} (d_rpe == D), H == 4, all leading dims and pointers 16-byte aligned.
  * ------------------------------------------------------------------------------------------------- */
-int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu,
+int tb_knarpe_attn(const void* q, int ldq, const void* u, int ldu,
                    const void* kv0, int ldkv0, int T0, int div0, int K0,
                    const void* kv1, int ldkv1, int T1, int div1, int K1,
                    const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,

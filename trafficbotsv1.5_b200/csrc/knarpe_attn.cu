@@ -43,9 +43,10 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false>  // OUT_H: [ov|z] written as fp16
+// OUT_H: [ov|z] written as fp16; IN_H: q / u rows are fp16 (tensor-core mode intermediates)
+template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false, bool IN_H = false>
 __global__ void __launch_bounds__(kWarps * 32, TB_ATTN_MINB)
-knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ u, int ldu,
+knarpe_attn_kernel(const void* __restrict__ q_, int ldq, const void* __restrict__ u_, int ldu,
                    const float* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
                    const float* __restrict__ kv1, int ldkv1, int T1, int div1, int K1,
                    const int32_t* __restrict__ idx, const uint8_t* __restrict__ invalid,
@@ -83,17 +84,33 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   float qr[NV];
   float2 u01[NC], u23[NC], z[H][NC / 2];
   {
-    const float* qp = q + (size_t)tok * ldq + lane * NV;
+    if (IN_H) {
+      const __half* qp = static_cast<const __half*>(q_) + (size_t)tok * ldq + lane * NV;
 #pragma unroll
-    for (int i = 0; i < NV; i += 4) {
-      float4 t = ldg4(qp + i);
-      qr[i] = t.x; qr[i + 1] = t.y; qr[i + 2] = t.z; qr[i + 3] = t.w;
-    }
-    const float* up = u + (size_t)tok * ldu + lane;
+      for (int i = 0; i < NV; i += 2) {
+        const float2 t = __half22float2(__ldg(reinterpret_cast<const __half2*>(qp + i)));
+        qr[i] = t.x; qr[i + 1] = t.y;
+      }
+      const __half* up = static_cast<const __half*>(u_) + (size_t)tok * ldu + lane;
+      auto ld = [&](int h, int k) { return __half2float(__ldg(up + h * D + 32 * k)); };
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      u01[k] = make_float2(__ldg(up + (0 ^ hh) * D + 32 * k), __ldg(up + (1 ^ hh) * D + 32 * k));
-      u23[k] = make_float2(__ldg(up + (2 ^ hh) * D + 32 * k), __ldg(up + (3 ^ hh) * D + 32 * k));
+      for (int k = 0; k < NC; ++k) {
+        u01[k] = make_float2(ld(0 ^ hh, k), ld(1 ^ hh, k));
+        u23[k] = make_float2(ld(2 ^ hh, k), ld(3 ^ hh, k));
+      }
+    } else {
+      const float* qp = static_cast<const float*>(q_) + (size_t)tok * ldq + lane * NV;
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        float4 t = ldg4(qp + i);
+        qr[i] = t.x; qr[i + 1] = t.y; qr[i + 2] = t.z; qr[i + 3] = t.w;
+      }
+      const float* up = static_cast<const float*>(u_) + (size_t)tok * ldu + lane;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        u01[k] = make_float2(__ldg(up + (0 ^ hh) * D + 32 * k), __ldg(up + (1 ^ hh) * D + 32 * k));
+        u23[k] = make_float2(__ldg(up + (2 ^ hh) * D + 32 * k), __ldg(up + (3 ^ hh) * D + 32 * k));
+      }
     }
 #pragma unroll
     for (int i = 0; i < H; ++i)
@@ -290,14 +307,14 @@ knarpe_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   if (lane == 0 && out_none_valid) out_none_valid[tok] = sm > 0.f ? 0 : 1;
 }
 
-template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false>
-int launch(const float* q, int ldq, const float* u, int ldu, const float* kv0, int ldkv0, int T0, int div0, int K0,
+template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false, bool IN_H = false>
+int launch(const void* q, int ldq, const void* u, int ldu, const float* kv0, int ldkv0, int T0, int div0, int K0,
            const float* kv1, int ldkv1, int T1, int div1, int K1, const int32_t* idx, const uint8_t* invalid,
            const float* rel, const float* emb, const float* pe_freq_xy, int B, int S, void* out_ov, void* out_z,
            int ldo, uint8_t* out_none_valid, cudaStream_t st) {
   const int n_tok = B * S;
   const int grid = (n_tok + kWarps - 1) / kWarps;
-  knarpe_attn_kernel<D, FROM_EMB, FAST_TRIG, OUT_H><<<grid, kWarps * 32, 0, st>>>(q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1,
+  knarpe_attn_kernel<D, FROM_EMB, FAST_TRIG, OUT_H, IN_H><<<grid, kWarps * 32, 0, st>>>(q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1,
                                                               T1, div1, K1, idx, invalid, rel, emb, pe_freq_xy, n_tok,
                                                               S, out_ov, out_z, ldo, out_none_valid);
   TB_CHECK_LAUNCH();
@@ -307,14 +324,14 @@ int launch(const float* q, int ldq, const float* u, int ldu, const float* kv0, i
 }  // namespace
 
 // tensor-core variant (knarpe_attn_mma.cu)
-int tb_knarpe_attn_mma_launch(const float* q, int ldq, const float* u, int ldu, const void* kv0, int ldkv0, int T0,
+int tb_knarpe_attn_mma_launch(const void* q, int ldq, const void* u, int ldu, int in_f16, const void* kv0, int ldkv0, int T0,
                               int div0, int K0, const void* kv1, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* pe_freq_xy,
                               int B, int S, void* out_ov, void* out_z, int ldo, int out_f16, uint8_t* out_none_valid,
                               cudaStream_t st);
 bool tb_knarpe_attn_mma_supported(int D, int Hh, int Ktot);
 
-extern "C" int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu, const void* kv0_, int ldkv0, int T0,
+extern "C" int tb_knarpe_attn(const void* q, int ldq, const void* u, int ldu, const void* kv0_, int ldkv0, int T0,
                               int div0, int K0, const void* kv1_, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,
                               const float* pe_freq_xy, int B, int S, int D, int Hh, void* out_ov, void* out_z,
@@ -336,16 +353,17 @@ extern "C" int tb_knarpe_attn(const float* q, int ldq, const float* u, int ldu, 
                     pe_freq_xy, B, S, out_ov, out_z, ldo, out_none_valid, st
   const bool fast = (flags & 1) != 0;  // bit 0: SFU-only range reduction of the embedding angles (tensor-core mode)
   const int out_h = (flags & 4) != 0;  // bit 2: out_ov / out_z are fp16 rows (ldo in halves)
-  if (out_h && (ldo & 7)) return TB_ERR_MISALIGNED;
+  const int in_h = (flags & 8) != 0;   // bit 3: q / u are fp16 rows (ldq, ldu in halves)
+  if ((out_h && (ldo & 7)) || (in_h && ((ldq | ldu) & 7))) return TB_ERR_MISALIGNED;
   if (flags & 2) {  // bit 1: fp16 K|V tables, all contractions on mma.sync (knarpe_attn_mma.cu)
     if (!rel || !tb_knarpe_attn_mma_supported(D, Hh, K0 + K1)) return TB_ERR_UNSUPPORTED;
     if ((ldkv0 | (K1 > 0 ? ldkv1 : 0)) & 7) return TB_ERR_MISALIGNED;
-    return tb_knarpe_attn_mma_launch(q, ldq, u, ldu, kv0_, ldkv0, T0, div0, K0, kv1_, ldkv1, T1, div1, K1, idx, invalid,
-                                     rel, pe_freq_xy, B, S, out_ov, out_z, ldo, out_h, out_none_valid, st);
+    return tb_knarpe_attn_mma_launch(q, ldq, u, ldu, in_h, kv0_, ldkv0, T0, div0, K0, kv1_, ldkv1, T1, div1, K1, idx,
+                                     invalid, rel, pe_freq_xy, B, S, out_ov, out_z, ldo, out_h, out_none_valid, st);
   }
-  if (out_h) {  // fp16 [ov|z] rows from the SIMT kernel: the tensor-core mode's short neighbour lists
-    if (D != 128 || !rel || !fast) return TB_ERR_UNSUPPORTED;
-    return launch<128, false, true, true>(TB_ATT_ARGS);
+  if (out_h || in_h) {  // fp16 intermediates with the SIMT kernel: the tensor-core mode's short neighbour lists
+    if (D != 128 || !rel || !fast || !out_h) return TB_ERR_UNSUPPORTED;
+    return in_h ? launch<128, false, true, true, true>(TB_ATT_ARGS) : launch<128, false, true, true, false>(TB_ATT_ARGS);
   }
   if (D == 128) {
     if (!rel) return launch<128, true, false>(TB_ATT_ARGS);

@@ -80,9 +80,11 @@ __device__ __forceinline__ uint4 ldg128(const __half* p) { return __ldg(reinterp
 __host__ __device__ constexpr int cos_base(int c) { return c < 2 ? 8 * c : (c < 4 ? 32 + 8 * (c - 2) : 64 + 8 * (c - 4)); }
 __host__ __device__ constexpr int sin_base(int c) { return cos_base(c) + (c < 4 ? 16 : 32); }
 
-template <bool OUT_H>  // OUT_H: [ov|z] rows are written as fp16 (consumed by the kind::f16 output projection)
+// OUT_H: [ov|z] rows are written as fp16 (consumed by the kind::f16 output projection). IN_H: q / u rows are fp16
+// (written by the in-projection's fp16 epilogue): they are MMA operands as they are, no residual columns.
+template <bool OUT_H, bool IN_H>
 __global__ void __launch_bounds__(kWarps * 32, TB_MMA_MINB)
-knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ u, int ldu,
+knarpe_attn_mma_kernel(const void* __restrict__ q_, int ldq, const void* __restrict__ u_, int ldu,
                        const __half* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
                        const __half* __restrict__ kv1, int ldkv1, int T1, int div1, int K1,
                        const int32_t* __restrict__ idx, const uint8_t* __restrict__ invalid,
@@ -133,16 +135,29 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
     fq[c][1] = __ldg(pe_freq_xy + 8 * c + 2 * t + 1);
   }
   float2 u_raw[8][2];
-  {
-    const float* up = u + (size_t)tok * ldu + hA * D + 2 * t;
+  float4 q_lo4 = make_float4(0.f, 0.f, 0.f, 0.f), q_hi4 = q_lo4;
+  uint32_t uB[8][2], qB[2][2];
+  if (IN_H) {  // fp16 rows: the half2 pairs are the B registers themselves (columns 4-7 of B stay zero)
+    const __half* up = static_cast<const __half*>(u_) + (size_t)tok * ldu + hA * D + 2 * t;
+    const __half* qp = static_cast<const __half*>(q_) + (size_t)tok * ldq + 32 * hA + 8 * t;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uB[c][0] = lo_part ? 0u : __ldg(reinterpret_cast<const uint32_t*>(up + cos_base(c)));
+      uB[c][1] = lo_part ? 0u : __ldg(reinterpret_cast<const uint32_t*>(up + sin_base(c)));
+    }
+    const uint4 qq = lo_part ? make_uint4(0u, 0u, 0u, 0u) : __ldg(reinterpret_cast<const uint4*>(qp));
+    qB[0][0] = qq.x; qB[0][1] = qq.y; qB[1][0] = qq.z; qB[1][1] = qq.w;
+  } else {
+    const float* up = static_cast<const float*>(u_) + (size_t)tok * ldu + hA * D + 2 * t;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       u_raw[c][0] = __ldg(reinterpret_cast<const float2*>(up + cos_base(c)));
       u_raw[c][1] = __ldg(reinterpret_cast<const float2*>(up + sin_base(c)));
     }
+    const float* qp = static_cast<const float*>(q_) + (size_t)tok * ldq + 32 * hA + 8 * t;
+    q_lo4 = ldg4(qp);
+    q_hi4 = ldg4(qp + 4);
   }
-  const float* qp = q + (size_t)tok * ldq + 32 * hA + 8 * t;
-  const float4 q_lo4 = ldg4(qp), q_hi4 = ldg4(qp + 4);
 
   // ---- compact the unmasked neighbours; pad to a multiple of 16 with weight-0 dummies
   int nvalid = 0;
@@ -173,16 +188,17 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
 
   // B fragments of u (chunk c: b0 = slots 2t,2t+1, b1 = slots 2t+8,2t+9; column g = head hA, residual for g >= 4) and
   // of the block-diagonal q (chunks 2 hA + e only; other chunks are zero for this column)
-  uint32_t uB[8][2], qB[2][2];
+  if (!IN_H) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uB[c][0] = split_h2(u_raw[c][0].x, u_raw[c][0].y, lo_part);
-    uB[c][1] = split_h2(u_raw[c][1].x, u_raw[c][1].y, lo_part);
+    for (int c = 0; c < 8; ++c) {
+      uB[c][0] = split_h2(u_raw[c][0].x, u_raw[c][0].y, lo_part);
+      uB[c][1] = split_h2(u_raw[c][1].x, u_raw[c][1].y, lo_part);
+    }
+    qB[0][0] = split_h2(q_lo4.x, q_lo4.y, lo_part);
+    qB[0][1] = split_h2(q_lo4.z, q_lo4.w, lo_part);
+    qB[1][0] = split_h2(q_hi4.x, q_hi4.y, lo_part);
+    qB[1][1] = split_h2(q_hi4.z, q_hi4.w, lo_part);
   }
-  qB[0][0] = split_h2(q_lo4.x, q_lo4.y, lo_part);
-  qB[0][1] = split_h2(q_lo4.z, q_lo4.w, lo_part);
-  qB[1][0] = split_h2(q_hi4.x, q_hi4.y, lo_part);
-  qB[1][1] = split_h2(q_hi4.z, q_hi4.w, lo_part);
 
   float zacc[8][4], oacc[2][4];
 #pragma unroll
@@ -388,21 +404,22 @@ knarpe_attn_mma_kernel(const float* __restrict__ q, int ldq, const float* __rest
 
 // Called by tb_knarpe_attn (knarpe_attn.cu) after argument validation when flags bit 1 is set. kv tables are fp16
 // with leading dimensions in halves.
-int tb_knarpe_attn_mma_launch(const float* q, int ldq, const float* u, int ldu, const void* kv0, int ldkv0, int T0,
+int tb_knarpe_attn_mma_launch(const void* q, int ldq, const void* u, int ldu, int in_f16, const void* kv0, int ldkv0, int T0,
                               int div0, int K0, const void* kv1, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* pe_freq_xy,
                               int B, int S, void* out_ov, void* out_z, int ldo, int out_f16, uint8_t* out_none_valid,
                               cudaStream_t st) {
   const int n_tok = B * S;
   const int grid = (n_tok + kWarps - 1) / kWarps;
-  if (out_f16)
-    knarpe_attn_mma_kernel<true><<<grid, kWarps * 32, 0, st>>>(
-        q, ldq, u, ldu, static_cast<const __half*>(kv0), ldkv0, T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1,
-        div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid);
-  else
-    knarpe_attn_mma_kernel<false><<<grid, kWarps * 32, 0, st>>>(
-        q, ldq, u, ldu, static_cast<const __half*>(kv0), ldkv0, T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1,
-        div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid);
+#define TB_MMA_LAUNCH(OH, IH)                                                                                          \
+  knarpe_attn_mma_kernel<OH, IH><<<grid, kWarps * 32, 0, st>>>(                                                        \
+      q, ldq, u, ldu, static_cast<const __half*>(kv0), ldkv0, T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, \
+      div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid)
+  if (out_f16 && in_f16) TB_MMA_LAUNCH(true, true);
+  else if (out_f16) TB_MMA_LAUNCH(true, false);
+  else if (in_f16) TB_MMA_LAUNCH(false, true);
+  else TB_MMA_LAUNCH(false, false);
+#undef TB_MMA_LAUNCH
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

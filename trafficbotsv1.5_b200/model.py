@@ -48,6 +48,7 @@ def fuse_attention(P: Dict[str, Tensor], prefix: str, d: int, n_head: int = H) -
     b_qu = torch.cat([b_q] + b_u, 0)
     out = dict(
         w_in_self=torch.cat([w_qu, w_in[d:]], 0), b_in_self=torch.cat([b_qu, b_in[d:]], 0),
+        w_in_self_kvfirst=torch.cat([w_in[d:], w_qu], 0), b_in_self_kvfirst=torch.cat([b_in[d:], b_qu], 0),
         w_in_q=w_qu, b_in_q=b_qu, w_kv=w_in[d:], b_kv=b_in[d:],
         w_out=torch.cat([w_o] + w_oz, 1), b_out=b_o + w_o @ b_rv,
     )
@@ -151,12 +152,24 @@ class HotPathModel:
         neighbour lists (K < mma_min_k) stay on the fp32 SIMT kernel: the tensor-core kernel works on groups of 16
         neighbours and has a higher per-token cost (measured in profiles/r1_notes.md)."""
         nq = self.d + H * self.d
-        if self.kv_half and K >= self.mma_min_k:
-            kv = torch.empty(x.shape[0], 2 * self.d, dtype=torch.float16, device=x.device)
-            proj = ops.linear(x, f["w_in_self"], f["b_in_self"], precision=1, out_h=kv, col_h=nq)
-            return proj, kv
+        if self.kv_half and K >= self.mma_min_k:  # everything fp16: [q|u|k|v] rows of one buffer
+            row = torch.empty(x.shape[0], nq + 2 * self.d, dtype=torch.float16, device=x.device)
+            ops.linear(x, f["w_in_self"], f["b_in_self"], precision=1, out_h=row, col_h=0)
+            return row[:, :nq], row[:, nq:]
+        if self.kv_half:  # SIMT kernel on a short list: fp32 [k|v] (leading columns), fp16 [q|u]
+            qu = torch.empty(x.shape[0], nq, dtype=torch.float16, device=x.device)
+            kv = ops.linear(x, f["w_in_self_kvfirst"], f["b_in_self_kvfirst"], precision=1, out_h=qu, col_h=2 * self.d)
+            return qu, kv
         proj = ops.linear(x, f["w_in_self"], f["b_in_self"], precision=self.precision)
         return proj, proj[:, nq:]
+
+    def _in_q(self, f, x):
+        """[q|u] rows for a cross-attention: fp16 in tensor-core mode (the attention kernel's MMA operands)."""
+        if self.kv_half:
+            qu = torch.empty(x.shape[0], self.d + H * self.d, dtype=torch.float16, device=x.device)
+            ops.linear(x, f["w_in_q"], f["b_in_q"], precision=1, out_h=qu, col_h=0)
+            return qu
+        return ops.linear(x, f["w_in_q"], f["b_in_q"], precision=self.precision)
 
     def _attend(self, fa, proj, B, S, kv0, T0, div0, K0, knn, kv1=None, T1=0, div1=1, K1=0):
         d = self.d
@@ -189,7 +202,7 @@ class HotPathModel:
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src = self._out_proj(f"{p}.attn_src", f, o, nv, src)
             f = self.fa[f"{p}.attn"]
-            proj = ops.linear(self.ln(src, f"{p}.norm1"), f["w_in_q"], f["b_in_q"], precision=pr)
+            proj = self._in_q(f, self.ln(src, f"{p}.norm1"))
             o, nv = self._attend(f, proj, B, S, cross["kv0"], cross["T0"], cross["div0"], cross["K0"], cross,
                                  cross.get("kv1"), cross.get("T1", 0), cross.get("div1", 1), cross.get("K1", 0))
             src = self._out_proj(f"{p}.attn", f, o, nv, src)

@@ -73,7 +73,7 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
     M = B * S
     rpe_mma = kv0.dtype == torch.float16
     for t in (q, u):
-        assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
+        assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == q.dtype and t.dtype in (torch.float32, torch.float16)
     for t in (kv0,) + ((kv1,) if kv1 is not None else ()):
         assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == kv0.dtype and t.dtype in (torch.float32, torch.float16)
     if out is None:
@@ -92,7 +92,8 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
         L.ptr(q), q.stride(0), L.ptr(u), u.stride(0), L.ptr(kv0), kv0.stride(0), T0, div0, K0,
         L.ptr(kv1), kv1.stride(0) if kv1 is not None else 0, T1, div1, K1, L.ptr(idx), L.ptr(inv), L.ptr(rel),
         L.ptr(emb), L.ptr(freq_xy), B, S, D, H, L.ptr(out), L.ptr(z), out.stride(0), L.ptr(_u8(none_valid)),
-        int(fast_trig) | (2 if rpe_mma else 0) | (4 if out.dtype == torch.float16 else 0), L.stream()), "tb_knarpe_attn")
+        int(fast_trig) | (2 if rpe_mma else 0) | (4 if out.dtype == torch.float16 else 0) |
+        (8 if q.dtype == torch.float16 else 0), L.stream()), "tb_knarpe_attn")
     _count()
     return out, none_valid
 
