@@ -141,11 +141,26 @@ int tb_pose_emb(const float* pose, const float* frame, int frame_div, const floa
  *   hist_valid [B,A,W] u8 (1 = valid), hist_pose/hist_motion [B,A,W,3], ag_attr [B,A,6]
  * out: tok_pose [B,A,3], tok_invalid [B,A], row_invalid [B,A,W] (window order, oldest first; absent = 1),
  *      attr rows [B*A*W, 20] = [attr6 | motion3 | one-hot11 (agent_encoder.py:154)] (ld lda),
- *      pe rows: PoseEmb pe_dim=64 of the history pose in the token frame, written at pe_out (ld ldpe). */
+ *      pe rows: PoseEmb pe_dim=64 of the history pose in the token frame, written at pe_out (ld ldpe).
+ * row_invalid, attr_out and pe_out may all be NULL: only tok_pose / tok_invalid are produced (used to start the KNN
+ * selects while tb_ag_frontend encodes the history). */
 int tb_ag_featurize(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
                     const float* ag_attr, const int* d_step, const float* freq_xy, int B, int A, int W,
                     float* tok_pose, uint8_t* tok_invalid, uint8_t* row_invalid, float* attr_out, int lda,
                     float* pe_out, int ldpe, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused agent history encoder of the tensor-core mode — agent_encoder.py:130-162 in one kernel (one warp per agent):
+ * tb_ag_featurize's rows -> input MLP [9+W -> 64 -> 64 -> 64] ++ PoseEmb64 -> PointNet 3 x (128 -> 64, max over the
+ * valid steps) -> token [max h | max h]; mma.sync f16 operands / f32 accumulate, activations never leave registers.
+ *   wblob: tb_ag_frontend_blob_halves() fp16 values = the six weight matrices, row-major [64 outputs][inputs] with
+ *   row strides 40 (W1, inputs zero-padded to 32), 72 (W2, W3), 136 (P0, P1, P2), in that order; bias: fp32 [6][64].
+ *   tok_out [B*A, 128] fp32 (ld ldo): zeros for agents without a valid step; tok_pose [B,A,3], tok_invalid [B,A].
+ * W <= 16 (one MMA tile of history rows). */
+int tb_ag_frontend_blob_halves(void);
+int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion, const float* ag_attr,
+                   const int* d_step, const float* freq_xy, int B, int A, int W, const void* wblob, const float* bias,
+                   float* tok_out, int ldo, float* tok_pose, uint8_t* tok_invalid, void* stream);
 
 /* Traffic-light history rows — traffic_light.py:223-225: [state5 | one-hot11] per (b,tl,window slot).
  *   hist_tl [B,TL,W,5] u8 one-hot, tl_invalid [B,TL]; out rows [B*TL*W,16] (ld lda), row_invalid [B,TL,W]. */

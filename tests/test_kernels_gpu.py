@@ -440,3 +440,53 @@ def test_linear_fp16_operands(M, N, K, flags):
     assert float((out.cpu().double() - y).abs().max()) < 2e-5 * max(1.0, float(y.abs().max()))
     with pytest.raises(AssertionError):
         ops.linear(dv(x).float(), dv(w), dv(b), precision=2)
+
+
+@pytest.mark.parametrize("s", [15, 11, 4, 1])
+def test_ag_frontend_fused_vs_oracle(s):
+    """tb_ag_frontend (fused history encoder of the tensor-core mode: featurise + input MLP + PoseEmb64 + PointNet on
+    mma.sync, fp16 operands) vs the fp32 oracle front-end (agent_encoder.py:130-162) on random ring-buffer states,
+    full (s >= W) and partial (s < W) windows, invalid steps and fully invalid agents."""
+    from trafficbotsv1_5_b200 import lib as L, config
+    from trafficbotsv1_5_b200.model import HotPathModel
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, seed=3)
+    m = HotPathModel(P, cfg, config.derived_sizes(cfg), DEV, precision=1)
+    W, d, B, A = cfg["temp_window_size"], cfg["hidden_dim"], 3, 37
+    g = torch.Generator().manual_seed(100 + s)
+    n_step = min(s, W)
+    hv = torch.rand(B, A, n_step, generator=g) < 0.8
+    hv[0, :3] = False
+    hp = torch.cat([(torch.rand(B, A, n_step, 2, generator=g) * 2 - 1) * 120, (torch.rand(B, A, n_step, 1, generator=g) * 2 - 1) * 3], -1)
+    hm = torch.cat([torch.rand(B, A, n_step, 1, generator=g) * 20, torch.randn(B, A, n_step, 2, generator=g)], -1)
+    attr = torch.cat([torch.rand(B, A, 3, generator=g) * 5, torch.nn.functional.one_hot(torch.randint(0, 3, (B, A), generator=g), 3).float()], -1)
+    # oracle (time order, oldest first)
+    tok_pose = O.last_valid(hp, hv)
+    xy = O.to_local_xy(hp[..., :2], tok_pose[:, :, None, :2], tok_pose[..., 2])
+    yaw = hp[..., 2] - tok_pose[..., 2:3]
+    rows = torch.cat([attr[:, :, None, :].expand(-1, -1, n_step, -1), hm, torch.eye(W)[None, None, -n_step:].expand(B, A, -1, -1)], -1)
+    feat = torch.cat([O.mlp(P, "ag_encoder.input_encoder.mlp", rows, (0, 2, 4), False), O.pose_emb_xy_yaw(xy, yaw, d // 2)], -1)
+    ref = O.pointnet(P, "ag_encoder.temp_encoder", feat, ~hv)
+    # ring-buffer state: time tau = s - n_step + i lives in slot tau % W
+    ring_v = torch.zeros(B, A, W, dtype=torch.uint8)
+    ring_p, ring_m = torch.zeros(B, A, W, 3), torch.zeros(B, A, W, 3)
+    for i in range(n_step):
+        slot = (s - n_step + i) % W
+        ring_v[:, :, slot], ring_p[:, :, slot], ring_m[:, :, slot] = hv[:, :, i].to(torch.uint8), hp[:, :, i], hm[:, :, i]
+    dv = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    blob, bias = m._ag_frontend_weights()
+    tok = torch.full((B * A, d + 8), 5.0, device=DEV)
+    tp, ti = torch.empty(B, A, 3, device=DEV), torch.empty(B, A, dtype=torch.uint8, device=DEV)
+    step = torch.tensor([s], dtype=torch.int32, device=DEV)
+    rv, rp, rm, at = dv(ring_v), dv(ring_p), dv(ring_m), dv(attr)
+    L.check(L.load().tb_ag_frontend(L.ptr(rv), L.ptr(rp), L.ptr(rm), L.ptr(at), L.ptr(step), L.ptr(m.freq_ag), B, A, W,
+                                    L.ptr(blob), L.ptr(bias), L.ptr(tok), d + 8, L.ptr(tp), L.ptr(ti), L.stream()),
+            "tb_ag_frontend")
+    assert torch.equal(ti.cpu().bool(), ~hv.any(-1)) and float((tp.cpu() - tok_pose).abs().max()) == 0.0
+    out = tok[:, :d].cpu().view(B, A, d)
+    scale = float(ref.abs().max())
+    err = float((out - ref).abs().max())
+    print(f"fused agent front-end s={s}: max err {err:.3e} (scale {scale:.2f})")
+    assert err < 2e-3 * scale                       # fp16 operands, 6 layers (measured 4-6e-4)
+    assert float(out[0, :3].abs().max()) == 0.0     # agents without a valid step
+    assert float((tok[:, d:] - 5.0).abs().max()) == 0.0

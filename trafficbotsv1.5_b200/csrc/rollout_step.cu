@@ -46,6 +46,7 @@ ag_featurize_kernel(const uint8_t* __restrict__ hist_valid, const float* __restr
     tok_pose[(size_t)ba * 3] = px; tok_pose[(size_t)ba * 3 + 1] = py; tok_pose[(size_t)ba * 3 + 2] = pw;
     tok_invalid[ba] = last_wp < 0;
   }
+  if (!attr_out) return;  // token-only mode (the fused front-end builds the rows itself)
   float sn, cs;
   sincosf(pw, &sn, &cs);
   for (int wp = 0; wp < W; ++wp) {
@@ -237,10 +238,11 @@ extern "C" int tb_ag_featurize(const uint8_t* hist_valid, const float* hist_pose
                                const float* ag_attr, const int* d_step, const float* freq_xy, int B, int A, int W,
                                float* tok_pose, uint8_t* tok_invalid, uint8_t* row_invalid, float* attr_out, int lda,
                                float* pe_out, int ldpe, void* stream) {
-  if (!hist_valid || !hist_pose || !hist_motion || !ag_attr || !d_step || !freq_xy || !tok_pose || !tok_invalid ||
-      !row_invalid || !attr_out || !pe_out)
+  if (!hist_valid || !hist_pose || !hist_motion || !ag_attr || !d_step || !freq_xy || !tok_pose || !tok_invalid)
     return TB_ERR_NULL;
-  if (B <= 0 || A <= 0 || W <= 0 || W > 23 || lda < 9 + W || ldpe < 64) return TB_ERR_BAD_SHAPE;
+  const bool rows = attr_out || pe_out || row_invalid;  // all three or none (none: token pose / validity only)
+  if (rows && (!row_invalid || !attr_out || !pe_out)) return TB_ERR_NULL;
+  if (B <= 0 || A <= 0 || W <= 0 || W > 23 || (rows && (lda < 9 + W || ldpe < 64))) return TB_ERR_BAD_SHAPE;
   const int n = B * A;
   ag_featurize_kernel<<<(n + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       hist_valid, hist_pose, hist_motion, ag_attr, d_step, freq_xy, n, W, tok_pose, tok_invalid, row_invalid, attr_out,

@@ -316,13 +316,18 @@ class HotPathModel:
         M, MW = B * A, B * A * W
         tok_pose = torch.empty(B, A, 3, device=self.dev)
         tok_inv = torch.empty(B, A, dtype=torch.bool, device=self.dev)
-        row_inv = torch.empty(MW, dtype=torch.bool, device=self.dev)
-        attr = torch.empty(MW, 9 + W, device=self.dev)
-        x = torch.empty(MW, d, device=self.dev)
-        L.check(L.load().tb_ag_featurize(L.ptr(st["hist_valid"]), L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]),
-                                         L.ptr(st["ag_attr"]), L.ptr(st["d_step"]), L.ptr(self.freq_ag), B, A, W,
-                                         L.ptr(tok_pose), L.ptr(ops._u8(tok_inv)), L.ptr(ops._u8(row_inv)),
-                                         L.ptr(attr), 9 + W, L.ptr(x[:, d // 2:]), d, L.stream()), "tb_ag_featurize")
+        fused = self.kv_half and W <= 16 and d == 128  # tensor-core mode: one fused kernel for the history encoder
+        hist = (L.ptr(st["hist_valid"]), L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]), L.ptr(st["ag_attr"]),
+                L.ptr(st["d_step"]), L.ptr(self.freq_ag), B, A, W)
+        if fused:  # token pose / validity first (tiny), so that the KNN selects start beside the fused encoder
+            L.check(L.load().tb_ag_featurize(*hist, L.ptr(tok_pose), L.ptr(ops._u8(tok_inv)), None, None, 0, None, 0,
+                                             L.stream()), "tb_ag_featurize")
+        else:
+            row_inv = torch.empty(MW, dtype=torch.bool, device=self.dev)
+            attr = torch.empty(MW, 9 + W, device=self.dev)
+            x = torch.empty(MW, d, device=self.dev)
+            L.check(L.load().tb_ag_featurize(*hist, L.ptr(tok_pose), L.ptr(ops._u8(tok_inv)), L.ptr(ops._u8(row_inv)),
+                                             L.ptr(attr), 9 + W, L.ptr(x[:, d // 2:]), d, L.stream()), "tb_ag_featurize")
         ops._count()
         # re-localisation + KNN re-selection, every step (:321-387). The three selects only need the token poses, so
         # they run on a forked stream beside the (bandwidth-bound) input MLP + PointNet projections.
@@ -346,8 +351,16 @@ class HotPathModel:
             knn_stream.wait_stream(main)
             with torch.cuda.stream(knn_stream):
                 selects()
-        self.mlp(attr, "ag_encoder.input_encoder.mlp", (0, 2, 4), False, out=x[:, : d // 2])          # :159
-        tok = self.pointnet(x, row_inv, M, W, "ag_encoder.temp_encoder")                              # :162
+        if fused:
+            blob, bias = self._ag_frontend_weights()
+            tok = torch.empty(M, d, device=self.dev)
+            tp2, ti2 = torch.empty_like(tok_pose), torch.empty_like(tok_inv)  # same values as tok_pose / tok_inv
+            L.check(L.load().tb_ag_frontend(*hist, L.ptr(blob), L.ptr(bias), L.ptr(tok), d, L.ptr(tp2),
+                                            L.ptr(ops._u8(ti2)), L.stream()), "tb_ag_frontend")          # :130-162
+            ops._count()
+        else:
+            self.mlp(attr, "ag_encoder.input_encoder.mlp", (0, 2, 4), False, out=x[:, : d // 2])      # :159
+            tok = self.pointnet(x, row_inv, M, W, "ag_encoder.temp_encoder")                          # :162
         if knn_stream is not None:
             main.wait_stream(knn_stream)
         else:
@@ -417,6 +430,25 @@ class HotPathModel:
                | (ag_type[:, :, [2]] & mp_type[:, :, :3].any(-1).unsqueeze(1)))
         logits = logits.masked_fill(inv, float("-inf"))
         return logits.masked_fill((~tok_valid).unsqueeze(-1) | inv.all(-1, keepdim=True), 0.0)
+
+    def _ag_frontend_weights(self):
+        """fp16 weight blob + fp32 biases of tb_ag_frontend (layout: include/tb_knarpe.h), built once."""
+        if not hasattr(self, "_ag_front"):
+            from . import lib as L
+            n = L.load().tb_ag_frontend_blob_halves()
+            blob = torch.zeros(n, dtype=torch.float16, device=self.dev)
+            names = [f"ag_encoder.input_encoder.mlp.fc_layers.{i}" for i in (0, 2, 4)] + \
+                    [f"ag_encoder.temp_encoder.mlp_layers.{i}.fc_layers.0" for i in range(3)]
+            off = 0
+            for nm, stride in zip(names, (40, 72, 72, 136, 136, 136)):
+                w = self.P[f"{nm}.weight"]
+                assert w.shape[0] == 64 and w.shape[1] <= stride - 8, w.shape
+                blob[off:off + 64 * stride].view(64, stride)[:, : w.shape[1]] = w.to(torch.float16)
+                off += 64 * stride
+            assert off == n
+            bias = torch.cat([self.P[f"{nm}.bias"] for nm in names]).contiguous()
+            self._ag_front = (blob, bias)
+        return self._ag_front
 
     # ------------------------------------------------------------------------------------------ heads (per step)
     def navi_static(self, mp: Dict[str, Tensor], dest_idx: Tensor, R: int) -> dict:
