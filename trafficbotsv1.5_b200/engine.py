@@ -105,7 +105,8 @@ class RolloutEngine:
         self._graph = None
         self._shape = None
         self._side = torch.cuda.Stream(device=self.dev)  # traffic-light branch runs beside the agent front-end
-        self._side2 = torch.cuda.Stream(device=self.dev)  # KNN selects run beside the input MLP / PointNet GEMMs
+        self._side2 = torch.cuda.Stream(device=self.dev)  # KNN selects run beside the history encoder and layer 0
+        self._side3 = torch.cuda.Stream(device=self.dev)
         # constants rounded the way the reference's fp32 tensor ops round them (traffic_rule_checker.py:94-96,103,308)
         one = torch.ones(1)
         self.thresh_lane = float(one * 50 * (1 - torch.zeros(1) * 0.8))
@@ -244,7 +245,8 @@ class RolloutEngine:
             m.tl_forward(st["hist_tl"], st["d_step"], static["tl"], out_feat=st["tl_feat"], out_logits=st["tl_logits"])
         tl_feat, logits = st["tl_feat"], st["tl_logits"]
         m.ag_forward(st, static["mp"], static["kv_mp"], static["tl"], tl_feat, self.R, out=st["x_cat"][:, :d],
-                     aux=aux, before_tl=lambda: main.wait_stream(self._side), knn_stream=self._side2)
+                     aux=aux, before_tl=lambda: main.wait_stream(self._side), knn_stream=self._side2,
+                     knn_stream2=self._side3)
         act = m.heads(st["x_cat"], st, navi)
         if aux is not None:
             aux.update(tl_feat=tl_feat, logits=logits, act=act, ag_feat=st["x_cat"][:, :d].clone())

@@ -193,16 +193,21 @@ class HotPathModel:
         return ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=res, precision=self.precision)
 
     def tf_layer(self, p: str, mode: str, src: Tensor, src_inv: Tensor, B: int, S: int, knn_self: dict,
-                 cross: Optional[dict] = None, out: Optional[Tensor] = None) -> Tensor:
-        """TransformerRPE.forward (transformer_rpe.py:175-245), eval mode."""
+                 cross: Optional[dict] = None, out: Optional[Tensor] = None, before_self=None, before_cross=None) -> Tensor:
+        """TransformerRPE.forward (transformer_rpe.py:175-245), eval mode. `before_self` / `before_cross` are join
+        hooks called right before the self / cross attention launch (streams that produce the neighbour lists)."""
         d, pr = self.d, self.precision
         if mode == "dec_cross_attn":
             f = self.fa[f"{p}.attn_src"]
             proj, kv = self._in_self(f, self.ln(src, f"{p}.norm_src"), knn_self["idx"].shape[-1])
+            if before_self is not None:
+                before_self()
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src = self._out_proj(f"{p}.attn_src", f, o, nv, src)
             f = self.fa[f"{p}.attn"]
             proj = self._in_q(f, self.ln(src, f"{p}.norm1"))
+            if before_cross is not None:
+                before_cross()
             o, nv = self._attend(f, proj, B, S, cross["kv0"], cross["T0"], cross["div0"], cross["K0"], cross,
                                  cross.get("kv1"), cross.get("T1", 0), cross.get("div1", 1), cross.get("K1", 0))
             src = self._out_proj(f"{p}.attn", f, o, nv, src)
@@ -305,7 +310,8 @@ class HotPathModel:
                 for i in range(self.cfg["ag_encoder"]["n_layer_tf"])]
 
     def ag_forward(self, st: dict, mp: Dict[str, Tensor], kv_mp: list, tl: dict, tl_feat: Tensor, R: int,
-                   out: Optional[Tensor] = None, aux: Optional[dict] = None, before_tl=None, knn_stream=None) -> Tensor:
+                   out: Optional[Tensor] = None, aux: Optional[dict] = None, before_tl=None, knn_stream=None,
+                   knn_stream2=None) -> Tensor:
         """AgentEncoder._forward_hptr (agent_encoder.py:114-178). `st` holds the rollout state rings
         (engine.RolloutState); batch b uses map / traffic-light tables of scene b // R."""
         from . import lib as L
@@ -339,18 +345,29 @@ class HotPathModel:
         cinv = torch.empty(B, A, Kc, dtype=torch.bool, device=self.dev)
         crel = torch.empty(B, A, Kc, 3, device=self.dev)
 
-        def selects():
+        def select_self():
+            ops.knn_select(tok_pose, tok_inv, tok_pose, tok_inv, Ka, sz["dl_ag"], out=(i_aa, m_aa, r_aa))
+
+        def select_cross():
             ops.knn_select(tok_pose, tok_inv, mp["mp_token_pose"], mp["mp_token_invalid"], sz["k_ag2mp"], sz["dl_ag"],
                            tgt_div=R, out=(cidx, cinv, crel), koff=0)
-            ops.knn_select(tok_pose, tok_inv, tok_pose, tok_inv, Ka, sz["dl_ag"], out=(i_aa, m_aa, r_aa))
             ops.knn_select(tok_pose, tok_inv, tl["tl_token_pose"], tl["tl_token_invalid"], sz["k_ag2tl"], sz["dl_ag"],
                            tgt_div=tl_div, out=(cidx, cinv, crel), koff=sz["k_ag2mp"])
 
+        # The agent->agent list is needed by the first self-attention, the agent->map/TL lists only by the first
+        # cross-attention: with two side streams the big map select also overlaps layer 0's projections + self-attn.
         main = torch.cuda.current_stream()
+        join_self = join_cross = None
         if knn_stream is not None:
+            s2 = knn_stream2 if knn_stream2 is not None else knn_stream
+            s2.wait_stream(main)
+            with torch.cuda.stream(s2):
+                select_self()
             knn_stream.wait_stream(main)
             with torch.cuda.stream(knn_stream):
-                selects()
+                select_cross()
+            join_self = lambda: main.wait_stream(s2)          # noqa: E731
+            join_cross = lambda: main.wait_stream(knn_stream)  # noqa: E731
         if fused:
             blob, bias = self._ag_frontend_weights()
             tok = torch.empty(M, d, device=self.dev)
@@ -361,10 +378,9 @@ class HotPathModel:
         else:
             self.mlp(attr, "ag_encoder.input_encoder.mlp", (0, 2, 4), False, out=x[:, : d // 2])      # :159
             tok = self.pointnet(x, row_inv, M, W, "ag_encoder.temp_encoder")                          # :162
-        if knn_stream is not None:
-            main.wait_stream(knn_stream)
-        else:
-            selects()
+        if knn_stream is None:
+            select_self()
+            select_cross()
         knn_self = dict(idx=i_aa, inv=m_aa, rel=r_aa)
         flat_inv = tok_inv.reshape(-1)
         nl = self.cfg["ag_encoder"]["n_layer_tf"]
@@ -378,7 +394,8 @@ class HotPathModel:
             cross = dict(kv0=kv_mp[i], T0=n_mp, div0=R, K0=sz["k_ag2mp"], kv1=kv_tl, T1=n_tl, div1=tl_div,
                          K1=sz["k_ag2tl"], idx=cidx, inv=cinv, rel=crel)
             tok = self.tf_layer(p, "dec_cross_attn", tok, flat_inv, B, A, knn_self, cross,
-                                out=out if i == nl - 1 else None)
+                                out=out if i == nl - 1 else None, before_self=join_self if i == 0 else None,
+                                before_cross=join_cross if i == 0 else None)
         return tok
 
     # ------------------------------------------------------------------------------------------ destinations (once / scene)
