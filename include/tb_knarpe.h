@@ -106,10 +106,11 @@ int tb_linear(const void* X, int ldx, const void* W, const float* bias, int bias
               int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
               int precision, void* Yh, int ldyh, int col_h, void* stream);
 
-/* LayerNorm over the last dim (eps 1e-5, affine) — transformer_rpe.py:156-171; relu != 0 applies ReLU to the result
- * (the Linear -> LayerNorm -> ReLU layers of modules/mlp.py:47-51 with use_layernorm). D in {128,256}. */
-int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy, int M, int D,
-                 int relu, void* stream);
+/* LayerNorm over the last dim (eps 1e-5, affine) — transformer_rpe.py:156-171. flags bit 0: ReLU on the result (the
+ * Linear -> LayerNorm -> ReLU layers of modules/mlp.py:47-51 with use_layernorm); bit 1: Y rows are IEEE fp16 (ldy in
+ * halves, multiple of 8) — the operand a tb_linear precision-2 projection reads. D in {128,256}. */
+int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, void* Y, int ldy, int M, int D,
+                 int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * PointNet pooling step over groups of L consecutive rows — modules/polyline_encoder.py:50-53 and

@@ -32,6 +32,7 @@ def test_error_codes_without_gpu(handle):
     assert handle.tb_knn_select(one, one, one, one, 1, 1, 4, 1, 4, 1.0, one, one, one, 4, 0, None) == -2  # K == T
     assert handle.tb_knn_select(one, one, one, one, 1, 1, 4096, 1, 4, 1.0, one, one, one, 4, 0, None) == -3
     assert handle.tb_layernorm(one, 128, one, one, one, 128, 4, 96, 0, None) == -3
+    assert handle.tb_layernorm(one, 128, one, one, one, 132, 4, 128, 2, None) == -4  # fp16 rows: ldy % 8
     assert handle.tb_linear(one, 4, one, None, 0, one, 4, 0, 4, 4, 0, None, None, 0, None, 0, None, 0, 0, None) == -1
     assert handle.tb_linear(one, 4, one, None, 0, one, 32, 8, 64, 4, 0, None, None, 0, None, 0, one, 64, 32, None) == -3  # fp16 out needs precision 1
     assert handle.tb_linear(one, 4, one, None, 0, one, 4, 8, 64, 4, 0, None, None, 0, None, 1, one, 64, 16, None) == -1  # col_h % 32

@@ -142,6 +142,8 @@ def test_layernorm(D):
     y = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-5)
     close(ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV)), y, 1e-5, 1e-5, "layernorm")
     close(ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), relu=True), y.relu(), 1e-5, 1e-5, "layernorm + relu")
+    yh = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), out_dtype=torch.float16)
+    assert yh.dtype == torch.float16 and torch.equal(yh.cpu(), ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV)).cpu().half())
 
 
 @pytest.mark.parametrize("pe", [64, 128, 256])

@@ -1,13 +1,15 @@
 // Row-wise helpers around the projections: LayerNorm, PointNet pooling, pose embedding, row gather.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
 
 // ---- LayerNorm (transformer_rpe.py:156-171): one warp per row, D/32 floats per lane, two-pass in registers.
-template <int D>
+template <int D, bool OUT_H>  // OUT_H: fp16 rows (operands of a tb_linear precision-2 projection)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float* __restrict__ Y, int ldy, int M, int relu) {
+                 const float* __restrict__ beta, void* __restrict__ Y_, int ldy, int M, int relu) {
   constexpr int NV = D / 32;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -30,7 +32,8 @@ layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
 #pragma unroll
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(TB_FULL_MASK, q, o);
   const float rstd = 1.f / sqrtf(q * (1.f / D) + 1e-5f);
-  float* yp = Y + (size_t)row * ldy + lane * NV;
+  float* yp = static_cast<float*>(Y_) + (size_t)row * ldy + lane * NV;
+  __half* yh = static_cast<__half*>(Y_) + (size_t)row * ldy + lane * NV;
 #pragma unroll
   for (int i = 0; i < NV; i += 4) {
     const float4 g = ldg4(gamma + lane * NV + i), bb = ldg4(beta + lane * NV + i);
@@ -40,7 +43,13 @@ layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
     o.z = (v[i + 2] - mean) * rstd * g.z + bb.z;
     o.w = (v[i + 3] - mean) * rstd * g.w + bb.w;
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    *reinterpret_cast<float4*>(yp + i) = o;
+    if (OUT_H) {
+      const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+      *reinterpret_cast<uint2*>(yh + i) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    } else {
+      *reinterpret_cast<float4*>(yp + i) = o;
+    }
   }
 }
 
@@ -139,8 +148,9 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, int ldt, int
 
 }  // namespace
 
-extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, float* Y, int ldy, int M,
-                            int D, int relu, void* stream) {
+extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, void* Y, int ldy, int M,
+                            int D, int flags, void* stream) {
+  const int relu = flags & 1, out_h = (flags & 2) != 0;
   if (!X || !gamma || !beta || !Y) return TB_ERR_NULL;
   if (M <= 0 || ldx < D || ldy < D) return TB_ERR_BAD_SHAPE;
   if (D != 128 && D != 256) return TB_ERR_UNSUPPORTED;
@@ -148,8 +158,11 @@ extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const f
     return TB_ERR_MISALIGNED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = (M + 7) / 8;
-  if (D == 128) layernorm_kernel<128><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
-  else layernorm_kernel<256><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
+  if (out_h && (ldy & 7)) return TB_ERR_MISALIGNED;
+  if (D == 128 && out_h) layernorm_kernel<128, true><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
+  else if (D == 128) layernorm_kernel<128, false><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
+  else if (out_h) layernorm_kernel<256, true><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
+  else layernorm_kernel<256, false><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

@@ -103,8 +103,16 @@ class HotPathModel:
         return ops.linear(x, self.P[f"{wname}.weight"], self.P[f"{wname}.bias"], relu=relu, precision=self.precision,
                           **kw)
 
-    def ln(self, x, name):
-        return ops.layernorm(x, self.P[f"{name}.weight"], self.P[f"{name}.bias"])
+    def ln(self, x, name, half: bool = False):
+        """LayerNorm; `half`: fp16 rows for a following kind::f16 projection (tensor-core mode)."""
+        return ops.layernorm(x, self.P[f"{name}.weight"], self.P[f"{name}.bias"],
+                             out_dtype=torch.float16 if half else torch.float32)
+
+    def _proj(self, x: Tensor, key: str, w: Tensor, b: Tensor, **kw):
+        """Projection of LayerNorm output: fp16 rows x fp16 weights (tb_linear precision 2) or the fp32 / tf32 path."""
+        if x.dtype == torch.float16:
+            return ops.linear(x, self._half(key, w), b, precision=2, **kw)
+        return ops.linear(x, w, b, precision=self.precision, **kw)
 
     def mlp(self, x, prefix, idxs, end_act, **last_kw):
         for n, i in enumerate(idxs):
@@ -140,34 +148,35 @@ class HotPathModel:
     def kv_table(self, feat: Tensor, layer_prefix: str, norm: str, attn: str = "attn") -> Tensor:
         """K/V rows of a target table for one layer: W_kv LN(x) + b  (project-once-then-gather)."""
         f = self.fa[f"{layer_prefix}.{attn}"]
-        x = self.ln(feat, f"{layer_prefix}.{norm}")
+        x = self.ln(feat, f"{layer_prefix}.{norm}", half=self.kv_half)
         if self.kv_half:  # tensor-core mode: fp16 tables straight from the projection's epilogue
             tbl = torch.empty(x.shape[0], 2 * self.d, dtype=torch.float16, device=x.device)
-            ops.linear(x, f["w_kv"], f["b_kv"], precision=1, out_h=tbl, col_h=0)
+            self._proj(x, f"{layer_prefix}.{attn}.w_kv", f["w_kv"], f["b_kv"], out_h=tbl, col_h=0)
             return tbl
         return ops.linear(x, f["w_kv"], f["b_kv"], precision=self.precision)
 
-    def _in_self(self, f, x, K):
+    def _in_self(self, f, x, K, key=""):
         """[q|u] (fp32) and the token's own [k|v] rows from one projection; k|v are fp16 in tensor-core mode. Short
         neighbour lists (K < mma_min_k) stay on the fp32 SIMT kernel: the tensor-core kernel works on groups of 16
         neighbours and has a higher per-token cost (measured in profiles/r1_notes.md)."""
         nq = self.d + H * self.d
         if self.kv_half and K >= self.mma_min_k:  # everything fp16: [q|u|k|v] rows of one buffer
             row = torch.empty(x.shape[0], nq + 2 * self.d, dtype=torch.float16, device=x.device)
-            ops.linear(x, f["w_in_self"], f["b_in_self"], precision=1, out_h=row, col_h=0)
+            self._proj(x, f"{key}.w_in_self", f["w_in_self"], f["b_in_self"], out_h=row, col_h=0)
             return row[:, :nq], row[:, nq:]
         if self.kv_half:  # SIMT kernel on a short list: fp32 [k|v] (leading columns), fp16 [q|u]
             qu = torch.empty(x.shape[0], nq, dtype=torch.float16, device=x.device)
-            kv = ops.linear(x, f["w_in_self_kvfirst"], f["b_in_self_kvfirst"], precision=1, out_h=qu, col_h=2 * self.d)
+            kv = self._proj(x, f"{key}.w_in_self_kvfirst", f["w_in_self_kvfirst"], f["b_in_self_kvfirst"], out_h=qu,
+                            col_h=2 * self.d)
             return qu, kv
         proj = ops.linear(x, f["w_in_self"], f["b_in_self"], precision=self.precision)
         return proj, proj[:, nq:]
 
-    def _in_q(self, f, x):
+    def _in_q(self, f, x, key=""):
         """[q|u] rows for a cross-attention: fp16 in tensor-core mode (the attention kernel's MMA operands)."""
         if self.kv_half:
             qu = torch.empty(x.shape[0], self.d + H * self.d, dtype=torch.float16, device=x.device)
-            ops.linear(x, f["w_in_q"], f["b_in_q"], precision=1, out_h=qu, col_h=0)
+            self._proj(x, f"{key}.w_in_q", f["w_in_q"], f["b_in_q"], out_h=qu, col_h=0)
             return qu
         return ops.linear(x, f["w_in_q"], f["b_in_q"], precision=self.precision)
 
@@ -199,13 +208,14 @@ class HotPathModel:
         d, pr = self.d, self.precision
         if mode == "dec_cross_attn":
             f = self.fa[f"{p}.attn_src"]
-            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm_src"), knn_self["idx"].shape[-1])
+            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm_src", half=self.kv_half), knn_self["idx"].shape[-1],
+                                     f"{p}.attn_src")
             if before_self is not None:
                 before_self()
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src = self._out_proj(f"{p}.attn_src", f, o, nv, src)
             f = self.fa[f"{p}.attn"]
-            proj = self._in_q(f, self.ln(src, f"{p}.norm1"))
+            proj = self._in_q(f, self.ln(src, f"{p}.norm1", half=self.kv_half), f"{p}.attn")
             if before_cross is not None:
                 before_cross()
             o, nv = self._attend(f, proj, B, S, cross["kv0"], cross["T0"], cross["div0"], cross["K0"], cross,
@@ -213,13 +223,14 @@ class HotPathModel:
             src = self._out_proj(f"{p}.attn", f, o, nv, src)
         else:  # enc_self_attn: q and k/v both from norm1(src) (:218-221)
             f = self.fa[f"{p}.attn"]
-            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm1"), knn_self["idx"].shape[-1])
+            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm1", half=self.kv_half), knn_self["idx"].shape[-1],
+                                     f"{p}.attn")
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src = self._out_proj(f"{p}.attn", f, o, nv, src)
-        x2 = self.ln(src, f"{p}.norm2")
+        x2 = self.ln(src, f"{p}.norm2", half=self.kv_half)
         if self.kv_half:  # FFN hidden (ReLU output) as fp16: written by the first projection, read by a kind::f16 one
             h = torch.empty(x2.shape[0], self.P[f"{p}.linear1.weight"].shape[0], dtype=torch.float16, device=x2.device)
-            ops.linear(x2, self.P[f"{p}.linear1.weight"], self.P[f"{p}.linear1.bias"], relu=True, precision=1, out_h=h,
+            self._proj(x2, f"{p}.linear1", self.P[f"{p}.linear1.weight"], self.P[f"{p}.linear1.bias"], relu=True, out_h=h,
                        col_h=0)
             return ops.linear(h, self._half(f"{p}.linear2", self.P[f"{p}.linear2.weight"]), self.P[f"{p}.linear2.bias"],
                               res=src, mask_post=src_inv, out=out, precision=2)

@@ -129,13 +129,15 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False,
     return out
 
 
-def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, out: Optional[Tensor] = None, relu: bool = False) -> Tensor:
-    assert x.dim() == 2 and x.stride(1) == 1
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, out: Optional[Tensor] = None, relu: bool = False,
+              out_dtype: torch.dtype = torch.float32) -> Tensor:
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
     M, D = x.shape
     if out is None:
-        out = torch.empty(M, D, dtype=torch.float32, device=x.device)
+        out = torch.empty(M, D, dtype=out_dtype, device=x.device)
+    assert out.dtype in (torch.float32, torch.float16) and out.stride(1) == 1
     L.check(L.load().tb_layernorm(L.ptr(x), x.stride(0), L.ptr(gamma), L.ptr(beta), L.ptr(out), out.stride(0), M, D,
-                                  int(relu), L.stream()), "tb_layernorm")
+                                  int(relu) | (2 if out.dtype == torch.float16 else 0), L.stream()), "tb_layernorm")
     _count()
     return out
 
