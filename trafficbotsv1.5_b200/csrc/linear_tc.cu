@@ -94,6 +94,47 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool f16) {
          ((uint32_t)(m >> 4) << 24);
 }
 
+// Store phase of the epilogue for one 32x32 block: lane -> (row 4i + rsub, 16-byte chunk cc), 8 rows per lane.
+// Everything that does not change inside the loop is a template parameter or hoisted (ncu of the generic version:
+// 774 warp instructions per block, the projections with K = 128 were bound by the epilogue's instruction issue).
+template <bool RELU, bool TO_H, bool EXTRA>
+__device__ __forceinline__ void store_block(uint32_t st_s, int rsub, int cc, int rbase, int col, int M, float4 bv,
+                                            float* __restrict__ Y, int ldy, const Epi& ep) {
+  const bool all_rows = rbase + 32 <= M;
+  const int row0 = rbase + rsub;
+  float* yp = Y + (size_t)row0 * ldy + col;
+  __half* hp = TO_H ? ep.yh + (size_t)row0 * ep.ldyh + (col - ep.colh) : nullptr;
+  const float* rp = (EXTRA && ep.res) ? ep.res + (size_t)row0 * ep.ldr + col : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + rsub;
+    if (all_rows || rbase + rr < M) {
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "r"(st_s + (uint32_t)(rr * 32 + ((cc ^ (rr & 7)) << 2)) * 4));
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (EXTRA) {
+        const int row = rbase + rr;
+        if (ep.mask_pre && ep.mask_pre[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rp) {
+          const float4 rv = *reinterpret_cast<const float4*>(rp + (size_t)i * 4 * ep.ldr);
+          v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+        }
+        if (ep.mask_post && ep.mask_post[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (TO_H) {
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(hp + (size_t)i * 4 * ep.ldyh) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      } else {
+        *reinterpret_cast<float4*>(yp + (size_t)i * 4 * ldy) = v;
+      }
+    }
+  }
+}
+
 // F16: operands are fp16 in memory (kind::f16, 64 elements per k-block) instead of fp32 read as tf32 (32 per k-block)
 template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -176,6 +217,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // column slice (w>>2) of the tile =====
     const int quarter = warp & 3, half = warp >> 2;
     float* st = sE + warp * (32 * 32);  // this warp's 32x32 staging block, 16-byte chunks XOR-swizzled by row
+    const uint32_t st_s = smem_u32(st);
+    const bool extra = ep.mask_pre || ep.res || ep.mask_post;  // row masks / residual: the slower store variant
     const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
                         (!ep.yh || (((ep.ldyh & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.yh) & 7) == 0))) &&
                         (!ep.res || (((ep.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.res) & 15) == 0))) &&
@@ -226,36 +269,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // registers (row = lane) -> swizzled staging block
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(st + lane * 32 + ((c ^ (lane & 7)) << 2)) =
-              make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(st_s + (uint32_t)(lane * 32 + ((c ^ (lane & 7)) << 2)) * 4),
+                       "r"(r[4 * c]), "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3]) : "memory");
         __syncwarp();
         const bool to_h = ep.yh != nullptr && cbase >= ep.colh;  // warp-uniform: colh is a multiple of 32
         if (vec_ok && cbase + 32 <= N) {
           const int col = cbase + cc * 4;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ep.bias && !ep.bgroup) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + rsub, row = rbase + rr;
-            if (row < M) {
-              float4 v = *reinterpret_cast<const float4*>(st + rr * 32 + ((cc ^ (rr & 7)) << 2));
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-              if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-              if (ep.mask_pre && ep.mask_pre[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ep.res) {
-                const float4 rv = *reinterpret_cast<const float4*>(ep.res + (size_t)row * ep.ldr + col);
-                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-              }
-              if (ep.mask_post && ep.mask_post[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (to_h) {
-                const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-                *reinterpret_cast<uint2*>(ep.yh + (size_t)row * ep.ldyh + (col - ep.colh)) =
-                    make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-              } else {
-                *reinterpret_cast<float4*>(Y + (size_t)row * ldy + col) = v;
-              }
-            }
+#define TB_STORE(R, H, X) store_block<R, H, X>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep)
+          if (extra) {
+            if (ep.relu) { if (to_h) TB_STORE(true, true, true); else TB_STORE(true, false, true); }
+            else { if (to_h) TB_STORE(false, true, true); else TB_STORE(false, false, true); }
+          } else {
+            if (ep.relu) { if (to_h) TB_STORE(true, true, false); else TB_STORE(true, false, false); }
+            else { if (to_h) TB_STORE(false, true, false); else TB_STORE(false, false, false); }
           }
+#undef TB_STORE
         } else {  // N tail / unaligned views: scalar, bounds-checked
 #pragma unroll 1
           for (int i = 0; i < 32; ++i) {
