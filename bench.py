@@ -147,11 +147,11 @@ def attention_roofline(eng, peaks):
     p = "ag_encoder.tf_ag2agmptl.layers.0"
     f = m.fa[f"{p}.attn"]
     x = aux["ag_feat"]
-    proj = ops.linear(m.ln(x, f"{p}.norm1"), f["w_in_q"], f["b_in_q"])
+    proj = m._in_q(f, m.ln(x, f"{p}.norm1", half=m.kv_half), f"{p}.attn")  # [q|u] rows as the step produces them
     kv_tl = m.kv_table(aux["tl_feat"], p, "norm_tgt")
     sz = eng.sz
     n_mp, n_tl = static["mp"]["mp_token_pose"].shape[1], static["tl"]["n_tl"]
-    out = torch.empty(M, 5 * d, device=x.device)
+    out = torch.empty(M, 5 * d, device=x.device, dtype=torch.float16 if m.kv_half else torch.float32)
 
     def launch():
         ops.knarpe_attn(proj[:, :d], proj[:, d:], static["kv_mp"][0], n_mp, eng.R, sz["k_ag2mp"], aux["cidx"],
@@ -172,7 +172,8 @@ def attention_roofline(eng, peaks):
     n_valid = int((~aux["cinv"]).sum())
     # algorithmic bytes: K,V rows of the unmasked neighbours as issued + q,u in + ov,z out + idx/mask/rel
     kv_sz = static["kv_mp"][0].element_size()  # 2 in the tensor-core mode (fp16 K|V tables), 4 in the fp32 mode
-    bytes_alg = n_valid * 2 * d * kv_sz + M * (d + 4 * d) * 4 * 2 + M * K * (4 + 1 + 12)
+    io_sz = proj.element_size() + out.element_size()  # q,u rows in + ov,z rows out (fp16 in the tensor-core mode)
+    bytes_alg = n_valid * 2 * d * kv_sz + M * (d + 4 * d) * io_sz + M * K * (4 + 1 + 12)
     peak = peaks.get("hbm_gbs", 6650.0)
     ach = bytes_alg / t / 1e9
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
@@ -181,7 +182,7 @@ def attention_roofline(eng, peaks):
     except Exception:
         pass
     kname = "knarpe_attn_mma_kernel" if kv_sz == 2 else "knarpe_attn_kernel<128,false>"
-    return dict(bound="hbm", kernel=f"{kname} (agent cross-attn, K=89, {8 * kv_sz}-bit K|V rows)", achieved=ach, peak=peak,
+    return dict(bound="hbm", kernel=f"{kname} (agent cross-attn, K=89, {8 * kv_sz}-bit K|V / q|u / ov|z rows)", achieved=ach, peak=peak,
                 unit="GB/s", frac=ach / peak, traffic=traffic, us_per_launch=t * 1e6,
                 note="as-issued gather bytes are served by L2 (~85 % hit): DRAM traffic is a fraction of them; the "
                      "kernel's real ceiling is instruction issue / latency, not HBM (DESIGN.md 5)", algorithmic_bytes=bytes_alg,
