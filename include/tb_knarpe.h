@@ -89,6 +89,20 @@ int tb_knarpe_attn(const void* q, int ldq, const void* u, int ldu,
                    void* out_ov, void* out_z, int ldo, uint8_t* out_none_valid, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Backward of the KNARPE attention core (first piece; autograd through
+ * modules/attention_rpe.py:137-190 in the re-associated form above). Inputs as tb_knarpe_attn (fp32 tables, rel pose
+ * form, D == 128, H == 4, K0 + K1 <= 128) plus the upstream gradients d_ov [B*S, D] / d_z [B*S, H*D] (ld ldo).
+ * Outputs: d_qu rows [d_q (D) | d_u (H*D)] (ld ldg); d_kv0 / d_kv1: gradient tables with the layout and leading
+ * dimension of kv0 / kv1, ACCUMULATED with vector atomics (the caller zero-fills them). No gradient flows into the
+ * relative pose. All-masked rows contribute zeros.
+ * ------------------------------------------------------------------------------------------------- */
+int tb_knarpe_attn_bwd(const float* q, int ldq, const float* u, int ldu, const float* kv0, int ldkv0, int T0, int div0,
+                       int K0, const float* kv1, int ldkv1, int T1, int div1, int K1, const int32_t* idx,
+                       const uint8_t* invalid, const float* rel, const float* pe_freq_xy, int B, int S, int D, int H,
+                       const float* d_ov, const float* d_z, int ldo, float* d_qu, int ldg, float* d_kv0, float* d_kv1,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Dense projection  Y = epilogue(X W^T + bias)  — replaces F.linear / nn.Linear call sites
  * (attention_rpe.py:96-97,147,186; transformer_rpe.py:237-238; modules/mlp.py:69).
  *   X [M,K] ld ldx;  W [N,K] (nn.Linear layout) ld K;  Y [M,N] ld ldy

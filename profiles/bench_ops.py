@@ -41,3 +41,22 @@ for M, N, K, name in shapes:
         t = time_op(lambda: ops.linear(x, w, b, out=y, precision=prec))
         print(f"{name:20s} M={M:7d} N={N:4d} K={K:4d} prec={prec}: {t:8.1f} us  {gb / t * 1e6 / 1e3:6.2f} TB/s  "
               f"{2 * M * N * K / t / 1e6:7.1f} TFLOP/s")
+
+# ---- KNARPE core forward / backward at the agent cross-attention shape (fp32 tables; SURVEY 8(f) rank 2 first piece)
+B, S, T0, K0, d = 512, 128, 1024, 89, 128
+g = torch.Generator(device=dev).manual_seed(0)
+M = B * S
+q = torch.randn(M, d, device=dev, generator=g) * 0.3
+u = torch.randn(M, 4 * d, device=dev, generator=g) * 0.1
+kv = torch.randn(16 * T0, 2 * d, device=dev, generator=g)
+idx = torch.randint(0, T0, (B, S, K0), device=dev, generator=g, dtype=torch.int32)
+inv = torch.rand(B, S, K0, device=dev, generator=g) < 0.1
+rel = torch.cat([(torch.rand(B, S, K0, 2, device=dev, generator=g) * 2 - 1) * 100,
+                 (torch.rand(B, S, K0, 1, device=dev, generator=g) * 2 - 1) * 3], -1).contiguous()
+freq = ops.pe_freq_xy(d, 1e3, dev)
+d_out = torch.randn(M, 5 * d, device=dev, generator=g)
+args = (q, u, kv, T0, 32, K0, idx, inv, rel, freq, B, S, d)
+t_f = time_op(lambda: ops.knarpe_attn(*args), 5)
+t_b = time_op(lambda: ops.knarpe_attn_bwd(*args, d_out), 5)
+print(f"KNARPE core fp32, {M} tokens x {K0} neighbours: forward {t_f:.0f} us, backward {t_b:.0f} us "
+      f"(incl. zero-fill of the gradient table)")

@@ -13,14 +13,14 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("TB_LIB", os.path.join(_PKG, "libtbknarpe.so"))
-_SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "knarpe_attn_mma.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu", "post_process.cu", "ag_frontend.cu",
+_SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "knarpe_attn_mma.cu", "knarpe_attn_bwd.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu", "post_process.cu", "ag_frontend.cu",
             "rollout_step.cu", "rule_check.cu"]
 _lib = None
 
 EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_linear", "tb_layernorm",
            "tb_pointnet_pool", "tb_pose_emb", "tb_ag_featurize", "tb_tl_featurize", "tb_dyn_step", "tb_tl_step",
            "tb_step_advance", "tb_gather_rows", "tb_action_mean", "tb_rule_check", "tb_future_filter",
-           "tb_traj_global", "tb_ag_frontend", "tb_ag_frontend_blob_halves"]
+           "tb_traj_global", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -72,6 +72,7 @@ def load() -> ctypes.CDLL:
         "tb_traj_global": [P, P, P, P, I, I, I, I, I, I, P, P, P],
         "tb_ag_frontend": [P, P, P, P, P, P, I, I, I, P, P, P, I, P, P, P],
         "tb_ag_frontend_blob_halves": [],
+        "tb_knarpe_attn_bwd": [P, I, P, I, P, I, I, I, I, P, I, I, I, I, P, P, P, P, I, I, I, I, P, P, I, P, I, P, P, P],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -215,3 +215,27 @@ def traj_global(pose: Tensor, sel: Optional[Tensor], center: Tensor, yaw: Tensor
                                     L.ptr(pos), L.ptr(oyaw), L.stream()), "tb_traj_global")
     _count()
     return pos, oyaw
+
+
+def knarpe_attn_bwd(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, idx: Tensor, invalid: Tensor,
+                    rel: Tensor, freq_xy: Tensor, B: int, S: int, D: int, d_out: Tensor, H: int = 4,
+                    kv1: Optional[Tensor] = None, T1: int = 0, div1: int = 1, K1: int = 0
+                    ) -> Tuple[Tensor, Tensor, Optional[Tensor]]:
+    """Backward of the KNARPE core (tb_knarpe_attn_bwd): d_out [B*S, D+H*D] = [d_ov | d_z] ->
+    (d_qu [B*S, D+H*D] = [d_q | d_u], d_kv0 like kv0, d_kv1 like kv1 or None). fp32 tables only."""
+    M = B * S
+    for t in (q, u, kv0, d_out) + ((kv1,) if kv1 is not None else ()):
+        assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
+    assert kv0.is_contiguous() and (kv1 is None or kv1.is_contiguous())
+    d_qu = torch.empty(M, D + H * D, dtype=torch.float32, device=q.device)
+    d_kv0 = torch.zeros_like(kv0)
+    d_kv1 = torch.zeros_like(kv1) if kv1 is not None else None
+    inv = _u8(invalid)
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and inv.is_contiguous() and rel.is_contiguous()
+    L.check(L.load().tb_knarpe_attn_bwd(
+        L.ptr(q), q.stride(0), L.ptr(u), u.stride(0), L.ptr(kv0), kv0.stride(0), T0, div0, K0,
+        L.ptr(kv1), kv1.stride(0) if kv1 is not None else 0, T1, div1, K1, L.ptr(idx), L.ptr(inv), L.ptr(rel),
+        L.ptr(freq_xy), B, S, D, H, L.ptr(d_out), L.ptr(d_out[:, D:]), d_out.stride(0), L.ptr(d_qu), d_qu.stride(0),
+        L.ptr(d_kv0), L.ptr(d_kv1), L.stream()), "tb_knarpe_attn_bwd")
+    _count()
+    return d_qu, d_kv0, d_kv1

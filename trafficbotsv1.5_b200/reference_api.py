@@ -17,6 +17,8 @@ project-once-then-gather form instead.
 """
 from typing import Optional, Tuple, Union
 
+import math
+
 import torch
 from torch import Tensor, nn
 
@@ -118,6 +120,27 @@ def _knn_dict(idx: Tensor, mask: Tensor, rpe: Tensor, d_rpe: int) -> dict:
     return out
 
 
+class _KnarpeCore(torch.autograd.Function):
+    """Differentiable KNARPE core: forward tb_knarpe_attn, backward tb_knarpe_attn_bwd (fp32; gradients w.r.t. q, u and
+    the K|V table, none into the relative pose). Used by AttentionRPE when gradients are required."""
+
+    @staticmethod
+    def forward(ctx, q, u, kv, idx, inv, rel, freq, B, S, K):
+        d = q.shape[1]
+        out, nv = ops.knarpe_attn(q, u, kv, S * K, 1, K, idx, inv, rel, freq, B, S, d, H)
+        ctx.save_for_backward(q, u, kv, idx, inv, rel, freq)
+        ctx.dims = (B, S, K, d)
+        ctx.mark_non_differentiable(nv)
+        return out, nv
+
+    @staticmethod
+    def backward(ctx, d_out, _d_nv):
+        q, u, kv, idx, inv, rel, freq = ctx.saved_tensors
+        B, S, K, d = ctx.dims
+        d_qu, d_kv, _ = ops.knarpe_attn_bwd(q, u, kv, S * K, 1, K, idx, inv, rel, freq, B, S, d, d_out.contiguous())
+        return d_qu[:, :d], d_qu[:, d:], d_kv, None, None, None, None, None, None, None
+
+
 class AttentionRPE(nn.Module, _FusedMixin):
     """KNARPE attention, src/models/modules/attention_rpe.py:10-198 (same parameters: in_proj_weight, in_proj_bias,
     out_proj_weight, out_proj_bias, linear_rpe.*)."""
@@ -141,7 +164,6 @@ class AttentionRPE(nn.Module, _FusedMixin):
         nn.init.constant_(self.in_proj_bias, 0.0)
         nn.init.constant_(self.out_proj_bias, 0.0)
 
-    @torch.no_grad()
     def forward(self, src: Tensor, tgt: Optional[Tensor] = None, tgt_padding_mask: Optional[Tensor] = None,
                 attn_mask: Optional[Tensor] = None, rpe: Optional[Tensor] = None, need_weights=False
                 ) -> Tuple[Tensor, Optional[Tensor]]:
@@ -150,6 +172,43 @@ class AttentionRPE(nn.Module, _FusedMixin):
         if rpe is None or tgt is None or tgt.dim() != 4 or attn_mask is not None or need_weights:
             raise NotImplementedError("only the KNN + RPE branch (attention_rpe.py:137-164) is implemented")
         assert self.d_rpe > 0  # attention_rpe.py:139
+        # gradients are produced when autograd is on and either an input carries a graph or the module is in train()
+        # mode (eval-mode calls on plain tensors take the fused inference path, like the reference under no_grad)
+        needs_grad = torch.is_grad_enabled() and (src.requires_grad or tgt.requires_grad or self.training)
+        if needs_grad:
+            return self._forward_autograd(src, tgt, tgt_padding_mask, rpe), None
+        with torch.no_grad():
+            return self._forward_inference(src, tgt, tgt_padding_mask, rpe), None
+
+    def _forward_autograd(self, src: Tensor, tgt: Tensor, tgt_padding_mask: Optional[Tensor], rpe: Tensor) -> Tensor:
+        """Differentiable path (fp32): the projections are torch GEMMs (autograd), the attention core is the CUDA
+        kernel pair tb_knarpe_attn / tb_knarpe_attn_bwd. Same re-association as DESIGN.md 3, written with the
+        module's own parameters so that gradients reach in_proj / linear_rpe / out_proj (attention_rpe.py:92-97,
+        147-161, 180-186)."""
+        B, S, K, d = tgt.shape
+        if d != 128 or rpe.shape[-1] != 3:
+            raise NotImplementedError("autograd path: d_model 128 and raw relative poses [B,S,K,3] only")
+        M, dh = B * S, self.d_head
+        w_q, w_kv = self.in_proj_weight[:d], self.in_proj_weight[d:]
+        b_q, b_kv = self.in_proj_bias[:d], self.in_proj_bias[d:]
+        w_rk, w_rv = self.linear_rpe.weight[:d], self.linear_rpe.weight[d:]
+        b_rv = self.linear_rpe.bias[d:]
+        scale = math.log2(math.e) / math.sqrt(dh)
+        q = torch.nn.functional.linear(src.reshape(M, d).float(), w_q, b_q) * scale
+        u = torch.einsum("mhc,hcr->mhr", q.view(M, H, dh), w_rk.view(H, dh, self.d_rpe)).reshape(M, H * self.d_rpe)
+        kv = torch.nn.functional.linear(tgt.reshape(M * K, d).float(), w_kv, b_kv)
+        idx = torch.arange(S * K, dtype=torch.int32, device=src.device).view(1, S, K).expand(B, -1, -1).contiguous()
+        mask = (tgt_padding_mask if tgt_padding_mask is not None
+                else torch.zeros(B, S, K, dtype=torch.bool, device=src.device)).contiguous()
+        freq = ops.pe_freq_xy(d, 1e3, src.device)
+        o, nv = _KnarpeCore.apply(q.contiguous(), u.contiguous(), kv.contiguous(), idx, mask,
+                                  rpe.float().contiguous(), freq, B, S, K)
+        ov, z = o[:, :d], o[:, d:].view(M, H, self.d_rpe)
+        rv = torch.einsum("mhr,hcr->mhc", z, w_rv.view(H, dh, self.d_rpe)).reshape(M, d) + b_rv  # sum_j a_j = 1
+        out = torch.nn.functional.linear(ov + rv, self.out_proj_weight, self.out_proj_bias)
+        return out.masked_fill(nv[:, None], 0.0).view(B, S, d)                                   # :188-190
+
+    def _forward_inference(self, src: Tensor, tgt: Tensor, tgt_padding_mask: Optional[Tensor], rpe: Tensor) -> Tensor:
         B, S, K, d = tgt.shape
         m = self._runner(d)
         f = m.fa[""]
@@ -162,7 +221,7 @@ class AttentionRPE(nn.Module, _FusedMixin):
         o, nv = ops.knarpe_attn(proj[:, :d], proj[:, d:], kv, S * K, 1, K, knn["idx"], knn["inv"], knn.get("rel"),
                                 m.freq_rpe, B, S, d, H, emb=knn.get("emb"))
         out = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, precision=m.precision)
-        return out.view(B, S, d), None
+        return out.view(B, S, d)
 
 
 class TransformerRPE(nn.Module):
