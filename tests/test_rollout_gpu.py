@@ -409,3 +409,16 @@ def test_post_process_wosac_after_rollout():
     assert maxerr(out["pos_sim"], pos) < 5e-4 and maxerr(out["yaw_sim"], yaw) < 2e-6
     with pytest.raises(RuntimeError):
         RolloutEngine(P, cfg, DEV, n_rollout=6, step_end=30).post_process_wosac(res, batch, n_keep=4)
+
+
+def test_rollout_golden_tf32_fp32_intermediates(golden_rollout):
+    """precision=1 with `kv_half = False`: tf32 tcgen05 projections, fp32 intermediates, SIMT attention, unfused history
+    encoder — the fall-back for checkpoints whose activations exceed the fp16 range."""
+    g = golden_rollout
+    eng, batch, P, cfg = _engine(g["shape"], g["R"], g["T"], precision=1)
+    eng.model.kv_half = False
+    res = eng.rollout(batch)
+    assert int((res["pred_valid"].cpu() != g["pred_valid"]).sum()) == 0
+    assert int((res["tl_state"].cpu() != g["tl_state"]).sum()) == 0
+    assert maxerr(res["pred_pose"][..., :2], g["pred_pose"][..., :2]) < TC_TOL_XY
+    assert maxerr(res["pred_pose"][..., 2], g["pred_pose"][..., 2]) < TC_TOL_YAW
