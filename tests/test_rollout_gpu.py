@@ -252,24 +252,27 @@ def test_rule_checks_in_rollout_vs_oracle():
     (dict(n_sc=1, n_ag=37, n_mp=70, n_tl=27, seed=5, boundary=103.0), 3, 15),      # ragged sizes just above the K's
     (dict(n_sc=3, n_ag=26, n_mp=65, n_tl=26, seed=6, boundary=101.0), 1, 13),      # minimum sizes (K < T), 1 rollout
 ])
-def test_rollout_ragged_shapes_vs_oracle(shape, R, T):
-    """Row counts that are not multiples of any tile (128-row GEMM tiles, 8-token attention CTAs, 64-row select CTAs)
-    and target counts one above the KNN sizes (K_ag2ag = 25 < 26, K_ag2mp = 64 < 65, K_tl2* = 24)."""
-    eng, batch, P, cfg = _engine(shape, R, T)
+@pytest.mark.parametrize("precision", [0, 1])
+def test_rollout_ragged_shapes_vs_oracle(shape, R, T, precision):
+    """Row counts that are not multiples of any tile (128-row GEMM tiles, 8-token attention CTAs, 64-row select CTAs,
+    16-neighbour MMA groups, 8 agents per CTA of the fused history encoder) and target counts one above the KNN sizes
+    (K_ag2ag = 25 < 26, K_ag2mp = 64 < 65, K_tl2* = 24), in the fp32 and in the tensor-core mode."""
+    eng, batch, P, cfg = _engine(shape, R, T, precision=precision)
     res = eng.rollout(batch)
     ref = O.rollout(P, cfg, config.derived_sizes(cfg), config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, T)
     assert torch.equal(res["pred_valid"].cpu(), ref["pred_valid"])
     assert torch.equal(res["tl_state"].cpu(), ref["tl_state"])
-    assert maxerr(res["pred_pose"][..., :2], ref["pred_pose"][..., :2]) < TOL_XY
-    assert maxerr(res["pred_pose"][..., 2], ref["pred_pose"][..., 2]) < TOL_YAW
+    assert maxerr(res["pred_pose"][..., :2], ref["pred_pose"][..., :2]) < (TC_TOL_XY if precision else TOL_XY)
+    assert maxerr(res["pred_pose"][..., 2], ref["pred_pose"][..., 2]) < (TC_TOL_YAW if precision else TOL_YAW)
 
 
-def test_rollout_degenerate_scenes():
+@pytest.mark.parametrize("precision", [0, 1])
+def test_rollout_degenerate_scenes(precision):
     """All agents invalid / all traffic lights invalid / all map polylines invalid: every attention row is fully
-    masked -> exact zeros, no NaN; agents that are never valid stay exactly zero."""
+    masked -> exact zeros, no NaN; agents that are never valid stay exactly zero (fp32 and tensor-core mode)."""
     shape = dict(n_sc=2, n_ag=30, n_mp=80, n_tl=28, seed=9, boundary=110.0)
     R, T = 2, 12
-    eng, batch, P, cfg = _engine(shape, R, T)
+    eng, batch, P, cfg = _engine(shape, R, T, precision=precision)
     batch["sc/ag_valid"][0] = False          # scene 0: no agent at all
     batch["ag_navi_valid"][0] = False
     batch["ag_latent_valid"][0] = False
@@ -281,7 +284,7 @@ def test_rollout_degenerate_scenes():
     assert bool(torch.isfinite(res["pred_pose"]).all()) and bool(torch.isfinite(res["pred_motion"]).all())
     assert torch.equal(res["pred_valid"].cpu(), ref["pred_valid"])
     assert float(res["pred_pose"][: R].abs().max()) == 0.0
-    assert maxerr(res["pred_pose"], ref["pred_pose"]) < TOL_XY
+    assert maxerr(res["pred_pose"], ref["pred_pose"]) < (TC_TOL_XY if precision else TOL_XY)
 
 
 def test_module_api_in_reference_loop(golden_rollout):
