@@ -575,7 +575,7 @@ def test_attention_rpe_dropin_autograd_vs_oracle():
     out, _ = mod(sg, tg, mask.to(DEV), None, rel.to(DEV))
     (out * G.to(DEV)).sum().backward()
     assert rel_l2(out.detach(), ref.detach().float()) < 1e-5
-    assert float(out[1, 2].abs().max()) == 0.0
+    assert float(out.detach()[1, 2].abs().max()) == 0.0
     checks = [("src", sg.grad, s64.grad), ("tgt", tg.grad, t64.grad)] + \
              [(k, dict(mod.named_parameters())[k].grad, P[f"a.{k}"].grad) for k in shapes]
     for name, a, b_ in checks:
