@@ -243,10 +243,11 @@ class RolloutEngine:
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
             m.tl_forward(st["hist_tl"], st["d_step"], static["tl"], out_feat=st["tl_feat"], out_logits=st["tl_logits"])
+            kv_tl = m.ag_tl_tables(st["tl_feat"])  # still on the TL stream: joined at the first cross-attention
         tl_feat, logits = st["tl_feat"], st["tl_logits"]
         m.ag_forward(st, static["mp"], static["kv_mp"], static["tl"], tl_feat, self.R, out=st["x_cat"][:, :d],
                      aux=aux, before_tl=lambda: main.wait_stream(self._side), knn_stream=self._side2,
-                     knn_stream2=self._side3)
+                     knn_stream2=self._side3, kv_tl=kv_tl)
         act = m.heads(st["x_cat"], st, navi)
         if aux is not None:
             aux.update(tl_feat=tl_feat, logits=logits, act=act, ag_feat=st["x_cat"][:, :d].clone())

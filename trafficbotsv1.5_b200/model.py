@@ -322,9 +322,11 @@ class HotPathModel:
 
     def ag_forward(self, st: dict, mp: Dict[str, Tensor], kv_mp: list, tl: dict, tl_feat: Tensor, R: int,
                    out: Optional[Tensor] = None, aux: Optional[dict] = None, before_tl=None, knn_stream=None,
-                   knn_stream2=None) -> Tensor:
+                   knn_stream2=None, kv_tl: Optional[list] = None) -> Tensor:
         """AgentEncoder._forward_hptr (agent_encoder.py:114-178). `st` holds the rollout state rings
-        (engine.RolloutState); batch b uses map / traffic-light tables of scene b // R."""
+        (engine.RolloutState); batch b uses map / traffic-light tables of scene b // R. `kv_tl`: per-layer K|V tables
+        of the traffic-light tokens when the caller already built them (on the TL stream); `before_tl` is then
+        only called right before the first cross-attention instead of before layer 0."""
         from . import lib as L
         sz, d, W = self.sz, self.d, self.W
         B, A = st["B"], st["A"]
@@ -397,17 +399,29 @@ class HotPathModel:
         nl = self.cfg["ag_encoder"]["n_layer_tf"]
         if aux is not None:
             aux.update(tok_pose=tok_pose, tok_inv=tok_inv, tok0=tok, knn_self=knn_self, cidx=cidx, cinv=cinv, crel=crel)
-        if before_tl is not None:
+        if before_tl is not None and kv_tl is None:
             before_tl()  # join point: the traffic-light branch (side stream) must have produced tl_feat
+
+        def join_first_cross():  # the first consumer of the agent->map/TL lists and of the TL tables
+            if join_cross is not None:
+                join_cross()
+            if before_tl is not None and kv_tl is not None:
+                before_tl()
+
         for i in range(nl):
             p = f"ag_encoder.tf_ag2agmptl.layers.{i}"
-            kv_tl = self.kv_table(tl_feat, p, "norm_tgt")
-            cross = dict(kv0=kv_mp[i], T0=n_mp, div0=R, K0=sz["k_ag2mp"], kv1=kv_tl, T1=n_tl, div1=tl_div,
+            kv1 = kv_tl[i] if kv_tl is not None else self.kv_table(tl_feat, p, "norm_tgt")
+            cross = dict(kv0=kv_mp[i], T0=n_mp, div0=R, K0=sz["k_ag2mp"], kv1=kv1, T1=n_tl, div1=tl_div,
                          K1=sz["k_ag2tl"], idx=cidx, inv=cinv, rel=crel)
             tok = self.tf_layer(p, "dec_cross_attn", tok, flat_inv, B, A, knn_self, cross,
                                 out=out if i == nl - 1 else None, before_self=join_self if i == 0 else None,
-                                before_cross=join_cross if i == 0 else None)
+                                before_cross=join_first_cross if i == 0 else None)
         return tok
+
+    def ag_tl_tables(self, tl_feat: Tensor) -> list:
+        """K|V tables of the traffic-light tokens for the 4 agent layers (rows of tf_ag2agmptl's cross-attention)."""
+        return [self.kv_table(tl_feat, f"ag_encoder.tf_ag2agmptl.layers.{i}", "norm_tgt")
+                for i in range(self.cfg["ag_encoder"]["n_layer_tf"])]
 
     # ------------------------------------------------------------------------------------------ destinations (once / scene)
     def navi_predictor(self, ag_valid: Tensor, ag_attr: Tensor, ag_motion: Tensor, ag_pose: Tensor,
