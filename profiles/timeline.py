@@ -19,12 +19,12 @@ eng.prepare(synth.make_scene_batch(n_sc=16, seed=1000))
 eng.run()
 torch.cuda.synchronize()
 eng._reset(eng._st)
-for _ in range(14):
-    eng._graph.replay()
+for s_ in range(1, 15):
+    eng._graph[(s_ + 1) % 2].replay()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    for _ in range(3):
-        eng._graph.replay()
+    for s_ in range(15, 18):
+        eng._graph[(s_ + 1) % 2].replay()
     torch.cuda.synchronize()
 import json  # noqa: E402
 import tempfile  # noqa: E402

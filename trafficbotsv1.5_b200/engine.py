@@ -102,7 +102,8 @@ class RolloutEngine:
         self.use_graph = use_graph
         self.rule_checks = rule_checks  # also evaluate the logging-only TrafficRuleChecker checks every step
         self.dyn = C.DYNAMICS_CFG
-        self._graph = None
+        self._graph = None   # (graph for odd steps, graph for even steps): the TL branch is double-buffered
+        self._host_step = 1  # parity source for eager _step calls
         self._shape = None
         self._side = torch.cuda.Stream(device=self.dev)  # traffic-light branch runs beside the agent front-end
         self._side2 = torch.cuda.Stream(device=self.dev)  # KNN selects run beside the history encoder and layer 0
@@ -167,7 +168,12 @@ class RolloutEngine:
                   mp_node_invalid=z(n_sc, n_mp, n_node, dt=u8), mp_kind=z(n_sc, n_mp, dt=u8),
                   pred_valid=z(B, A, T, dt=u8), pred_pose=z(B, A, T, 3), pred_motion=z(B, A, T, 3),
                   tl_out=z(Bt, n_tl, T, 5, dt=u8), x_cat=z(B * A, 2 * d),
-                  tl_feat=z(Bt * n_tl, d), tl_logits=z(Bt * n_tl, self.cfg["tl_state_dim"]),
+                  # traffic-light branch, double-buffered by step parity: TL(s+1) is evaluated during iteration s
+                  tl_feat=z(2, Bt * n_tl, d), tl_logits=z(2, Bt * n_tl, self.cfg["tl_state_dim"]),
+                  kv_tl=[[torch.empty(Bt * n_tl, 2 * d, device=dev,
+                                      dtype=torch.float16 if self.model.kv_half else torch.float32)
+                          for _ in range(self.cfg["ag_encoder"]["n_layer_tf"])] for _ in range(2)],
+                  d_step_tl=z(1, dt=torch.int32),
                   init_navi_valid=z(B, A, dt=torch.bool))
         if self.rule_checks:
             st.update(ag_size=z(n_sc, A, 3), passive_counter=z(B, A), seg=z(n_sc, n_mp, n_node, 4),
@@ -233,21 +239,43 @@ class RolloutEngine:
         st["hist_motion"][:, :, 0] = st["motion"]
         st["hist_tl"][:, :, 0] = st["gt_tl"][:, :, 0]
         st["d_step"].fill_(1)
+        st["d_step_tl"].fill_(1)
+        self._host_step = 1
+        # prologue of the TL pipeline: tokens / logits / agent-layer tables of step 1 (buffer set 1 = odd steps)
+        self._tl_branch(st, self._static, 1)
+        st["d_step_tl"].fill_(2)
+
+    def _tl_branch(self, st: dict, static: dict, dst: int):
+        """Traffic-light encoder + state predictor for the step `d_step_tl` points to, into buffer set `dst`."""
+        m = self.model
+        m.tl_forward(st["hist_tl"], st["d_step_tl"], static["tl"], out_feat=st["tl_feat"][dst],
+                     out_logits=st["tl_logits"][dst])
+        m.ag_tl_tables(st["tl_feat"][dst], out=st["kv_tl"][dst])
 
     # ---------------------------------------------------------------------------------------------- one step
-    def _step(self, st: dict, static: dict, navi: dict, aux: Optional[dict] = None):
+    def _step(self, st: dict, static: dict, navi: dict, aux: Optional[dict] = None, parity: Optional[int] = None):
+        """One policy iteration s. The traffic-light branch depends only on its own history (its state feedback is
+        the argmax of its own logits, dynamics.py:154-159), so it is software-pipelined: while the agents of step s
+        are encoded on the main stream, the side stream applies the TL feedback of step s and evaluates the TL
+        tokens of step s+1 into the other buffer set. The ~70 tiny TL launches then fill the tails of the large
+        agent kernels instead of sitting on the critical path of the first agent cross-attention
+        (profiles/r1/timeline_final.txt)."""
         m, lib = self.model, L.load()
         d = m.d
-        # fork: the TL branch (640 rows, launch-latency bound) overlaps the agent featurise / PointNet / KNN kernels
+        if parity is None:  # eager call: the host knows the step number
+            parity = self._host_step % 2
+            self._host_step += 1
+        cur, nxt = parity, 1 - parity
+        tl_feat, logits = st["tl_feat"][cur], st["tl_logits"][cur]
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
-            m.tl_forward(st["hist_tl"], st["d_step"], static["tl"], out_feat=st["tl_feat"], out_logits=st["tl_logits"])
-            kv_tl = m.ag_tl_tables(st["tl_feat"])  # still on the TL stream: joined at the first cross-attention
-        tl_feat, logits = st["tl_feat"], st["tl_logits"]
+            L.check(lib.tb_tl_step(L.ptr(logits), L.ptr(ops._u8(static["tl"]["tl_token_invalid"])), L.ptr(st["gt_tl"]),
+                                   st["n_gt"], L.ptr(st["d_step"]), st["Bt"], st["n_tl"], m.W, self.T,
+                                   L.ptr(st["hist_tl"]), L.ptr(st["tl_out"]), L.stream()), "tb_tl_step")
+            self._tl_branch(st, static, nxt)
         m.ag_forward(st, static["mp"], static["kv_mp"], static["tl"], tl_feat, self.R, out=st["x_cat"][:, :d],
-                     aux=aux, before_tl=lambda: main.wait_stream(self._side), knn_stream=self._side2,
-                     knn_stream2=self._side3, kv_tl=kv_tl)
+                     aux=aux, knn_stream=self._side2, knn_stream2=self._side3, kv_tl=st["kv_tl"][cur])
         act = m.heads(st["x_cat"], st, navi)
         if aux is not None:
             aux.update(tl_feat=tl_feat, logits=logits, act=act, ag_feat=st["x_cat"][:, :d].clone())
@@ -263,9 +291,7 @@ class RolloutEngine:
             self.thresh_edge, self.cos_rot, L.ptr(st["d_step"]), st["B"], st["A"], m.W, self.T, L.ptr(st["hist_valid"]),
             L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]), L.ptr(st["pred_valid"]), L.ptr(st["pred_pose"]),
             L.ptr(st["pred_motion"]), L.stream()), "tb_dyn_step")
-        L.check(lib.tb_tl_step(L.ptr(logits), L.ptr(ops._u8(static["tl"]["tl_token_invalid"])), L.ptr(st["gt_tl"]),
-                               st["n_gt"], L.ptr(st["d_step"]), st["Bt"], st["n_tl"], m.W, self.T, L.ptr(st["hist_tl"]),
-                               L.ptr(st["tl_out"]), L.stream()), "tb_tl_step")
+        main.wait_stream(self._side)  # TL feedback of this step applied, TL tokens of the next step ready
         if self.rule_checks:
             tlp = static["tl"]
             L.check(lib.tb_rule_check(
@@ -277,7 +303,8 @@ class RolloutEngine:
                 st["n_tl"], self.R, self.R, 1.1, L.stream()), "tb_rule_check")
             ops._count()
         L.check(lib.tb_step_advance(L.ptr(st["d_step"]), L.stream()), "tb_step_advance")
-        ops._count(3)
+        L.check(lib.tb_step_advance(L.ptr(st["d_step_tl"]), L.stream()), "tb_step_advance")
+        ops._count(4)
 
     # ---------------------------------------------------------------------------------------------- public API
     def prepare(self, batch: Dict[str, Tensor], static: Optional[dict] = None) -> dict:
@@ -313,13 +340,17 @@ class RolloutEngine:
                     self._step(st, self._static, self._navi)  # warm-up (allocator, lazy module load)
                 torch.cuda.current_stream().wait_stream(s)
                 self._reset(st)
-                n0 = ops.LAUNCHES
-                self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph):
-                    self._step(st, self._static, self._navi)
-                self.launches_per_step = ops.LAUNCHES - n0
-            for _ in range(n_steps):
-                self._graph.replay()
+                graphs = []
+                for parity in (1, 0):  # first step is odd
+                    n0 = ops.LAUNCHES
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._step(st, self._static, self._navi, parity=parity)
+                    self.launches_per_step = ops.LAUNCHES - n0
+                    graphs.append(g)
+                self._graph = (graphs[0], graphs[1])  # indexed by (step + 1) % 2: odd steps first
+            for s_ in range(1, n_steps + 1):
+                self._graph[(s_ + 1) % 2].replay()
         else:
             for s_ in range(1, n_steps + 1):
                 aux = {} if record is not None else None

@@ -145,15 +145,16 @@ class HotPathModel:
             self._pn_split[key] = (w[:, :half].contiguous(), w[:, half:].contiguous())
         return self._pn_split[key]
 
-    def kv_table(self, feat: Tensor, layer_prefix: str, norm: str, attn: str = "attn") -> Tensor:
+    def kv_table(self, feat: Tensor, layer_prefix: str, norm: str, attn: str = "attn", out: Optional[Tensor] = None
+                 ) -> Tensor:
         """K/V rows of a target table for one layer: W_kv LN(x) + b  (project-once-then-gather)."""
         f = self.fa[f"{layer_prefix}.{attn}"]
         x = self.ln(feat, f"{layer_prefix}.{norm}", half=self.kv_half)
         if self.kv_half:  # tensor-core mode: fp16 tables straight from the projection's epilogue
-            tbl = torch.empty(x.shape[0], 2 * self.d, dtype=torch.float16, device=x.device)
+            tbl = out if out is not None else torch.empty(x.shape[0], 2 * self.d, dtype=torch.float16, device=x.device)
             self._proj(x, f"{layer_prefix}.{attn}.w_kv", f["w_kv"], f["b_kv"], out_h=tbl, col_h=0)
             return tbl
-        return ops.linear(x, f["w_kv"], f["b_kv"], precision=self.precision)
+        return ops.linear(x, f["w_kv"], f["b_kv"], precision=self.precision, out=out)
 
     def _in_self(self, f, x, K, key=""):
         """[q|u] (fp32) and the token's own [k|v] rows from one projection; k|v are fp16 in tensor-core mode. Short
@@ -418,9 +419,10 @@ class HotPathModel:
                                 before_cross=join_first_cross if i == 0 else None)
         return tok
 
-    def ag_tl_tables(self, tl_feat: Tensor) -> list:
+    def ag_tl_tables(self, tl_feat: Tensor, out: Optional[list] = None) -> list:
         """K|V tables of the traffic-light tokens for the 4 agent layers (rows of tf_ag2agmptl's cross-attention)."""
-        return [self.kv_table(tl_feat, f"ag_encoder.tf_ag2agmptl.layers.{i}", "norm_tgt")
+        return [self.kv_table(tl_feat, f"ag_encoder.tf_ag2agmptl.layers.{i}", "norm_tgt",
+                              out=out[i] if out is not None else None)
                 for i in range(self.cfg["ag_encoder"]["n_layer_tf"])]
 
     # ------------------------------------------------------------------------------------------ destinations (once / scene)
