@@ -47,11 +47,19 @@ int tb_version(void);
  * can be concatenated in place (agent_encoder.py:165-167).
  *   src_pose [B,S,3] src_invalid [B,S]  tgt_pose [B/div,T,3] tgt_invalid [B/div,T]
  *   out_idx [B,S,ldk] int32   out_invalid [B,S,ldk] u8   out_rel [B,S,ldk,3] f32
+ * Optional (all may be NULL / 0) — repeated selections against STATIC targets (agent -> map, every rollout step):
+ *   tgt_index_map [B/div,T] int32: the targets are passed in a caller-chosen order and out_idx reports
+ *     tgt_index_map[position] (ties and output order then follow the passed order);
+ *   sorted_by_x != 0: the caller promises tgt_pose[..,0] ascending within each target batch;
+ *   row_state [B,S,3] f32 (in/out): (x, y, K-th smallest squared distance) of the previous call for the same row,
+ *     K-th = +inf to start. With sorted targets only the slab |x_t - x_s| <= sqrt(K-th) + |displacement| is scanned
+ *     (the K nearest of the previous call still lie within that radius: same result as a full scan).
  * Limits: 0 < K < T <= 2048.
  * ------------------------------------------------------------------------------------------------- */
 int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float* tgt_pose,
                   const uint8_t* tgt_invalid, int B, int S, int T, int tgt_batch_div, int K, float dist_limit,
-                  int32_t* out_idx, uint8_t* out_invalid, float* out_rel, int out_ldk, int out_koff, void* stream);
+                  int32_t* out_idx, uint8_t* out_invalid, float* out_rel, int out_ldk, int out_koff,
+                  const int32_t* tgt_index_map, float* row_state, int sorted_by_x, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * KNARPE attention core (gather + relative-pose bias + masked softmax + weighted sum).

@@ -27,10 +27,10 @@ def test_exports_match_header(handle):
 
 def test_error_codes_without_gpu(handle):
     # NULL pointers / bad shapes are rejected before any launch
-    assert handle.tb_knn_select(None, None, None, None, 1, 1, 4, 1, 2, 1.0, None, None, None, 2, 0, None) == -5
+    assert handle.tb_knn_select(None, None, None, None, 1, 1, 4, 1, 2, 1.0, None, None, None, 2, 0, None, None, 0, None) == -5
     one = 16  # any non-null, 16-byte aligned fake address; never dereferenced because validation fails first
-    assert handle.tb_knn_select(one, one, one, one, 1, 1, 4, 1, 4, 1.0, one, one, one, 4, 0, None) == -2  # K == T
-    assert handle.tb_knn_select(one, one, one, one, 1, 1, 4096, 1, 4, 1.0, one, one, one, 4, 0, None) == -3
+    assert handle.tb_knn_select(one, one, one, one, 1, 1, 4, 1, 4, 1.0, one, one, one, 4, 0, None, None, 0, None) == -2  # K == T
+    assert handle.tb_knn_select(one, one, one, one, 1, 1, 4096, 1, 4, 1.0, one, one, one, 4, 0, None, None, 0, None) == -3
     assert handle.tb_layernorm(one, 128, one, one, one, 128, 4, 96, 0, None) == -3
     assert handle.tb_layernorm(one, 128, one, one, one, 132, 4, 128, 2, None) == -4  # fp16 rows: ldy % 8
     assert handle.tb_linear(one, 4, one, None, 0, one, 4, 0, 4, 4, 0, None, None, 0, None, 0, None, 0, 0, None) == -1

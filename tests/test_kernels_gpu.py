@@ -586,3 +586,38 @@ def test_attention_rpe_dropin_autograd_vs_oracle():
     with torch.no_grad():
         out2, _ = mod(src.to(DEV), tgt.to(DEV), mask.to(DEV), None, rel.to(DEV))
     assert rel_l2(out2, ref.detach().float()) < 1e-5
+
+
+def test_knn_select_temporal_slab_path_exact():
+    """tb_knn_select with x-sorted static targets + row_state (the per-step agent -> map select): over a sequence of
+    moving / teleporting / invalidated sources the selected SETS, masks and relative poses equal the stateless full
+    scan (the slab |x - sx| <= sqrt(kth_prev) + |displacement| always contains the K nearest)."""
+    B, S, T, K, div, lim = 6, 70, 1024, 64, 3, 80.0
+    g = torch.Generator().manual_seed(11)
+    tgt = torch.cat([(torch.rand(B // div, T, 2, generator=g) * 2 - 1) * 150, (torch.rand(B // div, T, 1, generator=g) * 2 - 1) * 3], -1)
+    tinv = torch.rand(B // div, T, generator=g) < 0.1
+    order = torch.argsort(tgt[..., 0], dim=1)
+    s_pose = torch.gather(tgt, 1, order[..., None].expand(-1, -1, 3)).contiguous().to(DEV)
+    s_inv = torch.gather(tinv, 1, order).contiguous().to(DEV)
+    s_idx = order.to(torch.int32).contiguous().to(DEV)
+    state = torch.full((B, S, 3), float("inf"), device=DEV)
+    src = torch.cat([(torch.rand(B, S, 2, generator=g) * 2 - 1) * 120, (torch.rand(B, S, 1, generator=g) * 2 - 1) * 3], -1)
+    for step in range(8):
+        sinv = torch.rand(B, S, generator=g) < 0.1
+        if step:
+            src = src + torch.cat([torch.randn(B, S, 2, generator=g) * (0.5 + step), torch.randn(B, S, 1, generator=g) * 0.1], -1)
+        if step == 4:
+            src[:, :10, :2] = (torch.rand(B, 10, 2, generator=g) * 2 - 1) * 140      # teleports
+        i0, m0, r0 = ops.knn_select(src.to(DEV), sinv.to(DEV), tgt.to(DEV), tinv.to(DEV), K, lim, tgt_div=div)
+        i1, m1, r1 = ops.knn_select(src.to(DEV), sinv.to(DEV), s_pose, s_inv, K, lim, tgt_div=div, index_map=s_idx,
+                                    row_state=state, sorted_by_x=True)
+        ok = ~sinv.to(DEV)  # rows of invalid sources: fillers only
+        o0, o1 = i0.argsort(-1), i1.argsort(-1)
+        a0, a1 = torch.gather(i0, 2, o0), torch.gather(i1, 2, o1)
+        assert torch.equal(a0[ok], a1[ok]), f"step {step}: selected sets differ"
+        assert torch.equal(torch.gather(m0, 2, o0)[ok], torch.gather(m1, 2, o1)[ok])
+        rr0 = torch.gather(r0, 2, o0[..., None].expand(-1, -1, -1, 3))[ok]
+        rr1 = torch.gather(r1, 2, o1[..., None].expand(-1, -1, -1, 3))[ok]
+        assert torch.equal(rr0, rr1)
+        assert bool(m1[~ok].all())
+    assert bool(torch.isfinite(state[..., 2][ok]).all())  # the fast path was armed

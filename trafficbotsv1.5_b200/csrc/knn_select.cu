@@ -20,8 +20,8 @@ constexpr int kCap = 12;         // pruned candidate list: up to kCap*32 survivo
 
 // K-th smallest of the warp's keys (N per lane) by bisection on the bit pattern; returns tau and #keys < tau.
 template <int N>
-__device__ __forceinline__ uint32_t kth_smallest(const uint32_t (&key)[N], int K, uint32_t hi, int* c_lt_out) {
-  uint32_t lo = 0u;
+__device__ __forceinline__ uint32_t kth_smallest(const uint32_t (&key)[N], int K, uint32_t hi, int* c_lt_out,
+                                                 uint32_t lo = 0u) {
   while (lo < hi) {
     const uint32_t mid = lo + ((hi - lo) >> 1);
     int c = 0;
@@ -42,6 +42,7 @@ struct RowCtx {
   const float *tx, *ty, *tyaw;
   const uint8_t* tinv;
   bool sinv;
+  const int32_t* tmap;  // staged target position -> caller's target index (NULL: identity)
   int32_t* out_idx; uint8_t* out_invalid; float* out_rel;
   size_t obase;
 };
@@ -52,10 +53,36 @@ __device__ __forceinline__ void emit(const RowCtx& c, int pos, int t) {
   const float lx = fmaf(dx, c.cs, dy * c.sn), ly = fmaf(dy, c.cs, -dx * c.sn);
   const bool dead = c.sinv || c.tinv[t];
   const float d = dead ? __int_as_float(0x7f800000) : sqrtf(fmaf(lx, lx, ly * ly));
-  c.out_idx[c.obase + pos] = t;
+  c.out_idx[c.obase + pos] = c.tmap ? c.tmap[t] : t;
   c.out_invalid[c.obase + pos] = (uint8_t)((c.tinv[t] != 0) | (d > c.dist_limit));
   float* r = c.out_rel + (c.obase + pos) * 3;
   r[0] = lx; r[1] = ly; r[2] = c.tyaw[t] - c.syaw;
+}
+
+// K smallest of a compacted candidate list (keys + staged target positions, ascending position order): bisection on
+// [lo, hi], winners emitted in list order (ties: earlier entries). Returns the K-th smallest key.
+template <int NC>
+__device__ __forceinline__ uint32_t select_from_list(const RowCtx& c, const uint32_t* ckey, const uint16_t* cidx, int cnt,
+                                                     int K, uint32_t lo, uint32_t hi, int lane, unsigned lt_mask) {
+  uint32_t ck[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) ck[j] = (j * 32 + lane < cnt) ? ckey[j * 32 + lane] : 0xffffffffu;
+  int c_lt;
+  const uint32_t tau = kth_smallest<NC>(ck, K, hi, &c_lt, lo);
+  const int need_ties = K - c_lt;
+  int n_out = 0, n_tie = 0;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    if (j * 32 >= cnt) break;  // warp-uniform
+    const bool is_tie = ck[j] == tau;
+    const unsigned tie_b = __ballot_sync(TB_FULL_MASK, is_tie);
+    const bool sel = (ck[j] < tau) || (is_tie && n_tie + __popc(tie_b & lt_mask) < need_ties);
+    const unsigned sel_b = __ballot_sync(TB_FULL_MASK, sel);
+    if (sel) emit(c, n_out + __popc(sel_b & lt_mask), cidx[j * 32 + lane]);
+    n_out += __popc(sel_b);
+    n_tie += __popc(tie_b);
+  }
+  return tau;
 }
 
 template <int TPL>
@@ -63,7 +90,8 @@ __global__ void __launch_bounds__(kWarps * 32)
 knn_select_kernel(const float* __restrict__ src_pose, const uint8_t* __restrict__ src_invalid,
                   const float* __restrict__ tgt_pose, const uint8_t* __restrict__ tgt_invalid, int S, int T, int div,
                   int K, float dist_limit, int32_t* __restrict__ out_idx, uint8_t* __restrict__ out_invalid,
-                  float* __restrict__ out_rel, int ldk, int koff) {
+                  float* __restrict__ out_rel, int ldk, int koff, const int32_t* __restrict__ tgt_index_map,
+                  float* __restrict__ row_state, int sorted_by_x) {
   extern __shared__ float smem[];
   float* tx = smem;
   float* ty = tx + T;
@@ -77,6 +105,7 @@ knn_select_kernel(const float* __restrict__ src_pose, const uint8_t* __restrict_
   const int bt = b / div;
   const float* tp = tgt_pose + (size_t)bt * T * 3;
   const uint8_t* ti = tgt_invalid + (size_t)bt * T;
+  const int32_t* tmap = tgt_index_map ? tgt_index_map + (size_t)bt * T : nullptr;
   for (int i = threadIdx.x; i < T; i += blockDim.x) {
     tx[i] = tp[i * 3 + 0];
     ty[i] = tp[i * 3 + 1];
@@ -100,12 +129,71 @@ knn_select_kernel(const float* __restrict__ src_pose, const uint8_t* __restrict_
     c.sinv = src_invalid[row] != 0;
     sincosf(c.syaw, &c.sn, &c.cs);
     c.dist_limit = dist_limit; c.tx = tx; c.ty = ty; c.tyaw = tyaw; c.tinv = tinv;
-    c.out_idx = out_idx; c.out_invalid = out_invalid; c.out_rel = out_rel;
+    c.out_idx = out_idx; c.out_invalid = out_invalid; c.out_rel = out_rel; c.tmap = tmap;
     c.obase = row * (size_t)ldk + koff;
+    float* rs = row_state ? row_state + row * 3 : nullptr;  // (x, y, K-th smallest squared distance) of the last call
 
     if (c.sinv) {  // invalid source: every distance is +inf, the (always masked) fillers are targets 0..K-1
       for (int pos = lane; pos < K; pos += 32) emit(c, pos, pos);
+      if (rs && lane == 0) rs[2] = __int_as_float(0x7f800000);
       continue;
+    }
+
+    // ---- temporal-coherence fast path (static targets sorted by x, e.g. agent -> map): at least K valid targets lay
+    // within sqrt(kth_prev) of the previous source position, so they lie within r = sqrt(kth_prev) + |displacement|
+    // of the current one (triangle inequality): the K nearest are among the targets with |x - sx| <= r and d <= r.
+    // Only that x-slab is scanned (binary search in the staged, x-sorted coordinates); everything else is unchanged.
+    if (rs && sorted_by_x && TPL >= 8) {
+      const float kprev = rs[2];
+      if (kprev < 3.0e38f) {
+        const float ddx = c.sx - rs[0], ddy = c.sy - rs[1];
+        const float r = (sqrtf(kprev) + sqrtf(fmaf(ddx, ddx, ddy * ddy))) * 1.00001f + 1e-3f;
+        const float r2 = r * r;
+        int lo = 0, hi = T;  // lo = first t with tx[t] >= sx - r, hi = first t with tx[t] > sx + r
+        {
+          int a = 0, b2 = T;
+          const float xl = c.sx - r, xh = c.sx + r;
+          while (a < b2) { const int m = (a + b2) >> 1; if (tx[m] < xl) a = m + 1; else b2 = m; }
+          lo = a;
+          b2 = T;
+          while (a < b2) { const int m = (a + b2) >> 1; if (tx[m] <= xh) a = m + 1; else b2 = m; }
+          hi = a;
+        }
+        __syncwarp();
+        int cnt = 0;
+        bool overflow = false;
+        for (int base = lo; base < hi; base += 32) {  // warp-uniform bounds
+          const int t = base + lane;
+          uint32_t k = 0xffffffffu;
+          if (t < hi) {
+            const float dx = tx[t] - c.sx, dy = ty[t] - c.sy;
+            k = tinv[t] ? 0x7f800000u : __float_as_uint(fmaf(dx, dx, dy * dy));
+          }
+          const bool sel = k <= __float_as_uint(r2);
+          const unsigned sb = __ballot_sync(TB_FULL_MASK, sel);
+          if (cnt + __popc(sb) > kCap * 32) { overflow = true; break; }
+          if (sel) {
+            const int p = cnt + __popc(sb & lt_mask);
+            ckey[p] = k;
+            cidx[p] = (uint16_t)t;
+          }
+          cnt += __popc(sb);
+        }
+        __syncwarp();
+        if (!overflow && cnt >= K) {
+          // the K-th distance cannot have shrunk by more than the displacement either: bracket for the bisection
+          const float dl = (sqrtf(kprev) - sqrtf(fmaf(ddx, ddx, ddy * ddy))) * 0.9999f - 1e-3f;
+          const uint32_t lo_bits = dl > 0.f ? __float_as_uint(dl * dl) : 0u;
+          uint32_t tau;
+          if (cnt <= 4 * 32) {  // the usual case: K + a few survivors
+            tau = select_from_list<4>(c, ckey, cidx, cnt, K, lo_bits, __float_as_uint(r2), lane, lt_mask);
+          } else {
+            tau = select_from_list<kCap>(c, ckey, cidx, cnt, K, lo_bits, __float_as_uint(r2), lane, lt_mask);
+          }
+          if (lane == 0) { rs[0] = c.sx; rs[1] = c.sy; rs[2] = __uint_as_float(tau); }
+          continue;
+        }
+      }
     }
 
     // selection keys of this lane's candidates t = i*32 + lane: squared distance (the rotation into the source frame
@@ -169,6 +257,7 @@ knn_select_kernel(const float* __restrict__ src_pose, const uint8_t* __restrict_
           n_out += __popc(sel_b);
           n_tie += __popc(tie_b);
         }
+        if (rs && lane == 0) { rs[0] = c.sx; rs[1] = c.sy; rs[2] = __uint_as_float(tau); }
         done = true;
       }
     }
@@ -189,17 +278,20 @@ knn_select_kernel(const float* __restrict__ src_pose, const uint8_t* __restrict_
       n_out += __popc(sel_b);
       n_tie += __popc(tie_b);
     }
+    if (rs && lane == 0) { rs[0] = c.sx; rs[1] = c.sy; rs[2] = __uint_as_float(tau); }
   }
 }
 
 template <int TPL>
 int launch(const float* src_pose, const uint8_t* src_invalid, const float* tgt_pose, const uint8_t* tgt_invalid,
            int B, int S, int T, int div, int K, float dist_limit, int32_t* out_idx, uint8_t* out_invalid,
-           float* out_rel, int ldk, int koff, cudaStream_t st) {
+           float* out_rel, int ldk, int koff, const int32_t* tgt_index_map, float* row_state, int sorted_by_x,
+           cudaStream_t st) {
   dim3 grid((S + kWarps * kRowsPerWarp - 1) / (kWarps * kRowsPerWarp), B);
   size_t smem = (size_t)T * 12 + ((T + 15) / 16) * 16 + (size_t)kWarps * kCap * 32 * 6;
   knn_select_kernel<TPL><<<grid, kWarps * 32, smem, st>>>(src_pose, src_invalid, tgt_pose, tgt_invalid, S, T, div, K,
-                                                         dist_limit, out_idx, out_invalid, out_rel, ldk, koff);
+                                                         dist_limit, out_idx, out_invalid, out_rel, ldk, koff,
+                                                         tgt_index_map, row_state, sorted_by_x);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }
@@ -209,7 +301,8 @@ int launch(const float* src_pose, const uint8_t* src_invalid, const float* tgt_p
 extern "C" int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float* tgt_pose,
                              const uint8_t* tgt_invalid, int B, int S, int T, int tgt_batch_div, int K,
                              float dist_limit, int32_t* out_idx, uint8_t* out_invalid, float* out_rel, int out_ldk,
-                             int out_koff, void* stream) {
+                             int out_koff, const int32_t* tgt_index_map, float* row_state, int sorted_by_x,
+                             void* stream) {
   if (!src_pose || !src_invalid || !tgt_pose || !tgt_invalid || !out_idx || !out_invalid || !out_rel)
     return TB_ERR_NULL;
   if (B <= 0 || S <= 0 || T <= 0 || tgt_batch_div <= 0 || out_koff < 0 || out_ldk < out_koff + K)
@@ -218,7 +311,7 @@ extern "C" int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, 
   if (B > 65535) return TB_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define TB_KNN_ARGS src_pose, src_invalid, tgt_pose, tgt_invalid, B, S, T, tgt_batch_div, K, dist_limit, out_idx, \
-                    out_invalid, out_rel, out_ldk, out_koff, st
+                    out_invalid, out_rel, out_ldk, out_koff, tgt_index_map, row_state, sorted_by_x, st
   if (T <= 64) return launch<2>(TB_KNN_ARGS);
   if (T <= 128) return launch<4>(TB_KNN_ARGS);
   if (T <= 256) return launch<8>(TB_KNN_ARGS);

@@ -174,6 +174,7 @@ class RolloutEngine:
                                       dtype=torch.float16 if self.model.kv_half else torch.float32)
                           for _ in range(self.cfg["ag_encoder"]["n_layer_tf"])] for _ in range(2)],
                   d_step_tl=z(1, dt=torch.int32),
+                  knn_state=z(B, A, 3),  # agent -> map select: (x, y, K-th squared distance) of the previous step
                   init_navi_valid=z(B, A, dt=torch.bool))
         if self.rule_checks:
             st.update(ag_size=z(n_sc, A, 3), passive_counter=z(B, A), seg=z(n_sc, n_mp, n_node, 4),
@@ -238,6 +239,7 @@ class RolloutEngine:
         st["hist_pose"][:, :, 0] = st["pose"]
         st["hist_motion"][:, :, 0] = st["motion"]
         st["hist_tl"][:, :, 0] = st["gt_tl"][:, :, 0]
+        st["knn_state"].fill_(float("inf"))
         st["d_step"].fill_(1)
         st["d_step_tl"].fill_(1)
         self._host_step = 1

@@ -53,7 +53,7 @@ def load() -> ctypes.CDLL:
     lib.tb_strerror.argtypes = [c_int]
     P, I, F = c_void_p, c_int, c_float
     sig = {
-        "tb_knn_select": [P, P, P, P, I, I, I, I, I, F, P, P, P, I, I, P],
+        "tb_knn_select": [P, P, P, P, I, I, I, I, I, F, P, P, P, I, I, P, P, I, P],
         "tb_knarpe_attn": [P, I, P, I, P, I, I, I, I, P, I, I, I, I, P, P, P, P, P, I, I, I, I, P, P, I, P, I, P],
         "tb_linear": [P, I, P, P, I, P, I, I, I, I, I, P, P, I, P, I, P, I, I, P],
         "tb_layernorm": [P, I, P, P, P, I, I, I, I, P],

@@ -264,8 +264,13 @@ class HotPathModel:
         flat_inv = tok_inv.reshape(-1).contiguous()
         for i in range(self.cfg["mp_encoder"]["n_layer_tf"]):
             tok = self.tf_layer(f"mp_encoder.tf_mp2mp.layers.{i}", "enc_self_attn", tok, flat_inv, n_sc, n_mp, knn)
+        # x-sorted copy of the (static) token poses for the per-step agent -> map select (tb_knn_select row_state)
+        order = torch.argsort(tok_pose[..., 0], dim=1)
         return dict(mp_token_invalid=tok_inv.contiguous(), mp_token_feature=tok.view(n_sc, n_mp, d),
-                    mp_token_pose=tok_pose, knn_mp2mp=knn)
+                    mp_token_pose=tok_pose, knn_mp2mp=knn,
+                    mp_sorted_pose=torch.gather(tok_pose, 1, order[..., None].expand(-1, -1, 3)).contiguous(),
+                    mp_sorted_invalid=torch.gather(tok_inv, 1, order).contiguous(),
+                    mp_sorted_index=order.to(torch.int32).contiguous())
 
     # ------------------------------------------------------------------------------------------ traffic lights
     def tl_pre_compute(self, tl_valid: Tensor, tl_attr: Tensor, tl_pose: Tensor, mp: Dict[str, Tensor]) -> dict:
@@ -363,8 +368,13 @@ class HotPathModel:
             ops.knn_select(tok_pose, tok_inv, tok_pose, tok_inv, Ka, sz["dl_ag"], out=(i_aa, m_aa, r_aa))
 
         def select_cross():
-            ops.knn_select(tok_pose, tok_inv, mp["mp_token_pose"], mp["mp_token_invalid"], sz["k_ag2mp"], sz["dl_ag"],
-                           tgt_div=R, out=(cidx, cinv, crel), koff=0)
+            if "knn_state" in st and "mp_sorted_pose" in mp:  # static targets + per-row state: x-slab fast path
+                ops.knn_select(tok_pose, tok_inv, mp["mp_sorted_pose"], mp["mp_sorted_invalid"], sz["k_ag2mp"],
+                               sz["dl_ag"], tgt_div=R, out=(cidx, cinv, crel), koff=0,
+                               index_map=mp["mp_sorted_index"], row_state=st["knn_state"], sorted_by_x=True)
+            else:
+                ops.knn_select(tok_pose, tok_inv, mp["mp_token_pose"], mp["mp_token_invalid"], sz["k_ag2mp"],
+                               sz["dl_ag"], tgt_div=R, out=(cidx, cinv, crel), koff=0)
             ops.knn_select(tok_pose, tok_inv, tl["tl_token_pose"], tl["tl_token_invalid"], sz["k_ag2tl"], sz["dl_ag"],
                            tgt_div=tl_div, out=(cidx, cinv, crel), koff=sz["k_ag2mp"])
 

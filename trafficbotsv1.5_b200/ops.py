@@ -40,7 +40,8 @@ def pe_freq_xy(pe_dim: int, theta: float = 1e3, device="cuda") -> Tensor:
 
 def knn_select(src_pose: Tensor, src_invalid: Tensor, tgt_pose: Tensor, tgt_invalid: Tensor, k: int,
                dist_limit: float, tgt_div: int = 1, out: Optional[Tuple[Tensor, Tensor, Tensor]] = None,
-               koff: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
+               koff: int = 0, index_map: Optional[Tensor] = None, row_state: Optional[Tensor] = None,
+               sorted_by_x: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """Fused get_rel_pose + get_tgt_knn_idx (utils/rpe.py:9-90). Returns idx int32 [B,S,K], invalid bool [B,S,K],
     rel [B,S,K,3]; with `out`/`koff` writes into columns koff..koff+K of preallocated [B,S,ldk(,3)] buffers."""
     B, S, _ = src_pose.shape
@@ -55,8 +56,13 @@ def knn_select(src_pose: Tensor, src_invalid: Tensor, tgt_pose: Tensor, tgt_inva
     else:
         idx, inv, rel = out
     ldk = idx.shape[2]
+    if index_map is not None:
+        assert index_map.dtype == torch.int32 and index_map.is_contiguous() and index_map.shape == tgt_pose.shape[:2]
+    if row_state is not None:
+        assert row_state.dtype == torch.float32 and row_state.is_contiguous() and row_state.shape == (B, S, 3)
     L.check(L.load().tb_knn_select(L.ptr(src_pose), L.ptr(si), L.ptr(tgt_pose), L.ptr(ti), B, S, T, tgt_div, k,
-                                   float(dist_limit), L.ptr(idx), L.ptr(_u8(inv)), L.ptr(rel), ldk, koff, L.stream()),
+                                   float(dist_limit), L.ptr(idx), L.ptr(_u8(inv)), L.ptr(rel), ldk, koff,
+                                   L.ptr(index_map), L.ptr(row_state), int(sorted_by_x), L.stream()),
             "tb_knn_select")
     _count()
     return idx, inv, rel
