@@ -53,7 +53,8 @@ int tb_version(void);
  *   sorted_by_x != 0: the caller promises tgt_pose[..,0] ascending within each target batch;
  *   row_state [B,S,3] f32 (in/out): (x, y, K-th smallest squared distance) of the previous call for the same row,
  *     K-th = +inf to start. With sorted targets only the slab |x_t - x_s| <= sqrt(K-th) + |displacement| is scanned
- *     (the K nearest of the previous call still lie within that radius: same result as a full scan).
+ *     (the K nearest of the previous call still lie within that radius: same result as a full scan). Without
+ *     sorted targets the state still brackets the bisection for the K-th distance. A row state REQUIRES static targets.
  * Limits: 0 < K < T <= 2048.
  * ------------------------------------------------------------------------------------------------- */
 int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float* tgt_pose,

@@ -263,9 +263,18 @@ knn_select_kernel(const float* __restrict__ src_pose, const uint8_t* __restrict_
     }
     if (done) continue;
 
-    // ---- general path: bisection over all T keys
+    // ---- general path: bisection over all T keys (bracketed by the previous call's K-th distance when the caller
+    // keeps a row state: static targets, so |sqrt(kth) - sqrt(kth_prev)| <= |displacement|)
+    uint32_t b_lo = 0u, b_hi = 0x7f800000u;
+    if (rs && rs[2] < 3.0e38f) {
+      const float ddx = c.sx - rs[0], ddy = c.sy - rs[1];
+      const float disp = sqrtf(fmaf(ddx, ddx, ddy * ddy)), dk = sqrtf(rs[2]);
+      const float dh = (dk + disp) * 1.00001f + 1e-3f, dl = (dk - disp) * 0.9999f - 1e-3f;
+      b_hi = __float_as_uint(dh * dh);
+      b_lo = dl > 0.f ? __float_as_uint(dl * dl) : 0u;
+    }
     int c_lt;
-    const uint32_t tau = kth_smallest<TPL>(key, K, 0x7f800000u, &c_lt);
+    const uint32_t tau = kth_smallest<TPL>(key, K, b_hi, &c_lt, b_lo);
     const int need_ties = K - c_lt;  // >= 1
     int n_out = 0, n_tie = 0;
 #pragma unroll

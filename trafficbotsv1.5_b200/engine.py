@@ -175,6 +175,7 @@ class RolloutEngine:
                           for _ in range(self.cfg["ag_encoder"]["n_layer_tf"])] for _ in range(2)],
                   d_step_tl=z(1, dt=torch.int32),
                   knn_state=z(B, A, 3),  # agent -> map select: (x, y, K-th squared distance) of the previous step
+                  knn_state_tl=z(B, A, 3),  # same for the agent -> traffic-light select
                   init_navi_valid=z(B, A, dt=torch.bool))
         if self.rule_checks:
             st.update(ag_size=z(n_sc, A, 3), passive_counter=z(B, A), seg=z(n_sc, n_mp, n_node, 4),
@@ -240,6 +241,7 @@ class RolloutEngine:
         st["hist_motion"][:, :, 0] = st["motion"]
         st["hist_tl"][:, :, 0] = st["gt_tl"][:, :, 0]
         st["knn_state"].fill_(float("inf"))
+        st["knn_state_tl"].fill_(float("inf"))
         st["d_step"].fill_(1)
         st["d_step_tl"].fill_(1)
         self._host_step = 1

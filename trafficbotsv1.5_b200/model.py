@@ -376,7 +376,8 @@ class HotPathModel:
                 ops.knn_select(tok_pose, tok_inv, mp["mp_token_pose"], mp["mp_token_invalid"], sz["k_ag2mp"],
                                sz["dl_ag"], tgt_div=R, out=(cidx, cinv, crel), koff=0)
             ops.knn_select(tok_pose, tok_inv, tl["tl_token_pose"], tl["tl_token_invalid"], sz["k_ag2tl"], sz["dl_ag"],
-                           tgt_div=tl_div, out=(cidx, cinv, crel), koff=sz["k_ag2mp"])
+                           tgt_div=tl_div, out=(cidx, cinv, crel), koff=sz["k_ag2mp"],
+                           row_state=st.get("knn_state_tl"))  # static targets too: bracketed bisection
 
         # The agent->agent list is needed by the first self-attention, the agent->map/TL lists only by the first
         # cross-attention: with two side streams the big map select also overlaps layer 0's projections + self-attn.
