@@ -545,6 +545,15 @@ class HotPathModel:
             else:
                 self.mlp(z, f"{prefix}.mlp_in", (0, 3, 6), True, mask_post=zinv, out=cat_in[:, d:])
             h = self.mlp(cat_in, f"{prefix}.mlp", (0, 3, 6), True, mask_pre=zinv, res=cat_in[:, :d], out=cat_out)
+        if self.kv_half:  # tensor-core mode: the two hidden layers of the 3 type branches as fp16 rows
+            h0 = torch.empty(M, 3 * d, dtype=torch.float16, device=self.dev)
+            ops.linear(h, self.act_w0, self.act_b0, relu=True, precision=1, out_h=h0, col_h=0)       # action_head.py:78-82
+            h1 = torch.empty_like(h0)
+            for t in range(3):
+                nm = f"action_head.mlp_mean.{t}.fc_layers.2"
+                ops.linear(h0[:, t * d:(t + 1) * d], self._half(nm, self.P[f"{nm}.weight"]), self.P[f"{nm}.bias"],
+                           relu=True, precision=2, out_h=h1[:, t * d:(t + 1) * d], col_h=0)
+            return ops.linear(h1, self._half("action_head.w4", self.act_w4), self.act_b4, precision=2)
         h0 = ops.linear(h, self.act_w0, self.act_b0, relu=True, precision=self.precision)            # action_head.py:78-82
         h1 = torch.empty_like(h0)
         for t in range(3):
