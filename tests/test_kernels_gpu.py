@@ -183,12 +183,16 @@ def test_pointnet(golden_ops):
 
 
 # ------------------------------------------------------------------------------------------------ KNARPE attention
-def _run_attention(sd, src, tgt, mask, rel, use_emb=False, half_kv=False, **flags):
+def _run_attention(sd, src, tgt, mask, rel, use_emb=False, half_kv=False, half_qu=False, **flags):
     """AttentionRPE semantics with an arbitrary pre-gathered tgt [B,S,K,d]: table = tgt flattened, idx = s*K+k."""
     B, S, K, d = tgt.shape
     P = {f"a.{k}": v for k, v in sd.items()}
     f = {k: v.to(DEV) for k, v in fuse_attention(P, "a", d).items()}
-    proj = ops.linear(src.reshape(B * S, d).to(DEV), f["w_in_q"], f["b_in_q"])
+    if half_qu:  # fp16 [q|u] rows straight from the projection's epilogue (tensor-core mode)
+        proj = torch.empty(B * S, d + H * d, dtype=torch.float16, device=DEV)
+        ops.linear(src.reshape(B * S, d).to(DEV), f["w_in_q"], f["b_in_q"], precision=1, out_h=proj, col_h=0)
+    else:
+        proj = ops.linear(src.reshape(B * S, d).to(DEV), f["w_in_q"], f["b_in_q"])
     if half_kv:  # tensor-core mode: the projection writes the fp16 table (tf32 MMA), the attention runs on mma.sync
         kv = torch.empty(B * S * K, 2 * d, dtype=torch.float16, device=DEV)
         ops.linear(tgt.reshape(B * S * K, d).to(DEV), f["w_kv"], f["b_kv"], precision=1, out_h=kv, col_h=0)
@@ -621,3 +625,30 @@ def test_knn_select_temporal_slab_path_exact():
         assert torch.equal(rr0, rr1)
         assert bool(m1[~ok].all())
     assert bool(torch.isfinite(state[..., 2][ok]).all())  # the fast path was armed
+
+
+@pytest.mark.parametrize("B,S,K,p_mask", [(3, 33, 25, 0.2), (1, 7, 32, 0.0), (2, 40, 9, 0.5), (1, 64, 25, 0.9), (5, 1, 3, 0.3),
+                                          (2, 30, 50, 0.3)])
+def test_attention_tensor_core_fp16_operands(B, S, K, p_mask):
+    """fp16 [q|u] rows + fp16 K|V tables: lists of <= 32 candidates take the two-tokens-per-warp kernel (odd token
+    counts, a single token, empty and ragged lists of the two tokens of a warp), longer ones the one-token kernel."""
+    d = 128
+    g = torch.Generator().manual_seed(K * 7 + S)
+    shapes = {"in_proj_weight": (3 * d, d), "in_proj_bias": (3 * d,), "out_proj_weight": (d, d), "out_proj_bias": (d,),
+              "linear_rpe.weight": (2 * d, d), "linear_rpe.bias": (2 * d,)}
+    sd = params.rand_like_state_dict(shapes, 23)
+    src, tgt = torch.randn(B, S, d, generator=g), torch.randn(B, S, K, d, generator=g)
+    mask = torch.rand(B, S, K, generator=g) < p_mask
+    mask[0, 0] = True
+    if S > 2:
+        mask[-1, -2, 1:] = True  # one valid neighbour next to a fuller list
+    rel = torch.cat([(torch.rand(B, S, K, 2, generator=g) * 2 - 1) * 300, (torch.rand(B, S, K, 1, generator=g) * 2 - 1) * 3.2], -1)
+    P = {f"a.{k}": v for k, v in sd.items()}
+    ref = O.attention_rpe(P, "a", src, tgt, mask, O.pose_emb_xy_yaw(rel[..., :2], rel[..., 2], d), H)
+    out, nv = _run_attention(sd, src, tgt, mask, rel, half_kv=True, half_qu=True, fast_trig=True)
+    scale = float(ref.abs().max())
+    err = float((out.cpu() - ref).abs().max()) / scale
+    print(f"fp16-operand attention B={B} S={S} K={K}: max err / scale {err:.2e}, rel_l2 {rel_l2(out, ref):.2e}")
+    close(out, ref, 4e-3, 4e-3 * scale, "fp16-operand tensor-core attention vs oracle")
+    assert rel_l2(out, ref) < 1.5e-3
+    assert torch.equal(nv.cpu(), mask.all(-1)) and float(out[0, 0].abs().max()) == 0.0

@@ -39,6 +39,9 @@ namespace {
 #ifndef TB_MMA_MINB
 #define TB_MMA_MINB 3
 #endif
+#ifndef TB_MMA_PAIR_MAX_K
+#define TB_MMA_PAIR_MAX_K 32  // lists up to this length (fp16 q/u, one table) use the two-tokens-per-warp kernel
+#endif
 constexpr int kWarps = TB_MMA_WARPS;
 constexpr int D = 128;
 constexpr int H = 4;
@@ -400,6 +403,304 @@ knarpe_attn_mma_kernel(const void* __restrict__ q_, int ldq, const void* __restr
   if (lane == 0 && out_none_valid) out_none_valid[tok] = nvalid > 0 ? 0 : 1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two tokens per warp for SHORT neighbour lists (agent self-attention, K = 25): MMA rows 0-7 are 8 neighbours of token
+// A, rows 8-15 are 8 neighbours of token B; B-operand columns 0-3 carry A's heads, columns 4-7 carry B's (fp16 q / u:
+// no residual columns needed). Every MMA then serves both tokens: logits rows 0-7 x cols 0-3 and rows 8-15 x cols 4-7
+// are the useful blocks, p^T is block structured (zero cross blocks), so z^T / ov^T columns 0-3 accumulate A's and
+// columns 4-7 B's outputs. Lanes t < 2 own token A (heads 2t, 2t+1), lanes t >= 2 token B (heads 2(t-2), +1).
+// Versus one token per warp: 8-neighbour granularity (24 instead of 32 slots for 21 valid neighbours) and the
+// per-token set-up / epilogue shared by two tokens. Needs fp16 q / u rows, a single K|V table, K0 <= 64.
+constexpr int KPAIR = 64;  // compacted neighbour slots per token
+constexpr int kPairSmem = 2 * (D + H * D) * 4;  // 2 x 640-float output staging; the two neighbour lists live in it first
+static_assert(kPairSmem >= 2 * (KPAIR * 8 + KPAIR * 12), "neighbour lists must fit");
+
+template <bool OUT_H>
+__global__ void __launch_bounds__(kWarps * 32, TB_MMA_MINB)
+knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ u, int ldu,
+                            const __half* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
+                            const int32_t* __restrict__ idx, const uint8_t* __restrict__ invalid,
+                            const float* __restrict__ rel, const float* __restrict__ pe_freq_xy, int n_tok, int S,
+                            void* __restrict__ out_ov_, void* __restrict__ out_z_, int ldo,
+                            uint8_t* __restrict__ out_none_valid) {
+  __shared__ __align__(16) unsigned char s_raw[kWarps][kPairSmem];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tok0 = (blockIdx.x * kWarps + warp) * 2;
+  if (tok0 >= n_tok) return;  // warp-uniform
+  const bool has_b = tok0 + 1 < n_tok;
+  const __half** s_ptr = reinterpret_cast<const __half**>(s_raw[warp]);               // [2][KPAIR]
+  float (*s_rel)[3] = reinterpret_cast<float (*)[3]>(s_raw[warp] + 2 * KPAIR * 8);     // [2][KPAIR]
+  float* s_out = reinterpret_cast<float*>(s_raw[warp]);                                // epilogue: 2 x [ov | z]
+
+  const int g = lane >> 2, t = lane & 3;
+  const int hA = g & 3;          // operand column g: head hA of token (g >> 2)
+  const int my = t >> 1;         // token whose softmax state / accumulator columns this lane owns
+  const int h0 = 2 * (t & 1);    // its heads h0, h0 + 1
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // ---- neighbour lists of both tokens: lanes 0-31 cover K0 <= 64 candidates of a token in two chunks
+  int nvalid[2] = {0, 0};
+  float fq[2][2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    fq[c][0] = __ldg(pe_freq_xy + 8 * c + 2 * t);
+    fq[c][1] = __ldg(pe_freq_xy + 8 * c + 2 * t + 1);
+  }
+  uint8_t n_inv[2][2];
+  int n_id[2][2];
+  float n_rel[2][2][3];
+#pragma unroll
+  for (int tk = 0; tk < 2; ++tk)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int j = c * 32 + lane;
+      n_inv[tk][c] = 1; n_id[tk][c] = 0; n_rel[tk][c][0] = n_rel[tk][c][1] = n_rel[tk][c][2] = 0.f;
+      if ((tk == 0 || has_b) && c * 32 < K0 && j < K0) {
+        const size_t p = (size_t)(tok0 + tk) * K0 + j;
+        n_inv[tk][c] = __ldg(invalid + p);
+        n_id[tk][c] = __ldg(idx + p);
+        n_rel[tk][c][0] = __ldg(rel + p * 3 + 0);
+        n_rel[tk][c][1] = __ldg(rel + p * 3 + 1);
+        n_rel[tk][c][2] = __ldg(rel + p * 3 + 2);
+      }
+    }
+  // B fragments: column g takes head hA of token g >> 2 (token B absent: zeros)
+  uint32_t uB[8][2], qB[2][2];
+  {
+    const int tkc = g >> 2;
+    const bool live = tkc == 0 || has_b;
+    const __half* up = u + (size_t)(tok0 + (live ? tkc : 0)) * ldu + hA * D + 2 * t;
+    const __half* qp = q + (size_t)(tok0 + (live ? tkc : 0)) * ldq + 32 * hA + 8 * t;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uB[c][0] = live ? __ldg(reinterpret_cast<const uint32_t*>(up + cos_base(c))) : 0u;
+      uB[c][1] = live ? __ldg(reinterpret_cast<const uint32_t*>(up + sin_base(c))) : 0u;
+    }
+    const uint4 qq = live ? __ldg(reinterpret_cast<const uint4*>(qp)) : make_uint4(0u, 0u, 0u, 0u);
+    qB[0][0] = qq.x; qB[0][1] = qq.y; qB[1][0] = qq.z; qB[1][1] = qq.w;
+  }
+  const __half* kb[2];
+#pragma unroll
+  for (int tk = 0; tk < 2; ++tk) {
+    const int b = (tok0 + (tk && has_b ? 1 : 0)) / S;
+    kb[tk] = kv0 + (size_t)(b / div0) * T0 * ldkv0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      if (c * 32 < K0) {  // warp-uniform
+        const bool valid = n_inv[tk][c] == 0;
+        const unsigned vb = __ballot_sync(TB_FULL_MASK, valid);
+        if (valid) {
+          const int pos = tk * KPAIR + nvalid[tk] + __popc(vb & lt_mask);
+          s_ptr[pos] = kb[tk] + (size_t)n_id[tk][c] * ldkv0;
+          s_rel[pos][0] = n_rel[tk][c][0];
+          s_rel[pos][1] = n_rel[tk][c][1];
+          s_rel[pos][2] = n_rel[tk][c][2];
+        }
+        nvalid[tk] += __popc(vb);
+      }
+    }
+    const int npad_t = (nvalid[tk] + 7) & ~7;
+    if (lane < npad_t - nvalid[tk]) {  // weight-0 dummies up to a multiple of 8
+      s_ptr[tk * KPAIR + nvalid[tk] + lane] = kb[tk];
+      s_rel[tk * KPAIR + nvalid[tk] + lane][0] = 0.f;
+      s_rel[tk * KPAIR + nvalid[tk] + lane][1] = 0.f;
+      s_rel[tk * KPAIR + nvalid[tk] + lane][2] = 0.f;
+    }
+  }
+  const int npad = max((nvalid[0] + 7) & ~7, (nvalid[1] + 7) & ~7);
+  // a token whose list is shorter than the other's keeps reading (masked) dummies: fill the rest of its list
+  for (int tk = 0; tk < 2; ++tk)
+    for (int j = ((nvalid[tk] + 7) & ~7) + lane; j < npad; j += 32) {
+      s_ptr[tk * KPAIR + j] = kb[tk];
+      s_rel[tk * KPAIR + j][0] = 0.f; s_rel[tk * KPAIR + j][1] = 0.f; s_rel[tk * KPAIR + j][2] = 0.f;
+    }
+  __syncwarp();
+
+  float zacc[8][4], oacc[2][4];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) zacc[c][r] = 0.f;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) oacc[m][r] = 0.f;
+  float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f};  // heads h0, h0+1 of token `my`
+  const int my_nvalid = my ? nvalid[1] : nvalid[0];
+
+  for (int g0 = 0; g0 < npad; g0 += 8) {
+    const __half* rowp[2];
+    uint4 kf[2][4];
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+      rowp[tile] = s_ptr[tile * KPAIR + g0 + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) kf[tile][i] = ldg128(rowp[tile] + 32 * i + 8 * t);
+    }
+    uint32_t eA[8][4];
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+      const float* rp = s_rel[tile * KPAIR + g0 + g];
+      const float x = rp[0], y = rp[1], w = rp[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float s0, c0, s1, c1;
+        __sincosf(x * fq[c][0], &s0, &c0);
+        __sincosf(x * fq[c][1], &s1, &c1);
+        eA[c][tile] = pack_h2(c0, c1);
+        eA[c][2 + tile] = pack_h2(s0, s1);
+        __sincosf(y * fq[c][0], &s0, &c0);
+        __sincosf(y * fq[c][1], &s1, &c1);
+        eA[2 + c][tile] = pack_h2(c0, c1);
+        eA[2 + c][2 + tile] = pack_h2(s0, s1);
+      }
+      float cA, sA, c1, s1, c8, s8;
+      __sincosf(w * (float)(2 * t + 1), &sA, &cA);
+      __sincosf(w, &s1, &c1);
+      __sincosf(w * 8.f, &s8, &c8);
+      float2 cv = make_float2(cA, fmaf(cA, c1, -sA * s1)), sv = make_float2(sA, fmaf(sA, c1, cA * s1));
+      const float2 c8v = make_float2(c8, c8), s8v = make_float2(s8, s8), ns8v = make_float2(-s8, -s8);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        eA[4 + cc][tile] = pack_h2(cv.x, cv.y);
+        eA[4 + cc][2 + tile] = pack_h2(sv.x, sv.y);
+        if (cc < 3) {
+          const float2 nc = __ffma2_rn(cv, c8v, __fmul2_rn(sv, ns8v));
+          sv = __ffma2_rn(sv, c8v, __fmul2_rn(cv, s8v));
+          cv = nc;
+        }
+      }
+    }
+    // ---- logits: rows 0-7 x cols 0-3 (token A) and rows 8-15 x cols 4-7 (token B) are the useful blocks
+    float sc[4] = {0.f, 0.f, 0.f, 0.f}, sc1[4] = {0.f, 0.f, 0.f, 0.f}, sc2[4] = {0.f, 0.f, 0.f, 0.f},
+          sc3[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mma16816((c & 1) ? sc1 : sc, eA[c][0], eA[c][1], eA[c][2], eA[c][3], uB[c][0], uB[c][1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool mine = hA == i;
+      mma16816(sc2, kf[0][i].x, kf[1][i].x, kf[0][i].y, kf[1][i].y, mine ? qB[0][0] : 0u, mine ? qB[0][1] : 0u);
+      mma16816(sc3, kf[0][i].z, kf[1][i].z, kf[0][i].w, kf[1][i].w, mine ? qB[1][0] : 0u, mine ? qB[1][1] : 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) sc[r] = (sc[r] + sc1[r]) + (sc2[r] + sc3[r]);
+
+    uint4 vf[2][4];
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vf[tile][i] = ldg128(rowp[tile] + D + 32 * i + 8 * t);
+
+    // ---- softmax of this lane's token (row block `my`), heads h0 / h0+1, over the 8 rows (lanes with the same t)
+    const bool row_ok = g0 + g < my_nvalid;
+    float lg[2], p[2];
+    bool grew = false;
+    float mn[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      lg[j] = row_ok ? (my ? sc[2 + j] : sc[j]) : -INFINITY;
+      float gm = lg[j];
+      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 4));
+      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 8));
+      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 16));
+      mn[j] = fmaxf(mx[j], gm);
+      p[j] = row_ok ? ex2(lg[j] - mn[j]) : 0.f;  // mn is finite whenever row_ok
+      float s = p[j];
+      s += __shfl_xor_sync(TB_FULL_MASK, s, 4);
+      s += __shfl_xor_sync(TB_FULL_MASK, s, 8);
+      s += __shfl_xor_sync(TB_FULL_MASK, s, 16);
+      lg[j] = s;  // reuse: group sum
+      grew |= mn[j] > mx[j];
+    }
+    if (__any_sync(TB_FULL_MASK, grew)) {
+      const float ca = mn[0] > mx[0] ? ex2(mx[0] - mn[0]) : 1.f, cb = mn[1] > mx[1] ? ex2(mx[1] - mn[1]) : 1.f;
+      mx[0] = mn[0]; mx[1] = mn[1];
+      sm[0] *= ca; sm[1] *= cb;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { zacc[c][0] *= ca; zacc[c][1] *= cb; zacc[c][2] *= ca; zacc[c][3] *= cb; }
+#pragma unroll
+      for (int m = 0; m < 2; ++m) { oacc[m][0] *= ca; oacc[m][1] *= cb; oacc[m][2] *= ca; oacc[m][3] *= cb; }
+    }
+    sm[0] += lg[0];
+    sm[1] += lg[1];
+    // p^T B fragment: tile 0 = rows 0-7 (token A's neighbours) has values only in columns 0-3 (lanes t < 2), tile 1
+    // only in columns 4-7 (lanes t >= 2)
+    const uint32_t pk = pack_h2(p[0], p[1]);
+    const uint32_t pB0 = movm_trans(my == 0 ? pk : 0u), pB1 = movm_trans(my == 1 ? pk : 0u);
+
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t a0 = movm_trans(eA[c][0]), a1 = movm_trans(eA[c][2]);
+      const uint32_t a2 = movm_trans(eA[c][1]), a3 = movm_trans(eA[c][3]);
+      mma16816(zacc[c], a0, a1, a2, a3, pB0, pB1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool mine = hA == i;
+      const uint32_t b0 = mine ? pB0 : 0u, b1 = mine ? pB1 : 0u;
+      {
+        const uint32_t a0 = movm_trans(vf[0][i].x), a1 = movm_trans(vf[0][i].y);
+        const uint32_t a2 = movm_trans(vf[1][i].x), a3 = movm_trans(vf[1][i].y);
+        mma16816(oacc[0], a0, a1, a2, a3, b0, b1);
+      }
+      {
+        const uint32_t a0 = movm_trans(vf[0][i].z), a1 = movm_trans(vf[0][i].w);
+        const uint32_t a2 = movm_trans(vf[1][i].z), a3 = movm_trans(vf[1][i].w);
+        mma16816(oacc[1], a0, a1, a2, a3, b0, b1);
+      }
+    }
+  }
+
+  // ---- epilogue: lanes t < 2 hold token A's columns, t >= 2 token B's; staging block per token
+  const float ia = sm[0] > 0.f ? 1.f / sm[0] : 0.f, ib = sm[1] > 0.f ? 1.f / sm[1] : 0.f;
+  __syncwarp();
+  {
+    float* so = s_out + my * (D + H * D);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int cp = 8 * (g >> 1) + 4 * m + (g & 1);
+      so[32 * h0 + cp] = oacc[m][0] * ia;
+      so[32 * (h0 + 1) + cp] = oacc[m][1] * ib;
+      so[32 * h0 + cp + 2] = oacc[m][2] * ia;
+      so[32 * (h0 + 1) + cp + 2] = oacc[m][3] * ib;
+    }
+    float* zs = so + D + g;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      zs[h0 * D + cos_base(c)] = zacc[c][0] * ia;
+      zs[(h0 + 1) * D + cos_base(c)] = zacc[c][1] * ib;
+      zs[h0 * D + sin_base(c)] = zacc[c][2] * ia;
+      zs[(h0 + 1) * D + sin_base(c)] = zacc[c][3] * ib;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int tk = 0; tk < 2; ++tk) {
+    if (tk == 1 && !has_b) break;  // warp-uniform
+    const int tok = tok0 + tk;
+    const float* so = s_out + tk * (D + H * D);
+    if (OUT_H) {
+      auto to_h4 = [](const float* pp) {
+        const float4 v = *reinterpret_cast<const float4*>(pp);
+        return make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
+      };
+      __half* ov_h = static_cast<__half*>(out_ov_) + (size_t)tok * ldo + lane * 4;
+      __half* z_h = static_cast<__half*>(out_z_) + (size_t)tok * ldo + lane * 4;
+      *reinterpret_cast<uint2*>(ov_h) = to_h4(so + lane * 4);
+#pragma unroll
+      for (int k = 0; k < H; ++k) *reinterpret_cast<uint2*>(z_h + k * D) = to_h4(so + D + k * D + lane * 4);
+    } else {
+      float* ovp = static_cast<float*>(out_ov_) + (size_t)tok * ldo + lane * 4;
+      float* zp = static_cast<float*>(out_z_) + (size_t)tok * ldo + lane * 4;
+      *reinterpret_cast<float4*>(ovp) = *reinterpret_cast<const float4*>(so + lane * 4);
+#pragma unroll
+      for (int k = 0; k < H; ++k)
+        *reinterpret_cast<float4*>(zp + k * D) = *reinterpret_cast<const float4*>(so + D + k * D + lane * 4);
+    }
+    if (lane == 0 && out_none_valid) out_none_valid[tok] = nvalid[tk] > 0 ? 0 : 1;
+  }
+}
+
 }  // namespace
 
 // Called by tb_knarpe_attn (knarpe_attn.cu) after argument validation when flags bit 1 is set. kv tables are fp16
@@ -411,6 +712,19 @@ int tb_knarpe_attn_mma_launch(const void* q, int ldq, const void* u, int ldu, in
                               cudaStream_t st) {
   const int n_tok = B * S;
   const int grid = (n_tok + kWarps - 1) / kWarps;
+  if (in_f16 && K1 == 0 && K0 <= TB_MMA_PAIR_MAX_K) {  // short lists: two tokens per warp
+    const int grid2 = (n_tok + 2 * kWarps - 1) / (2 * kWarps);
+    if (out_f16)
+      knarpe_attn_mma_pair_kernel<true><<<grid2, kWarps * 32, 0, st>>>(
+          static_cast<const __half*>(q), ldq, static_cast<const __half*>(u), ldu, static_cast<const __half*>(kv0), ldkv0,
+          T0, div0, K0, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid);
+    else
+      knarpe_attn_mma_pair_kernel<false><<<grid2, kWarps * 32, 0, st>>>(
+          static_cast<const __half*>(q), ldq, static_cast<const __half*>(u), ldu, static_cast<const __half*>(kv0), ldkv0,
+          T0, div0, K0, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid);
+    TB_CHECK_LAUNCH();
+    return TB_OK;
+  }
 #define TB_MMA_LAUNCH(OH, IH)                                                                                          \
   knarpe_attn_mma_kernel<OH, IH><<<grid, kWarps * 32, 0, st>>>(                                                        \
       q, ldq, u, ldu, static_cast<const __half*>(kv0), ldkv0, T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, \

@@ -62,7 +62,7 @@ class HotPathModel:
         self.cfg, self.sz, self.dev, self.precision = cfg, sizes, torch.device(device), precision
         self.d = cfg["hidden_dim"]
         self.kv_half = precision == 1 and self.d == 128  # fp16 K|V tables + tensor-core attention (tb_knarpe_attn bit 1)
-        self.mma_min_k = int(os.environ.get("TB_MMA_MIN_K", "33"))
+        self.mma_min_k = int(os.environ.get("TB_MMA_MIN_K", "0"))
         self.W = cfg["temp_window_size"]
         self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in P.items()}
         self.fa: Dict[str, Dict[str, Tensor]] = {}
@@ -87,7 +87,7 @@ class HotPathModel:
         self.cfg, self.sz, self.dev, self.precision = None, None, torch.device(device), precision
         self.d, self.W = d_model, None
         self.kv_half = precision == 1 and d_model == 128
-        self.mma_min_k = int(os.environ.get("TB_MMA_MIN_K", "33"))
+        self.mma_min_k = int(os.environ.get("TB_MMA_MIN_K", "0"))
         self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in sd.items()}
         self.fa = {}
         for k in sd:
