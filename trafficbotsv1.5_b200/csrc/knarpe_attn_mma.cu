@@ -40,7 +40,7 @@ namespace {
 #define TB_MMA_MINB 3
 #endif
 #ifndef TB_MMA_PAIR_MAX_K
-#define TB_MMA_PAIR_MAX_K 32  // lists up to this length (fp16 q/u, one table) use the two-tokens-per-warp kernel
+#define TB_MMA_PAIR_MAX_K 128  // lists up to this length (fp16 q/u rows) use the two-tokens-per-warp kernel
 #endif
 constexpr int kWarps = TB_MMA_WARPS;
 constexpr int D = 128;
@@ -410,8 +410,8 @@ knarpe_attn_mma_kernel(const void* __restrict__ q_, int ldq, const void* __restr
 // are the useful blocks, p^T is block structured (zero cross blocks), so z^T / ov^T columns 0-3 accumulate A's and
 // columns 4-7 B's outputs. Lanes t < 2 own token A (heads 2t, 2t+1), lanes t >= 2 token B (heads 2(t-2), +1).
 // Versus one token per warp: 8-neighbour granularity (24 instead of 32 slots for 21 valid neighbours) and the
-// per-token set-up / epilogue shared by two tokens. Needs fp16 q / u rows, a single K|V table, K0 <= 64.
-constexpr int KPAIR = 64;  // compacted neighbour slots per token
+// per-token set-up / epilogue shared by two tokens. Needs fp16 q / u rows and K0 + K1 <= 128.
+constexpr int KPAIR = 128;  // compacted neighbour slots per token
 constexpr int kPairSmem = 2 * (D + H * D) * 4;  // 2 x 640-float output staging; the two neighbour lists live in it first
 static_assert(kPairSmem >= 2 * (KPAIR * 8 + KPAIR * 12), "neighbour lists must fit");
 
@@ -419,11 +419,13 @@ template <bool OUT_H>
 __global__ void __launch_bounds__(kWarps * 32, TB_MMA_MINB)
 knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ u, int ldu,
                             const __half* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
+                            const __half* __restrict__ kv1, int ldkv1, int T1, int div1, int K1,
                             const int32_t* __restrict__ idx, const uint8_t* __restrict__ invalid,
                             const float* __restrict__ rel, const float* __restrict__ pe_freq_xy, int n_tok, int S,
                             void* __restrict__ out_ov_, void* __restrict__ out_z_, int ldo,
                             uint8_t* __restrict__ out_none_valid) {
   __shared__ __align__(16) unsigned char s_raw[kWarps][kPairSmem];
+  const int Ktot = K0 + K1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok0 = (blockIdx.x * kWarps + warp) * 2;
   if (tok0 >= n_tok) return;  // warp-uniform
@@ -446,17 +448,17 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
     fq[c][0] = __ldg(pe_freq_xy + 8 * c + 2 * t);
     fq[c][1] = __ldg(pe_freq_xy + 8 * c + 2 * t + 1);
   }
-  uint8_t n_inv[2][2];
-  int n_id[2][2];
-  float n_rel[2][2][3];
+  uint8_t n_inv[2][4];
+  int n_id[2][4];
+  float n_rel[2][4][3];
 #pragma unroll
   for (int tk = 0; tk < 2; ++tk)
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < 4; ++c) {
       const int j = c * 32 + lane;
       n_inv[tk][c] = 1; n_id[tk][c] = 0; n_rel[tk][c][0] = n_rel[tk][c][1] = n_rel[tk][c][2] = 0.f;
-      if ((tk == 0 || has_b) && c * 32 < K0 && j < K0) {
-        const size_t p = (size_t)(tok0 + tk) * K0 + j;
+      if ((tk == 0 || has_b) && c * 32 < Ktot && j < Ktot) {
+        const size_t p = (size_t)(tok0 + tk) * Ktot + j;
         n_inv[tk][c] = __ldg(invalid + p);
         n_id[tk][c] = __ldg(idx + p);
         n_rel[tk][c][0] = __ldg(rel + p * 3 + 0);
@@ -484,14 +486,16 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
   for (int tk = 0; tk < 2; ++tk) {
     const int b = (tok0 + (tk && has_b ? 1 : 0)) / S;
     kb[tk] = kv0 + (size_t)(b / div0) * T0 * ldkv0;
+    const __half* kb1 = (K1 > 0) ? kv1 + (size_t)(b / div1) * T1 * ldkv1 : kb[tk];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      if (c * 32 < K0) {  // warp-uniform
+    for (int c = 0; c < 4; ++c) {
+      if (c * 32 < Ktot) {  // warp-uniform
         const bool valid = n_inv[tk][c] == 0;
         const unsigned vb = __ballot_sync(TB_FULL_MASK, valid);
         if (valid) {
           const int pos = tk * KPAIR + nvalid[tk] + __popc(vb & lt_mask);
-          s_ptr[pos] = kb[tk] + (size_t)n_id[tk][c] * ldkv0;
+          s_ptr[pos] = (c * 32 + lane < K0) ? kb[tk] + (size_t)n_id[tk][c] * ldkv0
+                                             : kb1 + (size_t)n_id[tk][c] * ldkv1;
           s_rel[pos][0] = n_rel[tk][c][0];
           s_rel[pos][1] = n_rel[tk][c][1];
           s_rel[pos][2] = n_rel[tk][c][2];
@@ -712,16 +716,18 @@ int tb_knarpe_attn_mma_launch(const void* q, int ldq, const void* u, int ldu, in
                               cudaStream_t st) {
   const int n_tok = B * S;
   const int grid = (n_tok + kWarps - 1) / kWarps;
-  if (in_f16 && K1 == 0 && K0 <= TB_MMA_PAIR_MAX_K) {  // short lists: two tokens per warp
+  if (in_f16 && K0 + K1 <= TB_MMA_PAIR_MAX_K) {  // two tokens per warp
     const int grid2 = (n_tok + 2 * kWarps - 1) / (2 * kWarps);
     if (out_f16)
       knarpe_attn_mma_pair_kernel<true><<<grid2, kWarps * 32, 0, st>>>(
           static_cast<const __half*>(q), ldq, static_cast<const __half*>(u), ldu, static_cast<const __half*>(kv0), ldkv0,
-          T0, div0, K0, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid);
+          T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S,
+          out_ov, out_z, ldo, out_none_valid);
     else
       knarpe_attn_mma_pair_kernel<false><<<grid2, kWarps * 32, 0, st>>>(
           static_cast<const __half*>(q), ldq, static_cast<const __half*>(u), ldu, static_cast<const __half*>(kv0), ldkv0,
-          T0, div0, K0, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid);
+          T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S,
+          out_ov, out_z, ldo, out_none_valid);
     TB_CHECK_LAUNCH();
     return TB_OK;
   }
