@@ -181,7 +181,8 @@ def attention_roofline(eng, peaks):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["knarpe_attn_ag_cross_bytes"]
     except Exception:
         pass
-    kname = "knarpe_attn_mma_kernel" if kv_sz == 2 else "knarpe_attn_kernel<128,false>"
+    kname = ("knarpe_attn_mma_pair_kernel" if proj.element_size() == 2 else "knarpe_attn_mma_kernel") if kv_sz == 2 \
+        else "knarpe_attn_kernel<128,false>"
     return dict(bound="hbm", kernel=f"{kname} (agent cross-attn, K=89, {8 * kv_sz}-bit K|V / q|u / ov|z rows)", achieved=ach, peak=peak,
                 unit="GB/s", frac=ach / peak, traffic=traffic, us_per_launch=t * 1e6,
                 note="as-issued gather bytes are served by L2 (~85 % hit): DRAM traffic is a fraction of them; the "
