@@ -156,7 +156,7 @@ def attention_roofline(eng, peaks):
     def launch():
         ops.knarpe_attn(proj[:, :d], proj[:, d:], static["kv_mp"][0], n_mp, eng.R, sz["k_ag2mp"], aux["cidx"],
                         aux["cinv"], aux["crel"], m.freq_rpe, B, A, d, 4, kv1=kv_tl, T1=n_tl, div1=eng.R,
-                        K1=sz["k_ag2tl"], out=out, fast_trig=m.precision == 1)
+                        K1=sz["k_ag2tl"], out=out, fast_trig=m.precision == 1, interleaved=m.kv_il)
     for _ in range(3):
         launch()
     n = 20

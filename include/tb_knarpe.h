@@ -88,6 +88,12 @@ int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float
  *   Needs D == 128, rel != NULL and bit 0 (or bit 1).
  * flags bit 3: q / u are IEEE fp16 rows (ldq, ldu in halves, multiples of 8) as written by tb_linear's Yh output;
  *   with bit 1 they are MMA operands as they are (no residual). Needs bit 2 when bit 1 is not set.
+ * flags bit 4: head-interleaved channels. The q rows and the K and V halves of the table rows store channel c
+ *   (0..31) of head h at position 64*(h>>1) + 16*(c>>3) + 8*(h&1) + (c&7), so that a lane reads 32 contiguous bytes
+ *   (one 256-bit load) holding its MMA fragments of two heads - half the L1 wavefronts per gathered row. The caller
+ *   gets the layout for free by permuting the output features of the q / k / v projection weights; u, out_ov and
+ *   out_z keep the natural order. Needs bits 1 and 3, K0 + K1 <= 128, table pointers 32-byte aligned and table leading
+ *   dims multiples of 16 halves.
  * Limits: D in {128,256} (d_rpe == D), H == 4, all leading dims and pointers 16-byte aligned.
  * ------------------------------------------------------------------------------------------------- */
 int tb_knarpe_attn(const void* q, int ldq, const void* u, int ldu,

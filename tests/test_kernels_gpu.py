@@ -188,6 +188,14 @@ def _run_attention(sd, src, tgt, mask, rel, use_emb=False, half_kv=False, half_q
     B, S, K, d = tgt.shape
     P = {f"a.{k}": v for k, v in sd.items()}
     f = {k: v.to(DEV) for k, v in fuse_attention(P, "a", d).items()}
+    if flags.get("interleaved"):  # tb_knarpe_attn flags bit 4: q / k / v output features stored head-interleaved
+        from trafficbotsv1_5_b200.model import head_interleave_perm
+        perm = head_interleave_perm(d).to(DEV)
+        rq = torch.arange(d + H * d, device=DEV)
+        rq[:d] = perm
+        rkv = torch.cat([perm, d + perm])
+        f = dict(f, w_in_q=f["w_in_q"][rq].contiguous(), b_in_q=f["b_in_q"][rq].contiguous(),
+                 w_kv=f["w_kv"][rkv].contiguous(), b_kv=f["b_kv"][rkv].contiguous())
     if half_qu:  # fp16 [q|u] rows straight from the projection's epilogue (tensor-core mode)
         proj = torch.empty(B * S, d + H * d, dtype=torch.float16, device=DEV)
         ops.linear(src.reshape(B * S, d).to(DEV), f["w_in_q"], f["b_in_q"], precision=1, out_h=proj, col_h=0)
@@ -652,3 +660,40 @@ def test_attention_tensor_core_fp16_operands(B, S, K, p_mask):
     close(out, ref, 4e-3, 4e-3 * scale, "fp16-operand tensor-core attention vs oracle")
     assert rel_l2(out, ref) < 1.5e-3
     assert torch.equal(nv.cpu(), mask.all(-1)) and float(out[0, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,S,K,p_mask", [(3, 33, 25, 0.2), (1, 7, 32, 0.0), (5, 1, 3, 0.3), (2, 30, 50, 0.3), (2, 21, 128, 0.4)])
+def test_attention_head_interleaved_layout_is_bit_identical(B, S, K, p_mask):
+    """tb_knarpe_attn flags bit 4: permuting the q / k / v projection features into the head-interleaved order and
+    gathering rows with 256-bit loads feeds the MMAs the same fragments -> the same bits as the plain layout."""
+    d = 128
+    g = torch.Generator().manual_seed(K * 11 + S)
+    shapes = {"in_proj_weight": (3 * d, d), "in_proj_bias": (3 * d,), "out_proj_weight": (d, d), "out_proj_bias": (d,),
+              "linear_rpe.weight": (2 * d, d), "linear_rpe.bias": (2 * d,)}
+    sd = params.rand_like_state_dict(shapes, 29)
+    src, tgt = torch.randn(B, S, d, generator=g), torch.randn(B, S, K, d, generator=g)
+    mask = torch.rand(B, S, K, generator=g) < p_mask
+    mask[0, 0] = True
+    rel = torch.cat([(torch.rand(B, S, K, 2, generator=g) * 2 - 1) * 300, (torch.rand(B, S, K, 1, generator=g) * 2 - 1) * 3.2], -1)
+    a, nva = _run_attention(sd, src, tgt, mask, rel, half_kv=True, half_qu=True, fast_trig=True)
+    b, nvb = _run_attention(sd, src, tgt, mask, rel, half_kv=True, half_qu=True, fast_trig=True, interleaved=True)
+    assert torch.equal(a, b) and torch.equal(nva, nvb)
+    P = {f"a.{k}": v for k, v in sd.items()}
+    ref = O.attention_rpe(P, "a", src, tgt, mask, O.pose_emb_xy_yaw(rel[..., :2], rel[..., 2], d), H)
+    close(b, ref, 4e-3, 4e-3 * float(ref.abs().max()), "head-interleaved tensor-core attention vs oracle")
+
+
+def test_attention_head_interleaved_layout_argument_checks():
+    d, B, S, K = 128, 1, 4, 8
+    q = torch.zeros(B * S, d + H * d, dtype=torch.float16, device=DEV)
+    kv = torch.zeros(B * S * K + 1, 2 * d, dtype=torch.float16, device=DEV)
+    idx = torch.zeros(B, S, K, dtype=torch.int32, device=DEV)
+    inv = torch.zeros(B, S, K, dtype=torch.bool, device=DEV)
+    rel = torch.zeros(B, S, K, 3, device=DEV)
+    freq = ops.pe_freq_xy(d, 1e3, DEV)
+    with pytest.raises(RuntimeError):  # fp32 q rows: the layout needs flags bits 1 and 3
+        ops.knarpe_attn(q[:, :d].float(), q[:, d:].float(), kv, S * K, 1, K, idx, inv, rel, freq, B, S, d, H,
+                        interleaved=True, fast_trig=True)
+    with pytest.raises(RuntimeError):  # table base only 16-byte aligned
+        ops.knarpe_attn(q[:, :d], q[:, d:], kv.view(-1)[8:8 + B * S * K * 2 * d].view(-1, 2 * d), S * K, 1, K, idx, inv,
+                        rel, freq, B, S, d, H, interleaved=True, fast_trig=True)

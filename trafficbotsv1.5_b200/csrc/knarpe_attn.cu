@@ -328,7 +328,7 @@ int tb_knarpe_attn_mma_launch(const void* q, int ldq, const void* u, int ldu, in
                               int div0, int K0, const void* kv1, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* pe_freq_xy,
                               int B, int S, void* out_ov, void* out_z, int ldo, int out_f16, uint8_t* out_none_valid,
-                              cudaStream_t st);
+                              int interleaved, cudaStream_t st);
 bool tb_knarpe_attn_mma_supported(int D, int Hh, int Ktot);
 
 extern "C" int tb_knarpe_attn(const void* q, int ldq, const void* u, int ldu, const void* kv0_, int ldkv0, int T0,
@@ -358,9 +358,17 @@ extern "C" int tb_knarpe_attn(const void* q, int ldq, const void* u, int ldu, co
   if (flags & 2) {  // bit 1: fp16 K|V tables, all contractions on mma.sync (knarpe_attn_mma.cu)
     if (!rel || !tb_knarpe_attn_mma_supported(D, Hh, K0 + K1)) return TB_ERR_UNSUPPORTED;
     if ((ldkv0 | (K1 > 0 ? ldkv1 : 0)) & 7) return TB_ERR_MISALIGNED;
+    const int il = (flags & 16) != 0;  // bit 4: head-interleaved q / K / V channels, rows read 32 bytes per lane
+    if (il) {
+      if (!in_h) return TB_ERR_UNSUPPORTED;
+      if (((ldkv0 | (K1 > 0 ? ldkv1 : 0)) & 15) || (reinterpret_cast<uintptr_t>(kv0_) & 31) ||
+          (K1 > 0 && (reinterpret_cast<uintptr_t>(kv1_) & 31)))
+        return TB_ERR_MISALIGNED;
+    }
     return tb_knarpe_attn_mma_launch(q, ldq, u, ldu, in_h, kv0_, ldkv0, T0, div0, K0, kv1_, ldkv1, T1, div1, K1, idx,
-                                     invalid, rel, pe_freq_xy, B, S, out_ov, out_z, ldo, out_h, out_none_valid, st);
+                                     invalid, rel, pe_freq_xy, B, S, out_ov, out_z, ldo, out_h, out_none_valid, il, st);
   }
+  if (flags & 16) return TB_ERR_UNSUPPORTED;
   if (out_h || in_h) {  // fp16 intermediates with the SIMT kernel: the tensor-core mode's short neighbour lists
     if (D != 128 || !rel || !fast || !out_h) return TB_ERR_UNSUPPORTED;
     return in_h ? launch<128, false, true, true, true>(TB_ATT_ARGS) : launch<128, false, true, true, false>(TB_ATT_ARGS);

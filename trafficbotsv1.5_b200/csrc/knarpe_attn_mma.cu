@@ -415,7 +415,29 @@ constexpr int KPAIR = 128;  // compacted neighbour slots per token
 constexpr int kPairSmem = 2 * (D + H * D) * 4;  // 2 x 640-float output staging; the two neighbour lists live in it first
 static_assert(kPairSmem >= 2 * (KPAIR * 8 + KPAIR * 12), "neighbour lists must fit");
 
-template <bool OUT_H>
+// One 128-channel fp16 row into 16 registers per lane. Plain layout: four 128-bit pieces, piece i = head i, lane t
+// takes halves [32 i + 8 t, +8). Head-interleaved layout (IL): two 256-bit pieces, lane t takes halves
+// [64 i + 16 t, +16) whose first 8 belong to head 2 i and last 8 to head 2 i + 1 - half as many L1 wavefronts per row.
+// Either way registers 4 h .. 4 h + 3 hold head h, and the position inside the head is 8 t + (0..7).
+template <bool IL>
+__device__ __forceinline__ void load_row(uint32_t (&r)[16], const __half* row, int t) {
+  if (IL) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(r[8 * i]), "=r"(r[8 * i + 1]), "=r"(r[8 * i + 2]), "=r"(r[8 * i + 3]), "=r"(r[8 * i + 4]),
+                     "=r"(r[8 * i + 5]), "=r"(r[8 * i + 6]), "=r"(r[8 * i + 7])
+                   : "l"(row + 64 * i + 16 * t));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 v = ldg128(row + 32 * i + 8 * t);
+      r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+    }
+  }
+}
+
+template <bool OUT_H, bool IL>
 __global__ void __launch_bounds__(kWarps * 32, TB_MMA_MINB)
 knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ u, int ldu,
                             const __half* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
@@ -472,7 +494,8 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
     const int tkc = g >> 2;
     const bool live = tkc == 0 || has_b;
     const __half* up = u + (size_t)(tok0 + (live ? tkc : 0)) * ldu + hA * D + 2 * t;
-    const __half* qp = q + (size_t)(tok0 + (live ? tkc : 0)) * ldq + 32 * hA + 8 * t;
+    const __half* qp = q + (size_t)(tok0 + (live ? tkc : 0)) * ldq +
+                       (IL ? 64 * (hA >> 1) + 16 * t + 8 * (hA & 1) : 32 * hA + 8 * t);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       uB[c][0] = live ? __ldg(reinterpret_cast<const uint32_t*>(up + cos_base(c))) : 0u;
@@ -534,12 +557,11 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
 
   for (int g0 = 0; g0 < npad; g0 += 8) {
     const __half* rowp[2];
-    uint4 kf[2][4];
+    uint32_t kf[2][16];  // IL: two 256-bit pieces per row; else four 128-bit pieces (one per head)
 #pragma unroll
     for (int tile = 0; tile < 2; ++tile) {
       rowp[tile] = s_ptr[tile * KPAIR + g0 + g];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) kf[tile][i] = ldg128(rowp[tile] + 32 * i + 8 * t);
+      load_row<IL>(kf[tile], rowp[tile], t);
     }
     uint32_t eA[8][4];
 #pragma unroll
@@ -581,19 +603,19 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
 #pragma unroll
     for (int c = 0; c < 8; ++c) mma16816((c & 1) ? sc1 : sc, eA[c][0], eA[c][1], eA[c][2], eA[c][3], uB[c][0], uB[c][1]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 4; ++i) {  // either layout: registers 4i..4i+3 of a row belong to head i
       const bool mine = hA == i;
-      mma16816(sc2, kf[0][i].x, kf[1][i].x, kf[0][i].y, kf[1][i].y, mine ? qB[0][0] : 0u, mine ? qB[0][1] : 0u);
-      mma16816(sc3, kf[0][i].z, kf[1][i].z, kf[0][i].w, kf[1][i].w, mine ? qB[1][0] : 0u, mine ? qB[1][1] : 0u);
+      mma16816(sc2, kf[0][4 * i], kf[1][4 * i], kf[0][4 * i + 1], kf[1][4 * i + 1], mine ? qB[0][0] : 0u,
+               mine ? qB[0][1] : 0u);
+      mma16816(sc3, kf[0][4 * i + 2], kf[1][4 * i + 2], kf[0][4 * i + 3], kf[1][4 * i + 3], mine ? qB[1][0] : 0u,
+               mine ? qB[1][1] : 0u);
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) sc[r] = (sc[r] + sc1[r]) + (sc2[r] + sc3[r]);
 
-    uint4 vf[2][4];
+    uint32_t vf[2][16];
 #pragma unroll
-    for (int tile = 0; tile < 2; ++tile)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) vf[tile][i] = ldg128(rowp[tile] + D + 32 * i + 8 * t);
+    for (int tile = 0; tile < 2; ++tile) load_row<IL>(vf[tile], rowp[tile] + D, t);
 
     // ---- softmax of this lane's token (row block `my`), heads h0 / h0+1, over the 8 rows (lanes with the same t)
     const bool row_ok = g0 + g < my_nvalid;
@@ -643,13 +665,13 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
       const bool mine = hA == i;
       const uint32_t b0 = mine ? pB0 : 0u, b1 = mine ? pB1 : 0u;
       {
-        const uint32_t a0 = movm_trans(vf[0][i].x), a1 = movm_trans(vf[0][i].y);
-        const uint32_t a2 = movm_trans(vf[1][i].x), a3 = movm_trans(vf[1][i].y);
+        const uint32_t a0 = movm_trans(vf[0][4 * i]), a1 = movm_trans(vf[0][4 * i + 1]);
+        const uint32_t a2 = movm_trans(vf[1][4 * i]), a3 = movm_trans(vf[1][4 * i + 1]);
         mma16816(oacc[0], a0, a1, a2, a3, b0, b1);
       }
       {
-        const uint32_t a0 = movm_trans(vf[0][i].z), a1 = movm_trans(vf[0][i].w);
-        const uint32_t a2 = movm_trans(vf[1][i].z), a3 = movm_trans(vf[1][i].w);
+        const uint32_t a0 = movm_trans(vf[0][4 * i + 2]), a1 = movm_trans(vf[0][4 * i + 3]);
+        const uint32_t a2 = movm_trans(vf[1][4 * i + 2]), a3 = movm_trans(vf[1][4 * i + 3]);
         mma16816(oacc[1], a0, a1, a2, a3, b0, b1);
       }
     }
@@ -713,24 +735,25 @@ int tb_knarpe_attn_mma_launch(const void* q, int ldq, const void* u, int ldu, in
                               int div0, int K0, const void* kv1, int ldkv1, int T1, int div1, int K1,
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* pe_freq_xy,
                               int B, int S, void* out_ov, void* out_z, int ldo, int out_f16, uint8_t* out_none_valid,
-                              cudaStream_t st) {
+                              int interleaved, cudaStream_t st) {
   const int n_tok = B * S;
   const int grid = (n_tok + kWarps - 1) / kWarps;
   if (in_f16 && K0 + K1 <= TB_MMA_PAIR_MAX_K) {  // two tokens per warp
     const int grid2 = (n_tok + 2 * kWarps - 1) / (2 * kWarps);
-    if (out_f16)
-      knarpe_attn_mma_pair_kernel<true><<<grid2, kWarps * 32, 0, st>>>(
-          static_cast<const __half*>(q), ldq, static_cast<const __half*>(u), ldu, static_cast<const __half*>(kv0), ldkv0,
-          T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S,
-          out_ov, out_z, ldo, out_none_valid);
-    else
-      knarpe_attn_mma_pair_kernel<false><<<grid2, kWarps * 32, 0, st>>>(
-          static_cast<const __half*>(q), ldq, static_cast<const __half*>(u), ldu, static_cast<const __half*>(kv0), ldkv0,
-          T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S,
-          out_ov, out_z, ldo, out_none_valid);
+#define TB_PAIR_LAUNCH(OH, IL)                                                                                         \
+  knarpe_attn_mma_pair_kernel<OH, IL><<<grid2, kWarps * 32, 0, st>>>(                                                  \
+      static_cast<const __half*>(q), ldq, static_cast<const __half*>(u), ldu, static_cast<const __half*>(kv0), ldkv0,  \
+      T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S,     \
+      out_ov, out_z, ldo, out_none_valid)
+    if (out_f16 && interleaved) TB_PAIR_LAUNCH(true, true);
+    else if (out_f16) TB_PAIR_LAUNCH(true, false);
+    else if (interleaved) TB_PAIR_LAUNCH(false, true);
+    else TB_PAIR_LAUNCH(false, false);
+#undef TB_PAIR_LAUNCH
     TB_CHECK_LAUNCH();
     return TB_OK;
   }
+  if (interleaved) return TB_ERR_UNSUPPORTED;  // the head-interleaved layout is the pair kernel's
 #define TB_MMA_LAUNCH(OH, IH)                                                                                          \
   knarpe_attn_mma_kernel<OH, IH><<<grid, kWarps * 32, 0, st>>>(                                                        \
       q, ldq, u, ldu, static_cast<const __half*>(kv0), ldkv0, T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, \

@@ -55,6 +55,15 @@ def fuse_attention(P: Dict[str, Tensor], prefix: str, d: int, n_head: int = H) -
     return {k: v.float().contiguous() for k, v in out.items()}
 
 
+def head_interleave_perm(d: int = 128, n_head: int = H) -> Tensor:
+    """Row order of a q / k / v projection block for tb_knarpe_attn flags bit 4: position
+    64*(h>>1) + 16*(c>>3) + 8*(h&1) + (c&7) holds channel c of head h (d == 128, 4 heads of 32)."""
+    assert d == 128 and n_head == 4
+    s = torch.arange(d)
+    head = 2 * (s >> 6) + ((s >> 3) & 1)
+    return 32 * head + 8 * ((s >> 4) & 3) + (s & 7)
+
+
 class HotPathModel:
     """Device-resident weights + the kernel sequences of the hot-path modules."""
 
@@ -108,11 +117,32 @@ class HotPathModel:
         return ops.layernorm(x, self.P[f"{name}.weight"], self.P[f"{name}.bias"],
                              out_dtype=torch.float16 if half else torch.float32)
 
-    def _proj(self, x: Tensor, key: str, w: Tensor, b: Tensor, **kw):
-        """Projection of LayerNorm output: fp16 rows x fp16 weights (tb_linear precision 2) or the fp32 / tf32 path."""
+    @property
+    def kv_il(self) -> bool:
+        """Head-interleaved q / K / V rows (tb_knarpe_attn flags bit 4): every attention of the tensor-core mode runs
+        on the pair kernel, so the projections write the layout it gathers with 256-bit loads."""
+        return self.kv_half and self.mma_min_k == 0 and os.environ.get("TB_ATTN_IL", "1") != "0"
+
+    def _proj(self, x: Tensor, key: str, w: Tensor, b: Tensor, il_blocks=(), **kw):
+        """Projection of LayerNorm output: fp16 rows x fp16 weights (tb_linear precision 2) or the fp32 / tf32 path.
+        `il_blocks`: first rows of the d-row blocks (q, k, v) stored head-interleaved when kv_il is on."""
         if x.dtype == torch.float16:
+            if il_blocks and self.kv_il:
+                w, b = self._interleaved(key, w, b, il_blocks)
+                key += ".il"
             return ops.linear(x, self._half(key, w), b, precision=2, **kw)
         return ops.linear(x, w, b, precision=self.precision, **kw)
+
+    def _interleaved(self, key: str, w: Tensor, b: Tensor, blocks):
+        if not hasattr(self, "_w_il"):
+            self._w_il = {}
+        if key not in self._w_il:
+            rows = torch.arange(w.shape[0], device=w.device)
+            perm = head_interleave_perm(self.d).to(w.device)
+            for r0 in blocks:
+                rows[r0:r0 + self.d] = r0 + perm
+            self._w_il[key] = (w[rows].contiguous(), b[rows].contiguous())
+        return self._w_il[key]
 
     def mlp(self, x, prefix, idxs, end_act, **last_kw):
         for n, i in enumerate(idxs):
@@ -152,7 +182,8 @@ class HotPathModel:
         x = self.ln(feat, f"{layer_prefix}.{norm}", half=self.kv_half)
         if self.kv_half:  # tensor-core mode: fp16 tables straight from the projection's epilogue
             tbl = out if out is not None else torch.empty(x.shape[0], 2 * self.d, dtype=torch.float16, device=x.device)
-            self._proj(x, f"{layer_prefix}.{attn}.w_kv", f["w_kv"], f["b_kv"], out_h=tbl, col_h=0)
+            self._proj(x, f"{layer_prefix}.{attn}.w_kv", f["w_kv"], f["b_kv"], out_h=tbl, col_h=0,
+                       il_blocks=(0, self.d))
             return tbl
         return ops.linear(x, f["w_kv"], f["b_kv"], precision=self.precision, out=out)
 
@@ -163,7 +194,8 @@ class HotPathModel:
         nq = self.d + H * self.d
         if self.kv_half and K >= self.mma_min_k:  # everything fp16: [q|u|k|v] rows of one buffer
             row = torch.empty(x.shape[0], nq + 2 * self.d, dtype=torch.float16, device=x.device)
-            self._proj(x, f"{key}.w_in_self", f["w_in_self"], f["b_in_self"], out_h=row, col_h=0)
+            self._proj(x, f"{key}.w_in_self", f["w_in_self"], f["b_in_self"], out_h=row, col_h=0,
+                       il_blocks=(0, nq, nq + self.d))
             return row[:, :nq], row[:, nq:]
         if self.kv_half:  # SIMT kernel on a short list: fp32 [k|v] (leading columns), fp16 [q|u]
             qu = torch.empty(x.shape[0], nq, dtype=torch.float16, device=x.device)
@@ -177,7 +209,7 @@ class HotPathModel:
         """[q|u] rows for a cross-attention: fp16 in tensor-core mode (the attention kernel's MMA operands)."""
         if self.kv_half:
             qu = torch.empty(x.shape[0], self.d + H * self.d, dtype=torch.float16, device=x.device)
-            self._proj(x, f"{key}.w_in_q", f["w_in_q"], f["b_in_q"], out_h=qu, col_h=0)
+            self._proj(x, f"{key}.w_in_q", f["w_in_q"], f["b_in_q"], out_h=qu, col_h=0, il_blocks=(0,))
             return qu
         return ops.linear(x, f["w_in_q"], f["b_in_q"], precision=self.precision)
 
@@ -185,7 +217,7 @@ class HotPathModel:
         d = self.d
         return ops.knarpe_attn(proj[:, :d], proj[:, d:d + H * d], kv0, T0, div0, K0, knn["idx"], knn["inv"],
                                knn.get("rel"), self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1,
-                               emb=knn.get("emb"), fast_trig=self.precision == 1,
+                               emb=knn.get("emb"), fast_trig=self.precision == 1, interleaved=self.kv_il,
                                out_dtype=torch.float16 if self.kv_half else torch.float32)
 
     def _half(self, key: str, w: Tensor) -> Tensor:

@@ -72,6 +72,7 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
                 rel: Optional[Tensor], freq_xy: Tensor, B: int, S: int, D: int, H: int = 4,
                 kv1: Optional[Tensor] = None, T1: int = 0, div1: int = 1, K1: int = 0,
                 emb: Optional[Tensor] = None, out: Optional[Tensor] = None, fast_trig: bool = False,
+                interleaved: bool = False,
                 out_dtype: torch.dtype = torch.float32) -> Tuple[Tensor, Tensor]:
     """KNARPE core. q/u/kv*: 2-D (possibly column-sliced, row-strided) views; returns (out [B*S, D+H*D] = [ov|z],
     none_valid bool [B*S]). float16 kv tables select the tensor-core kernel (tb_knarpe_attn flags bit 1), a float16
@@ -99,7 +100,7 @@ def knarpe_attn(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, 
         L.ptr(kv1), kv1.stride(0) if kv1 is not None else 0, T1, div1, K1, L.ptr(idx), L.ptr(inv), L.ptr(rel),
         L.ptr(emb), L.ptr(freq_xy), B, S, D, H, L.ptr(out), L.ptr(z), out.stride(0), L.ptr(_u8(none_valid)),
         int(fast_trig) | (2 if rpe_mma else 0) | (4 if out.dtype == torch.float16 else 0) |
-        (8 if q.dtype == torch.float16 else 0), L.stream()), "tb_knarpe_attn")
+        (8 if q.dtype == torch.float16 else 0) | (16 if interleaved else 0), L.stream()), "tb_knarpe_attn")
     _count()
     return out, none_valid
 
