@@ -95,43 +95,66 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool f16) {
 }
 
 // Store phase of the epilogue for one 32x32 block: lane -> (row 4i + rsub, 16-byte chunk cc), 8 rows per lane.
-// Everything that does not change inside the loop is a template parameter or hoisted (ncu of the generic version:
-// 774 warp instructions per block, the projections with K = 128 were bound by the epilogue's instruction issue).
-template <bool RELU, bool TO_H, bool EXTRA>
-__device__ __forceinline__ void store_block(uint32_t st_s, int rsub, int cc, int rbase, int col, int M, float4 bv,
-                                            float* __restrict__ Y, int ldy, const Epi& ep) {
-  const bool all_rows = rbase + 32 <= M;
+// Everything that does not change inside the loop is a template parameter or hoisted (ncu source page of the first
+// version: 339 warp instructions per block, ~20 per stored row of which 10 were 64-bit address arithmetic and row
+// bound checks; the projections with K = 128 are bound by the epilogue's instruction issue). ALL: the block has all
+// 32 rows (every block but the last M tile's). Residual rows and row masks (EXTRA) are fetched by `Prefetch` before the
+// accumulator is waited for, so their latency overlaps the MMAs of the tile.
+struct Prefetch {
+  float4 rv[8];
+  uint32_t zero_pre, zero_post;  // bit i: row 4i + rsub is masked
+};
+template <bool ALL>
+__device__ __forceinline__ void prefetch_rows(Prefetch& pf, int rsub, int rbase, int col, int M, const Epi& ep) {
+  pf.zero_pre = pf.zero_post = 0u;
   const int row0 = rbase + rsub;
-  float* yp = Y + (size_t)row0 * ldy + col;
-  __half* hp = TO_H ? ep.yh + (size_t)row0 * ep.ldyh + (col - ep.colh) : nullptr;
-  const float* rp = (EXTRA && ep.res) ? ep.res + (size_t)row0 * ep.ldr + col : nullptr;
+  const float* rp = ep.res ? ep.res + (size_t)row0 * ep.ldr + col : nullptr;
+  const size_t rstep = (size_t)4 * ep.ldr;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int rr = i * 4 + rsub;
-    if (all_rows || rbase + rr < M) {
+    pf.rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ALL || row0 + 4 * i < M) {
+      if (rp) pf.rv[i] = *reinterpret_cast<const float4*>(rp);
+      if (ep.mask_pre && ep.mask_pre[row0 + 4 * i]) pf.zero_pre |= 1u << i;
+      if (ep.mask_post && ep.mask_post[row0 + 4 * i]) pf.zero_post |= 1u << i;
+    }
+    if (rp) rp += rstep;
+  }
+}
+template <bool RELU, bool TO_H, bool EXTRA, bool ALL>
+__device__ __forceinline__ void store_block(uint32_t st_s, int rsub, int cc, int rbase, int col, int M, float4 bv,
+                                            float* __restrict__ Y, int ldy, const Epi& ep, const Prefetch& pf) {
+  const int row0 = rbase + rsub;
+  float* yp = Y + (size_t)row0 * ldy + col;
+  const size_t ystep = (size_t)4 * ldy;
+  __half* hp = TO_H ? ep.yh + (size_t)row0 * ep.ldyh + (col - ep.colh) : nullptr;
+  const size_t hstep = (size_t)4 * ep.ldyh;
+  // row rr = 4 i + rsub sits at rr * 128 bytes, chunk cc ^ (rr & 7): (rr & 7) alternates between rsub and rsub + 4
+  const uint32_t sa0 = st_s + (uint32_t)rsub * 128u + ((uint32_t)(cc ^ rsub) << 4);
+  const uint32_t sa1 = st_s + (uint32_t)rsub * 128u + ((uint32_t)(cc ^ (rsub + 4)) << 4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (ALL || row0 + 4 * i < M) {
       float4 v;
       asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                    : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                   : "r"(st_s + (uint32_t)(rr * 32 + ((cc ^ (rr & 7)) << 2)) * 4));
+                   : "r"(((i & 1) ? sa1 : sa0) + (uint32_t)i * 512u));
       v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
       if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       if (EXTRA) {
-        const int row = rbase + rr;
-        if (ep.mask_pre && ep.mask_pre[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rp) {
-          const float4 rv = *reinterpret_cast<const float4*>(rp + (size_t)i * 4 * ep.ldr);
-          v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-        }
-        if (ep.mask_post && ep.mask_post[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pf.zero_pre & (1u << i)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        v.x += pf.rv[i].x; v.y += pf.rv[i].y; v.z += pf.rv[i].z; v.w += pf.rv[i].w;
+        if (pf.zero_post & (1u << i)) v = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (TO_H) {
         const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-        *reinterpret_cast<uint2*>(hp + (size_t)i * 4 * ep.ldyh) =
+        *reinterpret_cast<uint2*>(hp) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
       } else {
-        *reinterpret_cast<float4*>(yp + (size_t)i * 4 * ldy) = v;
+        *reinterpret_cast<float4*>(yp) = v;
       }
     }
+    if (TO_H) hp += hstep; else yp += ystep;
   }
 }
 
@@ -225,12 +248,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         (!ep.bias || (((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) && (!ep.bgroup || (N & 3) == 0)));
     const int rsub = lane >> 3, cc = lane & 7;  // store phase: lane -> (row i*4 + rsub, 16-byte chunk cc)
     int lt = 0;
+    // (m, n) tile coordinates advance by gridDim.x tiles without a division per tile
+    int tm = blockIdx.x / n_tiles, tn = blockIdx.x % n_tiles;
+    const int dm = gridDim.x / n_tiles, dn = gridDim.x % n_tiles;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m0 = tm * BM, n0 = tn * BN;
+      tm += dm; tn += dn;
+      if (tn >= n_tiles) { tn -= n_tiles; ++tm; }
       const int buf = lt & 1;
-      mbar_wait(&tfull[buf], (lt >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int rbase = m0 + quarter * 32;
+      const bool all_rows = rbase + 32 <= M;
+      bool waited = false;
       // grouped bias: this thread's accumulator row (TMEM lane) is fixed for the tile -> one division per tile
       const float* gb_row = (ep.bgroup && rbase + lane < M)
                                 ? ep.bias + (size_t)((rbase + lane) / ep.bgroup) * N : nullptr;
@@ -238,6 +266,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP; c0 += 32) {
         const int cbase = n0 + c0;
         if (cbase >= N) break;  // warp-uniform
+        const bool fast = vec_ok && cbase + 32 <= N;
+        Prefetch pf;
+        if (extra && fast) {  // residual rows / row masks of this block: in flight while the accumulator completes
+          if (all_rows) prefetch_rows<true>(pf, rsub, rbase, cbase + cc * 4, M, ep);
+          else prefetch_rows<false>(pf, rsub, rbase, cbase + cc * 4, M, ep);
+        }
+        if (!waited) {
+          mbar_wait(&tfull[buf], (lt >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          waited = true;
+        }
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c0);
         asm volatile(
@@ -273,11 +312,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                        "r"(r[4 * c]), "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3]) : "memory");
         __syncwarp();
         const bool to_h = ep.yh != nullptr && cbase >= ep.colh;  // warp-uniform: colh is a multiple of 32
-        if (vec_ok && cbase + 32 <= N) {
+        if (fast) {
           const int col = cbase + cc * 4;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ep.bias && !ep.bgroup) bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-#define TB_STORE(R, H, X) store_block<R, H, X>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep)
+#define TB_STORE(R, H, X)                                                                          \
+  do {                                                                                             \
+    if (all_rows) store_block<R, H, X, true>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf);   \
+    else store_block<R, H, X, false>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf);           \
+  } while (0)
           if (extra) {
             if (ep.relu) { if (to_h) TB_STORE(true, true, true); else TB_STORE(true, false, true); }
             else { if (to_h) TB_STORE(false, true, true); else TB_STORE(false, false, true); }
@@ -304,6 +347,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         __syncwarp();
       }
+      if (!waited) mbar_wait(&tfull[buf], (lt >> 1) & 1);  // column slice entirely past N: keep the phases in step
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&tempty[buf]);
     }
