@@ -27,6 +27,24 @@ def time_op(fn, n=10):
     return ts[len(ts) // 2]
 
 
+def time_burst(fn, n=20, reps=5):
+    """n back-to-back launches per event pair (launch latency amortised; inputs stay L2-warm as inside the step)."""
+    fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3 / n)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 shapes = [(65536, 896, 128, "in-proj self"), (65536, 640, 128, "in-proj cross q|u"), (65536, 128, 640, "out-proj"),
           (65536, 512, 128, "ffn1"), (65536, 128, 512, "ffn2"), (65536, 128, 128, "head 128"),
           (720896, 64, 128, "pointnet"), (720896, 64, 20, "ag input mlp0"), (720896, 64, 64, "ag input mlp"),
@@ -41,6 +59,34 @@ for M, N, K, name in shapes:
         t = time_op(lambda: ops.linear(x, w, b, out=y, precision=prec))
         print(f"{name:20s} M={M:7d} N={N:4d} K={K:4d} prec={prec}: {t:8.1f} us  {gb / t * 1e6 / 1e3:6.2f} TB/s  "
               f"{2 * M * N * K / t / 1e6:7.1f} TFLOP/s")
+
+# ---- the same projections as the tensor-core mode runs them: fp16 rows in (kind::f16), fp16 rows or fp32 + residual out
+if os.environ.get("TB_BENCH_F16", "1") != "0":
+    M = 65536
+    for N, K, name, out_h, extra in [(896, 128, "in-proj self", True, False), (640, 128, "in-proj cross q|u", True, False),
+                                     (128, 640, "out-proj", False, True), (512, 128, "ffn1 (relu)", True, False),
+                                     (128, 512, "ffn2", False, True)]:
+        x = (torch.randn(M, K, device=dev)).half()
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+        b = torch.randn(N, device=dev)
+        res = torch.randn(M, N, device=dev) if extra else None
+        nv = (torch.rand(M, device=dev) < 0.01) if extra else None
+        yh = torch.empty(M, N, dtype=torch.float16, device=dev) if out_h else None
+        y = None if out_h else torch.empty(M, N, device=dev)
+        nbytes = M * K * 2 + N * K * 2 + (M * N * 2 if out_h else M * N * 8)
+        if out_h:
+            fn = lambda: ops.linear(x, w, b, precision=2, out_h=yh, col_h=0, relu="relu" in name)  # noqa: E731
+        else:
+            fn = lambda: ops.linear(x, w, b, precision=2, out=y, res=res, mask_pre=nv)  # noqa: E731
+        t = time_burst(fn)
+        print(f"f16 {name:18s} M={M:7d} N={N:4d} K={K:4d}: {t:8.1f} us  {nbytes / t / 1e6:6.2f} TB/s "
+              f"(byte bound {nbytes / 6545.3e3:5.1f} us)")
+
+    x = torch.randn(M, 128, device=dev)
+    g_, b_ = torch.randn(128, device=dev), torch.randn(128, device=dev)
+    t = time_burst(lambda: ops.layernorm(x, g_, b_, out_dtype=torch.float16))
+    print(f"f16 layernorm          M={M:7d} D= 128        : {t:8.1f} us  {M * 128 * 6 / t / 1e6:6.2f} TB/s "
+          f"(byte bound {M * 128 * 6 / 6545.3e3:5.1f} us)")
 
 # ---- KNARPE core forward / backward at the agent cross-attention shape (fp32 tables; SURVEY 8(f) rank 2 first piece)
 B, S, T0, K0, d = 512, 128, 1024, 89, 128

@@ -5,50 +5,68 @@
 
 namespace {
 
-// ---- LayerNorm (transformer_rpe.py:156-171): one warp per row, D/32 floats per lane, two-pass in registers.
+// ---- LayerNorm (transformer_rpe.py:156-171): one warp per LN_ROWS rows, D/32 floats per lane and row, two-pass in
+// registers. The rows of a warp are independent load -> shuffle-reduce -> store chains that the scheduler interleaves
+// (one row per warp left the kernel latency-bound at ~55 % of the HBM rate on the 65,536 x 128 agent rows).
+constexpr int LN_ROWS = 4;
 template <int D, bool OUT_H>  // OUT_H: fp16 rows (operands of a tb_linear precision-2 projection)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, void* __restrict__ Y_, int ldy, int M, int relu) {
   constexpr int NV = D / 32;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float v[NV];
-  const float* xp = X + (size_t)row * ldx + lane * NV;
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_ROWS;
+  if (row0 >= M) return;
+  float v[LN_ROWS][NV];
 #pragma unroll
-  for (int i = 0; i < NV; i += 4) {
-    float4 t = *reinterpret_cast<const float4*>(xp + i);
-    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+  for (int r = 0; r < LN_ROWS; ++r) {
+    const float* xp = X + (size_t)min(row0 + r, M - 1) * ldx + lane * NV;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      float4 t = *reinterpret_cast<const float4*>(xp + i);
+      v[r][i] = t.x; v[r][i + 1] = t.y; v[r][i + 2] = t.z; v[r][i + 3] = t.w;
+    }
   }
-  float s = 0.f;
+  float mean[LN_ROWS], rstd[LN_ROWS];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) s += v[i];
+  for (int r = 0; r < LN_ROWS; ++r) {
+    float s = 0.f;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(TB_FULL_MASK, s, o);
-  const float mean = s * (1.f / D);
-  float q = 0.f;
+    for (int i = 0; i < NV; ++i) s += v[r][i];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(TB_FULL_MASK, s, o);
+    mean[r] = s * (1.f / D);
+  }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(TB_FULL_MASK, q, o);
-  const float rstd = 1.f / sqrtf(q * (1.f / D) + 1e-5f);
-  float* yp = static_cast<float*>(Y_) + (size_t)row * ldy + lane * NV;
-  __half* yh = static_cast<__half*>(Y_) + (size_t)row * ldy + lane * NV;
+  for (int r = 0; r < LN_ROWS; ++r) {
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { const float d = v[r][i] - mean[r]; q = fmaf(d, d, q); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(TB_FULL_MASK, q, o);
+    rstd[r] = 1.f / sqrtf(q * (1.f / D) + 1e-5f);
+  }
 #pragma unroll
   for (int i = 0; i < NV; i += 4) {
     const float4 g = ldg4(gamma + lane * NV + i), bb = ldg4(beta + lane * NV + i);
-    float4 o;
-    o.x = (v[i] - mean) * rstd * g.x + bb.x;
-    o.y = (v[i + 1] - mean) * rstd * g.y + bb.y;
-    o.z = (v[i + 2] - mean) * rstd * g.z + bb.z;
-    o.w = (v[i + 3] - mean) * rstd * g.w + bb.w;
-    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    if (OUT_H) {
-      const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
-      *reinterpret_cast<uint2*>(yh + i) =
-          make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-    } else {
-      *reinterpret_cast<float4*>(yp + i) = o;
+#pragma unroll
+    for (int r = 0; r < LN_ROWS; ++r) {
+      if (row0 + r >= M) break;
+      float4 o;
+      o.x = (v[r][i] - mean[r]) * rstd[r] * g.x + bb.x;
+      o.y = (v[r][i + 1] - mean[r]) * rstd[r] * g.y + bb.y;
+      o.z = (v[r][i + 2] - mean[r]) * rstd[r] * g.z + bb.z;
+      o.w = (v[r][i + 3] - mean[r]) * rstd[r] * g.w + bb.w;
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (OUT_H) {
+        __half* yh = static_cast<__half*>(Y_) + (size_t)(row0 + r) * ldy + lane * NV;
+        const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+        *reinterpret_cast<uint2*>(yh + i) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      } else {
+        float* yp = static_cast<float*>(Y_) + (size_t)(row0 + r) * ldy + lane * NV;
+        *reinterpret_cast<float4*>(yp + i) = o;
+      }
     }
   }
 }
@@ -157,7 +175,7 @@ extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const f
   if ((ldx | ldy) & 3 || !tb_aligned16(X) || !tb_aligned16(Y) || !tb_aligned16(gamma) || !tb_aligned16(beta))
     return TB_ERR_MISALIGNED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = (M + 7) / 8;
+  const int grid = (M + 8 * LN_ROWS - 1) / (8 * LN_ROWS);
   if (out_h && (ldy & 7)) return TB_ERR_MISALIGNED;
   if (D == 128 && out_h) layernorm_kernel<128, true><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
   else if (D == 128) layernorm_kernel<128, false><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
