@@ -8,7 +8,10 @@ namespace {
 // ---- LayerNorm (transformer_rpe.py:156-171): one warp per LN_ROWS rows, D/32 floats per lane and row, two-pass in
 // registers. The rows of a warp are independent load -> shuffle-reduce -> store chains that the scheduler interleaves
 // (one row per warp left the kernel latency-bound at ~55 % of the HBM rate on the 65,536 x 128 agent rows).
-constexpr int LN_ROWS = 4;
+#ifndef TB_LN_ROWS
+#define TB_LN_ROWS 4
+#endif
+constexpr int LN_ROWS = TB_LN_ROWS;
 template <int D, bool OUT_H>  // OUT_H: fp16 rows (operands of a tb_linear precision-2 projection)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma,
