@@ -129,7 +129,7 @@ def run_reference(args):
                                      "history; CPU sample per step: " + sample),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------ GPU arm
@@ -312,14 +312,27 @@ def run_ours(args):
         rate, sample, _ = cpu_rollout_rate(cores, 1, 16, 16)
         line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_OUT = sys.stdout
+
+
+def _reserve_stdout():
+    """stdout carries exactly one JSON line: anything a library prints to fd 1 (NCCL's version banner under torchrun)
+    goes to stderr instead, and the line itself is written to the original descriptor (_OUT)."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
     a = parse()
+    _reserve_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
