@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(256) rule_check_kernel(Args p) {
   __shared__ unsigned s_flag[MAX_A];
   __shared__ unsigned s_q[QCAP];
   __shared__ int s_qn;
+  __shared__ float4 s_veh4[MAX_A];  // valid vehicles, compacted: (x, y, map reach, agent id bits)
+  __shared__ int s_nveh;
+  __shared__ float s_bb[4];         // their bounding box grown by the reach: x0, y0, x1, y1
 
   const int b = blockIdx.x, sc = b / p.div, A = p.A;
   const int s = *p.d_step;
@@ -137,33 +140,69 @@ __global__ void __launch_bounds__(256) rule_check_kernel(Args p) {
     s_rad[a] = 0.5f * sqrtf(len * len + wid * wid) + 1e-3f;                       // conservative circumradius
     s_flag[a] = 0u;
   }
-  if (threadIdx.x == 0) s_qn = 0;
+  if (threadIdx.x == 0) { s_qn = 0; s_nveh = 0; }
   __syncthreads();
+  // valid vehicles for the map phase (ncu: 60 % of the kernel's instructions were the polyline x agent circle tests
+  // re-reading validity / type bytes and three floats per pair)
+  for (int a = threadIdx.x; a < A; a += blockDim.x)
+    if (s_valid[a] && s_veh[a])
+      s_veh4[atomicAdd(&s_nveh, 1)] = make_float4(s_x[a], s_y[a], fmaxf(s_rad[a], 2.001f), __int_as_float(a));
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float x0 = 3.0e38f, y0 = 3.0e38f, x1 = -3.0e38f, y1 = -3.0e38f;
+    for (int i = threadIdx.x; i < s_nveh; i += 32) {
+      const float4 g = s_veh4[i];
+      x0 = fminf(x0, g.x - g.z); y0 = fminf(y0, g.y - g.z); x1 = fmaxf(x1, g.x + g.z); y1 = fmaxf(y1, g.y + g.z);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      x0 = fminf(x0, __shfl_xor_sync(TB_FULL_MASK, x0, o)); y0 = fminf(y0, __shfl_xor_sync(TB_FULL_MASK, y0, o));
+      x1 = fmaxf(x1, __shfl_xor_sync(TB_FULL_MASK, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(TB_FULL_MASK, y1, o));
+    }
+    if (threadIdx.x == 0) { s_bb[0] = x0; s_bb[1] = y0; s_bb[2] = x1; s_bb[3] = y1; }
+  }
+  // (s_bb is first read after the __syncthreads() calls of the agent x agent phase)
 
-  // ---- agent x agent: collision (SAT), WOSAC collision, "agent ahead" of the passive check
+  // ---- agent x agent: collision (SAT), WOSAC collision, "agent ahead" of the passive check.
+  // Pass 1 runs the cheap distance tests over all A^2 ordered pairs and queues the few whose circumcircles touch;
+  // pass 2 runs SAT + the Minkowski signed distance densely over the queue (inline in pass 1 the ~550-instruction
+  // branch was taken by one or two lanes of half the warps' iterations).
+  auto near_pair = [&](int a, int j) {
+    unsigned f = 0u;
+    if (!(s_ped[a] && s_ped[j])) {  // collision_invalid_mask (:48-51)
+      const bool no_col = separated_by_edges(s_bx[a], s_by[a], s_bx[j], s_by[j]) ||
+                          separated_by_edges(s_bx[j], s_by[j], s_bx[a], s_by[a]);
+      if (!no_col) f |= F_COL;
+    }
+    float sd = wosac_signed_distance(s_wx[a], s_wy[a], s_wx[j], s_wy[j]);
+    sd = sub(sub(sd, s_shrink[j]), s_shrink[a]);                                 // :231-232
+    if (sd < 0.0f) f |= F_WOSAC;
+    if (f) atomicOr(&s_flag[a], f);
+  };
   for (int q = threadIdx.x; q < A * A; q += blockDim.x) {
     const int a = q / A, j = q - a * A;
     if (a == j || !s_valid[a] || !s_valid[j]) continue;
     const float dx = sub(s_x[j], s_x[a]), dy = sub(s_y[j], s_y[a]);
     const float d2 = dx * dx + dy * dy;
-    unsigned f = 0u;
     const float reach = s_rad[a] + s_rad[j];
     if (d2 <= reach * reach) {
-      if (!(s_ped[a] && s_ped[j])) {  // collision_invalid_mask (:48-51)
-        const bool no_col = separated_by_edges(s_bx[a], s_by[a], s_bx[j], s_by[j]) ||
-                            separated_by_edges(s_bx[j], s_by[j], s_bx[a], s_by[a]);
-        if (!no_col) f |= F_COL;
-      }
-      float sd = wosac_signed_distance(s_wx[a], s_wy[a], s_wx[j], s_wy[j]);
-      sd = sub(sub(sd, s_shrink[j]), s_shrink[a]);                                 // :231-232
-      if (sd < 0.0f) f |= F_WOSAC;
+      const int k = atomicAdd(&s_qn, 1);
+      if (k < QCAP) s_q[k] = ((unsigned)a << 8) | (unsigned)j;
+      else near_pair(a, j);  // queue full (a crowd): inline
     }
     if (d2 < 101.f) {  // _check_passive (:262-268): norm < 10 m and cos(angle to heading) > 0.95
       const float n = sqrtf(add(mul(dx, dx), mul(dy, dy)));
-      if (n < 10.f && (add(mul(s_c[a], dx), mul(s_s[a], dy)) / n) > 0.95f) f |= F_AGAHEAD;
+      if (n < 10.f && (add(mul(s_c[a], dx), mul(s_s[a], dy)) / n) > 0.95f) atomicOr(&s_flag[a], F_AGAHEAD);
     }
-    if (f) atomicOr(&s_flag[a], f);
   }
+  __syncthreads();
+  {
+    const int npair = min(s_qn, QCAP);
+    for (int it = threadIdx.x; it < npair; it += blockDim.x) near_pair((int)(s_q[it] >> 8), (int)(s_q[it] & 255u));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_qn = 0;  // the queue is reused by the map phase
+  __syncthreads();
 
   // ---- agent x traffic light: red-light running (:176-218) and "red light ahead" of the passive check (:250-256)
   const int slot = s % p.W;
@@ -223,10 +262,13 @@ __global__ void __launch_bounds__(256) rule_check_kernel(Args p) {
     const unsigned kind = p.poly_kind[pi];
     if (!kind) continue;
     const float pcx = p.poly_circle[pi * 3], pcy = p.poly_circle[pi * 3 + 1], pr = p.poly_circle[pi * 3 + 2];
-    for (int a = 0; a < A; ++a) {
-      if (!s_valid[a] || !s_veh[a]) continue;
-      const float rx = pcx - s_x[a], ry = pcy - s_y[a], reach = pr + fmaxf(s_rad[a], 2.001f);
+    if (pcx + pr < s_bb[0] || pcy + pr < s_bb[1] || pcx - pr > s_bb[2] || pcy - pr > s_bb[3]) continue;
+    const int n_veh = s_nveh;
+    for (int i = 0; i < n_veh; ++i) {
+      const float4 g = s_veh4[i];
+      const float rx = pcx - g.x, ry = pcy - g.y, reach = pr + g.z;
       if (rx * rx + ry * ry > reach * reach) continue;
+      const int a = __float_as_int(g.w);
       const int k = atomicAdd(&s_qn, 1);
       if (k < QCAP) s_q[k] = ((unsigned)pl << 8) | (unsigned)a;
       else for (int n = 0; n < p.n_node; ++n) test_node(a, pi * p.n_node + n, kind);  // queue full: inline (rare)
