@@ -412,8 +412,10 @@ knarpe_attn_mma_kernel(const void* __restrict__ q_, int ldq, const void* __restr
 // Versus one token per warp: 8-neighbour granularity (24 instead of 32 slots for 21 valid neighbours) and the
 // per-token set-up / epilogue shared by two tokens. Needs fp16 q / u rows and K0 + K1 <= 128.
 constexpr int KPAIR = 128;  // compacted neighbour slots per token
-constexpr int kPairSmem = 2 * (D + H * D) * 4;  // 2 x 640-float output staging; the two neighbour lists live in it first
-static_assert(kPairSmem >= 2 * (KPAIR * 8 + KPAIR * 12), "neighbour lists must fit");
+// per warp: the two neighbour lists (row pointer + float4 relative pose per slot), reused as the 2 x 640-float output
+// staging of the epilogue
+constexpr int kPairSmem = 2 * (KPAIR * 8 + KPAIR * 16);
+static_assert(kPairSmem >= 2 * (D + H * D) * 4, "output staging must fit");
 
 // One 128-channel fp16 row into 16 registers per lane. Plain layout: four 128-bit pieces, piece i = head i, lane t
 // takes halves [32 i + 8 t, +8). Head-interleaved layout (IL): two 256-bit pieces, lane t takes halves
@@ -453,7 +455,7 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
   if (tok0 >= n_tok) return;  // warp-uniform
   const bool has_b = tok0 + 1 < n_tok;
   const __half** s_ptr = reinterpret_cast<const __half**>(s_raw[warp]);               // [2][KPAIR]
-  float (*s_rel)[3] = reinterpret_cast<float (*)[3]>(s_raw[warp] + 2 * KPAIR * 8);     // [2][KPAIR]
+  float4* s_rel = reinterpret_cast<float4*>(s_raw[warp] + 2 * KPAIR * 8);              // [2][KPAIR] (x, y, yaw, -)
   float* s_out = reinterpret_cast<float*>(s_raw[warp]);                                // epilogue: 2 x [ov | z]
 
   const int g = lane >> 2, t = lane & 3;
@@ -504,12 +506,23 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
     const uint4 qq = live ? __ldg(reinterpret_cast<const uint4*>(qp)) : make_uint4(0u, 0u, 0u, 0u);
     qB[0][0] = qq.x; qB[0][1] = qq.y; qB[1][0] = qq.z; qB[1][1] = qq.w;
   }
+  // table bases: the two tokens are consecutive, so the scene index needs one division per warp and the second
+  // token almost always shares the first one's tables (the divisions were ~100 instructions per pair)
   const __half* kb[2];
+  const __half* kbx[2];
+  {
+    const unsigned b0 = (unsigned)tok0 / (unsigned)S;
+    kb[0] = kv0 + (size_t)(b0 / (unsigned)div0) * T0 * ldkv0;
+    kbx[0] = (K1 > 0) ? kv1 + (size_t)(b0 / (unsigned)div1) * T1 * ldkv1 : kb[0];
+    kb[1] = kb[0]; kbx[1] = kbx[0];
+    if (has_b && (unsigned)(tok0 + 1) - b0 * (unsigned)S >= (unsigned)S) {  // token B opens the next scene
+      kb[1] = kv0 + (size_t)((b0 + 1) / (unsigned)div0) * T0 * ldkv0;
+      kbx[1] = (K1 > 0) ? kv1 + (size_t)((b0 + 1) / (unsigned)div1) * T1 * ldkv1 : kb[1];
+    }
+  }
 #pragma unroll
   for (int tk = 0; tk < 2; ++tk) {
-    const int b = (tok0 + (tk && has_b ? 1 : 0)) / S;
-    kb[tk] = kv0 + (size_t)(b / div0) * T0 * ldkv0;
-    const __half* kb1 = (K1 > 0) ? kv1 + (size_t)(b / div1) * T1 * ldkv1 : kb[tk];
+    const __half* kb1 = kbx[tk];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       if (c * 32 < Ktot) {  // warp-uniform
@@ -519,9 +532,7 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
           const int pos = tk * KPAIR + nvalid[tk] + __popc(vb & lt_mask);
           s_ptr[pos] = (c * 32 + lane < K0) ? kb[tk] + (size_t)n_id[tk][c] * ldkv0
                                              : kb1 + (size_t)n_id[tk][c] * ldkv1;
-          s_rel[pos][0] = n_rel[tk][c][0];
-          s_rel[pos][1] = n_rel[tk][c][1];
-          s_rel[pos][2] = n_rel[tk][c][2];
+          s_rel[pos] = make_float4(n_rel[tk][c][0], n_rel[tk][c][1], n_rel[tk][c][2], 0.f);
         }
         nvalid[tk] += __popc(vb);
       }
@@ -529,9 +540,7 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
     const int npad_t = (nvalid[tk] + 7) & ~7;
     if (lane < npad_t - nvalid[tk]) {  // weight-0 dummies up to a multiple of 8
       s_ptr[tk * KPAIR + nvalid[tk] + lane] = kb[tk];
-      s_rel[tk * KPAIR + nvalid[tk] + lane][0] = 0.f;
-      s_rel[tk * KPAIR + nvalid[tk] + lane][1] = 0.f;
-      s_rel[tk * KPAIR + nvalid[tk] + lane][2] = 0.f;
+      s_rel[tk * KPAIR + nvalid[tk] + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   const int npad = max((nvalid[0] + 7) & ~7, (nvalid[1] + 7) & ~7);
@@ -539,7 +548,7 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
   for (int tk = 0; tk < 2; ++tk)
     for (int j = ((nvalid[tk] + 7) & ~7) + lane; j < npad; j += 32) {
       s_ptr[tk * KPAIR + j] = kb[tk];
-      s_rel[tk * KPAIR + j][0] = 0.f; s_rel[tk * KPAIR + j][1] = 0.f; s_rel[tk * KPAIR + j][2] = 0.f;
+      s_rel[tk * KPAIR + j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   __syncwarp();
 
@@ -566,8 +575,8 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
     uint32_t eA[8][4];
 #pragma unroll
     for (int tile = 0; tile < 2; ++tile) {
-      const float* rp = s_rel[tile * KPAIR + g0 + g];
-      const float x = rp[0], y = rp[1], w = rp[2];
+      const float4 rp = s_rel[tile * KPAIR + g0 + g];
+      const float x = rp.x, y = rp.y, w = rp.z;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float s0, c0, s1, c1;
@@ -638,7 +647,9 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
       lg[j] = s;  // reuse: group sum
       grew |= mn[j] > mx[j];
     }
-    if (__any_sync(TB_FULL_MASK, grew)) {
+    if (g0 == 0) {  // first group: the accumulators are still zero, nothing to rescale
+      mx[0] = mn[0]; mx[1] = mn[1];
+    } else if (__any_sync(TB_FULL_MASK, grew)) {
       const float ca = mn[0] > mx[0] ? ex2(mx[0] - mn[0]) : 1.f, cb = mn[1] > mx[1] ? ex2(mx[1] - mn[1]) : 1.f;
       mx[0] = mn[0]; mx[1] = mn[1];
       sm[0] *= ca; sm[1] *= cb;
