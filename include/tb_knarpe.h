@@ -271,6 +271,27 @@ int tb_future_filter(const uint8_t* collided, const uint8_t* run_road_edge, cons
 int tb_traj_global(const float* pose, const int32_t* sel, const float* center, const float* yaw, int n_sc, int K,
                    int n_keep, int A, int T, int t0, float* out_pos, float* out_yaw, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * WOMD post-processing on the device — data_modules/womd_post_processing.py:36-106 with the
+ * configured parameters of configs/model/sim_agent.yaml:170-177 (top-k + `mpa_nms`; `mtr_nms` / `traj_aggr` are not
+ * configured and not built). Per (scene, agent):
+ *   p = softmax_k(scores[sc, k, a])                (scores NULL: uniform)                               :48-53
+ *   K > k_pred: keep the k_pred most probable futures (descending p, ties by lower index; the reference's
+ *     topk(sorted=False) leaves the order unspecified) and renormalise                                   :170-190
+ *   nms_on: d(m,n) = mean_t |xy_m(t) - xy_n(t)| (use_ade) or the distance at the last step; visiting the modes in
+ *     descending score order, a mode with d < thresh(type) to a currently higher-scored mode drops to 1e-3; then
+ *     renormalise. thresh = sum_i ag_type[sc,a,i] * thr_i                                                :75-106
+ *   score_temperature > 0: p = softmax(log p / temperature)                                              :66-67
+ *   out_trajs[sc, a, m, j, :] = trajs[sc, mode m, a, t_first + j * t_stride, :], t < min(t_end, T)      :69
+ * trajs [n_sc, K, A, T, 3] f32 (the rollout's layout), scores [n_sc, K, A] f32 log-probs, ag_type [n_sc, A, 3] u8;
+ * out_trajs [n_sc, A, k, n_out, 3], out_scores / out_mode (may be NULL) [n_sc, A, k] with k = min(K, k_pred).
+ * Limits: K <= 128, k_pred <= 8 (TB_ERR_UNSUPPORTED).
+ * ------------------------------------------------------------------------------------------------- */
+int tb_womd_post(const float* trajs, const float* scores, const uint8_t* ag_type, int n_sc, int K, int A, int T,
+                 int k_pred, int use_ade, int nms_on, float thr_veh, float thr_ped, float thr_cyc,
+                 float score_temperature, int t_first, int t_stride, int t_end, float* out_trajs, float* out_scores,
+                 int32_t* out_mode, void* stream);
+
 /* Sum of the three type-masked branches is done inside tb_dyn_step; this helper exposes the masked action
  * mean [B,A,2] for the module-level API (action_head.py:78-82). */
 int tb_action_mean(const float* act_branch, const uint8_t* ag_type, const uint8_t* valid, int M, float* mean,

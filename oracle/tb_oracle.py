@@ -719,3 +719,47 @@ def wosac_to_global(trajs: Tensor, center: Tensor, yaw: Tensor) -> Tuple[Tensor,
     yy = trajs[..., 2:3]
     oy = (yy.flatten(1, 4) + yaw.unsqueeze(-1) + math.pi) % (2 * math.pi) - math.pi
     return out.view(pos.shape), oy.view(yy.shape)
+
+
+# --------------------------------------------------------------------------------------------------
+# WOMD post-processing: data_modules/womd_post_processing.py:36-106, the configured path of
+# configs/model/sim_agent.yaml:170-177 (k_pred 6, use_ade, mpa_nms_thresh [2,2,2]; mtr_nms / traj_aggr off)
+# --------------------------------------------------------------------------------------------------
+def womd_post_processing(ag_type: Tensor, trajs: Tensor, scores: Optional[Tensor], k_pred: int, use_ade: bool,
+                         mpa_nms_thresh, score_temperature: float, track_future_samples: int
+                         ) -> Tuple[Tensor, Tensor, Tensor]:
+    """`WOMDPostProcessing.forward` (:36-72): softmax of the joint-future log-probs per agent (:48-53), `traj_topk`
+    (:170-190) when there are more futures than k_pred, `mpa_nms` (:75-106), optional temperature (:66-67), 2 Hz
+    down-sampling (:69). trajs [n_sc,K,n_ag,T,3], scores [n_sc,K,n_ag] or None, ag_type [n_sc,n_ag,3].
+    Returns (trajs [n_sc,n_ag,k,n_out,3], scores [n_sc,n_ag,k], mode index [n_sc,n_ag,k]). The reference's top-k is
+    `sorted=False` (order unspecified); here modes come in descending score, ties by lower index."""
+    tr = trajs.transpose(1, 2)                                       # [n_sc,n_ag,K,T,3]
+    n_sc, n_ag, K = tr.shape[:3]
+    sc = torch.zeros(n_sc, n_ag, K) if scores is None else scores.transpose(1, 2)
+    sc = sc.float().softmax(-1)
+    mode = torch.arange(K).expand(n_sc, n_ag, K)
+    if K > k_pred:                                                   # traj_topk :170-190
+        key = -sc.double() * 4.0 * K + torch.arange(K, dtype=torch.float64) * 1e-12
+        mode = torch.argsort(key, dim=-1, stable=True)[..., :k_pred]
+        tr = torch.gather(tr, 2, mode[..., None, None].expand(-1, -1, -1, tr.shape[3], 3))
+        sc = torch.gather(sc, 2, mode)
+        sc = sc / sc.sum(-1, keepdim=True)
+    if len(mpa_nms_thresh) > 0:                                      # mpa_nms :75-106
+        thresh = sum(ag_type[:, :, i].float() * float(mpa_nms_thresh[i]) for i in range(len(mpa_nms_thresh)))
+        xy = tr[..., :2]
+        if use_ade:
+            dist = torch.norm(xy.unsqueeze(2) - xy.unsqueeze(3), dim=-1).mean(-1)
+        else:
+            dist = torch.norm(xy[:, :, :, -1].unsqueeze(2) - xy[:, :, :, -1].unsqueeze(3), dim=-1)
+        within = dist < thresh[:, :, None, None]
+        sc = sc.clone()
+        for i in range(n_sc):
+            for j in range(n_ag):
+                order = sorted(range(sc.shape[-1]), key=lambda k: (-float(sc[i, j, k]), k))
+                for k in order:
+                    if bool((within[i, j, k] & (sc[i, j] > sc[i, j, k])).any()):
+                        sc[i, j, k] = 1e-3
+        sc = sc / sc.sum(-1, keepdim=True)
+    if score_temperature > 0:
+        sc = torch.softmax(torch.log(sc) / score_temperature, dim=-1)
+    return tr[:, :, :, 4:track_future_samples:5], sc, mode

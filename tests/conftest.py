@@ -47,3 +47,25 @@ def golden_navi():
 @pytest.fixture(scope="session")
 def golden_wosac():
     return torch.load(os.path.join(GOLDEN, "wosac_post.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_womd():
+    return torch.load(os.path.join(GOLDEN, "womd_post.pt"), weights_only=False)
+
+
+def _match_womd_modes(trajs, scores, ref_trajs, ref_scores, rtol=1e-5):
+    """The reference's top-k is `sorted=False`: match every kept mode to the reference's by its (bit-identical,
+    gathered) trajectory, then compare the scores mode by mode. Shapes [n_sc,n_ag,k,n_out,3] / [n_sc,n_ag,k]."""
+    assert trajs.shape == ref_trajs.shape and scores.shape == ref_scores.shape
+    d = (trajs[:, :, :, None] - ref_trajs[:, :, None]).abs().flatten(4).amax(-1)  # [n_sc,n_ag,k,k]
+    idx = d.argmin(-1)
+    assert float(d.min(-1)[0].max()) == 0.0, "a kept trajectory is not among the reference's"
+    assert all(len(set(r.tolist())) == r.numel() for r in idx.flatten(0, 1)), "modes must map one to one"
+    ref = torch.gather(ref_scores, 2, idx)
+    assert torch.allclose(scores, ref, rtol=rtol, atol=1e-7), float((scores - ref).abs().max())
+
+
+@pytest.fixture(scope="session")
+def match_womd_modes():
+    return _match_womd_modes

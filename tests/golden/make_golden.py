@@ -272,6 +272,24 @@ def golden_wosac_post():
     print("wosac_post.pt", os.path.getsize(os.path.join(HERE, "wosac_post.pt")) // 1024, "KiB")
 
 
+def golden_womd_post():
+    """the real WOMDPostProcessing (womd_post_processing.py:36-106) with the configured
+    parameters of configs/model/sim_agent.yaml:170-177 on seeded joint futures + log-prob scores."""
+    from data_modules.womd_post_processing import WOMDPostProcessing  # reference
+    fix = {}
+    for name, shape, temp in [("k12", dict(seed=8000, n_sc=2, K=12, A=24, T=80), -1.0),
+                              ("k32_temp", dict(seed=8001, n_sc=1, K=32, A=16, T=80), 0.7),
+                              ("k6", dict(seed=8002, n_sc=1, K=6, A=8, T=80), -1.0)]:
+        inp = synth.make_womd_post_inputs(**shape)
+        pp = WOMDPostProcessing(k_pred=6, score_temperature=temp, mpa_nms_thresh=[2.0, 1.0, 3.0], mtr_nms_thresh=[],
+                                aggr_thresh=[], n_iter_em=3, use_ade=True, step_gt=90, step_current=10)
+        out = pp(ag_type=inp["ag_type"], trajs=inp["trajs"].clone(), scores=inp["scores"].clone())
+        fix[name] = dict(shape=shape, score_temperature=temp, mpa_nms_thresh=[2.0, 1.0, 3.0], k_pred=6,
+                         trajs=out["trajs"].clone(), scores=out["scores"].clone())
+    torch.save(fix, os.path.join(HERE, "womd_post.pt"))
+    print("womd_post.pt", os.path.getsize(os.path.join(HERE, "womd_post.pt")) // 1024, "KiB")
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -279,6 +297,8 @@ def main():
         return golden_navi_predictor()
     if len(sys.argv) > 1 and sys.argv[1] == "wosac":  # only (re)generate wosac_post.pt
         return golden_wosac_post()
+    if len(sys.argv) > 1 and sys.argv[1] == "womd":  # only (re)generate womd_post.pt
+        return golden_womd_post()
     ops = golden_ops()
     torch.save(ops, os.path.join(HERE, "ops.pt"))
     print("ops.pt", os.path.getsize(os.path.join(HERE, "ops.pt")) // 1024, "KiB")
@@ -315,6 +335,7 @@ def main():
           {k: int(res[k].sum()) for k in keep[4:]})
     golden_navi_predictor()
     golden_wosac_post()
+    golden_womd_post()
 
 
 if __name__ == "__main__":

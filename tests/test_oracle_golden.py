@@ -153,3 +153,17 @@ def test_wosac_post_processing_oracle_vs_reference(golden_wosac):
     trajs = inp["pose"].view(n_sc, K, A, T, 3)[torch.arange(n_sc)[:, None], g["sel"]][:, :, :, g["t0"]:]
     pos, yaw = O.wosac_to_global(trajs, inp["center"], inp["yaw"])
     assert torch.equal(pos, g["pos_sim"]) and torch.equal(yaw, g["yaw_sim"])
+
+
+@pytest.mark.parametrize("case", ["k12", "k32_temp", "k6"])
+def test_womd_post_processing_oracle_vs_reference(golden_womd, match_womd_modes, case):
+    """softmax + top-k + type-dependent ADE NMS + 2 Hz down-sampling
+    (womd_post_processing.py:36-106) — oracle vs the real WOMDPostProcessing; more futures than k_pred, exactly
+    k_pred (no top-k), and the score-temperature branch."""
+    g = golden_womd[case]
+    inp = synth.make_womd_post_inputs(**g["shape"])
+    trajs, scores, mode = O.womd_post_processing(inp["ag_type"], inp["trajs"], inp["scores"], g["k_pred"], True,
+                                                 g["mpa_nms_thresh"], g["score_temperature"], 80)
+    assert trajs.shape[3] == 16 and trajs.shape[2] == min(g["k_pred"], g["shape"]["K"])
+    match_womd_modes(trajs, scores, g["trajs"], g["scores"])
+    assert int((scores < 0.05).sum()) > 0 and int((scores > 0.3).sum()) > 0  # the NMS suppressed some modes, kept others

@@ -425,3 +425,54 @@ def test_rollout_golden_tf32_fp32_intermediates(golden_rollout):
     assert int((res["tl_state"].cpu() != g["tl_state"]).sum()) == 0
     assert maxerr(res["pred_pose"][..., :2], g["pred_pose"][..., :2]) < TC_TOL_XY
     assert maxerr(res["pred_pose"][..., 2], g["pred_pose"][..., 2]) < TC_TOL_YAW
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["k12", "k32_temp", "k6"])
+def test_womd_post_processing_kernel_vs_reference(golden_womd, match_womd_modes, case):
+    """tb_womd_post vs the real WOMDPostProcessing (golden) and vs the oracle mode by mode."""
+    from trafficbotsv1_5_b200 import ops
+    g = golden_womd[case]
+    inp = synth.make_womd_post_inputs(**g["shape"])
+    trajs, scores, mode = ops.womd_post(inp["trajs"].to(DEV), inp["scores"].to(DEV), inp["ag_type"].to(DEV), g["k_pred"],
+                                        True, g["mpa_nms_thresh"], g["score_temperature"], 4, 5, 80)
+    match_womd_modes(trajs.cpu(), scores.cpu(), g["trajs"], g["scores"])
+    o_trajs, o_scores, o_mode = O.womd_post_processing(inp["ag_type"], inp["trajs"], inp["scores"], g["k_pred"], True,
+                                                       g["mpa_nms_thresh"], g["score_temperature"], 80)
+    assert torch.equal(mode.cpu().long(), o_mode) and torch.equal(trajs.cpu(), o_trajs)  # same modes, same order
+    assert torch.allclose(scores.cpu(), o_scores, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_womd_post_processing_variants_vs_oracle():
+    """Uniform scores (reactive replay: scores=None), FDE instead of ADE, NMS off, and the argument checks."""
+    from trafficbotsv1_5_b200 import ops
+    inp = synth.make_womd_post_inputs(seed=8100, n_sc=2, K=9, A=13, T=37)
+    tr, ty = inp["trajs"].to(DEV), inp["ag_type"].to(DEV)
+    for scores, use_ade, thr in [(inp["scores"], False, [2.0, 2.0, 2.0]), (inp["scores"], True, []),
+                                 (None, True, [1.0, 2.0, 3.0])]:
+        t, s, m = ops.womd_post(tr, None if scores is None else scores.to(DEV), ty, 6, use_ade, thr, -1.0, 4, 5, 80)
+        ot, os_, om = O.womd_post_processing(inp["ag_type"], inp["trajs"], scores, 6, use_ade, thr, -1.0, 80)
+        assert t.shape == (2, 13, 6, 7, 3)  # steps 4, 9, ..., 34 of the 37 available
+        assert torch.equal(m.cpu().long(), om) and torch.equal(t.cpu(), ot)
+        assert torch.allclose(s.cpu(), os_, rtol=1e-5, atol=1e-7)
+    with pytest.raises(RuntimeError):  # more joint futures than the kernel's 128
+        ops.womd_post(torch.zeros(1, 129, 2, 10, 3, device=DEV), None, torch.zeros(1, 2, 3, dtype=torch.bool, device=DEV))
+    with pytest.raises(RuntimeError):  # k_pred > 8
+        ops.womd_post(tr, None, ty, k_pred=9)
+
+
+@pytest.mark.gpu
+def test_post_process_womd_after_rollout():
+    """RolloutEngine.post_process_womd on a real rollout: 8 joint futures -> 6 modes per agent at 2 Hz."""
+    eng, batch, P, cfg = _engine(dict(n_sc=2, n_ag=48, n_mp=96, n_tl=30, seed=3100, boundary=60.0), 8, 90)
+    res = eng.rollout(batch)
+    g = torch.Generator().manual_seed(5)
+    scores = torch.randn(2, 8, 48, generator=g)
+    out = eng.post_process_womd(res, batch, scores)
+    assert out["trajs"].shape == (2, 48, 6, 16, 3) and out["scores"].shape == (2, 48, 6)
+    fut = res["pred_pose"].view(2, 8, 48, -1, 3)[:, :, :, 10:].cpu()
+    ot, os_, om = O.womd_post_processing(batch["ref/ag_type"], fut, scores, 6, True, [2.0, 2.0, 2.0], -1.0, 80)
+    assert torch.equal(out["mode"].cpu().long(), om) and torch.equal(out["trajs"].cpu(), ot)
+    assert torch.allclose(out["scores"].cpu(), os_, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(out["scores"].sum(-1).cpu(), torch.ones(2, 48), atol=1e-5)

@@ -397,6 +397,24 @@ class RolloutEngine:
         pos, yaw = ops.traj_global(res["pred_pose"], sel, g("scenario_center"), g("scenario_yaw"), n_sc, R, t0)
         return dict(pos_sim=pos, yaw_sim=yaw, sel=sel, score=score)
 
+    def post_process_womd(self, res: Dict[str, Tensor], batch: Dict[str, Tensor], scores: Optional[Tensor] = None,
+                          k_pred: int = 6, use_ade: bool = True, mpa_nms_thresh=(2.0, 2.0, 2.0),
+                          score_temperature: float = -1.0, step_future_start: Optional[int] = None
+                          ) -> Dict[str, Tensor]:
+        """WOMDPostProcessing.forward on the device (womd_post_processing.py:36-106 with the parameters of
+        configs/model/sim_agent.yaml:170-177): per agent, the k_pred most probable of the R joint
+        futures, type-dependent ADE NMS of their scores, 2 Hz down-sampling. `scores` [n_sc, R, A] are the joint
+        futures' log-probs (waymo_motion.py:632; None = uniform, as for reactive replay :610-613)."""
+        R = self.R
+        n_sc = res["pred_pose"].shape[0] // R
+        t0 = C.ROLLOUT_CFG["time_step_current"] if step_future_start is None else step_future_start
+        pose = res["pred_pose"]
+        fut = pose.view(n_sc, R, *pose.shape[1:])[:, :, :, t0:].contiguous()
+        n_fut = C.ROLLOUT_CFG["time_step_end"] - C.ROLLOUT_CFG["time_step_current"]  # track_future_samples
+        trajs, sc, mode = ops.womd_post(fut, None if scores is None else scores.to(self.dev), batch["ref/ag_type"].to(self.dev),
+                                        k_pred, use_ade, mpa_nms_thresh, score_temperature, 4, 5, n_fut)
+        return dict(trajs=trajs, scores=sc, mode=mode)
+
     def rollout(self, batch: Dict[str, Tensor], n_steps: Optional[int] = None) -> Dict[str, Tensor]:
         self.prepare(batch)
         return self.run(n_steps)

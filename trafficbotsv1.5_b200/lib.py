@@ -20,7 +20,7 @@ _lib = None
 EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_linear", "tb_layernorm",
            "tb_pointnet_pool", "tb_pose_emb", "tb_ag_featurize", "tb_tl_featurize", "tb_dyn_step", "tb_tl_step",
            "tb_step_advance", "tb_gather_rows", "tb_action_mean", "tb_rule_check", "tb_future_filter",
-           "tb_traj_global", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd"]
+           "tb_traj_global", "tb_womd_post", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -70,6 +70,7 @@ def load() -> ctypes.CDLL:
         "tb_rule_check": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],
         "tb_future_filter": [P, P, P, I, I, I, I, I, F, I, P, P, P],
         "tb_traj_global": [P, P, P, P, I, I, I, I, I, I, P, P, P],
+        "tb_womd_post": [P, P, P, I, I, I, I, I, I, I, F, F, F, F, I, I, I, P, P, P, P],
         "tb_ag_frontend": [P, P, P, P, P, P, I, I, I, P, P, P, I, P, P, P],
         "tb_ag_frontend_blob_halves": [],
         "tb_knarpe_attn_bwd": [P, I, P, I, P, I, I, I, I, P, I, I, I, I, P, P, P, P, I, I, I, I, P, P, I, P, I, P, P, P],

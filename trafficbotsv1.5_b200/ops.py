@@ -224,6 +224,31 @@ def traj_global(pose: Tensor, sel: Optional[Tensor], center: Tensor, yaw: Tensor
     return pos, oyaw
 
 
+def womd_post(trajs: Tensor, scores: Optional[Tensor], ag_type: Tensor, k_pred: int = 6, use_ade: bool = True,
+              mpa_nms_thresh=(2.0, 2.0, 2.0), score_temperature: float = -1.0, t_first: int = 4, t_stride: int = 5,
+              t_end: int = 80) -> Tuple[Tensor, Tensor, Tensor]:
+    """tb_womd_post (womd_post_processing.py:36-106): trajs [n_sc, K, A, T, 3], scores [n_sc, K, A] log-probs or None,
+    ag_type [n_sc, A, 3] -> (trajs [n_sc, A, k, n_out, 3], scores [n_sc, A, k], mode [n_sc, A, k] int32)."""
+    trajs = _f32c(trajs)
+    n_sc, K, A, T, _ = trajs.shape
+    scores = None if scores is None else _f32c(scores)
+    assert scores is None or scores.shape == (n_sc, K, A)
+    ag_type = _u8(ag_type.contiguous())
+    assert ag_type.shape == (n_sc, A, 3)
+    k = min(K, k_pred)
+    n_out = len(range(t_first, min(t_end, T), t_stride))
+    out_t = torch.empty(n_sc, A, k, n_out, 3, dtype=torch.float32, device=trajs.device)
+    out_s = torch.empty(n_sc, A, k, dtype=torch.float32, device=trajs.device)
+    out_m = torch.empty(n_sc, A, k, dtype=torch.int32, device=trajs.device)
+    thr = list(mpa_nms_thresh) + [0.0] * 3
+    L.check(L.load().tb_womd_post(L.ptr(trajs), L.ptr(scores), L.ptr(ag_type), n_sc, K, A, T, k_pred, int(use_ade),
+                                  int(len(mpa_nms_thresh) > 0), float(thr[0]), float(thr[1]), float(thr[2]),
+                                  float(score_temperature), t_first, t_stride, t_end, L.ptr(out_t), L.ptr(out_s),
+                                  L.ptr(out_m), L.stream()), "tb_womd_post")
+    _count()
+    return out_t, out_s, out_m
+
+
 def knarpe_attn_bwd(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, idx: Tensor, invalid: Tensor,
                     rel: Tensor, freq_xy: Tensor, B: int, S: int, D: int, d_out: Tensor, H: int = 4,
                     kv1: Optional[Tensor] = None, T1: int = 0, div1: int = 1, K1: int = 0

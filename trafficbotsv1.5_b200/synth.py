@@ -111,3 +111,20 @@ def make_wosac_post_inputs(seed: int, n_sc: int, K: int, A: int, T: int):
     center = (torch.rand(n_sc, 2, generator=g) * 2 - 1) * 5000
     yaw = (torch.rand(n_sc, generator=g) * 2 - 1) * 3.1
     return dict(pose=pose, role=role, collided=col, run_road_edge=edge, center=center, yaw=yaw)
+
+
+def make_womd_post_inputs(seed: int, n_sc: int, K: int, A: int, T: int):
+    """Seeded inputs of the WOMD post-processing fixture (womd_post_processing.py:36-72): joint futures that form a few
+    clusters per agent (so the 2 m ADE test of `mpa_nms` has both outcomes), distinct log-prob scores, agent types."""
+    g = torch.Generator().manual_seed(seed)
+    base = (torch.rand(n_sc, 4, A, 1, 2, generator=g) * 2 - 1) * 30           # 4 cluster end points per agent
+    which = torch.randint(0, 4, (n_sc, K, A), generator=g)
+    end = torch.gather(base.expand(-1, -1, -1, 1, -1), 1, which[..., None, None].expand(-1, -1, -1, 1, 2))
+    t = torch.linspace(0, 1, T).view(1, 1, 1, T, 1)
+    xy = end * t + torch.randn(n_sc, K, A, T, 2, generator=g) * 0.4
+    yaw = (torch.rand(n_sc, K, A, T, 1, generator=g) * 2 - 1) * 3.1
+    trajs = torch.cat([xy, yaw], -1).contiguous()
+    scores = torch.randn(n_sc, K, A, generator=g) * 1.5                        # log-probs, distinct with probability 1
+    ag_type = torch.zeros(n_sc, A, 3, dtype=torch.bool)
+    ag_type[torch.arange(n_sc)[:, None], torch.arange(A)[None], torch.randint(0, 3, (n_sc, A), generator=g)] = True
+    return dict(trajs=trajs, scores=scores, ag_type=ag_type)
