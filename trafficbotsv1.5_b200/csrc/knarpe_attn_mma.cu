@@ -626,40 +626,41 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
 #pragma unroll
     for (int tile = 0; tile < 2; ++tile) load_row<IL>(vf[tile], rowp[tile] + D, t);
 
-    // ---- softmax of this lane's token (row block `my`), heads h0 / h0+1, over the 8 rows (lanes with the same t)
+    // ---- softmax of this lane's token (row block `my`), heads h0 / h0+1, over the 8 rows (lanes with the same t).
+    // The reference maximum is lazy: it is re-established (3 shuffles per head + accumulator rescale) only for the
+    // first group and when some logit exceeds it by more than 2^kSlack — otherwise p = 2^(logit - mx) <= 2^kSlack
+    // is used as it is (exact in real arithmetic; fp32 accumulators, fp16 p keeps its 11 bits). The denominator is a
+    // per-lane partial sum reduced once in the epilogue. Saves 12 of the ~200 LSU wavefronts of a group.
+    constexpr float kSlack = 8.f;
     const bool row_ok = g0 + g < my_nvalid;
     float lg[2], p[2];
-    bool grew = false;
-    float mn[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) lg[j] = row_ok ? (my ? sc[2 + j] : sc[j]) : -INFINITY;
+    if (g0 == 0 || __any_sync(TB_FULL_MASK, lg[0] > mx[0] + kSlack || lg[1] > mx[1] + kSlack)) {
+      float mn[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float gm = lg[j];
+        gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 4));
+        gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 8));
+        gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 16));
+        mn[j] = fmaxf(mx[j], gm);
+      }
+      if (g0 != 0) {  // (first group: the accumulators are still zero, nothing to rescale)
+        const float ca = mn[0] > mx[0] ? ex2(mx[0] - mn[0]) : 1.f, cb = mn[1] > mx[1] ? ex2(mx[1] - mn[1]) : 1.f;
+        sm[0] *= ca; sm[1] *= cb;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { zacc[c][0] *= ca; zacc[c][1] *= cb; zacc[c][2] *= ca; zacc[c][3] *= cb; }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) { oacc[m][0] *= ca; oacc[m][1] *= cb; oacc[m][2] *= ca; oacc[m][3] *= cb; }
+      }
+      mx[0] = mn[0]; mx[1] = mn[1];
+    }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      lg[j] = row_ok ? (my ? sc[2 + j] : sc[j]) : -INFINITY;
-      float gm = lg[j];
-      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 4));
-      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 8));
-      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 16));
-      mn[j] = fmaxf(mx[j], gm);
-      p[j] = row_ok ? ex2(lg[j] - mn[j]) : 0.f;  // mn is finite whenever row_ok
-      float s = p[j];
-      s += __shfl_xor_sync(TB_FULL_MASK, s, 4);
-      s += __shfl_xor_sync(TB_FULL_MASK, s, 8);
-      s += __shfl_xor_sync(TB_FULL_MASK, s, 16);
-      lg[j] = s;  // reuse: group sum
-      grew |= mn[j] > mx[j];
+      p[j] = row_ok ? ex2(lg[j] - mx[j]) : 0.f;  // mx is finite whenever row_ok
+      sm[j] += p[j];                              // this lane's rows only
     }
-    if (g0 == 0) {  // first group: the accumulators are still zero, nothing to rescale
-      mx[0] = mn[0]; mx[1] = mn[1];
-    } else if (__any_sync(TB_FULL_MASK, grew)) {
-      const float ca = mn[0] > mx[0] ? ex2(mx[0] - mn[0]) : 1.f, cb = mn[1] > mx[1] ? ex2(mx[1] - mn[1]) : 1.f;
-      mx[0] = mn[0]; mx[1] = mn[1];
-      sm[0] *= ca; sm[1] *= cb;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { zacc[c][0] *= ca; zacc[c][1] *= cb; zacc[c][2] *= ca; zacc[c][3] *= cb; }
-#pragma unroll
-      for (int m = 0; m < 2; ++m) { oacc[m][0] *= ca; oacc[m][1] *= cb; oacc[m][2] *= ca; oacc[m][3] *= cb; }
-    }
-    sm[0] += lg[0];
-    sm[1] += lg[1];
     // p^T B fragment: tile 0 = rows 0-7 (token A's neighbours) has values only in columns 0-3 (lanes t < 2), tile 1
     // only in columns 4-7 (lanes t >= 2)
     const uint32_t pk = pack_h2(p[0], p[1]);
@@ -689,6 +690,12 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
   }
 
   // ---- epilogue: lanes t < 2 hold token A's columns, t >= 2 token B's; staging block per token
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {  // denominators: the 8 lanes with the same t hold the partial sums of a column pair
+    sm[j] += __shfl_xor_sync(TB_FULL_MASK, sm[j], 4);
+    sm[j] += __shfl_xor_sync(TB_FULL_MASK, sm[j], 8);
+    sm[j] += __shfl_xor_sync(TB_FULL_MASK, sm[j], 16);
+  }
   const float ia = sm[0] > 0.f ? 1.f / sm[0] : 0.f, ib = sm[1] > 0.f ? 1.f / sm[1] : 0.f;
   __syncwarp();
   {
