@@ -476,3 +476,20 @@ def test_post_process_womd_after_rollout():
     assert torch.equal(out["mode"].cpu().long(), om) and torch.equal(out["trajs"].cpu(), ot)
     assert torch.allclose(out["scores"].cpu(), os_, rtol=1e-5, atol=1e-7)
     assert torch.allclose(out["scores"].sum(-1).cpu(), torch.ones(2, 48), atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_rollout_head_interleaved_layout_is_bit_identical(golden_rollout, monkeypatch):
+    """The head-interleaved q / K / V rows (tb_knarpe_attn flags bit 4, the tensor-core mode's default) are a
+    permutation of projection output features: the whole closed-loop rollout is bit-identical to the natural layout
+    (TB_ATTN_IL=0, 128-bit gathers)."""
+    g = golden_rollout
+    eng, batch, P, cfg = _engine(g["shape"], g["R"], g["T"], precision=1)
+    assert eng.model.kv_il
+    res = {k: v.clone() for k, v in eng.rollout(batch).items() if torch.is_tensor(v)}
+    monkeypatch.setenv("TB_ATTN_IL", "0")
+    eng2, _, _, _ = _engine(g["shape"], g["R"], g["T"], precision=1)
+    assert not eng2.model.kv_il
+    res2 = eng2.rollout(batch)
+    for k in ("pred_pose", "pred_motion", "pred_valid", "tl_state"):
+        assert torch.equal(res[k], res2[k]), k
