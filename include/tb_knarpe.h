@@ -135,6 +135,17 @@ int tb_linear(const void* X, int ldx, const void* W, const float* bias, int bias
               int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
               int precision, void* Yh, int ldyh, int col_h, void* stream);
 
+/* tb_linear with the LayerNorm of its result fused into the epilogue (tensor-core mode, N == 128):
+ *   Y = X W^T + bias, masks / residual as tb_linear (no ReLU); ln_out[row] = fp16(LayerNorm(Y[row]) * gamma + beta),
+ *   eps 1e-5 (transformer_rpe.py:156-171 applied to the residual stream right after attention / FFN, :233-245) —
+ *   the rows the next kind::f16 projection reads, so the residual stream is not re-read by a LayerNorm launch.
+ *   precision 1 (fp32 X, W) or 2 (fp16 X, W). Y, res, bias, gamma, beta 16-byte aligned, ln_out 8-byte aligned,
+ *   leading dims multiples of 4; anything else: TB_ERR_UNSUPPORTED / TB_ERR_MISALIGNED (call tb_linear + tb_layernorm).
+ *   Variance is E[y^2] - E[y]^2 in fp32 (one pass over the accumulator registers). */
+int tb_linear_ln(const void* X, int ldx, const void* W, const float* bias, float* Y, int ldy, int M, int N, int K,
+                 const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post, int precision,
+                 const float* ln_gamma, const float* ln_beta, void* ln_out, int ld_ln, void* stream);
+
 /* LayerNorm over the last dim (eps 1e-5, affine) — transformer_rpe.py:156-171. flags bit 0: ReLU on the result (the
  * Linear -> LayerNorm -> ReLU layers of modules/mlp.py:47-51 with use_layernorm); bit 1: Y rows are IEEE fp16 (ldy in
  * halves, multiple of 8) — the operand a tb_linear precision-2 projection reads. D in {128,256}. */

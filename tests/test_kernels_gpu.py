@@ -697,3 +697,37 @@ def test_attention_head_interleaved_layout_argument_checks():
     with pytest.raises(RuntimeError):  # table base only 16-byte aligned
         ops.knarpe_attn(q[:, :d], q[:, d:], kv.view(-1)[8:8 + B * S * K * 2 * d].view(-1, 2 * d), S * K, 1, K, idx, inv,
                         rel, freq, B, S, d, H, interleaved=True, fast_trig=True)
+
+
+@pytest.mark.parametrize("M,K,extras", [(4096, 640, "mr"), (1000, 512, "rp"), (77, 128, ""), (65536, 640, "mr")])
+def test_linear_fused_layernorm(M, K, extras):
+    """tb_linear_ln: the projection's fp32 result is bit-identical to tb_linear's, and the fp16 LayerNorm rows written
+    by the same epilogue match LayerNorm of that result (eps 1e-5, transformer_rpe.py:156-171) to fp16 rounding.
+    Covers full and partial row blocks, residual / pre- and post-masks, many tiles per CTA."""
+    N = 128
+    g = torch.Generator().manual_seed(M + K)
+    x = (torch.randn(M, K, generator=g) * 0.7).half().to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).half().to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    res = (torch.randn(M, N, generator=g) * 2 + 0.5).to(DEV) if "r" in extras else None
+    mpre = (torch.rand(M, generator=g) < 0.1).to(DEV) if "m" in extras else None
+    mpost = (torch.rand(M, generator=g) < 0.1).to(DEV) if "p" in extras else None
+    gamma, beta = (torch.rand(N, generator=g) + 0.5).to(DEV), torch.randn(N, generator=g).to(DEV)
+    y0 = ops.linear(x, w, b, mask_pre=mpre, res=res, mask_post=mpost, precision=2)
+    y1, ln = ops.linear_ln(x, w, b, gamma, beta, mask_pre=mpre, res=res, mask_post=mpost, precision=2)
+    assert torch.equal(y0, y1)
+    ref = torch.nn.functional.layer_norm(y1.double(), (N,), gamma.double(), beta.double(), 1e-5)
+    err = float((ln.double() - ref).abs().max())
+    assert err < 4e-3 * max(1.0, float(ref.abs().max())), err  # fp16 output rounding (2^-11 relative)
+    ln2 = ops.layernorm(y1, gamma, beta, out_dtype=torch.float16)
+    assert float((ln.float() - ln2.float()).abs().max()) < 4e-3 * max(1.0, float(ref.abs().max()))
+
+
+def test_linear_fused_layernorm_argument_checks():
+    x = torch.zeros(256, 128, dtype=torch.float16, device=DEV)
+    g = torch.ones(256, device=DEV)
+    with pytest.raises(RuntimeError):  # N != 128
+        ops.linear_ln(x, torch.zeros(256, 128, dtype=torch.float16, device=DEV), None, g, g)
+    w = torch.zeros(128, 128, dtype=torch.float16, device=DEV)
+    with pytest.raises(RuntimeError):  # residual rows only 4-byte aligned
+        ops.linear_ln(x, w, None, g[:128], g[:128], res=torch.zeros(256, 132, device=DEV)[:, 1:129])

@@ -8,7 +8,8 @@ int tb_linear_f32(const float* X, int ldx, const float* W, const float* bias, in
 int tb_linear_tc(const void* X, int ldx, const void* W, int in_f16, const float* bias, int bias_group, float* Y,
                  int ldy, int M, int N, int K,
                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
-                 void* Yh, int ldyh, int colh, cudaStream_t st);
+                 void* Yh, int ldyh, int colh, cudaStream_t st, const float* ln_g = nullptr,
+                 const float* ln_b = nullptr, void* ln_out = nullptr, int ld_ln = 0);
 
 extern "C" const char* tb_strerror(int code) {
   switch (code) {
@@ -44,4 +45,17 @@ extern "C" int tb_linear(const void* X, int ldx, const void* W, const float* bia
     return tb_linear_tc(X, ldx, W, precision == 2, bias, bias_group, Y, ldy, M, N, K, relu, mask_pre, res, ldr,
                         mask_post, Yh, ldyh, col_h, st);
   return TB_ERR_UNSUPPORTED;
+}
+
+// Projection + residual + LayerNorm of the result in one launch (tensor-core mode): Y = X W^T + bias (+ masks / residual
+// as tb_linear) and ln_out = fp16(LayerNorm(Y) * gamma + beta), the operand rows of the next kind::f16 projection.
+extern "C" int tb_linear_ln(const void* X, int ldx, const void* W, const float* bias, float* Y, int ldy, int M, int N,
+                            int K, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
+                            int precision, const float* ln_gamma, const float* ln_beta, void* ln_out, int ld_ln,
+                            void* stream) {
+  if (!X || !W || !Y || !ln_gamma || !ln_beta || !ln_out) return TB_ERR_NULL;
+  if (M <= 0 || N <= 0 || K <= 0 || ldx < K || ldy < N || ld_ln < N || (res && ldr < N)) return TB_ERR_BAD_SHAPE;
+  if (precision != 1 && precision != 2) return TB_ERR_UNSUPPORTED;
+  return tb_linear_tc(X, ldx, W, precision == 2, bias, 0, Y, ldy, M, N, K, 0, mask_pre, res, ldr, mask_post, nullptr, 0, 0,
+                      static_cast<cudaStream_t>(stream), ln_gamma, ln_beta, ln_out, ld_ln);
 }

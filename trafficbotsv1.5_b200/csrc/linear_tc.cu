@@ -29,12 +29,16 @@ constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
 constexpr int NUM_THREADS = (EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 2 * BN;
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + 256;
+constexpr int LN_BYTES = 2 * 4 * 4 * 32 * 8;          // fused LayerNorm: (sum, sum of squares) partials [parity][quarter][col block][row]
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + LN_BYTES + 256;
 
 struct Epi {
   const float* bias; int bgroup; int relu; const uint8_t* mask_pre; const float* res; int ldr; const uint8_t* mask_post;
   __half* yh; int ldyh; int colh;  // columns >= colh (multiple of 32) are written as fp16 to yh[row*ldyh + col - colh]
+  // fused LayerNorm of the output rows (N == 128, one n tile): ln_out[row] = fp16(LN(Y[row]) * gamma + beta)
+  const float* ln_g; const float* ln_b; __half* ln_out; int ld_ln;
 };
+struct LnCtx { float2* part; uint32_t st_s; int quarter, half, parity; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -121,9 +125,10 @@ __device__ __forceinline__ void prefetch_rows(Prefetch& pf, int rsub, int rbase,
     if (rp) rp += rstep;
   }
 }
-template <bool RELU, bool TO_H, bool EXTRA, bool ALL>
+template <bool RELU, bool TO_H, bool EXTRA, bool ALL, bool LN = false>
 __device__ __forceinline__ void store_block(uint32_t st_s, int rsub, int cc, int rbase, int col, int M, float4 bv,
-                                            float* __restrict__ Y, int ldy, const Epi& ep, const Prefetch& pf) {
+                                            float* __restrict__ Y, int ldy, const Epi& ep, const Prefetch& pf,
+                                            const LnCtx* ln = nullptr) {
   const int row0 = rbase + rsub;
   float* yp = Y + (size_t)row0 * ldy + col;
   const size_t ystep = (size_t)4 * ldy;
@@ -156,8 +161,67 @@ __device__ __forceinline__ void store_block(uint32_t st_s, int rsub, int cc, int
       } else {
         *reinterpret_cast<float4*>(yp) = v;
       }
+      if (LN) vv[i] = v;
     }
     if (TO_H) hp += hstep; else yp += ystep;
+  }
+  if (LN) {
+    // ---- LayerNorm of the finished rows (transformer_rpe.py:156-171, eps 1e-5): a row's 128 columns sit in the four
+    // warps of this TMEM lane quarter. Per-row (sum, sum of squares) of this warp's 32 columns by a butterfly over the
+    // 8 lanes of a row group (7 shuffles per quantity; lane (rsub, cc) ends up owning row 4 cc + rsub), partials of the
+    // four warps through shared memory + a 128-thread named barrier, statistics back to the lanes through the warp's
+    // staging block.
+    const bool b2 = cc & 4, b1 = cc & 2, b0 = cc & 1;
+    float q1[8], q2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      q1[i] = (vv[i].x + vv[i].y) + (vv[i].z + vv[i].w);
+      q2[i] = fmaf(vv[i].x, vv[i].x, fmaf(vv[i].y, vv[i].y, fmaf(vv[i].z, vv[i].z, vv[i].w * vv[i].w)));
+    }
+    float t1[4], t2[4], u1[2], u2[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      t1[j] = (b2 ? q1[j + 4] : q1[j]) + __shfl_xor_sync(TB_FULL_MASK, b2 ? q1[j] : q1[j + 4], 4);
+      t2[j] = (b2 ? q2[j + 4] : q2[j]) + __shfl_xor_sync(TB_FULL_MASK, b2 ? q2[j] : q2[j + 4], 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      u1[j] = (b1 ? t1[j + 2] : t1[j]) + __shfl_xor_sync(TB_FULL_MASK, b1 ? t1[j] : t1[j + 2], 2);
+      u2[j] = (b1 ? t2[j + 2] : t2[j]) + __shfl_xor_sync(TB_FULL_MASK, b1 ? t2[j] : t2[j + 2], 2);
+    }
+    const float w1 = (b0 ? u1[1] : u1[0]) + __shfl_xor_sync(TB_FULL_MASK, b0 ? u1[0] : u1[1], 1);
+    const float w2 = (b0 ? u2[1] : u2[0]) + __shfl_xor_sync(TB_FULL_MASK, b0 ? u2[0] : u2[1], 1);
+    const int own = 4 * cc + rsub;  // the block row this lane now holds the 32-column sums of
+    float2* part = ln->part + (ln->parity * 4 + ln->quarter) * 4 * 32;
+    part[ln->half * 32 + own] = make_float2(w1, w2);
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + ln->quarter) : "memory");
+    float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float2 pp = part[h * 32 + own];
+      S1 += pp.x; S2 += pp.y;
+    }
+    const float mean = S1 * (1.f / BN);
+    const float rstd = 1.f / sqrtf(fmaxf(S2 * (1.f / BN) - mean * mean, 0.f) + 1e-5f);
+    __syncwarp();  // every lane has read its rows from the staging block
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(st_s + (uint32_t)own * 8u), "f"(mean), "f"(rstd) : "memory");
+    __syncwarp();
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(ep.ln_g + col));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(ep.ln_b + col));
+    __half* lp = ep.ln_out + (size_t)row0 * ep.ld_ln + col;
+    const size_t lstep = (size_t)4 * ep.ld_ln;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (ALL || row0 + 4 * i < M) {
+        float mu, rs;
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(mu), "=f"(rs) : "r"(st_s + (uint32_t)(4 * i + rsub) * 8u));
+        const __half2 h0 = __floats2half2_rn((vv[i].x - mu) * rs * gg.x + be.x, (vv[i].y - mu) * rs * gg.y + be.y);
+        const __half2 h1 = __floats2half2_rn((vv[i].z - mu) * rs * gg.z + be.z, (vv[i].w - mu) * rs * gg.w + be.w);
+        *reinterpret_cast<uint2*>(lp) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
+      lp += lstep;
+    }
   }
 }
 
@@ -172,7 +236,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   float* sE = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES) + EPI_BYTES);
+  float2* sLN = reinterpret_cast<float2*>(smem + STAGES * (A_BYTES + B_BYTES) + EPI_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + LN_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -267,7 +332,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (cbase >= N) break;  // warp-uniform
         const bool fast = vec_ok && cbase + 32 <= N;
         Prefetch pf;
-        if (extra && fast) {  // residual rows / row masks of this block: in flight while the accumulator completes
+        if ((extra || ep.ln_out) && fast) {  // residual rows / row masks of this block: in flight while the accumulator completes
           if (all_rows) prefetch_rows<true>(pf, rsub, rbase, cbase + cc * 4, M, ep);
           else prefetch_rows<false>(pf, rsub, rbase, cbase + cc * 4, M, ep);
         }
@@ -320,7 +385,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (all_rows) store_block<R, H, X, true>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf);   \
     else store_block<R, H, X, false>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf);           \
   } while (0)
-          if (extra) {
+          if (ep.ln_out) {  // host guarantees: N == BN, fp32 output, this (vectorised) path
+            const LnCtx ln{sLN, st_s, quarter, half, lt & 1};
+            if (all_rows) store_block<false, false, true, true, true>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf, &ln);
+            else store_block<false, false, true, false, true>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf, &ln);
+          } else if (extra) {
             if (ep.relu) { if (to_h) TB_STORE(true, true, true); else TB_STORE(true, false, true); }
             else { if (to_h) TB_STORE(false, true, true); else TB_STORE(false, false, true); }
           } else {
@@ -396,9 +465,16 @@ bool make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int
 int tb_linear_tc(const void* X, int ldx, const void* W, int in_f16, const float* bias, int bias_group, float* Y,
                  int ldy, int M, int N, int K,
                  int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
-                 void* Yh, int ldyh, int colh, cudaStream_t st) {
+                 void* Yh, int ldyh, int colh, cudaStream_t st, const float* ln_g, const float* ln_b, void* ln_out,
+                 int ld_ln) {
   const int ea = in_f16 ? 8 : 4;  // elements per 16 bytes: TMA needs 16-byte aligned rows
   const bool ok = (K % ea == 0) && (ldx % ea == 0) && tb_aligned16(X) && tb_aligned16(W);
+  if (ln_out) {  // fused LayerNorm: one n tile, the vectorised epilogue path, no ReLU / fp16 split / grouped bias
+    if (!ok || N != BN || relu || Yh || bias_group) return TB_ERR_UNSUPPORTED;
+    if ((ldy & 3) || !tb_aligned16(Y) || (res && ((ldr & 3) || !tb_aligned16(res))) || (bias && !tb_aligned16(bias)) ||
+        !tb_aligned16(ln_g) || !tb_aligned16(ln_b) || (ld_ln & 3) || (reinterpret_cast<uintptr_t>(ln_out) & 7))
+      return TB_ERR_MISALIGNED;
+  }
   if (!ok) {
     if (Yh || in_f16) return TB_ERR_UNSUPPORTED;  // the fp32 kernel has no fp16 input / output path
     return tb_linear_f32(static_cast<const float*>(X), ldx, static_cast<const float*>(W), bias, bias_group, Y, ldy, M, N, K,
@@ -425,7 +501,8 @@ int tb_linear_tc(const void* X, int ldx, const void* W, int in_f16, const float*
   }
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms ? total : num_sms;  // persistent: one CTA per SM
-  Epi ep{bias, bias_group, relu, mask_pre, res, ldr, mask_post, static_cast<__half*>(Yh), ldyh, colh};
+  Epi ep{bias, bias_group, relu, mask_pre, res, ldr, mask_post, static_cast<__half*>(Yh), ldyh, colh,
+         ln_g, ln_b, static_cast<__half*>(ln_out), ld_ln};
   if (in_f16) linear_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
   else linear_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
   TB_CHECK_LAUNCH();

@@ -17,7 +17,7 @@ _SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "knarpe_attn_mma.cu", "
             "rollout_step.cu", "rule_check.cu"]
 _lib = None
 
-EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_linear", "tb_layernorm",
+EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_linear", "tb_linear_ln", "tb_layernorm",
            "tb_pointnet_pool", "tb_pose_emb", "tb_ag_featurize", "tb_tl_featurize", "tb_dyn_step", "tb_tl_step",
            "tb_step_advance", "tb_gather_rows", "tb_action_mean", "tb_rule_check", "tb_future_filter",
            "tb_traj_global", "tb_womd_post", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd"]
@@ -56,6 +56,7 @@ def load() -> ctypes.CDLL:
         "tb_knn_select": [P, P, P, P, I, I, I, I, I, F, P, P, P, I, I, P, P, I, P],
         "tb_knarpe_attn": [P, I, P, I, P, I, I, I, I, P, I, I, I, I, P, P, P, P, P, I, I, I, I, P, P, I, P, I, P],
         "tb_linear": [P, I, P, P, I, P, I, I, I, I, I, P, P, I, P, I, P, I, I, P],
+        "tb_linear_ln": [P, I, P, P, P, I, I, I, I, P, P, I, P, I, P, P, P, I, P],
         "tb_layernorm": [P, I, P, P, P, I, I, I, I, P],
         "tb_pointnet_pool": [P, I, P, I, I, I, I, P, I, P],
         "tb_pose_emb": [P, P, I, P, I, I, P, I, P],

@@ -228,47 +228,78 @@ class HotPathModel:
             self._w_half[key] = w.to(torch.float16).contiguous()
         return self._w_half[key]
 
-    def _out_proj(self, p: str, f: dict, o: Tensor, nv: Tensor, res: Tensor) -> Tensor:
-        """Output projection over [ov|z] (fp16 rows in tensor-core mode -> kind::f16 MMA, fp32 accumulate/residual)."""
+    @property
+    def ln_fused(self) -> bool:
+        """LayerNorm of the residual stream inside the epilogue of the projection that produces it (tb_linear_ln)."""
+        return self.kv_half and self.d == 128 and os.environ.get("TB_LN_FUSED", "1") != "0"
+
+    def _out_proj(self, p: str, f: dict, o: Tensor, nv: Tensor, res: Tensor, ln_next: Optional[str] = None):
+        """Output projection over [ov|z] (fp16 rows in tensor-core mode -> kind::f16 MMA, fp32 accumulate/residual).
+        `ln_next`: name of the LayerNorm applied to the result next -> returns (result, fp16 LN rows) from one launch."""
         if o.dtype == torch.float16:
-            return ops.linear(o, self._half(f"{p}.w_out", f["w_out"]), f["b_out"], mask_pre=nv, res=res, precision=2)
-        return ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=res, precision=self.precision)
+            w = self._half(f"{p}.w_out", f["w_out"])
+            if ln_next is not None and self.ln_fused:
+                return ops.linear_ln(o, w, f["b_out"], self.P[f"{ln_next}.weight"], self.P[f"{ln_next}.bias"], mask_pre=nv,
+                                     res=res, precision=2)
+            y = ops.linear(o, w, f["b_out"], mask_pre=nv, res=res, precision=2)
+        else:
+            y = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=res, precision=self.precision)
+        return y if ln_next is None else (y, self.ln(y, ln_next, half=self.kv_half))
 
     def tf_layer(self, p: str, mode: str, src: Tensor, src_inv: Tensor, B: int, S: int, knn_self: dict,
-                 cross: Optional[dict] = None, out: Optional[Tensor] = None, before_self=None, before_cross=None) -> Tensor:
+                 cross: Optional[dict] = None, out: Optional[Tensor] = None, before_self=None, before_cross=None,
+                 ln_in: Optional[Tensor] = None, ln_next: Optional[str] = None):
         """TransformerRPE.forward (transformer_rpe.py:175-245), eval mode. `before_self` / `before_cross` are join
-        hooks called right before the self / cross attention launch (streams that produce the neighbour lists)."""
+        hooks called right before the self / cross attention launch (streams that produce the neighbour lists).
+        `ln_in`: the layer's first LayerNorm already applied to `src` (by the previous layer's epilogue);
+        `ln_next`: name of the LayerNorm the caller applies to the result next -> returns (result, LN rows)."""
         d, pr = self.d, self.precision
         if mode == "dec_cross_attn":
             f = self.fa[f"{p}.attn_src"]
-            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm_src", half=self.kv_half), knn_self["idx"].shape[-1],
-                                     f"{p}.attn_src")
+            x0 = ln_in if ln_in is not None else self.ln(src, f"{p}.norm_src", half=self.kv_half)
+            proj, kv = self._in_self(f, x0, knn_self["idx"].shape[-1], f"{p}.attn_src")
             if before_self is not None:
                 before_self()
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
-            src = self._out_proj(f"{p}.attn_src", f, o, nv, src)
+            src, x1 = self._out_proj(f"{p}.attn_src", f, o, nv, src, ln_next=f"{p}.norm1")
             f = self.fa[f"{p}.attn"]
-            proj = self._in_q(f, self.ln(src, f"{p}.norm1", half=self.kv_half), f"{p}.attn")
+            proj = self._in_q(f, x1, f"{p}.attn")
             if before_cross is not None:
                 before_cross()
             o, nv = self._attend(f, proj, B, S, cross["kv0"], cross["T0"], cross["div0"], cross["K0"], cross,
                                  cross.get("kv1"), cross.get("T1", 0), cross.get("div1", 1), cross.get("K1", 0))
-            src = self._out_proj(f"{p}.attn", f, o, nv, src)
+            src, x2 = self._out_proj(f"{p}.attn", f, o, nv, src, ln_next=f"{p}.norm2")
         else:  # enc_self_attn: q and k/v both from norm1(src) (:218-221)
             f = self.fa[f"{p}.attn"]
-            proj, kv = self._in_self(f, self.ln(src, f"{p}.norm1", half=self.kv_half), knn_self["idx"].shape[-1],
-                                     f"{p}.attn")
+            x0 = ln_in if ln_in is not None else self.ln(src, f"{p}.norm1", half=self.kv_half)
+            proj, kv = self._in_self(f, x0, knn_self["idx"].shape[-1], f"{p}.attn")
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
-            src = self._out_proj(f"{p}.attn", f, o, nv, src)
-        x2 = self.ln(src, f"{p}.norm2", half=self.kv_half)
+            src, x2 = self._out_proj(f"{p}.attn", f, o, nv, src, ln_next=f"{p}.norm2")
         if self.kv_half:  # FFN hidden (ReLU output) as fp16: written by the first projection, read by a kind::f16 one
             h = torch.empty(x2.shape[0], self.P[f"{p}.linear1.weight"].shape[0], dtype=torch.float16, device=x2.device)
             self._proj(x2, f"{p}.linear1", self.P[f"{p}.linear1.weight"], self.P[f"{p}.linear1.bias"], relu=True, out_h=h,
                        col_h=0)
-            return ops.linear(h, self._half(f"{p}.linear2", self.P[f"{p}.linear2.weight"]), self.P[f"{p}.linear2.bias"],
-                              res=src, mask_post=src_inv, out=out, precision=2)
-        h = self.lin(x2, f"{p}.linear1", relu=True)
-        return self.lin(h, f"{p}.linear2", res=src, mask_post=src_inv, out=out)
+            w2 = self._half(f"{p}.linear2", self.P[f"{p}.linear2.weight"])
+            if ln_next is not None and self.ln_fused:  # the next layer's first LayerNorm rides on this epilogue
+                return ops.linear_ln(h, w2, self.P[f"{p}.linear2.bias"], self.P[f"{ln_next}.weight"],
+                                     self.P[f"{ln_next}.bias"], res=src, mask_post=src_inv, out=out, precision=2)
+            y = ops.linear(h, w2, self.P[f"{p}.linear2.bias"], res=src, mask_post=src_inv, out=out, precision=2)
+        else:
+            h = self.lin(x2, f"{p}.linear1", relu=True)
+            y = self.lin(h, f"{p}.linear2", res=src, mask_post=src_inv, out=out)
+        return y if ln_next is None else (y, self.ln(y, ln_next, half=self.kv_half))
+
+    def tf_stack(self, prefix: str, n_layer: int, mode: str, tok: Tensor, layer_kw) -> Tensor:
+        """n_layer TransformerRPE layers; layer i's closing projection also produces layer i+1's first LayerNorm rows
+        (tb_linear_ln) when the tensor-core mode allows it. `layer_kw(i)` -> (positional args after src, kwargs)."""
+        first = "norm_src" if mode == "dec_cross_attn" else "norm1"
+        ln_in = None
+        for i in range(n_layer):
+            args, kw = layer_kw(i)
+            nxt = f"{prefix}.{i + 1}.{first}" if (i + 1 < n_layer and self.ln_fused) else None
+            r = self.tf_layer(f"{prefix}.{i}", mode, tok, *args, ln_in=ln_in, ln_next=nxt, **kw)
+            tok, ln_in = r if nxt is not None else (r, None)
+        return tok
 
     # ------------------------------------------------------------------------------------------ map (once / scene)
     def map_encoder(self, mp_valid: Tensor, mp_attr: Tensor, mp_pose: Tensor) -> Dict[str, Tensor]:
@@ -294,8 +325,8 @@ class HotPathModel:
         idx, inv, rel = ops.knn_select(tok_pose, tok_inv, tok_pose, tok_inv, sz["k_mp2mp"], sz["dl_mp"])
         knn = dict(idx=idx, inv=inv, rel=rel)
         flat_inv = tok_inv.reshape(-1).contiguous()
-        for i in range(self.cfg["mp_encoder"]["n_layer_tf"]):
-            tok = self.tf_layer(f"mp_encoder.tf_mp2mp.layers.{i}", "enc_self_attn", tok, flat_inv, n_sc, n_mp, knn)
+        tok = self.tf_stack("mp_encoder.tf_mp2mp.layers", self.cfg["mp_encoder"]["n_layer_tf"], "enc_self_attn", tok,
+                            lambda i: ((flat_inv, n_sc, n_mp, knn), {}))
         # x-sorted copy of the (static) token poses for the per-step agent -> map select (tb_knn_select row_state)
         order = torch.argsort(tok_pose[..., 0], dim=1)
         return dict(mp_token_invalid=tok_inv.contiguous(), mp_token_feature=tok.view(n_sc, n_mp, d),
@@ -344,9 +375,9 @@ class HotPathModel:
         tok = self.pointnet(x, row_inv, Bt * n_tl, W, "tl_encoder.temp_encoder")                      # :228
         flat_inv = tl["tl_token_invalid"].reshape(-1)
         nl = self.cfg["tl_encoder"]["n_layer_tf"]
-        for i in range(nl):
-            tok = self.tf_layer(f"tl_encoder.tf_tl2tlmp.layers.{i}", "dec_cross_attn", tok, flat_inv, Bt, n_tl,
-                                tl["knn_self"], tl["cross"][i], out=out_feat if i == nl - 1 else None)  # :231-240
+        tok = self.tf_stack("tl_encoder.tf_tl2tlmp.layers", nl, "dec_cross_attn", tok,                  # :231-240
+                            lambda i: ((flat_inv, Bt, n_tl, tl["knn_self"], tl["cross"][i]),
+                                       dict(out=out_feat if i == nl - 1 else None)))
         logits = self.mlp(tok, "tl_state_predictor.mlp", (0, 2, 4), False, out=out_logits)            # :284
         return tok, logits
 
@@ -452,14 +483,16 @@ class HotPathModel:
             if before_tl is not None and kv_tl is not None:
                 before_tl()
 
-        for i in range(nl):
+        def layer_kw(i):
             p = f"ag_encoder.tf_ag2agmptl.layers.{i}"
             kv1 = kv_tl[i] if kv_tl is not None else self.kv_table(tl_feat, p, "norm_tgt")
             cross = dict(kv0=kv_mp[i], T0=n_mp, div0=R, K0=sz["k_ag2mp"], kv1=kv1, T1=n_tl, div1=tl_div,
                          K1=sz["k_ag2tl"], idx=cidx, inv=cinv, rel=crel)
-            tok = self.tf_layer(p, "dec_cross_attn", tok, flat_inv, B, A, knn_self, cross,
-                                out=out if i == nl - 1 else None, before_self=join_self if i == 0 else None,
-                                before_cross=join_first_cross if i == 0 else None)
+            return (flat_inv, B, A, knn_self, cross), dict(out=out if i == nl - 1 else None,
+                                                           before_self=join_self if i == 0 else None,
+                                                           before_cross=join_first_cross if i == 0 else None)
+
+        tok = self.tf_stack("ag_encoder.tf_ag2agmptl.layers", nl, "dec_cross_attn", tok, layer_kw)
         return tok
 
     def ag_tl_tables(self, tl_feat: Tensor, out: Optional[list] = None) -> list:

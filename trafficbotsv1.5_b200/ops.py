@@ -136,6 +136,29 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False,
     return out
 
 
+def linear_ln(x: Tensor, w: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Tensor, mask_pre: Optional[Tensor] = None,
+              res: Optional[Tensor] = None, mask_post: Optional[Tensor] = None, out: Optional[Tensor] = None,
+              precision: int = 2) -> Tuple[Tensor, Tensor]:
+    """tb_linear_ln: (Y, fp16 LayerNorm(Y) * gamma + beta) from one launch; N must be 128 (tensor-core mode)."""
+    in_dt = torch.float16 if precision == 2 else torch.float32
+    assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.dtype == in_dt and w.dtype == in_dt
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and gamma.shape == (N,) and beta.shape == (N,)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    if res is not None:
+        assert res.stride(1) == 1 and res.shape == (M, N)
+    ln_out = torch.empty(M, N, dtype=torch.float16, device=x.device)
+    L.check(L.load().tb_linear_ln(L.ptr(x), x.stride(0), L.ptr(w), L.ptr(b), L.ptr(out), out.stride(0), M, N, K,
+                                  L.ptr(_u8(mask_pre)), L.ptr(res), res.stride(0) if res is not None else 0,
+                                  L.ptr(_u8(mask_post)), precision, L.ptr(_f32c(gamma)), L.ptr(_f32c(beta)),
+                                  L.ptr(ln_out), ln_out.stride(0), L.stream()), "tb_linear_ln")
+    _count()
+    return out, ln_out
+
+
 def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, out: Optional[Tensor] = None, relu: bool = False,
               out_dtype: torch.dtype = torch.float32) -> Tensor:
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
