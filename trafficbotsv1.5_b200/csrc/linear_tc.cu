@@ -226,7 +226,8 @@ __device__ __forceinline__ void store_block(uint32_t st_s, int rsub, int cc, int
 }
 
 // F16: operands are fp16 in memory (kind::f16, 64 elements per k-block) instead of fp32 read as tf32 (32 per k-block)
-template <bool F16>
+// LN: the fused-LayerNorm epilogue (its own instantiation: its register pressure must not leak into the others)
+template <bool F16, bool LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  float* __restrict__ Y, int ldy, int M, int N, int K, Epi ep) {
@@ -332,7 +333,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (cbase >= N) break;  // warp-uniform
         const bool fast = vec_ok && cbase + 32 <= N;
         Prefetch pf;
-        if ((extra || ep.ln_out) && fast) {  // residual rows / row masks of this block: in flight while the accumulator completes
+        if ((extra || LN) && fast) {  // residual rows / row masks of this block: in flight while the accumulator completes
           if (all_rows) prefetch_rows<true>(pf, rsub, rbase, cbase + cc * 4, M, ep);
           else prefetch_rows<false>(pf, rsub, rbase, cbase + cc * 4, M, ep);
         }
@@ -385,10 +386,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (all_rows) store_block<R, H, X, true>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf);   \
     else store_block<R, H, X, false>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf);           \
   } while (0)
-          if (ep.ln_out) {  // host guarantees: N == BN, fp32 output, this (vectorised) path
+          if (LN) {  // host guarantees: N == BN, fp32 output, this (vectorised) path
             const LnCtx ln{sLN, st_s, quarter, half, lt & 1};
-            if (all_rows) store_block<false, false, true, true, true>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf, &ln);
-            else store_block<false, false, true, false, true>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf, &ln);
+            if (all_rows) store_block<false, false, true, true, LN>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf, &ln);
+            else store_block<false, false, true, false, LN>(st_s, rsub, cc, rbase, col, M, bv, Y, ldy, ep, pf, &ln);
           } else if (extra) {
             if (ep.relu) { if (to_h) TB_STORE(true, true, true); else TB_STORE(true, false, true); }
             else { if (to_h) TB_STORE(false, true, true); else TB_STORE(false, false, true); }
@@ -484,10 +485,14 @@ int tb_linear_tc(const void* X, int ldx, const void* W, int in_f16, const float*
   if (!make_map(&mapA, X, M, K, ldx, BM, in_f16) || !make_map(&mapB, W, N, K, K, BN, in_f16)) return TB_ERR_CUDA;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
-            cudaSuccess)
+    if (cudaFuncSetAttribute(linear_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(linear_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(linear_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(linear_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_BYTES) != cudaSuccess)
       return TB_ERR_CUDA;
     attr_set = true;
   }
@@ -503,8 +508,13 @@ int tb_linear_tc(const void* X, int ldx, const void* W, int in_f16, const float*
   const int grid = total < num_sms ? total : num_sms;  // persistent: one CTA per SM
   Epi ep{bias, bias_group, relu, mask_pre, res, ldr, mask_post, static_cast<__half*>(Yh), ldyh, colh,
          ln_g, ln_b, static_cast<__half*>(ln_out), ld_ln};
-  if (in_f16) linear_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
-  else linear_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
+  if (ln_out) {
+    if (in_f16) linear_tc_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
+    else linear_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
+  } else {
+    if (in_f16) linear_tc_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
+    else linear_tc_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
+  }
   TB_CHECK_LAUNCH();
   return TB_OK;
 }
