@@ -493,3 +493,22 @@ def test_rollout_head_interleaved_layout_is_bit_identical(golden_rollout, monkey
     res2 = eng2.rollout(batch)
     for k in ("pred_pose", "pred_motion", "pred_valid", "tl_state"):
         assert torch.equal(res[k], res2[k]), k
+
+
+@pytest.mark.gpu
+def test_rollout_fused_layernorm_vs_separate(golden_rollout, monkeypatch):
+    """tb_linear_ln (LayerNorm inside the producing projection's epilogue, one-pass variance) against the separate
+    tb_layernorm launches (two-pass): same closed-loop rollout within the tensor-core mode's rounding."""
+    g = golden_rollout
+    eng, batch, P, cfg = _engine(g["shape"], g["R"], g["T"], precision=1)
+    assert eng.model.ln_fused
+    res = {k: v.clone() for k, v in eng.rollout(batch).items() if torch.is_tensor(v)}
+    n_fused = eng.launches_per_step
+    monkeypatch.setenv("TB_LN_FUSED", "0")
+    eng2, _, _, _ = _engine(g["shape"], g["R"], g["T"], precision=1)
+    assert not eng2.model.ln_fused
+    res2 = eng2.rollout(batch)
+    assert eng2.launches_per_step > n_fused
+    assert maxerr(res["pred_pose"][..., :2], res2["pred_pose"][..., :2]) < 5e-3
+    assert maxerr(res["pred_pose"][..., 2], res2["pred_pose"][..., 2]) < 2e-3
+    assert torch.equal(res["pred_valid"], res2["pred_valid"]) and torch.equal(res["tl_state"], res2["tl_state"])
