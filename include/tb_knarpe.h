@@ -197,11 +197,14 @@ int tb_ag_featurize(const uint8_t* hist_valid, const float* hist_pose, const flo
  *   wblob: tb_ag_frontend_blob_halves() fp16 values = the six weight matrices, row-major [64 outputs][inputs] with
  *   row strides 40 (W1, inputs zero-padded to 32), 72 (W2, W3), 136 (P0, P1, P2), in that order; bias: fp32 [6][64].
  *   tok_out [B*A, 128] fp32 (ld ldo): zeros for agents without a valid step; tok_pose [B,A,3], tok_invalid [B,A].
+ *   ln_out (may be NULL): fp16 rows [B*A, 128] (ld ld_ln, multiple of 2) = LayerNorm(token) * ln_gamma + ln_beta, eps
+ *   1e-5 — the first LayerNorm of the agent transformer (transformer_rpe.py:156-171) from the same warp.
  * W <= 16 (one MMA tile of history rows). */
 int tb_ag_frontend_blob_halves(void);
 int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion, const float* ag_attr,
                    const int* d_step, const float* freq_xy, int B, int A, int W, const void* wblob, const float* bias,
-                   float* tok_out, int ldo, float* tok_pose, uint8_t* tok_invalid, void* stream);
+                   float* tok_out, int ldo, float* tok_pose, uint8_t* tok_invalid, const float* ln_gamma,
+                   const float* ln_beta, void* ln_out, int ld_ln, void* stream);
 
 /* Traffic-light history rows — traffic_light.py:223-225: [state5 | one-hot11] per (b,tl,window slot).
  *   hist_tl [B,TL,W,5] u8 one-hot, tl_invalid [B,TL]; out rows [B*TL*W,16] (ld lda), row_invalid [B,TL,W]. */

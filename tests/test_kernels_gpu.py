@@ -495,9 +495,17 @@ def test_ag_frontend_fused_vs_oracle(s):
     tp, ti = torch.empty(B, A, 3, device=DEV), torch.empty(B, A, dtype=torch.uint8, device=DEV)
     step = torch.tensor([s], dtype=torch.int32, device=DEV)
     rv, rp, rm, at = dv(ring_v), dv(ring_p), dv(ring_m), dv(attr)
+    gen = torch.Generator().manual_seed(s)
+    ln_g, ln_b = (torch.rand(d, generator=gen) + 0.5).to(DEV), torch.randn(d, generator=gen).to(DEV)
+    ln = torch.full((B * A, d + 8), 7.0, dtype=torch.float16, device=DEV)
     L.check(L.load().tb_ag_frontend(L.ptr(rv), L.ptr(rp), L.ptr(rm), L.ptr(at), L.ptr(step), L.ptr(m.freq_ag), B, A, W,
-                                    L.ptr(blob), L.ptr(bias), L.ptr(tok), d + 8, L.ptr(tp), L.ptr(ti), L.stream()),
+                                    L.ptr(blob), L.ptr(bias), L.ptr(tok), d + 8, L.ptr(tp), L.ptr(ti), L.ptr(ln_g),
+                                    L.ptr(ln_b), L.ptr(ln), d + 8, L.stream()),
             "tb_ag_frontend")
+    # the fused first LayerNorm: LayerNorm of the token the kernel wrote, fp16 rows, padding untouched
+    ln_ref = torch.nn.functional.layer_norm(tok[:, :d].double(), (d,), ln_g.double(), ln_b.double(), 1e-5)
+    assert float((ln[:, :d].double() - ln_ref).abs().max()) < 4e-3 * max(1.0, float(ln_ref.abs().max()))
+    assert float((ln[:, d:].float() - 7.0).abs().max()) == 0.0
     assert torch.equal(ti.cpu().bool(), ~hv.any(-1)) and float((tp.cpu() - tok_pose).abs().max()) == 0.0
     out = tok[:, :d].cpu().view(B, A, d)
     scale = float(ref.abs().max())

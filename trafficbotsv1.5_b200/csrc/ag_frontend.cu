@@ -94,7 +94,9 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
                    const float* __restrict__ hist_motion, const float* __restrict__ ag_attr,
                    const int* __restrict__ d_step, const float* __restrict__ freq_xy, int n_ag_tot, int W,
                    const __half* __restrict__ wblob, const float* __restrict__ bias, float* __restrict__ tok_out,
-                   int ldo, float* __restrict__ tok_pose, uint8_t* __restrict__ tok_invalid) {
+                   int ldo, float* __restrict__ tok_pose, uint8_t* __restrict__ tok_invalid,
+                   const float* __restrict__ ln_g, const float* __restrict__ ln_b, __half* __restrict__ ln_out,
+                   int ld_ln) {
   extern __shared__ __align__(16) unsigned char smem[];
   __half* sW = reinterpret_cast<__half*>(smem);
   float* sB = reinterpret_cast<float*>(smem + (size_t)W_HALVES * 2);
@@ -217,6 +219,25 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
     float* op = tok_out + (size_t)ba * ldo + 8 * g + 2 * t;
     *reinterpret_cast<float2*>(op) = o;
     *reinterpret_cast<float2*>(op + 64) = o;
+    if (ln_out) {  // LayerNorm of the 128-wide token = of its 64 distinct values (each lane holds two of them)
+      float sum = o.x + o.y;
+#pragma unroll
+      for (int of = 16; of; of >>= 1) sum += __shfl_xor_sync(TB_FULL_MASK, sum, of);
+      const float mean = sum * (1.f / 64.f);
+      const float dx = o.x - mean, dy = o.y - mean;
+      float sq = fmaf(dx, dx, dy * dy);
+#pragma unroll
+      for (int of = 16; of; of >>= 1) sq += __shfl_xor_sync(TB_FULL_MASK, sq, of);
+      const float rstd = 1.f / sqrtf(sq * (1.f / 64.f) + 1e-5f);
+      const int c0 = 8 * g + 2 * t;
+      __half* lp = ln_out + (size_t)ba * ld_ln + c0;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const float2 gg = *reinterpret_cast<const float2*>(ln_g + c0 + 64 * hlf);
+        const float2 bb = *reinterpret_cast<const float2*>(ln_b + c0 + 64 * hlf);
+        *reinterpret_cast<__half2*>(lp + 64 * hlf) = __floats2half2_rn(dx * rstd * gg.x + bb.x, dy * rstd * gg.y + bb.y);
+      }
+    }
   }
 }
 
@@ -227,13 +248,21 @@ extern "C" int tb_ag_frontend_blob_halves(void) { return W_HALVES; }
 extern "C" int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
                               const float* ag_attr, const int* d_step, const float* freq_xy, int B, int A, int W,
                               const void* wblob, const float* bias, float* tok_out, int ldo, float* tok_pose,
-                              uint8_t* tok_invalid, void* stream) {
+                              uint8_t* tok_invalid, const float* ln_gamma, const float* ln_beta, void* ln_out, int ld_ln,
+                              void* stream) {
   if (!hist_valid || !hist_pose || !hist_motion || !ag_attr || !d_step || !freq_xy || !wblob || !bias || !tok_out ||
       !tok_pose || !tok_invalid)
     return TB_ERR_NULL;
   if (B <= 0 || A <= 0 || W <= 0 || ldo < 128) return TB_ERR_BAD_SHAPE;
   if (W > 16 || 9 + W > 32) return TB_ERR_UNSUPPORTED;
   if ((ldo & 1) || !tb_aligned16(wblob) || (reinterpret_cast<uintptr_t>(tok_out) & 7)) return TB_ERR_MISALIGNED;
+  if (ln_out) {
+    if (!ln_gamma || !ln_beta) return TB_ERR_NULL;
+    if (ld_ln < 128) return TB_ERR_BAD_SHAPE;
+    if ((ld_ln & 1) || (reinterpret_cast<uintptr_t>(ln_out) & 3) || (reinterpret_cast<uintptr_t>(ln_gamma) & 7) ||
+        (reinterpret_cast<uintptr_t>(ln_beta) & 7))
+      return TB_ERR_MISALIGNED;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(ag_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess)
@@ -252,7 +281,7 @@ extern "C" int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose,
   const int grid = want < 2 * num_sms ? want : 2 * num_sms;  // persistent: 2 CTAs per SM, warps loop over agents
   ag_frontend_kernel<<<grid, AW * 32, SMEM, static_cast<cudaStream_t>(stream)>>>(
       hist_valid, hist_pose, hist_motion, ag_attr, d_step, freq_xy, n, W, static_cast<const __half*>(wblob), bias,
-      tok_out, ldo, tok_pose, tok_invalid);
+      tok_out, ldo, tok_pose, tok_invalid, ln_gamma, ln_beta, static_cast<__half*>(ln_out), ld_ln);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

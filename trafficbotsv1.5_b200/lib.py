@@ -72,7 +72,7 @@ def load() -> ctypes.CDLL:
         "tb_future_filter": [P, P, P, I, I, I, I, I, F, I, P, P, P],
         "tb_traj_global": [P, P, P, P, I, I, I, I, I, I, P, P, P],
         "tb_womd_post": [P, P, P, I, I, I, I, I, I, I, F, F, F, F, I, I, I, P, P, P, P],
-        "tb_ag_frontend": [P, P, P, P, P, P, I, I, I, P, P, P, I, P, P, P],
+        "tb_ag_frontend": [P, P, P, P, P, P, I, I, I, P, P, P, I, P, P, P, P, P, I, P],
         "tb_ag_frontend_blob_halves": [],
         "tb_knarpe_attn_bwd": [P, I, P, I, P, I, I, I, I, P, I, I, I, I, P, P, P, P, I, I, I, I, P, P, I, P, I, P, P, P],
     }

@@ -289,11 +289,11 @@ class HotPathModel:
             y = self.lin(h, f"{p}.linear2", res=src, mask_post=src_inv, out=out)
         return y if ln_next is None else (y, self.ln(y, ln_next, half=self.kv_half))
 
-    def tf_stack(self, prefix: str, n_layer: int, mode: str, tok: Tensor, layer_kw) -> Tensor:
+    def tf_stack(self, prefix: str, n_layer: int, mode: str, tok: Tensor, layer_kw, ln_in: Optional[Tensor] = None
+                 ) -> Tensor:
         """n_layer TransformerRPE layers; layer i's closing projection also produces layer i+1's first LayerNorm rows
         (tb_linear_ln) when the tensor-core mode allows it. `layer_kw(i)` -> (positional args after src, kwargs)."""
         first = "norm_src" if mode == "dec_cross_attn" else "norm1"
-        ln_in = None
         for i in range(n_layer):
             args, kw = layer_kw(i)
             nxt = f"{prefix}.{i + 1}.{first}" if (i + 1 < n_layer and self.ln_fused) else None
@@ -460,10 +460,18 @@ class HotPathModel:
             blob, bias = self._ag_frontend_weights()
             tok = torch.empty(M, d, device=self.dev)
             tp2, ti2 = torch.empty_like(tok_pose), torch.empty_like(tok_inv)  # same values as tok_pose / tok_inv
+            ln0 = None
+            if self.ln_fused:  # the first LayerNorm of the agent transformer rides on the encoder's epilogue
+                ln0 = torch.empty(M, d, dtype=torch.float16, device=self.dev)
+                nm = "ag_encoder.tf_ag2agmptl.layers.0.norm_src"
+                ln_args = (L.ptr(self.P[f"{nm}.weight"]), L.ptr(self.P[f"{nm}.bias"]), L.ptr(ln0), d)
+            else:
+                ln_args = (None, None, None, 0)
             L.check(L.load().tb_ag_frontend(*hist, L.ptr(blob), L.ptr(bias), L.ptr(tok), d, L.ptr(tp2),
-                                            L.ptr(ops._u8(ti2)), L.stream()), "tb_ag_frontend")          # :130-162
+                                            L.ptr(ops._u8(ti2)), *ln_args, L.stream()), "tb_ag_frontend")  # :130-162
             ops._count()
         else:
+            ln0 = None
             self.mlp(attr, "ag_encoder.input_encoder.mlp", (0, 2, 4), False, out=x[:, : d // 2])      # :159
             tok = self.pointnet(x, row_inv, M, W, "ag_encoder.temp_encoder")                          # :162
         if knn_stream is None:
@@ -492,7 +500,7 @@ class HotPathModel:
                                                            before_self=join_self if i == 0 else None,
                                                            before_cross=join_first_cross if i == 0 else None)
 
-        tok = self.tf_stack("ag_encoder.tf_ag2agmptl.layers", nl, "dec_cross_attn", tok, layer_kw)
+        tok = self.tf_stack("ag_encoder.tf_ag2agmptl.layers", nl, "dec_cross_attn", tok, layer_kw, ln_in=ln0)
         return tok
 
     def ag_tl_tables(self, tl_feat: Tensor, out: Optional[list] = None) -> list:
