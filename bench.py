@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU")
     ap.add_argument("--rollouts", type=int, default=32)
     ap.add_argument("--precision", type=int, default=1,
-                    help="1 (default): tcgen05 kind::tf32 projections, fp32 everything else; 0: fp32 FFMA projections")
+                    help="1 (default): tcgen05 kind::tf32 / kind::f16 projections with fp16 K|V, q|u, ov|z, FFN-hidden and "
+                         "LayerNorm rows (fp32 accumulators, residual stream and rollout state); 0: fp32 everywhere")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp32 / rule-check extra measurements")
     ap.add_argument("--rule-checks", action="store_true",
@@ -109,6 +110,50 @@ def cpu_rollout_rate(n_threads, n_sc=1, R=8, iters=6):
     sample = (f"{n_sc} scene x {R} rollouts x {iters} policy iterations (128 agents, 1024 polylines, 40 TL) in "
               f"{dt:.1f} s; scaled to 80 counted of 90 iterations")
     return rate, sample, per_iter
+
+
+def eager_cuda_rate(dev, n_sc, R, iters, autocast):
+    """The bar SURVEY 8(d) / BASELINE.md 3.2 name: the reference's own operation order (gather-then-project KNARPE,
+    materialised [B,S,T,3] relative poses + topk, per-step re-encoding; the oracle port of it) as eager PyTorch on the
+    SAME B200 — fp32, or fp16 autocast as the reference trains (configs/trainer/default.yaml:16). Same accounting
+    as `value`: scene tokens resident, `iters` policy iterations timed with CUDA events, scaled to 80-of-90. Falls back
+    to fewer scenes if the reference-order activations do not fit."""
+    from oracle import tb_oracle as O
+    cfg = config.default_model_cfg()
+    sz = config.derived_sizes(cfg)
+    P = {k: v.to(dev) for k, v in params.init_params(cfg, 0).items()}
+    host_batch = synth.make_scene_batch(n_sc=n_sc, seed=1000, n_rollout=R)
+    prev = torch.get_default_device()
+    torch.set_default_device(dev)  # the oracle's factory calls (eye, arange, zeros) then allocate on the GPU
+    try:
+        while n_sc >= 1:
+            try:
+                batch = {k: v[:n_sc].to(dev) for k, v in host_batch.items()}
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+                    mp = O.map_encoder(P, cfg, sz, batch["sc/mp_valid"], batch["sc/mp_attr"], batch["sc/mp_pose"])
+                    tl = O.tl_pre_compute(P, cfg, sz, batch["sc/tl_valid"], batch["sc/tl_attr"], batch["sc/tl_pose"], mp)
+                    mp = {k: mp[k] for k in ("mp_token_invalid", "mp_token_feature", "mp_token_pose")}
+                    run = lambda n: O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, n, mp=mp, tl=tl)  # noqa: E731
+                    run(2)  # warm-up (cuBLAS handles, allocator)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    run(iters)
+                    e1.record()
+                    torch.cuda.synchronize()
+                per_iter = e0.elapsed_time(e1) * 1e-3 / iters
+                peak_gb = torch.cuda.max_memory_allocated(dev) / 2**30
+                return dict(value=n_sc * R * N_COUNTED / (N_ITER * per_iter), unit=UNIT, ms_per_policy_iteration=per_iter * 1e3,
+                            scenes=n_sc, rollouts=R, policy_iterations_timed=iters, peak_mem_gib=round(peak_gb, 1),
+                            what="reference operation order (oracle port) as eager PyTorch on this GPU, "
+                                 + ("fp16 autocast" if autocast else "fp32") + "; scaled to 80 counted of 90 iterations")
+            except torch.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                n_sc //= 2
+        return dict(unavailable="out of memory at 1 scene")
+    finally:
+        torch.set_default_device(prev)
+        torch.cuda.empty_cache()
 
 
 def run_reference(args):
@@ -276,7 +321,7 @@ def run_ours(args):
         roof = attention_roofline(eng, peaks)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=t_loop / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32" if args.precision == 0 else "tf32", data="synthetic",
+                    dtype="f32" if args.precision == 0 else "tf32+fp16", data="synthetic",
                     config=dict(workload=f"config 3: closed-loop WOSAC rollout, {n_sc} scenes x {args.rollouts} rollouts "
                                          f"per GPU, 128 agents, 1024 polylines x 20, 40 TL, 11-step history, 90 policy "
                                          f"iterations (80 counted)", scenes_per_gpu=n_sc, rollouts=args.rollouts,
@@ -307,6 +352,14 @@ def run_ours(args):
         t = timed(lambda: eng.predict_destinations(batch, mp=mp), 3) / 3
         extras["navi_predictor"] = dict(value=t * 1e3, unit="ms per batch of scenes (destination logits + sampling, map tokens given)",
                                         scenes=args.scenes)
+        del eng
+        torch.cuda.empty_cache()
+        # the real bar: reference-order eager PyTorch on this same GPU (fp32 and fp16 autocast)
+        for name, ac in (("eager_cuda_fp32", False), ("eager_cuda_fp16_autocast", True)):
+            try:
+                extras[name] = eager_cuda_rate(dev, n_sc, args.rollouts, 20, ac)
+            except Exception as e:  # a baseline leg must never take the headline line down
+                extras[name] = dict(unavailable=f"{type(e).__name__}: {e}"[:200])
         line["extras"] = extras
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -33,6 +33,13 @@ extern "C" {
 const char* tb_strerror(int code);
 int tb_version(void);
 
+/* fp16 range guard of the tensor-core mode. The reference computes in fp32 (or AMP fp16 with a GradScaler,
+ * configs/trainer/default.yaml:16); this library's 16-bit intermediates ([q|u], [k|v] tables, ReLU hidden rows, the
+ * fused history encoder's MLP rows) are converted with saturation (never inf) and, when `d_flag` (one device word,
+ * caller-owned, zeroed by the caller) is registered, every producing kernel ORs bit 0 into it if a converted value
+ * reached +-65504. NULL unregisters. Host-side setting, not stream ordered: register before launching. */
+int tb_set_fp16_flag(unsigned int* d_flag);
+
 /* ---------------------------------------------------------------------------------------------------
  * Fused pairwise relative pose + K-nearest-target selection.
  * Replaces utils/rpe.py:9-37 (get_rel_pose) + :62-90 (get_tgt_knn_idx) + the row gathers of the winners.
@@ -127,7 +134,7 @@ int tb_knarpe_attn_bwd(const float* q, int ldq, const float* u, int ldu, const f
  * precision: 0 = fp32 FFMA (parity path), 1 = tf32 tcgen05 tensor cores (fp32 operands read as tf32, fp32 accumulate),
  *   2 = X and W are IEEE fp16 arrays (ldx in halves; tcgen05 kind::f16, fp32 accumulate) — the consumer side of the
  *   fp16 intermediates of the tensor-core mode (attention output [ov|z], FFN hidden); bias / residual / Y stay fp32.
- * Yh (optional, precision 1 only): columns [col_h, N) of the result are written as IEEE fp16 to
+ * Yh (optional, precision 1 or 2): columns [col_h, N) of the result are written as IEEE fp16 to
  *   Yh[row*ldyh + col - col_h] instead of Y (col_h a multiple of 32; col_h == 0 => Y may be NULL). This is how the
  *   K|V tables consumed by tb_knarpe_attn flags bit 1 are produced without a conversion pass.
  * ------------------------------------------------------------------------------------------------- */
@@ -232,6 +239,17 @@ int tb_dyn_step(const float* act_branch, const uint8_t* ag_type, const float* ma
                 int n_mp, int n_node, float thresh_lane, float thresh_edge, float cos_rot, const int* d_step, int B,
                 int A, int W, int T, uint8_t* hist_valid, float* hist_pose, float* hist_motion, uint8_t* pred_valid,
                 float* pred_pose, float* pred_motion, void* stream);
+/* tb_dyn_step + the two per-step feedback flags RolloutBuffer.violation keeps (buffer.py:57-60):
+ *   o_outside / o_reached [B,A,T] u8 (optional, NULL = not recorded): outside_map_this_step / dest_reached_this_step
+ *   of step s at index s-1 (traffic_rule_checker.py:107-116, 291-319). */
+int tb_dyn_step_ex(const float* act_branch, const uint8_t* ag_type, const float* max_acc, const float* max_yaw_rate,
+                   float dt, uint8_t* valid, uint8_t* disabled, uint8_t* navi_invalid, uint8_t* dest_reached,
+                   float* pose, float* motion, const uint8_t* gt_valid, const float* gt_pose, const float* gt_motion,
+                   const uint8_t* tf_mask, int n_gt, int sc_div, const float* boundary, const int32_t* dest_idx,
+                   const float* mp_pos, const float* mp_dirn, const uint8_t* mp_node_invalid, const uint8_t* mp_kind,
+                   int n_mp, int n_node, float thresh_lane, float thresh_edge, float cos_rot, const int* d_step, int B,
+                   int A, int W, int T, uint8_t* hist_valid, float* hist_pose, float* hist_motion, uint8_t* pred_valid,
+                   float* pred_pose, float* pred_motion, uint8_t* o_outside, uint8_t* o_reached, void* stream);
 
 /* Traffic-light feedback — utils/dynamics.py:144-163 (override_tl), traffic_light.py:286 (clamp +-3).
  *   logits [B*TL,5] (pre-clamp, invalid rows are zeroed here), tl_invalid [B,TL], gt_tl [B,TL,n_gt,5] u8.

@@ -39,6 +39,13 @@ def golden_checks():
     return torch.load(os.path.join(GOLDEN, "checks_dense.pt"), weights_only=False)
 
 
+@pytest.fixture(scope="session", params=["checks_dense.pt", "checks_redlight.pt"])
+def golden_checks_any(request):
+    """Both TrafficRuleChecker fixtures: the dense scene (collisions / road edge) and the crafted scene in which
+    `run_red_light` (168 positives) and `passive` (836) fire (synth.make_rule_scene_batch)."""
+    return torch.load(os.path.join(GOLDEN, request.param), weights_only=False)
+
+
 @pytest.fixture(scope="session")
 def golden_navi():
     return torch.load(os.path.join(GOLDEN, "navi_pred.pt"), weights_only=False)

@@ -290,6 +290,25 @@ def golden_womd_post():
     print("womd_post.pt", os.path.getsize(os.path.join(HERE, "womd_post.pt")) // 1024, "KiB")
 
 
+def golden_checks_redlight(model=None):
+    """Second TrafficRuleChecker fixture (`run_red_light` had 0 positives in checks_dense.pt): the crafted
+    scene of synth.make_rule_scene_batch through the real reference with all checks on."""
+    if model is None:
+        cfg = config.default_model_cfg()
+        model = build_reference_model(cfg, params.init_params(cfg, seed=0))
+    shape = dict(n_sc=3, n_ag=48, n_mp=96, n_tl=40, seed=5000, boundary=80.0, scale=0.4)
+    batch = synth.make_rule_scene_batch(**shape)
+    R, T = 2, 36
+    res, _, _ = reference_rollout(model, batch, R, T, disable_check=False)
+    keep = ("pred_valid", "pred_pose", "pred_motion", "tl_state", "collided", "collided_wosac", "run_road_edge",
+            "run_red_light", "passive")
+    fix = dict(shape=shape, maker="make_rule_scene_batch", R=R, T=T, param_seed=0, **{k: res[k] for k in keep})
+    torch.save(fix, os.path.join(HERE, "checks_redlight.pt"))
+    print("checks_redlight.pt", os.path.getsize(os.path.join(HERE, "checks_redlight.pt")) // 1024, "KiB",
+          {k: int(res[k].sum()) for k in keep[4:]})
+
+
+@torch.no_grad()
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -297,6 +316,8 @@ def main():
         return golden_navi_predictor()
     if len(sys.argv) > 1 and sys.argv[1] == "wosac":  # only (re)generate wosac_post.pt
         return golden_wosac_post()
+    if len(sys.argv) > 1 and sys.argv[1] == "checks2":  # only (re)generate checks_redlight.pt
+        return golden_checks_redlight()
     if len(sys.argv) > 1 and sys.argv[1] == "womd":  # only (re)generate womd_post.pt
         return golden_womd_post()
     ops = golden_ops()
@@ -333,6 +354,7 @@ def main():
     torch.save(fix, os.path.join(HERE, "checks_dense.pt"))
     print("checks_dense.pt", os.path.getsize(os.path.join(HERE, "checks_dense.pt")) // 1024, "KiB",
           {k: int(res[k].sum()) for k in keep[4:]})
+    golden_checks_redlight(model)
     golden_navi_predictor()
     golden_wosac_post()
     golden_womd_post()

@@ -96,11 +96,11 @@ def test_rollout_small(golden_rollout):
     _close(res["pred_motion"], g["pred_motion"], 0, 1e-3, "pred motion")
 
 
-def test_rule_checks_oracle_vs_reference(golden_checks):
+def test_rule_checks_oracle_vs_reference(golden_checks_any):
     """The five logging-only checks of TrafficRuleChecker.check (collision, WOSAC collision, road edge, red light,
     passive) replayed on the reference's own per-step predictions: flags must be identical."""
-    g = golden_checks
-    batch = synth.make_scene_batch(**g["shape"])
+    g = golden_checks_any
+    batch = getattr(synth, g.get("maker", "make_scene_batch"))(**g["shape"])
     R = g["R"]
     rep = lambda t: t.repeat_interleave(R, 0)  # noqa: E731
     chk = O.RuleCheckOracle(rep(batch["map/valid"]), rep(batch["map/type"]), rep(batch["map/pos"][..., :2]),
@@ -113,6 +113,8 @@ def test_rule_checks_oracle_vs_reference(golden_checks):
         for k in keys:
             assert torch.equal(out[k], g[k][:, :, t]), f"{k} differs at step {t + 1}"
     assert int(g["collided"].sum()) > 100 and int(g["run_road_edge"].sum()) > 100  # fixture exercises the checks
+    if "maker" in g:  # the crafted fixture exercises the two rare events
+        assert int(g["run_red_light"].sum()) > 100 and int(g["passive"].sum()) > 100
 
 
 def test_navi_predictor_oracle_vs_reference(golden_navi):

@@ -152,55 +152,139 @@ def test_rollout_golden_tensor_core(golden_rollout):
     assert e_xy < TC_TOL_XY and e_yaw < TC_TOL_YAW and e_spd < TC_TOL_SPD
 
 
-def test_rollout_full_90_steps_vs_oracle():
+# Stated closed-loop tolerance of the BENCHMARKED mode (precision=1: tcgen05 tf32 / fp16 projections, fp16 K|V, q|u,
+# ov|z, FFN-hidden and LayerNorm rows, mma.sync attention, fused history encoder) against the fp32 oracle over ALL 90
+# policy iterations (80 counted WOSAC steps): at policy iteration t the position error stays below
+# 2e-3 + 7.5e-5 t^2 m (0.03 m at t = 20, 0.19 m at t = 50, 0.61 m at t = 90) and the heading error below
+# 1e-3 + 1e-5 t^2 rad; validity, traffic-light and navigation masks identical. Measured on four scenes: 0.21-0.35 m /
+# 0.011-0.044 rad at t = 90 while the agents travel 50-90 m. The envelope is quadratic because the error is not noise:
+# 10-bit-mantissa WEIGHTS (tf32 / fp16 operands, as in the reference's own AMP-fp16 runs) are a fixed ~5e-4 relative
+# perturbation of the policy, i.e. a nearly constant acceleration error that integrates twice. The oracle itself with
+# nothing but its nn.Linear weights rounded to fp16 drifts 0.29 m by t = 90 on the config-1 scene (activations
+# rounded instead: 0.05 m) - profiles/precision_floor.py, profiles/r2/precision_floor.txt. The fp32 mode
+# (precision=0) keeps 1e-2 m / 2e-3 rad over the whole horizon.
+def _tc90_envelope(T):
+    t = torch.arange(1, T + 1, dtype=torch.float32)
+    return 2e-3 + 7.5e-5 * t * t, 1e-3 + 1e-5 * t * t
+_ORACLE_CACHE = {}
+
+
+def _oracle_rollout(shape, R, T, P, cfg):
+    key = (tuple(sorted(shape.items())), R, T)
+    if key not in _ORACLE_CACHE:
+        batch = synth.make_scene_batch(**shape)
+        _ORACLE_CACHE[key] = O.rollout(P, cfg, config.derived_sizes(cfg), config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch,
+                                       R, T)
+    return _ORACLE_CACHE[key]
+
+
+def _compare_90(res, ref, precision, what):
+    n_bad = {k: int((res[k].cpu() != ref[k]).sum()) for k in ("pred_valid", "tl_state", "final_valid", "final_navi_valid")}
+    err = (res["pred_pose"].cpu() - ref["pred_pose"]).abs()
+    xy, yaw = err[..., :2].amax(dim=(0, 1, 3)), err[..., 2].amax(dim=(0, 1))
+    print(f"{what} precision={precision}: mask mismatches {n_bad}")
+    print("  max xy err per 10th step [m]:  ", " ".join(f"{float(v):.1e}" for v in xy[9::10]))
+    print("  max yaw err per 10th step [rad]:", " ".join(f"{float(v):.1e}" for v in yaw[9::10]))
+    assert not any(n_bad.values()), n_bad
+    if precision:
+        tol_xy, tol_yaw = _tc90_envelope(xy.numel())
+        print("  tolerance envelope at those steps [m]:", " ".join(f"{float(v):.1e}" for v in tol_xy[9::10]))
+        assert bool((xy < tol_xy).all()) and bool((yaw < tol_yaw).all()), (float((xy / tol_xy).max()),
+                                                                             float((yaw / tol_yaw).max()))
+    else:
+        assert float(xy.max()) < 1e-2 and float(yaw.max()) < 2e-3, (float(xy.max()), float(yaw.max()))
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_rollout_full_90_steps_vs_oracle(precision):
     """BASELINE config-1-sized scene (64 agents, 256 polylines x 20, 40 TL, 11-step history), all 90 policy iterations
-    (80 counted WOSAC steps) x 2 rollouts against the CPU oracle. Stated per-step position tolerance over the whole
-    horizon: 1e-2 m / 2e-3 rad. This is the fp32 noise floor of the closed loop, not slack: the fp32 oracle (= the
-    reference's arithmetic) differs from ITS OWN float64 evaluation by 4.2e-3 m at step 90 on this scene (PoseEmb
-    evaluates cos(x * 1 rad/m) on coordinates up to ~150 m, so fp32 rounding of x is amplified); the float64 oracle is
-    therefore checked too. Masks must be identical."""
+    (80 counted WOSAC steps) x 2 rollouts against the CPU oracle, in the fp32 mode AND in the benchmarked tensor-core
+    mode. fp32: stated per-step position tolerance over the whole horizon 1e-2 m / 2e-3 rad. This is the fp32 noise
+    floor of the closed loop, not slack: the fp32 oracle (= the reference's arithmetic) differs from ITS OWN float64
+    evaluation by 4.2e-3 m at step 90 on this scene (PoseEmb evaluates cos(x * 1 rad/m) on coordinates up to ~150 m,
+    so fp32 rounding of x is amplified); the float64 oracle is therefore checked too. Masks must be identical."""
     shape = dict(n_sc=1, n_ag=64, n_mp=256, n_tl=40, seed=31, boundary=120.0)
     R, T = 2, 90
-    eng, batch, P, cfg = _engine(shape, R, T)
+    eng, batch, P, cfg = _engine(shape, R, T, precision=precision)
     res = eng.rollout(batch)
     sz = config.derived_sizes(cfg)
-    ref = O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, T)
-    assert torch.equal(res["pred_valid"].cpu(), ref["pred_valid"])
-    assert torch.equal(res["tl_state"].cpu(), ref["tl_state"])
-    assert torch.equal(res["final_navi_valid"].cpu(), ref["final_navi_valid"])
-    err = (res["pred_pose"].cpu() - ref["pred_pose"]).abs()
-    per_step = err[..., :2].amax(dim=(0, 1, 3))
-    print("max xy err vs fp32 oracle (every 10th step):", [f"{float(v):.1e}" for v in per_step[9::10]])
-    assert float(per_step.max()) < 1e-2 and float(err[..., 2].max()) < 2e-3
-    # float64 evaluation of the same algorithm
-    torch.set_default_dtype(torch.float64)
-    try:
-        P64 = {k: v.double() for k, v in P.items()}
-        b64 = {k: (v.double() if v.dtype == torch.float32 else v) for k, v in batch.items()}
-        ref64 = O.rollout(P64, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, b64, R, T)
-    finally:
-        torch.set_default_dtype(torch.float32)
-    e64 = (res["pred_pose"].cpu().double() - ref64["pred_pose"]).abs()[..., :2].amax(dim=(0, 1, 3))
-    o64 = (ref["pred_pose"].double() - ref64["pred_pose"]).abs()[..., :2].amax(dim=(0, 1, 3))
-    print("max xy err vs fp64 oracle:", [f"{float(v):.1e}" for v in e64[9::10]], "| fp32 oracle vs fp64 oracle:",
-          [f"{float(v):.1e}" for v in o64[9::10]])
-    assert float(e64.max()) < 1e-2
+    ref = _oracle_rollout(shape, R, T, P, cfg)
+    _compare_90(res, ref, precision, "config-1 scene, 90 iterations")
+    if precision == 0:
+        # float64 evaluation of the same algorithm
+        torch.set_default_dtype(torch.float64)
+        try:
+            P64 = {k: v.double() for k, v in P.items()}
+            b64 = {k: (v.double() if v.dtype == torch.float32 else v) for k, v in batch.items()}
+            ref64 = O.rollout(P64, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, b64, R, T)
+        finally:
+            torch.set_default_dtype(torch.float32)
+        e64 = (res["pred_pose"].cpu().double() - ref64["pred_pose"]).abs()[..., :2].amax(dim=(0, 1, 3))
+        o64 = (ref["pred_pose"].double() - ref64["pred_pose"]).abs()[..., :2].amax(dim=(0, 1, 3))
+        print("max xy err vs fp64 oracle:", [f"{float(v):.1e}" for v in e64[9::10]], "| fp32 oracle vs fp64 oracle:",
+              [f"{float(v):.1e}" for v in o64[9::10]])
+        assert float(e64.max()) < 1e-2
     # WOSAC slice = the 80 steps after the 10-step warm start (wosac_post_processing / waymo_motion.py:888-902)
     assert res["pred_pose"][:, :, 10:].shape[2] == 80
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_rollout_config3_shape_90_steps_vs_oracle(precision):
+    """The BENCHMARKED scene shape and horizon (BASELINE config 3: 128 agents, 1024 polylines x 20, 40 TL; 1 scene x 4
+    rollouts, all 90 policy iterations) in the parity mode and in the benchmarked mode, against the CPU oracle."""
+    shape = dict(n_sc=1, n_ag=128, n_mp=1024, n_tl=40, seed=1000, n_rollout=4)
+    R, T = 4, 90
+    eng, batch, P, cfg = _engine(shape, R, T, precision=precision)
+    res = eng.rollout(batch)
+    ref = _oracle_rollout(shape, R, T, P, cfg)
+    _compare_90(res, ref, precision, "config-3 scene shape, 90 iterations")
+
+
+def test_run_refuses_more_steps_than_step_end():
+    eng, batch, P, cfg = _engine(dict(n_sc=1, n_ag=30, n_mp=80, n_tl=28, seed=9, boundary=110.0), 2, 12)
+    eng.prepare(batch)
+    with pytest.raises(ValueError):
+        eng.run(13)
+    res = eng.run(12)
+    assert bool(torch.isfinite(res["pred_pose"]).all())
+
+
+def test_fp16_range_guard_trips_on_large_activations():
+    """the tensor-core mode keeps [q|u], [k|v] and the FFN hidden rows in fp16. With weights scaled so that
+    the ReLU hidden rows exceed 65,504 the conversions saturate (no inf / NaN) and the engine raises instead of
+    returning silently clamped trajectories; the same weights run cleanly in the fp32 mode."""
+    shape = dict(n_sc=1, n_ag=30, n_mp=80, n_tl=28, seed=9, boundary=110.0)
+    cfg = config.default_model_cfg()
+    P = dict(params.init_params(cfg, seed=0))
+    k = "ag_encoder.tf_ag2agmptl.layers.1.linear1"
+    P[f"{k}.weight"] = P[f"{k}.weight"] * 3e5
+    P[f"{k}.bias"] = P[f"{k}.bias"] + 1e5
+    k2 = "ag_encoder.tf_ag2agmptl.layers.1.linear2"
+    P[f"{k2}.weight"] = P[f"{k2}.weight"] / 3e5
+    batch = synth.make_scene_batch(**shape)
+    eng = RolloutEngine(P, cfg, DEV, precision=1, n_rollout=2, step_end=12)
+    with pytest.raises(FloatingPointError):
+        eng.rollout(batch)
+    assert bool(torch.isfinite(eng.results()["pred_pose"]).all())  # saturated, not inf / NaN
+    eng0 = RolloutEngine(P, cfg, DEV, precision=0, n_rollout=2, step_end=12)
+    assert bool(torch.isfinite(eng0.rollout(batch)["pred_pose"]).all())
+    # and the unscaled weights do not trip it
+    eng1 = RolloutEngine(params.init_params(cfg, seed=0), cfg, DEV, precision=1, n_rollout=2, step_end=12)
+    eng1.rollout(batch)
 
 
 # ---------------------------------------------------------------------------------------------- rule checks (8(f) rank 1)
 VIO = ("collided", "collided_wosac", "run_road_edge", "run_red_light", "passive")
 
 
-def test_rule_check_kernel_on_reference_predictions(golden_checks):
+def test_rule_check_kernel_on_reference_predictions(golden_checks_any):
     """tb_rule_check replayed step by step on the reference's own per-step predictions of a dense scene (thousands of
     collision / road-edge events): flags must equal the reference's, up to knife-edge fp32 cases (<= 0.5 % of the
     positives may flip; cos/sin of the heading differ by 1 ulp between libm and CUDA)."""
     from trafficbotsv1_5_b200 import lib as L, ops
     from trafficbotsv1_5_b200.engine import rule_tables
-    g = golden_checks
-    batch = {k: v.to(DEV) for k, v in synth.make_scene_batch(**g["shape"]).items()}
+    g = golden_checks_any
+    batch = {k: v.to(DEV) for k, v in getattr(synth, g.get("maker", "make_scene_batch"))(**g["shape"]).items()}
     R, T, W = g["R"], g["T"], 11
     B, A = g["pred_valid"].shape[:2]
     n_sc, n_tl = batch["sc/tl_valid"].shape
@@ -228,6 +312,8 @@ def test_rule_check_kernel_on_reference_predictions(golden_checks):
         n_diff, n_pos = int((mine != ref).sum()), int(ref.sum())
         print(f"{k}: reference positives {n_pos}, mismatches {n_diff}")
         assert n_diff <= max(1, int(0.005 * n_pos)), f"{k}: {n_diff} mismatches of {n_pos} positives"
+    if "maker" in g:
+        assert int(g["run_red_light"].sum()) > 100 and int(g["passive"].sum()) > 100
 
 
 def test_rule_checks_in_rollout_vs_oracle():
@@ -340,7 +426,7 @@ def test_navi_predictor_vs_reference_golden(golden_navi):
     batch = synth.make_scene_batch(**g["shape"])
     for prec, tol in ((0, 1e-5), (1, 2e-3)):  # measured 1e-7 / 8e-5
         eng = RolloutEngine(P, cfg, "cuda", precision=prec, n_rollout=4, step_end=20, use_graph=False)
-        out = eng.predict_destinations(batch)
+        out = eng.predict_destinations(batch, deterministic_k0=True)
         probs = out["probs"].cpu()
         assert torch.equal(probs > 0, g["probs"] > 0)
         err = float((probs - g["probs"]).abs().max())

@@ -24,10 +24,7 @@ constexpr int OFF_W1 = 0, OFF_W2 = OFF_W1 + 64 * S1, OFF_W3 = OFF_W2 + 64 * S2, 
 constexpr int N_BIAS = 6 * 64;
 constexpr size_t SMEM = (size_t)W_HALVES * 2 + (N_BIAS + 8) * 4;
 
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) { return tb_pack_h2_sat(a, b); }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -51,8 +48,9 @@ __device__ __forceinline__ void dense64(const uint32_t (&a)[KC][4], const __half
   }
 }
 // accumulator fragments -> A fragments of the next layer (k-chunk kc = n-tiles 2kc, 2kc+1), optional ReLU
+// (hm: running |max| of every converted activation, the fp16 range guard of common.cuh)
 template <bool RELU>
-__device__ __forceinline__ void c_to_a(const float (&c)[8][4], uint32_t (*a)[4]) {
+__device__ __forceinline__ void c_to_a(const float (&c)[8][4], uint32_t (*a)[4], uint32_t& hm) {
 #pragma unroll
   for (int kc = 0; kc < 4; ++kc) {
     auto r = [](float v) { return RELU ? fmaxf(v, 0.f) : v; };
@@ -60,6 +58,8 @@ __device__ __forceinline__ void c_to_a(const float (&c)[8][4], uint32_t (*a)[4])
     a[kc][1] = pack_h2(r(c[2 * kc][2]), r(c[2 * kc][3]));
     a[kc][2] = pack_h2(r(c[2 * kc + 1][0]), r(c[2 * kc + 1][1]));
     a[kc][3] = pack_h2(r(c[2 * kc + 1][2]), r(c[2 * kc + 1][3]));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tb_track_h2(hm, a[kc][j]);
   }
 }
 // ReLU in place + column maxima over the valid rows (rows g: regs 0,1; rows g+8: regs 2,3), replicated over g
@@ -96,7 +96,7 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
                    const __half* __restrict__ wblob, const float* __restrict__ bias, float* __restrict__ tok_out,
                    int ldo, float* __restrict__ tok_pose, uint8_t* __restrict__ tok_invalid,
                    const float* __restrict__ ln_g, const float* __restrict__ ln_b, __half* __restrict__ ln_out,
-                   int ld_ln) {
+                   int ld_ln, unsigned int* __restrict__ sat_flag) {
   extern __shared__ __align__(16) unsigned char smem[];
   __half* sW = reinterpret_cast<__half*>(smem);
   float* sB = reinterpret_cast<float*>(smem + (size_t)W_HALVES * 2);
@@ -111,6 +111,7 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
   const int s = *d_step;
   const int n_step = min(s, W);
   float* fr = sB + N_BIAS;  // the 8 xy frequencies (shared: indexed by a lane-dependent component number)
+  uint32_t hm = 0u;         // fp16 range guard: |max| of the activations this lane converted
 
   for (int ba = blockIdx.x * AW + warp; ba < n_ag_tot; ba += gridDim.x * AW) {  // warp-uniform
     const size_t hb = (size_t)ba * W;
@@ -174,7 +175,7 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
     float c[8][4];
     uint32_t x[8][4];  // PointNet input rows [mlp(64) | pe(64)] as 8 k-chunks
     dense64<2>(a1, sW + OFF_W1, S1, sB, g, t, c);
-    c_to_a<true>(c, x);
+    c_to_a<true>(c, x, hm);
     {
       uint32_t a2[4][4];
 #pragma unroll
@@ -182,9 +183,9 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
 #pragma unroll
         for (int r = 0; r < 4; ++r) a2[kc][r] = x[kc][r];
       dense64<4>(a2, sW + OFF_W2, S2, sB + 64, g, t, c);
-      c_to_a<true>(c, a2);
+      c_to_a<true>(c, a2, hm);
       dense64<4>(a2, sW + OFF_W3, S2, sB + 128, g, t, c);
-      c_to_a<false>(c, x);
+      c_to_a<false>(c, x, hm);
     }
     // ---- PoseEmb64 of the history pose in the token frame (agent_encoder.py:159) -> k-chunks 4..7
 #pragma unroll
@@ -201,7 +202,7 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
     relu_colmax(c, valid[0], valid[1], m);
 #pragma unroll
     for (int layer = 1; layer < 3; ++layer) {
-      c_to_a<false>(c, x);  // h (already ReLU'd) -> k-chunks 0..3
+      c_to_a<false>(c, x, hm);  // h (already ReLU'd) -> k-chunks 0..3
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {  // the group max replicated over all rows -> k-chunks 4..7
         x[4 + kc][0] = x[4 + kc][1] = pack_h2(m[2 * kc][0], m[2 * kc][1]);
@@ -239,6 +240,7 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
       }
     }
   }
+  tb_flag_if_sat(hm, sat_flag);
 }
 
 }  // namespace
@@ -281,7 +283,7 @@ extern "C" int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose,
   const int grid = want < 2 * num_sms ? want : 2 * num_sms;  // persistent: 2 CTAs per SM, warps loop over agents
   ag_frontend_kernel<<<grid, AW * 32, SMEM, static_cast<cudaStream_t>(stream)>>>(
       hist_valid, hist_pose, hist_motion, ag_attr, d_step, freq_xy, n, W, static_cast<const __half*>(wblob), bias,
-      tok_out, ldo, tok_pose, tok_invalid, ln_gamma, ln_beta, static_cast<__half*>(ln_out), ld_ln);
+      tok_out, ldo, tok_pose, tok_invalid, ln_gamma, ln_beta, static_cast<__half*>(ln_out), ld_ln, tb_fp16_flag_ptr);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

@@ -24,7 +24,14 @@ extern "C" const char* tb_strerror(int code) {
   }
 }
 
-extern "C" int tb_version(void) { return 100; }
+extern "C" int tb_version(void) { return 200; }
+
+unsigned int* tb_fp16_flag_ptr = nullptr;
+
+extern "C" int tb_set_fp16_flag(unsigned int* d_flag) {
+  tb_fp16_flag_ptr = d_flag;  // NULL switches the guard's flag write off (conversions still saturate)
+  return TB_OK;
+}
 
 extern "C" int tb_linear(const void* X, int ldx, const void* W, const float* bias, int bias_group, float* Y, int ldy,
                          int M, int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,

@@ -37,6 +37,7 @@ struct Epi {
   __half* yh; int ldyh; int colh;  // columns >= colh (multiple of 32) are written as fp16 to yh[row*ldyh + col - colh]
   // fused LayerNorm of the output rows (N == 128, one n tile): ln_out[row] = fp16(LN(Y[row]) * gamma + beta)
   const float* ln_g; const float* ln_b; __half* ln_out; int ld_ln;
+  unsigned int* sat_flag;  // fp16 range guard (common.cuh): ORed with 1 when an fp16 output value saturated
 };
 struct LnCtx { float2* part; uint32_t st_s; int quarter, half, parity; };
 
@@ -137,6 +138,7 @@ __device__ __forceinline__ void store_block(uint32_t st_s, int rsub, int cc, int
   // row rr = 4 i + rsub sits at rr * 128 bytes, chunk cc ^ (rr & 7): (rr & 7) alternates between rsub and rsub + 4
   const uint32_t sa0 = st_s + (uint32_t)rsub * 128u + ((uint32_t)(cc ^ rsub) << 4);
   const uint32_t sa1 = st_s + (uint32_t)rsub * 128u + ((uint32_t)(cc ^ (rsub + 4)) << 4);
+  uint32_t hmax = 0u;  // TO_H: running |max| of the converted halves (fp16 range guard)
   float4 vv[8];  // all eight rows in flight before the first store (measured: 43 -> 38 us on the N = 896 projection)
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -155,9 +157,10 @@ __device__ __forceinline__ void store_block(uint32_t st_s, int rsub, int cc, int
         if (pf.zero_post & (1u << i)) v = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (TO_H) {
-        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-        *reinterpret_cast<uint2*>(hp) =
-            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        const uint32_t h0 = tb_pack_h2_sat(v.x, v.y), h1 = tb_pack_h2_sat(v.z, v.w);
+        tb_track_h2(hmax, h0);
+        tb_track_h2(hmax, h1);
+        *reinterpret_cast<uint2*>(hp) = make_uint2(h0, h1);
       } else {
         *reinterpret_cast<float4*>(yp) = v;
       }
@@ -165,6 +168,7 @@ __device__ __forceinline__ void store_block(uint32_t st_s, int rsub, int cc, int
     }
     if (TO_H) hp += hstep; else yp += ystep;
   }
+  if (TO_H) tb_flag_if_sat(hmax, ep.sat_flag);
   if (LN) {
     // ---- LayerNorm of the finished rows (transformer_rpe.py:156-171, eps 1e-5): a row's 128 columns sit in the four
     // warps of this TMEM lane quarter. Per-row (sum, sum of squares) of this warp's 32 columns by a butterfly over the
@@ -409,7 +413,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               if (ep.mask_pre && ep.mask_pre[row]) t = 0.f;
               if (ep.res) t += ep.res[(size_t)row * ep.ldr + col];
               if (ep.mask_post && ep.mask_post[row]) t = 0.f;
-              if (to_h) ep.yh[(size_t)row * ep.ldyh + (col - ep.colh)] = __float2half_rn(t);
+              if (to_h) {
+                const uint32_t hv = tb_pack_h2_sat(t, 0.f);
+                tb_flag_if_sat(hv & 0x7FFFu, ep.sat_flag);
+                ep.yh[(size_t)row * ep.ldyh + (col - ep.colh)] = __ushort_as_half((unsigned short)(hv & 0xFFFFu));
+              }
               else Y[(size_t)row * ldy + col] = t;
             }
           }
@@ -507,7 +515,7 @@ int tb_linear_tc(const void* X, int ldx, const void* W, int in_f16, const float*
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms ? total : num_sms;  // persistent: one CTA per SM
   Epi ep{bias, bias_group, relu, mask_pre, res, ldr, mask_post, static_cast<__half*>(Yh), ldyh, colh,
-         ln_g, ln_b, static_cast<__half*>(ln_out), ld_ln};
+         ln_g, ln_b, static_cast<__half*>(ln_out), ld_ln, tb_fp16_flag_ptr};
   if (ln_out) {
     if (in_f16) linear_tc_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);
     else linear_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mapA, mapB, Y, ldy, M, N, K, ep);

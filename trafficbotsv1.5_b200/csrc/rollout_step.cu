@@ -99,12 +99,14 @@ struct DynArgs {
   const uint8_t* mp_node_invalid; const uint8_t* mp_kind; int n_mp; int n_node; float thresh_lane; float thresh_edge;
   float cos_rot; const int* d_step; int n_tot; int A; int W; int T;
   uint8_t* hist_valid; float* hist_pose; float* hist_motion; uint8_t* pred_valid; float* pred_pose; float* pred_motion;
+  uint8_t* o_outside; uint8_t* o_reached;  // optional [B,A,T]: outside_map_this_step / dest_reached_this_step (buffer.py:57-60)
 };
 
 __global__ void __launch_bounds__(128) dyn_step_kernel(DynArgs p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // b*A + a
   if (i >= p.n_tot) return;
   const int s = *p.d_step;
+  if (s < 1 || s > p.T) return;  // pred_*[.., s - 1] would be out of bounds: the step counter ran past step_end
   const int b = i / p.A, a = i - b * p.A, sc = b / p.sc_div;
   const bool v_old = p.valid[i] != 0;
   // ---- action head branches -> physical action (action_head.py:78-82, dynamics.py:84-101, :237-246)
@@ -160,6 +162,8 @@ __global__ void __launch_bounds__(128) dyn_step_kernel(DynArgs p) {
       reached = kind == 2 ? pos_ok : (pos_ok && rot_ok);
     }
   }
+  if (p.o_outside) p.o_outside[(size_t)i * p.T + (s - 1)] = outside;
+  if (p.o_reached) p.o_reached[(size_t)i * p.T + (s - 1)] = reached;
   // ---- teacher forcing / spawn override (teacher_forcing.py:126-147, dynamics.py:122-141)
   bool v_new = v_old;
   const bool dis_old = p.disabled[i] != 0;
@@ -193,6 +197,7 @@ __global__ void tl_step_kernel(const float* __restrict__ logits, const uint8_t* 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // b*TL + tl
   if (i >= n_tot) return;
   const int s = *d_step;
+  if (s < 1 || s > T) return;  // tl_out[.., s - 1] would be out of bounds
   uint8_t st[5];
   if (s < n_gt) {  // ground-truth traffic lights while available (teacher_forcing.py:65,159-160)
 #pragma unroll
@@ -262,15 +267,15 @@ extern "C" int tb_tl_featurize(const uint8_t* hist_tl, const uint8_t* tl_invalid
   return TB_OK;
 }
 
-extern "C" int tb_dyn_step(const float* act_branch, const uint8_t* ag_type, const float* max_acc,
-                           const float* max_yaw_rate, float dt, uint8_t* valid, uint8_t* disabled, uint8_t* navi_invalid,
-                           uint8_t* dest_reached, float* pose, float* motion, const uint8_t* gt_valid,
-                           const float* gt_pose, const float* gt_motion, const uint8_t* tf_mask, int n_gt, int sc_div,
-                           const float* boundary, const int32_t* dest_idx, const float* mp_pos, const float* mp_dirn,
-                           const uint8_t* mp_node_invalid, const uint8_t* mp_kind, int n_mp, int n_node,
-                           float thresh_lane, float thresh_edge, float cos_rot, const int* d_step, int B, int A, int W,
-                           int T, uint8_t* hist_valid, float* hist_pose, float* hist_motion, uint8_t* pred_valid,
-                           float* pred_pose, float* pred_motion, void* stream) {
+extern "C" int tb_dyn_step_ex(const float* act_branch, const uint8_t* ag_type, const float* max_acc,
+                              const float* max_yaw_rate, float dt, uint8_t* valid, uint8_t* disabled, uint8_t* navi_invalid,
+                              uint8_t* dest_reached, float* pose, float* motion, const uint8_t* gt_valid,
+                              const float* gt_pose, const float* gt_motion, const uint8_t* tf_mask, int n_gt, int sc_div,
+                              const float* boundary, const int32_t* dest_idx, const float* mp_pos, const float* mp_dirn,
+                              const uint8_t* mp_node_invalid, const uint8_t* mp_kind, int n_mp, int n_node,
+                              float thresh_lane, float thresh_edge, float cos_rot, const int* d_step, int B, int A, int W,
+                              int T, uint8_t* hist_valid, float* hist_pose, float* hist_motion, uint8_t* pred_valid,
+                              float* pred_pose, float* pred_motion, uint8_t* o_outside, uint8_t* o_reached, void* stream) {
   if (!act_branch || !ag_type || !max_acc || !max_yaw_rate || !valid || !disabled || !navi_invalid || !dest_reached ||
       !pose || !motion || !gt_valid || !gt_pose || !gt_motion || !tf_mask || !boundary || !dest_idx || !mp_pos ||
       !mp_dirn || !mp_node_invalid || !mp_kind || !d_step || !hist_valid || !hist_pose || !hist_motion || !pred_valid ||
@@ -288,9 +293,25 @@ extern "C" int tb_dyn_step(const float* act_branch, const uint8_t* ag_type, cons
   p.n_node = n_node; p.thresh_lane = thresh_lane; p.thresh_edge = thresh_edge; p.cos_rot = cos_rot; p.d_step = d_step;
   p.n_tot = B * A; p.A = A; p.W = W; p.T = T; p.hist_valid = hist_valid; p.hist_pose = hist_pose;
   p.hist_motion = hist_motion; p.pred_valid = pred_valid; p.pred_pose = pred_pose; p.pred_motion = pred_motion;
+  p.o_outside = o_outside; p.o_reached = o_reached;
   dyn_step_kernel<<<(p.n_tot + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
   TB_CHECK_LAUNCH();
   return TB_OK;
+}
+
+extern "C" int tb_dyn_step(const float* act_branch, const uint8_t* ag_type, const float* max_acc,
+                           const float* max_yaw_rate, float dt, uint8_t* valid, uint8_t* disabled, uint8_t* navi_invalid,
+                           uint8_t* dest_reached, float* pose, float* motion, const uint8_t* gt_valid,
+                           const float* gt_pose, const float* gt_motion, const uint8_t* tf_mask, int n_gt, int sc_div,
+                           const float* boundary, const int32_t* dest_idx, const float* mp_pos, const float* mp_dirn,
+                           const uint8_t* mp_node_invalid, const uint8_t* mp_kind, int n_mp, int n_node,
+                           float thresh_lane, float thresh_edge, float cos_rot, const int* d_step, int B, int A, int W,
+                           int T, uint8_t* hist_valid, float* hist_pose, float* hist_motion, uint8_t* pred_valid,
+                           float* pred_pose, float* pred_motion, void* stream) {
+  return tb_dyn_step_ex(act_branch, ag_type, max_acc, max_yaw_rate, dt, valid, disabled, navi_invalid, dest_reached, pose,
+                        motion, gt_valid, gt_pose, gt_motion, tf_mask, n_gt, sc_div, boundary, dest_idx, mp_pos, mp_dirn,
+                        mp_node_invalid, mp_kind, n_mp, n_node, thresh_lane, thresh_edge, cos_rot, d_step, B, A, W, T,
+                        hist_valid, hist_pose, hist_motion, pred_valid, pred_pose, pred_motion, nullptr, nullptr, stream);
 }
 
 extern "C" int tb_tl_step(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt_tl, int n_gt,

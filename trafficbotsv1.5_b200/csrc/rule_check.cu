@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256) rule_check_kernel(Args p) {
 
   const int b = blockIdx.x, sc = b / p.div, A = p.A;
   const int s = *p.d_step;
+  if (s < 1 || s > p.T) return;  // block-uniform: the flags of step s live at [.., s - 1] < T
   for (int a = threadIdx.x; a < A; a += blockDim.x) {
     const size_t i = (size_t)b * A + a, o = i * p.T + (s - 1);
     const float x = p.pred_pose[o * 3], y = p.pred_pose[o * 3 + 1], w = p.pred_pose[o * 3 + 2];

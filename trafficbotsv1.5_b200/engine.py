@@ -90,7 +90,7 @@ def _copy_tree(dst, src) -> None:
 class RolloutEngine:
     def __init__(self, P: Dict[str, Tensor], cfg: Optional[dict] = None, device="cuda", precision: int = 0,
                  n_rollout: int = 32, step_end: Optional[int] = None, use_graph: bool = True,
-                 rule_checks: bool = False):
+                 rule_checks: bool = False, record_feedback: bool = False):
         L.load()  # fail loudly if the CUDA library is missing
         self.cfg = cfg or C.default_model_cfg()
         self.sz = C.derived_sizes(self.cfg)
@@ -101,6 +101,8 @@ class RolloutEngine:
         self.tl_per_scene = True  # the TL branch is a function of (scene, TL history) only: evaluated once per scene
         self.use_graph = use_graph
         self.rule_checks = rule_checks  # also evaluate the logging-only TrafficRuleChecker checks every step
+        # also keep outside_map_this_step / dest_reached_this_step of every step (RolloutBuffer.violation, buffer.py:57-60)
+        self.record_feedback = record_feedback
         self.dyn = C.DYNAMICS_CFG
         self._graph = None   # (graph for odd steps, graph for even steps): the TL branch is double-buffered
         self._host_step = 1  # parity source for eager _step calls
@@ -108,6 +110,7 @@ class RolloutEngine:
         self._side = torch.cuda.Stream(device=self.dev)  # traffic-light branch runs beside the agent front-end
         self._side2 = torch.cuda.Stream(device=self.dev)  # KNN selects run beside the history encoder and layer 0
         self._side3 = torch.cuda.Stream(device=self.dev)
+        self._sat = ops.fp16_flag(self.dev)  # fp16 range guard of the tensor-core mode (include/tb_knarpe.h)
         # constants rounded the way the reference's fp32 tensor ops round them (traffic_rule_checker.py:94-96,103,308)
         one = torch.ones(1)
         self.thresh_lane = float(one * 50 * (1 - torch.zeros(1) * 0.8))
@@ -125,12 +128,14 @@ class RolloutEngine:
         return dict(mp=mp, tl=tl, kv_mp=kv_mp)
 
     @torch.no_grad()
-    def predict_destinations(self, batch: Dict[str, Tensor], mp: Optional[dict] = None, deterministic_k0: bool = True,
+    def predict_destinations(self, batch: Dict[str, Tensor], mp: Optional[dict] = None, deterministic_k0: bool = False,
                              generator: Optional[torch.Generator] = None) -> Dict[str, Tensor]:
         """The once-per-scene step right before the loop (waymo_motion.py:469-495): destination
         distribution of every agent over the map polylines (NaviPredictor "dest" mode, needs `navi_predictor.*`
         weights) and one destination per rollout: rollout 0 takes the argmax when `deterministic_k0`
-        (`joint_future_pred_deterministic_k0`), the others are sampled (DestCategorical.sample, distributions.py:143-159).
+        (`joint_future_pred_deterministic_k0`, default False as in configs/model/sim_agent.yaml:13), the others are
+        sampled (DestCategorical.sample, distributions.py:143-159) with torch's multinomial — once per scene, not part
+        of the per-step loop.
         Returns logits [n_sc,n_ag,n_mp], probs, dest int64 [n_sc,R,n_ag] (feed as batch["agent/dest"]) and
         navi_valid [n_sc,n_ag] (batch["ag_navi_valid"])."""
         dev = self.dev
@@ -177,6 +182,8 @@ class RolloutEngine:
                   knn_state=z(B, A, 3),  # agent -> map select: (x, y, K-th squared distance) of the previous step
                   knn_state_tl=z(B, A, 3),  # same for the agent -> traffic-light select
                   init_navi_valid=z(B, A, dt=torch.bool))
+        if self.record_feedback:
+            st.update(fb_outside=z(B, A, T, dt=u8), fb_reached=z(B, A, T, dt=u8))
         if self.rule_checks:
             st.update(ag_size=z(n_sc, A, 3), passive_counter=z(B, A), seg=z(n_sc, n_mp, n_node, 4),
                       node_invalid=z(n_sc, n_mp, n_node, dt=u8), poly_circle=z(n_sc, n_mp, 3),
@@ -204,12 +211,13 @@ class RolloutEngine:
         st["ag_type"].copy_(rep(g("ref/ag_type")))
         lat = g("ag_latent")[:, :R]
         st["latent"].copy_(lat.reshape(n_sc * R * st["A"], -1))
-        st["latent_invalid"].copy_(~rep(g("ag_latent_valid")))
+        per_rollout = lambda t: t if t.shape[0] == n_sc * R else rep(t)  # noqa: E731  [n_sc, A] or [n_sc*R, A]
+        st["latent_invalid"].copy_(~per_rollout(g("ag_latent_valid")))
         dest = g("agent/dest")
         if dest.dim() == 2:  # one destination per (scene, agent); [n_sc, R, A] = per-rollout samples
             dest = dest[:, None].expand(-1, R, -1)
         st["dest_idx"].copy_(dest.reshape(n_sc * R, -1))
-        st["init_navi_valid"].copy_(rep(g("ag_navi_valid")))
+        st["init_navi_valid"].copy_(per_rollout(g("ag_navi_valid")))
         mp_dir = g("map/dir")[..., :2]
         st["mp_pos"].copy_(g("map/pos")[..., :2])
         st["mp_dirn"].copy_(mp_dir / torch.norm(mp_dir, dim=-1, keepdim=True))
@@ -226,7 +234,7 @@ class RolloutEngine:
         R = self.R
         rep = lambda t: t.repeat_interleave(R, 0)  # noqa: E731
         for k in ("disabled", "dest_reached", "hist_valid", "hist_pose", "hist_motion", "hist_tl", "pred_valid",
-                  "pred_pose", "pred_motion", "tl_out"):
+                  "pred_pose", "pred_motion", "tl_out") + (("fb_outside", "fb_reached") if self.record_feedback else ()):
             st[k].zero_()
         if self.rule_checks:
             st["passive_counter"].zero_()
@@ -285,7 +293,7 @@ class RolloutEngine:
             aux.update(tl_feat=tl_feat, logits=logits, act=act, ag_feat=st["x_cat"][:, :d].clone())
         dy = self.dyn
         order = ("veh", "ped", "cyc")
-        L.check(lib.tb_dyn_step(
+        L.check(lib.tb_dyn_step_ex(
             L.ptr(act), L.ptr(st["ag_type"]), ops.host_f3([dy[k]["max_acc"] for k in order]),
             ops.host_f3([dy[k]["max_yaw_rate"] for k in order]), dy["dt"], L.ptr(st["valid"]), L.ptr(st["disabled"]),
             L.ptr(ops._u8(st["navi_invalid"])), L.ptr(st["dest_reached"]), L.ptr(st["pose"]), L.ptr(st["motion"]),
@@ -294,7 +302,7 @@ class RolloutEngine:
             L.ptr(st["mp_node_invalid"]), L.ptr(st["mp_kind"]), st["n_mp"], st["n_node"], self.thresh_lane,
             self.thresh_edge, self.cos_rot, L.ptr(st["d_step"]), st["B"], st["A"], m.W, self.T, L.ptr(st["hist_valid"]),
             L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]), L.ptr(st["pred_valid"]), L.ptr(st["pred_pose"]),
-            L.ptr(st["pred_motion"]), L.stream()), "tb_dyn_step")
+            L.ptr(st["pred_motion"]), L.ptr(st.get("fb_outside")), L.ptr(st.get("fb_reached")), L.stream()), "tb_dyn_step_ex")
         main.wait_stream(self._side)  # TL feedback of this step applied, TL tokens of the next step ready
         if self.rule_checks:
             tlp = static["tl"]
@@ -317,6 +325,7 @@ class RolloutEngine:
         n_tl = batch["sc/tl_valid"].shape[1]
         _, n_mp, n_node = batch["sc/mp_valid"].shape
         shape = (n_sc, A, n_tl, n_gt, n_mp, n_node)
+        self._sat.zero_()  # sticky from here on: scene encoding and every run() of this batch OR into it
         if self._shape != shape:
             self._st = self._alloc(*shape)
             self._shape, self._graph = shape, None
@@ -335,6 +344,8 @@ class RolloutEngine:
     def run(self, n_steps: Optional[int] = None, record=None) -> Dict[str, Tensor]:
         """Run the closed loop from time 0 for n_steps (default: all). Returns views of the trajectory buffers."""
         st, n_steps = self._st, n_steps or self.T
+        if not 1 <= n_steps <= self.T:  # pred_* / tl_out hold step_end columns; the kernels also refuse s > T
+            raise ValueError(f"run(n_steps={n_steps}): the engine was built with step_end={self.T}")
         self._reset(st)
         if self.use_graph and record is None:
             if self._graph is None:
@@ -370,6 +381,8 @@ class RolloutEngine:
         n_sc, A = st["n_sc"], st["A"]
         tl = st["tl_out"] if not self.tl_per_scene else st["tl_out"].repeat_interleave(R, 0)
         vio = {k: st[f"vio_{k}"].bool() for k in VIOLATIONS} if self.rule_checks else {}
+        if self.record_feedback:
+            vio.update(outside_map=st["fb_outside"].bool(), dest_reached=st["fb_reached"].bool())
         return dict(**vio, pred_valid=st["pred_valid"].bool(), pred_pose=st["pred_pose"], pred_motion=st["pred_motion"],
                     tl_state=tl.bool(), final_valid=st["valid"].bool(), final_navi_valid=~st["navi_invalid"],
                     joint_pose=st["pred_pose"].view(n_sc, R, A, self.T, 3))
@@ -415,6 +428,17 @@ class RolloutEngine:
                                         k_pred, use_ade, mpa_nms_thresh, score_temperature, 4, 5, n_fut)
         return dict(trajs=trajs, scores=sc, mode=mode)
 
+    def check_fp16_range(self) -> None:
+        """Raise if a 16-bit intermediate of the tensor-core mode saturated since the last reset (one 4-byte read,
+        synchronises). The reference computes these in fp32; a checkpoint whose [q|u], [k|v] or ReLU hidden rows exceed
+        65,504 must run with `precision=0`, or `model.kv_half = False` (tf32 projections, fp32 intermediates)."""
+        if int(self._sat.item()) != 0:
+            raise FloatingPointError("an fp16 intermediate of the tensor-core mode saturated at 65504: rerun this "
+                                     "checkpoint with RolloutEngine(precision=0) or engine.model.kv_half = False")
+
     def rollout(self, batch: Dict[str, Tensor], n_steps: Optional[int] = None) -> Dict[str, Tensor]:
         self.prepare(batch)
-        return self.run(n_steps)
+        res = self.run(n_steps)
+        if self.model.kv_half:
+            self.check_fp16_range()
+        return res

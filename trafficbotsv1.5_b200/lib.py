@@ -20,24 +20,41 @@ _lib = None
 EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_linear", "tb_linear_ln", "tb_layernorm",
            "tb_pointnet_pool", "tb_pose_emb", "tb_ag_featurize", "tb_tl_featurize", "tb_dyn_step", "tb_tl_step",
            "tb_step_advance", "tb_gather_rows", "tb_action_mean", "tb_rule_check", "tb_future_filter",
-           "tb_traj_global", "tb_womd_post", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd"]
+           "tb_traj_global", "tb_womd_post", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd", "tb_set_fp16_flag", "tb_dyn_step_ex"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a -> trafficbotsv1.5_b200/libtbknarpe.so (cross-compiles on CPU)."""
-    src = [os.path.join(_PKG, "csrc", s) for s in _SOURCES]
-    deps = src + glob.glob(os.path.join(_PKG, "csrc", "*.cuh")) + [os.path.join(_ROOT, "include", "tb_knarpe.h")]
-    if not force and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
-        return SO_PATH
+    """nvcc -gencode arch=compute_100a,code=sm_100a -> trafficbotsv1.5_b200/libtbknarpe.so (cross-compiles on CPU).
+    Every csrc/*.cu is compiled to its own object (in parallel, rebuilt only when it or a header changed; objects live
+    under csrc/_obj, git- and gpurun-ignored) and the objects are linked into the one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+    csrc = os.path.join(_PKG, "csrc")
+    hdrs = glob.glob(os.path.join(csrc, "*.cuh")) + [os.path.join(_ROOT, "include", "tb_knarpe.h")]
+    hdr_t = max(os.path.getmtime(h) for h in hdrs)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-           "-Xcompiler", "-fPIC", "-I", os.path.join(_ROOT, "include"), "-lcuda", "-o", SO_PATH] + src
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+             "-I", os.path.join(_ROOT, "include")]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+        flags.insert(0, "-Xptxas=-v")
     extra = os.environ.get("TB_NVCC_FLAGS")  # tuning experiments only (e.g. -DTB_ATTN_G=2)
     if extra:
-        cmd[1:1] = extra.split()
-    subprocess.run(cmd, check=True)
+        flags[0:0] = extra.split()
+        force = True
+    objdir = os.path.join(csrc, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    jobs, objs = [], []
+    for name in _SOURCES:
+        src, obj = os.path.join(csrc, name), os.path.join(objdir, name[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append([nvcc] + flags + ["-c", src, "-o", obj])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for r in ex.map(lambda c: subprocess.run(c, capture_output=not verbose, text=True), jobs):
+                if r.returncode != 0:
+                    raise RuntimeError(f"nvcc failed: {' '.join(r.args)}\n{r.stdout or ''}{r.stderr or ''}")
+    if jobs or not os.path.exists(SO_PATH) or any(os.path.getmtime(o) > os.path.getmtime(SO_PATH) for o in objs):
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs + ["-lcuda"], check=True)
     return SO_PATH
 
 
@@ -64,6 +81,8 @@ def load() -> ctypes.CDLL:
         "tb_tl_featurize": [P, P, P, I, I, I, P, I, P, P],
         "tb_dyn_step": [P, P, P, P, F, P, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P, I, I, F, F, F, P, I, I, I,
                         I, P, P, P, P, P, P, P],
+        "tb_dyn_step_ex": [P, P, P, P, F, P, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P, I, I, F, F, F, P, I, I,
+                           I, I, P, P, P, P, P, P, P, P, P],
         "tb_tl_step": [P, P, P, I, P, I, I, I, I, P, P, P],
         "tb_step_advance": [P, P],
         "tb_gather_rows": [P, I, I, P, I, I, I, I, P, I, P],
@@ -74,6 +93,7 @@ def load() -> ctypes.CDLL:
         "tb_womd_post": [P, P, P, I, I, I, I, I, I, I, F, F, F, F, I, I, I, P, P, P, P],
         "tb_ag_frontend": [P, P, P, P, P, P, I, I, I, P, P, P, I, P, P, P, P, P, I, P],
         "tb_ag_frontend_blob_halves": [],
+        "tb_set_fp16_flag": [P],
         "tb_knarpe_attn_bwd": [P, I, P, I, P, I, I, I, I, P, I, I, I, I, P, P, P, P, I, I, I, I, P, P, I, P, I, P, P, P],
     }
     for name, args in sig.items():

@@ -64,6 +64,24 @@ def head_interleave_perm(d: int = 128, n_head: int = H) -> Tensor:
     return 32 * head + 8 * ((s >> 4) & 3) + (s & 7)
 
 
+def _probe_fp32(fn):
+    """Error-attribution hook of profiles/parity_probe.py: with `model._probe_heads_fp32` set, the decorated head
+    functions run on the fp32 path while the rest of the model keeps its precision. Never set on the product path."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if getattr(self, "_probe_heads_fp32", False) and self.precision != 0:
+            saved = (self.precision, self.kv_half)
+            self.precision, self.kv_half = 0, False
+            try:
+                return fn(self, *a, **k)
+            finally:
+                self.precision, self.kv_half = saved
+        return fn(self, *a, **k)
+    return wrapped
+
+
 class HotPathModel:
     """Device-resident weights + the kernel sequences of the hot-path modules."""
 
@@ -579,6 +597,7 @@ class HotPathModel:
         return self._ag_front
 
     # ------------------------------------------------------------------------------------------ heads (per step)
+    @_probe_fp32
     def navi_static(self, mp: Dict[str, Tensor], dest_idx: Tensor, R: int) -> dict:
         """Static halves of NaviEncoder.forward (navigation.py:65-71): mlp_mp(map feature of the destination) and the
         destination's global pose. dest_idx int32 [B, A]."""
@@ -588,6 +607,7 @@ class HotPathModel:
         pose = ops.gather_rows(mp["mp_token_pose"].contiguous(), flat, A, R)
         return dict(feat=self.lin(f, "navi_encoder.mlp_mp.fc_layers.0"), pose=pose)
 
+    @_probe_fp32
     def latent_static(self, navi: dict, st: dict) -> None:
         """AddNaviLatent.mlp_in(latent) (add_navi_latent.py:50) depends only on the rollout's fixed latent sample:
         evaluated once per rollout into the right half of a persistent cat buffer."""
@@ -599,6 +619,7 @@ class HotPathModel:
         navi["latent_cat"] = cat
         navi["latent_feat"] = True
 
+    @_probe_fp32
     def heads(self, x_cat: Tensor, st: dict, navi: dict) -> Tensor:
         """navi_encoder (per-step half) -> add_navi -> add_latent -> action-head branches
         (traffic_bots.py:191-217). x_cat [M, 2d] with the agent feature already in the left half.

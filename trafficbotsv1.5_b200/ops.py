@@ -11,6 +11,21 @@ from . import lib as L
 LAUNCHES = 0  # number of kernels launched through this module (bench.py reports it as gpu_launches)
 
 
+_FP16_FLAG = {}
+
+
+def fp16_flag(device) -> Tensor:
+    """The sticky fp16-saturation word of this process' device (tb_set_fp16_flag): allocated once, never freed (its
+    address is baked into captured graphs), zeroed by the caller before a rollout and read after it."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _FP16_FLAG:
+        assert not _FP16_FLAG, "one process drives one GPU (the flag pointer is a per-process setting)"
+        _FP16_FLAG[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.check(L.load().tb_set_fp16_flag(L.ptr(_FP16_FLAG[key])), "tb_set_fp16_flag")
+    return _FP16_FLAG[key]
+
+
 def _count(n=1):
     global LAUNCHES
     LAUNCHES += n

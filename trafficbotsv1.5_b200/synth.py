@@ -90,6 +90,55 @@ def _one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed, boundary, n_rollout, late
     return d
 
 
+def make_rule_scene_batch(n_sc: int, n_ag: int = 48, n_mp: int = 96, n_tl: int = 40, seed: int = 5000,
+                          boundary: float = 80.0, scale: float = 0.4, **kw) -> Dict[str, torch.Tensor]:
+    """A `make_scene_batch` scene edited so that the two rare TrafficRuleChecker events fire often
+    (traffic_rule_checker.py:176-274): the first n_tl agents are long, fast vehicles with a RED traffic light 0.5-3 m
+    ahead of their start pose (they drive over it during the ground-truth warm start -> `run_red_light`), the next
+    n_ag/4 agents are slow vehicles standing on distinct lane-centre polylines with nothing ahead (-> `passive` once
+    their counter passes 20 steps)."""
+    b = make_scene_batch(n_sc=n_sc, n_ag=n_ag, n_mp=n_mp, n_tl=n_tl, seed=seed, boundary=boundary, scale=scale, **kw)
+    n_hist = b["sc/ag_valid"].shape[-1]
+    th = torch.arange(n_hist, dtype=torch.float32) * 0.1
+    veh = torch.tensor([True, False, False])
+    n_red, n_slow = min(n_tl, n_ag // 2), n_ag // 4
+    for s in range(n_sc):
+        g = torch.Generator().manual_seed(seed + 77 * (s + 1))
+        U = lambda n, lo, hi: torch.rand(n, generator=g) * (hi - lo) + lo  # noqa: E731
+
+        def put(i, xy0, yaw, spd, length):
+            hd = torch.stack([torch.cos(yaw), torch.sin(yaw)])
+            b["sc/ag_pose"][s, i, :, :2] = xy0[None] + th[:, None] * spd * hd[None]
+            b["sc/ag_pose"][s, i, :, 2] = yaw
+            b["sc/ag_motion"][s, i] = 0.0
+            b["sc/ag_motion"][s, i, :, 0] = spd
+            b["sc/ag_valid"][s, i] = True
+            b["ref/ag_type"][s, i] = veh
+            b["ref/ag_size"][s, i, 0] = length
+            b["ref/ag_size"][s, i, 1] = 2.0
+
+        spd, length, dist = U(n_red, 5.0, 10.0), U(n_red, 3.0, 5.0), U(n_red, 0.5, 3.0)
+        for j in range(n_red):  # a red light ahead of agent j
+            xy0, yaw = b["sc/ag_pose"][s, j, 0, :2].clone(), b["sc/ag_pose"][s, j, 0, 2].clone()
+            put(j, xy0, yaw, spd[j], length[j])
+            hd = torch.stack([torch.cos(yaw), torch.sin(yaw)])
+            b["sc/tl_pose"][s, j, :2] = xy0 + dist[j] * hd
+            b["sc/tl_pose"][s, j, 2] = yaw
+            b["sc/tl_valid"][s, j] = True
+            b["sc/tl_state"][s, j] = False
+            b["sc/tl_state"][s, j, :, 1] = True  # LANE_STATE_STOP during the whole history
+        lanes = torch.nonzero(b["map/type"][s, :, :3].any(-1) & b["map/valid"][s].all(-1)).flatten()
+        lanes = lanes[torch.randperm(len(lanes), generator=g)][:n_slow]
+        slow = U(len(lanes), 0.0, 1.0)
+        for k, pl in enumerate(lanes.tolist()):  # a slow vehicle on lane polyline pl, node 5
+            put(n_red + k, b["sc/mp_pose"][s, pl, 5, :2].clone(), b["sc/mp_pose"][s, pl, 0, 2].clone(), slow[k],
+                torch.tensor(4.0))
+    b["sc/ag_attr"] = torch.cat([b["ref/ag_size"], b["ref/ag_type"].float()], -1)
+    b["ag_navi_valid"] = b["sc/ag_valid"].any(-1)
+    b["ag_latent_valid"] = b["sc/ag_valid"].any(-1)
+    return b
+
+
 def make_wosac_post_inputs(seed: int, n_sc: int, K: int, A: int, T: int):
     """Seeded inputs of the WOSAC post-processing fixture (wosac_post_processing.py:31-75; shared by the golden
     generator and the tests): scene-centric joint futures, violation
