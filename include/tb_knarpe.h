@@ -256,6 +256,20 @@ int tb_dyn_step_ex(const float* act_branch, const uint8_t* ag_type, const float*
  *   writes the new one-hot state into ring slot s%W of hist_tl [B,TL,W,5] and tl_out [B,TL,T,5] at s-1. */
 int tb_tl_step(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt_tl, int n_gt, const int* d_step,
                int B, int TL, int W, int T, uint8_t* hist_tl, uint8_t* tl_out, void* stream);
+/* tb_tl_step + RolloutBuffer.tl_state_nll (waymo_motion.py:270-277): o_nll [B,TL,T] (optional) receives, at s-1,
+ * -log_softmax(clamp(logits))[argmax gt state] while s < n_gt and 0 afterwards. */
+int tb_tl_step_ex(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt_tl, int n_gt, const int* d_step,
+                  int B, int TL, int W, int T, uint8_t* hist_tl, uint8_t* tl_out, float* o_nll, void* stream);
+
+/* Dynamics.update_ag of a stand-alone Dynamics object (utils/dynamics.py:66-120, MultiPathPP :237-274):
+ *   action_unbounded [n,2] (mean or sample of the action distribution), ag_type [n,3] u8, valid [n] u8,
+ *   player_valid [n] u8 / player_action [n,2] (optional override of the physical action, :96-99),
+ *   max_acc[3], max_yaw_rate[3] (HOST arrays: veh, ped, cyc), dt; pose / motion [n,3] in;
+ *   out_pose / out_motion [n,3], out_action [n,2] (physical action: m/s^2, rad/s). Invalid agents -> zeros. */
+int tb_dyn_update(const float* action_unbounded, const uint8_t* ag_type, const uint8_t* valid,
+                  const uint8_t* player_valid, const float* player_action, const float* max_acc,
+                  const float* max_yaw_rate, float dt, int n, const float* pose, const float* motion, float* out_pose,
+                  float* out_motion, float* out_action, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Logging-only traffic-rule checks of one step — TrafficRuleChecker.check

@@ -62,3 +62,35 @@ def test_fused_attention_weights_reproduce_the_reference_formulation():
         out = torch.cat([ov, z], -1) @ f["w_out"].T + f["b_out"]
         out = out.masked_fill(mask.all(-1)[..., None], 0.0)
         assert float((out - ref).abs().max()) < 1e-5 * float(ref.abs().max()), interleaved
+
+
+def test_rollout_buffer_layout_and_log_prob():
+    """RolloutBuffer of the rollout-level drop-in (utils/buffer.py:103-146): joint-future flattening and the navigation
+    log-probability average, on hand-made tensors (no GPU)."""
+    from trafficbotsv1_5_b200.waymo_motion import RolloutBuffer, TeacherForcing, _check_teacher_forcing
+    n_sc, R, A, T, n_tl = 2, 3, 4, 5, 2
+    B = n_sc * R
+    buf = RolloutBuffer(step_end=T, step_current=1)
+    assert (buf.step_start, buf.step_end, buf.step_future_start) == (1, T, 1)
+    lp0 = torch.arange(B * A, dtype=torch.float32).view(B, A)
+    v0 = torch.ones(B, A, dtype=torch.bool)
+    v0[0, 0] = False
+    buf.add_navi_log_prob(lp0, v0)
+    buf.add_navi_log_prob(lp0 * 3, torch.zeros(B, A, dtype=torch.bool))  # a later re-prediction nobody needed
+    buf._finish()
+    buf.pred_valid = torch.ones(B, A, T, dtype=torch.bool)
+    buf.pred_pose = torch.zeros(B, A, T, 3)
+    buf.pred_motion = torch.zeros(B, A, T, 3)
+    buf.action_log_prob = torch.zeros(B, A, T)
+    buf.mask_teacher_forcing = torch.zeros(B, A, T, dtype=torch.bool)
+    buf.tl_state_nll = torch.zeros(B, n_tl, T)
+    buf.tl_state_nll_invalid = torch.zeros(B, n_tl, T, dtype=torch.bool)
+    buf.violation = {"collided": torch.zeros(B, A, T, dtype=torch.bool)}
+    buf.flatten_joint_future(R)
+    assert buf.pred_pose.shape == (n_sc, R, A, T, 3) and buf.navi_log_prob.shape == (n_sc, R, A, 2)
+    assert buf.tl_state_nll.shape == (n_sc, R, n_tl, T) and buf.violation["collided"].shape == (n_sc, R, A, T)
+    buf.compute_log_prob(torch.ones(B, A))
+    exp = lp0.view(n_sc, R, A).clone() + 1
+    exp[0, 0, 0] = 1.0  # no valid navigation sample: 0 (+ the latent term)
+    assert torch.equal(buf.log_prob, exp)
+    assert _check_teacher_forcing(TeacherForcing(step_spawn_agent=7, step_warm_start=9)) == (7, 9)

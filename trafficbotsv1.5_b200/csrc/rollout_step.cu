@@ -193,12 +193,37 @@ __global__ void __launch_bounds__(128) dyn_step_kernel(DynArgs p) {
 
 __global__ void tl_step_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ tl_invalid,
                                const uint8_t* __restrict__ gt_tl, int n_gt, const int* __restrict__ d_step, int n_tot,
-                               int W, int T, uint8_t* __restrict__ hist_tl, uint8_t* __restrict__ tl_out) {
+                               int W, int T, uint8_t* __restrict__ hist_tl, uint8_t* __restrict__ tl_out,
+                               float* __restrict__ o_nll) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // b*TL + tl
   if (i >= n_tot) return;
   const int s = *d_step;
   if (s < 1 || s > T) return;  // tl_out[.., s - 1] would be out of bounds
   uint8_t st[5];
+  if (o_nll) {  // tl_state_nll of the step (waymo_motion.py:270-277): -log_softmax(clamped logits)[gt state], 0 past the gt
+    float nll = 0.f;
+    if (s < n_gt) {
+      const bool inv = tl_invalid[i] != 0;
+      float v[5], mx = -INFINITY;
+      int gt = 0;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        v[c] = inv ? 0.f : fminf(fmaxf(logits[(size_t)i * 5 + c], -3.f), 3.f);
+        mx = fmaxf(mx, v[c]);
+      }
+      uint8_t best = 0;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {  // max(-1)[1] of a bool one-hot: first maximal entry
+        const uint8_t g = gt_tl[((size_t)i * n_gt + s) * 5 + c];
+        if (g > best) { best = g; gt = c; }
+      }
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) se += expf(v[c] - mx);
+      nll = -(v[gt] - mx - logf(se));
+    }
+    o_nll[(size_t)i * T + (s - 1)] = nll;
+  }
   if (s < n_gt) {  // ground-truth traffic lights while available (teacher_forcing.py:65,159-160)
 #pragma unroll
     for (int c = 0; c < 5; ++c) st[c] = gt_tl[((size_t)i * n_gt + s) * 5 + c];
@@ -314,14 +339,69 @@ extern "C" int tb_dyn_step(const float* act_branch, const uint8_t* ag_type, cons
                         hist_valid, hist_pose, hist_motion, pred_valid, pred_pose, pred_motion, nullptr, nullptr, stream);
 }
 
-extern "C" int tb_tl_step(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt_tl, int n_gt,
-                          const int* d_step, int B, int TL, int W, int T, uint8_t* hist_tl, uint8_t* tl_out,
-                          void* stream) {
+extern "C" int tb_tl_step_ex(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt_tl, int n_gt,
+                             const int* d_step, int B, int TL, int W, int T, uint8_t* hist_tl, uint8_t* tl_out,
+                             float* o_nll, void* stream) {
   if (!logits || !tl_invalid || !gt_tl || !d_step || !hist_tl || !tl_out) return TB_ERR_NULL;
   if (B <= 0 || TL <= 0 || W <= 0 || T <= 0 || n_gt <= 0) return TB_ERR_BAD_SHAPE;
   const int n = B * TL;
   tl_step_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(logits, tl_invalid, gt_tl, n_gt, d_step,
-                                                                               n, W, T, hist_tl, tl_out);
+                                                                               n, W, T, hist_tl, tl_out, o_nll);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+extern "C" int tb_tl_step(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt_tl, int n_gt,
+                          const int* d_step, int B, int TL, int W, int T, uint8_t* hist_tl, uint8_t* tl_out,
+                          void* stream) {
+  return tb_tl_step_ex(logits, tl_invalid, gt_tl, n_gt, d_step, B, TL, W, T, hist_tl, tl_out, nullptr, stream);
+}
+
+// Dynamics.update_ag for a stand-alone Dynamics object (utils/dynamics.py:66-120 + MultiPathPP :237-274): unbounded
+// action (the distribution's mean or sample) -> physical action per agent type -> optional player override ->
+// unicycle update; invalid agents and agents without a type come out as zeros (:108-119).
+__global__ void dyn_update_kernel(const float* __restrict__ act, const uint8_t* __restrict__ ag_type,
+                                  const uint8_t* __restrict__ valid, const uint8_t* __restrict__ player_valid,
+                                  const float* __restrict__ player_action, float3 max_acc, float3 max_yaw, float dt, int n,
+                                  const float* __restrict__ pose, const float* __restrict__ motion,
+                                  float* __restrict__ o_pose, float* __restrict__ o_motion, float* __restrict__ o_action) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool v = valid[i] != 0;
+  const float ma[3] = {max_acc.x, max_acc.y, max_acc.z}, my[3] = {max_yaw.x, max_yaw.y, max_yaw.z};
+  float acc = 0.f, yr = 0.f, n_type = 0.f;
+  const float t0 = tanhf(act[(size_t)i * 2]), t1 = tanhf(act[(size_t)i * 2 + 1]);
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+    if (ag_type[(size_t)i * 3 + t]) { acc += t0 * ma[t]; yr += t1 * my[t]; n_type += 1.f; }  // masked sum over the types
+  if (!v) { acc = 0.f; yr = 0.f; }
+  if (player_valid && player_valid[i] && v) { acc = player_action[(size_t)i * 2]; yr = player_action[(size_t)i * 2 + 1]; }
+  const float x = pose[(size_t)i * 3], y = pose[(size_t)i * 3 + 1], w = pose[(size_t)i * 3 + 2], spd = motion[(size_t)i * 3];
+  const float hdt = 0.5f * dt;
+  const float v_t = __fadd_rn(spd, __fmul_rn(hdt, acc)), th_t = __fadd_rn(w, __fmul_rn(hdt, yr));
+  float sn, cs;
+  sincosf(th_t, &sn, &cs);
+  // every type's MultiPathPP.update gives the same state; the masked sum over types multiplies it by the type count
+  float nx = __fadd_rn(x, __fmul_rn(dt, __fmul_rn(v_t, cs))) * n_type, ny = __fadd_rn(y, __fmul_rn(dt, __fmul_rn(v_t, sn))) * n_type;
+  float nw = __fadd_rn(w, __fmul_rn(dt, yr)) * n_type, nspd = __fadd_rn(spd, __fmul_rn(dt, acc)) * n_type;
+  float nacc = acc * n_type, nyr = yr * n_type;
+  if (!v) { nx = ny = nw = nspd = nacc = nyr = 0.f; }
+  o_pose[(size_t)i * 3] = nx; o_pose[(size_t)i * 3 + 1] = ny; o_pose[(size_t)i * 3 + 2] = nw;
+  o_motion[(size_t)i * 3] = nspd; o_motion[(size_t)i * 3 + 1] = nacc; o_motion[(size_t)i * 3 + 2] = nyr;
+  o_action[(size_t)i * 2] = acc; o_action[(size_t)i * 2 + 1] = yr;
+}
+
+extern "C" int tb_dyn_update(const float* action_unbounded, const uint8_t* ag_type, const uint8_t* valid,
+                             const uint8_t* player_valid, const float* player_action, const float* max_acc,
+                             const float* max_yaw_rate, float dt, int n, const float* pose, const float* motion,
+                             float* out_pose, float* out_motion, float* out_action, void* stream) {
+  if (!action_unbounded || !ag_type || !valid || !max_acc || !max_yaw_rate || !pose || !motion || !out_pose || !out_motion ||
+      !out_action || (player_valid && !player_action))
+    return TB_ERR_NULL;
+  if (n <= 0) return TB_ERR_BAD_SHAPE;
+  dyn_update_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      action_unbounded, ag_type, valid, player_valid, player_action, make_float3(max_acc[0], max_acc[1], max_acc[2]),
+      make_float3(max_yaw_rate[0], max_yaw_rate[1], max_yaw_rate[2]), dt, n, pose, motion, out_pose, out_motion, out_action);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

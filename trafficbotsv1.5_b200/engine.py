@@ -90,7 +90,7 @@ def _copy_tree(dst, src) -> None:
 class RolloutEngine:
     def __init__(self, P: Dict[str, Tensor], cfg: Optional[dict] = None, device="cuda", precision: int = 0,
                  n_rollout: int = 32, step_end: Optional[int] = None, use_graph: bool = True,
-                 rule_checks: bool = False, record_feedback: bool = False):
+                 rule_checks: bool = False, record_feedback: bool = False, dynamics_cfg: Optional[dict] = None):
         L.load()  # fail loudly if the CUDA library is missing
         self.cfg = cfg or C.default_model_cfg()
         self.sz = C.derived_sizes(self.cfg)
@@ -103,7 +103,9 @@ class RolloutEngine:
         self.rule_checks = rule_checks  # also evaluate the logging-only TrafficRuleChecker checks every step
         # also keep outside_map_this_step / dest_reached_this_step of every step (RolloutBuffer.violation, buffer.py:57-60)
         self.record_feedback = record_feedback
-        self.dyn = C.DYNAMICS_CFG
+        self.dyn = dynamics_cfg or C.DYNAMICS_CFG
+        # inference teacher forcing (teacher_forcing.py:51-82): spawn up to / warm start up to these steps
+        self.tf_steps = (C.ROLLOUT_CFG["step_spawn_agent"], C.ROLLOUT_CFG["step_warm_start"])
         self._graph = None   # (graph for odd steps, graph for even steps): the TL branch is double-buffered
         self._host_step = 1  # parity source for eager _step calls
         self._shape = None
@@ -125,6 +127,48 @@ class RolloutEngine:
         mp = self.model.map_encoder(g("sc/mp_valid"), g("sc/mp_attr"), g("sc/mp_pose"))
         tl = self.model.tl_pre_compute(g("sc/tl_valid"), g("sc/tl_attr"), g("sc/tl_pose"), mp)
         kv_mp = self.model.ag_static(mp)
+        return dict(mp=mp, tl=tl, kv_mp=kv_mp)
+
+    @torch.no_grad()
+    def static_from_tokens(self, mp_tokens: Dict[str, Tensor], tl_tokens: Dict[str, Tensor]) -> dict:
+        """The `static` argument of `prepare` from per-scene token dicts in the reference's layout, as the `TrafficBots`
+        drop-in's `mp_encoder` / `tl_encoder.pre_compute` return them (map_encoder.py:107-113, traffic_light.py:76-154;
+        relative poses raw [.., 3], optional `b200_kv_*` per-layer K|V tables): nothing is re-encoded."""
+        m, d, W = self.model, self.model.d, self.model.W
+        c = lambda t: t.contiguous()  # noqa: E731
+        n_sc, n_mp = mp_tokens["mp_token_pose"].shape[:2]
+        n_tl = tl_tokens["tl_token_pose"].shape[1]
+        tok_pose, tok_inv = c(mp_tokens["mp_token_pose"].float()), c(mp_tokens["mp_token_invalid"])
+        mp = dict(mp_token_invalid=tok_inv, mp_token_feature=c(mp_tokens["mp_token_feature"].float()),
+                  mp_token_pose=tok_pose, **m.sorted_map(tok_pose, tok_inv))
+        kv_dt = torch.float16 if m.kv_half else torch.float32
+        n_ag_l, n_tl_l = self.cfg["ag_encoder"]["n_layer_tf"], self.cfg["tl_encoder"]["n_layer_tf"]
+
+        def tables(prefix, n_layer, layer_name):
+            keys = [f"{prefix}{i}" for i in range(n_layer)]
+            if all(k in mp_tokens or k in tl_tokens for k in keys):
+                tabs = [(mp_tokens.get(k) if k in mp_tokens else tl_tokens[k]) for k in keys]
+                if all(t.dtype == kv_dt for t in tabs):
+                    return [c(t).view(n_sc * n_mp, 2 * d) for t in tabs]
+            feat2d = mp["mp_token_feature"].reshape(n_sc * n_mp, d)
+            return [m.kv_table(feat2d, f"{layer_name}.{i}", "norm_tgt") for i in range(n_layer)]
+
+        kv_mp = tables("b200_kv_ag_", n_ag_l, "ag_encoder.tf_ag2agmptl.layers")
+        kv_tl = tables("b200_kv_tl_", n_tl_l, "tl_encoder.tf_tl2tlmp.layers")
+        for k in ("rpe_tl2tl", "rpe_tl2mp"):
+            if tl_tokens[k].shape[-1] != 3:
+                raise NotImplementedError(f"{k}: pass the raw relative poses [.., 3] of the drop-in's pre_compute (the "
+                                          "embedding is evaluated inside the attention kernel)")
+        knn = lambda i, v, r: dict(idx=c(tl_tokens[i].to(torch.int32)), inv=c(tl_tokens[v]), rel=c(tl_tokens[r].float()))  # noqa
+        if "knn_idx_tl2mp" not in tl_tokens:
+            raise NotImplementedError("tl_tokens need knn_idx_tl2mp (indices), not the pre-gathered knn_tgt_tl2mp features")
+        c0 = knn("knn_idx_tl2mp", "knn_invalid_tl2mp", "rpe_tl2mp")
+        attr = c(tl_tokens["tl_token_attr"].float()).view(n_sc * n_tl, d)
+        tl = dict(n_sc=n_sc, n_tl=n_tl, tl_token_invalid=c(tl_tokens["tl_token_invalid"]),
+                  tl_token_pose=c(tl_tokens["tl_token_pose"].float()), tl_token_attr=attr,
+                  tl_attr_rows=attr.view(n_sc * n_tl, 1, d).expand(-1, W, -1).reshape(-1, d).contiguous(),
+                  knn_self=knn("knn_idx_tl2tl", "knn_invalid_tl2tl", "rpe_tl2tl"),
+                  cross=[dict(c0, kv0=kv_tl[i], T0=n_mp, div0=1, K0=self.sz["k_tl2mp"]) for i in range(n_tl_l)])
         return dict(mp=mp, tl=tl, kv_mp=kv_mp)
 
     @torch.no_grad()
@@ -183,7 +227,7 @@ class RolloutEngine:
                   knn_state_tl=z(B, A, 3),  # same for the agent -> traffic-light select
                   init_navi_valid=z(B, A, dt=torch.bool))
         if self.record_feedback:
-            st.update(fb_outside=z(B, A, T, dt=u8), fb_reached=z(B, A, T, dt=u8))
+            st.update(fb_outside=z(B, A, T, dt=u8), fb_reached=z(B, A, T, dt=u8), tl_nll=z(Bt, n_tl, T))
         if self.rule_checks:
             st.update(ag_size=z(n_sc, A, 3), passive_counter=z(B, A), seg=z(n_sc, n_mp, n_node, 4),
                       node_invalid=z(n_sc, n_mp, n_node, dt=u8), poly_circle=z(n_sc, n_mp, 3),
@@ -203,7 +247,7 @@ class RolloutEngine:
         st["gt_valid"].copy_(gt_valid)
         st["gt_pose"].copy_(g("sc/ag_pose"))
         st["gt_motion"].copy_(g("sc/ag_motion"))
-        st["tf_mask"].copy_(teacher_forcing_mask(gt_valid, rc["step_spawn_agent"], rc["step_warm_start"]))
+        st["tf_mask"].copy_(teacher_forcing_mask(gt_valid, *self.tf_steps))
         tl_gt = g("sc/tl_state")
         st["gt_tl"].copy_(tl_gt if self.tl_per_scene else rep(tl_gt))
         st["boundary"].copy_(g("map/boundary"))
@@ -282,9 +326,10 @@ class RolloutEngine:
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
-            L.check(lib.tb_tl_step(L.ptr(logits), L.ptr(ops._u8(static["tl"]["tl_token_invalid"])), L.ptr(st["gt_tl"]),
-                                   st["n_gt"], L.ptr(st["d_step"]), st["Bt"], st["n_tl"], m.W, self.T,
-                                   L.ptr(st["hist_tl"]), L.ptr(st["tl_out"]), L.stream()), "tb_tl_step")
+            L.check(lib.tb_tl_step_ex(L.ptr(logits), L.ptr(ops._u8(static["tl"]["tl_token_invalid"])), L.ptr(st["gt_tl"]),
+                                      st["n_gt"], L.ptr(st["d_step"]), st["Bt"], st["n_tl"], m.W, self.T,
+                                      L.ptr(st["hist_tl"]), L.ptr(st["tl_out"]), L.ptr(st.get("tl_nll")), L.stream()),
+                    "tb_tl_step_ex")
             self._tl_branch(st, static, nxt)
         m.ag_forward(st, static["mp"], static["kv_mp"], static["tl"], tl_feat, self.R, out=st["x_cat"][:, :d],
                      aux=aux, knn_stream=self._side2, knn_stream2=self._side3, kv_tl=st["kv_tl"][cur])

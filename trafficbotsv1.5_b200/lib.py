@@ -20,7 +20,8 @@ _lib = None
 EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_linear", "tb_linear_ln", "tb_layernorm",
            "tb_pointnet_pool", "tb_pose_emb", "tb_ag_featurize", "tb_tl_featurize", "tb_dyn_step", "tb_tl_step",
            "tb_step_advance", "tb_gather_rows", "tb_action_mean", "tb_rule_check", "tb_future_filter",
-           "tb_traj_global", "tb_womd_post", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd", "tb_set_fp16_flag", "tb_dyn_step_ex"]
+           "tb_traj_global", "tb_womd_post", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd", "tb_set_fp16_flag", "tb_dyn_step_ex", "tb_tl_step_ex",
+           "tb_dyn_update"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -84,6 +85,8 @@ def load() -> ctypes.CDLL:
         "tb_dyn_step_ex": [P, P, P, P, F, P, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P, I, I, F, F, F, P, I, I,
                            I, I, P, P, P, P, P, P, P, P, P],
         "tb_tl_step": [P, P, P, I, P, I, I, I, I, P, P, P],
+        "tb_tl_step_ex": [P, P, P, I, P, I, I, I, I, P, P, P, P],
+        "tb_dyn_update": [P, P, P, P, P, P, P, F, I, P, P, P, P, P, P],
         "tb_step_advance": [P, P],
         "tb_gather_rows": [P, I, I, P, I, I, I, I, P, I, P],
         "tb_action_mean": [P, P, P, I, P, P],

@@ -345,11 +345,14 @@ class HotPathModel:
         flat_inv = tok_inv.reshape(-1).contiguous()
         tok = self.tf_stack("mp_encoder.tf_mp2mp.layers", self.cfg["mp_encoder"]["n_layer_tf"], "enc_self_attn", tok,
                             lambda i: ((flat_inv, n_sc, n_mp, knn), {}))
-        # x-sorted copy of the (static) token poses for the per-step agent -> map select (tb_knn_select row_state)
-        order = torch.argsort(tok_pose[..., 0], dim=1)
         return dict(mp_token_invalid=tok_inv.contiguous(), mp_token_feature=tok.view(n_sc, n_mp, d),
-                    mp_token_pose=tok_pose, knn_mp2mp=knn,
-                    mp_sorted_pose=torch.gather(tok_pose, 1, order[..., None].expand(-1, -1, 3)).contiguous(),
+                    mp_token_pose=tok_pose, knn_mp2mp=knn, **self.sorted_map(tok_pose, tok_inv))
+
+    @staticmethod
+    def sorted_map(tok_pose: Tensor, tok_inv: Tensor) -> Dict[str, Tensor]:
+        """x-sorted copy of the (static) map token poses for the per-step agent -> map select (tb_knn_select row_state)."""
+        order = torch.argsort(tok_pose[..., 0], dim=1)
+        return dict(mp_sorted_pose=torch.gather(tok_pose, 1, order[..., None].expand(-1, -1, 3)).contiguous(),
                     mp_sorted_invalid=torch.gather(tok_inv, 1, order).contiguous(),
                     mp_sorted_index=order.to(torch.int32).contiguous())
 
