@@ -86,11 +86,12 @@ int tb_knn_select(const float* src_pose, const uint8_t* src_invalid, const float
  *   pe_freq_xy: D/8 floats = PositionalEmbedding(dim=D/4, theta).freqs[::2] (utils/positional_emb.py:11)
  * flags bit 0: evaluate the embedding angles with the SFU's own range reduction (no 2-term Cody-Waite step): abs error
  *   grows with |angle| (<= ~2e-5 at 150 rad, the fp32 rounding of a 150 m coordinate); used with the tf32 projections.
- * flags bit 1: tensor-core mode. kv0 / kv1 are IEEE fp16 tables (leading dims in halves, multiples of 8) as written
- *   by tb_linear's Yh output, and all four contractions (q.k, u.e, sum a e, sum a v) run on mma.sync (f16 operands,
- *   f32 accumulate; q, u and a are split into fp16 head + residual, k, v and e are rounded to fp16: 2^-11 relative
- *   per component, the rounding a tf32 projection applies to its inputs anyway). Needs D == 128, rel != NULL and
- *   K0 + K1 <= 128 (TB_ERR_UNSUPPORTED otherwise). Implies the bit-0 trig.
+ * flags bit 1: 16-bit mode. kv0 / kv1 are IEEE fp16 tables (leading dims in halves, multiples of 8) as written
+ *   by tb_linear's Yh output. For D == 128 and K0 + K1 <= 128 all four contractions (q.k, u.e, sum a e, sum a v) run
+ *   on mma.sync (f16 operands, f32 accumulate; q, u and a are split into fp16 head + residual, k, v and e are rounded
+ *   to fp16: 2^-11 relative per component, the rounding a tf32 projection applies to its inputs anyway; implies the
+ *   bit-0 trig). Other shapes (D == 256: BASELINE config 2; longer lists) gather the fp16 rows with the fp32-arithmetic
+ *   kernel: they need bit 0 and bits 2 and 3 both set or both clear. Needs rel != NULL.
  * flags bit 2: out_ov / out_z are IEEE fp16 rows (ldo in halves, multiple of 8) — what tb_linear precision 2 consumes.
  *   Needs D == 128, rel != NULL and bit 0 (or bit 1).
  * flags bit 3: q / u are IEEE fp16 rows (ldq, ldu in halves, multiples of 8) as written by tb_linear's Yh output;

@@ -211,8 +211,37 @@ def _run_attention(sd, src, tgt, mask, rel, use_emb=False, half_kv=False, half_q
     emb = O.pose_emb_xy_yaw(rel[..., :2], rel[..., 2], d).to(DEV).contiguous() if use_emb else None
     o, nv = ops.knarpe_attn(proj[:, :d], proj[:, d:], kv, S * K, 1, K, idx, mask.to(DEV).contiguous(),
                             None if use_emb else rel.to(DEV).contiguous(), freq, B, S, d, H, emb=emb, **flags)
-    out = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv)
+    if o.dtype == torch.float16:  # fp16 [ov|z] rows feed a kind::f16 out-projection
+        out = ops.linear(o, f["w_out"].half().contiguous(), f["b_out"], mask_pre=nv, precision=2)
+    else:
+        out = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv)
     return out.view(B, S, d), nv.view(B, S)
+
+
+def test_attention_d256_16bit_golden(golden_ops):
+    """BASELINE config 2's model size (d_model 256, 4 heads of 64, K = 36) in the 16-bit mode: fp16 [q|u] rows, fp16
+    K|V table, the SIMT core on fp16 tables (tb_knarpe_attn flags bit 1 with D = 256), fp16 [ov|z] rows, against the
+    real reference's fp32 output. Stated 16-bit tolerance: 4e-3 of the output scale, 1.5e-3 in L2 (10-bit-mantissa
+    operands; bf16 would be 4x coarser), all-masked rows exactly zero. Also through the drop-in module."""
+    from trafficbotsv1_5_b200 import reference_api as R
+    g = golden_ops["attn_d256"]
+    sd = params.rand_like_state_dict(g["sd_shapes"], g["sd_seed"])
+    out, nv = _run_attention(sd, g["src"], g["tgt"], g["mask"], g["rel"], half_kv=True, half_qu=True, fast_trig=True,
+                             out_dtype=torch.float16)
+    scale = float(g["out"].abs().max())
+    print("d256 16-bit: max abs / scale", float((out.cpu() - g["out"]).abs().max()) / scale, "rel_l2", rel_l2(out, g["out"]))
+    close(out, g["out"], 4e-3, 4e-3 * scale, "attn_d256 16-bit")
+    assert rel_l2(out, g["out"]) < 1.5e-3
+    assert bool(nv[0, 0]) and float(out[0, 0].abs().max()) == 0.0
+    att = R.AttentionRPE(256, 4, dropout_p=0.1, bias=True, d_rpe=256, precision=1).eval()
+    att.load_state_dict(sd)
+    att = att.to(DEV)
+    o2, _ = att(g["src"].to(DEV), g["tgt"].to(DEV), tgt_padding_mask=g["mask"].to(DEV), rpe=g["rel"].to(DEV))
+    close(o2, g["out"], 4e-3, 4e-3 * scale, "drop-in AttentionRPE d256 16-bit")
+    att.precision = 0
+    att._tb_ver = None
+    o3, _ = att(g["src"].to(DEV), g["tgt"].to(DEV), tgt_padding_mask=g["mask"].to(DEV), rpe=g["rel"].to(DEV))
+    close(o3, g["out"], 1e-4, 1e-4 * scale, "drop-in AttentionRPE d256 fp32")
 
 
 @pytest.mark.parametrize("name", ["attn_d128", "attn_d256"])

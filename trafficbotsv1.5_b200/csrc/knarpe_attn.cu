@@ -21,6 +21,8 @@
 //     interleave (the v2 kernel was latency-bound: 33% stall_wait, 26% short-scoreboard at 14 warps/SM).
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -43,12 +45,14 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// OUT_H: [ov|z] written as fp16; IN_H: q / u rows are fp16 (tensor-core mode intermediates)
-template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false, bool IN_H = false>
+// OUT_H: [ov|z] written as fp16; IN_H: q / u rows are fp16 (tensor-core mode intermediates); KV_H: the K|V tables are
+// fp16 rows (ldkv in halves) - the 16-bit variant for shapes the mma.sync kernel does not cover (d_model 256,
+// BASELINE config 2; lists longer than 128): half the gather bytes, fp32 arithmetic.
+template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false, bool IN_H = false, bool KV_H = false>
 __global__ void __launch_bounds__(kWarps * 32, TB_ATTN_MINB)
 knarpe_attn_kernel(const void* __restrict__ q_, int ldq, const void* __restrict__ u_, int ldu,
-                   const float* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
-                   const float* __restrict__ kv1, int ldkv1, int T1, int div1, int K1,
+                   const void* __restrict__ kv0_, int ldkv0, int T0, int div0, int K0,
+                   const void* __restrict__ kv1_, int ldkv1, int T1, int div1, int K1,
                    const int32_t* __restrict__ idx, const uint8_t* __restrict__ invalid,
                    const float* __restrict__ rel, const float* __restrict__ emb,
                    const float* __restrict__ pe_freq_xy, int n_tok, int S,
@@ -58,7 +62,10 @@ knarpe_attn_kernel(const void* __restrict__ q_, int ldq, const void* __restrict_
   constexpr int NC = D / 32;            // embedding components per lane (l + 32k)
   constexpr int G = (D == 128) ? TB_ATTN_G : 2; // neighbours per group
   constexpr int NF = D / 8;             // number of xy frequencies
-  __shared__ const float* s_ptr[kWarps][32];  // compacted valid neighbours of the current chunk: K/V row pointer,
+  using KvT = typename std::conditional<KV_H, __half, float>::type;
+  const KvT* kv0 = static_cast<const KvT*>(kv0_);
+  const KvT* kv1 = static_cast<const KvT*>(kv1_);
+  __shared__ const KvT* s_ptr[kWarps][32];    // compacted valid neighbours of the current chunk: K/V row pointer,
   __shared__ float s_rel[kWarps][32][3];      // relative pose,
   __shared__ int s_j[kWarps][32];             // and original neighbour slot (materialised-embedding mode)
 
@@ -123,14 +130,14 @@ knarpe_attn_kernel(const void* __restrict__ q_, int ldq, const void* __restrict_
   float mx = -INFINITY, sm = 0.f;
 
   const size_t prow = (size_t)tok * Ktot;
-  const float* kb0 = kv0 + (size_t)(b / div0) * T0 * ldkv0;
-  const float* kb1 = (K1 > 0) ? kv1 + (size_t)(b / div1) * T1 * ldkv1 : kb0;
+  const KvT* kb0 = kv0 + (size_t)(b / div0) * T0 * ldkv0;
+  const KvT* kb1 = (K1 > 0) ? kv1 + (size_t)(b / div1) * T1 * ldkv1 : kb0;
 
   for (int c0 = 0; c0 < Ktot; c0 += 32) {
     // ---- stage the chunk: compact the unmasked neighbours (ballot), pad the last group with weight-0 dummies
     const int j = c0 + lane;
     bool valid = false;
-    const float* rptr = kb0;
+    const KvT* rptr = kb0;
     float rx = 0.f, ry = 0.f, rw = 0.f;
     if (j < Ktot) {
       const size_t p = prow + j;
@@ -156,7 +163,7 @@ knarpe_attn_kernel(const void* __restrict__ q_, int ldq, const void* __restrict_
     for (int g0 = 0; g0 < nvalid; g0 += G) {  // 32 % G == 0: slots g0..g0+G-1 are always staged
       // ---- L1 prefetch of the NEXT group's K|V rows (G rows x 2*D*4 B = 32 lines for D=128: one line per lane), so
       // that its gathers hit L1 instead of stalling on L2 (ncu v4: 21 % long-scoreboard stalls)
-      if (D == 128 && g0 + G < nvalid) {
+      if (D == 128 && !KV_H && g0 + G < nvalid) {
         const char* pf = reinterpret_cast<const char*>(s_ptr[warp][g0 + G + (lane >> 3)]) + (lane & 7) * 128;
         asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
       }
@@ -164,13 +171,28 @@ knarpe_attn_kernel(const void* __restrict__ q_, int ldq, const void* __restrict_
       float kr[G][NV], vr[G][NV];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const float* rp = s_ptr[warp][g0 + g] + lane * NV;
+        if (KV_H) {  // NV halves of K and of V per lane: one 8-byte (D = 128) or 16-byte (D = 256) load each
+          const __half* rp = reinterpret_cast<const __half*>(s_ptr[warp][g0 + g]) + lane * NV;
 #pragma unroll
-        for (int i = 0; i < NV; i += 4) {
-          float4 t = ldg4(rp + i);
-          kr[g][i] = t.x; kr[g][i + 1] = t.y; kr[g][i + 2] = t.z; kr[g][i + 3] = t.w;
-          float4 w = ldg4(rp + D + i);
-          vr[g][i] = w.x; vr[g][i + 1] = w.y; vr[g][i + 2] = w.z; vr[g][i + 3] = w.w;
+          for (int i = 0; i < NV; i += 4) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2*>(rp + i));
+            const uint2 c = __ldg(reinterpret_cast<const uint2*>(rp + D + i));
+            const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+            const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+            const float2 c0_ = __half22float2(*reinterpret_cast<const __half2*>(&c.x));
+            const float2 c1_ = __half22float2(*reinterpret_cast<const __half2*>(&c.y));
+            kr[g][i] = a0.x; kr[g][i + 1] = a0.y; kr[g][i + 2] = a1.x; kr[g][i + 3] = a1.y;
+            vr[g][i] = c0_.x; vr[g][i + 1] = c0_.y; vr[g][i + 2] = c1_.x; vr[g][i + 3] = c1_.y;
+          }
+        } else {
+          const float* rp = reinterpret_cast<const float*>(s_ptr[warp][g0 + g]) + lane * NV;
+#pragma unroll
+          for (int i = 0; i < NV; i += 4) {
+            float4 t = ldg4(rp + i);
+            kr[g][i] = t.x; kr[g][i + 1] = t.y; kr[g][i + 2] = t.z; kr[g][i + 3] = t.w;
+            float4 w = ldg4(rp + D + i);
+            vr[g][i] = w.x; vr[g][i + 1] = w.y; vr[g][i + 2] = w.z; vr[g][i + 3] = w.w;
+          }
         }
       }
 
@@ -307,14 +329,14 @@ knarpe_attn_kernel(const void* __restrict__ q_, int ldq, const void* __restrict_
   if (lane == 0 && out_none_valid) out_none_valid[tok] = sm > 0.f ? 0 : 1;
 }
 
-template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false, bool IN_H = false>
-int launch(const void* q, int ldq, const void* u, int ldu, const float* kv0, int ldkv0, int T0, int div0, int K0,
-           const float* kv1, int ldkv1, int T1, int div1, int K1, const int32_t* idx, const uint8_t* invalid,
+template <int D, bool FROM_EMB, bool FAST_TRIG, bool OUT_H = false, bool IN_H = false, bool KV_H = false>
+int launch(const void* q, int ldq, const void* u, int ldu, const void* kv0, int ldkv0, int T0, int div0, int K0,
+           const void* kv1, int ldkv1, int T1, int div1, int K1, const int32_t* idx, const uint8_t* invalid,
            const float* rel, const float* emb, const float* pe_freq_xy, int B, int S, void* out_ov, void* out_z,
            int ldo, uint8_t* out_none_valid, cudaStream_t st) {
   const int n_tok = B * S;
   const int grid = (n_tok + kWarps - 1) / kWarps;
-  knarpe_attn_kernel<D, FROM_EMB, FAST_TRIG, OUT_H, IN_H><<<grid, kWarps * 32, 0, st>>>(q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1,
+  knarpe_attn_kernel<D, FROM_EMB, FAST_TRIG, OUT_H, IN_H, KV_H><<<grid, kWarps * 32, 0, st>>>(q, ldq, u, ldu, kv0, ldkv0, T0, div0, K0, kv1, ldkv1,
                                                               T1, div1, K1, idx, invalid, rel, emb, pe_freq_xy, n_tok,
                                                               S, out_ov, out_z, ldo, out_none_valid);
   TB_CHECK_LAUNCH();
@@ -336,8 +358,8 @@ extern "C" int tb_knarpe_attn(const void* q, int ldq, const void* u, int ldu, co
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* emb,
                               const float* pe_freq_xy, int B, int S, int D, int Hh, void* out_ov, void* out_z,
                               int ldo, uint8_t* out_none_valid, int flags, void* stream) {
-  const float* kv0 = static_cast<const float*>(kv0_);
-  const float* kv1 = static_cast<const float*>(kv1_);
+  const void* kv0 = kv0_;
+  const void* kv1 = kv1_;
   if (!q || !u || !kv0 || !idx || !invalid || !out_ov || !out_z || !pe_freq_xy) return TB_ERR_NULL;
   if ((rel == nullptr) == (emb == nullptr)) return TB_ERR_NULL;  // exactly one
   if (B <= 0 || S <= 0 || K0 <= 0 || K1 < 0 || T0 <= 0 || div0 <= 0 || (K1 > 0 && (!kv1 || T1 <= 0 || div1 <= 0)))
@@ -355,9 +377,18 @@ extern "C" int tb_knarpe_attn(const void* q, int ldq, const void* u, int ldu, co
   const int out_h = (flags & 4) != 0;  // bit 2: out_ov / out_z are fp16 rows (ldo in halves)
   const int in_h = (flags & 8) != 0;   // bit 3: q / u are fp16 rows (ldq, ldu in halves)
   if ((out_h && (ldo & 7)) || (in_h && ((ldq | ldu) & 7))) return TB_ERR_MISALIGNED;
-  if (flags & 2) {  // bit 1: fp16 K|V tables, all contractions on mma.sync (knarpe_attn_mma.cu)
-    if (!rel || !tb_knarpe_attn_mma_supported(D, Hh, K0 + K1)) return TB_ERR_UNSUPPORTED;
+  if (flags & 2) {  // bit 1: fp16 K|V tables: all contractions on mma.sync (knarpe_attn_mma.cu) where that kernel applies
+    if (!rel) return TB_ERR_UNSUPPORTED;
     if ((ldkv0 | (K1 > 0 ? ldkv1 : 0)) & 7) return TB_ERR_MISALIGNED;
+    if (!tb_knarpe_attn_mma_supported(D, Hh, K0 + K1)) {
+      // d_model 256 (BASELINE config 2) or lists longer than 128: the SIMT kernel on fp16 tables (fp32 arithmetic)
+      if ((flags & 16) || !fast || out_h != in_h) return TB_ERR_UNSUPPORTED;
+      if (D == 128)
+        return out_h ? launch<128, false, true, true, true, true>(TB_ATT_ARGS)
+                     : launch<128, false, true, false, false, true>(TB_ATT_ARGS);
+      return out_h ? launch<256, false, true, true, true, true>(TB_ATT_ARGS)
+                   : launch<256, false, true, false, false, true>(TB_ATT_ARGS);
+    }
     const int il = (flags & 16) != 0;  // bit 4: head-interleaved q / K / V channels, rows read 32 bytes per lane
     if (il) {
       if (!in_h) return TB_ERR_UNSUPPORTED;

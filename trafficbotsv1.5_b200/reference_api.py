@@ -146,8 +146,9 @@ class AttentionRPE(nn.Module, _FusedMixin):
     out_proj_weight, out_proj_bias, linear_rpe.*)."""
 
     def __init__(self, d_model: int, n_head: int, dropout_p: float = 0.1, bias: bool = True, d_rpe: int = -1,
-                 apply_q_rpe: bool = False) -> None:
+                 apply_q_rpe: bool = False, precision: int = 0) -> None:
         super().__init__()
+        self.precision = precision  # 0: fp32 everywhere (1e-4 parity); 1: 16-bit mode (extra argument of the drop-in)
         self.d_model, self.n_head, self.d_head = d_model, n_head, d_model // n_head
         self.apply_q_rpe, self.d_rpe = apply_q_rpe, d_rpe
         assert self.d_head * n_head == d_model, "d_model must be divisible by n_head"  # attention_rpe.py:31
@@ -212,12 +213,25 @@ class AttentionRPE(nn.Module, _FusedMixin):
         B, S, K, d = tgt.shape
         m = self._runner(d)
         f = m.fa[""]
-        proj = ops.linear(src.reshape(B * S, d).float().contiguous(), f["w_in_q"], f["b_in_q"], precision=m.precision)
-        kv = ops.linear(tgt.reshape(B * S * K, d).float().contiguous(), f["w_kv"], f["b_kv"], precision=m.precision)
         idx = torch.arange(S * K, dtype=torch.int32, device=src.device).view(1, S, K).expand(B, -1, -1)
         mask = tgt_padding_mask if tgt_padding_mask is not None else torch.zeros(B, S, K, dtype=torch.bool,
                                                                                   device=src.device)
         knn = _knn_dict(idx, mask, rpe, self.d_rpe)
+        x, t = src.reshape(B * S, d).float().contiguous(), tgt.reshape(B * S * K, d).float().contiguous()
+        if m.precision == 1 and "rel" in knn:
+            # 16-bit mode (`precision = 1` on the module): tcgen05 projections that write fp16 [q|u] rows and the fp16
+            # K|V table, the 16-bit attention core (mma.sync kernel for d_model 128 and K <= 128, the SIMT kernel on
+            # fp16 tables otherwise: d_model 256 = BASELINE config 2), fp16 [ov|z] rows into a kind::f16 out-projection.
+            qu = torch.empty(B * S, d + H * d, dtype=torch.float16, device=src.device)
+            ops.linear(x, f["w_in_q"], f["b_in_q"], precision=1, out_h=qu, col_h=0)
+            kv = torch.empty(B * S * K, 2 * d, dtype=torch.float16, device=src.device)
+            ops.linear(t, f["w_kv"], f["b_kv"], precision=1, out_h=kv, col_h=0)
+            o, nv = ops.knarpe_attn(qu[:, :d], qu[:, d:], kv, S * K, 1, K, knn["idx"], knn["inv"], knn["rel"], m.freq_rpe,
+                                    B, S, d, H, fast_trig=True, out_dtype=torch.float16)
+            out = ops.linear(o, m._half("w_out", f["w_out"]), f["b_out"], mask_pre=nv, precision=2)
+            return out.view(B, S, d)
+        proj = ops.linear(x, f["w_in_q"], f["b_in_q"], precision=m.precision)
+        kv = ops.linear(t, f["w_kv"], f["b_kv"], precision=m.precision)
         o, nv = ops.knarpe_attn(proj[:, :d], proj[:, d:], kv, S * K, 1, K, knn["idx"], knn["inv"], knn.get("rel"),
                                 m.freq_rpe, B, S, d, H, emb=knn.get("emb"))
         out = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, precision=m.precision)
