@@ -44,6 +44,9 @@ def parse():
                          "LayerNorm rows (fp32 accumulators, residual stream and rollout state); 0: fp32 everywhere")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp32 / rule-check extra measurements")
+    ap.add_argument("--scenes-total", type=int, default=0,
+                    help="BASELINE config 5: sweep this many scenes (512) sharded over the ranks in batches of --scenes, "
+                         "NCCL gather of every batch's trajectories overlapped with the next batch (strong scaling)")
     ap.add_argument("--rule-checks", action="store_true",
                     help="also run the logging-only TrafficRuleChecker checks (collision, road edge, ...) every step")
     return ap.parse_args()
@@ -356,6 +359,132 @@ def attention_roofline(eng, peaks):
                 valid_pairs=n_valid, pairs=M * K, peak_source="MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback")
 
 
+def run_sweep(args):
+    """BASELINE config 5 as written: `--scenes-total` scenes x 32 rollouts x 80 steps, scenes sharded over the ranks in
+    contiguous blocks (parallel.shard_range), every rank walks its shard in batches of `--scenes`; the trajectories of
+    batch i are all-gathered over NCCL on a side stream while batch i+1 computes (parallel.OverlappedGather; reference:
+    torchmetrics cat states, waymo_motion.py:894-909, submission.py:45-46,169-170). A bench step = one whole sweep.
+      value: batches resident in HBM; scene encoding of every batch, its 90 policy iterations and the gather are timed
+      e2e  : batches start in pinned host memory (H2D per batch) and every rank's trajectories go back to the host."""
+    import torch.distributed as dist
+    from trafficbotsv1_5_b200 import ops, parallel
+    from trafficbotsv1_5_b200.engine import RolloutEngine
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback for the product path"
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    total, per_batch, R = args.scenes_total, args.scenes, args.rollouts
+    lo, hi = parallel.shard_range(total, world, rank)
+    assert total % (world * per_batch) == 0, "scenes-total must be a multiple of gpus x scenes-per-batch"
+    n_batches = (hi - lo) // per_batch
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, 0)
+    eng = RolloutEngine(P, cfg, dev, precision=args.precision, n_rollout=R, step_end=N_ITER)
+    host = [{k: v.pin_memory() for k, v in synth.make_scene_batch(n_sc=per_batch, seed=1000 + lo + b * per_batch,
+                                                                    n_rollout=R).items()} for b in range(n_batches)]
+    resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
+    A = host[0]["sc/ag_valid"].shape[1]
+    og = parallel.OverlappedGather(n_batches, (per_batch * R, A, N_COUNTED, 3), torch.float32, dev)
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values()) * n_batches
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def sweep(batches):
+        for b in batches:
+            res = eng.rollout(b)
+            og.submit(res["pred_pose"][:, :, N_ITER - N_COUNTED:])
+        return og.wait()
+
+    # ---- verification sweep (untimed): the gathered store must hold every scene's bytes where the shard map says
+    sums = []
+    for b in resident:
+        res = eng.rollout(b)
+        out = res["pred_pose"][:, :, N_ITER - N_COUNTED:]
+        sums.append(parallel.scene_checksums(out.reshape(per_batch, -1)))
+        og.submit(out)
+    store = og.wait()
+    mine = torch.stack(sums)                                           # [n_batches, per_batch]
+    all_sums = [torch.empty_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(all_sums, mine)
+    else:
+        all_sums = [mine]
+    got = torch.stack([parallel.scene_checksums(store[:, r].reshape(n_batches * per_batch, -1)).view(n_batches, per_batch)
+                       for r in range(world)])
+    gather_ok = bool(torch.equal(got, torch.stack(all_sums)))
+    distinct = int(torch.stack(all_sums).unique().numel())
+    assert gather_ok, "gathered trajectories do not match the per-scene checksums of their source ranks"
+
+    for _ in range(max(args.warmup - 1, 0)):
+        sweep(resident)
+    l0 = ops.LAUNCHES
+    with ClockSampler(local) as cs:
+        t_val = timed(lambda: sweep(resident), args.steps)
+    launches = (ops.LAUNCHES - l0) + args.steps * n_batches * N_ITER * eng.launches_per_step
+    clocks = cs.summary()
+    units = total * R * N_COUNTED
+    value = units * args.steps / t_val
+
+    host_out = [torch.empty(per_batch * R, A, N_COUNTED, 3).pin_memory() for _ in range(2)]
+    d2h_stream = torch.cuda.Stream(device=dev)
+
+    def sweep_e2e():
+        for i, b in enumerate(host):
+            res = eng.rollout(b)  # pinned host batch: H2D inside
+            og.submit(res["pred_pose"][:, :, N_ITER - N_COUNTED:])
+            d2h_stream.wait_stream(og.side)
+            with torch.cuda.stream(d2h_stream):  # this rank's trajectories back to the host, behind the gather
+                host_out[i % 2].copy_(og.stage[i % 2], non_blocking=True)
+            og.free[i % 2] = torch.cuda.Event()
+            og.free[i % 2].record(d2h_stream)
+        og.wait()
+        torch.cuda.current_stream().wait_stream(d2h_stream)
+        torch.cuda.current_stream().synchronize()
+
+    sweep_e2e()
+    t_e2e = timed(sweep_e2e, max(1, args.steps))
+    e2e = dict(value=units * max(1, args.steps) / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d,
+               d2h_bytes_per_step=n_batches * host_out[0].numel() * 4)
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=t_val / args.steps * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="f32" if args.precision == 0 else "tf32+fp16", data="synthetic",
+                    config=dict(workload=f"config 5: scenario-sharded rollout sweep, {total} scenes x {R} rollouts x 80 steps "
+                                         f"(90 policy iterations), {per_batch} scenes per batch, {n_batches} batches per GPU, NCCL "
+                                         f"all-gather of every batch's 80-step trajectories overlapped with the next batch",
+                                scenes_total=total, scenes_per_batch=per_batch, batches_per_gpu=n_batches, rollouts=R,
+                                policy_iterations=N_ITER, counted_steps=N_COUNTED,
+                                gathered_bytes_per_gpu=int(store.numel() * 4), gather_verified=gather_ok,
+                                distinct_scene_checksums=distinct,
+                                l2="per-iteration working set (>1 GB of activations) exceeds the 126 MB L2; no flush",
+                                launches_per_policy_iteration=eng.launches_per_step),
+                    clocks=clocks, e2e=e2e, gpu_launches=launches)
+        print(json.dumps(line), file=_OUT, flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch.distributed as dist
     from trafficbotsv1_5_b200 import ops
@@ -397,15 +526,27 @@ def run_ours(args):
 
     # ---- value: rollout loop only, inputs + scene tokens resident
     eng.prepare(batch)
-    gathered = None
-    if world > 1:
-        gathered = [torch.empty(n_sc * args.rollouts, batch["sc/ag_valid"].shape[1], N_COUNTED, 3, device=dev)
-                    for _ in range(world)]
+    from trafficbotsv1_5_b200 import parallel
+    A_ = batch["sc/ag_valid"].shape[1]
+    og = parallel.OverlappedGather(1, (n_sc * args.rollouts, A_, N_COUNTED, 3), torch.float32, dev) if world > 1 else None
 
     def loop_step():
         res = eng.run()
         if world > 1:  # the only cross-GPU step: gather of the 80-step trajectories (waymo_motion.py:894-909)
-            dist.all_gather(gathered, res["pred_pose"][:, :, N_ITER - N_COUNTED:].contiguous())
+            og.submit(res["pred_pose"][:, :, N_ITER - N_COUNTED:])
+            og.wait()
+
+    gather_ok = None
+    if world > 1:  # once, untimed: the gathered bytes of every rank match the checksums that rank computed locally
+        res = eng.run()
+        mine = parallel.scene_checksums(res["pred_pose"][:, :, N_ITER - N_COUNTED:].reshape(n_sc, -1))
+        og.submit(res["pred_pose"][:, :, N_ITER - N_COUNTED:])
+        store = og.wait()
+        all_sums = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(all_sums, mine)
+        got = torch.stack([parallel.scene_checksums(store[0, r].reshape(n_sc, -1)) for r in range(world)])
+        gather_ok = bool(torch.equal(got, torch.stack(all_sums))) and int(got.unique().numel()) == world * n_sc
+        assert gather_ok, "gathered trajectories do not match their source ranks' checksums"
 
     for _ in range(args.warmup):
         loop_step()
@@ -448,7 +589,7 @@ def run_ours(args):
                                          f"iterations (80 counted)", scenes_per_gpu=n_sc, rollouts=args.rollouts,
                                 policy_iterations=N_ITER, counted_steps=N_COUNTED, rule_checks=bool(args.rule_checks),
                                 l2="per-iteration working set (>1 GB of activations) exceeds the 126 MB L2; no flush",
-                                launches_per_policy_iteration=eng.launches_per_step),
+                                launches_per_policy_iteration=eng.launches_per_step, gather_verified=gather_ok),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof, roofline_select=roof_sel)
     if rank == 0 and world == 1 and not args.rule_checks and not args.no_extras:
         # extra lines (not the headline): fp32-parity projections, and the loop with ALL TrafficRuleChecker checks on
@@ -514,5 +655,7 @@ if __name__ == "__main__":
     _reserve_stdout()
     if a.impl == "reference":
         run_reference(a)
+    elif a.scenes_total > 0:
+        run_sweep(a)
     else:
         run_ours(a)

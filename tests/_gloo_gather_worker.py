@@ -25,6 +25,28 @@ def main():
         assert torch.equal(full, fake_rollout(ids)), (rank, n_scenes)
         batch = {"a": torch.arange(n_scenes * 2).view(n_scenes, 2)}
         assert parallel.shard_batch(batch, world, rank)["a"].shape[0] == hi - lo
+    # batched sweep: every rank walks its shard in batches, each batch is gathered (OverlappedGather; synchronous on
+    # CPU) and rank 0 verifies the gathered bytes against per-scene checksums gathered separately
+    n_scenes, per_batch = 8, 2
+    lo, hi = parallel.shard_range(n_scenes, world, rank)
+    n_batches = (hi - lo) // per_batch
+    og = parallel.OverlappedGather(n_batches, (per_batch, 3, 4, 5, 3), torch.float32, "cpu")
+    sums = []
+    for b in range(n_batches):
+        ids = torch.arange(lo + b * per_batch, lo + (b + 1) * per_batch)
+        local = fake_rollout(ids)
+        sums.append(parallel.scene_checksums(local))
+        og.submit(local)
+    store = og.wait()
+    all_sums = [torch.empty(n_batches, per_batch, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_sums, torch.stack(sums))
+    for r in range(world):
+        rlo, _ = parallel.shard_range(n_scenes, world, r)
+        for b in range(n_batches):
+            ids = torch.arange(rlo + b * per_batch, rlo + (b + 1) * per_batch)
+            assert torch.equal(store[b, r], fake_rollout(ids)), (rank, r, b)
+            assert torch.equal(parallel.scene_checksums(store[b, r]), all_sums[r][b])
+    assert not torch.equal(parallel.scene_checksums(store[0, 0]), parallel.scene_checksums(store[0, 0].flip(1)))
     dist.barrier()
     if rank == 0:
         print("GLOO_GATHER_OK")
