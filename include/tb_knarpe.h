@@ -252,6 +252,45 @@ int tb_dyn_step_ex(const float* act_branch, const uint8_t* ag_type, const float*
                    int A, int W, int T, uint8_t* hist_valid, float* hist_pose, float* hist_motion, uint8_t* pred_valid,
                    float* pred_pose, float* pred_motion, uint8_t* o_outside, uint8_t* o_reached, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Fused MLP chain (csrc/mlp_chain.cu): a sequence of dense layers over 128-row tiles with every intermediate kept on
+ * the SM (tcgen05 MMAs, fp16 activation tiles in shared memory, fp32 accumulators in TMEM). One launch replaces the
+ * head chain of a policy step — NaviEncoder.mlp_pe, AddNaviLatent x 2, ActionHead (models/traffic_bots.py:191-217,
+ * modules/add_navi_latent.py:46-64, modules/action_head.py:78-82) — or the FFN of a transformer layer with its residual
+ * and LayerNorm (modules/transformer_rpe.py:236-245).
+ * A program is a list of units executed in order for every tile; `buffers` are on-chip fp16 tiles [128 rows x 128 cols]:
+ *   kind 1 LOAD: rows of an external tensor (binding `src`, leading dim lds, first column src_col; fp32 or, with src_f16,
+ *     IEEE fp16) -> buffer out_buf.
+ *   kind 0 GEMM: acc[128 x 128] = A W[n0 : n0+128, :]^T with A = the 128-column buffers a_buf[0 .. K/128) side by side
+ *     (K a multiple of 64, <= 512) and W [N, K] fp16 row-major (rows past N read as zero);
+ *     v = acc + bias[n0 + c]; relu; if mask_pre[row]: 0; += res[row, res_col + c]; if mask_post[row]: 0 — the epilogue of
+ *     tb_linear. v goes to buffer out_buf as fp16 and/or to fp32 rows out_g[row, g_col + c] (c < n_valid) and/or fp16 rows
+ *     out_h[row, h_col + c]; with ln_out, fp16(LayerNorm(v) * ln_gamma + ln_beta) (eps 1e-5) goes to ln_out[row, c].
+ * bias / ln_gamma / ln_beta / W are device pointers baked into the program (model constants; bias must hold n0 + 128
+ * floats); mask_pre, mask_post, res, out_g, out_h, ln_out, src are indices into the `bindings` array passed at run time.
+ * ------------------------------------------------------------------------------------------------- */
+#define TB_CHAIN_MAX_UNITS 32
+#define TB_CHAIN_MAX_KB 8
+#define TB_CHAIN_MAX_BIND 16
+typedef struct tb_chain_unit {
+  int kind;
+  const void* W; int K, N, n0;
+  int a_buf[4];
+  const float* bias; int relu, n_valid;
+  int mask_pre, mask_post, res, ldr, res_col;
+  int out_buf;
+  int out_g, ldg, g_col;
+  int out_h, ldh, h_col;
+  int ln_out, ld_ln; const float* ln_gamma; const float* ln_beta;
+  int src, lds, src_col, src_f16;
+} tb_chain_unit;
+int tb_chain_program_bytes(void);
+/* host_blob: tb_chain_program_bytes() bytes of host memory; copy it to 128-byte aligned device memory afterwards.
+ * n_buf: on-chip activation buffers (2..6; the rest of the 227 KB of shared memory is the weight ring). */
+int tb_chain_encode(const tb_chain_unit* units, int n_units, int n_buf, void* host_blob);
+/* bindings: HOST array of n_bind (<= 15) device pointers. Rows >= M of the last tile are neither read nor written. */
+int tb_chain_run(const void* d_program, const void* host_blob, void* const* bindings, int n_bind, int M, void* stream);
+
 /* Traffic-light feedback — utils/dynamics.py:144-163 (override_tl), traffic_light.py:286 (clamp +-3).
  *   logits [B*TL,5] (pre-clamp, invalid rows are zeroed here), tl_invalid [B,TL], gt_tl [B,TL,n_gt,5] u8.
  *   writes the new one-hot state into ring slot s%W of hist_tl [B,TL,W,5] and tl_out [B,TL,T,5] at s-1. */

@@ -768,3 +768,81 @@ def test_linear_fused_layernorm_argument_checks():
     w = torch.zeros(128, 128, dtype=torch.float16, device=DEV)
     with pytest.raises(RuntimeError):  # residual rows only 4-byte aligned
         ops.linear_ln(x, w, None, g[:128], g[:128], res=torch.zeros(256, 132, device=DEV)[:, 1:129])
+
+
+# ------------------------------------------------------------------------------------------------ fused MLP chain
+def _h(t):
+    return t.half().float()
+
+
+@pytest.mark.parametrize("M", [1, 1000, 148 * 3 * 128 + 77])
+def test_mlp_chain_program_vs_torch(M):
+    """tb_chain_*: a head-chain-shaped program (fp32 LOAD, K = 128 / 256 / 384 GEMM units, ReLU, row masks, fp32 residual,
+    in-place units, a 6-wide output) and an FFN-shaped one (fp16 LOAD, 4 hidden units, K = 512, residual, LayerNorm) against
+    plain torch on fp16-rounded operands. Error budget: fp16 rounding of every intermediate activation (2^-11 relative)."""
+    g = torch.Generator().manual_seed(M)
+    d = 128
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc)  # noqa: E731
+    x = rnd(M, 2 * d).to(DEV)                       # x in columns 0..127 of a 256-wide buffer
+    ext = rnd(M, d).to(DEV)
+    m_pre = (torch.rand(M, generator=g) < 0.3).to(DEV)
+    m_post = (torch.rand(M, generator=g) < 0.3).to(DEV)
+    W1, b1 = rnd(d, d, sc=0.1), rnd(d, sc=0.1)
+    W2, b2 = rnd(d, 2 * d, sc=0.07), rnd(d, sc=0.1)
+    W3, b3 = rnd(3 * d, d, sc=0.1), rnd(3 * d, sc=0.1)
+    W3b = [rnd(d, d, sc=0.1) for _ in range(3)]
+    W4, b4 = rnd(6, 3 * d, sc=0.1), rnd(6, sc=0.1)
+    hw = lambda w: w.half().contiguous().to(DEV)  # noqa: E731
+    out2 = torch.zeros(M, 2 * d, device=DEV)
+    out6 = torch.full((M, 6), 7.0, device=DEV)
+    p = ops.ChainProgram(DEV, n_buf=4)
+    # bindings: 0 x, 1 ext, 2 m_pre, 3 m_post, 4 out2, 5 out6
+    p.load(1, d, 1)
+    p.gemm(hw(W1), [1], b1, relu=True, out_buf=2, mask_post=3)
+    p.load(0, 2 * d, 0)
+    p.gemm(hw(W2), [0, 2], b2, relu=True, mask_pre=2, res=0, ldr=2 * d, out_buf=0, out_g=4, ldg=2 * d, g_col=d)
+    for t in range(3):
+        p.gemm(hw(W3), [0], b3, n0=t * d, relu=True, out_buf=1 + t)
+    for t in range(3):
+        p.gemm(hw(W3b[t]), [1 + t], None, relu=True, out_buf=1 + t)  # in place
+    p.gemm(hw(W4), [1, 2, 3], b4, out_g=5, ldg=6, n_valid=6)
+    p.finish()
+    p.run([x, ext, ops._u8(m_pre), ops._u8(m_post), out2, out6], M)
+    torch.cuda.synchronize()
+    xc, ec = x.cpu(), ext.cpu()
+    a1 = torch.relu(_h(ec) @ _h(W1).T + b1).masked_fill(m_post.cpu()[:, None], 0.0)
+    cat = torch.cat([_h(xc[:, :d]), _h(a1)], 1)
+    x2 = torch.relu(cat @ _h(W2).T + b2).masked_fill(m_pre.cpu()[:, None], 0.0) + xc[:, :d]
+    h0 = torch.relu(_h(x2) @ _h(W3).T + b3)
+    h1 = torch.cat([torch.relu(_h(h0[:, t * d:(t + 1) * d]) @ _h(W3b[t]).T) for t in range(3)], 1)
+    o6 = _h(h1) @ _h(W4).T + b4
+    assert float(out2[:, :d].abs().max()) == 0.0                      # untouched columns
+    close(out2[:, d:], x2, 2e-3, 2e-3 * float(x2.abs().max()), "chain x2")
+    close(out6, o6, 3e-3, 3e-3 * float(o6.abs().max()), "chain 6-wide output")
+    # ---- FFN-shaped program: LN rows (fp16) -> linear1 + ReLU (512) -> linear2 + residual + mask -> fp32 out + LN rows
+    ln_in = rnd(M, d).half().to(DEV)
+    src = rnd(M, d).to(DEV)
+    Wa, ba, Wb, bb = rnd(4 * d, d, sc=0.1), rnd(4 * d, sc=0.1), rnd(d, 4 * d, sc=0.05), rnd(d, sc=0.1)
+    gam, bet = rnd(d).abs() + 0.5, rnd(d, sc=0.1)
+    y = torch.zeros(M, d, device=DEV)
+    ln_out = torch.zeros(M, d, dtype=torch.float16, device=DEV)
+    q = ops.ChainProgram(DEV, n_buf=5)
+    q.load(0, d, 0, f16=True)
+    for t in range(4):
+        q.gemm(hw(Wa), [0], ba, n0=t * d, relu=True, out_buf=1 + t)
+    q.gemm(hw(Wb), [1, 2, 3, 4], bb, res=1, ldr=d, mask_post=2, out_g=3, ldg=d, ln_out=4, ld_ln=d, ln_gamma=gam.to(DEV),
+           ln_beta=bet.to(DEV))
+    q.finish()
+    q.run([ln_in, src, ops._u8(m_post), y, ln_out], M)
+    torch.cuda.synchronize()
+    hid = torch.relu(ln_in.cpu().float() @ _h(Wa).T + ba)
+    yr = (_h(hid) @ _h(Wb).T + bb + src.cpu()).masked_fill(m_post.cpu()[:, None], 0.0)
+    close(y, yr, 2e-3, 2e-3 * float(yr.abs().max()), "chain FFN output")
+    lnr = torch.nn.functional.layer_norm(yr, (d,), gam, bet, 1e-5)
+    live = ~m_post.cpu()
+    close(ln_out.float()[live.to(DEV)], lnr[live], 5e-3, 5e-3 * float(lnr.abs().max()), "chain FFN LayerNorm rows")
+    # argument checks
+    bad = ops.ChainProgram(DEV, n_buf=4)
+    bad.gemm(hw(W1), [1], b1, out_buf=2)  # reads a buffer nobody wrote
+    with pytest.raises(RuntimeError):
+        bad.finish()

@@ -13,7 +13,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("TB_LIB", os.path.join(_PKG, "libtbknarpe.so"))
-_SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "knarpe_attn_mma.cu", "knarpe_attn_bwd.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu", "post_process.cu", "ag_frontend.cu",
+_SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "knarpe_attn_mma.cu", "knarpe_attn_bwd.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu", "post_process.cu", "ag_frontend.cu", "mlp_chain.cu",
             "rollout_step.cu", "rule_check.cu"]
 _lib = None
 
@@ -21,7 +21,7 @@ EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_l
            "tb_pointnet_pool", "tb_pose_emb", "tb_ag_featurize", "tb_tl_featurize", "tb_dyn_step", "tb_tl_step",
            "tb_step_advance", "tb_gather_rows", "tb_action_mean", "tb_rule_check", "tb_future_filter",
            "tb_traj_global", "tb_womd_post", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd", "tb_set_fp16_flag", "tb_dyn_step_ex", "tb_tl_step_ex",
-           "tb_dyn_update"]
+           "tb_dyn_update", "tb_chain_program_bytes", "tb_chain_encode", "tb_chain_run"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -88,6 +88,9 @@ def load() -> ctypes.CDLL:
         "tb_tl_step_ex": [P, P, P, I, P, I, I, I, I, P, P, P, P],
         "tb_dyn_update": [P, P, P, P, P, P, P, F, I, P, P, P, P, P, P],
         "tb_step_advance": [P, P],
+        "tb_chain_program_bytes": [],
+        "tb_chain_encode": [P, I, I, P],
+        "tb_chain_run": [P, P, P, I, I, P],
         "tb_gather_rows": [P, I, I, P, I, I, I, I, P, I, P],
         "tb_action_mean": [P, P, P, I, P, P],
         "tb_rule_check": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P, P, I, I, I, I, I, I, I, F, P],

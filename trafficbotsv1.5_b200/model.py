@@ -247,6 +247,78 @@ class HotPathModel:
         return self._w_half[key]
 
     @property
+    def chain_fused(self) -> bool:
+        """Head chain and FFNs as fused tcgen05 chain programs (tb_chain_run) in the tensor-core mode; TB_CHAIN=0 keeps
+        the one-launch-per-layer path (A/B and bisecting)."""
+        return os.environ.get("TB_CHAIN", "1") != "0"
+
+    def _ffn_program(self, p: str, ldy: int, ln_next: Optional[str]):
+        """bindings: 0 LayerNorm rows fp16 [M,d], 1 residual fp32 [M,d], 2 row mask u8 [M], 3 out fp32 (ld ldy),
+        4 LayerNorm rows of the result fp16 [M,d] (when ln_next)."""
+        if not hasattr(self, "_chain"):
+            self._chain = {}
+        key = ("ffn", p, ldy, ln_next)
+        if key not in self._chain:
+            d = self.d
+            w1 = self._half(f"{p}.linear1", self.P[f"{p}.linear1.weight"])
+            w2 = self._half(f"{p}.linear2", self.P[f"{p}.linear2.weight"])
+            nh = w1.shape[0] // d
+            assert w1.shape == (nh * d, d) and w2.shape == (d, nh * d) and nh <= 4
+            q = ops.ChainProgram(self.dev, n_buf=nh)
+            q.load(0, d, 0, f16=True)
+            # hidden slice t -> buffer t + 1; the last one overwrites the input buffer (its MMAs, and those of the earlier
+            # slices, have read it by the time its epilogue runs): nh buffers leave a deeper weight ring than nh + 1
+            hb = [(t + 1) % nh for t in range(nh)]
+            for t in range(nh):
+                q.gemm(w1, [0], self.P[f"{p}.linear1.bias"], n0=t * d, relu=True, out_buf=hb[t])
+            ln = dict(ln_out=4, ld_ln=d, ln_gamma=self.P[f"{ln_next}.weight"], ln_beta=self.P[f"{ln_next}.bias"]) if ln_next else {}
+            q.gemm(w2, hb, self.P[f"{p}.linear2.bias"], res=1, ldr=d, mask_post=2, out_g=3, ldg=ldy, **ln)
+            self._chain[key] = q.finish()
+        return self._chain[key]
+
+    def _heads_program(self):
+        """The per-step head chain as one program. bindings: 0 x_cat fp32 [M,2d] (agent feature in the left half),
+        1 PoseEmb of the destination in the agent frame fp32 [M,d], 2 static navigation feature fp32 [M,d],
+        3 navi_invalid u8 [M], 4 latent cat buffer fp32 [M,2d] (left: add_navi result, written here; right: static latent
+        feature), 5 latent_invalid u8 [M], 6 act_branch fp32 [M,6]."""
+        if not hasattr(self, "_chain"):
+            self._chain = {}
+        if "heads" not in self._chain:
+            d = self.d
+            hw = lambda n: self._half(n, self.P[f"{n}.weight"])  # noqa: E731
+            b = lambda n: self.P[f"{n}.bias"]  # noqa: E731
+            q = ops.ChainProgram(self.dev, n_buf=4)
+            q.load(1, d, 1)                                                                        # pe -> B1
+            q.load(0, 2 * d, 0)                                                                    # x -> B0 (used by add_navi.mlp)
+            n = "navi_encoder.mlp_pe.fc_layers.0"
+            q.gemm(hw(n), [1], b(n), res=2, ldr=d, out_buf=2)                                      # nf (navigation.py:73-79)
+            for i, (src_b, dst_b) in zip((0, 3, 6), ((2, 1), (1, 2), (2, 1))):                     # add_navi.mlp_in
+                n = f"add_navi.mlp_in.fc_layers.{i}"
+                q.gemm(hw(n), [src_b], b(n), relu=True, out_buf=dst_b, mask_post=3 if i == 6 else -1)
+            n = "add_navi.mlp.fc_layers.0"
+            q.gemm(hw(n), [0, 1], b(n), relu=True, out_buf=2)                                      # cat(x, a1)
+            n = "add_navi.mlp.fc_layers.3"
+            q.gemm(hw(n), [2], b(n), relu=True, out_buf=3)
+            n = "add_navi.mlp.fc_layers.6"
+            q.gemm(hw(n), [3], b(n), relu=True, mask_pre=3, res=0, ldr=2 * d, out_buf=0, out_g=4, ldg=2 * d)  # x2
+            q.load(4, 2 * d, 1, src_col=d)                                                         # latent feature -> B1
+            n = "add_latent.mlp.fc_layers.0"
+            q.gemm(hw(n), [0, 1], b(n), relu=True, out_buf=2)
+            n = "add_latent.mlp.fc_layers.3"
+            q.gemm(hw(n), [2], b(n), relu=True, out_buf=3)
+            n = "add_latent.mlp.fc_layers.6"
+            q.gemm(hw(n), [3], b(n), relu=True, mask_pre=5, res=4, ldr=2 * d, out_buf=0)           # x3
+            w0 = self._half("action_head.w0", self.act_w0)
+            for t in range(3):                                                                     # action_head.py:78-82
+                q.gemm(w0, [0], self.act_b0, n0=t * d, relu=True, out_buf=1 + t)
+            for t in range(3):
+                n = f"action_head.mlp_mean.{t}.fc_layers.2"
+                q.gemm(hw(n), [1 + t], b(n), relu=True, out_buf=1 + t)
+            q.gemm(self._half("action_head.w4", self.act_w4), [1, 2, 3], self.act_b4, out_g=6, ldg=6, n_valid=6)
+            self._chain["heads"] = q.finish()
+        return self._chain["heads"]
+
+    @property
     def ln_fused(self) -> bool:
         """LayerNorm of the residual stream inside the epilogue of the projection that produces it (tb_linear_ln)."""
         return self.kv_half and self.d == 128 and os.environ.get("TB_LN_FUSED", "1") != "0"
@@ -293,6 +365,16 @@ class HotPathModel:
             proj, kv = self._in_self(f, x0, knn_self["idx"].shape[-1], f"{p}.attn")
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src, x2 = self._out_proj(f"{p}.attn", f, o, nv, src, ln_next=f"{p}.norm2")
+        if self.kv_half and self.chain_fused and self.d == 128 and os.environ.get("TB_CHAIN_FFN", "0") == "1":
+            # FFN-1 -> ReLU -> FFN-2 -> + residual -> row mask (-> next layer's LayerNorm rows) in ONE launch: the
+            # [rows, 512] hidden tile stays on the SM (tb_chain_run, csrc/mlp_chain.cu). Measured SLOWER than the two
+            # launches at 65,536 rows (83 vs 58 us, profiles/r2_notes.md: one tile in flight per SM, the 256 KB of
+            # weights re-streamed per tile), so it is off unless TB_CHAIN_FFN=1; the head chain (20 launches -> 1) wins.
+            M = x2.shape[0]
+            y = out if out is not None else torch.empty(M, self.d, device=x2.device)
+            ln_rows = torch.empty(M, self.d, dtype=torch.float16, device=x2.device) if ln_next is not None else None
+            self._ffn_program(p, y.stride(0), ln_next).run([x2, src, ops._u8(src_inv), y, ln_rows], M)
+            return y if ln_next is None else (y, ln_rows)
         if self.kv_half:  # FFN hidden (ReLU output) as fp16: written by the first projection, read by a kind::f16 one
             h = torch.empty(x2.shape[0], self.P[f"{p}.linear1.weight"].shape[0], dtype=torch.float16, device=x2.device)
             self._proj(x2, f"{p}.linear1", self.P[f"{p}.linear1.weight"], self.P[f"{p}.linear1.bias"], relu=True, out_h=h,
@@ -630,6 +712,11 @@ class HotPathModel:
         d = self.d
         M = x_cat.shape[0]
         pe = ops.pose_emb(navi["pose"], self.freq_rpe, d, frame=st["pose"], frame_div=1)             # navigation.py:73-79
+        if self.kv_half and self.chain_fused and d == 128 and "latent_cat" in navi and x_cat.is_contiguous():
+            act = torch.empty(M, 6, device=self.dev)
+            self._heads_program().run([x_cat, pe, navi["feat"], ops._u8(st["navi_invalid"]).reshape(-1), navi["latent_cat"],
+                                       ops._u8(st["latent_invalid"]).reshape(-1), act], M)
+            return act
         nf = self.lin(pe, "navi_encoder.mlp_pe.fc_layers.0", res=navi["feat"])
         # add_navi writes its result straight into the left half of add_latent's cat buffer
         x_cat2 = navi["latent_cat"] if "latent_cat" in navi else torch.empty(M, 2 * d, device=self.dev)

@@ -309,3 +309,80 @@ def knarpe_attn_bwd(q: Tensor, u: Tensor, kv0: Tensor, T0: int, div0: int, K0: i
         L.ptr(d_kv0), L.ptr(d_kv1), L.stream()), "tb_knarpe_attn_bwd")
     _count()
     return d_qu, d_kv0, d_kv1
+
+
+# ---------------------------------------------------------------------------------------------------- fused MLP chain
+class _ChainUnit(ctypes.Structure):
+    """tb_chain_unit of include/tb_knarpe.h."""
+    _fields_ = [("kind", ctypes.c_int), ("W", ctypes.c_void_p), ("K", ctypes.c_int), ("N", ctypes.c_int),
+                ("n0", ctypes.c_int), ("a_buf", ctypes.c_int * 4), ("bias", ctypes.c_void_p), ("relu", ctypes.c_int),
+                ("n_valid", ctypes.c_int), ("mask_pre", ctypes.c_int), ("mask_post", ctypes.c_int), ("res", ctypes.c_int),
+                ("ldr", ctypes.c_int), ("res_col", ctypes.c_int), ("out_buf", ctypes.c_int), ("out_g", ctypes.c_int),
+                ("ldg", ctypes.c_int), ("g_col", ctypes.c_int), ("out_h", ctypes.c_int), ("ldh", ctypes.c_int),
+                ("h_col", ctypes.c_int), ("ln_out", ctypes.c_int), ("ld_ln", ctypes.c_int), ("ln_gamma", ctypes.c_void_p),
+                ("ln_beta", ctypes.c_void_p), ("src", ctypes.c_int), ("lds", ctypes.c_int), ("src_col", ctypes.c_int),
+                ("src_f16", ctypes.c_int)]
+
+
+class ChainProgram:
+    """Builder / runner of a fused MLP chain (tb_chain_encode / tb_chain_run): `load` and `gemm` append units,
+    `finish` encodes the program (TMA descriptors of the weights included) and uploads it, `run` launches it on a set of
+    binding tensors. Weights are fp16 [N, K] row-major device tensors kept alive by the program."""
+
+    def __init__(self, device, n_buf: int = 4):
+        self.dev, self.n_buf = torch.device(device), n_buf
+        self.units, self.keep = [], []
+        self.blob = self.host = None
+
+    def _unit(self, **kw) -> _ChainUnit:
+        u = _ChainUnit()
+        for f in ("mask_pre", "mask_post", "res", "out_buf", "out_g", "out_h", "ln_out", "src"):
+            setattr(u, f, -1)
+        for i in range(4):
+            u.a_buf[i] = -1
+        for k, v in kw.items():
+            setattr(u, k, v)
+        self.units.append(u)
+        return u
+
+    def load(self, src: int, lds: int, out_buf: int, src_col: int = 0, f16: bool = False) -> None:
+        self._unit(kind=1, src=src, lds=lds, src_col=src_col, src_f16=int(f16), out_buf=out_buf)
+
+    def gemm(self, w: Tensor, a_bufs, bias: Optional[Tensor] = None, n0: int = 0, relu: bool = False, out_buf: int = -1,
+             mask_pre: int = -1, mask_post: int = -1, res: int = -1, ldr: int = 0, res_col: int = 0, out_g: int = -1,
+             ldg: int = 0, g_col: int = 0, n_valid: int = 0, out_h: int = -1, ldh: int = 0, h_col: int = 0, ln_out: int = -1,
+             ld_ln: int = 0, ln_gamma: Optional[Tensor] = None, ln_beta: Optional[Tensor] = None) -> None:
+        assert w.dtype == torch.float16 and w.is_contiguous() and w.is_cuda and w.dim() == 2
+        N, K = w.shape
+        assert K == 128 * len(a_bufs), (w.shape, a_bufs)
+        u = self._unit(kind=0, W=w.data_ptr(), K=K, N=N, n0=n0, relu=int(relu), out_buf=out_buf, mask_pre=mask_pre,
+                       mask_post=mask_post, res=res, ldr=ldr, res_col=res_col, out_g=out_g, ldg=ldg, g_col=g_col,
+                       n_valid=n_valid, out_h=out_h, ldh=ldh, h_col=h_col, ln_out=ln_out, ld_ln=ld_ln)
+        for i, b in enumerate(a_bufs):
+            u.a_buf[i] = b
+        self.keep.append(w)
+        if bias is not None:  # the epilogue reads bias[n0 : n0 + 128] unconditionally
+            b = bias.detach().to(self.dev, torch.float32).contiguous()
+            if b.numel() < n0 + 128:
+                b = torch.cat([b, b.new_zeros(n0 + 128 - b.numel())])
+            self.keep.append(b)
+            u.bias = b.data_ptr()
+        if ln_out >= 0:
+            g, be = _f32c(ln_gamma), _f32c(ln_beta)
+            self.keep += [g, be]
+            u.ln_gamma, u.ln_beta = g.data_ptr(), be.data_ptr()
+
+    def finish(self) -> "ChainProgram":
+        lib = L.load()
+        n = lib.tb_chain_program_bytes()
+        self.host = (ctypes.c_uint8 * n)()
+        arr = (_ChainUnit * len(self.units))(*self.units)
+        L.check(lib.tb_chain_encode(arr, len(self.units), self.n_buf, self.host), "tb_chain_encode")
+        self.blob = torch.frombuffer(bytearray(self.host), dtype=torch.uint8).to(self.dev)
+        assert self.blob.data_ptr() % 128 == 0
+        return self
+
+    def run(self, bindings, M: int) -> None:
+        ptrs = (ctypes.c_void_p * len(bindings))(*[None if t is None else t.data_ptr() for t in bindings])
+        L.check(L.load().tb_chain_run(L.ptr(self.blob), self.host, ptrs, len(bindings), M, L.stream()), "tb_chain_run")
+        _count()
