@@ -9,17 +9,18 @@
 //   logits[h, j] = sum_c q[c in head h] k_j[c] + sum_c u[h, c] e_j[c]
 //   z[h, c] = sum_j p[h, j] e_j[c]          ov[c in head h] = sum_j p[h, j] v_j[c]
 // Here they run on mma.sync.m16n8k16 (f16 operands, f32 accumulate) with every operand built IN FRAGMENT LAYOUT in
-// registers - nothing is staged through shared memory:
-//   * a group = 16 compacted neighbours = two 8-wide MMA tiles. Lane (g = lane>>2, t = lane&3) owns neighbours g and
-//     g+8: it loads 16-byte pieces of their fp16 K and V rows that are exactly its A-fragment registers, and evaluates
-//     the cos/sin of 16 embedding angles per neighbour - the A-fragment elements (m = neighbour, k = channel slot) of
-//     the e.u MMA. The yaw harmonics of a lane form arithmetic progressions: 6 SFU evaluations + 7 plane rotations
-//     replace 32 SFU evaluations; the geometric x/y frequencies are evaluated directly.
-//   * logits [16 nbr x 8] = A(k) B(q, block-diagonal over heads) + A(e) B(u): B columns 0-3 hold fp16(operand) of
-//     heads 0-3, columns 4-7 its fp16 residual, so q and u keep ~22 significant bits; one shuffle adds the halves.
-//   * z^T [128 x 8] = A(e^T) B(p^T) and ov^T [32 x 8] = sum_heads A(v_head^T) B(p^T masked to that head): columns 0-3
-//     take fp16(p_h) (no residual: e and v are fp16-rounded anyway); the transposed fragments (e^T, v^T, p^T) come
-//     from movmatrix (register-only 8x8 transposes).
+// registers - nothing is staged through shared memory. Two tokens share a warp (knarpe_attn_mma_pair_kernel below):
+//   * a group = 8 compacted neighbours of token A (MMA rows 0-7) + 8 of token B (rows 8-15). Lane (g = lane>>2,
+//     t = lane&3) owns row g of both: it loads 32-byte pieces of their fp16 K and V rows that are exactly its
+//     A-fragment registers, and evaluates the cos/sin of 16 embedding angles per neighbour - the A-fragment elements
+//     (m = neighbour, k = channel slot) of the e.u MMA. The yaw harmonics of a lane form arithmetic progressions:
+//     3 SFU sincos + packed plane rotations replace 16; the geometric x/y frequencies are evaluated directly.
+//   * logits [16 x 8] = A(k) B(q, block-diagonal over heads) + A(e) B(u): B columns 0-3 hold the fp16 q / u of token
+//     A's heads, columns 4-7 of token B's (q / u arrive as fp16 rows from the in-projection's epilogue).
+//   * z^T [128 x 8] = A(e^T) B(p^T) and ov^T [32 x 8] = sum_heads A(v_head^T) B(p^T masked to that head); the
+//     transposed fragments (e^T, v^T, p^T) come from movmatrix (register-only 8x8 transposes).
+// (Round 1 also had a one-token-per-warp kernel with split-fp16 q / u for fp32 callers; it was never on the engine's
+// path and was removed in round 2: fp32 q / u rows on fp16 tables run on the SIMT kernel of knarpe_attn.cu.)
 // Staging the gathered rows in shared memory instead (cp.async + ldmatrix: 835 us, cp.async.bulk per row + ldmatrix:
 // 634 us on the agent cross-attention launch) lost against these direct fragment loads (493 us): the per-lane
 // cp.async clogs the LSU queue, and bulk copies need uniform-register operands, i.e. a serialised 16-trip loop per
@@ -42,15 +43,9 @@ namespace {
 #ifndef TB_MMA_MINB
 #define TB_MMA_MINB 12
 #endif
-#ifndef TB_MMA_PAIR_MAX_K
-#define TB_MMA_PAIR_MAX_K 128  // lists up to this length (fp16 q/u rows) use the two-tokens-per-warp kernel
-#endif
 constexpr int kWarps = TB_MMA_WARPS;
 constexpr int D = 128;
 constexpr int H = 4;
-constexpr int KMAX = 128;  // compacted neighbour slots per token (K0 + K1 rounded up to 16)
-constexpr int kWarpSmem = KMAX * 8 + KMAX * 12;  // row pointers + relative poses; reused as 640-float output staging
-static_assert(kWarpSmem >= (D + H * D) * 4, "output staging must fit");
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -60,14 +55,6 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
-}
-// fp16 head (lo == false) or fp16 residual (lo == true) of a pair of floats
-__device__ __forceinline__ uint32_t split_h2(float a, float b, bool lo) {
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 f = __half22float2(h);
-  const __half2 r = __floats2half2_rn(a - f.x, b - f.y);
-  const __half2 s = lo ? r : h;
-  return *reinterpret_cast<const uint32_t*>(&s);
 }
 __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
@@ -85,326 +72,6 @@ __device__ __forceinline__ uint4 ldg128(const __half* p) { return __ldg(reinterp
 // reference embedding index of slot 0 (cos half) / slot 8 (sin half) of chunk c; slots are consecutive from there
 __host__ __device__ constexpr int cos_base(int c) { return c < 2 ? 8 * c : (c < 4 ? 32 + 8 * (c - 2) : 64 + 8 * (c - 4)); }
 __host__ __device__ constexpr int sin_base(int c) { return cos_base(c) + (c < 4 ? 16 : 32); }
-
-// OUT_H: [ov|z] rows are written as fp16 (consumed by the kind::f16 output projection). IN_H: q / u rows are fp16
-// (written by the in-projection's fp16 epilogue): they are MMA operands as they are, no residual columns.
-template <bool OUT_H, bool IN_H>
-__global__ void __launch_bounds__(kWarps * 32, TB_MMA_MINB)
-knarpe_attn_mma_kernel(const void* __restrict__ q_, int ldq, const void* __restrict__ u_, int ldu,
-                       const __half* __restrict__ kv0, int ldkv0, int T0, int div0, int K0,
-                       const __half* __restrict__ kv1, int ldkv1, int T1, int div1, int K1,
-                       const int32_t* __restrict__ idx, const uint8_t* __restrict__ invalid,
-                       const float* __restrict__ rel, const float* __restrict__ pe_freq_xy, int n_tok, int S,
-                       void* __restrict__ out_ov_, void* __restrict__ out_z_, int ldo,
-                       uint8_t* __restrict__ out_none_valid) {
-  __shared__ __align__(16) unsigned char s_raw[kWarps][kWarpSmem];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tok = blockIdx.x * kWarps + warp;
-  if (tok >= n_tok) return;  // warp-uniform; only warp-level synchronisation below
-  const __half** s_ptr = reinterpret_cast<const __half**>(s_raw[warp]);           // [KMAX] K|V row pointers
-  float (*s_rel)[3] = reinterpret_cast<float (*)[3]>(s_raw[warp] + KMAX * 8);      // [KMAX] relative poses
-  float* s_out = reinterpret_cast<float*>(s_raw[warp]);                            // epilogue: [ov(128) | z(512)]
-
-  const int b = tok / S;
-  const int Ktot = K0 + K1;
-  const int g = lane >> 2, t = lane & 3;
-  const int hA = g & 3;               // operand column g <-> head hA ...
-  const bool lo_part = (g & 4) != 0;  // ... columns 4-7: fp16 residual operands
-  const unsigned lt_mask = (1u << lane) - 1u;
-
-  // ---- neighbour list: every load of the row is issued before the first use (Ktot <= 128: at most 4 chunks of 32)
-  const size_t prow = (size_t)tok * Ktot;
-  const __half* kb0 = kv0 + (size_t)(b / div0) * T0 * ldkv0;
-  const __half* kb1 = (K1 > 0) ? kv1 + (size_t)(b / div1) * T1 * ldkv1 : kb0;
-  uint8_t n_inv[4];
-  int n_id[4];
-  float n_rel[4][3];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int j = c * 32 + lane;
-    n_inv[c] = 1; n_id[c] = 0; n_rel[c][0] = n_rel[c][1] = n_rel[c][2] = 0.f;
-    if (c * 32 < Ktot && j < Ktot) {
-      const size_t p = prow + j;
-      n_inv[c] = __ldg(invalid + p);
-      n_id[c] = __ldg(idx + p);
-      n_rel[c][0] = __ldg(rel + p * 3 + 0);
-      n_rel[c][1] = __ldg(rel + p * 3 + 1);
-      n_rel[c][2] = __ldg(rel + p * 3 + 2);
-    }
-  }
-  // ---- per-token operands (loads in flight across the compaction)
-  float fq[2][2];  // x/y frequencies of this lane's slots: chunk c (0/1), slot pair j
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    fq[c][0] = __ldg(pe_freq_xy + 8 * c + 2 * t);
-    fq[c][1] = __ldg(pe_freq_xy + 8 * c + 2 * t + 1);
-  }
-  float2 u_raw[8][2];
-  float4 q_lo4 = make_float4(0.f, 0.f, 0.f, 0.f), q_hi4 = q_lo4;
-  uint32_t uB[8][2], qB[2][2];
-  if (IN_H) {  // fp16 rows: the half2 pairs are the B registers themselves (columns 4-7 of B stay zero)
-    const __half* up = static_cast<const __half*>(u_) + (size_t)tok * ldu + hA * D + 2 * t;
-    const __half* qp = static_cast<const __half*>(q_) + (size_t)tok * ldq + 32 * hA + 8 * t;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uB[c][0] = lo_part ? 0u : __ldg(reinterpret_cast<const uint32_t*>(up + cos_base(c)));
-      uB[c][1] = lo_part ? 0u : __ldg(reinterpret_cast<const uint32_t*>(up + sin_base(c)));
-    }
-    const uint4 qq = lo_part ? make_uint4(0u, 0u, 0u, 0u) : __ldg(reinterpret_cast<const uint4*>(qp));
-    qB[0][0] = qq.x; qB[0][1] = qq.y; qB[1][0] = qq.z; qB[1][1] = qq.w;
-  } else {
-    const float* up = static_cast<const float*>(u_) + (size_t)tok * ldu + hA * D + 2 * t;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      u_raw[c][0] = __ldg(reinterpret_cast<const float2*>(up + cos_base(c)));
-      u_raw[c][1] = __ldg(reinterpret_cast<const float2*>(up + sin_base(c)));
-    }
-    const float* qp = static_cast<const float*>(q_) + (size_t)tok * ldq + 32 * hA + 8 * t;
-    q_lo4 = ldg4(qp);
-    q_hi4 = ldg4(qp + 4);
-  }
-
-  // ---- compact the unmasked neighbours; pad to a multiple of 16 with weight-0 dummies
-  int nvalid = 0;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c * 32 < Ktot) {  // warp-uniform
-      const int j = c * 32 + lane;
-      const bool valid = n_inv[c] == 0;
-      const unsigned vb = __ballot_sync(TB_FULL_MASK, valid);
-      if (valid) {
-        const int pos = nvalid + __popc(vb & lt_mask);
-        s_ptr[pos] = (j < K0) ? kb0 + (size_t)n_id[c] * ldkv0 : kb1 + (size_t)n_id[c] * ldkv1;
-        s_rel[pos][0] = n_rel[c][0];
-        s_rel[pos][1] = n_rel[c][1];
-        s_rel[pos][2] = n_rel[c][2];
-      }
-      nvalid += __popc(vb);
-    }
-  }
-  const int npad = (nvalid + 15) & ~15;
-  if (lane < npad - nvalid) {
-    s_ptr[nvalid + lane] = kb0;
-    s_rel[nvalid + lane][0] = 0.f;
-    s_rel[nvalid + lane][1] = 0.f;
-    s_rel[nvalid + lane][2] = 0.f;
-  }
-  __syncwarp();
-
-  // B fragments of u (chunk c: b0 = slots 2t,2t+1, b1 = slots 2t+8,2t+9; column g = head hA, residual for g >= 4) and
-  // of the block-diagonal q (chunks 2 hA + e only; other chunks are zero for this column)
-  if (!IN_H) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uB[c][0] = split_h2(u_raw[c][0].x, u_raw[c][0].y, lo_part);
-      uB[c][1] = split_h2(u_raw[c][1].x, u_raw[c][1].y, lo_part);
-    }
-    qB[0][0] = split_h2(q_lo4.x, q_lo4.y, lo_part);
-    qB[0][1] = split_h2(q_lo4.z, q_lo4.w, lo_part);
-    qB[1][0] = split_h2(q_hi4.x, q_hi4.y, lo_part);
-    qB[1][1] = split_h2(q_hi4.z, q_hi4.w, lo_part);
-  }
-
-  float zacc[8][4], oacc[2][4];
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) zacc[c][r] = 0.f;
-#pragma unroll
-  for (int m = 0; m < 2; ++m)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) oacc[m][r] = 0.f;
-  // softmax state of the heads of this lane's accumulator columns 2t, 2t+1: heads 2 (t&1), 2 (t&1) + 1
-  float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f};
-
-  for (int g0 = 0; g0 < npad; g0 += 16) {
-    const int nb = nvalid - g0;  // valid neighbours in this group (>= 1; may exceed 16)
-    // ---- K pieces: row of neighbour g0 + 8 tile + g, 16 B at halves [32 i + 8 t, +8): A registers (a0|a2 for tile 0,
-    // a1|a3 for tile 1) of the chunks 2i (x, y) and 2i+1 (z, w) of the q.k MMA
-    const __half* rowp[2];
-    uint4 kf[2][4];
-#pragma unroll
-    for (int tile = 0; tile < 2; ++tile) {
-      rowp[tile] = s_ptr[g0 + tile * 8 + g];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) kf[tile][i] = ldg128(rowp[tile] + 32 * i + 8 * t);
-    }
-
-    // ---- relative-pose embedding in A-fragment layout: eA[chunk] = {a0, a1, a2, a3} = {slots 2t,2t+1 of neighbour g,
-    // of neighbour g+8, slots 2t+8,2t+9 of g, of g+8}. chunks 0-1: x, 2-3: y, 4-7: yaw; slots 0-7 cos, 8-15 sin
-    uint32_t eA[8][4];
-#pragma unroll
-    for (int tile = 0; tile < 2; ++tile) {
-      const float* rp = s_rel[g0 + tile * 8 + g];
-      const float x = rp[0], y = rp[1], w = rp[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float s0, c0, s1, c1;
-        __sincosf(x * fq[c][0], &s0, &c0);
-        __sincosf(x * fq[c][1], &s1, &c1);
-        eA[c][tile] = pack_h2(c0, c1);
-        eA[c][2 + tile] = pack_h2(s0, s1);
-        __sincosf(y * fq[c][0], &s0, &c0);
-        __sincosf(y * fq[c][1], &s1, &c1);
-        eA[2 + c][tile] = pack_h2(c0, c1);
-        eA[2 + c][2 + tile] = pack_h2(s0, s1);
-      }
-      // yaw harmonics 8 cc + 2t + 1 (+1): bases by SFU, steps of 8 by plane rotation (pose_emb.py:52, integer freqs)
-      float cA, sA, c1, s1, c8, s8;
-      __sincosf(w * (float)(2 * t + 1), &sA, &cA);
-      __sincosf(w, &s1, &c1);
-      __sincosf(w * 8.f, &s8, &c8);
-      float2 cv = make_float2(cA, fmaf(cA, c1, -sA * s1)), sv = make_float2(sA, fmaf(sA, c1, cA * s1));
-      const float2 c8v = make_float2(c8, c8), s8v = make_float2(s8, s8), ns8v = make_float2(-s8, -s8);
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        eA[4 + cc][tile] = pack_h2(cv.x, cv.y);
-        eA[4 + cc][2 + tile] = pack_h2(sv.x, sv.y);
-        if (cc < 3) {  // rotate both harmonics by 8 w (packed FMUL2 / FFMA2)
-          const float2 nc = __ffma2_rn(cv, c8v, __fmul2_rn(sv, ns8v));
-          sv = __ffma2_rn(sv, c8v, __fmul2_rn(cv, s8v));
-          cv = nc;
-        }
-      }
-    }
-
-    // ---- logits[row = neighbour g | g+8][col = head (+4: residual of q / u)]
-    // (four independent accumulator chains of 4 MMAs each instead of one chain of 16)
-    float sc[4] = {0.f, 0.f, 0.f, 0.f}, sc1[4] = {0.f, 0.f, 0.f, 0.f}, sc2[4] = {0.f, 0.f, 0.f, 0.f},
-          sc3[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c = 0; c < 8; ++c) mma16816((c & 1) ? sc1 : sc, eA[c][0], eA[c][1], eA[c][2], eA[c][3], uB[c][0], uB[c][1]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {  // q.k: chunks 2i, 2i+1 carry head i only
-      const bool mine = hA == i;
-      mma16816(sc2, kf[0][i].x, kf[1][i].x, kf[0][i].y, kf[1][i].y, mine ? qB[0][0] : 0u, mine ? qB[0][1] : 0u);
-      mma16816(sc3, kf[0][i].z, kf[1][i].z, kf[0][i].w, kf[1][i].w, mine ? qB[1][0] : 0u, mine ? qB[1][1] : 0u);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) sc[r] = (sc[r] + sc1[r]) + (sc2[r] + sc3[r]);
-
-    // ---- V pieces (same addressing as K, second half of the row): in flight across the softmax
-    uint4 vf[2][4];
-#pragma unroll
-    for (int tile = 0; tile < 2; ++tile)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) vf[tile][i] = ldg128(rowp[tile] + D + 32 * i + 8 * t);
-
-    // ---- softmax: this lane holds neighbours g (sc[0..1]) and g+8 (sc[2..3]) for heads 2(t&1), 2(t&1)+1
-    float lg[2][2];  // [tile][head j]
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float v = sc[r] + __shfl_xor_sync(TB_FULL_MASK, sc[r], 2);  // head + residual column
-      lg[r >> 1][r & 1] = ((r >> 1) * 8 + g < nb) ? v : -INFINITY;
-    }
-    float mn[2], p[2][2], ps[2];
-    bool grew = false;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      float gm = fmaxf(lg[0][j], lg[1][j]);
-      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 4));
-      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 8));
-      gm = fmaxf(gm, __shfl_xor_sync(TB_FULL_MASK, gm, 16));
-      mn[j] = fmaxf(mx[j], gm);  // finite: slot g0 is a valid neighbour
-      p[0][j] = ex2(lg[0][j] - mn[j]);
-      p[1][j] = ex2(lg[1][j] - mn[j]);
-      float s = p[0][j] + p[1][j];
-      s += __shfl_xor_sync(TB_FULL_MASK, s, 4);
-      s += __shfl_xor_sync(TB_FULL_MASK, s, 8);
-      s += __shfl_xor_sync(TB_FULL_MASK, s, 16);
-      ps[j] = s;
-      grew |= mn[j] > mx[j];
-    }
-    if (__any_sync(TB_FULL_MASK, grew)) {  // lazy rescale (warp-uniform); accumulator columns 2t, 2t+1 = these heads
-      const float ca = ex2(mx[0] - mn[0]), cb = ex2(mx[1] - mn[1]);  // 1 where the max did not move, 0 at the start
-      mx[0] = mn[0]; mx[1] = mn[1];
-      sm[0] *= ca; sm[1] *= cb;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { zacc[c][0] *= ca; zacc[c][1] *= cb; zacc[c][2] *= ca; zacc[c][3] *= cb; }
-#pragma unroll
-      for (int m = 0; m < 2; ++m) { oacc[m][0] *= ca; oacc[m][1] *= cb; oacc[m][2] *= ca; oacc[m][3] *= cb; }
-    }
-    sm[0] += ps[0];
-    sm[1] += ps[1];
-    // p^T as B fragment: [neighbour g][cols 2t,2t+1] tiles transposed. Columns 4-7 stay zero: the e and v operands
-    // are fp16-rounded anyway, a residual of p would not buy accuracy
-    const uint32_t pB0 = movm_trans(t < 2 ? pack_h2(p[0][0], p[0][1]) : 0u);
-    const uint32_t pB1 = movm_trans(t < 2 ? pack_h2(p[1][0], p[1][1]) : 0u);
-
-    // ---- z^T[row = channel slot][col = head (+4: residual of p)] += e^T p^T; e^T fragments by register transpose
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const uint32_t a0 = movm_trans(eA[c][0]), a1 = movm_trans(eA[c][2]);
-      const uint32_t a2 = movm_trans(eA[c][1]), a3 = movm_trans(eA[c][3]);
-      mma16816(zacc[c], a0, a1, a2, a3, pB0, pB1);
-    }
-
-    // ---- ov^T[row = channel within head][col = head (+4)] += sum over heads i of v_i^T (p^T masked to head i).
-    // Register r of piece i holds channels 32 i + 8 t + 2 r + {0,1}; after the transpose row g' of the tile is
-    // channel 32 i + 8 (g'>>1) + 2 r + (g'&1): m-tile m stacks r = 2m (rows 0-7) and r = 2m+1 (rows 8-15).
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const bool mine = hA == i;
-      const uint32_t b0 = mine ? pB0 : 0u, b1 = mine ? pB1 : 0u;
-      {
-        const uint32_t a0 = movm_trans(vf[0][i].x), a1 = movm_trans(vf[0][i].y);
-        const uint32_t a2 = movm_trans(vf[1][i].x), a3 = movm_trans(vf[1][i].y);
-        mma16816(oacc[0], a0, a1, a2, a3, b0, b1);
-      }
-      {
-        const uint32_t a0 = movm_trans(vf[0][i].z), a1 = movm_trans(vf[0][i].w);
-        const uint32_t a2 = movm_trans(vf[1][i].z), a3 = movm_trans(vf[1][i].w);
-        mma16816(oacc[1], a0, a1, a2, a3, b0, b1);
-      }
-    }
-  }
-
-  // ---- normalise, un-permute through shared memory, store coalesced (all-masked row: zeros,
-  // attention_rpe.py:188-190)
-  const float ia = sm[0] > 0.f ? 1.f / sm[0] : 0.f, ib = sm[1] > 0.f ? 1.f / sm[1] : 0.f;
-  __syncwarp();  // every lane is done with s_ptr / s_rel
-  if (t < 2) {   // accumulator columns 2t, 2t+1 = heads 2t, 2t+1 (columns 4-7 are unused)
-    const int h0 = 2 * t;
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {  // rows g (register 2m of the piece) and g+8 (register 2m+1)
-      const int cp = 8 * (g >> 1) + 4 * m + (g & 1);
-      s_out[32 * h0 + cp] = oacc[m][0] * ia;
-      s_out[32 * (h0 + 1) + cp] = oacc[m][1] * ib;
-      s_out[32 * h0 + cp + 2] = oacc[m][2] * ia;
-      s_out[32 * (h0 + 1) + cp + 2] = oacc[m][3] * ib;
-    }
-    float* zs = s_out + D + g;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {  // rows g (cos slot) and g+8 (sin slot)
-      zs[h0 * D + cos_base(c)] = zacc[c][0] * ia;
-      zs[(h0 + 1) * D + cos_base(c)] = zacc[c][1] * ib;
-      zs[h0 * D + sin_base(c)] = zacc[c][2] * ia;
-      zs[(h0 + 1) * D + sin_base(c)] = zacc[c][3] * ib;
-    }
-  }
-  __syncwarp();
-  if (OUT_H) {
-    auto to_h4 = [](const float* p) {
-      const float4 v = *reinterpret_cast<const float4*>(p);
-      return make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w));
-    };
-    __half* ov_h = static_cast<__half*>(out_ov_) + (size_t)tok * ldo + lane * 4;
-    __half* z_h = static_cast<__half*>(out_z_) + (size_t)tok * ldo + lane * 4;
-    *reinterpret_cast<uint2*>(ov_h) = to_h4(s_out + lane * 4);
-#pragma unroll
-    for (int k = 0; k < H; ++k) *reinterpret_cast<uint2*>(z_h + k * D) = to_h4(s_out + D + k * D + lane * 4);
-  } else {
-    float* out_ov = static_cast<float*>(out_ov_);
-    float* out_z = static_cast<float*>(out_z_);
-    *reinterpret_cast<float4*>(out_ov + (size_t)tok * ldo + lane * 4) = *reinterpret_cast<const float4*>(s_out + lane * 4);
-    float* zp = out_z + (size_t)tok * ldo + lane * 4;
-#pragma unroll
-    for (int k = 0; k < H; ++k)
-      *reinterpret_cast<float4*>(zp + k * D) = *reinterpret_cast<const float4*>(s_out + D + k * D + lane * 4);
-  }
-  if (lane == 0 && out_none_valid) out_none_valid[tok] = nvalid > 0 ? 0 : 1;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Two tokens per warp for SHORT neighbour lists (agent self-attention, K = 25): MMA rows 0-7 are 8 neighbours of token
@@ -757,35 +424,21 @@ int tb_knarpe_attn_mma_launch(const void* q, int ldq, const void* u, int ldu, in
                               const int32_t* idx, const uint8_t* invalid, const float* rel, const float* pe_freq_xy,
                               int B, int S, void* out_ov, void* out_z, int ldo, int out_f16, uint8_t* out_none_valid,
                               int interleaved, cudaStream_t st) {
+  if (!in_f16) return TB_ERR_UNSUPPORTED;  // fp32 q / u rows go to the SIMT kernel (knarpe_attn.cu)
   const int n_tok = B * S;
-  const int grid = (n_tok + kWarps - 1) / kWarps;
-  if (in_f16 && K0 + K1 <= TB_MMA_PAIR_MAX_K) {  // two tokens per warp
-    const int grid2 = (n_tok + 2 * kWarps - 1) / (2 * kWarps);
+  const int grid2 = (n_tok + 2 * kWarps - 1) / (2 * kWarps);  // two tokens per warp
 #define TB_PAIR_LAUNCH(OH, IL)                                                                                         \
   knarpe_attn_mma_pair_kernel<OH, IL><<<grid2, kWarps * 32, 0, st>>>(                                                  \
       static_cast<const __half*>(q), ldq, static_cast<const __half*>(u), ldu, static_cast<const __half*>(kv0), ldkv0,  \
       T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S,     \
       out_ov, out_z, ldo, out_none_valid)
-    if (out_f16 && interleaved) TB_PAIR_LAUNCH(true, true);
-    else if (out_f16) TB_PAIR_LAUNCH(true, false);
-    else if (interleaved) TB_PAIR_LAUNCH(false, true);
-    else TB_PAIR_LAUNCH(false, false);
+  if (out_f16 && interleaved) TB_PAIR_LAUNCH(true, true);
+  else if (out_f16) TB_PAIR_LAUNCH(true, false);
+  else if (interleaved) TB_PAIR_LAUNCH(false, true);
+  else TB_PAIR_LAUNCH(false, false);
 #undef TB_PAIR_LAUNCH
-    TB_CHECK_LAUNCH();
-    return TB_OK;
-  }
-  if (interleaved) return TB_ERR_UNSUPPORTED;  // the head-interleaved layout is the pair kernel's
-#define TB_MMA_LAUNCH(OH, IH)                                                                                          \
-  knarpe_attn_mma_kernel<OH, IH><<<grid, kWarps * 32, 0, st>>>(                                                        \
-      q, ldq, u, ldu, static_cast<const __half*>(kv0), ldkv0, T0, div0, K0, static_cast<const __half*>(kv1), ldkv1, T1, \
-      div1, K1, idx, invalid, rel, pe_freq_xy, n_tok, S, out_ov, out_z, ldo, out_none_valid)
-  if (out_f16 && in_f16) TB_MMA_LAUNCH(true, true);
-  else if (out_f16) TB_MMA_LAUNCH(true, false);
-  else if (in_f16) TB_MMA_LAUNCH(false, true);
-  else TB_MMA_LAUNCH(false, false);
-#undef TB_MMA_LAUNCH
   TB_CHECK_LAUNCH();
   return TB_OK;
 }
 
-bool tb_knarpe_attn_mma_supported(int D_, int Hh, int Ktot) { return D_ == D && Hh == H && ((Ktot + 15) & ~15) <= KMAX; }
+bool tb_knarpe_attn_mma_supported(int D_, int Hh, int Ktot) { return D_ == D && Hh == H && Ktot <= KPAIR; }

@@ -48,7 +48,6 @@ def fuse_attention(P: Dict[str, Tensor], prefix: str, d: int, n_head: int = H) -
     b_qu = torch.cat([b_q] + b_u, 0)
     out = dict(
         w_in_self=torch.cat([w_qu, w_in[d:]], 0), b_in_self=torch.cat([b_qu, b_in[d:]], 0),
-        w_in_self_kvfirst=torch.cat([w_in[d:], w_qu], 0), b_in_self_kvfirst=torch.cat([b_in[d:], b_qu], 0),
         w_in_q=w_qu, b_in_q=b_qu, w_kv=w_in[d:], b_kv=b_in[d:],
         w_out=torch.cat([w_o] + w_oz, 1), b_out=b_o + w_o @ b_rv,
     )
@@ -89,7 +88,6 @@ class HotPathModel:
         self.cfg, self.sz, self.dev, self.precision = cfg, sizes, torch.device(device), precision
         self.d = cfg["hidden_dim"]
         self.kv_half = precision == 1 and self.d == 128  # fp16 K|V tables + tensor-core attention (tb_knarpe_attn bit 1)
-        self.mma_min_k = int(os.environ.get("TB_MMA_MIN_K", "0"))
         self.W = cfg["temp_window_size"]
         self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in P.items()}
         self.fa: Dict[str, Dict[str, Tensor]] = {}
@@ -114,7 +112,6 @@ class HotPathModel:
         self.cfg, self.sz, self.dev, self.precision = None, None, torch.device(device), precision
         self.d, self.W = d_model, None
         self.kv_half = precision == 1 and d_model == 128
-        self.mma_min_k = int(os.environ.get("TB_MMA_MIN_K", "0"))
         self.P = {k: v.detach().to(self.dev, torch.float32).contiguous() for k, v in sd.items()}
         self.fa = {}
         for k in sd:
@@ -139,7 +136,7 @@ class HotPathModel:
     def kv_il(self) -> bool:
         """Head-interleaved q / K / V rows (tb_knarpe_attn flags bit 4): every attention of the tensor-core mode runs
         on the pair kernel, so the projections write the layout it gathers with 256-bit loads."""
-        return self.kv_half and self.mma_min_k == 0 and os.environ.get("TB_ATTN_IL", "1") != "0"
+        return self.kv_half and os.environ.get("TB_ATTN_IL", "1") != "0"
 
     def _proj(self, x: Tensor, key: str, w: Tensor, b: Tensor, il_blocks=(), **kw):
         """Projection of LayerNorm output: fp16 rows x fp16 weights (tb_linear precision 2) or the fp32 / tf32 path.
@@ -206,20 +203,14 @@ class HotPathModel:
         return ops.linear(x, f["w_kv"], f["b_kv"], precision=self.precision, out=out)
 
     def _in_self(self, f, x, K, key=""):
-        """[q|u] (fp32) and the token's own [k|v] rows from one projection; k|v are fp16 in tensor-core mode. Short
-        neighbour lists (K < mma_min_k) stay on the fp32 SIMT kernel: the tensor-core kernel works on groups of 16
-        neighbours and has a higher per-token cost (measured in profiles/r1_notes.md)."""
+        """[q|u] and the token's own [k|v] rows from one projection: one fp16 [q|u|k|v] row buffer in tensor-core mode
+        (the pair attention kernel's operands), one fp32 buffer otherwise."""
         nq = self.d + H * self.d
-        if self.kv_half and K >= self.mma_min_k:  # everything fp16: [q|u|k|v] rows of one buffer
+        if self.kv_half:
             row = torch.empty(x.shape[0], nq + 2 * self.d, dtype=torch.float16, device=x.device)
             self._proj(x, f"{key}.w_in_self", f["w_in_self"], f["b_in_self"], out_h=row, col_h=0,
                        il_blocks=(0, nq, nq + self.d))
             return row[:, :nq], row[:, nq:]
-        if self.kv_half:  # SIMT kernel on a short list: fp32 [k|v] (leading columns), fp16 [q|u]
-            qu = torch.empty(x.shape[0], nq, dtype=torch.float16, device=x.device)
-            kv = self._proj(x, f"{key}.w_in_self_kvfirst", f["w_in_self_kvfirst"], f["b_in_self_kvfirst"], out_h=qu,
-                            col_h=2 * self.d)
-            return qu, kv
         proj = ops.linear(x, f["w_in_self"], f["b_in_self"], precision=self.precision)
         return proj, proj[:, nq:]
 
