@@ -380,8 +380,9 @@ extern "C" int tb_knarpe_attn(const void* q, int ldq, const void* u, int ldu, co
   if (flags & 2) {  // bit 1: fp16 K|V tables: all contractions on mma.sync (knarpe_attn_mma.cu) where that kernel applies
     if (!rel) return TB_ERR_UNSUPPORTED;
     if ((ldkv0 | (K1 > 0 ? ldkv1 : 0)) & 7) return TB_ERR_MISALIGNED;
-    if (!tb_knarpe_attn_mma_supported(D, Hh, K0 + K1)) {
-      // d_model 256 (BASELINE config 2) or lists longer than 128: the SIMT kernel on fp16 tables (fp32 arithmetic)
+    if (!tb_knarpe_attn_mma_supported(D, Hh, K0 + K1) || !in_h) {
+      // d_model 256 (BASELINE config 2), lists longer than 128 or fp32 q / u rows: the SIMT kernel on fp16 tables
+      // (fp32 arithmetic)
       if ((flags & 16) || !fast || out_h != in_h) return TB_ERR_UNSUPPORTED;
       if (D == 128)
         return out_h ? launch<128, false, true, true, true, true>(TB_ATT_ARGS)
