@@ -160,6 +160,69 @@ int tb_linear_ln(const void* X, int ldx, const void* W, const float* bias, float
 int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, void* Y, int ldy, int M, int D,
                  int flags, void* stream);
 
+/* LayerNorm backward (training path; nn.LayerNorm of transformer_rpe.py:156-171):
+ *   dX[row] = rstd (g - mean(g) - xhat mean(g xhat)), g = dY gamma, xhat = (X - mean) rstd (statistics recomputed);
+ *   dgamma[c] += sum_rows dY xhat, dbeta[c] += sum_rows dY  (the caller zeroes dgamma / dbeta; atomics).
+ *   D in {128, 256}; pointers 16-byte aligned, leading dims multiples of 4. */
+int tb_layernorm_bwd(const float* X, int ldx, const float* gamma, const float* dY, int lddy, float* dX, int lddx,
+                     float* dgamma, float* dbeta, int M, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Training path (BASELINE config 4): gradients of the layers above and the differentiable
+ * part of the closed loop. Reference: pl_modules/waymo_motion.py:313-385 (training_step body), autograd through
+ * modules/mlp.py:69, transformer_rpe.py:175-245, polyline_encoder.py:50-53, utils/dynamics.py:66-141,237-274,
+ * utils/rewards.py:35-85, models/metrics/loss.py:9-37, models/metrics/training.py:76-160.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Weight gradient of Y = X W^T + b:  dW[n,k] += sum_m dY[m,n] X[m,k],  db[n] += sum_m dY[m,n]  (db may be NULL).
+ * fp32 FFMA, split over M with fp32 atomics: dW (ld lddw) / db are ACCUMULATED (the caller zero-fills them once and
+ * may collect every use of a shared weight in the same buffer). The data gradient dX = dY W is tb_linear with W^T. */
+int tb_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, int M, int N, int K, float* dW, int lddw,
+                    float* db, void* stream);
+
+/* Backward of a tb_linear epilogue: out[m,n] = dY[m,n] where the row is in neither mask and (Y == NULL or Y[m,n] > 0),
+ * else 0. Y is the epilogue's own output (ReLU and pre/post row masks all leave zeros there). */
+int tb_grad_mask(const float* dY, int lddy, const float* Y, int ldy, const uint8_t* mask_a, const uint8_t* mask_b, int M,
+                 int N, float* out, int ldo, void* stream);
+
+/* out[g, :] = sum of the L consecutive rows of group g of X: gradient of a grouped bias (tb_linear bias_group). */
+int tb_group_sum(const float* X, int ldx, int G, int L, int N, float* out, int ldo, void* stream);
+
+/* Backward of tb_pointnet_pool modes 1 / 2 (x.amax over the valid rows of a group, polyline_encoder.py:52,
+ * utils/pooling.py:38): dX[row, c] = dOut[g, c] (+ dOut[g, C + c] in mode 2) on the first valid row attaining the
+ * maximum, 0 elsewhere (ties only occur at ReLU zeros, where the ReLU backward drops the gradient). */
+int tb_pointnet_pool_bwd(const float* X, int ldx, const uint8_t* invalid, int G, int L, int C, int mode,
+                         const float* dOut, int ldo, float* dX, int lddx, void* stream);
+
+/* Imitation loss of a recorded closed-loop rollout and its gradient w.r.t. the action-head outputs of every step.
+ * The policy inputs are detached in training (waymo_motion.py:158-161), so the chain through time is the state
+ * recurrence only (dynamics.py:84-141, MultiPathPP :237-274; teacher-forced / spawned rows are replaced by the ground
+ * truth, which cuts the chain). One thread per (rollout-scene, agent).
+ *   act [T, B*A, 6] action-head outputs (pre-tanh; (veh, ped, cyc) x (acc, yaw rate)); pred_valid [B*A, T] u8 as
+ *   recorded by tb_dyn_step; pose0 / motion0 [B*A, 3] state at time 0; gt_* [B/sc_div, A, n_gt(, 3)]; tf_mask as
+ *   tb_dyn_step; loss_mask [B*A] u8 or NULL (relevant-agent mask, training.py:93-98); step_start: first counted
+ *   buffer index (training.py:99-101); weights of rewards.py:62-70 (SmoothL1 position / speed, 0.5 (1 - cos) heading).
+ * fwd: state_in [T, B*A, 4] (16-byte aligned) <- (x, y, yaw, speed) before every step; out[0] += sum of the weighted
+ *   errors, out[1] += number of counted entries (caller zero-fills; loss = -w_diffbar_reward * (-out[0]) / out[1]).
+ * bwd: d_act [T, B*A, 6] <- g_out[0] * d out[0] / d act (every element written). */
+int tb_il_loss_fwd(const float* act, const uint8_t* ag_type, const float* max_acc, const float* max_yaw_rate, float dt,
+                   const uint8_t* pred_valid, const float* pose0, const float* motion0, const uint8_t* gt_valid,
+                   const float* gt_pose, const float* gt_motion, const uint8_t* tf_mask, const uint8_t* loss_mask,
+                   int n_gt, int sc_div, int B, int A, int T, int step_start, float w_pos, float w_rot, float w_spd,
+                   float* state_in, float* out, void* stream);
+int tb_il_loss_bwd(const float* act, const uint8_t* ag_type, const float* max_acc, const float* max_yaw_rate, float dt,
+                   const uint8_t* pred_valid, const uint8_t* gt_valid, const float* gt_pose, const float* gt_motion,
+                   const uint8_t* tf_mask, const uint8_t* loss_mask, int n_gt, int sc_div, int B, int A, int T,
+                   int step_start, float w_pos, float w_rot, float w_spd, const float* state_in, const float* g_out,
+                   float* d_act, void* stream);
+
+/* Traffic-light state NLL of all steps (waymo_motion.py:270-277, traffic_light.py:284-286, training.py:155-160):
+ * -log_softmax(clamp(logits, -3, 3))[argmax gt] over valid lights and steps s < n_gt.
+ *   logits [T, n, 5] (step s at index s - 1), tl_invalid [n] u8, gt_tl [n, n_gt, 5] u8.
+ * out != NULL: out[0] += sum, out[1] += count. d_logits != NULL: d_logits <- g_out[0] * d out[0] / d logits. */
+int tb_tl_nll(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt_tl, int n_gt, int n, int T, float* out,
+              const float* g_out, float* d_logits, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * PointNet pooling step over groups of L consecutive rows — modules/polyline_encoder.py:50-53 and
  * utils/pooling.py:18-19,38. X rows have 2*C columns; the left C columns hold relu(Linear(x)).

@@ -74,6 +74,75 @@ layernorm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__
   }
 }
 
+// ---- LayerNorm backward (training path): dx = rstd (g - mean(g) - xhat mean(g xhat)) with
+// g = dy gamma, xhat = (x - mean) rstd; dgamma += sum_rows dy xhat, dbeta += sum_rows dy. One warp per row (statistics
+// recomputed from x: cheaper than storing them), the parameter gradients reduced per CTA in shared memory and added to
+// the (caller-zeroed) global accumulators with one atomic per CTA and column.
+template <int D>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ gamma, const float* __restrict__ dY,
+                     int lddy, float* __restrict__ dX, int lddx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     int M, int rows_per_cta) {
+  constexpr int NV = D / 32;
+  __shared__ float s_g[D], s_b[D];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) { s_g[i] = 0.f; s_b[i] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ag[NV], ab[NV], gm[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { ag[i] = 0.f; ab[i] = 0.f; gm[i] = __ldg(gamma + lane * NV + i); }
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, M);
+  for (int row = r0 + warp; row < r1; row += 8) {
+    float x[NV], dy[NV];
+    const float* xp = X + (size_t)row * ldx + lane * NV;
+    const float* dp = dY + (size_t)row * lddy + lane * NV;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(xp + i), b = *reinterpret_cast<const float4*>(dp + i);
+      x[i] = a.x; x[i + 1] = a.y; x[i + 2] = a.z; x[i + 3] = a.w;
+      dy[i] = b.x; dy[i + 1] = b.y; dy[i + 2] = b.z; dy[i + 3] = b.w;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += x[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(TB_FULL_MASK, s, o);
+    const float mean = s * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { x[i] -= mean; q = fmaf(x[i], x[i], q); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(TB_FULL_MASK, q, o);
+    const float rstd = 1.f / sqrtf(q * (1.f / D) + 1e-5f);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      x[i] *= rstd;  // xhat
+      ag[i] = fmaf(dy[i], x[i], ag[i]);
+      ab[i] += dy[i];
+      dy[i] *= gm[i];  // g
+      sg += dy[i];
+      sgx = fmaf(dy[i], x[i], sgx);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      sg += __shfl_xor_sync(TB_FULL_MASK, sg, o);
+      sgx += __shfl_xor_sync(TB_FULL_MASK, sgx, o);
+    }
+    sg *= 1.f / D; sgx *= 1.f / D;
+    float* op = dX + (size_t)row * lddx + lane * NV;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4)
+      *reinterpret_cast<float4*>(op + i) =
+          make_float4(rstd * (dy[i] - sg - x[i] * sgx), rstd * (dy[i + 1] - sg - x[i + 1] * sgx),
+                      rstd * (dy[i + 2] - sg - x[i + 2] * sgx), rstd * (dy[i + 3] - sg - x[i + 3] * sgx));
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { atomicAdd(&s_g[lane * NV + i], ag[i]); atomicAdd(&s_b[lane * NV + i], ab[i]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) { atomicAdd(dgamma + i, s_g[i]); atomicAdd(dbeta + i, s_b[i]); }
+}
+
 // ---- PointNet pooling (polyline_encoder.py:50-53, pooling.py:18-19,38): one warp per group of L rows.
 // mode 0: right half <- max over valid rows of left half (broadcast to valid rows); invalid rows <- 0.
 // mode 1: out[g] <- max over valid rows of all C2 columns (0 if none valid); mode 2: same, written twice
@@ -184,6 +253,21 @@ extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const f
   else if (D == 128) layernorm_kernel<128, false><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
   else if (out_h) layernorm_kernel<256, true><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
   else layernorm_kernel<256, false><<<grid, 256, 0, st>>>(X, ldx, gamma, beta, Y, ldy, M, relu);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+extern "C" int tb_layernorm_bwd(const float* X, int ldx, const float* gamma, const float* dY, int lddy, float* dX, int lddx,
+                                float* dgamma, float* dbeta, int M, int D, void* stream) {
+  if (!X || !gamma || !dY || !dX || !dgamma || !dbeta) return TB_ERR_NULL;
+  if (M <= 0 || ldx < D || lddy < D || lddx < D) return TB_ERR_BAD_SHAPE;
+  if (D != 128 && D != 256) return TB_ERR_UNSUPPORTED;
+  if ((ldx | lddy | lddx) & 3 || !tb_aligned16(X) || !tb_aligned16(dY) || !tb_aligned16(dX)) return TB_ERR_MISALIGNED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows_per_cta = 256;  // 32 rows per warp: amortises the per-CTA parameter-gradient reduction
+  const int grid = (M + rows_per_cta - 1) / rows_per_cta;
+  if (D == 128) layernorm_bwd_kernel<128><<<grid, 256, 0, st>>>(X, ldx, gamma, dY, lddy, dX, lddx, dgamma, dbeta, M, rows_per_cta);
+  else layernorm_bwd_kernel<256><<<grid, 256, 0, st>>>(X, ldx, gamma, dY, lddy, dX, lddx, dgamma, dbeta, M, rows_per_cta);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

@@ -23,13 +23,19 @@ from . import ops
 H = 4
 
 
-def fuse_attention(P: Dict[str, Tensor], prefix: str, d: int, n_head: int = H) -> Dict[str, Tensor]:
+def fuse_attention(P: Dict[str, Tensor], prefix: str, d: int, n_head: int = H, differentiable: bool = False
+                   ) -> Dict[str, Tensor]:
     """attention_rpe.py:35-41,92-97,147-161,180-186 -> packed projections.
     in-proj rows: [ q*s (d) | u*s (H*d_rpe) | k (d) | v (d) ],  s = log2(e)/sqrt(d_head)
         u_h = W_rk,h^T q_h  =>  W_u[h] = W_rk,h^T W_q,h ,  b_u[h] = W_rk,h^T b_q,h
     out-proj columns: [ W_o (d) | W_o[:,h] W_rv,h (H*d_rpe) ],  bias b_o + W_o b_rv
-    (the logit constant q_h.b_rk,h is softmax-invariant and dropped)."""
-    f64 = lambda k: P[f"{prefix}.{k}"].detach().double().cpu()  # noqa: E731
+    (the logit constant q_h.b_rk,h is softmax-invariant and dropped).
+    `differentiable` (training path): the same re-packing with torch ops on the parameters' device, so autograd maps the
+    gradients of the packed matrices back onto the reference's parameters (b_rk gets none: it cancels in the softmax)."""
+    if differentiable:
+        f64 = lambda k: P[f"{prefix}.{k}"].double()  # noqa: E731
+    else:
+        f64 = lambda k: P[f"{prefix}.{k}"].detach().double().cpu()  # noqa: E731
     w_in, b_in = f64("in_proj_weight"), f64("in_proj_bias")
     w_o, b_o = f64("out_proj_weight"), f64("out_proj_bias")
     w_r, b_r = f64("linear_rpe.weight"), f64("linear_rpe.bias")
@@ -224,6 +230,10 @@ class HotPathModel:
 
     def _attend(self, fa, proj, B, S, kv0, T0, div0, K0, knn, kv1=None, T1=0, div1=1, K1=0):
         d = self.d
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (proj, kv0, kv1)):
+            from . import autograd as AG  # training path: differentiable core (tb_knarpe_attn_bwd)
+            return AG.knarpe_attn(proj[:, :d + H * d], kv0, T0, div0, K0, knn["idx"], knn["inv"], knn["rel"],
+                                  self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1)
         return ops.knarpe_attn(proj[:, :d], proj[:, d:d + H * d], kv0, T0, div0, K0, knn["idx"], knn["inv"],
                                knn.get("rel"), self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1,
                                emb=knn.get("emb"), fast_trig=self.precision == 1, interleaved=self.kv_il,
@@ -453,9 +463,9 @@ class HotPathModel:
                            for i in range(len(kv))], n_sc=n_sc, n_tl=n_tl)
 
     def tl_forward(self, hist_tl: Tensor, d_step: Tensor, tl: dict, out_feat: Optional[Tensor] = None,
-                   out_logits: Optional[Tensor] = None):
+                   out_logits: Optional[Tensor] = None, with_logits: bool = True):
         """TrafficLightEncoder.forward (traffic_light.py:210-240) + TrafficLightStatePredictor (:270-286, pre-clamp).
-        hist_tl [Bt, n_tl, W, 5] u8 ring."""
+        hist_tl [Bt, n_tl, W, 5] u8 ring. `with_logits=False`: tokens only (the latent encoders' TL branch)."""
         from . import lib as L
         Bt, n_tl, W, d = tl["n_sc"], tl["n_tl"], self.W, self.d
         M = Bt * n_tl * W
@@ -472,7 +482,11 @@ class HotPathModel:
         tok = self.tf_stack("tl_encoder.tf_tl2tlmp.layers", nl, "dec_cross_attn", tok,                  # :231-240
                             lambda i: ((flat_inv, Bt, n_tl, tl["knn_self"], tl["cross"][i]),
                                        dict(out=out_feat if i == nl - 1 else None)))
-        logits = self.mlp(tok, "tl_state_predictor.mlp", (0, 2, 4), False, out=out_logits)            # :284
+        if not with_logits:
+            return tok, None
+        # training: the state predictor reads detached tokens (traffic_light.py:279-280, detach_tl_feature)
+        tok_in = tok.detach() if getattr(self, "detach_tl_feature", False) else tok
+        logits = self.mlp(tok_in, "tl_state_predictor.mlp", (0, 2, 4), False, out=out_logits)         # :284
         return tok, logits
 
     # ------------------------------------------------------------------------------------------ agents (per step)

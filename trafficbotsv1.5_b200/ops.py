@@ -125,7 +125,11 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False,
            precision: int = 0, bias_group: int = 0, out_h: Optional[Tensor] = None, col_h: int = 0) -> Tensor:
     """Y = epilogue(X W^T + b) on 2-D row-strided views (see tb_linear). With `out_h` (float16 [M, N - col_h]) the
     columns >= col_h go there instead (tensor-core mode only) and `out` holds the first col_h columns
-    (returned; None when col_h == 0)."""
+    (returned; None when col_h == 0). Inputs that require grad route to the differentiable form (autograd.linear)."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, w, b, res)):
+        from . import autograd as AG
+        assert out_h is None, "the training path keeps fp32 activations"
+        return AG.linear(x, w, b, relu, mask_pre, res, mask_post, out, precision, bias_group)
     in_dt = torch.float16 if precision == 2 else torch.float32  # precision 2: fp16 activations x fp16 weights
     assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.dtype == in_dt and w.dtype == in_dt, \
         (x.dtype, w.dtype, precision)
@@ -176,6 +180,10 @@ def linear_ln(x: Tensor, w: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Te
 
 def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, out: Optional[Tensor] = None, relu: bool = False,
               out_dtype: torch.dtype = torch.float32) -> Tensor:
+    if torch.is_grad_enabled() and (x.requires_grad or gamma.requires_grad or beta.requires_grad):
+        from . import autograd as AG
+        assert out_dtype == torch.float32, "the training path keeps fp32 activations"
+        return AG.layernorm(x, gamma, beta, relu, out)
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
     M, D = x.shape
     if out is None:
@@ -190,6 +198,9 @@ def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, out: Optional[Tensor] = No
 def pointnet_pool(x: Tensor, invalid: Tensor, G: int, Lg: int, mode: int) -> Optional[Tensor]:
     """x [G*L, C2] modified in place (mode 0) / max-pooled over valid rows to [G, C2] (mode 1) or [G, 2*C2] = [m|m]
     (mode 2)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        from . import autograd as AG
+        return AG.pointnet_pool(x, invalid, G, Lg, mode)
     assert x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == G * Lg
     C2 = x.shape[1]
     out = torch.empty(G, C2 * mode, dtype=torch.float32, device=x.device) if mode else None

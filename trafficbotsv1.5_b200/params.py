@@ -92,8 +92,34 @@ def navi_predictor_shapes(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
     return s
 
 
-def init_params(cfg: dict, seed: int = 0, bias_scale: float = 1.0, with_navi_predictor: bool = False
-                ) -> Dict[str, torch.Tensor]:
+def latent_post_shapes(cfg: dict) -> "OrderedDict[str, Tuple[int, ...]]":
+    """`latent_encoder.{tl,ag}_encoder_post.*` + `latent_encoder.latent_dist_post.*` (LatentEncoder with
+    share_post_prior_encoders False and a std_gaus prior, latent_encoder.py:27-54,124-190): the posterior's own
+    traffic-light and agent encoders over the down-sampled ground truth (window (time_step_gt + 1) // rate + 1 = 19
+    steps) and the diag-Gaussian head. Used by the training step only."""
+    d = cfg["hidden_dim"]
+    rate = cfg["latent_encoder"]["temporal_down_sample_rate"]
+    n = cfg["time_step_gt"] + 1
+    W = n // rate + 1 if rate > 1 else n
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    tp, ap = "latent_encoder.tl_encoder_post", "latent_encoder.ag_encoder_post"
+    _mlp(s, f"{tp}.input_encoder.mlp", [cfg["tl_state_dim"] + W] + [d] * 3, (0, 2, 4))
+    for i in range(3):
+        _mlp(s, f"{tp}.temp_encoder.mlp_layers.{i}", [d, d // 2], (0,))
+    for i in range(cfg["tl_encoder"]["n_layer_tf"]):
+        _tf_layer(s, f"{tp}.tf_tl2tlmp.layers.{i}", d, d, True)
+    _mlp(s, f"{ap}.input_encoder.mlp", [cfg["ag_attr_dim"] + cfg["ag_motion_dim"] + W] + [d // 2] * 3, (0, 2, 4))
+    for i in range(3):
+        _mlp(s, f"{ap}.temp_encoder.mlp_layers.{i}", [d, d // 2], (0,))
+    for i in range(cfg["ag_encoder"]["n_layer_tf"]):
+        _tf_layer(s, f"{ap}.tf_ag2agmptl.layers.{i}", d, d, True)
+    _mlp(s, "latent_encoder.latent_dist_post.mlp_mean", [d, d, d, cfg["latent_encoder"]["latent_dim"]], (0, 2, 4))
+    s["latent_encoder.latent_dist_post.log_std"] = (cfg["latent_encoder"]["latent_dim"],)
+    return s
+
+
+def init_params(cfg: dict, seed: int = 0, bias_scale: float = 1.0, with_navi_predictor: bool = False,
+                with_latent_post: bool = False) -> Dict[str, torch.Tensor]:
     """Seeded random init (CPU generator, fp32): Linear-style U(+-1/sqrt(fan_in)) for matrices and
     biases (so attention biases are exercised, unlike the reference's zero init, attention_rpe.py:50-56),
     LayerNorm gamma 1+0.1N / beta 0.1N, log_std -2 (action_head.py:48-50). `navi_predictor.*` tensors are drawn
@@ -105,6 +131,11 @@ def init_params(cfg: dict, seed: int = 0, bias_scale: float = 1.0, with_navi_pre
         P.update(rand_like_state_dict({k.replace("fc_layers.1.", "fc_layers.1.norm.").replace("fc_layers.4.", "fc_layers.4.norm."): v
                                        for k, v in navi_predictor_shapes(cfg).items()}, seed + 7919))
         P = {k.replace(".norm.", "."): v for k, v in P.items()}
+    if with_latent_post:
+        lp = rand_like_state_dict(latent_post_shapes(cfg), seed + 104729)
+        lp["latent_encoder.latent_dist_post.log_std"] = torch.full_like(lp["latent_encoder.latent_dist_post.log_std"],
+                                                                        float(cfg["latent_encoder"]["latent_post"]["log_std"]))
+        P.update(lp)
     for k, shp in shapes.items():
         if "log_std" in k:
             P[k] = torch.full(shp, -2.0)

@@ -90,6 +90,51 @@ def _one_scene(n_ag, n_mp, n_tl, n_node, n_hist, seed, boundary, n_rollout, late
     return d
 
 
+def make_train_batch(n_sc: int, n_ag: int = 128, n_mp: int = 1024, n_tl: int = 40, n_step: int = 91, n_hist: int = 11,
+                     seed: int = 3000, p_forcing_agent: float = 0.3, **kw) -> Dict[str, torch.Tensor]:
+    """The dict `SceneCentricPreProcessing` hands to `training_step` (scene_centric.py:39-147): "gt/*" = the whole
+    n_step-long track (here: speed ramps and constant yaw rates, so position, heading and speed errors are all
+    exercised), "sc/*" = its first n_hist steps, plus the step's random draws as inputs — "tf/forcing_agent"
+    (teacher_forcing.py:87-92), "ag_latent_eps" (rsample noise of the latent), "gt/ag_navi" a destination that passes
+    the type masks of the destination classifier (navigation.py:265-278), "ref/ag_role"."""
+    b = make_scene_batch(n_sc=n_sc, n_ag=n_ag, n_mp=n_mp, n_tl=n_tl, n_hist=n_step, seed=seed, n_rollout=1, **kw)
+    g = torch.Generator().manual_seed(seed + 31)
+    t = torch.arange(n_step, dtype=torch.float32) * 0.1
+    spd0 = b["sc/ag_motion"][:, :, 0, 0]
+    acc = (torch.rand(n_sc, n_ag, generator=g) * 2 - 1) * 1.0
+    yr = (torch.rand(n_sc, n_ag, generator=g) * 2 - 1) * 0.2
+    spd = (spd0[..., None] + acc[..., None] * t).clamp(min=0.0)
+    yaw = b["sc/ag_pose"][:, :, 0, 2][..., None] + yr[..., None] * t
+    vel = torch.stack([yaw.cos(), yaw.sin()], -1) * spd[..., None]
+    xy = b["sc/ag_pose"][:, :, :1, :2] + torch.cumsum(vel * 0.1, 2) - vel[:, :, :1] * 0.1
+    b["gt/ag_pose"] = torch.cat([xy, yaw[..., None]], -1).contiguous()
+    b["gt/ag_motion"] = torch.stack([spd, acc[..., None].expand(-1, -1, n_step), yr[..., None].expand(-1, -1, n_step)],
+                                    -1).contiguous()
+    gv = b["sc/ag_valid"].clone()
+    drop = torch.rand(n_sc, n_ag, generator=g) < 0.15   # tracks that end early
+    t_end = torch.randint(n_hist + 5, n_step, (n_sc, n_ag), generator=g)
+    gv &= ~(drop[..., None] & (torch.arange(n_step)[None, None] >= t_end[..., None]))
+    b["gt/ag_valid"] = gv
+    b["gt/tl_state"] = b["sc/tl_state"]
+    for k in ("ag_valid", "ag_pose", "ag_motion"):
+        b[f"sc/{k}"] = b[f"gt/{k}"][:, :, :n_hist].contiguous()
+    b["sc/tl_state"] = b["gt/tl_state"][:, :, :n_hist].contiguous()
+    # a destination that survives the type masks: FREEWAY..ROAD_EDGE_BOUNDARY minus the per-type exclusions
+    mt, at = b["ref/mp_type"], b["ref/ag_type"]
+    ok = (mt[:, :, :5].any(-1) & b["sc/mp_valid"][:, :, 0])[:, None] & ~(
+        (at[:, :, [0]] & mt[:, :, 3][:, None]) | (at[:, :, [1]] & mt[:, :, :4].any(-1)[:, None])
+        | (at[:, :, [2]] & mt[:, :, :3].any(-1)[:, None]))
+    w = ok.float() + 1e-9
+    b["gt/ag_navi"] = torch.multinomial(w.view(n_sc * n_ag, -1), 1, generator=g).view(n_sc, n_ag)
+    b["agent/dest"] = b["gt/ag_navi"]
+    b["tf/forcing_agent"] = torch.rand(n_sc, n_ag, generator=g) < p_forcing_agent
+    b["ag_latent_eps"] = torch.randn(n_sc, n_ag, b["ag_latent"].shape[-1], generator=g)
+    b["ref/ag_role"] = torch.rand(n_sc, n_ag, 3, generator=g) < 0.2
+    b["ag_navi_valid"] = gv.any(-1)
+    b["ag_latent_valid"] = gv.any(-1)
+    return b
+
+
 def make_rule_scene_batch(n_sc: int, n_ag: int = 48, n_mp: int = 96, n_tl: int = 40, seed: int = 5000,
                           boundary: float = 80.0, scale: float = 0.4, **kw) -> Dict[str, torch.Tensor]:
     """A `make_scene_batch` scene edited so that the two rare TrafficRuleChecker events fire often
