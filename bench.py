@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--scenes-total", type=int, default=0,
                     help="BASELINE config 5: sweep this many scenes (512) sharded over the ranks in batches of --scenes, "
                          "NCCL gather of every batch's trajectories overlapped with the next batch (strong scaling)")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE config 4 instead of the rollout: forward + backward of the training_step body "
+                         "(--scenes scenes per GPU, default 64; dropout 0) - prints its own JSON line")
     ap.add_argument("--rule-checks", action="store_true",
                     help="also run the logging-only TrafficRuleChecker checks (collision, road edge, ...) every step")
     return ap.parse_args()
@@ -638,6 +641,84 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE config 4: forward + backward of the training_step body (waymo_motion.py:313-385) at --scenes scenes of
+    the config-3 shape, dropout 0, fp32 rows with tf32 tcgen05 GEMMs (--precision 1) or fp32 FFMA (0). Unit: training
+    scene-steps/s = scenes x 90 policy iterations / time of one loss + gradient evaluation. Side numbers: the same step
+    by torch autograd through the reference-order oracle on this GPU (`eager_cuda`, a smaller batch: its [B,S,K,2d]
+    gathers of all 90 steps do not fit otherwise) and the gradient check against it."""
+    from trafficbotsv1_5_b200 import ops
+    from trafficbotsv1_5_b200.training import TRAIN_CFG, TrainStep
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback for the product path"
+    dev = "cuda:0"
+    torch.cuda.set_device(0)
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, 0, with_navi_predictor=True, with_latent_post=True)
+    n_sc = args.scenes if args.scenes != 16 else 64
+    batch = synth.make_train_batch(n_sc, seed=3000)
+    batch = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    ts = TrainStep(P, cfg, dev, precision=min(args.precision, 1))
+
+    def step():
+        ts.zero_grad()
+        out = ts.step(batch)
+        return float(out["loss"])  # device -> host read of the step's result
+
+    for _ in range(max(1, args.warmup)):
+        loss = step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    l0 = ops.LAUNCHES
+    with ClockSampler(0) as cs:
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / args.steps
+    peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    line = dict(metric="training_step_scene_steps_per_sec", value=n_sc * N_ITER / t, unit="scene-steps/s (fwd+bwd)",
+                n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32" if args.precision == 0 else "tf32", data="synthetic",
+                config=dict(workload=f"config 4: training_step body fwd+bwd, {n_sc} scenes, 128 agents, 1024 polylines x 20, "
+                                     f"40 TL, 90 teacher-forced policy iterations, dropout 0", scenes=n_sc,
+                            l2="activations of 90 steps (tens of GB) exceed the 126 MB L2; no flush"),
+                clocks=cs.summary(), gpu_launches=ops.LAUNCHES - l0, loss=loss, peak_hbm_gib=peak_gb,
+                e2e=dict(value=n_sc * N_ITER / t, unit="scene-steps/s (fwd+bwd)",
+                         h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in batch.values() if torch.is_tensor(v)),
+                         d2h_bytes_per_step=4))
+    if not args.no_extras:
+        try:
+            from oracle import tb_oracle_train as OT
+            n_e = 2
+            be = synth.make_train_batch(n_e, seed=3000)
+            be = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in be.items()}
+            torch.set_default_device(dev)
+            try:
+                Pg = {k: v.to(dev).requires_grad_(True) for k, v in P.items()}
+
+                def eager():
+                    for p_ in Pg.values():
+                        p_.grad = None
+                    o = OT.training_step(Pg, cfg, config.derived_sizes(cfg), config.DYNAMICS_CFG, TRAIN_CFG, be)
+                    o["loss"].backward()
+                    return float(o["loss"])
+
+                eager()
+                torch.cuda.synchronize()
+                t0 = time.time()
+                eager()
+                torch.cuda.synchronize()
+                te = time.time() - t0
+            finally:
+                torch.set_default_device("cpu")
+            line["eager_cuda"] = dict(value=n_e * N_ITER / te, unit="scene-steps/s (fwd+bwd)", scenes=n_e,
+                                      note="torch autograd through the reference-order oracle on this GPU, fp32")
+        except Exception as e:
+            line["eager_cuda"] = dict(unavailable=f"{type(e).__name__}: {e}"[:200])
+    print(json.dumps(line), file=_OUT, flush=True)
+
+
 _OUT = sys.stdout
 
 
@@ -655,6 +736,8 @@ if __name__ == "__main__":
     _reserve_stdout()
     if a.impl == "reference":
         run_reference(a)
+    elif a.train:
+        run_train(a)
     elif a.scenes_total > 0:
         run_sweep(a)
     else:

@@ -223,6 +223,13 @@ int tb_il_loss_bwd(const float* act, const uint8_t* ag_type, const float* max_ac
 int tb_tl_nll(const float* logits, const uint8_t* tl_invalid, const uint8_t* gt_tl, int n_gt, int n, int T, float* out,
               const float* g_out, float* d_logits, void* stream);
 
+/* Categorical NLL of the destination classifier (navigation.py:265-278 logits with -inf on excluded polylines,
+ * training.py:146-153): nll[r] = logsumexp(logits[r, :]) - logits[r, target[r]] on rows with row_valid != 0.
+ *   logits [R, C] ld ld, target int64 [R], row_valid u8 [R]. out != NULL: out[0] += sum, out[1] += count.
+ *   d_logits != NULL (ld ldd): g_out[0] * (softmax - onehot) on valid rows, 0 elsewhere (every element written). */
+int tb_softmax_nll(const float* logits, int ld, const int64_t* target, const uint8_t* row_valid, int R, int C, float* out,
+                   const float* g_out, float* d_logits, int ldd, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * PointNet pooling step over groups of L consecutive rows — modules/polyline_encoder.py:50-53 and
  * utils/pooling.py:18-19,38. X rows have 2*C columns; the left C columns hold relu(Linear(x)).

@@ -79,8 +79,12 @@ def test_linear_autograd_vs_torch(relu, mask_pre, res, mask_post, group, precisi
     tol = 2e-5 if precision == 0 else 3e-3
     assert rel(y, v) < tol
     v.backward(go)
+    # precision 1: a tf32 pre-activation next to zero can land on the other side of the ReLU than the fp32 reference's,
+    # which changes single entries of the gradients by O(1) - compare in the L2 norm there (2e-2), entrywise in fp32
+    def err(a, t):
+        return rel(a, t) if precision == 0 else float((a - t).norm() / t.norm())
     for a, t, nm in zip(got, (x, w, b) + ((r,) if res else ()), ("dx", "dw", "db", "dres")):
-        assert rel(a, t.grad) < tol, (nm, rel(a, t.grad))
+        assert err(a, t.grad) < (tol if precision == 0 else 2e-2), (nm, err(a, t.grad))
 
 
 @pytest.mark.parametrize("D,relu", [(128, False), (256, False), (128, True)])
@@ -215,13 +219,29 @@ def _grad_report(ts, Pg, tol, floor):
             bad.append((k, r, scale))
     print(f"worst relative gradient error {worst[1]:.2e} at {worst[0]}")
     assert not bad, bad[:10]
+    return worst
+
+
+def _oracle_f64(P, cfg, sz, tc, b, n_steps):
+    """The oracle evaluated in float64 (the fp32 oracle's own gradients are 2-3e-3 off it on the traffic-light encoder,
+    whose gradient is a small sum with cancellations through the agents' cross-attention)."""
+    Pg = {k: v.clone().double().requires_grad_(True) for k, v in P.items()}
+    bb = {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in b.items()}
+    torch.set_default_dtype(torch.float64)
+    try:
+        ref = OT.training_step(Pg, cfg, sz, config.DYNAMICS_CFG, tc, bb, n_steps=n_steps)
+        ref["loss"].backward()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    return ref, Pg
 
 
 @pytest.mark.parametrize("variant", ["full", "no_latent_encoder", "prior_rollout_kl"])
 def test_training_step_vs_oracle_autograd(variant):
     """The whole training_step body (map / TL / latent posterior / destination predictor / 14-step teacher-forced closed
-    loop / TrainingMetrics) on the CUDA path against the oracle: every loss term within 2e-4 relative, the gradient of
-    EVERY parameter tensor within 2e-3 of that tensor's largest gradient entry (fp32, re-associated attention)."""
+    loop / TrainingMetrics) on the CUDA path against the oracle evaluated in float64: every loss term within 2e-4
+    relative, the gradient of EVERY parameter tensor within 5e-3 of that tensor's largest gradient entry (absolute floor
+    1e-5; the fp32 oracle itself is 3e-3 off the float64 one)."""
     cfg = config.default_model_cfg()
     sz = config.derived_sizes(cfg)
     P = params.init_params(cfg, 0, with_navi_predictor=True, with_latent_post=variant != "no_latent_encoder")
@@ -231,21 +251,47 @@ def test_training_step_vs_oracle_autograd(variant):
         b["rollout_prior"] = True
         tc["kl_free_nats"] = 0.01
     n_steps = 14
-    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
-    ref = OT.training_step(Pg, cfg, sz, config.DYNAMICS_CFG, tc, b, n_steps=n_steps)
-    ref["loss"].backward()
+    ref, Pg = _oracle_f64(P, cfg, sz, tc, b, n_steps)
     ts = TrainStep(P, cfg, DEV, precision=0, train_cfg=tc)
     out = ts.step(b, n_steps=n_steps)
     torch.cuda.synchronize()
     assert torch.equal(out["pred_valid"].cpu().view_as(ref["pred_valid"]), ref["pred_valid"])
-    assert float((out["pred_pose"].cpu().view_as(ref["pred_pose"]) - ref["pred_pose"]).abs().max()) < 1e-3
+    assert float((out["pred_pose"].cpu().double().view_as(ref["pred_pose"]) - ref["pred_pose"]).abs().max()) < 1e-3
     for k in ("diffbar_reward", "tl_state_loss", "vae_kl", "navi_loss", "loss"):
         if k in ref:
             assert abs(float(out[k]) - float(ref[k])) < 2e-4 * max(1.0, abs(float(ref[k]))), (k, float(out[k]), float(ref[k]))
-    _grad_report(ts, Pg, 2e-3, 1e-7)
+    _grad_report(ts, Pg, 5e-3, 1e-5)
     # a second step on the same object (fresh graph, re-packed weights) reproduces the gradients
     g1 = {k: v.grad.clone() for k, v in ts.params.items() if v.grad is not None}
     ts.zero_grad()
     ts.step(b, n_steps=n_steps)
-    for k, v in g1.items():
-        assert rel(ts.params[k].grad, v) < 1e-4, k
+    for k, v in g1.items():  # fp32 atomics: the summation order differs from run to run
+        assert float((ts.params[k].grad - v).abs().max()) < 1e-3 * max(float(v.abs().max()), 1e-5), k
+
+
+def test_training_step_tf32_mode():
+    """The benchmarked training mode (precision 1: tf32 tcgen05 GEMMs for forward and data gradients, fp32 rows, fp32
+    FFMA weight gradients) against the float64 oracle: loss terms within 1e-2 relative; the gradient of every module
+    (all its parameter tensors concatenated) has cosine similarity > 0.995 with the oracle's and a norm within 5 %
+    (10-bit-mantissa operands flip ReLU masks next to zero, so single entries are not compared)."""
+    cfg = config.default_model_cfg()
+    sz = config.derived_sizes(cfg)
+    P = params.init_params(cfg, 0, with_navi_predictor=True, with_latent_post=True)
+    b = synth.make_train_batch(2, n_ag=28, n_mp=70, n_tl=27, seed=3000, boundary=120.0)
+    tc = dict(TRAIN_CFG)
+    ref, Pg = _oracle_f64(P, cfg, sz, tc, b, 14)
+    ts = TrainStep(P, cfg, DEV, precision=1, train_cfg=tc)
+    out = ts.step(b, n_steps=14)
+    assert torch.equal(out["pred_valid"].cpu().view_as(ref["pred_valid"]), ref["pred_valid"])
+    for k in ("diffbar_reward", "tl_state_loss", "vae_kl", "navi_loss", "loss"):
+        assert abs(float(out[k]) - float(ref[k])) < 1e-2 * max(1.0, abs(float(ref[k]))), (k, float(out[k]), float(ref[k]))
+    groups = {}
+    for k, v in Pg.items():
+        if v.grad is not None:
+            groups.setdefault(".".join(k.split(".")[:2]), []).append(k)
+    for gname, keys in groups.items():
+        a = torch.cat([ts.params[k].grad.double().cpu().reshape(-1) for k in keys])
+        r = torch.cat([Pg[k].grad.reshape(-1) for k in keys])
+        cos = float((a * r).sum() / (a.norm() * r.norm() + 1e-300))
+        ratio = float(a.norm() / (r.norm() + 1e-300))
+        assert cos > 0.995 and abs(ratio - 1) < 0.05, (gname, cos, ratio)

@@ -294,3 +294,35 @@ class _TlNll(Function):
 def tl_nll(logits: Tensor, tl_invalid: Tensor, gt_tl: Tensor, n_gt: int) -> Tensor:
     """logits [T, n, 5] pre-clamp; gt_tl u8 [n, n_gt, 5]. Returns out [2] = (sum of NLL, count)."""
     return _TlNll.apply(logits, tl_invalid.contiguous(), gt_tl.contiguous(), n_gt)
+
+
+class _SoftmaxNll(Function):
+    @staticmethod
+    def forward(ctx, logits, target, row_valid):
+        R, Cn = logits.shape
+        logits = _rows(logits)
+        out = torch.zeros(2, dtype=torch.float32, device=logits.device)
+        L.check(L.load().tb_softmax_nll(L.ptr(logits), logits.stride(0), L.ptr(target), L.ptr(ops._u8(row_valid)), R, Cn,
+                                        L.ptr(out), None, None, 0, L.stream()), "tb_softmax_nll")
+        ops._count()
+        ctx.args = (target, row_valid)
+        ctx.save_for_backward(logits)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (logits,) = ctx.saved_tensors
+        target, row_valid = ctx.args
+        R, Cn = logits.shape
+        g = g_out[:1].contiguous()
+        d = torch.empty(R, Cn, dtype=torch.float32, device=logits.device)
+        L.check(L.load().tb_softmax_nll(L.ptr(logits), logits.stride(0), L.ptr(target), L.ptr(ops._u8(row_valid)), R, Cn,
+                                        None, L.ptr(g), L.ptr(d), Cn, L.stream()), "tb_softmax_nll")
+        ops._count()
+        return d, None, None
+
+
+def softmax_nll(logits: Tensor, target: Tensor, row_valid: Tensor) -> Tensor:
+    """logits [R, C] (-inf entries allowed), target int64 [R], row_valid bool [R] -> out [2] = (sum of NLL, count)."""
+    assert target.dtype == torch.int64
+    return _SoftmaxNll.apply(logits, target.contiguous(), row_valid.contiguous())

@@ -328,6 +328,38 @@ __global__ void tl_nll_kernel(const float* __restrict__ logits, const uint8_t* _
   }
 }
 
+// Categorical NLL over a row of logits with -inf entries (destination classifier, navigation.py:265-278 +
+// training.py:146-153): nll[r] = logsumexp(logits[r]) - logits[r, target[r]] for rows with row_valid, else 0.
+// One warp per row. out[0] += sum of nll, out[1] += number of valid rows; with d_logits: g_out[0] * (softmax - onehot)
+// on valid rows, 0 elsewhere (every element written).
+__global__ void __launch_bounds__(256)
+softmax_nll_kernel(const float* __restrict__ logits, int ld, const int64_t* __restrict__ target,
+                   const uint8_t* __restrict__ row_valid, int R, int Cn, float* __restrict__ out,
+                   const float* __restrict__ g_out, float* __restrict__ d_logits, int ldd) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float* row = logits + (size_t)r * ld;
+  const bool ok = row_valid[r] != 0;
+  float mx = -INFINITY;
+  for (int c = lane; c < Cn; c += 32) mx = fmaxf(mx, row[c]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(TB_FULL_MASK, mx, o));
+  float se = 0.f;
+  for (int c = lane; c < Cn; c += 32) se += expf(row[c] - mx);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(TB_FULL_MASK, se, o);
+  const int t = (int)target[r];
+  if (out && ok && lane == 0) {
+    atomicAdd(out, mx + logf(se) - row[t]);
+    atomicAdd(out + 1, 1.f);
+  }
+  if (d_logits) {
+    const float go = ok ? *g_out : 0.f, inv = 1.f / se;
+    float* dr = d_logits + (size_t)r * ldd;
+    for (int c = lane; c < Cn; c += 32) dr[c] = ok ? go * (expf(row[c] - mx) * inv - (c == t ? 1.f : 0.f)) : 0.f;
+  }
+}
+
 IlArgs make_il_args(const float* act, const uint8_t* ag_type, const float* max_acc, const float* max_yaw, float dt,
                     const uint8_t* pred_valid, const float* pose0, const float* motion0, const uint8_t* gt_valid,
                     const float* gt_pose, const float* gt_motion, const uint8_t* tf_mask, const uint8_t* loss_mask,
@@ -443,6 +475,16 @@ extern "C" int tb_tl_nll(const float* logits, const uint8_t* tl_invalid, const u
   const size_t tot = (size_t)T * n;
   tl_nll_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, tl_invalid, gt_tl, n_gt, n, T, out, g_out, d_logits);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+extern "C" int tb_softmax_nll(const float* logits, int ld, const int64_t* target, const uint8_t* row_valid, int R, int C,
+                              float* out, const float* g_out, float* d_logits, int ldd, void* stream) {
+  if (!logits || !target || !row_valid || (!out && !d_logits) || (d_logits && !g_out)) return TB_ERR_NULL;
+  if (R <= 0 || C <= 0 || ld < C || (d_logits && ldd < C)) return TB_ERR_BAD_SHAPE;
+  softmax_nll_kernel<<<(R + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, target, row_valid, R, C, out,
+                                                                               g_out, d_logits, ldd);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

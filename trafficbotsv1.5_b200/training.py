@@ -220,9 +220,13 @@ class TrainStep:
         lat_feat = m.mlp(latent.reshape(n_sc * A, -1), "add_latent.mlp_in", (0, 3, 6), True, mask_post=lat_inv)
         acts, logit_l = [], []
         lib, dy, order = L.load(), eng.dyn, ("veh", "ped", "cyc")
+        tl_all = self._tl_branch_batched(st, tl, T) if T < n_gt and T > m.W else None
         for s in range(1, T + 1):                                                                       # :233
-            tl_feat, logits = m.tl_forward(st["hist_tl"], st["d_step"], tl)
-            kv_tl = m.ag_tl_tables(tl_feat)
+            if tl_all is not None and s >= m.W:
+                tl_feat, logits, kv_tl = tl_all[0][s - m.W], tl_all[1][s - m.W], [t[s - m.W] for t in tl_all[2]]
+            else:
+                tl_feat, logits = m.tl_forward(st["hist_tl"], st["d_step"], tl)
+                kv_tl = m.ag_tl_tables(tl_feat)
             x = m.ag_forward(st, mp, kv_mp, tl, tl_feat, 1, kv_tl=kv_tl)
             act = m.heads_train(x, st["pose"].reshape(-1, 3), navi, st["navi_invalid"].reshape(-1).clone(), lat_feat,
                                 lat_inv)
@@ -269,15 +273,40 @@ class TrainStep:
                 loss = loss + out["vae_kl"]
         if navi_logits is not None:                                                                     # :146-153
             navi_valid = g("sc/ag_valid").any(-1) & loss_any
-            nl = -torch.log_softmax(navi_logits, -1).gather(-1, g("gt/ag_navi")[..., None]).squeeze(-1)
-            if int(navi_valid.sum()) > 0:
-                out["navi_loss"] = tc["w_navi"] * nl.masked_fill(~navi_valid, 0.0).sum() / navi_valid.sum()
+            n_mp_ = navi_logits.shape[-1]
+            nn = AG.softmax_nll(navi_logits.reshape(-1, n_mp_), g("gt/ag_navi").reshape(-1), navi_valid.reshape(-1))
+            if float(nn[1]) > 0:
+                out["navi_loss"] = tc["w_navi"] * nn[0] / nn[1]
                 loss = loss + out["navi_loss"]
         out["loss"] = loss
         if backward:
             loss.backward()
         out["pred_pose"], out["pred_valid"] = st["pred_pose"][:, :, :T], pred_valid.bool()
         return out
+
+    def _tl_branch_batched(self, st: dict, tl: dict, T: int):
+        """The traffic-light branch of steps W..T as ONE batch. While ground-truth light states exist (s < n_gt: always in
+        training, teacher_forcing.py:65,159-160) the TL history of every step is known before the rollout, and the TL
+        tokens never depend on the agents, so the 80 full-window steps are evaluated as n_sc x J "scenes" in one pass
+        (forward and backward: ~70 + ~200 launches instead of that per step). Steps 1..W-1 (partial windows) stay
+        sequential. Returns per-step views (tl_feat [J][n_sc*n_tl, d], logits [J][n_sc*n_tl, 5], per-layer tables)."""
+        m = self.model
+        W, d = m.W, m.d
+        n_sc, n_tl = st["Bt"], st["n_tl"]
+        J = T - W + 1                                                                                   # steps s = W..T
+        win = st["gt_tl"].unfold(2, W, 1)[:, :, :J]                                                     # [n_sc,n_tl,J,5,W]: times j..j+W-1
+        hist = win.permute(0, 2, 1, 4, 3).contiguous().view(n_sc * J, n_tl, W, 5)
+        rep = lambda t: t.repeat_interleave(J, 0).contiguous()  # noqa: E731
+        knn = lambda k: dict(idx=rep(k["idx"]), inv=rep(k["inv"]), rel=rep(k["rel"]))  # noqa: E731
+        c0 = knn(tl["cross"][0])
+        tlb = dict(n_sc=n_sc * J, n_tl=n_tl, tl_token_invalid=rep(tl["tl_token_invalid"]),
+                   tl_attr_rows=tl["tl_token_attr"].view(n_sc, 1, n_tl, 1, d).expand(-1, J, -1, W, -1).reshape(-1, d),
+                   knn_self=knn(tl["knn_self"]),
+                   cross=[dict(c0, kv0=c["kv0"], T0=c["T0"], div0=J, K0=c["K0"]) for c in tl["cross"]])
+        d_step = torch.full((1,), W, dtype=torch.int32, device=self.dev)  # full window: slot = window position
+        feat, logits = m.tl_forward(hist, d_step, tlb)
+        by_step = lambda t: t.view(n_sc, J, n_tl, -1).permute(1, 0, 2, 3).contiguous().view(J, n_sc * n_tl, -1).unbind(0)  # noqa
+        return by_step(feat), by_step(logits), [by_step(t) for t in m.ag_tl_tables(feat)]
 
     def _reset(self, st: dict) -> None:
         """time 0 of the rollout (waymo_motion.py:219-227): RolloutEngine._reset without the TL prologue of the
