@@ -676,6 +676,7 @@ def run_train(args):
         e1.record()
         torch.cuda.synchronize()
     t = e0.elapsed_time(e1) * 1e-3 / args.steps
+    phases = ts.timings_ms()
     peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
     line = dict(metric="training_step_scene_steps_per_sec", value=n_sc * N_ITER / t, unit="scene-steps/s (fwd+bwd)",
                 n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True,
@@ -683,7 +684,7 @@ def run_train(args):
                 config=dict(workload=f"config 4: training_step body fwd+bwd, {n_sc} scenes, 128 agents, 1024 polylines x 20, "
                                      f"40 TL, 90 teacher-forced policy iterations, dropout 0", scenes=n_sc,
                             l2="activations of 90 steps (tens of GB) exceed the 126 MB L2; no flush"),
-                clocks=cs.summary(), gpu_launches=ops.LAUNCHES - l0, loss=loss, peak_hbm_gib=peak_gb,
+                clocks=cs.summary(), gpu_launches=ops.LAUNCHES - l0, loss=loss, peak_hbm_gib=peak_gb, phases_ms=phases,
                 e2e=dict(value=n_sc * N_ITER / t, unit="scene-steps/s (fwd+bwd)",
                          h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in batch.values() if torch.is_tensor(v)),
                          d2h_bytes_per_step=4))

@@ -267,6 +267,13 @@ int tb_ag_featurize(const uint8_t* hist_valid, const float* hist_pose, const flo
                     const float* ag_attr, const int* d_step, const float* freq_xy, int B, int A, int W,
                     float* tok_pose, uint8_t* tok_invalid, uint8_t* row_invalid, float* attr_out, int lda,
                     float* pe_out, int ldpe, void* stream);
+/* Same with one loop counter per batch row: s(b) = d_step[b * step_stride] (step_stride 0 = the shared scalar above).
+ * The training path evaluates the policy of ALL steps of a recorded rollout as one batch of scenes x steps rows
+ * (waymo_motion.py:158-161: the policy inputs are detached, so every step's forward / backward is independent). */
+int tb_ag_featurize_ex(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
+                       const float* ag_attr, const int* d_step, int step_stride, const float* freq_xy, int B, int A,
+                       int W, float* tok_pose, uint8_t* tok_invalid, uint8_t* row_invalid, float* attr_out, int lda,
+                       float* pe_out, int ldpe, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fused agent history encoder of the tensor-core mode — agent_encoder.py:130-162 in one kernel (one warp per agent):
@@ -288,6 +295,9 @@ int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose, const floa
  *   hist_tl [B,TL,W,5] u8 one-hot, tl_invalid [B,TL]; out rows [B*TL*W,16] (ld lda), row_invalid [B,TL,W]. */
 int tb_tl_featurize(const uint8_t* hist_tl, const uint8_t* tl_invalid, const int* d_step, int B, int TL, int W,
                     float* attr_out, int lda, uint8_t* row_invalid, void* stream);
+/* Same with one loop counter per batch row, s(b) = d_step[b * step_stride] (see tb_ag_featurize_ex). */
+int tb_tl_featurize_ex(const uint8_t* hist_tl, const uint8_t* tl_invalid, const int* d_step, int step_stride, int B,
+                       int TL, int W, float* attr_out, int lda, uint8_t* row_invalid, void* stream);
 
 /* Agent dynamics + closed-loop bookkeeping for one step — utils/dynamics.py:66-141,166-204 (update_ag,
  * override_ag, disable_ag, disable_navi), MultiPathPP :237-274, teacher_forcing.py:126-147,

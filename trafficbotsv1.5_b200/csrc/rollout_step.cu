@@ -21,12 +21,13 @@ __device__ __forceinline__ float pe_component64(int c, float x, float y, float w
 __global__ void __launch_bounds__(256)
 ag_featurize_kernel(const uint8_t* __restrict__ hist_valid, const float* __restrict__ hist_pose,
                     const float* __restrict__ hist_motion, const float* __restrict__ ag_attr,
-                    const int* __restrict__ d_step, const float* __restrict__ freq_xy, int n_ag_tot, int W,
-                    float* __restrict__ tok_pose, uint8_t* __restrict__ tok_invalid, uint8_t* __restrict__ row_invalid,
-                    float* __restrict__ attr_out, int lda, float* __restrict__ pe_out, int ldpe) {
+                    const int* __restrict__ d_step, int step_stride, int A, const float* __restrict__ freq_xy,
+                    int n_ag_tot, int W, float* __restrict__ tok_pose, uint8_t* __restrict__ tok_invalid,
+                    uint8_t* __restrict__ row_invalid, float* __restrict__ attr_out, int lda,
+                    float* __restrict__ pe_out, int ldpe) {
   const int ba = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (ba >= n_ag_tot) return;
-  const int s = *d_step;
+  const int s = d_step[step_stride ? (size_t)(ba / A) * step_stride : 0];  // one step for all, or one per batch row
   const int n_step = min(s, W);
   const size_t hb = (size_t)ba * W;
   // window position wp in [W-n_step, W) <-> time t = s - W + wp, slot t % W ; wp < W-n_step: absent
@@ -75,13 +76,13 @@ ag_featurize_kernel(const uint8_t* __restrict__ hist_valid, const float* __restr
 }
 
 __global__ void tl_featurize_kernel(const uint8_t* __restrict__ hist_tl, const uint8_t* __restrict__ tl_invalid,
-                                    const int* __restrict__ d_step, int n_rows, int W, float* __restrict__ attr_out,
-                                    int lda, uint8_t* __restrict__ row_invalid) {
+                                    const int* __restrict__ d_step, int step_stride, int TL, int n_rows, int W,
+                                    float* __restrict__ attr_out, int lda, uint8_t* __restrict__ row_invalid) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (b*TL + tl)*W + wp
   if (i >= n_rows) return;
-  const int s = *d_step;
-  const int n_step = min(s, W);
   const int wp = i % W, bt = i / W;
+  const int s = d_step[step_stride ? (size_t)(bt / TL) * step_stride : 0];
+  const int n_step = min(s, W);
   const bool present = wp >= W - n_step;
   const int slot = present ? (s - W + wp) % W : 0;
   float* ar = attr_out + (size_t)i * lda;
@@ -264,32 +265,46 @@ __global__ void action_mean_kernel(const float* __restrict__ act_branch, const u
 
 }  // namespace
 
-extern "C" int tb_ag_featurize(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
-                               const float* ag_attr, const int* d_step, const float* freq_xy, int B, int A, int W,
-                               float* tok_pose, uint8_t* tok_invalid, uint8_t* row_invalid, float* attr_out, int lda,
-                               float* pe_out, int ldpe, void* stream) {
+extern "C" int tb_ag_featurize_ex(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
+                                  const float* ag_attr, const int* d_step, int step_stride, const float* freq_xy, int B,
+                                  int A, int W, float* tok_pose, uint8_t* tok_invalid, uint8_t* row_invalid,
+                                  float* attr_out, int lda, float* pe_out, int ldpe, void* stream) {
   if (!hist_valid || !hist_pose || !hist_motion || !ag_attr || !d_step || !freq_xy || !tok_pose || !tok_invalid)
     return TB_ERR_NULL;
   const bool rows = attr_out || pe_out || row_invalid;  // all three or none (none: token pose / validity only)
   if (rows && (!row_invalid || !attr_out || !pe_out)) return TB_ERR_NULL;
-  if (B <= 0 || A <= 0 || W <= 0 || W > 23 || (rows && (lda < 9 + W || ldpe < 64))) return TB_ERR_BAD_SHAPE;
+  if (B <= 0 || A <= 0 || W <= 0 || W > 23 || step_stride < 0 || (rows && (lda < 9 + W || ldpe < 64)))
+    return TB_ERR_BAD_SHAPE;
   const int n = B * A;
   ag_featurize_kernel<<<(n + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      hist_valid, hist_pose, hist_motion, ag_attr, d_step, freq_xy, n, W, tok_pose, tok_invalid, row_invalid, attr_out,
-      lda, pe_out, ldpe);
+      hist_valid, hist_pose, hist_motion, ag_attr, d_step, step_stride, A, freq_xy, n, W, tok_pose, tok_invalid,
+      row_invalid, attr_out, lda, pe_out, ldpe);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+extern "C" int tb_ag_featurize(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
+                               const float* ag_attr, const int* d_step, const float* freq_xy, int B, int A, int W,
+                               float* tok_pose, uint8_t* tok_invalid, uint8_t* row_invalid, float* attr_out, int lda,
+                               float* pe_out, int ldpe, void* stream) {
+  return tb_ag_featurize_ex(hist_valid, hist_pose, hist_motion, ag_attr, d_step, 0, freq_xy, B, A, W, tok_pose,
+                            tok_invalid, row_invalid, attr_out, lda, pe_out, ldpe, stream);
+}
+
+extern "C" int tb_tl_featurize_ex(const uint8_t* hist_tl, const uint8_t* tl_invalid, const int* d_step, int step_stride,
+                                  int B, int TL, int W, float* attr_out, int lda, uint8_t* row_invalid, void* stream) {
+  if (!hist_tl || !tl_invalid || !d_step || !attr_out || !row_invalid) return TB_ERR_NULL;
+  if (B <= 0 || TL <= 0 || W <= 0 || lda < 5 + W || step_stride < 0) return TB_ERR_BAD_SHAPE;
+  const int n = B * TL * W;
+  tl_featurize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      hist_tl, tl_invalid, d_step, step_stride, TL, n, W, attr_out, lda, row_invalid);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }
 
 extern "C" int tb_tl_featurize(const uint8_t* hist_tl, const uint8_t* tl_invalid, const int* d_step, int B, int TL,
                                int W, float* attr_out, int lda, uint8_t* row_invalid, void* stream) {
-  if (!hist_tl || !tl_invalid || !d_step || !attr_out || !row_invalid) return TB_ERR_NULL;
-  if (B <= 0 || TL <= 0 || W <= 0 || lda < 5 + W) return TB_ERR_BAD_SHAPE;
-  const int n = B * TL * W;
-  tl_featurize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist_tl, tl_invalid, d_step, n, W,
-                                                                                    attr_out, lda, row_invalid);
-  TB_CHECK_LAUNCH();
-  return TB_OK;
+  return tb_tl_featurize_ex(hist_tl, tl_invalid, d_step, 0, B, TL, W, attr_out, lda, row_invalid, stream);
 }
 
 extern "C" int tb_dyn_step_ex(const float* act_branch, const uint8_t* ag_type, const float* max_acc,

@@ -471,9 +471,10 @@ class HotPathModel:
         M = Bt * n_tl * W
         attr = torch.empty(M, 5 + W, device=self.dev)
         row_inv = torch.empty(M, dtype=torch.bool, device=self.dev)
-        L.check(L.load().tb_tl_featurize(L.ptr(hist_tl), L.ptr(ops._u8(tl["tl_token_invalid"])), L.ptr(d_step), Bt,
-                                         n_tl, W, L.ptr(attr), 5 + W, L.ptr(ops._u8(row_inv)), L.stream()),
-                "tb_tl_featurize")
+        # d_step: the shared loop counter, or (training: all steps of a rollout as one batch) one counter per batch row
+        L.check(L.load().tb_tl_featurize_ex(L.ptr(hist_tl), L.ptr(ops._u8(tl["tl_token_invalid"])), L.ptr(d_step),
+                                            1 if d_step.numel() > 1 else 0, Bt, n_tl, W, L.ptr(attr), 5 + W,
+                                            L.ptr(ops._u8(row_inv)), L.stream()), "tb_tl_featurize_ex")
         ops._count()
         x = self.mlp(attr, "tl_encoder.input_encoder.mlp", (0, 2, 4), False, res=tl["tl_attr_rows"])  # :176-180
         tok = self.pointnet(x, row_inv, Bt * n_tl, W, "tl_encoder.temp_encoder")                      # :228
@@ -499,11 +500,13 @@ class HotPathModel:
 
     def ag_forward(self, st: dict, mp: Dict[str, Tensor], kv_mp: list, tl: dict, tl_feat: Tensor, R: int,
                    out: Optional[Tensor] = None, aux: Optional[dict] = None, before_tl=None, knn_stream=None,
-                   knn_stream2=None, kv_tl: Optional[list] = None) -> Tensor:
+                   knn_stream2=None, kv_tl: Optional[list] = None, tl_pose_div: Optional[int] = None) -> Tensor:
         """AgentEncoder._forward_hptr (agent_encoder.py:114-178). `st` holds the rollout state rings
         (engine.RolloutState); batch b uses map / traffic-light tables of scene b // R. `kv_tl`: per-layer K|V tables
         of the traffic-light tokens when the caller already built them (on the TL stream); `before_tl` is then
-        only called right before the first cross-attention instead of before layer 0."""
+        only called right before the first cross-attention instead of before layer 0. `tl_pose_div`: batch rows per row
+        of tl["tl_token_pose"] when that differs from the rows per TL table (training: per-scene poses, per-step tables);
+        `st["d_step"]` may hold one loop counter per batch row (tb_ag_featurize_ex)."""
         from . import lib as L
         sz, d, W = self.sz, self.d, self.W
         B, A = st["B"], st["A"]
@@ -515,6 +518,8 @@ class HotPathModel:
         fused = self.kv_half and W <= 16 and d == 128  # tensor-core mode: one fused kernel for the history encoder
         hist = (L.ptr(st["hist_valid"]), L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]), L.ptr(st["ag_attr"]),
                 L.ptr(st["d_step"]), L.ptr(self.freq_ag), B, A, W)
+        per_row_step = st["d_step"].numel() > 1
+        assert not (fused and per_row_step)
         if fused:  # token pose / validity first (tiny), so that the KNN selects start beside the fused encoder
             L.check(L.load().tb_ag_featurize(*hist, L.ptr(tok_pose), L.ptr(ops._u8(tok_inv)), None, None, 0, None, 0,
                                              L.stream()), "tb_ag_featurize")
@@ -522,8 +527,9 @@ class HotPathModel:
             row_inv = torch.empty(MW, dtype=torch.bool, device=self.dev)
             attr = torch.empty(MW, 9 + W, device=self.dev)
             x = torch.empty(MW, d, device=self.dev)
-            L.check(L.load().tb_ag_featurize(*hist, L.ptr(tok_pose), L.ptr(ops._u8(tok_inv)), L.ptr(ops._u8(row_inv)),
-                                             L.ptr(attr), 9 + W, L.ptr(x[:, d // 2:]), d, L.stream()), "tb_ag_featurize")
+            L.check(L.load().tb_ag_featurize_ex(*hist[:5], 1 if per_row_step else 0, *hist[5:], L.ptr(tok_pose),
+                                                L.ptr(ops._u8(tok_inv)), L.ptr(ops._u8(row_inv)), L.ptr(attr), 9 + W,
+                                                L.ptr(x[:, d // 2:]), d, L.stream()), "tb_ag_featurize_ex")
         ops._count()
         # re-localisation + KNN re-selection, every step (:321-387). The three selects only need the token poses, so
         # they run on a forked stream beside the (bandwidth-bound) input MLP + PointNet projections.
@@ -547,7 +553,7 @@ class HotPathModel:
                 ops.knn_select(tok_pose, tok_inv, mp["mp_token_pose"], mp["mp_token_invalid"], sz["k_ag2mp"],
                                sz["dl_ag"], tgt_div=R, out=(cidx, cinv, crel), koff=0)
             ops.knn_select(tok_pose, tok_inv, tl["tl_token_pose"], tl["tl_token_invalid"], sz["k_ag2tl"], sz["dl_ag"],
-                           tgt_div=tl_div, out=(cidx, cinv, crel), koff=sz["k_ag2mp"],
+                           tgt_div=tl_pose_div or tl_div, out=(cidx, cinv, crel), koff=sz["k_ag2mp"],
                            row_state=st.get("knn_state_tl"))  # static targets too: bracketed bisection
 
         # The agent->agent list is needed by the first self-attention, the agent->map/TL lists only by the first

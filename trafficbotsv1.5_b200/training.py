@@ -61,6 +61,9 @@ class TrainModel(HotPathModel):
             self.act_b0 = torch.cat([P[f"action_head.mlp_mean.{t}.fc_layers.0.bias"] for t in range(3)], 0)
             self.act_w4 = torch.block_diag(*[P[f"action_head.mlp_mean.{t}.fc_layers.4.weight"] for t in range(3)])
             self.act_b4 = torch.cat([P[f"action_head.mlp_mean.{t}.fc_layers.4.bias"] for t in range(3)], 0)
+        self.drop_caches()
+
+    def drop_caches(self) -> None:
         for c in ("_pn_split", "_w_il", "_w_half", "_chain", "_ag_front"):
             if hasattr(self, c):
                 delattr(self, c)
@@ -166,6 +169,7 @@ class TrainStep:
         assert T <= self.T
         self._batch = batch
         g = lambda k: batch[k].to(dev)  # noqa: E731
+        self._marks = [("start", self._event())]
         m.refresh()
         if self.post is not None:
             self.post.refresh()
@@ -196,6 +200,7 @@ class TrainStep:
         if self.has_navi:
             navi_logits = m.navi_predictor(g("sc/ag_valid"), g("sc/ag_attr"), g("sc/ag_motion"), g("sc/ag_pose"), mp_det,
                                            g("ref/ag_type"), g("ref/mp_type"))
+        self._mark("scene_encoders")
         # ! rollout state (Dynamics.init / TeacherForcing.init, dynamics.py:29-64, teacher_forcing.py:51-92)
         n_mp, n_node = batch["sc/mp_valid"].shape[1:]
         rb = {"sc/ag_valid": batch["gt/ag_valid"], "sc/ag_pose": batch["gt/ag_pose"], "sc/ag_motion": batch["gt/ag_motion"],
@@ -218,47 +223,78 @@ class TrainStep:
         navi = m.navi_static(mp_det, st["dest_idx"], 1)                                                 # navigation.py:65-71
         lat_inv = (~lat_valid).reshape(-1).contiguous()
         lat_feat = m.mlp(latent.reshape(n_sc * A, -1), "add_latent.mlp_in", (0, 3, 6), True, mask_post=lat_inv)
-        acts, logit_l = [], []
+        if not T < n_gt:
+            raise NotImplementedError("the training rollout needs ground-truth traffic-light states for every step "
+                                      "(teacher_forcing.py:65): time_step_end < number of gt steps")
+        # ---- pass 1 (no grad): advance the closed loop and record the state every policy step sees. The policy inputs
+        # are detached (waymo_motion.py:158-161), so this IS the rollout; nothing of it is kept for the backward.
+        W = m.W
+        tidx, tmask = self._ring_index(T, W)
+        tlb, hist_tl_all = self._tl_batch(st, tl, T, tidx, tmask)
+        d_rows = torch.arange(1, T + 1, dtype=torch.int32, device=dev).repeat(n_sc).contiguous()        # step of row (sc, s)
+        by_step = lambda t, n: t.view(n_sc, T, n, -1).permute(1, 0, 2, 3).contiguous().view(T, n_sc * n, -1)  # noqa: E731
+        S_valid = torch.empty(T, n_sc, A, dtype=torch.uint8, device=dev)
+        S_pose, S_motion = torch.empty(T, n_sc, A, 3, device=dev), torch.empty(T, n_sc, A, 3, device=dev)
+        N_inv = torch.empty(T, n_sc, A, dtype=torch.bool, device=dev)
         lib, dy, order = L.load(), eng.dyn, ("veh", "ped", "cyc")
-        tl_all = self._tl_branch_batched(st, tl, T) if T < n_gt and T > m.W else None
-        for s in range(1, T + 1):                                                                       # :233
-            if tl_all is not None and s >= m.W:
-                tl_feat, logits, kv_tl = tl_all[0][s - m.W], tl_all[1][s - m.W], [t[s - m.W] for t in tl_all[2]]
-            else:
-                tl_feat, logits = m.tl_forward(st["hist_tl"], st["d_step"], tl)
-                kv_tl = m.ag_tl_tables(tl_feat)
-            x = m.ag_forward(st, mp, kv_mp, tl, tl_feat, 1, kv_tl=kv_tl)
-            act = m.heads_train(x, st["pose"].reshape(-1, 3), navi, st["navi_invalid"].reshape(-1).clone(), lat_feat,
-                                lat_inv)
-            acts.append(act)
-            logit_l.append(logits)
-            L.check(lib.tb_tl_step_ex(L.ptr(logits.detach()), L.ptr(ops._u8(tl["tl_token_invalid"])), L.ptr(st["gt_tl"]),
-                                      st["n_gt"], L.ptr(st["d_step"]), st["Bt"], st["n_tl"], m.W, self.T,
-                                      L.ptr(st["hist_tl"]), L.ptr(st["tl_out"]), None, L.stream()), "tb_tl_step_ex")
-            L.check(lib.tb_dyn_step_ex(
-                L.ptr(act.detach()), L.ptr(st["ag_type"]), ops.host_f3([dy[k]["max_acc"] for k in order]),
-                ops.host_f3([dy[k]["max_yaw_rate"] for k in order]), dy["dt"], L.ptr(st["valid"]), L.ptr(st["disabled"]),
-                L.ptr(ops._u8(st["navi_invalid"])), L.ptr(st["dest_reached"]), L.ptr(st["pose"]), L.ptr(st["motion"]),
-                L.ptr(st["gt_valid"]), L.ptr(st["gt_pose"]), L.ptr(st["gt_motion"]), L.ptr(st["tf_mask"]), st["n_gt"], 1,
-                L.ptr(st["boundary"]), L.ptr(st["dest_idx"]), L.ptr(st["mp_pos"]), L.ptr(st["mp_dirn"]),
-                L.ptr(st["mp_node_invalid"]), L.ptr(st["mp_kind"]), st["n_mp"], st["n_node"], eng.thresh_lane,
-                eng.thresh_edge, eng.cos_rot, L.ptr(st["d_step"]), st["B"], st["A"], m.W, self.T, L.ptr(st["hist_valid"]),
-                L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]), L.ptr(st["pred_valid"]), L.ptr(st["pred_pose"]),
-                L.ptr(st["pred_motion"]), None, None, L.stream()), "tb_dyn_step_ex")
-            L.check(lib.tb_step_advance(L.ptr(st["d_step"]), L.stream()), "tb_step_advance")
-            ops._count(3)
+        with torch.no_grad():
+            tl_feat_ng, logits_ng = m.tl_forward(hist_tl_all, d_rows, tlb)                              # all steps at once
+            kv_tl_ng = [by_step(t, n_tl) for t in m.ag_tl_tables(tl_feat_ng)]
+            tl_feat_ng, logits_ng = by_step(tl_feat_ng, n_tl), by_step(logits_ng, n_tl)
+            for s in range(1, T + 1):                                                                   # :233
+                S_valid[s - 1], S_pose[s - 1], S_motion[s - 1] = st["valid"], st["pose"], st["motion"]
+                N_inv[s - 1] = st["navi_invalid"]
+                x = m.ag_forward(st, mp, kv_mp, tl, tl_feat_ng[s - 1], 1, kv_tl=[t[s - 1] for t in kv_tl_ng])
+                act = m.heads_train(x, st["pose"].reshape(-1, 3), navi, st["navi_invalid"].reshape(-1), lat_feat, lat_inv)
+                L.check(lib.tb_tl_step_ex(L.ptr(logits_ng[s - 1]), L.ptr(ops._u8(tl["tl_token_invalid"])),
+                                          L.ptr(st["gt_tl"]), st["n_gt"], L.ptr(st["d_step"]), st["Bt"], st["n_tl"], W,
+                                          self.T, L.ptr(st["hist_tl"]), L.ptr(st["tl_out"]), None, L.stream()),
+                        "tb_tl_step_ex")
+                L.check(lib.tb_dyn_step_ex(
+                    L.ptr(act), L.ptr(st["ag_type"]), ops.host_f3([dy[k]["max_acc"] for k in order]),
+                    ops.host_f3([dy[k]["max_yaw_rate"] for k in order]), dy["dt"], L.ptr(st["valid"]),
+                    L.ptr(st["disabled"]), L.ptr(ops._u8(st["navi_invalid"])), L.ptr(st["dest_reached"]), L.ptr(st["pose"]),
+                    L.ptr(st["motion"]), L.ptr(st["gt_valid"]), L.ptr(st["gt_pose"]), L.ptr(st["gt_motion"]),
+                    L.ptr(st["tf_mask"]), st["n_gt"], 1, L.ptr(st["boundary"]), L.ptr(st["dest_idx"]), L.ptr(st["mp_pos"]),
+                    L.ptr(st["mp_dirn"]), L.ptr(st["mp_node_invalid"]), L.ptr(st["mp_kind"]), st["n_mp"], st["n_node"],
+                    eng.thresh_lane, eng.thresh_edge, eng.cos_rot, L.ptr(st["d_step"]), st["B"], st["A"], W, self.T,
+                    L.ptr(st["hist_valid"]), L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]), L.ptr(st["pred_valid"]),
+                    L.ptr(st["pred_pose"]), L.ptr(st["pred_motion"]), None, None, L.stream()), "tb_dyn_step_ex")
+                L.check(lib.tb_step_advance(L.ptr(st["d_step"]), L.stream()), "tb_step_advance")
+                ops._count(3)
+            del tl_feat_ng, logits_ng, kv_tl_ng
+        m.drop_caches()  # derived weights cached during the no-grad pass carry no graph
+        self._mark("rollout")
+        # ---- pass 2 (differentiable): the policy of ALL T steps as one batch of n_sc x T rollout-scenes, row (sc, s).
+        # Every step's input is the recorded state, so forward and backward are ~300 large launches in total instead of
+        # ~270 small ones per step; K|V tables of the map are indexed with div = T, TL tables are per (scene, step).
+        Bq = n_sc * T
+        ring = lambda S: S[tidx]  # noqa: E731  [T, W, n_sc, A, ...]: ring slot k of step s holds time tidx[s-1, k]
+        hv = (ring(S_valid).permute(2, 0, 3, 1) * tmask[None, :, None, :].to(torch.uint8)).contiguous().view(Bq, A, W)
+        hp = ring(S_pose).permute(2, 0, 3, 1, 4).contiguous().view(Bq, A, W, 3)
+        hm = ring(S_motion).permute(2, 0, 3, 1, 4).contiguous().view(Bq, A, W, 3)
+        over_t = lambda t: t.view(n_sc, 1, A, -1).expand(-1, T, -1, -1).reshape(Bq * A, -1)  # noqa: E731
+        stb = dict(B=Bq, A=A, hist_valid=hv, hist_pose=hp, hist_motion=hm, d_step=d_rows,
+                   ag_attr=st["ag_attr"].view(n_sc, 1, A, 6).expand(-1, T, -1, -1).contiguous().view(Bq, A, 6))
+        tl_feat, logits = m.tl_forward(hist_tl_all, d_rows, tlb)
+        x = m.ag_forward(stb, mp, kv_mp, tl, tl_feat, T, kv_tl=m.ag_tl_tables(tl_feat), tl_pose_div=T)
+        navi_b = dict(feat=over_t(navi["feat"]), pose=over_t(navi["pose"]).contiguous())
+        act = m.heads_train(x, S_pose.permute(1, 0, 2, 3).reshape(-1, 3), navi_b, N_inv.permute(1, 0, 2).reshape(-1),
+                            over_t(lat_feat), over_t(lat_inv.view(-1, 1)).reshape(-1))
+        acts = act.view(n_sc, T, A, 6).permute(1, 0, 2, 3).reshape(T, n_sc * A, 6)
+        logit_l = by_step(logits, n_tl)
         # ! losses (training.py:76-189)
         pred_valid = st["pred_valid"][:, :, :T].contiguous()
         rec = dict(B=n_sc, A=A, ag_type=st["ag_type"], pred_valid=pred_valid, pose0=pose0, motion0=motion0,
                    gt_valid=st["gt_valid"], gt_pose=st["gt_pose"], gt_motion=st["gt_motion"], tf_mask=st["tf_mask"],
                    n_gt=n_gt, sc_div=1)
         t0 = tc["step_training_start"]
-        il, _ = AG.il_loss(torch.stack(acts), rec, dy, (tc["w_pos"], tc["w_rot"], tc["w_spd"]), t0)
+        il, _ = AG.il_loss(acts, rec, dy, (tc["w_pos"], tc["w_rot"], tc["w_spd"]), t0)
         loss = torch.zeros((), device=dev)
         if float(il[1]) > 0:                                                                            # :170-181
             out["diffbar_reward"] = -tc["w_diffbar_reward"] * il[0] / il[1]
             loss = loss - out["diffbar_reward"]
-        nll = AG.tl_nll(torch.stack(logit_l), tl["tl_token_invalid"].reshape(-1), st["gt_tl"], n_gt)
+        nll = AG.tl_nll(logit_l, tl["tl_token_invalid"].reshape(-1), st["gt_tl"], n_gt)
         if float(nll[1]) > 0:                                                                           # :186-188
             out["tl_state_loss"] = tc["w_tl_state"] * nll[0] / nll[1]
             loss = loss + out["tl_state_loss"]
@@ -279,34 +315,52 @@ class TrainStep:
                 out["navi_loss"] = tc["w_navi"] * nn[0] / nn[1]
                 loss = loss + out["navi_loss"]
         out["loss"] = loss
+        self._mark("policy_forward_losses")
         if backward:
             loss.backward()
+            self._mark("backward")
         out["pred_pose"], out["pred_valid"] = st["pred_pose"][:, :, :T], pred_valid.bool()
         return out
 
-    def _tl_branch_batched(self, st: dict, tl: dict, T: int):
-        """The traffic-light branch of steps W..T as ONE batch. While ground-truth light states exist (s < n_gt: always in
-        training, teacher_forcing.py:65,159-160) the TL history of every step is known before the rollout, and the TL
-        tokens never depend on the agents, so the 80 full-window steps are evaluated as n_sc x J "scenes" in one pass
-        (forward and backward: ~70 + ~200 launches instead of that per step). Steps 1..W-1 (partial windows) stay
-        sequential. Returns per-step views (tl_feat [J][n_sc*n_tl, d], logits [J][n_sc*n_tl, 5], per-layer tables)."""
+    def _event(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _mark(self, name: str) -> None:
+        self._marks.append((name, self._event()))
+
+    def timings_ms(self) -> Dict[str, float]:
+        """Device time of the phases of the last step() (CUDA events on the current stream; synchronises)."""
+        torch.cuda.synchronize()
+        return {n: self._marks[i][1].elapsed_time(e) for i, (n, e) in enumerate(self._marks[1:])}
+
+    def _ring_index(self, T: int, W: int):
+        """History ring of policy step s (1-based): slot k holds time t = s-1 - ((s-1-k) mod W) when t >= 0
+        (traffic_bots.py:123-143 keeps the last W states; the kernels read slot = time % W). Returns the time index
+        [T, W] (clamped to 0) and its validity mask."""
+        s1 = torch.arange(T, device=self.dev)[:, None]              # s - 1
+        k = torch.arange(W, device=self.dev)[None, :]
+        t = s1 - torch.remainder(s1 - k, W)
+        return t.clamp(min=0), t >= 0
+
+    def _tl_batch(self, st: dict, tl: dict, T: int, tidx: Tensor, tmask: Tensor):
+        """Static TL dict + TL history rings for the batch of n_sc x T rollout-scenes (row (sc, s)). With ground-truth
+        light states for every step (always in training, teacher_forcing.py:65,159-160) the TL history of every step
+        is known before the rollout and the TL tokens never depend on the agents."""
         m = self.model
         W, d = m.W, m.d
         n_sc, n_tl = st["Bt"], st["n_tl"]
-        J = T - W + 1                                                                                   # steps s = W..T
-        win = st["gt_tl"].unfold(2, W, 1)[:, :, :J]                                                     # [n_sc,n_tl,J,5,W]: times j..j+W-1
-        hist = win.permute(0, 2, 1, 4, 3).contiguous().view(n_sc * J, n_tl, W, 5)
-        rep = lambda t: t.repeat_interleave(J, 0).contiguous()  # noqa: E731
+        hist = st["gt_tl"][:, :, tidx]                                                                  # [n_sc,n_tl,T,W,5]
+        hist = (hist.permute(0, 2, 1, 3, 4) * tmask[None, :, None, :, None].to(torch.uint8)).contiguous()
+        rep = lambda t: t.repeat_interleave(T, 0).contiguous()  # noqa: E731
         knn = lambda k: dict(idx=rep(k["idx"]), inv=rep(k["inv"]), rel=rep(k["rel"]))  # noqa: E731
         c0 = knn(tl["cross"][0])
-        tlb = dict(n_sc=n_sc * J, n_tl=n_tl, tl_token_invalid=rep(tl["tl_token_invalid"]),
-                   tl_attr_rows=tl["tl_token_attr"].view(n_sc, 1, n_tl, 1, d).expand(-1, J, -1, W, -1).reshape(-1, d),
+        tlb = dict(n_sc=n_sc * T, n_tl=n_tl, tl_token_invalid=rep(tl["tl_token_invalid"]),
+                   tl_attr_rows=tl["tl_token_attr"].view(n_sc, 1, n_tl, 1, d).expand(-1, T, -1, W, -1).reshape(-1, d),
                    knn_self=knn(tl["knn_self"]),
-                   cross=[dict(c0, kv0=c["kv0"], T0=c["T0"], div0=J, K0=c["K0"]) for c in tl["cross"]])
-        d_step = torch.full((1,), W, dtype=torch.int32, device=self.dev)  # full window: slot = window position
-        feat, logits = m.tl_forward(hist, d_step, tlb)
-        by_step = lambda t: t.view(n_sc, J, n_tl, -1).permute(1, 0, 2, 3).contiguous().view(J, n_sc * n_tl, -1).unbind(0)  # noqa
-        return by_step(feat), by_step(logits), [by_step(t) for t in m.ag_tl_tables(feat)]
+                   cross=[dict(c0, kv0=c["kv0"], T0=c["T0"], div0=T, K0=c["K0"]) for c in tl["cross"]])
+        return tlb, hist.view(n_sc * T, n_tl, W, 5)
 
     def _reset(self, st: dict) -> None:
         """time 0 of the rollout (waymo_motion.py:219-227): RolloutEngine._reset without the TL prologue of the
