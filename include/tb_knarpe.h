@@ -175,10 +175,15 @@ int tb_layernorm_bwd(const float* X, int ldx, const float* gamma, const float* d
  * ------------------------------------------------------------------------------------------------- */
 
 /* Weight gradient of Y = X W^T + b:  dW[n,k] += sum_m dY[m,n] X[m,k],  db[n] += sum_m dY[m,n]  (db may be NULL).
- * fp32 FFMA, split over M with fp32 atomics: dW (ld lddw) / db are ACCUMULATED (the caller zero-fills them once and
- * may collect every use of a shared weight in the same buffer). The data gradient dX = dY W is tb_linear with W^T. */
+ * Split over M with fp32 atomics: dW (ld lddw) / db are ACCUMULATED (the caller zero-fills them once and may collect
+ * every use of a shared weight in the same buffer). precision 0: fp32 FFMA; 1: tcgen05 kind::tf32 with both operands
+ * MN-major straight from the row-major activations via TMA (csrc/wgrad_tc.cu; leading dims multiples of 4 floats and
+ * 16-byte aligned pointers, else the FFMA kernel runs). The data gradient dX = dY W is tb_linear with W^T. */
 int tb_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, int M, int N, int K, float* dW, int lddw,
-                    float* db, void* stream);
+                    float* db, int precision, void* stream);
+
+/* out[n] += sum over the M rows of X[m, n] (bias gradient; out is accumulated with atomics). */
+int tb_colsum(const float* X, int ldx, int M, int N, float* out, void* stream);
 
 /* Backward of a tb_linear epilogue: out[m,n] = dY[m,n] where the row is in neither mask and (Y == NULL or Y[m,n] > 0),
  * else 0. Y is the epilogue's own output (ReLU and pre/post row masks all leave zeros there). */

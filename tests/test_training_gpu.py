@@ -38,9 +38,13 @@ def test_linear_wgrad_vs_torch(M, N, K, strided):
     assert rel(dw, dy.double().t() @ x.double()) < 2e-5
     assert rel(db, dy.double().sum(0)) < 2e-5
     dw2, _ = AG.wgrad(dy, x, False)  # accumulation semantics: a second call into the same buffer doubles it
-    L.check(L.load().tb_linear_wgrad(L.ptr(dy), dy.stride(0), L.ptr(x), x.stride(0), M, N, K, L.ptr(dw2), K, None,
+    L.check(L.load().tb_linear_wgrad(L.ptr(dy), dy.stride(0), L.ptr(x), x.stride(0), M, N, K, L.ptr(dw2), K, None, 0,
                                      L.stream()), "tb_linear_wgrad")
     assert rel(dw2, 2 * (dy.double().t() @ x.double())) < 2e-5
+    # tcgen05 path (precision 1: operands read as tf32 - 10-bit mantissas - fp32 accumulate): 2e-3 of the largest entry
+    dw3, db3 = AG.wgrad(dy, x, True, precision=1)
+    assert rel(dw3, dy.double().t() @ x.double()) < 2e-3
+    assert rel(db3, dy.double().sum(0)) < 2e-5
 
 
 @pytest.mark.parametrize("relu,mask_pre,res,mask_post,group", [(False, False, False, False, 0), (True, False, False, False, 0),

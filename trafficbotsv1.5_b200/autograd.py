@@ -48,13 +48,13 @@ def grad_mask(dy: Tensor, y: Optional[Tensor], mask_a: Optional[Tensor], mask_b:
     return out
 
 
-def wgrad(dv: Tensor, x: Tensor, want_bias: bool) -> Tuple[Tensor, Optional[Tensor]]:
+def wgrad(dv: Tensor, x: Tensor, want_bias: bool, precision: int = 0) -> Tuple[Tensor, Optional[Tensor]]:
     M, N = dv.shape
     K = x.shape[1]
     dw = torch.zeros(N, K, dtype=torch.float32, device=dv.device)
     db = torch.zeros(N, dtype=torch.float32, device=dv.device) if want_bias else None
     L.check(L.load().tb_linear_wgrad(L.ptr(dv), dv.stride(0), L.ptr(x), x.stride(0), M, N, K, L.ptr(dw), K, L.ptr(db),
-                                     L.stream()), "tb_linear_wgrad")
+                                     precision, L.stream()), "tb_linear_wgrad")
     ops._count()
     return dw, db
 
@@ -88,7 +88,7 @@ class _Linear(Function):
         dw = db = None
         if need[1] or (has_b and need[2]):
             plain_bias = has_b and need[2] and not bias_group
-            dw, db = wgrad(dv, x, plain_bias)
+            dw, db = wgrad(dv, x, plain_bias, precision)
             if has_b and need[2] and bias_group:
                 M, N = dv.shape
                 assert M % bias_group == 0

@@ -94,15 +94,40 @@ linear_wgrad_kernel(const float* __restrict__ dY, int lddy, const float* __restr
 // ------------------------------------------------------------------------------------------------ epilogue backward
 // out[m,n] = keep ? dY[m,n] : 0 with keep = !(mask_a[m] | mask_b[m]) && (Y == nullptr || Y[m,n] > 0): the gradient
 // w.r.t. the pre-activation of a tb_linear epilogue (ReLU and row masks; Y is the epilogue's own output).
-__global__ void grad_mask_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y, int ldy,
-                                 const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b, int M, int N,
-                                 float* __restrict__ out, int ldo) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)M * N) return;
-  const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
-  bool keep = !((mask_a && mask_a[m]) || (mask_b && mask_b[m]));
-  if (keep && Y) keep = Y[(size_t)m * ldy + n] > 0.f;
-  out[(size_t)m * ldo + n] = keep ? dY[(size_t)m * lddy + n] : 0.f;
+// blockDim (32, 8): one row per threadIdx.y, 16-byte pieces along the row (VEC) or single floats.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+grad_mask_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y, int ldy,
+                 const uint8_t* __restrict__ mask_a, const uint8_t* __restrict__ mask_b, int M, int N,
+                 float* __restrict__ out, int ldo) {
+  const int m = blockIdx.x * 8 + threadIdx.y;
+  if (m >= M) return;
+  const bool row_keep = !((mask_a && mask_a[m]) || (mask_b && mask_b[m]));
+  const float* dr = dY + (size_t)m * lddy;
+  const float* yr = Y ? Y + (size_t)m * ldy : nullptr;
+  float* orow = out + (size_t)m * ldo;
+  if (VEC) {
+    for (int c = threadIdx.x * 4; c < N; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_keep) {
+        v = *reinterpret_cast<const float4*>(dr + c);
+        if (yr) {
+          const float4 y = *reinterpret_cast<const float4*>(yr + c);
+          if (!(y.x > 0.f)) v.x = 0.f;
+          if (!(y.y > 0.f)) v.y = 0.f;
+          if (!(y.z > 0.f)) v.z = 0.f;
+          if (!(y.w > 0.f)) v.w = 0.f;
+        }
+      }
+      *reinterpret_cast<float4*>(orow + c) = v;
+    }
+  } else {
+    for (int c = threadIdx.x; c < N; c += 32) {
+      bool keep = row_keep;
+      if (keep && yr) keep = yr[c] > 0.f;
+      orow[c] = keep ? dr[c] : 0.f;
+    }
+  }
 }
 
 // out[g,n] = sum over the L rows of group g of X[g*L + l, n] (gradient of a grouped bias row).
@@ -377,10 +402,9 @@ IlArgs make_il_args(const float* act, const uint8_t* ag_type, const float* max_a
 
 }  // namespace
 
-extern "C" int tb_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, int M, int N, int K, float* dW,
-                               int lddw, float* db, void* stream) {
-  if (!dY || !X || !dW) return TB_ERR_NULL;
-  if (M <= 0 || N <= 0 || K <= 0 || lddy < N || ldx < K || lddw < K) return TB_ERR_BAD_SHAPE;
+// fp32 FFMA weight gradient (tb_linear_wgrad precision 0 and the shapes the tcgen05 kernel of wgrad_tc.cu cannot take)
+int tb_linear_wgrad_f32(const float* dY, int lddy, const float* X, int ldx, int M, int N, int K, float* dW, int lddw,
+                        float* db, cudaStream_t st) {
   const int tn = (N + WG_T - 1) / WG_T, tk = (K + WG_T - 1) / WG_T;
   int splits = (148 * 4 + tn * tk - 1) / (tn * tk);
   const int max_splits = (M + 2 * WG_R - 1) / (2 * WG_R);
@@ -392,7 +416,6 @@ extern "C" int tb_linear_wgrad(const float* dY, int lddy, const float* X, int ld
   splits = (M + rows - 1) / rows;
   const dim3 grid(tn, tk, splits);
   const bool vec = ((lddy | ldx) & 3) == 0 && tb_aligned16(dY) && tb_aligned16(X);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (vec) linear_wgrad_kernel<true><<<grid, 256, 0, st>>>(dY, lddy, X, ldx, M, N, K, dW, lddw, db, rows);
   else linear_wgrad_kernel<false><<<grid, 256, 0, st>>>(dY, lddy, X, ldx, M, N, K, dW, lddw, db, rows);
   TB_CHECK_LAUNCH();
@@ -403,9 +426,12 @@ extern "C" int tb_grad_mask(const float* dY, int lddy, const float* Y, int ldy, 
                             const uint8_t* mask_b, int M, int N, float* out, int ldo, void* stream) {
   if (!dY || !out) return TB_ERR_NULL;
   if (M <= 0 || N <= 0 || lddy < N || ldo < N || (Y && ldy < N)) return TB_ERR_BAD_SHAPE;
-  const size_t n = (size_t)M * N;
-  grad_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dY, lddy, Y, ldy, mask_a,
-                                                                                              mask_b, M, N, out, ldo);
+  const bool vec = (N & 3) == 0 && ((lddy | ldo | (Y ? ldy : 0)) & 3) == 0 && tb_aligned16(dY) && tb_aligned16(out) &&
+                   (!Y || tb_aligned16(Y));
+  const dim3 block(32, 8), grid((M + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec) grad_mask_kernel<true><<<grid, block, 0, st>>>(dY, lddy, Y, ldy, mask_a, mask_b, M, N, out, ldo);
+  else grad_mask_kernel<false><<<grid, block, 0, st>>>(dY, lddy, Y, ldy, mask_a, mask_b, M, N, out, ldo);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

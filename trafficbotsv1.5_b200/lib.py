@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("TB_LIB", os.path.join(_PKG, "libtbknarpe.so"))
 _SOURCES = ["api.cu", "knn_select.cu", "knarpe_attn.cu", "knarpe_attn_mma.cu", "knarpe_attn_bwd.cu", "linear_f32.cu", "linear_tc.cu", "elementwise.cu", "post_process.cu", "ag_frontend.cu", "mlp_chain.cu",
-            "rollout_step.cu", "rule_check.cu", "train_bwd.cu"]
+            "rollout_step.cu", "rule_check.cu", "train_bwd.cu", "wgrad_tc.cu"]
 _lib = None
 
 EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_linear", "tb_linear_ln", "tb_layernorm",
@@ -23,7 +23,7 @@ EXPORTS = ["tb_strerror", "tb_version", "tb_knn_select", "tb_knarpe_attn", "tb_l
            "tb_traj_global", "tb_womd_post", "tb_ag_frontend", "tb_ag_frontend_blob_halves", "tb_knarpe_attn_bwd", "tb_set_fp16_flag", "tb_dyn_step_ex", "tb_tl_step_ex",
            "tb_dyn_update", "tb_chain_program_bytes", "tb_chain_encode", "tb_chain_run", "tb_layernorm_bwd", "tb_linear_wgrad", "tb_grad_mask",
            "tb_group_sum", "tb_pointnet_pool_bwd", "tb_il_loss_fwd", "tb_il_loss_bwd", "tb_tl_nll", "tb_softmax_nll", "tb_ag_featurize_ex",
-           "tb_tl_featurize_ex"]
+           "tb_tl_featurize_ex", "tb_colsum"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -80,7 +80,8 @@ def load() -> ctypes.CDLL:
         "tb_layernorm": [P, I, P, P, P, I, I, I, I, P],
         "tb_pointnet_pool": [P, I, P, I, I, I, I, P, I, P],
         "tb_layernorm_bwd": [P, I, P, P, I, P, I, P, P, I, I, P],
-        "tb_linear_wgrad": [P, I, P, I, I, I, I, P, I, P, P],
+        "tb_linear_wgrad": [P, I, P, I, I, I, I, P, I, P, I, P],
+        "tb_colsum": [P, I, I, I, P, P],
         "tb_grad_mask": [P, I, P, I, P, P, I, I, P, I, P],
         "tb_group_sum": [P, I, I, I, I, P, I, P],
         "tb_pointnet_pool_bwd": [P, I, P, I, I, I, I, P, I, P, I, P],
