@@ -8,9 +8,9 @@
 // The projections around it (q|u, k|v, out) are plain GEMMs whose gradients are GEMMs. e_j depends on poses only: no
 // gradient is propagated into the relative pose (the reference detaches the states that feed it during the rollout
 // loss, waymo_motion.py:313-385 with teacher forcing).
-// fp32 only (parity path), d_model = d_rpe = 128, 4 heads. One warp per token, three passes over its neighbour list
-// (logits + softmax statistics; g and sum p g; gradients), the embedding is re-evaluated in registers in each pass,
-// logits and g live in 4 KB of shared memory per warp. K / V gradients are scattered with vector atomics
+// fp32 only (parity path), d_model = d_rpe = 128, 4 heads. One warp per token, two passes over its neighbour list
+// (A: logits and g together, reduced with a halving butterfly; softmax statistics from shared memory; B: gradients),
+// the embedding is re-evaluated in registers in each pass, logits and g live in 4 KB of shared memory per warp. K / V gradients are scattered with vector atomics
 // (red.global.add.v4.f32): rows shared by many tokens serialise in L2 - this is the straightforward version.
 #include "common.cuh"
 
@@ -84,27 +84,55 @@ knarpe_attn_bwd_kernel(const float* __restrict__ q, int ldq, const float* __rest
       gz[h][k] = __ldg(d_z + (size_t)tok * ldo + h * D + lane + 32 * k);
     }
 
-  // ---- pass 1: logits of the unmasked neighbours, running max per head
-  float mx[H] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  // ---- pass A: logits l_hj AND g_hj = d_ov_h.v_hj + d_z_h.e_j of the unmasked neighbours in one sweep (one embedding
+  // evaluation, K and V rows gathered together). The 8 per-lane partials (4 heads x {l, g}) are reduced over the warp
+  // with a halving butterfly: 4 + 2 + 1 exchanges fold 8 -> 1 value per lane, 2 more finish the sum = 9 shuffles per
+  // neighbour instead of 8 x 5. Lane 4 i (i = 0..7) ends up with value i and writes it to shared memory.
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
   for (int j = 0; j < Ktot; ++j) {
     if (invalid[prow + j]) continue;  // warp-uniform
     float e[4];
     emb(j, e);
     const float* kp = ((j < K0) ? kv0 : kv1) + row_off(j);
     const float4 k4 = ldg4(kp + lane * 4);
+    const float4 v4 = ldg4(kp + D + lane * 4);
     const float qk = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+    const float gv = go4.x * v4.x + go4.y * v4.y + go4.z * v4.z + go4.w * v4.w;
+    float val[8];
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      float part = uu[h][0] * e[0] + uu[h][1] * e[1] + uu[h][2] * e[2] + uu[h][3] * e[3];
-      if (h == hh) part += qk;
-      const float l = warp_sum(part);
-      mx[h] = fmaxf(mx[h], l);
-      if (lane == 0) s_l[warp][h][j] = l;
+      val[h] = uu[h][0] * e[0] + uu[h][1] * e[1] + uu[h][2] * e[2] + uu[h][3] * e[3] + (h == hh ? qk : 0.f);
+      val[4 + h] = gz[h][0] * e[0] + gz[h][1] * e[1] + gz[h][2] * e[2] + gz[h][3] * e[3] + (h == hh ? gv : 0.f);
+    }
+    float r4[4], r2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      r4[i] = (b16 ? val[i + 4] : val[i]) + __shfl_xor_sync(TB_FULL_MASK, b16 ? val[i] : val[i + 4], 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      r2[i] = (b8 ? r4[i + 2] : r4[i]) + __shfl_xor_sync(TB_FULL_MASK, b8 ? r4[i] : r4[i + 2], 8);
+    float r1 = (b4 ? r2[1] : r2[0]) + __shfl_xor_sync(TB_FULL_MASK, b4 ? r2[0] : r2[1], 4);
+    r1 += __shfl_xor_sync(TB_FULL_MASK, r1, 2);
+    r1 += __shfl_xor_sync(TB_FULL_MASK, r1, 1);
+    if ((lane & 3) == 0) {
+      const int vi = lane >> 2;  // 4 b16 + 2 b8 + b4: values 0-3 are the logits of heads 0-3, 4-7 their g
+      if (vi < 4) s_l[warp][vi][j] = r1; else s_g[warp][vi - 4][j] = r1;
     }
   }
   __syncwarp();
-  // ---- probabilities
-  float sm[H] = {0.f, 0.f, 0.f, 0.f};
+  // ---- softmax statistics and dot_h = sum_j p_hj g_hj from shared memory (lanes over neighbours)
+  float mx[H] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  for (int j = lane; j < Ktot; j += 32) {
+    if (invalid[prow + j]) continue;
+#pragma unroll
+    for (int h = 0; h < H; ++h) mx[h] = fmaxf(mx[h], s_l[warp][h][j]);
+  }
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx[h] = fmaxf(mx[h], __shfl_xor_sync(TB_FULL_MASK, mx[h], o));
+  }
+  float sm[H] = {0.f, 0.f, 0.f, 0.f}, dot[H] = {0.f, 0.f, 0.f, 0.f};
   for (int j = lane; j < Ktot; j += 32) {
     const bool ok = !invalid[prow + j];
 #pragma unroll
@@ -112,36 +140,20 @@ knarpe_attn_bwd_kernel(const float* __restrict__ q, int ldq, const float* __rest
       const float p = ok ? ex2(s_l[warp][h][j] - mx[h]) : 0.f;
       s_l[warp][h][j] = p;
       sm[h] += p;
+      dot[h] += ok ? p * s_g[warp][h][j] : 0.f;
     }
   }
-#pragma unroll
-  for (int h = 0; h < H; ++h) sm[h] = warp_sum(sm[h]);
-  __syncwarp();
   float inv[H];
 #pragma unroll
-  for (int h = 0; h < H; ++h) inv[h] = sm[h] > 0.f ? 1.f / sm[h] : 0.f;
-
-  // ---- pass 2: g_hj = d_ov_h.v_hj + d_z_h.e_j and dot_h = sum_j p_hj g_hj
-  float dot[H] = {0.f, 0.f, 0.f, 0.f};
-  for (int j = 0; j < Ktot; ++j) {
-    if (invalid[prow + j]) continue;
-    float e[4];
-    emb(j, e);
-    const float* vp = ((j < K0) ? kv0 : kv1) + row_off(j) + D;
-    const float4 v4 = ldg4(vp + lane * 4);
-    const float gv = go4.x * v4.x + go4.y * v4.y + go4.z * v4.z + go4.w * v4.w;
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      float part = gz[h][0] * e[0] + gz[h][1] * e[1] + gz[h][2] * e[2] + gz[h][3] * e[3];
-      if (h == hh) part += gv;
-      const float gsum = warp_sum(part);
-      dot[h] += s_l[warp][h][j] * inv[h] * gsum;
-      if (lane == 0) s_g[warp][h][j] = gsum;
-    }
+  for (int h = 0; h < H; ++h) {
+    sm[h] = warp_sum(sm[h]);
+    dot[h] = warp_sum(dot[h]);
+    inv[h] = sm[h] > 0.f ? 1.f / sm[h] : 0.f;
+    dot[h] *= inv[h];
   }
   __syncwarp();
 
-  // ---- pass 3: dl_hj = ln2 p_hj (g_hj - dot_h); accumulate d_q, d_u; scatter d_k, d_v
+  // ---- pass B: dl_hj = ln2 p_hj (g_hj - dot_h); accumulate d_q, d_u; scatter d_k, d_v
   float dq[4] = {0.f, 0.f, 0.f, 0.f};
   float du[H][4];
 #pragma unroll
