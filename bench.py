@@ -647,48 +647,70 @@ def run_train(args):
     scene-steps/s = scenes x 90 policy iterations / time of one loss + gradient evaluation. Side numbers: the same step
     by torch autograd through the reference-order oracle on this GPU (`eager_cuda`, a smaller batch: its [B,S,K,2d]
     gathers of all 90 steps do not fit otherwise) and the gradient check against it."""
+    import torch.distributed as dist
     from trafficbotsv1_5_b200 import ops
     from trafficbotsv1_5_b200.training import TRAIN_CFG, TrainStep
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback for the product path"
-    dev = "cuda:0"
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
     cfg = config.default_model_cfg()
     P = params.init_params(cfg, 0, with_navi_predictor=True, with_latent_post=True)
     n_sc = args.scenes if args.scenes != 16 else 64
-    batch = synth.make_train_batch(n_sc, seed=3000)
+    batch = synth.make_train_batch(n_sc, seed=3000 + rank * n_sc)  # data parallel: every rank its own scenes
     batch = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
     ts = TrainStep(P, cfg, dev, precision=min(args.precision, 1))
+    if world > 1:
+        ts.data_parallel()  # gradients averaged with one NCCL all-reduce per step (inside the timed region)
 
     def step():
         ts.zero_grad()
         out = ts.step(batch)
         return float(out["loss"])  # device -> host read of the step's result
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(max(1, args.warmup)):
         loss = step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     l0 = ops.LAUNCHES
-    with ClockSampler(0) as cs:
+    with ClockSampler(local) as cs:
         e0.record()
         for _ in range(args.steps):
             loss = step()
         e1.record()
-        torch.cuda.synchronize()
-    t = e0.elapsed_time(e1) * 1e-3 / args.steps
+        barrier()
+    tt = torch.tensor([e0.elapsed_time(e1) * 1e-3 / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t = float(tt)
     phases = ts.timings_ms()
     peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
-    line = dict(metric="training_step_scene_steps_per_sec", value=n_sc * N_ITER / t, unit="scene-steps/s (fwd+bwd)",
-                n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True,
+    if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    line = dict(metric="training_step_scene_steps_per_sec", value=world * n_sc * N_ITER / t, unit="scene-steps/s (fwd+bwd)",
+                n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32" if args.precision == 0 else "tf32", data="synthetic",
-                config=dict(workload=f"config 4: training_step body fwd+bwd, {n_sc} scenes, 128 agents, 1024 polylines x 20, "
-                                     f"40 TL, 90 teacher-forced policy iterations, dropout 0", scenes=n_sc,
+                config=dict(workload=f"config 4: training_step body fwd+bwd, {n_sc} scenes per GPU, 128 agents, 1024 polylines "
+                                     f"x 20, 40 TL, 90 teacher-forced policy iterations, dropout 0"
+                                     + (", gradients averaged over the ranks (one NCCL all-reduce)" if world > 1 else ""),
+                            scenes_per_gpu=n_sc,
                             l2="activations of 90 steps (tens of GB) exceed the 126 MB L2; no flush"),
                 clocks=cs.summary(), gpu_launches=ops.LAUNCHES - l0, loss=loss, peak_hbm_gib=peak_gb, phases_ms=phases,
-                e2e=dict(value=n_sc * N_ITER / t, unit="scene-steps/s (fwd+bwd)",
+                e2e=dict(value=world * n_sc * N_ITER / t, unit="scene-steps/s (fwd+bwd)",
                          h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in batch.values() if torch.is_tensor(v)),
                          d2h_bytes_per_step=4))
-    if not args.no_extras:
+    if not args.no_extras and world == 1:
         try:
             from oracle import tb_oracle_train as OT
             n_e = 2
@@ -718,6 +740,9 @@ def run_train(args):
         except Exception as e:
             line["eager_cuda"] = dict(unavailable=f"{type(e).__name__}: {e}"[:200])
     print(json.dumps(line), file=_OUT, flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 _OUT = sys.stdout

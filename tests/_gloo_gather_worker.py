@@ -47,6 +47,21 @@ def main():
             assert torch.equal(store[b, r], fake_rollout(ids)), (rank, r, b)
             assert torch.equal(parallel.scene_checksums(store[b, r]), all_sums[r][b])
     assert not torch.equal(parallel.scene_checksums(store[0, 0]), parallel.scene_checksums(store[0, 0].flip(1)))
+    # data-parallel training: gradients accumulate into one flat bucket through autograd, one all-reduce averages them
+    torch.manual_seed(0)
+    params = {"b.w": torch.randn(3, 4, requires_grad=True), "a.bias": torch.randn(5, requires_grad=True),
+              "unused": torch.randn(2, requires_grad=True)}
+    bucket = parallel.GradBucket(params)
+    x = torch.full((4,), float(rank + 1))
+    loss = (params["b.w"] @ x).sum() + (params["a.bias"] * (rank + 1)).sum()
+    loss.backward()
+    bucket.all_reduce()
+    mean = sum(range(1, world + 1)) / world
+    assert torch.allclose(params["b.w"].grad, torch.full((3, 4), mean)) and params["b.w"].grad.data_ptr() == bucket.views["b.w"].data_ptr()
+    assert torch.allclose(params["a.bias"].grad, torch.full((5,), mean))
+    assert float(params["unused"].grad.abs().max()) == 0.0
+    bucket.zero()
+    assert float(bucket.flat.abs().max()) == 0.0
     dist.barrier()
     if rank == 0:
         print("GLOO_GATHER_OK")

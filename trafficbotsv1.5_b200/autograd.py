@@ -179,9 +179,9 @@ class _Attn(Function):
     """KNARPE core on fp32 rows: qu [M, D + H*D] = [q | u], K|V tables kv0 (/ kv1) [rows, 2D] (row-strided views)."""
 
     @staticmethod
-    def forward(ctx, qu, kv0, kv1, T0, div0, K0, T1, div1, K1, idx, inv, rel, freq, B, S, D, H):
+    def forward(ctx, qu, kv0, kv1, T0, div0, K0, T1, div1, K1, idx, inv, rel, freq, B, S, D, H, fast_trig):
         out, nv = ops.knarpe_attn(qu[:, :D], qu[:, D:], kv0, T0, div0, K0, idx, inv, rel, freq, B, S, D, H, kv1=kv1,
-                                  T1=T1, div1=div1, K1=K1)
+                                  T1=T1, div1=div1, K1=K1, fast_trig=fast_trig)
         ctx.cfg = (T0, div0, K0, T1, div1, K1, B, S, D, H)
         ctx.lists = (idx, inv, rel, freq)
         ctx.save_for_backward(qu, kv0, kv1)
@@ -209,15 +209,15 @@ class _Attn(Function):
             L.ptr(rel), L.ptr(freq), B, S, D, H, L.ptr(d_out), L.ptr(d_out[:, D:]), d_out.stride(0), L.ptr(d_qu),
             d_qu.stride(0), L.ptr(d_kv0), L.ptr(d_kv1), L.stream()), "tb_knarpe_attn_bwd")
         ops._count()
-        return (d_qu, d_kv0, d_kv1) + (None,) * 14
+        return (d_qu, d_kv0, d_kv1) + (None,) * 15
 
 
 def knarpe_attn(qu: Tensor, kv0: Tensor, T0: int, div0: int, K0: int, idx: Tensor, inv: Tensor, rel: Tensor,
                 freq: Tensor, B: int, S: int, D: int, H: int, kv1: Optional[Tensor] = None, T1: int = 0, div1: int = 1,
-                K1: int = 0) -> Tuple[Tensor, Tensor]:
+                K1: int = 0, fast_trig: bool = False) -> Tuple[Tensor, Tensor]:
     assert qu.dtype == torch.float32 and kv0.dtype == torch.float32 and rel is not None
     return _Attn.apply(qu, kv0, kv1, T0, div0, K0, T1, div1, K1, idx.contiguous(), inv.contiguous(),
-                       rel.contiguous(), freq, B, S, D, H)
+                       rel.contiguous(), freq, B, S, D, H, fast_trig)
 
 
 # ---------------------------------------------------------------------------------------------------- closed loop

@@ -233,7 +233,8 @@ class HotPathModel:
         if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (proj, kv0, kv1)):
             from . import autograd as AG  # training path: differentiable core (tb_knarpe_attn_bwd)
             return AG.knarpe_attn(proj[:, :d + H * d], kv0, T0, div0, K0, knn["idx"], knn["inv"], knn["rel"],
-                                  self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1)
+                                  self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1,
+                                  fast_trig=self.precision == 1)
         return ops.knarpe_attn(proj[:, :d], proj[:, d:d + H * d], kv0, T0, div0, K0, knn["idx"], knn["inv"],
                                knn.get("rel"), self.freq_rpe, B, S, d, H, kv1=kv1, T1=T1, div1=div1, K1=K1,
                                emb=knn.get("emb"), fast_trig=self.precision == 1, interleaved=self.kv_il,

@@ -50,6 +50,45 @@ def scene_checksums(t: Tensor) -> Tensor:
     return (w * (pos % 65521)).sum(1)
 
 
+class GradBucket:
+    """Data-parallel training (the reference trains with Lightning DDP, configs/trainer/default.yaml): every rank
+    evaluates `training.TrainStep` on its own scenes; the ONE exchange of a step is the average of the gradients. All
+    gradients live in one flat fp32 buffer (each `param.grad` is a view of it, so autograd accumulates straight into
+    the bucket) and are reduced with a single all-reduce (NCCL over NVLink on the box: 32 MB for the 8 M parameters of
+    the training configuration; gloo in the CPU tests)."""
+
+    def __init__(self, params: Dict[str, Tensor]):
+        self.params = params
+        self.names = sorted(params)
+        n = sum(params[k].numel() for k in self.names)
+        any_p = params[self.names[0]]
+        self.flat = torch.zeros(n, dtype=any_p.dtype, device=any_p.device)
+        self.views, off = {}, 0
+        for k in self.names:
+            p = params[k]
+            self.views[k] = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.zero()
+
+    def zero(self) -> None:
+        """Zero the bucket and (re-)attach its views as the parameters' .grad."""
+        self.flat.zero_()
+        for k in self.names:
+            self.params[k].grad = self.views[k]
+
+    def all_reduce(self) -> None:
+        """Average the gradients over the ranks (no-op in a single process). Gradients autograd created outside the
+        bucket (a parameter whose .grad was None at backward time) are folded in first."""
+        for k in self.names:
+            g = self.params[k].grad
+            if g is not None and g.data_ptr() != self.views[k].data_ptr():
+                self.views[k].copy_(g)
+                self.params[k].grad = self.views[k]
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(dist.get_world_size())
+
+
 class OverlappedGather:
     """All-gather of per-batch results on a side stream, overlapped with the next batch's compute (SURVEY 5 last row;
     the reference gathers its `cat` metric states after every test step, submission.py:45-46,169-170). `submit` copies

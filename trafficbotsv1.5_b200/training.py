@@ -131,10 +131,20 @@ class TrainStep:
                                                         "latent_encoder.latent_dist_post.": "latent_dist."}),
                                    cfg_l, self.sz, device, precision)
         self.has_navi = any(k.startswith("navi_predictor.") for k in self.params)
+        self.bucket = None
 
     def zero_grad(self) -> None:
-        for p in self.params.values():
-            p.grad = None
+        if self.bucket is not None:
+            self.bucket.zero()
+        else:
+            for p in self.params.values():
+                p.grad = None
+
+    def data_parallel(self) -> None:
+        """Keep all gradients in one flat bucket and average them over the ranks at the end of every step
+        (parallel.GradBucket: one NCCL all-reduce; the reference trains with Lightning DDP)."""
+        from .parallel import GradBucket
+        self.bucket = GradBucket(self.params)
 
     # ------------------------------------------------------------------------------------------ latent posterior
     def _posterior(self, g, mp: dict) -> Tensor:
@@ -319,6 +329,9 @@ class TrainStep:
         if backward:
             loss.backward()
             self._mark("backward")
+            if self.bucket is not None:
+                self.bucket.all_reduce()
+                self._mark("grad_all_reduce")
         out["pred_pose"], out["pred_valid"] = st["pred_pose"][:, :, :T], pred_valid.bool()
         return out
 
