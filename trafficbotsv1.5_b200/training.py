@@ -301,11 +301,11 @@ class TrainStep:
         t0 = tc["step_training_start"]
         il, _ = AG.il_loss(acts, rec, dy, (tc["w_pos"], tc["w_rot"], tc["w_spd"]), t0)
         loss = torch.zeros((), device=dev)
-        if float(il[1]) > 0:                                                                            # :170-181
+        if float(il.detach()[1]) > 0:                                                                            # :170-181
             out["diffbar_reward"] = -tc["w_diffbar_reward"] * il[0] / il[1]
             loss = loss - out["diffbar_reward"]
         nll = AG.tl_nll(logit_l, tl["tl_token_invalid"].reshape(-1), st["gt_tl"], n_gt)
-        if float(nll[1]) > 0:                                                                           # :186-188
+        if float(nll.detach()[1]) > 0:                                                                           # :186-188
             out["tl_state_loss"] = tc["w_tl_state"] * nll[0] / nll[1]
             loss = loss + out["tl_state_loss"]
         loss_any = pred_valid[:, :, t0:].bool().any(-1)                                                 # loss_valid.any(-1)
@@ -321,7 +321,7 @@ class TrainStep:
             navi_valid = g("sc/ag_valid").any(-1) & loss_any
             n_mp_ = navi_logits.shape[-1]
             nn = AG.softmax_nll(navi_logits.reshape(-1, n_mp_), g("gt/ag_navi").reshape(-1), navi_valid.reshape(-1))
-            if float(nn[1]) > 0:
+            if float(nn.detach()[1]) > 0:
                 out["navi_loss"] = tc["w_navi"] * nn[0] / nn[1]
                 loss = loss + out["navi_loss"]
         out["loss"] = loss
