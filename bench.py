@@ -443,7 +443,7 @@ def run_sweep(args):
     l0 = ops.LAUNCHES
     with ClockSampler(local) as cs:
         t_val = timed(lambda: sweep(resident), args.steps)
-    launches = (ops.LAUNCHES - l0) + args.steps * n_batches * N_ITER * eng.launches_per_step
+    launches = (ops.LAUNCHES - l0) + args.steps * n_batches * eng.graph_steps * eng.launches_per_step
     clocks = cs.summary()
     units = total * R * N_COUNTED
     value = units * args.steps / t_val
@@ -556,7 +556,7 @@ def run_ours(args):
     l0 = ops.LAUNCHES
     with ClockSampler(local) as cs:
         t_loop = timed(loop_step, args.steps)
-    launches = args.steps * N_ITER * eng.launches_per_step + (ops.LAUNCHES - l0)
+    launches = args.steps * eng.graph_steps * eng.launches_per_step + (ops.LAUNCHES - l0)  # graph replays + eager launches
     clocks = cs.summary()
     units = world * n_sc * args.rollouts * N_COUNTED
     value = units * args.steps / t_loop

@@ -295,6 +295,12 @@ int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose, const floa
                    const int* d_step, const float* freq_xy, int B, int A, int W, const void* wblob, const float* bias,
                    float* tok_out, int ldo, float* tok_pose, uint8_t* tok_invalid, const float* ln_gamma,
                    const float* ln_beta, void* ln_out, int ld_ln, void* stream);
+/* Same with one loop counter per batch row, s(b) = d_step[b * step_stride] (see tb_ag_featurize_ex): the engine encodes
+ * the rollout-invariant warm-start steps of all scenes as one batch of (scene, step) rows. */
+int tb_ag_frontend_ex(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion, const float* ag_attr,
+                      const int* d_step, int step_stride, const float* freq_xy, int B, int A, int W, const void* wblob,
+                      const float* bias, float* tok_out, int ldo, float* tok_pose, uint8_t* tok_invalid,
+                      const float* ln_gamma, const float* ln_beta, void* ln_out, int ld_ln, void* stream);
 
 /* Traffic-light history rows — traffic_light.py:223-225: [state5 | one-hot11] per (b,tl,window slot).
  *   hist_tl [B,TL,W,5] u8 one-hot, tl_invalid [B,TL]; out rows [B*TL*W,16] (ld lda), row_invalid [B,TL,W]. */

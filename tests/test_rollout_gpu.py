@@ -599,3 +599,32 @@ def test_rollout_fused_layernorm_vs_separate(golden_rollout, monkeypatch):
     assert maxerr(res["pred_pose"][..., :2], res2["pred_pose"][..., :2]) < 5e-3
     assert maxerr(res["pred_pose"][..., 2], res2["pred_pose"][..., 2]) < 2e-3
     assert torch.equal(res["pred_valid"], res2["pred_valid"]) and torch.equal(res["tl_state"], res2["tl_state"])
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("gap", [False, True])
+def test_warm_start_dedup_matches_per_rollout_encoding(precision, gap):
+    """Warm-start de-duplication (engine._warm_steps): while every valid agent is teacher-forced, the encoder inputs of
+    a scene's rollouts are identical, so the agent / TL encoders of steps 1 .. S0 run once per scene as one batch. The
+    result must equal the plain per-rollout, per-step path: masks identical, poses within 1e-4 m (fp32) / 2e-3 m
+    (16-bit mode: the neighbour order of the batched full-scan select and the step-wise temporal select differ, which
+    re-orders the attention sums). With a track gap inside the warm start (an agent valid but NOT forced at step 4)
+    only the steps before it are rollout-invariant: S0 shrinks and the rest runs on the regular path."""
+    shape = dict(n_sc=2, n_ag=40, n_mp=96, n_tl=30, seed=77, boundary=110.0)
+    eng, batch, P, cfg = _engine(shape, 3, 24, precision=precision)
+    if gap:
+        batch["sc/ag_valid"][0, 5, 4] = False   # valid at t = 3, ground truth missing at t = 4, back at t = 5
+        batch["sc/ag_valid"][0, 5, 3] = True
+        batch["sc/ag_valid"][0, 5, 5] = True
+    eng.prepare(batch)
+    assert eng._s0 == (4 if gap else 11), eng._s0
+    a = {k: v.clone() for k, v in eng.run().items()}
+    eng.warm_dedup = False
+    eng.prepare(batch)
+    assert eng._s0 == 0
+    b = eng.run()
+    for k in ("pred_valid", "tl_state", "final_valid", "final_navi_valid"):
+        assert torch.equal(a[k], b[k]), k
+    tol = 1e-4 if precision == 0 else 2e-3
+    assert maxerr(a["pred_pose"], b["pred_pose"]) < tol, maxerr(a["pred_pose"], b["pred_pose"])
+    assert maxerr(a["pred_motion"], b["pred_motion"]) < 5 * tol  # accelerations / yaw rates of up to 7 per second

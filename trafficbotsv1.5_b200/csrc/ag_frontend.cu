@@ -92,8 +92,8 @@ __device__ __forceinline__ float pe64(int c, float x, float y, float w, const fl
 __global__ void __launch_bounds__(AW * 32, 2)
 ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restrict__ hist_pose,
                    const float* __restrict__ hist_motion, const float* __restrict__ ag_attr,
-                   const int* __restrict__ d_step, const float* __restrict__ freq_xy, int n_ag_tot, int W,
-                   const __half* __restrict__ wblob, const float* __restrict__ bias, float* __restrict__ tok_out,
+                   const int* __restrict__ d_step, int step_stride, int A, const float* __restrict__ freq_xy,
+                   int n_ag_tot, int W, const __half* __restrict__ wblob, const float* __restrict__ bias, float* __restrict__ tok_out,
                    int ldo, float* __restrict__ tok_pose, uint8_t* __restrict__ tok_invalid,
                    const float* __restrict__ ln_g, const float* __restrict__ ln_b, __half* __restrict__ ln_out,
                    int ld_ln, unsigned int* __restrict__ sat_flag) {
@@ -108,13 +108,14 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int s = *d_step;
-  const int n_step = min(s, W);
+  const int s_all = *d_step;
   float* fr = sB + N_BIAS;  // the 8 xy frequencies (shared: indexed by a lane-dependent component number)
   uint32_t hm = 0u;         // fp16 range guard: |max| of the activations this lane converted
 
   for (int ba = blockIdx.x * AW + warp; ba < n_ag_tot; ba += gridDim.x * AW) {  // warp-uniform
     const size_t hb = (size_t)ba * W;
+    const int s = step_stride ? d_step[(size_t)(ba / A) * step_stride] : s_all;  // one loop counter per batch row
+    const int n_step = min(s, W);
     // window position wp in [W-n_step, W) <-> time s - W + wp, ring slot (s - W + wp) % W; wp < W - n_step: absent
     int last_wp = -1;
     for (int wp = W - n_step; wp < W; ++wp)
@@ -247,15 +248,15 @@ ag_frontend_kernel(const uint8_t* __restrict__ hist_valid, const float* __restri
 
 extern "C" int tb_ag_frontend_blob_halves(void) { return W_HALVES; }
 
-extern "C" int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
-                              const float* ag_attr, const int* d_step, const float* freq_xy, int B, int A, int W,
-                              const void* wblob, const float* bias, float* tok_out, int ldo, float* tok_pose,
-                              uint8_t* tok_invalid, const float* ln_gamma, const float* ln_beta, void* ln_out, int ld_ln,
-                              void* stream) {
+extern "C" int tb_ag_frontend_ex(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
+                                 const float* ag_attr, const int* d_step, int step_stride, const float* freq_xy, int B,
+                                 int A, int W, const void* wblob, const float* bias, float* tok_out, int ldo,
+                                 float* tok_pose, uint8_t* tok_invalid, const float* ln_gamma, const float* ln_beta,
+                                 void* ln_out, int ld_ln, void* stream) {
   if (!hist_valid || !hist_pose || !hist_motion || !ag_attr || !d_step || !freq_xy || !wblob || !bias || !tok_out ||
       !tok_pose || !tok_invalid)
     return TB_ERR_NULL;
-  if (B <= 0 || A <= 0 || W <= 0 || ldo < 128) return TB_ERR_BAD_SHAPE;
+  if (B <= 0 || A <= 0 || W <= 0 || ldo < 128 || step_stride < 0) return TB_ERR_BAD_SHAPE;
   if (W > 16 || 9 + W > 32) return TB_ERR_UNSUPPORTED;
   if ((ldo & 1) || !tb_aligned16(wblob) || (reinterpret_cast<uintptr_t>(tok_out) & 7)) return TB_ERR_MISALIGNED;
   if (ln_out) {
@@ -282,8 +283,18 @@ extern "C" int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose,
   const int want = (n + AW - 1) / AW;
   const int grid = want < 2 * num_sms ? want : 2 * num_sms;  // persistent: 2 CTAs per SM, warps loop over agents
   ag_frontend_kernel<<<grid, AW * 32, SMEM, static_cast<cudaStream_t>(stream)>>>(
-      hist_valid, hist_pose, hist_motion, ag_attr, d_step, freq_xy, n, W, static_cast<const __half*>(wblob), bias,
-      tok_out, ldo, tok_pose, tok_invalid, ln_gamma, ln_beta, static_cast<__half*>(ln_out), ld_ln, tb_fp16_flag_ptr);
+      hist_valid, hist_pose, hist_motion, ag_attr, d_step, step_stride, A, freq_xy, n, W,
+      static_cast<const __half*>(wblob), bias, tok_out, ldo, tok_pose, tok_invalid, ln_gamma, ln_beta,
+      static_cast<__half*>(ln_out), ld_ln, tb_fp16_flag_ptr);
   TB_CHECK_LAUNCH();
   return TB_OK;
+}
+
+extern "C" int tb_ag_frontend(const uint8_t* hist_valid, const float* hist_pose, const float* hist_motion,
+                              const float* ag_attr, const int* d_step, const float* freq_xy, int B, int A, int W,
+                              const void* wblob, const float* bias, float* tok_out, int ldo, float* tok_pose,
+                              uint8_t* tok_invalid, const float* ln_gamma, const float* ln_beta, void* ln_out, int ld_ln,
+                              void* stream) {
+  return tb_ag_frontend_ex(hist_valid, hist_pose, hist_motion, ag_attr, d_step, 0, freq_xy, B, A, W, wblob, bias, tok_out,
+                           ldo, tok_pose, tok_invalid, ln_gamma, ln_beta, ln_out, ld_ln, stream);
 }

@@ -520,15 +520,15 @@ class HotPathModel:
         hist = (L.ptr(st["hist_valid"]), L.ptr(st["hist_pose"]), L.ptr(st["hist_motion"]), L.ptr(st["ag_attr"]),
                 L.ptr(st["d_step"]), L.ptr(self.freq_ag), B, A, W)
         per_row_step = st["d_step"].numel() > 1
-        assert not (fused and per_row_step)
+        stride = 1 if per_row_step else 0
         if fused:  # token pose / validity first (tiny), so that the KNN selects start beside the fused encoder
-            L.check(L.load().tb_ag_featurize(*hist, L.ptr(tok_pose), L.ptr(ops._u8(tok_inv)), None, None, 0, None, 0,
-                                             L.stream()), "tb_ag_featurize")
+            L.check(L.load().tb_ag_featurize_ex(*hist[:5], stride, *hist[5:], L.ptr(tok_pose), L.ptr(ops._u8(tok_inv)),
+                                                None, None, 0, None, 0, L.stream()), "tb_ag_featurize_ex")
         else:
             row_inv = torch.empty(MW, dtype=torch.bool, device=self.dev)
             attr = torch.empty(MW, 9 + W, device=self.dev)
             x = torch.empty(MW, d, device=self.dev)
-            L.check(L.load().tb_ag_featurize_ex(*hist[:5], 1 if per_row_step else 0, *hist[5:], L.ptr(tok_pose),
+            L.check(L.load().tb_ag_featurize_ex(*hist[:5], stride, *hist[5:], L.ptr(tok_pose),
                                                 L.ptr(ops._u8(tok_inv)), L.ptr(ops._u8(row_inv)), L.ptr(attr), 9 + W,
                                                 L.ptr(x[:, d // 2:]), d, L.stream()), "tb_ag_featurize_ex")
         ops._count()
@@ -582,8 +582,9 @@ class HotPathModel:
                 ln_args = (L.ptr(self.P[f"{nm}.weight"]), L.ptr(self.P[f"{nm}.bias"]), L.ptr(ln0), d)
             else:
                 ln_args = (None, None, None, 0)
-            L.check(L.load().tb_ag_frontend(*hist, L.ptr(blob), L.ptr(bias), L.ptr(tok), d, L.ptr(tp2),
-                                            L.ptr(ops._u8(ti2)), *ln_args, L.stream()), "tb_ag_frontend")  # :130-162
+            L.check(L.load().tb_ag_frontend_ex(*hist[:5], stride, *hist[5:], L.ptr(blob), L.ptr(bias), L.ptr(tok), d,
+                                               L.ptr(tp2), L.ptr(ops._u8(ti2)), *ln_args, L.stream()),
+                    "tb_ag_frontend_ex")                                                              # :130-162
             ops._count()
         else:
             ln0 = None
