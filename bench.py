@@ -592,7 +592,10 @@ def run_ours(args):
                                          f"iterations (80 counted)", scenes_per_gpu=n_sc, rollouts=args.rollouts,
                                 policy_iterations=N_ITER, counted_steps=N_COUNTED, rule_checks=bool(args.rule_checks),
                                 l2="per-iteration working set (>1 GB of activations) exceeds the 126 MB L2; no flush",
-                                launches_per_policy_iteration=eng.launches_per_step, gather_verified=gather_ok),
+                                launches_per_policy_iteration=eng.launches_per_step, gather_verified=gather_ok,
+                                warm_start_dedup=f"encoders of the {eng._s0} teacher-forced (rollout-invariant) leading steps "
+                                                 f"run once per scene as one batch, inside the timed loop; steps "
+                                                 f"{eng._s0 + 1}..{N_ITER} per rollout (DESIGN.md 6)" if eng._s0 else "off"),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof, roofline_select=roof_sel)
     if rank == 0 and world == 1 and not args.rule_checks and not args.no_extras:
         # extra lines (not the headline): fp32-parity projections, and the loop with ALL TrafficRuleChecker checks on
