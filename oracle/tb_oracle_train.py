@@ -9,8 +9,11 @@ CUDA training path (trafficbotsv1.5_b200/training.py) is compared with.
   TrainingMetrics.update/compute  models/metrics/training.py:76-189, BalancedKL models/metrics/loss.py:40-76
   TeacherForcing.init (training)  utils/teacher_forcing.py:51-92
 
-Parity pin: the reference ships no test for this path ("parity unpinned by the reference"); the forward pieces used
-here are pinned by the golden vectors of tests/golden (real reference outputs); the loss assembly is a restatement.
+Parity pin: the reference ships no test for this path; the pin is `tests/golden/train_small.pt`, produced by
+`tests/golden/make_golden.py train`, which evaluates the same training_step body with the REAL reference modules
+(TrafficBots incl. LatentEncoder / NaviPredictor, Dynamics, TeacherForcing, RolloutBuffer, DifferentiableReward,
+TrainingMetrics / BalancedKL; only the Lightning wrapper is restated) and torch autograd: every loss term and two
+statistics of every one of the 656 gradient tensors (tests/test_oracle_golden.py, `-m "not gpu"`).
 Dropout is off (p = 0 configuration); the Bernoulli draws of a step are inputs. Only tests/ and bench.py's CPU /
 eager baseline legs may import this module.
 """

@@ -308,10 +308,150 @@ def golden_checks_redlight(model=None):
           {k: int(res[k].sum()) for k in keep[4:]})
 
 
+TRAIN_STATS_SEED = 12345
+
+
+def grad_stats(grads: dict) -> dict:
+    """Two numbers per gradient tensor (norm, projection on a seeded random direction): pins every gradient of the
+    training step with a few KB (the 656 tensors themselves are 32 MB)."""
+    out = {}
+    for i, k in enumerate(sorted(grads)):
+        g = grads[k]
+        if g is None:
+            out[k] = None
+            continue
+        r = torch.randn(g.shape, generator=torch.Generator().manual_seed(TRAIN_STATS_SEED + i), dtype=torch.float64)
+        out[k] = (float(g.double().norm()), float((g.double() * r).sum()))
+    return out
+
+
+def golden_train():
+    """the body of WaymoMotion.training_step (waymo_motion.py:313-385) restated around the REAL
+    reference modules - TrafficBots (map / TL / agent encoders, LatentEncoder posterior + prior, NaviPredictor, heads),
+    Dynamics, TeacherForcing, TrafficRuleChecker, RolloutBuffer, DifferentiableReward, TrainingMetrics (BalancedKL) -
+    with autograd. The step's random draws are the inputs of synth.make_train_batch (forced agents are OR-ed into the
+    TeacherForcing mask, the latent sample is mean + std * eps = Normal.rsample). Stores the loss terms and two
+    statistics per gradient tensor. Dropout is off (model.eval(): the p = 0 configuration; the hot path has no
+    batch-norm, so eval only switches dropout)."""
+    from utils.buffer import RolloutBuffer
+    from utils.rewards import DifferentiableReward
+    from models.metrics.training import TrainingMetrics
+    from trafficbotsv1_5_b200.training import TRAIN_CFG
+    cfg = config.default_model_cfg()
+    P = params.init_params(cfg, 0, with_navi_predictor=True, with_latent_post=True)
+    model = TrafficBots(**DictConfig(cfg))
+    sd = model.state_dict()
+    mine = {k: tuple(v) for k, v in params.latent_post_shapes(cfg).items()}
+    ref = {k: tuple(v.shape) for k, v in sd.items() if k.startswith(("latent_encoder.tl_encoder_post.",
+           "latent_encoder.ag_encoder_post.", "latent_encoder.latent_dist_post.")) and not k.endswith((".freqs", "hist_ohe"))}
+    assert ref == mine, set(ref) ^ set(mine)
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected, unexpected
+    assert all(m.startswith(("latent_encoder.tl_encoder_prior.", "latent_encoder.ag_encoder_prior.",
+                             "latent_encoder.latent_dist_prior.")) or m.endswith((".freqs", "pl_node_ohe", "hist_ohe"))
+               for m in missing), missing
+    model.eval()
+    tc = dict(TRAIN_CFG)
+    shape = dict(n_sc=2, n_ag=28, n_mp=70, n_tl=27, seed=3000, boundary=120.0)
+    n_steps = 14
+    batch = synth.make_train_batch(**shape)
+    out = {}
+    for variant in ("posterior", "prior_kl"):
+        if variant == "prior_kl":
+            batch["rollout_prior"] = True
+            tc["kl_free_nats"] = 0.01
+        model.zero_grad()
+        mp_tokens = model.mp_encoder(batch["sc/mp_valid"], batch["sc/mp_attr"], batch["sc/mp_pose"], batch["ref/mp_type"])
+        tl_tokens = model.tl_encoder.pre_compute(tl_valid=batch["sc/tl_valid"], tl_attr=batch["sc/tl_attr"],
+                                                 tl_pose=batch["sc/tl_pose"], **mp_tokens)                       # :317-324
+        lat = dict(ag_attr=batch["sc/ag_attr"], ag_type=batch["ref/ag_type"], mp_tokens=mp_tokens, tl_tokens=tl_tokens)
+        latent_post = model.latent_encoder(ag_valid=batch["gt/ag_valid"], ag_motion=batch["gt/ag_motion"],
+                                           ag_pose=batch["gt/ag_pose"], tl_state=batch["gt/tl_state"], posterior=True, **lat)
+        latent_prior = model.latent_encoder(ag_valid=batch["sc/ag_valid"], ag_motion=batch["sc/ag_motion"],
+                                            ag_pose=batch["sc/ag_pose"], tl_state=batch["sc/tl_state"], posterior=False, **lat)
+        ag_latent = latent_prior if batch.get("rollout_prior", False) else latent_post                          # :348
+        ag_latent_valid = ag_latent.valid
+        ag_latent = ag_latent.mean + ag_latent.stddev * batch["ag_latent_eps"]                                  # rsample
+        navi_pred = model.navi_predictor(ag_valid=batch["sc/ag_valid"], ag_attr=batch["sc/ag_attr"],
+                                         ag_motion=batch["sc/ag_motion"], ag_pose=batch["sc/ag_pose"],
+                                         ag_type=batch["ref/ag_type"], **mp_tokens)                              # :352-359
+        # ---- reactive_replay (:386-437) -> rollout (:206-311) -> forward (:118-204)
+        rule_checker = TrafficRuleChecker(
+            mp_boundary=batch["map/boundary"], mp_valid=batch["map/valid"], mp_type=batch["map/type"],
+            mp_pos=batch["map/pos"], mp_dir=batch["map/dir"], ag_type=batch["ref/ag_type"], ag_size=batch["ref/ag_size"],
+            ag_goal=None, ag_dest=batch["gt/ag_navi"], tl_valid=tl_tokens["tl_token_valid"],
+            tl_pose=tl_tokens["tl_token_pose"], disable_check=True)
+        ag_tokens = dict(ag_type=batch["ref/ag_type"], ag_size=batch["ref/ag_size"], ag_attr=batch["sc/ag_attr"],
+                         gt_valid=batch["gt/ag_valid"], gt_pose=batch["gt/ag_pose"], gt_motion=batch["gt/ag_motion"],
+                         ag_latent=ag_latent, ag_latent_valid=ag_latent_valid, ag_navi=batch["gt/ag_navi"],
+                         ag_navi_valid=batch["gt/ag_valid"].any(-1))
+        tl_state_gt = batch["gt/tl_state"]
+        tf = TeacherForcing(step_spawn_agent=tc["step_spawn_agent"], step_warm_start=tc["step_warm_start"],
+                            prob_forcing_agent=0.0)
+        tf.init(ag_valid=ag_tokens["gt_valid"], ag_pose=ag_tokens["gt_pose"], ag_motion=ag_tokens["gt_motion"],
+                tl_state=tl_state_gt, current_epoch=0)
+        tf.ag_teacher_forcing |= batch["tf/forcing_agent"].unsqueeze(-1) & ag_tokens["gt_valid"]              # teacher_forcing.py:87-92
+        dyn = make_dynamics()
+        dyn.init(tl_state=tl_state_gt, **ag_tokens)
+        model.init()
+        reward_fn = DifferentiableReward(
+            l_pos=DictConfig(dict(weight=tc["w_pos"], criterion="SmoothL1Loss")),
+            l_rot=DictConfig(dict(weight=tc["w_rot"], criterion="SmoothL1Loss", angular_type="cosine")),
+            l_spd=DictConfig(dict(weight=tc["w_spd"], criterion="SmoothL1Loss")),
+            w_collision=0, use_il_loss=True, reduce_collsion_with_max=True, is_enabled=True)
+        buf = RolloutBuffer(n_steps, 10)
+        buf.add_navi_log_prob(torch.zeros_like(batch["sc/ag_attr"][:, :, 0]), ag_tokens["ag_navi_valid"])
+        for step in range(1, n_steps + 1):
+            ag_override, tl_override = tf.get(step, dyn.ag_valid, dyn.ag_pose, dyn.ag_motion)
+            ag_valid = dyn.ag_valid
+            action_dist, tl_dist = model(
+                ag_valid=ag_valid, ag_pose=dyn.ag_pose.detach(), ag_motion=dyn.ag_motion.detach(), ag_attr=dyn.ag_attr,
+                ag_type=dyn.ag_type, ag_latent=dyn.ag_latent, ag_latent_valid=dyn.ag_latent_valid, ag_navi=dyn.ag_navi,
+                ag_navi_valid=dyn.ag_navi_valid, ag_navi_updated=dyn.ag_navi_updated, tl_state=dyn.tl_state.detach(),
+                tl_tokens=tl_tokens, mp_tokens=mp_tokens)                                                        # :158-177
+            _, action_log_prob = dyn.update_ag(action_dist, True, None)
+            pred = dict(action_log_prob=action_log_prob, pred_valid=ag_valid, pred_pose=dyn.ag_pose,
+                        pred_motion=dyn.ag_motion)
+            dyn.override_ag(ag_override)
+            dyn.override_tl(tl_dist, tl_override)
+            violation = rule_checker.check(pred["pred_valid"], pred["pred_pose"], pred["pred_motion"], dyn.tl_state)
+            gv, gp, gm = (ag_tokens[k][:, :, step] for k in ("gt_valid", "gt_pose", "gt_motion"))
+            reward = reward_fn.get(pred_valid=pred["pred_valid"], pred_pose=pred["pred_pose"],
+                                   pred_motion=pred["pred_motion"], gt_valid=gv, gt_pose=gp, gt_motion=gm,
+                                   ag_size=ag_tokens["ag_size"])
+            nll = -1.0 * tl_dist.log_prob(tl_state_gt[:, :, step].max(-1)[1])                                    # :270-277
+            buf.add(violation=violation, diffbar_reward=reward, tl_state_nll=nll,
+                    tl_state_nll_invalid=tl_tokens["tl_token_invalid"], vis_dict={}, ag_override=ag_override, **pred)
+            dyn.disable_ag(violation, gv)
+            dyn.disable_navi(violation)
+        buf.finish()
+        buf.flatten_joint_future(1)
+        metrics = TrainingMetrics(prefix="t", train_navi=True, train_latent=True, w_vae_kl=tc["w_vae_kl"],
+                                  kl_balance_scale=tc["kl_balance_scale"], kl_free_nats=tc["kl_free_nats"],
+                                  kl_for_unseen_agent=True, w_diffbar_reward=tc["w_diffbar_reward"], w_navi=tc["w_navi"],
+                                  w_tl_state=tc["w_tl_state"], w_relevant_agent=0, p_loss_for_irrelevant=1.0,
+                                  step_training_start=tc["step_training_start"], temporal_discount=-1.0,
+                                  loss_for_teacher_forcing=True)
+        md = metrics(buffer=buf, ag_role=batch["ref/ag_role"], navi_pred=navi_pred, navi_gt=batch["gt/ag_navi"],
+                     latent_post=latent_post, latent_prior=latent_prior)
+        md["t/loss"].backward()
+        grads = {k: p.grad for k, p in model.named_parameters() if k in P}
+        out[variant] = dict(terms={k[2:]: float(v) for k, v in md.items() if torch.is_tensor(v) and v.dim() == 0},
+                            grad_stats=grad_stats(grads), pred_valid=buf.pred_valid.squeeze(1).clone(),
+                            pred_pose=buf.pred_pose.squeeze(1).detach().clone())
+        print(variant, out[variant]["terms"], "tensors with gradient:", sum(g is not None for g in grads.values()))
+    fix = dict(shape=shape, n_steps=n_steps, param_seed=0, stats_seed=TRAIN_STATS_SEED, **out)
+    torch.save(fix, os.path.join(HERE, "train_small.pt"))
+    print("train_small.pt", os.path.getsize(os.path.join(HERE, "train_small.pt")) // 1024, "KiB")
+
+
 @torch.no_grad()
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "train":  # only (re)generate train_small.pt
+        with torch.enable_grad():
+            return golden_train()
     if len(sys.argv) > 1 and sys.argv[1] == "navi":  # only (re)generate navi_pred.pt
         return golden_navi_predictor()
     if len(sys.argv) > 1 and sys.argv[1] == "wosac":  # only (re)generate wosac_post.pt
