@@ -351,10 +351,13 @@ def golden_train():
                              "latent_encoder.latent_dist_prior.")) or m.endswith((".freqs", "pl_node_ohe", "hist_ohe"))
                for m in missing), missing
     model.eval()
+    model.double()  # float64 end to end: the fixture then pins the oracle to ~1e-9 instead of fp32 summation noise
     tc = dict(TRAIN_CFG)
     shape = dict(n_sc=2, n_ag=28, n_mp=70, n_tl=27, seed=3000, boundary=120.0)
     n_steps = 14
-    batch = synth.make_train_batch(**shape)
+    batch = {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v)
+             for k, v in synth.make_train_batch(**shape).items()}  # drawn in fp32 (the seeded scene), then widened
+    torch.set_default_dtype(torch.float64)
     out = {}
     for variant in ("posterior", "prior_kl"):
         if variant == "prior_kl":
@@ -436,11 +439,12 @@ def golden_train():
                      latent_post=latent_post, latent_prior=latent_prior)
         md["t/loss"].backward()
         grads = {k: p.grad for k, p in model.named_parameters() if k in P}
-        out[variant] = dict(terms={k[2:]: float(v) for k, v in md.items() if torch.is_tensor(v) and v.dim() == 0},
+        out[variant] = dict(terms={k[2:]: float(v.detach()) for k, v in md.items() if torch.is_tensor(v) and v.dim() == 0},
                             grad_stats=grad_stats(grads), pred_valid=buf.pred_valid.squeeze(1).clone(),
                             pred_pose=buf.pred_pose.squeeze(1).detach().clone())
         print(variant, out[variant]["terms"], "tensors with gradient:", sum(g is not None for g in grads.values()))
-    fix = dict(shape=shape, n_steps=n_steps, param_seed=0, stats_seed=TRAIN_STATS_SEED, **out)
+    torch.set_default_dtype(torch.float32)
+    fix = dict(shape=shape, n_steps=n_steps, param_seed=0, stats_seed=TRAIN_STATS_SEED, dtype="float64", **out)
     torch.save(fix, os.path.join(HERE, "train_small.pt"))
     print("train_small.pt", os.path.getsize(os.path.join(HERE, "train_small.pt")) // 1024, "KiB")
 
