@@ -93,7 +93,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------ CPU arm
-def cpu_rollout_rate(n_threads, n_sc=1, R=8, iters=6):
+def cpu_rollout_rate(n_threads, n_sc=1, R=8, iters=6, rule_checks=False):
     """The reference algorithm (oracle port, torch CPU fp32) on a bounded sample of the same workload shape:
     n_sc scene x R rollouts x `iters` policy iterations (history warm-up included, scene encoding excluded, like
     `value`). Rate is scaled to the metric's 80-of-90 accounting."""
@@ -107,9 +107,9 @@ def cpu_rollout_rate(n_threads, n_sc=1, R=8, iters=6):
         mp = O.map_encoder(P, cfg, sz, batch["sc/mp_valid"], batch["sc/mp_attr"], batch["sc/mp_pose"])
         tl = O.tl_pre_compute(P, cfg, sz, batch["sc/tl_valid"], batch["sc/tl_attr"], batch["sc/tl_pose"], mp)
         mp = {k: mp[k] for k in ("mp_token_invalid", "mp_token_feature", "mp_token_pose")}
-        O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, 1, mp=mp, tl=tl)  # warm-up
+        O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, 1, mp=mp, tl=tl, rule_checks=rule_checks)  # warm-up
         t0 = time.perf_counter()
-        O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, iters, mp=mp, tl=tl)
+        O.rollout(P, cfg, sz, config.DYNAMICS_CFG, config.ROLLOUT_CFG, batch, R, iters, mp=mp, tl=tl, rule_checks=rule_checks)
         dt = time.perf_counter() - t0
     per_iter = dt / iters
     rate = n_sc * R * N_COUNTED / (N_ITER * per_iter)
@@ -637,6 +637,11 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         rate, sample, _ = cpu_rollout_rate(cores, 1, 16, 16)
         line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample)
+        try:  # the same with every logging-only TrafficRuleChecker check on ("with and without")
+            rate_rc, sample_rc, _ = cpu_rollout_rate(cores, 1, 8, 6, rule_checks=True)
+            line["cpu_baseline"]["with_rule_checks"] = dict(value=rate_rc, sample=sample_rc)
+        except Exception as e:  # a side leg must never take the line down
+            line["cpu_baseline"]["with_rule_checks"] = dict(unavailable=f"{type(e).__name__}: {e}"[:200])
     if rank == 0:
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
