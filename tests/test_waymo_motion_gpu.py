@@ -209,3 +209,30 @@ def test_rollout_dropin_refuses_training_configurations():
         _check_teacher_forcing(TeacherForcing(prob_scheduled_sampling=0.5))
     with pytest.raises(NotImplementedError):
         Dynamics(veh=dict(_target_="utils.dynamics.StateIntegrator"), ped={}, cyc={}, navi_mode="dest")
+
+
+def test_training_step_dropin_trains_the_module():
+    """`WaymoMotionRollout.training_step`: the module's own parameters are the leaves of the CUDA training step, so a
+    torch optimiser over `model.parameters()` trains it. Same loss as a stand-alone `TrainStep` on the same weights; a
+    few AdamW steps on one batch lower the loss."""
+    from trafficbotsv1_5_b200.traffic_bots import TrafficBots
+    from trafficbotsv1_5_b200.training import TrainStep
+    from trafficbotsv1_5_b200.waymo_motion import WaymoMotionRollout
+    model = TrafficBots(seed=0, training_modules=True).cuda()
+    wm = WaymoMotionRollout(model, time_step_end=14)
+    batch = synth.make_train_batch(2, n_ag=28, n_mp=70, n_tl=27, seed=3000, boundary=120.0)
+    ref = TrainStep({k: v.detach().clone() for k, v in model.named_parameters()}, model.cfg, "cuda",
+                    train_cfg=dict(time_step_end=14))
+    loss_ref = float(ref.step(batch, backward=False)["loss"].detach())
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-4, weight_decay=1e-1, betas=(0.9, 0.95))
+    losses = []
+    for _ in range(4):
+        model.zero_grad()
+        out = wm.training_step(batch)
+        losses.append(float(out["loss"].detach()))
+        assert sum(p.grad is not None for p in model.parameters()) > 600
+        opt.step()
+    assert abs(losses[0] - loss_ref) < 1e-4 * abs(loss_ref), (losses[0], loss_ref)
+    assert losses[-1] < losses[0] - 1e-3, losses
+    # the updated weights drive the inference path of the same module (fused weights are rebuilt on a version change)
+    assert model._runner() is not None

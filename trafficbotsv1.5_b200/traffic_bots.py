@@ -54,14 +54,19 @@ class _Tree(nn.Module):
 
 
 class TrafficBots(_Tree):
-    def __init__(self, cfg: Optional[dict] = None, precision: int = 0, seed: int = 0, **overrides) -> None:
+    def __init__(self, cfg: Optional[dict] = None, precision: int = 0, seed: int = 0, training_modules: bool = False,
+                 **overrides) -> None:
+        """`training_modules`: also register `navi_predictor.*` and the posterior half of `latent_encoder.*` (the
+        modules only the training step uses; a full reference checkpoint then loads with strict=False leaving only the
+        unused prior encoders unmatched)."""
         super().__init__()
         self.cfg = cfg or C.default_model_cfg()
         self.cfg.update(overrides)
         self.sz = C.derived_sizes(self.cfg)
         self.precision = precision
         self.temp_window_size = self.cfg["temp_window_size"]
-        for k, v in params.init_params(self.cfg, seed).items():
+        for k, v in params.init_params(self.cfg, seed, with_navi_predictor=training_modules,
+                                       with_latent_post=training_modules).items():
             self.add(k, v)
         d, W, Ln = self.cfg["hidden_dim"], self.temp_window_size, self.cfg["n_mp_pl_node"]
         # persistent buffers of the reference (App. B); one shared PoseEmb is registered under several names
@@ -83,7 +88,8 @@ class TrafficBots(_Tree):
 
     # ------------------------------------------------------------------------------------------ weights -> kernels
     def _runner(self) -> HotPathModel:
-        sd = {k: v for k, v in self.state_dict().items() if not k.endswith(("freqs", "_ohe"))}
+        sd = {k: v for k, v in self.state_dict().items() if not k.endswith(("freqs", "_ohe"))
+              and not k.startswith("latent_encoder.")}
         ver = tuple((k, v._version, v.data_ptr()) for k, v in sd.items())
         if self._hp_ver != ver:
             dev = next(iter(sd.values())).device

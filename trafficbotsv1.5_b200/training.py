@@ -107,14 +107,24 @@ class TrainStep:
     `latent_encoder.{tl,ag}_encoder_post.*` + `latent_encoder.latent_dist_post.*` and `navi_predictor.*`)."""
 
     def __init__(self, P: Dict[str, Tensor], cfg: Optional[dict] = None, device="cuda", precision: int = 0,
-                 train_cfg: Optional[dict] = None, dynamics_cfg: Optional[dict] = None):
+                 train_cfg: Optional[dict] = None, dynamics_cfg: Optional[dict] = None, share_leaves: bool = False):
+        """`share_leaves`: use the given tensors themselves as the leaves (an nn.Module's CUDA fp32 parameters: their
+        `.grad` is then what a torch optimiser over the module updates) instead of private device copies."""
         L.load()
         self.cfg = cfg or C.default_model_cfg()
         self.sz = C.derived_sizes(self.cfg)
         self.dev = torch.device(device)
         self.tc = dict(TRAIN_CFG, **(train_cfg or {}))
         self.T = self.tc["time_step_end"]
-        self.params = {k: v.detach().to(self.dev, torch.float32).contiguous().requires_grad_(True) for k, v in P.items()}
+        if share_leaves:
+            for k, v in P.items():
+                if not (v.is_cuda and v.dtype == torch.float32 and v.is_contiguous() and v.is_leaf):
+                    raise ValueError(f"share_leaves: {k} must be a contiguous fp32 CUDA leaf tensor")
+                v.requires_grad_(True)
+            self.params = dict(P)
+        else:
+            self.params = {k: v.detach().to(self.dev, torch.float32).contiguous().requires_grad_(True)
+                           for k, v in P.items()}
         main = {k: v for k, v in self.params.items() if not k.startswith("latent_encoder.")}
         self.eng = RolloutEngine({k: v.detach() for k, v in main.items() if not k.startswith("navi_predictor.")},
                                  self.cfg, device, precision=0, n_rollout=1, step_end=self.T, use_graph=False,

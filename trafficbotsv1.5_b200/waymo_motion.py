@@ -315,6 +315,7 @@ class WaymoMotionRollout:
         self.n_joint_future, self.current_epoch = n_joint_future, current_epoch
         self.training = False
         self._engines: Dict[tuple, RolloutEngine] = {}
+        self._train_step = None
 
     def _engine(self, R: int, step_end: int, rule_checks: bool) -> RolloutEngine:
         hp = self.model._runner()  # (re)builds the fused weights when a parameter changed
@@ -329,6 +330,26 @@ class WaymoMotionRollout:
                                                step_end=step_end, rule_checks=rule_checks, record_feedback=True,
                                                dynamics_cfg=dyn)
         return self._engines[key]
+
+    def training_step(self, batch: Dict[str, Tensor], batch_idx: int = 0, n_steps: Optional[int] = None,
+                      train_cfg: Optional[dict] = None) -> Dict[str, Tensor]:
+        """Body of `WaymoMotion.training_step` (waymo_motion.py:313-385) on the CUDA training path (training.TrainStep;
+        the model must have been built with `training_modules=True`). The module's own parameters are the leaves: after
+        the call their `.grad` holds the gradients (a torch optimiser over `model.parameters()` steps on them; call
+        `model.zero_grad()` between steps). `batch`: the pre-processed dict plus the step's random draws
+        ("tf/forcing_agent", "ag_latent_eps", optional "rollout_prior"). Returns the loss terms (training.py:162-189)."""
+        from .training import TrainStep
+        if self._train_step is None:
+            leaves = {k: p for k, p in self.model.named_parameters()}
+            acc, yaw = self.dynamics.limits() if hasattr(self.dynamics, "limits") else (
+                [d._max_acc for d in self.dynamics.ag_dynamics], [d._max_yaw_rate for d in self.dynamics.ag_dynamics])
+            dyn = dict(veh=dict(max_acc=acc[0], max_yaw_rate=yaw[0]), ped=dict(max_acc=acc[1], max_yaw_rate=yaw[1]),
+                       cyc=dict(max_acc=acc[2], max_yaw_rate=yaw[2]), dt=self.dynamics.dt)
+            dev = next(iter(leaves.values())).device
+            self._train_step = TrainStep(leaves, self.model.cfg, dev, precision=min(self.model.precision, 1),
+                                         train_cfg=dict(train_cfg or {}, time_step_end=self.time_step_end),
+                                         dynamics_cfg=dyn, share_leaves=True)
+        return self._train_step.step(batch, n_steps=n_steps)
 
     @torch.no_grad()
     def rollout(self, ag_tokens: Dict[str, Tensor], mp_tokens: Dict[str, Tensor], tl_tokens: Dict[str, Tensor],
