@@ -593,6 +593,9 @@ def run_ours(args):
                                 policy_iterations=N_ITER, counted_steps=N_COUNTED, rule_checks=bool(args.rule_checks),
                                 l2="per-iteration working set (>1 GB of activations) exceeds the 126 MB L2; no flush",
                                 launches_per_policy_iteration=eng.launches_per_step, gather_verified=gather_ok,
+                                agent_slots=(f"{eng._st['A']} of {eng._A_full} per scene: slots without a valid ground-truth step can never "
+                                             f"become valid and are dropped for the rollout, results scattered back "
+                                             f"(DESIGN.md 6)" if eng._perm is not None else f"{eng._A_full} (no padding dropped)"),
                                 warm_start_dedup=f"encoders of the {eng._s0} teacher-forced (rollout-invariant) leading steps "
                                                  f"run once per scene as one batch, inside the timed loop; steps "
                                                  f"{eng._s0 + 1}..{N_ITER} per rollout (DESIGN.md 6)" if eng._s0 else "off"),

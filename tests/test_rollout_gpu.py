@@ -628,3 +628,33 @@ def test_warm_start_dedup_matches_per_rollout_encoding(precision, gap):
     tol = 1e-4 if precision == 0 else 2e-3
     assert maxerr(a["pred_pose"], b["pred_pose"]) < tol, maxerr(a["pred_pose"], b["pred_pose"])
     assert maxerr(a["pred_motion"], b["pred_motion"]) < 5 * tol  # accelerations / yaw rates of up to 7 per second
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_agent_compaction_matches_padded_run(precision):
+    """Agent compaction (engine._compact): slots that are invalid at every ground-truth step can never become valid, so
+    they are dropped for the whole rollout and results() scatters back to the caller's agent order. Against the same
+    engine with the padding kept: masks identical, dropped slots exactly zero, poses within 1e-5 m (fp32; the KNN lists
+    are the same sets in the same order, only the row tiling of the GEMMs changes) / 2e-3 m (16-bit mode)."""
+    shape = dict(n_sc=2, n_ag=64, n_mp=96, n_tl=30, seed=91, boundary=110.0)
+    eng, batch, P, cfg = _engine(shape, 3, 20, precision=precision, record_feedback=True)
+    batch["sc/ag_valid"][:, 40:] = False            # 24 padded slots at the end ...
+    batch["sc/ag_valid"][0, 3] = False              # ... and holes in the middle (per scene different)
+    batch["sc/ag_valid"][1, 7] = False
+    batch["sc/ag_valid"][1, 11] = False
+    batch["ag_navi_valid"] = batch["sc/ag_valid"].any(-1)
+    batch["ag_latent_valid"] = batch["sc/ag_valid"].any(-1)
+    eng.prepare(batch)
+    assert eng._perm is not None and eng._st["A"] == 40 and eng._A_full == 64
+    a = {k: v.clone() for k, v in eng.run().items()}
+    eng.compact_agents = False
+    eng.prepare(batch)
+    assert eng._perm is None and eng._st["A"] == 64
+    b = eng.run()
+    for k in ("pred_valid", "tl_state", "final_valid", "final_navi_valid", "outside_map", "dest_reached"):
+        assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+    never = ~batch["sc/ag_valid"].any(-1).repeat_interleave(3, 0).to(DEV)
+    assert float(a["pred_pose"][never].abs().max()) == 0.0
+    tol = 1e-5 if precision == 0 else 2e-3
+    assert maxerr(a["pred_pose"], b["pred_pose"]) < tol, maxerr(a["pred_pose"], b["pred_pose"])
+    assert a["joint_pose"].shape == b["joint_pose"].shape

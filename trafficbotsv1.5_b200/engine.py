@@ -111,6 +111,13 @@ class RolloutEngine:
         # truth alone, so the agent / TL encoders of those steps run ONCE per scene, all steps in one batch (_warm_*).
         self.warm_dedup = True
         self._s0 = 0         # number of leading policy steps handled that way for the prepared batch
+        # Agent compaction: agents without a single valid ground-truth step can never become valid (spawning needs
+        # ground truth, teacher_forcing.py:51-82), so every scene's agents are reordered valid-first and the padding
+        # beyond the largest valid count of the batch (rounded up to 8) is dropped for the whole rollout; results()
+        # scatters back to the caller's agent order. WOMD scenes are padded to 128 agents, few have that many.
+        self.compact_agents = True
+        self._perm = None    # [n_sc, A_eff] original agent index of every kept slot (None: nothing dropped)
+        self._A_full = 0
         self.graph_steps = 0  # graph replays of the last run() (bench.py: launch accounting)
         self._graph = None   # (graph for odd steps, graph for even steps): the TL branch is double-buffered
         self._host_step = 1  # parity source for eager _step calls
@@ -454,8 +461,47 @@ class RolloutEngine:
         return n_do
 
     # ---------------------------------------------------------------------------------------------- public API
+    _AGENT_KEYS = {"sc/ag_valid": 1, "sc/ag_pose": 1, "sc/ag_motion": 1, "sc/ag_attr": 1, "ref/ag_type": 1, "ref/ag_size": 1,
+                   "ag_latent": 2, "ag_latent_valid": 1, "ag_navi_valid": 1, "ref/ag_role": 1}
+
+    def _compact(self, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        """Drop the agent slots that are invalid at every ground-truth step in all scenes of the batch (see
+        `compact_agents`). Returns the batch to load (the caller's dict is not modified)."""
+        gt_valid = batch["sc/ag_valid"]
+        n_sc, A, _ = gt_valid.shape
+        self._perm, self._A_full = None, A
+        if not self.compact_agents:
+            return batch
+        ever = gt_valid.any(-1)
+        a_eff = max(int(ever.sum(1).max()), self.sz["k_ag2ag"] + 1)
+        a_eff = min(A, (a_eff + 7) // 8 * 8)
+        if a_eff >= A:
+            return batch
+        perm = torch.sort((~ever).to(torch.uint8), dim=1, stable=True)[1][:, :a_eff]           # valid first, original order kept
+        out = dict(batch)
+
+        def take(t, dim):
+            idx = perm.to(t.device)
+            shape = [1] * t.dim()
+            shape[0], shape[dim] = n_sc, a_eff
+            idx = idx.view(shape).expand([t.shape[i] if i != dim else a_eff for i in range(t.dim())])
+            return torch.gather(t, dim, idx)
+
+        for k, dim in self._AGENT_KEYS.items():
+            if k in batch and batch[k].shape[0] == n_sc:
+                out[k] = take(batch[k], dim)
+        dest = batch["agent/dest"]
+        out["agent/dest"] = take(dest, 1 if dest.dim() == 2 else 2)
+        for k in ("ag_latent_valid", "ag_navi_valid"):  # [n_sc, A] or per rollout [n_sc * R, A]
+            if k in batch and batch[k].shape[0] != n_sc:
+                t = batch[k].view(n_sc, -1, A)
+                out[k] = take(t, 2).reshape(-1, a_eff)
+        self._perm = perm.to(self.dev)
+        return out
+
     def prepare(self, batch: Dict[str, Tensor], static: Optional[dict] = None) -> dict:
         """Upload a batch of scenes, encode them (unless `static` is given) and build the step graph."""
+        batch = self._compact(batch)
         n_sc, A, n_gt = batch["sc/ag_valid"].shape
         n_tl = batch["sc/tl_valid"].shape[1]
         _, n_mp, n_node = batch["sc/mp_valid"].shape
@@ -530,9 +576,21 @@ class RolloutEngine:
         vio = {k: st[f"vio_{k}"].bool() for k in VIOLATIONS} if self.rule_checks else {}
         if self.record_feedback:
             vio.update(outside_map=st["fb_outside"].bool(), dest_reached=st["fb_reached"].bool())
-        return dict(**vio, pred_valid=st["pred_valid"].bool(), pred_pose=st["pred_pose"], pred_motion=st["pred_motion"],
-                    tl_state=tl.bool(), final_valid=st["valid"].bool(), final_navi_valid=~st["navi_invalid"],
-                    joint_pose=st["pred_pose"].view(n_sc, R, A, self.T, 3))
+        out = dict(**vio, pred_valid=st["pred_valid"].bool(), pred_pose=st["pred_pose"], pred_motion=st["pred_motion"],
+                   final_valid=st["valid"].bool(), final_navi_valid=~st["navi_invalid"])
+        if self._perm is not None:  # back to the caller's agent order; the dropped (never valid) slots read as zeros
+            A = self._A_full
+            sc = torch.arange(n_sc, device=self.dev)[:, None]
+
+            def scatter(t):
+                full = t.new_zeros((n_sc, R, A) + tuple(t.shape[2:]))
+                full[sc, :, self._perm] = t.view((n_sc, R, -1) + tuple(t.shape[2:])).transpose(1, 2)
+                return full.view((n_sc * R, A) + tuple(t.shape[2:]))
+
+            out = {k: scatter(v) for k, v in out.items()}
+        out["tl_state"] = tl.bool()
+        out["joint_pose"] = out["pred_pose"].view(n_sc, R, A, self.T, 3)
+        return out
 
     @torch.no_grad()
     def post_process_wosac(self, res: Dict[str, Tensor], batch: Dict[str, Tensor], n_keep: int = 32,
