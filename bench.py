@@ -680,7 +680,7 @@ def run_train(args):
     def step():
         ts.zero_grad()
         out = ts.step(batch)
-        return float(out["loss"])  # device -> host read of the step's result
+        return float(out["loss"].detach())  # device -> host read of the step's result
 
     def barrier():
         torch.cuda.synchronize()

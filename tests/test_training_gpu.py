@@ -240,7 +240,7 @@ def _oracle_f64(P, cfg, sz, tc, b, n_steps):
     return ref, Pg
 
 
-@pytest.mark.parametrize("variant", ["full", "no_latent_encoder", "prior_rollout_kl"])
+@pytest.mark.parametrize("variant", ["full", "no_latent_encoder", "prior_rollout_kl", "padded_agents"])
 def test_training_step_vs_oracle_autograd(variant):
     """The whole training_step body (map / TL / latent posterior / destination predictor / 14-step teacher-forced closed
     loop / TrainingMetrics) on the CUDA path against the oracle evaluated in float64: every loss term within 2e-4
@@ -249,7 +249,13 @@ def test_training_step_vs_oracle_autograd(variant):
     cfg = config.default_model_cfg()
     sz = config.derived_sizes(cfg)
     P = params.init_params(cfg, 0, with_navi_predictor=True, with_latent_post=variant != "no_latent_encoder")
-    b = synth.make_train_batch(2, n_ag=28, n_mp=70, n_tl=27, seed=3000, boundary=120.0)
+    b = synth.make_train_batch(2, n_ag=40 if variant == "padded_agents" else 28, n_mp=70, n_tl=27, seed=3000,
+                               boundary=120.0)
+    if variant == "padded_agents":  # never-valid slots (scattered): the CUDA path drops them (TrainStep._compact), the
+        for k in ("gt/ag_valid", "sc/ag_valid"):  # oracle carries them as masked rows - same loss, same gradients
+            b[k][0, 2::3] = False
+            b[k][1, 1::3] = False
+        b["ag_navi_valid"] = b["ag_latent_valid"] = b["gt/ag_valid"].any(-1)
     tc = dict(TRAIN_CFG)
     if variant == "prior_rollout_kl":  # rollout on the prior sample; free nats below the KL so its gradient is exercised
         b["rollout_prior"] = True
@@ -259,6 +265,8 @@ def test_training_step_vs_oracle_autograd(variant):
     ts = TrainStep(P, cfg, DEV, precision=0, train_cfg=tc)
     out = ts.step(b, n_steps=n_steps)
     torch.cuda.synchronize()
+    if variant == "padded_agents":
+        assert ts.eng._st["A"] == 32  # 40 slots, at most 27 ever valid per scene -> 32 kept
     assert torch.equal(out["pred_valid"].cpu().view_as(ref["pred_valid"]), ref["pred_valid"])
     assert float((out["pred_pose"].cpu().double().view_as(ref["pred_pose"]) - ref["pred_pose"]).abs().max()) < 1e-3
     for k in ("diffbar_reward", "tl_state_loss", "vae_kl", "navi_loss", "loss"):

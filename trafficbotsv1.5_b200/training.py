@@ -142,6 +142,7 @@ class TrainStep:
                                    cfg_l, self.sz, device, precision)
         self.has_navi = any(k.startswith("navi_predictor.") for k in self.params)
         self.bucket = None
+        self.compact_agents = True
 
     def zero_grad(self) -> None:
         if self.bucket is not None:
@@ -187,6 +188,7 @@ class TrainStep:
         m, eng, tc, dev = self.model, self.eng, self.tc, self.dev
         T = n_steps or self.T
         assert T <= self.T
+        batch, perm, A_full = self._compact(batch)
         self._batch = batch
         g = lambda k: batch[k].to(dev)  # noqa: E731
         self._marks = [("start", self._event())]
@@ -343,6 +345,12 @@ class TrainStep:
                 self.bucket.all_reduce()
                 self._mark("grad_all_reduce")
         out["pred_pose"], out["pred_valid"] = st["pred_pose"][:, :, :T], pred_valid.bool()
+        if perm is not None:  # back to the caller's agent order (dropped slots: zeros / False)
+            sc_i = torch.arange(n_sc, device=dev)[:, None]
+            for k in ("pred_pose", "pred_valid"):
+                full = out[k].new_zeros((n_sc, A_full) + tuple(out[k].shape[2:]))
+                full[sc_i, perm.to(dev)] = out[k]
+                out[k] = full
         return out
 
     def _event(self):
@@ -384,6 +392,32 @@ class TrainStep:
                    knn_self=knn(tl["knn_self"]),
                    cross=[dict(c0, kv0=c["kv0"], T0=c["T0"], div0=T, K0=c["K0"]) for c in tl["cross"]])
         return tlb, hist.view(n_sc * T, n_tl, W, 5)
+
+    _AGENT_KEYS = ("gt/ag_valid", "gt/ag_pose", "gt/ag_motion", "gt/ag_navi", "sc/ag_valid", "sc/ag_pose", "sc/ag_motion",
+                   "sc/ag_attr", "ref/ag_type", "ref/ag_size", "ref/ag_role", "tf/forcing_agent", "ag_latent_eps",
+                   "agent/dest", "ag_navi_valid", "ag_latent_valid")
+
+    def _compact(self, batch: Dict[str, Tensor]):
+        """Agent compaction as in RolloutEngine._compact: slots without a valid ground-truth step never become valid and
+        contribute neither loss nor gradient; they are dropped for the whole step (valid-first reorder per scene, the
+        largest valid count of the batch rounded up to 8). Returns (batch to use, perm [n_sc, A_eff] or None, A)."""
+        gt_valid = batch["gt/ag_valid"]
+        n_sc, A, _ = gt_valid.shape
+        if not self.compact_agents:
+            return batch, None, A
+        ever = gt_valid.any(-1)
+        a_eff = max(int(ever.sum(1).max()), self.sz["k_ag2ag"] + 1)
+        a_eff = min(A, (a_eff + 7) // 8 * 8)
+        if a_eff >= A:
+            return batch, None, A
+        perm = torch.sort((~ever).to(torch.uint8), dim=1, stable=True)[1][:, :a_eff]
+        out = dict(batch)
+        for k in self._AGENT_KEYS:
+            if k in batch and torch.is_tensor(batch[k]) and batch[k].dim() >= 2 and batch[k].shape[:2] == (n_sc, A):
+                t = batch[k]
+                idx = perm.to(t.device).view((n_sc, a_eff) + (1,) * (t.dim() - 2)).expand((n_sc, a_eff) + tuple(t.shape[2:]))
+                out[k] = torch.gather(t, 1, idx)
+        return out, perm, A
 
     def _reset(self, st: dict) -> None:
         """time 0 of the rollout (waymo_motion.py:219-227): RolloutEngine._reset without the TL prologue of the
