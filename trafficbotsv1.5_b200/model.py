@@ -250,7 +250,7 @@ class HotPathModel:
 
     @property
     def chain_fused(self) -> bool:
-        """Head chain and FFNs as fused tcgen05 chain programs (tb_chain_run) in the tensor-core mode; TB_CHAIN=0 keeps
+        """Head chain as one fused tcgen05 chain program (tb_chain_run) in the tensor-core mode; TB_CHAIN=0 keeps
         the one-launch-per-layer path (A/B and bisecting)."""
         return os.environ.get("TB_CHAIN", "1") != "0"
 
@@ -367,16 +367,8 @@ class HotPathModel:
             proj, kv = self._in_self(f, x0, knn_self["idx"].shape[-1], f"{p}.attn")
             o, nv = self._attend(f, proj, B, S, kv, S, 1, knn_self["idx"].shape[-1], knn_self)
             src, x2 = self._out_proj(f"{p}.attn", f, o, nv, src, ln_next=f"{p}.norm2")
-        if self.kv_half and self.chain_fused and self.d == 128 and os.environ.get("TB_CHAIN_FFN", "0") == "1":
-            # FFN-1 -> ReLU -> FFN-2 -> + residual -> row mask (-> next layer's LayerNorm rows) in ONE launch: the
-            # [rows, 512] hidden tile stays on the SM (tb_chain_run, csrc/mlp_chain.cu). Measured SLOWER than the two
-            # launches at 65,536 rows (83 vs 58 us, profiles/r2_notes.md: one tile in flight per SM, the 256 KB of
-            # weights re-streamed per tile), so it is off unless TB_CHAIN_FFN=1; the head chain (20 launches -> 1) wins.
-            M = x2.shape[0]
-            y = out if out is not None else torch.empty(M, self.d, device=x2.device)
-            ln_rows = torch.empty(M, self.d, dtype=torch.float16, device=x2.device) if ln_next is not None else None
-            self._ffn_program(p, y.stride(0), ln_next).run([x2, src, ops._u8(src_inv), y, ln_rows], M)
-            return y if ln_next is None else (y, ln_rows)
+        # (A fused FFN-1 -> ReLU -> FFN-2 chain program exists - `_ffn_program`, profiles/chain_probe.py - but measured
+        # slower than the two launches at 65,536 rows (83 vs 58 us, profiles/r2_notes.md 3); it is not on this path.)
         if self.kv_half:  # FFN hidden (ReLU output) as fp16: written by the first projection, read by a kind::f16 one
             h = torch.empty(x2.shape[0], self.P[f"{p}.linear1.weight"].shape[0], dtype=torch.float16, device=x2.device)
             self._proj(x2, f"{p}.linear1", self.P[f"{p}.linear1.weight"], self.P[f"{p}.linear1.bias"], relu=True, out_h=h,
