@@ -266,7 +266,7 @@ def test_training_step_vs_oracle_autograd(variant):
     out = ts.step(b, n_steps=n_steps)
     torch.cuda.synchronize()
     if variant == "padded_agents":
-        assert ts.eng._st["A"] == 32  # 40 slots, at most 27 ever valid per scene -> 32 kept
+        assert ts.eng._st["A"] == 28  # 40 slots, at most 27 ever valid per scene -> 28 kept
     assert torch.equal(out["pred_valid"].cpu().view_as(ref["pred_valid"]), ref["pred_valid"])
     assert float((out["pred_pose"].cpu().double().view_as(ref["pred_pose"]) - ref["pred_pose"]).abs().max()) < 1e-3
     for k in ("diffbar_reward", "tl_state_loss", "vae_kl", "navi_loss", "loss"):

@@ -113,7 +113,7 @@ class RolloutEngine:
         self._s0 = 0         # number of leading policy steps handled that way for the prepared batch
         # Agent compaction: agents without a single valid ground-truth step can never become valid (spawning needs
         # ground truth, teacher_forcing.py:51-82), so every scene's agents are reordered valid-first and the padding
-        # beyond the largest valid count of the batch (rounded up to 8) is dropped for the whole rollout; results()
+        # beyond the largest valid count of the batch (rounded up to 4) is dropped for the whole rollout; results()
         # scatters back to the caller's agent order. WOMD scenes are padded to 128 agents, few have that many.
         self.compact_agents = True
         self._perm = None    # [n_sc, A_eff] original agent index of every kept slot (None: nothing dropped)
@@ -474,7 +474,7 @@ class RolloutEngine:
             return batch
         ever = gt_valid.any(-1)
         a_eff = max(int(ever.sum(1).max()), self.sz["k_ag2ag"] + 1)
-        a_eff = min(A, (a_eff + 7) // 8 * 8)
+        a_eff = min(A, (a_eff + 3) // 4 * 4)
         if a_eff >= A:
             return batch
         perm = torch.sort((~ever).to(torch.uint8), dim=1, stable=True)[1][:, :a_eff]           # valid first, original order kept

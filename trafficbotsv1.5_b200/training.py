@@ -400,14 +400,14 @@ class TrainStep:
     def _compact(self, batch: Dict[str, Tensor]):
         """Agent compaction as in RolloutEngine._compact: slots without a valid ground-truth step never become valid and
         contribute neither loss nor gradient; they are dropped for the whole step (valid-first reorder per scene, the
-        largest valid count of the batch rounded up to 8). Returns (batch to use, perm [n_sc, A_eff] or None, A)."""
+        largest valid count of the batch rounded up to 4). Returns (batch to use, perm [n_sc, A_eff] or None, A)."""
         gt_valid = batch["gt/ag_valid"]
         n_sc, A, _ = gt_valid.shape
         if not self.compact_agents:
             return batch, None, A
         ever = gt_valid.any(-1)
         a_eff = max(int(ever.sum(1).max()), self.sz["k_ag2ag"] + 1)
-        a_eff = min(A, (a_eff + 7) // 8 * 8)
+        a_eff = min(A, (a_eff + 3) // 4 * 4)
         if a_eff >= A:
             return batch, None, A
         perm = torch.sort((~ever).to(torch.uint8), dim=1, stable=True)[1][:, :a_eff]
