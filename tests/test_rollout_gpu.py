@@ -645,7 +645,8 @@ def test_agent_compaction_matches_padded_run(precision):
     batch["ag_navi_valid"] = batch["sc/ag_valid"].any(-1)
     batch["ag_latent_valid"] = batch["sc/ag_valid"].any(-1)
     eng.prepare(batch)
-    assert eng._perm is not None and eng._st["A"] == 40 and eng._A_full == 64
+    kept = (max(int(batch["sc/ag_valid"].any(-1).sum(1).max()), 26) + 3) // 4 * 4   # largest valid count, rounded up to 4
+    assert eng._perm is not None and eng._st["A"] == kept < 44 and eng._A_full == 64
     a = {k: v.clone() for k, v in eng.run().items()}
     eng.compact_agents = False
     eng.prepare(batch)
