@@ -659,3 +659,26 @@ def test_agent_compaction_matches_padded_run(precision):
     tol = 1e-5 if precision == 0 else 2e-3
     assert maxerr(a["pred_pose"], b["pred_pose"]) < tol, maxerr(a["pred_pose"], b["pred_pose"])
     assert a["joint_pose"].shape == b["joint_pose"].shape
+
+
+def test_engine_keeps_state_and_graphs_per_batch_shape():
+    """Batches with different numbers of kept agent slots alternate (agent compaction): the engine keeps state buffers
+    and captured step graphs per shape, so coming back to a shape neither re-captures nor changes the results."""
+    shape = dict(n_sc=2, n_ag=64, n_mp=96, n_tl=30, seed=93, boundary=110.0)
+    eng, b1, P, cfg = _engine(shape, 2, 14, precision=1)
+    b2 = {k: v.clone() for k, v in b1.items()}
+    b2["sc/ag_valid"][:, 36:] = False
+    b2["ag_navi_valid"] = b2["ag_latent_valid"] = b2["sc/ag_valid"].any(-1)
+    keep = ("pred_valid", "pred_pose", "tl_state")
+    r1 = {k: eng.rollout(b1)[k].clone() for k in keep}
+    g1, a1 = eng._graph, eng._st["A"]
+    r2 = {k: eng.rollout(b2)[k].clone() for k in keep}
+    g2, a2 = eng._graph, eng._st["A"]
+    assert a1 != a2 and g1 is not g2
+    for _ in range(2):
+        out = eng.rollout(b1)
+        assert eng._graph is g1 and eng._st["A"] == a1
+        assert all(torch.equal(out[k], r1[k]) for k in keep)
+        out = eng.rollout(b2)
+        assert eng._graph is g2 and eng._st["A"] == a2
+        assert all(torch.equal(out[k], r2[k]) for k in keep)

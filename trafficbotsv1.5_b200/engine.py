@@ -119,6 +119,8 @@ class RolloutEngine:
         self._perm = None    # [n_sc, A_eff] original agent index of every kept slot (None: nothing dropped)
         self._A_full = 0
         self.graph_steps = 0  # graph replays of the last run() (bench.py: launch accounting)
+        self._by_shape = {}  # shape -> (state, static, navi, graphs, launches per step) of recently used batch shapes
+        self._static = self._navi = None
         self._graph = None   # (graph for odd steps, graph for even steps): the TL branch is double-buffered
         self._host_step = 1  # parity source for eager _step calls
         self._shape = None
@@ -508,8 +510,18 @@ class RolloutEngine:
         shape = (n_sc, A, n_tl, n_gt, n_mp, n_node)
         self._sat.zero_()  # sticky from here on: scene encoding and every run() of this batch OR into it
         if self._shape != shape:
-            self._st = self._alloc(*shape)
-            self._shape, self._graph = shape, None
+            # state buffers, scene tensors and step graphs are kept per shape (a few, LRU): with agent compaction
+            # consecutive batches may differ in the number of agent slots, and a re-capture costs ~0.3 s
+            if self._shape is not None:
+                self._by_shape[self._shape] = (self._st, self._static, self._navi, self._graph,
+                                               getattr(self, "launches_per_step", 0))
+                while len(self._by_shape) > 3:
+                    self._by_shape.pop(next(iter(self._by_shape)))
+            if shape in self._by_shape:
+                self._st, self._static, self._navi, self._graph, self.launches_per_step = self._by_shape.pop(shape)
+            else:
+                self._st, self._static, self._navi, self._graph = self._alloc(*shape), None, None, None
+            self._shape = shape
         st = self._st
         self._load_state(st, batch)
         new_static = static if static is not None else self.encode_scenes(batch)
