@@ -349,13 +349,44 @@ def attention_roofline(eng, peaks):
         sel_traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("knn_select_ag_map_bytes")
     except Exception:
         sel_traffic = None
+    # ---- the projection that writes most: self in-projection of an agent layer, fp16 rows in / out in the 16-bit mode
+    roof_proj = None
+    if m.kv_half:
+        fs = m.fa[f"{p}.attn_src"]
+        x0 = m.ln(x, f"{p}.norm_src", half=True)
+        row = torch.empty(M, fs["w_in_self"].shape[0], dtype=torch.float16, device=x.device)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=x.device)
+
+        def cold(fn, reps=7):  # L2 flushed before every launch: a projection inside the step starts from HBM too
+            fn()
+            ts = []
+            for _ in range(reps):
+                flush.zero_()
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+            return sorted(ts)[len(ts) // 2]
+
+        nq = d + 4 * d
+        t_p = cold(lambda: m._proj(x0, f"{p}.attn_src.w_in_self", fs["w_in_self"], fs["b_in_self"], out_h=row, col_h=0,
+                                   il_blocks=(0, nq, nq + d)))
+        t_fill = cold(lambda: row.zero_())  # what HBM gives a kernel that only WRITES these bytes
+        pb = x0.numel() * 2 + fs["w_in_self"].numel() * 2 + row.numel() * 2
+        roof_proj = dict(bound="hbm", kernel=f"linear_tc_kernel<F16> (self in-projection, M={M}, N={row.shape[1]}, K={d}, fp16 rows)",
+                         achieved=pb / t_p / 1e9, peak=peak, unit="GB/s", frac=pb / t_p / 1e9 / peak, traffic=None,
+                         us_per_launch=t_p * 1e6, algorithmic_bytes=pb, bytes_written=row.numel() * 2,
+                         write_only_floor_us=t_fill * 1e6, frac_of_write_floor=t_fill / t_p,
+                         note="write-dominated: `write_only_floor_us` is a fill of the output alone, measured here; the "
+                              "copy peak is not reachable by a kernel that mostly writes (profiles/r2_notes.md 9)")
     roof_sel = dict(bound="hbm", kernel="knn_select_kernel<32> (agent -> map, T=1024, K=64, temporal-coherence path)",
                     achieved=sel_bytes / t_sel / 1e9, peak=peak, unit="GB/s", frac=sel_bytes / t_sel / 1e9 / peak,
                     traffic=sel_traffic, us_per_launch=t_sel * 1e6, algorithmic_bytes=sel_bytes, rows=M, valid_rows=n_src,
                     pairs_per_s=M * T_mp / t_sel,
                     note="as-issued target bytes are shared-memory / L2 traffic (the 13 KB target block of a scene is staged "
                          "once per 64 rows); the kernel is bound by compare / select instruction issue (DESIGN.md 5)")
-    return roof_sel, dict(bound="hbm", kernel=f"{kname} (agent cross-attn, K=89, {8 * kv_sz}-bit K|V / q|u / ov|z rows)", achieved=ach, peak=peak,
+    return roof_sel, roof_proj, dict(bound="hbm", kernel=f"{kname} (agent cross-attn, K=89, {8 * kv_sz}-bit K|V / q|u / ov|z rows)", achieved=ach, peak=peak,
                 unit="GB/s", frac=ach / peak, traffic=traffic, us_per_launch=t * 1e6,
                 note="as-issued gather bytes are served by L2 (~85 % hit): DRAM traffic is a fraction of them; the "
                      "kernel's real ceiling is instruction issue / latency, not HBM (DESIGN.md 5)", algorithmic_bytes=bytes_alg,
@@ -583,7 +614,7 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        roof_sel, roof = attention_roofline(eng, peaks)
+        roof_sel, roof_proj, roof = attention_roofline(eng, peaks)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=t_loop / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32" if args.precision == 0 else "tf32+fp16", data="synthetic",
@@ -599,7 +630,8 @@ def run_ours(args):
                                 warm_start_dedup=f"encoders of the {eng._s0} teacher-forced (rollout-invariant) leading steps "
                                                  f"run once per scene as one batch, inside the timed loop; steps "
                                                  f"{eng._s0 + 1}..{N_ITER} per rollout (DESIGN.md 6)" if eng._s0 else "off"),
-                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof, roofline_select=roof_sel)
+                    clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roof, roofline_select=roof_sel,
+                    roofline_projection=roof_proj)
     if rank == 0 and world == 1 and not args.rule_checks and not args.no_extras:
         # extra lines (not the headline): fp32-parity projections, and the loop with ALL TrafficRuleChecker checks on
         extras = {}
