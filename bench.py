@@ -635,11 +635,12 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.rule_checks and not args.no_extras:
         # extra lines (not the headline): fp32-parity projections, and the loop with ALL TrafficRuleChecker checks on
         extras = {}
-        for name, kw in (("fp32_projections", dict(precision=0)), ("with_rule_checks", dict(precision=args.precision,
-                                                                                           rule_checks=True))):
+        for name, kw in (("fp32_projections", dict(precision=0)), ("fp32_projections_ffma", dict(precision=0)),
+                         ("with_rule_checks", dict(precision=args.precision, rule_checks=True))):
             del eng
             torch.cuda.empty_cache()
             eng = RolloutEngine(P, cfg, dev, n_rollout=args.rollouts, step_end=N_ITER, **kw)
+            eng.model.fp32_tc = name != "fp32_projections_ffma"  # strict-parity mode: 3xTF32 on tcgen05 vs the FFMA kernel
             eng.prepare(batch)
             eng.run()
             eng.run()

@@ -143,6 +143,13 @@ int tb_linear(const void* X, int ldx, const void* W, const float* bias, int bias
               int N, int K, int relu, const uint8_t* mask_pre, const float* res, int ldr, const uint8_t* mask_post,
               int precision, void* Yh, int ldyh, int col_h, void* stream);
 
+/* 3xTF32 operand split for fp32-accurate projections on the tf32 tensor cores (the strict-parity mode of the engine):
+ *   out[m, :] = [ X[m, :] | X[m, :] - trunc_tf32(X[m, :]) | X[m, :] ]   (3K columns, ld ldo)
+ * With W3 = [W | W | W - trunc_tf32(W)] (built once per weight by the host), tb_linear(precision 1) over K' = 3K computes
+ * x_hi W_hi + x_lo W_hi + x_hi W_lo: fp32-class accuracy (2^-20 relative) at tensor-core speed, same epilogue.
+ * K and the leading dims multiples of 4, pointers 16-byte aligned. */
+int tb_tf32_split3(const float* X, int ldx, int M, int K, float* out, int ldo, void* stream);
+
 /* tb_linear with the LayerNorm of its result fused into the epilogue (tensor-core mode, N == 128):
  *   Y = X W^T + bias, masks / residual as tb_linear (no ReLU); ln_out[row] = fp16(LayerNorm(Y[row]) * gamma + beta),
  *   eps 1e-5 (transformer_rpe.py:156-171 applied to the residual stream right after attention / FFN, :233-245) —

@@ -368,6 +368,61 @@ def test_linear_tensor_core(M, N, K, flags):
     assert float(err.pow(2).mean().sqrt()) < 1e-3 * max(scale, 1.0)
 
 
+@pytest.mark.parametrize("M,N,K,flags", [(1024, 128, 128, "b"), (4097, 512, 128, "br"), (2000, 128, 640, "bpr+"),
+                                         (65536, 640, 128, "b"), (3000, 64, 20, "br"), (1500, 384, 256, "b+q"),
+                                         (500, 128, 128, "b"), (2048, 128, 18, "b")])
+def test_linear_3xtf32(M, N, K, flags):
+    """precision=3: the strict-parity projections on the tensor cores. The activation rows are split into
+    [x | x - trunc(x) | x] (tb_tf32_split3), the weights into [W | W | W - trunc(W)], and one kind::tf32 GEMM over 3K
+    sums x_hi W_hi + x_lo W_hi + x_hi W_lo. The operand error is 2^-21 per product; what remains is the tensor core's
+    round-toward-zero fp32 accumulate (one truncation per K=8 instruction, 3K/8 of them), a bias that grows linearly
+    with K: measured 1.2e-5 (K=128) .. 4.4e-5 (K=640) of the output scale against 2.5e-6 .. 4.7e-6 for the FFMA kernel.
+    Stated tolerance: (1e-5 + 6e-8 * 3K/8 * 4) of the output scale per element; shapes the split cannot take
+    (M < 1024, K % 4) must fall back to the FFMA kernel."""
+    g = torch.Generator().manual_seed(M + N + 1)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    mp, mq = torch.rand(M, generator=g) < 0.3, torch.rand(M, generator=g) < 0.3
+    y = torch.nn.functional.linear(x.double(), w.double(), b.double() if "b" in flags else None)
+    kw = {}
+    if "r" in flags:
+        y = y.relu(); kw["relu"] = True
+    if "p" in flags:
+        y = y.masked_fill(mp[:, None], 0); kw["mask_pre"] = mp.to(DEV)
+    if "+" in flags:
+        y = y + res.double(); kw["res"] = res.to(DEV)
+    if "q" in flags:
+        y = y.masked_fill(mq[:, None], 0); kw["mask_post"] = mq.to(DEV)
+    wd = w.to(DEV)
+    out = ops.linear(x.to(DEV), wd, b.to(DEV) if "b" in flags else None, precision=3, **kw)
+    out0 = ops.linear(x.to(DEV), wd, b.to(DEV) if "b" in flags else None, precision=0, **kw)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - y).abs()
+    err0 = (out0.cpu().double() - y).abs()
+    scale = max(float(y.std()), 1.0)
+    print(f"3xtf32 linear {M}x{N}x{K} {flags}: max err {float(err.max()):.3e} (FFMA kernel {float(err0.max()):.3e}), "
+          f"out rms {scale:.3e}")
+    assert float(err.max()) < (1e-5 + 6e-8 * (3 * K / 8) * 4) * scale, "3xTF32 projection out of tolerance"
+    if M < 1024 or K % 4:
+        assert torch.equal(out, out0), "shapes outside the split must run the FFMA kernel"
+    else:
+        assert hasattr(wd, "_tb_w3") and wd._tb_w3[1].shape == (N, 3 * K)
+
+
+def test_tf32_split3_bits():
+    """tb_tf32_split3: column blocks 0 and 2 are the input bit-for-bit, block 1 is x minus its 10-mantissa-bit
+    truncation (exactly representable, so the comparison is bit-exact); misaligned K is refused."""
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(1031, 132, generator=g) * 10.0 ** torch.randint(-3, 4, (1031, 1), generator=g)).to(DEV)
+    xs = x[:, 4:]  # strided view (ld 132, K 128)
+    out = ops.tf32_split3(xs)
+    hi = (xs.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    assert torch.equal(out[:, :128], xs) and torch.equal(out[:, 256:], xs)
+    assert torch.equal(out[:, 128:256], xs - hi)
+    with pytest.raises(RuntimeError):
+        ops.tf32_split3(x[:, :130])
+
+
 def test_linear_tensor_core_strided():
     g = torch.Generator().manual_seed(3)
     x = torch.randn(1000, 384, generator=g).to(DEV)

@@ -277,8 +277,9 @@ def test_training_step_vs_oracle_autograd(variant):
     g1 = {k: v.grad.clone() for k, v in ts.params.items() if v.grad is not None}
     ts.zero_grad()
     ts.step(b, n_steps=n_steps)
-    for k, v in g1.items():  # fp32 atomics: the summation order differs from run to run
-        assert float((ts.params[k].grad - v).abs().max()) < 1e-3 * max(float(v.abs().max()), 1e-5), k
+    for k, v in g1.items():  # fp32 atomics: the summation order differs from run to run; the floor covers the scalar
+        # bias whose gradient cancels to exactly zero (softmax shift invariance) and comes out as +-2e-8 of rounding
+        assert float((ts.params[k].grad - v).abs().max()) < 1e-3 * max(float(v.abs().max()), 1e-4), k
 
 
 def test_training_step_tf32_mode():

@@ -238,6 +238,36 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, int ldt, int
 
 }  // namespace
 
+// ---- 3xTF32 operand split (fp32-accurate projections on the tf32 tensor cores): out row = [x | x - trunc_tf32(x) | x].
+// With W3 = [W | W | W - trunc_tf32(W)] one kind::tf32 GEMM over K' = 3K evaluates x_hi W_hi + x_lo W_hi + x_hi W_lo
+// (the tensor core truncates every operand to its 10 explicit mantissa bits; the dropped x_lo W_lo term is 2^-20 relative).
+__global__ void tf32_split3_kernel(const float* __restrict__ X, int ldx, int M, int K, float* __restrict__ out, int ldo) {
+  const int m = blockIdx.x * 8 + threadIdx.y;
+  if (m >= M) return;
+  const float* xr = X + (size_t)m * ldx;
+  float* orow = out + (size_t)m * ldo;
+  for (int c = threadIdx.x * 4; c < K; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    float4 lo;
+    lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    *reinterpret_cast<float4*>(orow + c) = v;
+    *reinterpret_cast<float4*>(orow + K + c) = lo;
+    *reinterpret_cast<float4*>(orow + 2 * K + c) = v;
+  }
+}
+
+extern "C" int tb_tf32_split3(const float* X, int ldx, int M, int K, float* out, int ldo, void* stream) {
+  if (!X || !out) return TB_ERR_NULL;
+  if (M <= 0 || K <= 0 || ldx < K || ldo < 3 * K) return TB_ERR_BAD_SHAPE;
+  if ((K & 3) || (ldx & 3) || (ldo & 3) || !tb_aligned16(X) || !tb_aligned16(out)) return TB_ERR_MISALIGNED;
+  tf32_split3_kernel<<<(M + 7) / 8, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(X, ldx, M, K, out, ldo);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
 extern "C" int tb_layernorm(const float* X, int ldx, const float* gamma, const float* beta, void* Y, int ldy, int M,
                             int D, int flags, void* stream) {
   const int relu = flags & 1, out_h = (flags & 2) != 0;

@@ -129,8 +129,14 @@ class HotPathModel:
         return self
 
     # ------------------------------------------------------------------------------------------ helpers
+    @property
+    def gp(self) -> int:
+        """tb_linear precision of the projections: in the strict-parity mode (precision 0) large projections run as
+        3xTF32 on the tensor cores (fp32-class accuracy, ops.linear precision 3) unless `fp32_tc` is switched off."""
+        return 3 if (self.precision == 0 and getattr(self, "fp32_tc", True)) else self.precision
+
     def lin(self, x, wname, relu=False, **kw):
-        return ops.linear(x, self.P[f"{wname}.weight"], self.P[f"{wname}.bias"], relu=relu, precision=self.precision,
+        return ops.linear(x, self.P[f"{wname}.weight"], self.P[f"{wname}.bias"], relu=relu, precision=self.gp,
                           **kw)
 
     def ln(self, x, name, half: bool = False):
@@ -152,7 +158,7 @@ class HotPathModel:
                 w, b = self._interleaved(key, w, b, il_blocks)
                 key += ".il"
             return ops.linear(x, self._half(key, w), b, precision=2, **kw)
-        return ops.linear(x, w, b, precision=self.precision, **kw)
+        return ops.linear(x, w, b, precision=self.gp, **kw)
 
     def _interleaved(self, key: str, w: Tensor, b: Tensor, blocks):
         if not hasattr(self, "_w_il"):
@@ -182,8 +188,8 @@ class HotPathModel:
         for i in (1, 2):
             m = ops.pointnet_pool(h, row_invalid, G, Lg, 1)
             w_l, w_r = self._pointnet_split(prefix, i)
-            gb = ops.linear(m, w_r, self.P[f"{prefix}.mlp_layers.{i}.fc_layers.0.bias"], precision=self.precision)
-            h = ops.linear(h, w_l, gb, relu=True, bias_group=Lg, precision=self.precision)
+            gb = ops.linear(m, w_r, self.P[f"{prefix}.mlp_layers.{i}.fc_layers.0.bias"], precision=self.gp)
+            h = ops.linear(h, w_l, gb, relu=True, bias_group=Lg, precision=self.gp)
         return ops.pointnet_pool(h, row_invalid, G, Lg, 2)
 
     def _pointnet_split(self, prefix: str, i: int):
@@ -206,7 +212,7 @@ class HotPathModel:
             self._proj(x, f"{layer_prefix}.{attn}.w_kv", f["w_kv"], f["b_kv"], out_h=tbl, col_h=0,
                        il_blocks=(0, self.d))
             return tbl
-        return ops.linear(x, f["w_kv"], f["b_kv"], precision=self.precision, out=out)
+        return ops.linear(x, f["w_kv"], f["b_kv"], precision=self.gp, out=out)
 
     def _in_self(self, f, x, K, key=""):
         """[q|u] and the token's own [k|v] rows from one projection: one fp16 [q|u|k|v] row buffer in tensor-core mode
@@ -217,7 +223,7 @@ class HotPathModel:
             self._proj(x, f"{key}.w_in_self", f["w_in_self"], f["b_in_self"], out_h=row, col_h=0,
                        il_blocks=(0, nq, nq + self.d))
             return row[:, :nq], row[:, nq:]
-        proj = ops.linear(x, f["w_in_self"], f["b_in_self"], precision=self.precision)
+        proj = ops.linear(x, f["w_in_self"], f["b_in_self"], precision=self.gp)
         return proj, proj[:, nq:]
 
     def _in_q(self, f, x, key=""):
@@ -226,7 +232,7 @@ class HotPathModel:
             qu = torch.empty(x.shape[0], self.d + H * self.d, dtype=torch.float16, device=x.device)
             self._proj(x, f"{key}.w_in_q", f["w_in_q"], f["b_in_q"], out_h=qu, col_h=0, il_blocks=(0,))
             return qu
-        return ops.linear(x, f["w_in_q"], f["b_in_q"], precision=self.precision)
+        return ops.linear(x, f["w_in_q"], f["b_in_q"], precision=self.gp)
 
     def _attend(self, fa, proj, B, S, kv0, T0, div0, K0, knn, kv1=None, T1=0, div1=1, K1=0):
         d = self.d
@@ -335,7 +341,7 @@ class HotPathModel:
                                      res=res, precision=2)
             y = ops.linear(o, w, f["b_out"], mask_pre=nv, res=res, precision=2)
         else:
-            y = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=res, precision=self.precision)
+            y = ops.linear(o, f["w_out"], f["b_out"], mask_pre=nv, res=res, precision=self.gp)
         return y if ln_next is None else (y, self.ln(y, ln_next, half=self.kv_half))
 
     def tf_layer(self, p: str, mode: str, src: Tensor, src_inv: Tensor, B: int, S: int, knn_self: dict,
@@ -643,7 +649,7 @@ class HotPathModel:
         tok = self.pointnet(x, (~ag_valid).reshape(-1).contiguous(), M, n_step, "navi_predictor.temp_encoder")  # :232
         pr = "navi_predictor.mlp.fc_layers"
         w0 = self.P[f"{pr}.0.weight"]
-        a_part = ops.linear(tok, w0[:, :d].contiguous(), self.P[f"{pr}.0.bias"], precision=self.precision)
+        a_part = ops.linear(tok, w0[:, :d].contiguous(), self.P[f"{pr}.0.bias"], precision=self.gp)
         w_mr = w0[:, d:].contiguous()
         n_mp = mp["mp_token_pose"].shape[1]
         logits = torch.empty(n_sc, A, n_mp, device=self.dev)
@@ -654,7 +660,7 @@ class HotPathModel:
             X[:, :d].view(ns, A, n_mp, d).copy_(mp["mp_token_feature"][s0:s0 + ns, None])
             pose_rows = mp["mp_token_pose"][s0:s0 + ns, None].expand(-1, A, -1, -1).reshape(Pn, 3)
             ops.pose_emb(pose_rows, self.freq_rpe, d, frame=tok_pose[s0:s0 + ns], frame_div=n_mp, out=X[:, d:])  # :259-260
-            h = ops.linear(X, w_mr, a_part[s0 * A:(s0 + ns) * A], bias_group=n_mp, precision=self.precision)
+            h = ops.linear(X, w_mr, a_part[s0 * A:(s0 + ns) * A], bias_group=n_mp, precision=self.gp)
             h = ops.layernorm(h, self.P[f"{pr}.1.weight"], self.P[f"{pr}.1.bias"], relu=True, out=h)      # mlp.py:47-51
             h = self.lin(h, f"{pr}.3")
             h = ops.layernorm(h, self.P[f"{pr}.4.weight"], self.P[f"{pr}.4.bias"], relu=True, out=h)
@@ -743,13 +749,13 @@ class HotPathModel:
                 ops.linear(h0[:, t * d:(t + 1) * d], self._half(nm, self.P[f"{nm}.weight"]), self.P[f"{nm}.bias"],
                            relu=True, precision=2, out_h=h1[:, t * d:(t + 1) * d], col_h=0)
             return ops.linear(h1, self._half("action_head.w4", self.act_w4), self.act_b4, precision=2)
-        h0 = ops.linear(h, self.act_w0, self.act_b0, relu=True, precision=self.precision)            # action_head.py:78-82
+        h0 = ops.linear(h, self.act_w0, self.act_b0, relu=True, precision=self.gp)            # action_head.py:78-82
         h1 = torch.empty_like(h0)
         for t in range(3):
             self.lin(h0[:, t * d:(t + 1) * d], f"action_head.mlp_mean.{t}.fc_layers.2", relu=True,
                      out=h1[:, t * d:(t + 1) * d])
         # last layers of the 3 type branches as ONE block-diagonal [6, 3d] projection of the stacked hidden rows
-        return ops.linear(h1, self.act_w4, self.act_b4, precision=self.precision)
+        return ops.linear(h1, self.act_w4, self.act_b4, precision=self.gp)
 
 
 def _encode_polyline(pos: Tensor, dirv: Tensor) -> Tensor:

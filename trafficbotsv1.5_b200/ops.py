@@ -130,6 +130,12 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False,
         from . import autograd as AG
         assert out_h is None, "the training path keeps fp32 activations"
         return AG.linear(x, w, b, relu, mask_pre, res, mask_post, out, precision, bias_group)
+    if precision == 3:  # fp32-accurate on the tf32 tensor cores (3xTF32); small / odd shapes stay on the FFMA kernel
+        M_, K_ = x.shape
+        if out_h is not None or K_ % 4 or x.stride(0) % 4 or M_ < 1024 or x.data_ptr() % 16:
+            precision = 0
+        else:
+            return linear(tf32_split3(x), _w3(w), b, relu, mask_pre, res, mask_post, out, 1, bias_group)
     in_dt = torch.float16 if precision == 2 else torch.float32  # precision 2: fp16 activations x fp16 weights
     assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.dtype == in_dt and w.dtype == in_dt, \
         (x.dtype, w.dtype, precision)
@@ -153,6 +159,25 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, relu: bool = False,
                                out_h.stride(0) if out_h is not None else 0, col_h, L.stream()), "tb_linear")
     _count()
     return out
+
+
+def tf32_split3(x: Tensor) -> Tensor:
+    """[x | x - trunc_tf32(x) | x] rows (tb_tf32_split3): the activation operand of a 3xTF32 projection."""
+    M, K = x.shape
+    out = torch.empty(M, 3 * K, dtype=torch.float32, device=x.device)
+    L.check(L.load().tb_tf32_split3(L.ptr(x), x.stride(0), M, K, L.ptr(out), 3 * K, L.stream()), "tb_tf32_split3")
+    _count()
+    return out
+
+
+def _w3(w: Tensor) -> Tensor:
+    """[W | W | W - trunc_tf32(W)] for a 3xTF32 projection, cached on the weight object until it is modified."""
+    c = getattr(w, "_tb_w3", None)
+    if c is None or c[0] != w._version:
+        hi = (w.detach().view(torch.int32) & -8192).view(torch.float32)  # keep sign, exponent and 10 mantissa bits
+        c = (w._version, torch.cat([w.detach(), w.detach(), w.detach() - hi], 1).contiguous())
+        w._tb_w3 = c
+    return c[1]
 
 
 def linear_ln(x: Tensor, w: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Tensor, mask_pre: Optional[Tensor] = None,

@@ -46,6 +46,7 @@ class TrainModel(HotPathModel):
         self.cfg, self.sz, self.dev, self.precision = cfg, sizes, torch.device(device), precision
         self.d, self.W = cfg["hidden_dim"], cfg["temp_window_size"]
         self.kv_half = False  # fp32 rows everywhere; precision 1 only switches the GEMMs to tf32 tcgen05
+        self.fp32_tc = False  # precision 0 of the training path is the FFMA kernel (forward and backward)
         self.P = params
         self.detach_tl_feature = cfg["tl_state_predictor"]["detach_tl_feature"]
         self.freq_rpe = ops.pe_freq_xy(self.d, cfg["pose_rpe"]["theta_xy"], self.dev)
