@@ -43,6 +43,9 @@ namespace {
 #ifndef TB_MMA_MINB
 #define TB_MMA_MINB 12
 #endif
+#ifndef TB_MMA_PREFETCH
+#define TB_MMA_PREFETCH 1
+#endif
 constexpr int kWarps = TB_MMA_WARPS;
 constexpr int D = 128;
 constexpr int H = 4;
@@ -85,7 +88,16 @@ constexpr int KPAIR = 128;  // compacted neighbour slots per token
 // per warp: the two neighbour lists (row pointer + float4 relative pose per slot), reused as the 2 x 640-float output
 // staging of the epilogue
 constexpr int kPairSmem = 2 * (KPAIR * 8 + KPAIR * 16);
-static_assert(kPairSmem >= 2 * (D + H * D) * 4, "output staging must fit");
+// epilogue staging of one token: [ov heads 0,1 | 4 pad | ov heads 2,3 | z head 0..3], z head rows kZHead floats apart
+// and token blocks kOutTok apart so that the four lanes of a row group (t = 0..3: heads 0 / 2 of token A / B) hit banks
+// 0 / 8 / 16 / 24 + g instead of one bank (the unpadded layout was a 4-way conflict on every staging store: 120 extra
+// wavefronts per pair)
+constexpr int kZHead = D + 4, kZBase = D + 4, kOutTok = kZBase + H * kZHead + 28;
+static_assert(kOutTok % 32 == 16 && (2 * kZHead) % 32 == 8 && kOutTok % 4 == 0, "bank spread / float4 alignment");
+static_assert(kPairSmem >= 2 * kOutTok * 4, "output staging must fit");
+// prologue staging of the two u rows (bytes): head rows 272 apart, token blocks 4 * 272 apart
+constexpr int kUHead = 2 * D + 16, kUTok = H * kUHead;
+static_assert(2 * kUTok <= 2 * KPAIR * 16, "u staging must fit in the s_rel area");
 
 // One 128-channel fp16 row into 16 registers per lane. Plain layout: four 128-bit pieces, piece i = head i, lane t
 // takes halves [32 i + 8 t, +8). Head-interleaved layout (IL): two 256-bit pieces, lane t takes halves
@@ -160,21 +172,35 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
         n_rel[tk][c][2] = __ldg(rel + p * 3 + 2);
       }
     }
-  // B fragments: column g takes head hA of token g >> 2 (token B absent: zeros)
+  // B fragments: column g takes head hA of token g >> 2 (token B absent: zeros). The u fragments are 4-byte pieces of
+  // 8 different (token, head) rows per load - 8 L1 tag look-ups for 128 useful bytes (ncu: "L1 Tag Requests" 8.0 on
+  // each of the 16 loads). Instead the two u rows are read coalesced (4 x 128-bit loads per lane), staged in the still
+  // unused list area with the head rows 272 bytes apart (bank = 16 token + 4 head + t: conflict-free) and picked up
+  // with 16 one-wavefront LDS: 16 tag look-ups per pair instead of 128 (time-neutral on its own, profiles/r2_notes.md 10).
   uint32_t uB[8][2], qB[2][2];
   {
     const int tkc = g >> 2;
     const bool live = tkc == 0 || has_b;
-    const __half* up = u + (size_t)(tok0 + (live ? tkc : 0)) * ldu + hA * D + 2 * t;
+    unsigned char* s_u = s_raw[warp] + 2 * KPAIR * 8;  // (the s_rel area: the lists are built after this block)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // piece i: token i >> 1, bytes [512 (i & 1) + 16 lane, +16) of its u row
+      const int tk = i >> 1, piece = (i & 1) * 32 + lane;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (tk == 0 || has_b) v = ldg128(u + (size_t)(tok0 + tk) * ldu + piece * 8);
+      *reinterpret_cast<uint4*>(s_u + tk * kUTok + (piece >> 4) * kUHead + (piece & 15) * 16) = v;
+    }
     const __half* qp = q + (size_t)(tok0 + (live ? tkc : 0)) * ldq +
                        (IL ? 64 * (hA >> 1) + 16 * t + 8 * (hA & 1) : 32 * hA + 8 * t);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uB[c][0] = live ? __ldg(reinterpret_cast<const uint32_t*>(up + cos_base(c))) : 0u;
-      uB[c][1] = live ? __ldg(reinterpret_cast<const uint32_t*>(up + sin_base(c))) : 0u;
-    }
     const uint4 qq = live ? __ldg(reinterpret_cast<const uint4*>(qp)) : make_uint4(0u, 0u, 0u, 0u);
     qB[0][0] = qq.x; qB[0][1] = qq.y; qB[1][0] = qq.z; qB[1][1] = qq.w;
+    __syncwarp();
+    const unsigned char* up = s_u + tkc * kUTok + hA * kUHead + 4 * t;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uB[c][0] = *reinterpret_cast<const uint32_t*>(up + 2 * cos_base(c));
+      uB[c][1] = *reinterpret_cast<const uint32_t*>(up + 2 * sin_base(c));
+    }
+    __syncwarp();  // the list build below overwrites the staging
   }
   // table bases: the two tokens are consecutive, so the scene index needs one division per warp and the second
   // token almost always shares the first one's tables (the divisions were ~100 instructions per pair)
@@ -242,6 +268,22 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
       rowp[tile] = s_ptr[tile * KPAIR + g0 + g];
       load_row<IL>(kf[tile], rowp[tile], t);
     }
+#if TB_MMA_PREFETCH
+    // ptxas sinks the V loads below the logits MMAs (no registers to hold them earlier), so their L2 round trip used to
+    // be exposed: the first V movmatrix carried 12 % of all stall samples, the K consumers another 11 %. L1 prefetches
+    // need no registers: lanes t < 2 pull the V half (lines 2, 3 of the 512-byte row) of THIS group's rows now, a whole
+    // trig + logits phase ahead of the loads; lanes t >= 2 pull the K half (lines 0, 1) of the NEXT group's rows.
+    {
+      const bool nxt = t >= 2;
+      if (!nxt || g0 + 8 < npad) {
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile) {
+          const __half* r = nxt ? s_ptr[tile * KPAIR + g0 + 8 + g] + 64 * (t - 2) : rowp[tile] + D + 64 * t;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+        }
+      }
+    }
+#endif
     uint32_t eA[8][4];
 #pragma unroll
     for (int tile = 0; tile < 2; ++tile) {
@@ -369,22 +411,22 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
   const float ia = sm[0] > 0.f ? 1.f / sm[0] : 0.f, ib = sm[1] > 0.f ? 1.f / sm[1] : 0.f;
   __syncwarp();
   {
-    float* so = s_out + my * (D + H * D);
+    float* so = s_out + my * kOutTok;
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
       const int cp = 8 * (g >> 1) + 4 * m + (g & 1);
-      so[32 * h0 + cp] = oacc[m][0] * ia;
-      so[32 * (h0 + 1) + cp] = oacc[m][1] * ib;
-      so[32 * h0 + cp + 2] = oacc[m][2] * ia;
-      so[32 * (h0 + 1) + cp + 2] = oacc[m][3] * ib;
+      so[32 * h0 + 2 * h0 + cp] = oacc[m][0] * ia;  // (+ 2 h0: the 4-float pad in front of heads 2, 3)
+      so[32 * (h0 + 1) + 2 * h0 + cp] = oacc[m][1] * ib;
+      so[32 * h0 + 2 * h0 + cp + 2] = oacc[m][2] * ia;
+      so[32 * (h0 + 1) + 2 * h0 + cp + 2] = oacc[m][3] * ib;
     }
-    float* zs = so + D + g;
+    float* zs = so + kZBase + g;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      zs[h0 * D + cos_base(c)] = zacc[c][0] * ia;
-      zs[(h0 + 1) * D + cos_base(c)] = zacc[c][1] * ib;
-      zs[h0 * D + sin_base(c)] = zacc[c][2] * ia;
-      zs[(h0 + 1) * D + sin_base(c)] = zacc[c][3] * ib;
+      zs[h0 * kZHead + cos_base(c)] = zacc[c][0] * ia;
+      zs[(h0 + 1) * kZHead + cos_base(c)] = zacc[c][1] * ib;
+      zs[h0 * kZHead + sin_base(c)] = zacc[c][2] * ia;
+      zs[(h0 + 1) * kZHead + sin_base(c)] = zacc[c][3] * ib;
     }
   }
   __syncwarp();
@@ -392,7 +434,7 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
   for (int tk = 0; tk < 2; ++tk) {
     if (tk == 1 && !has_b) break;  // warp-uniform
     const int tok = tok0 + tk;
-    const float* so = s_out + tk * (D + H * D);
+    const float* so = s_out + tk * kOutTok;
     if (OUT_H) {
       auto to_h4 = [](const float* pp) {
         const float4 v = *reinterpret_cast<const float4*>(pp);
@@ -400,16 +442,16 @@ knarpe_attn_mma_pair_kernel(const __half* __restrict__ q, int ldq, const __half*
       };
       __half* ov_h = static_cast<__half*>(out_ov_) + (size_t)tok * ldo + lane * 4;
       __half* z_h = static_cast<__half*>(out_z_) + (size_t)tok * ldo + lane * 4;
-      *reinterpret_cast<uint2*>(ov_h) = to_h4(so + lane * 4);
+      *reinterpret_cast<uint2*>(ov_h) = to_h4(so + lane * 4 + 4 * (lane >> 4));
 #pragma unroll
-      for (int k = 0; k < H; ++k) *reinterpret_cast<uint2*>(z_h + k * D) = to_h4(so + D + k * D + lane * 4);
+      for (int k = 0; k < H; ++k) *reinterpret_cast<uint2*>(z_h + k * D) = to_h4(so + kZBase + k * kZHead + lane * 4);
     } else {
       float* ovp = static_cast<float*>(out_ov_) + (size_t)tok * ldo + lane * 4;
       float* zp = static_cast<float*>(out_z_) + (size_t)tok * ldo + lane * 4;
-      *reinterpret_cast<float4*>(ovp) = *reinterpret_cast<const float4*>(so + lane * 4);
+      *reinterpret_cast<float4*>(ovp) = *reinterpret_cast<const float4*>(so + lane * 4 + 4 * (lane >> 4));
 #pragma unroll
       for (int k = 0; k < H; ++k)
-        *reinterpret_cast<float4*>(zp + k * D) = *reinterpret_cast<const float4*>(so + D + k * D + lane * 4);
+        *reinterpret_cast<float4*>(zp + k * D) = *reinterpret_cast<const float4*>(so + kZBase + k * kZHead + lane * 4);
     }
     if (lane == 0 && out_none_valid) out_none_valid[tok] = nvalid[tk] > 0 ? 0 : 1;
   }
