@@ -54,11 +54,11 @@ def main():
     ref, _, _ = run_heads(m32)
     scale = float(ref.abs().max())
     for chain in ("1", "0"):
-        os.environ["TB_CHAIN"] = chain
+        m16.opt["chain"] = chain == "1"
         out, navi, x_cat = run_heads(m16)
         err = float((out - ref).abs().max())
         t = time_us(lambda: m16.heads(x_cat, st, navi))
-        print(f"heads  TB_CHAIN={chain}: max |act - fp32| = {err:.3e} (scale {scale:.2f}), {t:.1f} us per call (M={M})")
+        print(f"heads  chain={chain}: max |act - fp32| = {err:.3e} (scale {scale:.2f}), {t:.1f} us per call (M={M})")
     # ---- FFN of agent layer 0
     p = "ag_encoder.tf_ag2agmptl.layers.0"
     src = torch.randn(M, d, generator=g).to(DEV)
@@ -82,12 +82,12 @@ def main():
                              m.P[f"{nxt}.weight"], m.P[f"{nxt}.bias"], res=src, mask_post=inv, precision=2)
 
     for chain in ("1", "0"):
-        os.environ["TB_CHAIN"] = chain
+        m16.opt["chain"] = chain == "1"
         y, ln_rows = ffn(m16)
         e1 = float((y - ref).abs().max())
         e2 = float((ln_rows.float() - ref_ln)[~inv].abs().max())
         t = time_us(lambda: ffn(m16))
-        print(f"FFN    TB_CHAIN={chain}: max |y - fp32| = {e1:.3e} (scale {float(ref.abs().max()):.2f}), LN rows {e2:.3e}, "
+        print(f"FFN    chain={chain}: max |y - fp32| = {e1:.3e} (scale {float(ref.abs().max()):.2f}), LN rows {e2:.3e}, "
               f"{t:.1f} us per call")
 
 

@@ -566,16 +566,16 @@ def test_post_process_womd_after_rollout():
 
 
 @pytest.mark.gpu
-def test_rollout_head_interleaved_layout_is_bit_identical(golden_rollout, monkeypatch):
+def test_rollout_head_interleaved_layout_is_bit_identical(golden_rollout):
     """The head-interleaved q / K / V rows (tb_knarpe_attn flags bit 4, the tensor-core mode's default) are a
     permutation of projection output features: the whole closed-loop rollout is bit-identical to the natural layout
-    (TB_ATTN_IL=0, 128-bit gathers)."""
+    (`model.opt["attn_il"] = False`, 128-bit gathers)."""
     g = golden_rollout
     eng, batch, P, cfg = _engine(g["shape"], g["R"], g["T"], precision=1)
     assert eng.model.kv_il
     res = {k: v.clone() for k, v in eng.rollout(batch).items() if torch.is_tensor(v)}
-    monkeypatch.setenv("TB_ATTN_IL", "0")
     eng2, _, _, _ = _engine(g["shape"], g["R"], g["T"], precision=1)
+    eng2.model.opt["attn_il"] = False
     assert not eng2.model.kv_il
     res2 = eng2.rollout(batch)
     for k in ("pred_pose", "pred_motion", "pred_valid", "tl_state"):
@@ -583,7 +583,7 @@ def test_rollout_head_interleaved_layout_is_bit_identical(golden_rollout, monkey
 
 
 @pytest.mark.gpu
-def test_rollout_fused_layernorm_vs_separate(golden_rollout, monkeypatch):
+def test_rollout_fused_layernorm_vs_separate(golden_rollout):
     """tb_linear_ln (LayerNorm inside the producing projection's epilogue, one-pass variance) against the separate
     tb_layernorm launches (two-pass): same closed-loop rollout within the tensor-core mode's rounding."""
     g = golden_rollout
@@ -591,8 +591,8 @@ def test_rollout_fused_layernorm_vs_separate(golden_rollout, monkeypatch):
     assert eng.model.ln_fused
     res = {k: v.clone() for k, v in eng.rollout(batch).items() if torch.is_tensor(v)}
     n_fused = eng.launches_per_step
-    monkeypatch.setenv("TB_LN_FUSED", "0")
     eng2, _, _, _ = _engine(g["shape"], g["R"], g["T"], precision=1)
+    eng2.model.opt["ln_fused"] = False
     assert not eng2.model.ln_fused
     res2 = eng2.rollout(batch)
     assert eng2.launches_per_step > n_fused

@@ -13,7 +13,6 @@ All tensors here are 2-D [rows, channels] views of flat HBM buffers; every compu
 import math
 from typing import Dict, Optional
 
-import os
 
 import torch
 from torch import Tensor
@@ -90,6 +89,17 @@ def _probe_fp32(fn):
 class HotPathModel:
     """Device-resident weights + the kernel sequences of the hot-path modules."""
 
+    # per-instance A/B switches of the tensor-core mode (defaults = the measured-best paths): head-interleaved q / K / V
+    # rows, LayerNorm fused into the producing projection, head chain as one tb_chain_run program. Set before the first
+    # forward (`model.opt["attn_il"] = False`); used by the bit-identity / equivalence tests and the profiling scripts.
+    _OPT = dict(attn_il=True, ln_fused=True, chain=True)
+
+    @property
+    def opt(self) -> dict:
+        if "_opt" not in self.__dict__:
+            self._opt = dict(self._OPT)
+        return self._opt
+
     def __init__(self, P: Dict[str, Tensor], cfg: dict, sizes: dict, device="cuda", precision: int = 0):
         self.cfg, self.sz, self.dev, self.precision = cfg, sizes, torch.device(device), precision
         self.d = cfg["hidden_dim"]
@@ -148,7 +158,7 @@ class HotPathModel:
     def kv_il(self) -> bool:
         """Head-interleaved q / K / V rows (tb_knarpe_attn flags bit 4): every attention of the tensor-core mode runs
         on the pair kernel, so the projections write the layout it gathers with 256-bit loads."""
-        return self.kv_half and os.environ.get("TB_ATTN_IL", "1") != "0"
+        return self.kv_half and self.opt["attn_il"]
 
     def _proj(self, x: Tensor, key: str, w: Tensor, b: Tensor, il_blocks=(), **kw):
         """Projection of LayerNorm output: fp16 rows x fp16 weights (tb_linear precision 2) or the fp32 / tf32 path.
@@ -256,9 +266,9 @@ class HotPathModel:
 
     @property
     def chain_fused(self) -> bool:
-        """Head chain as one fused tcgen05 chain program (tb_chain_run) in the tensor-core mode; TB_CHAIN=0 keeps
-        the one-launch-per-layer path (A/B and bisecting)."""
-        return os.environ.get("TB_CHAIN", "1") != "0"
+        """Head chain as one fused tcgen05 chain program (tb_chain_run) in the tensor-core mode; `opt["chain"] = False`
+        keeps the one-launch-per-layer path (A/B and bisecting)."""
+        return self.opt["chain"]
 
     def _ffn_program(self, p: str, ldy: int, ln_next: Optional[str]):
         """bindings: 0 LayerNorm rows fp16 [M,d], 1 residual fp32 [M,d], 2 row mask u8 [M], 3 out fp32 (ld ldy),
@@ -329,7 +339,7 @@ class HotPathModel:
     @property
     def ln_fused(self) -> bool:
         """LayerNorm of the residual stream inside the epilogue of the projection that produces it (tb_linear_ln)."""
-        return self.kv_half and self.d == 128 and os.environ.get("TB_LN_FUSED", "1") != "0"
+        return self.kv_half and self.d == 128 and self.opt["ln_fused"]
 
     def _out_proj(self, p: str, f: dict, o: Tensor, nv: Tensor, res: Tensor, ln_next: Optional[str] = None):
         """Output projection over [ov|z] (fp16 rows in tensor-core mode -> kind::f16 MMA, fp32 accumulate/residual).
