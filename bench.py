@@ -346,9 +346,10 @@ def attention_roofline(eng, peaks):
     n_src = int((~aux["tok_inv"]).sum())
     sel_bytes = M * (T_mp * 13 + K_mp * 17)  # targets as issued (x, y, yaw, invalid) + idx / mask / rel out
     try:
-        sel_traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("knn_select_ag_map_bytes")
+        _tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        sel_traffic, lin_traffic = _tr.get("knn_select_ag_map_bytes"), _tr.get("linear_in_self_bytes")
     except Exception:
-        sel_traffic = None
+        sel_traffic = lin_traffic = None
     # ---- the projection that writes most: self in-projection of an agent layer, fp16 rows in / out in the 16-bit mode
     roof_proj = None
     if m.kv_half:
@@ -375,7 +376,7 @@ def attention_roofline(eng, peaks):
         t_fill = cold(lambda: row.zero_())  # what HBM gives a kernel that only WRITES these bytes
         pb = x0.numel() * 2 + fs["w_in_self"].numel() * 2 + row.numel() * 2
         roof_proj = dict(bound="hbm", kernel=f"linear_tc_kernel<F16> (self in-projection, M={M}, N={row.shape[1]}, K={d}, fp16 rows)",
-                         achieved=pb / t_p / 1e9, peak=peak, unit="GB/s", frac=pb / t_p / 1e9 / peak, traffic=None,
+                         achieved=pb / t_p / 1e9, peak=peak, unit="GB/s", frac=pb / t_p / 1e9 / peak, traffic=lin_traffic,
                          us_per_launch=t_p * 1e6, algorithmic_bytes=pb, bytes_written=row.numel() * 2,
                          write_only_floor_us=t_fill * 1e6, frac_of_write_floor=t_fill / t_p,
                          note="write-dominated: `write_only_floor_us` is a fill of the output alone, measured here; the "
