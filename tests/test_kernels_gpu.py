@@ -901,3 +901,65 @@ def test_mlp_chain_program_vs_torch(M):
     bad.gemm(hw(W1), [1], b1, out_buf=2)  # reads a buffer nobody wrote
     with pytest.raises(RuntimeError):
         bad.finish()
+
+
+# ------------------------------------------------------------------------------------------------ plain entry points
+def test_colsum_accumulates_column_sums():
+    """tb_colsum (bias gradient): out[n] += sum_m X[m, n] on a strided view, accumulated into a pre-filled buffer."""
+    from trafficbotsv1_5_b200 import lib as L
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(70001, 200, generator=g).to(DEV)
+    xv = x[:, 8:8 + 130]
+    out = torch.full((130,), 3.0, device=DEV)
+    L.check(L.load().tb_colsum(L.ptr(xv), xv.stride(0), xv.shape[0], 130, L.ptr(out), L.stream()), "tb_colsum")
+    ref = 3.0 + xv.double().sum(0)
+    assert float((out.double() - ref).abs().max()) < 1e-5 * float(xv.abs().sum(0).max())
+
+
+def test_featurize_shared_counter_entry_points_match_per_row_counters():
+    """tb_ag_featurize / tb_tl_featurize (one device-side loop counter for the whole batch) are the step_stride = 0 case
+    of the *_ex entry points: a batch whose rows all carry the same counter must produce identical bytes either way."""
+    from trafficbotsv1_5_b200 import lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(4)
+    B, A, TL, W, s = 6, 9, 5, 11, 14
+    hv = (torch.rand(B, A, W, generator=g) < 0.8).to(torch.uint8).to(DEV)
+    hp = (torch.randn(B, A, W, 3, generator=g) * 20).to(DEV)
+    hm = torch.randn(B, A, W, 3, generator=g).to(DEV)
+    attr = torch.rand(B, A, 6, generator=g).to(DEV)
+    freq = ops.pe_freq_xy(64, 1e3, DEV)
+    d1 = torch.tensor([s], dtype=torch.int32, device=DEV)
+    dB = torch.full((B,), s, dtype=torch.int32, device=DEV)
+
+    def ag(ex):
+        o = dict(pose=torch.zeros(B, A, 3, device=DEV), inv=torch.zeros(B, A, dtype=torch.uint8, device=DEV),
+                 rinv=torch.zeros(B, A, W, dtype=torch.uint8, device=DEV), attr=torch.zeros(B * A * W, 9 + W, device=DEV),
+                 pe=torch.zeros(B * A * W, 64, device=DEV))
+        tail = (L.ptr(freq), B, A, W, L.ptr(o["pose"]), L.ptr(o["inv"]), L.ptr(o["rinv"]), L.ptr(o["attr"]), 9 + W,
+                L.ptr(o["pe"]), 64, L.stream())
+        if ex:
+            L.check(lib.tb_ag_featurize_ex(L.ptr(hv), L.ptr(hp), L.ptr(hm), L.ptr(attr), L.ptr(dB), 1, *tail), "ag_ex")
+        else:
+            L.check(lib.tb_ag_featurize(L.ptr(hv), L.ptr(hp), L.ptr(hm), L.ptr(attr), L.ptr(d1), *tail), "ag")
+        return o
+
+    a, b = ag(False), ag(True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert float(a["pe"].abs().sum()) > 0 and int(a["rinv"].sum()) > 0
+
+    ht = torch.nn.functional.one_hot(torch.randint(0, 5, (B, TL, W), generator=g), 5).to(torch.uint8).to(DEV)
+    tinv = (torch.rand(B, TL, generator=g) < 0.2).to(torch.uint8).to(DEV)
+
+    def tl(ex):
+        rows, rinv = torch.zeros(B * TL * W, 16, device=DEV), torch.zeros(B, TL, W, dtype=torch.uint8, device=DEV)
+        if ex:
+            L.check(lib.tb_tl_featurize_ex(L.ptr(ht), L.ptr(tinv), L.ptr(dB), 1, B, TL, W, L.ptr(rows), 16, L.ptr(rinv),
+                                           L.stream()), "tl_ex")
+        else:
+            L.check(lib.tb_tl_featurize(L.ptr(ht), L.ptr(tinv), L.ptr(d1), B, TL, W, L.ptr(rows), 16, L.ptr(rinv),
+                                        L.stream()), "tl")
+        return rows, rinv
+
+    (r0, i0), (r1, i1) = tl(False), tl(True)
+    assert torch.equal(r0, r1) and torch.equal(i0, i1) and float(r0.sum()) > 0
