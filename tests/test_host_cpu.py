@@ -94,3 +94,34 @@ def test_rollout_buffer_layout_and_log_prob():
     exp[0, 0, 0] = 1.0  # no valid navigation sample: 0 (+ the latent term)
     assert torch.equal(buf.log_prob, exp)
     assert _check_teacher_forcing(TeacherForcing(step_spawn_agent=7, step_warm_start=9)) == (7, 9)
+
+
+def test_3xtf32_weight_split_is_exact_and_cached():
+    """ops._w3 (strict-parity projections on the tf32 tensor cores): [W | W | W - trunc_tf32(W)] where the truncation
+    keeps sign, exponent and 10 mantissa bits. hi + lo must reproduce W bit for bit, lo must be below 2^-10 of |W|, and
+    the split is rebuilt only when the weight tensor is modified in place; the 3-term sum x_hi W_hi + x_lo W_hi +
+    x_hi W_lo (what one tf32 GEMM over [x | x_lo | x] . [W | W | W_lo] evaluates) drops only x_lo W_lo."""
+    from trafficbotsv1_5_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(40, 24, generator=g) * 10.0 ** torch.randint(-4, 4, (40, 1), generator=g)
+    w3 = ops._w3(w)
+    K = w.shape[1]
+    assert w3.shape == (40, 3 * K) and torch.equal(w3[:, :K], w) and torch.equal(w3[:, K:2 * K], w)
+    lo = w3[:, 2 * K:]
+    hi = w - lo
+    assert torch.equal(hi + lo, w)
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0          # 13 low mantissa bits cleared
+    assert bool((lo.abs() <= w.abs() * 2.0 ** -10).all())
+    assert ops._w3(w) is w3                                                # cached on the tensor object
+    w.mul_(2.0)
+    w3b = ops._w3(w)
+    assert w3b is not w3 and torch.equal(w3b[:, :K], w)                    # in-place update -> rebuilt
+    # the three-term product against float64: the dropped term is 2^-20 relative per product
+    x = torch.randn(50, K, generator=g)
+    trunc = lambda t: (t.view(torch.int32) & -8192).view(torch.float32)    # noqa: E731
+    xh, wh = trunc(x), trunc(w)
+    xl, wl = x - xh, w - wh
+    three = xh.double() @ wh.double().T + xl.double() @ wh.double().T + xh.double() @ wl.double().T
+    ref = x.double() @ w.double().T
+    scale = (x.abs().double() @ w.abs().double().T)
+    assert float(((three - ref).abs() / scale).max()) < 2.0 ** -19
