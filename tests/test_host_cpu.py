@@ -125,3 +125,37 @@ def test_3xtf32_weight_split_is_exact_and_cached():
     ref = x.double() @ w.double().T
     scale = (x.abs().double() @ w.abs().double().T)
     assert float(((three - ref).abs() / scale).max()) < 2.0 ** -19
+
+
+def test_agent_compaction_keeps_every_valid_agent_in_order():
+    """RolloutEngine._compact (host logic, no GPU): agent slots that are never valid in the ground truth are dropped,
+    the kept slots are the valid ones in their original order (stable), the slot count is the largest per-scene valid
+    count rounded up to 4 and at least k_ag2ag + 1, and every per-agent tensor of the batch is gathered consistently."""
+    from trafficbotsv1_5_b200 import config, synth
+    from trafficbotsv1_5_b200.engine import RolloutEngine
+    cfg = config.default_model_cfg()
+    batch = synth.make_scene_batch(n_sc=3, n_ag=64, n_mp=40, n_tl=6, seed=5)
+    keep = torch.zeros(3, 64, dtype=torch.bool)
+    keep[0, 3::2] = True        # 31 agents
+    keep[1, :29] = True         # 29 agents
+    keep[2, 10:45] = True       # 35 agents -> 36 slots
+    batch["sc/ag_valid"] = batch["sc/ag_valid"] & keep[:, :, None]
+    batch["sc/ag_valid"][:, :, 0] |= keep   # every kept agent is valid at least once
+    eng = RolloutEngine.__new__(RolloutEngine)
+    eng.compact_agents, eng.sz, eng.dev = True, config.derived_sizes(cfg), torch.device("cpu")
+    out = eng._compact(batch)
+    a_eff = out["sc/ag_valid"].shape[1]
+    assert a_eff == 36 and eng._A_full == 64 and eng._perm.shape == (3, 36)
+    ever = batch["sc/ag_valid"].any(-1)
+    for sc in range(3):
+        kept = eng._perm[sc].tolist()
+        valid_ids = ever[sc].nonzero().flatten().tolist()
+        assert kept[:len(valid_ids)] == valid_ids                        # valid first, original order
+        assert not ever[sc][kept[len(valid_ids):]].any()                 # the rest is padding
+        for k in ("sc/ag_valid", "sc/ag_pose", "sc/ag_motion", "sc/ag_attr"):
+            if k in batch:
+                assert torch.equal(out[k][sc], batch[k][sc][kept]), k
+    assert out["agent/dest"].shape[1 if batch["agent/dest"].dim() == 2 else 2] == 36
+    assert batch["sc/ag_valid"].shape[1] == 64                           # the caller's dict is untouched
+    eng.compact_agents = False
+    assert eng._compact(batch) is batch and eng._perm is None
