@@ -159,3 +159,33 @@ def test_agent_compaction_keeps_every_valid_agent_in_order():
     assert batch["sc/ag_valid"].shape[1] == 64                           # the caller's dict is untouched
     eng.compact_agents = False
     assert eng._compact(batch) is batch and eng._perm is None
+
+
+def test_warm_start_invariant_step_count():
+    """RolloutEngine._invariant_steps (host logic): the number of leading policy steps whose encoder inputs are the same
+    for every rollout of a scene. With the test-time teacher forcing (warm start 10, spawn window 11) and gap-free
+    tracks that is 11; an agent that is valid but NOT forced at time t (a track gap that closes after the spawn window,
+    or a track that outlives the warm start) makes the state rollout-dependent from t on, so only steps 1 .. t qualify;
+    fewer than 3 such steps switch the de-duplication off."""
+    from trafficbotsv1_5_b200.engine import RolloutEngine, teacher_forcing_mask
+    eng = RolloutEngine.__new__(RolloutEngine)
+    eng.T = 90
+
+    def s0(gt_valid, spawn=11, warm=10):
+        tf = teacher_forcing_mask(gt_valid, spawn, warm)
+        return eng._invariant_steps(dict(tf_mask=tf.to(torch.uint8), n_gt=gt_valid.shape[2]))
+
+    gt = torch.ones(2, 5, 91, dtype=torch.bool)
+    assert s0(gt) == 11                                   # times 0..10 forced; time 11 is the first free one
+    late = gt.clone()
+    late[1, 3, :7] = False                                # appears at t = 7 (inside the spawn window): forced there
+    assert s0(late) == 11
+    gap = gt.clone()
+    gap[0, 2, 4] = False                                  # a gap at t = 4: the agent lives on under the policy there
+    assert s0(gap) == 4                                   # (valid before, not forced) -> steps 1..4 only
+    assert s0(gt, spawn=11, warm=3) == 4                  # warm start 3: times 0..3 forced, step 5 already differs
+    assert s0(gt, spawn=0, warm=0) == 0                   # only time 0 forced: nothing worth batching
+    short = torch.ones(1, 4, 8, dtype=torch.bool)
+    assert s0(short) == 8                                 # bounded by the number of ground-truth steps
+    eng.T = 6
+    assert s0(gt) == 6                                    # and by the rollout length
