@@ -189,3 +189,20 @@ def test_warm_start_invariant_step_count():
     assert s0(short) == 8                                 # bounded by the number of ground-truth steps
     eng.T = 6
     assert s0(gt) == 6                                    # and by the rollout length
+
+
+def test_training_ring_index_matches_a_simulated_ring():
+    """TrainStep._ring_index (host logic): the batched training pass rebuilds, for every policy step s, the history ring
+    the step-by-step rollout would hold (slot = time % W, last W times). Simulate the ring write by write and compare."""
+    from trafficbotsv1_5_b200.training import TrainStep
+    ts = TrainStep.__new__(TrainStep)
+    ts.dev = torch.device("cpu")
+    for T, W in ((14, 11), (30, 11), (5, 11), (25, 4)):
+        tidx, tmask = ts._ring_index(T, W)
+        ring = [-1] * W                     # time stored in every slot, -1 = never written
+        for s in range(1, T + 1):           # before step s the ring holds times 0 .. s-1 (the newest W of them)
+            ring[(s - 1) % W] = s - 1
+            for k in range(W):
+                assert bool(tmask[s - 1, k]) == (ring[k] >= 0), (T, W, s, k)
+                if ring[k] >= 0:
+                    assert int(tidx[s - 1, k]) == ring[k], (T, W, s, k)
